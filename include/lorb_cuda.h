@@ -1,0 +1,336 @@
+/*
+ * lorb_cuda.h — C ABI of the B200 (sm_100a) hot-path library for LORB-SLAM.
+ *
+ * This is the drop-in boundary: the bodies of the reference's two stateless
+ * operator classes,
+ *     Matcher  (reference include/matcher.h:15-36, src/matcher.cpp)
+ *     BA       (reference include/bundle_adjust.h:12-21, src/bundle_adjust.cpp)
+ * flatten their Frame/MapPoint objects into the plain arrays below and call
+ * these entry points.  Nothing here knows about cv::Mat, Frame or MapPoint.
+ *
+ * Conventions
+ *  - every pointer is a HOST pointer owned by the caller for the duration of
+ *    the call, unless the parameter name ends in `_dev` or the function name in
+ *    `_resident` (then it refers to memory previously uploaded into the ctx);
+ *  - every function returns an int status: 0 = LORB_OK, <0 = error (see enum);
+ *    nothing throws or unwinds across the boundary; lorb_last_error() gives text;
+ *  - one lorb_ctx per calling thread (stream + device/pinned scratch live in it);
+ *    a ctx is not thread-safe, different ctxs are independent (re-entrant library);
+ *  - there is NO CPU fallback: without a usable CUDA device every compute entry
+ *    point returns LORB_ERR_CUDA.
+ *  - descriptors are 256-bit ORB strings, 32 bytes each, row-major contiguous
+ *    (reference src/ORBextractor.cpp:1114: N x 32 CV_8U).
+ */
+#ifndef LORB_CUDA_H
+#define LORB_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LORB_DESC_BYTES 32
+#define LORB_GRID_COLS 64 /* reference include/frame.h:14 FRAME_GRID_COLS */
+#define LORB_GRID_ROWS 48 /* reference include/frame.h:13 FRAME_GRID_ROWS */
+#define LORB_TH_HIGH 100  /* reference src/matcher.cpp:6 */
+#define LORB_TH_LOW 50    /* reference src/matcher.cpp:7 */
+#define LORB_HISTO_LENGTH 30 /* reference src/matcher.cpp:8 */
+
+enum {
+  LORB_OK = 0,
+  LORB_ERR_ARG = -1,     /* bad argument (null pointer, negative size, index out of range) */
+  LORB_ERR_CUDA = -2,    /* CUDA runtime error / no device */
+  LORB_ERR_NCCL = -3,    /* NCCL error / libnccl not loadable */
+  LORB_ERR_NOMEM = -4,   /* allocation failure */
+  LORB_ERR_STATE = -5,   /* call sequence error (e.g. sharded call without lorb_dist_init) */
+  LORB_ERR_NUMERIC = -6  /* solver broke down (non-finite step, Cholesky pivot <= 0 repeatedly) */
+};
+
+typedef struct lorb_ctx lorb_ctx; /* opaque */
+
+/* ------------------------------------------------------------------ context */
+
+/* Create a context bound to CUDA device `device` (cudaSetDevice ordinal). */
+int lorb_ctx_create(int device, lorb_ctx** out);
+int lorb_ctx_destroy(lorb_ctx* ctx);
+/* Block until all work queued on the ctx stream has finished. */
+int lorb_ctx_sync(lorb_ctx* ctx);
+/* Raw cudaStream_t of the ctx (as void*), for callers that time with CUDA events. */
+void* lorb_ctx_stream(lorb_ctx* ctx);
+/* Number of kernels this ctx has launched since creation (bench "gpu_launches"). */
+long long lorb_ctx_launch_count(lorb_ctx* ctx);
+/* Thread-local text of the last error raised by any entry point on this thread. */
+const char* lorb_last_error(void);
+/* Library version string. */
+const char* lorb_version(void);
+
+/* ------------------------------------------------- brute-force Hamming match */
+
+/* Cross-check mode.  MUTUAL is what OpenCV >= 3.4 / 4.x does (executable pin:
+ * cv2 4.13 in this image): keep (q,t) iff t = argmin_t' d(q,t') and
+ * q = argmin_q' d(q',t), lowest index winning ties on both sides.
+ * LEGACY restates OpenCV 3.1's batchDistance cross-check as recalled from its
+ * source (the version the reference pins, CMakeLists.txt:10; not executable
+ * here): for every train t take q = argmin_q' d(q',t); query q keeps the t of
+ * smallest d among those (lowest t on ties). */
+enum { LORB_CROSSCHECK_MUTUAL = 0, LORB_CROSSCHECK_LEGACY = 1 };
+
+/*
+ * Replaces the arithmetic of Matcher::SearchByProjection(Frame*,Frame*)
+ * (reference src/matcher.cpp:13-62) and Matcher::SearchLocalPoints
+ * (src/matcher.cpp:319-366): cv::BFMatcher(NORM_HAMMING, crossCheck=true)
+ * .match(query, train) followed by the minDist scan (:42-47) and the
+ * `distance > max(2*minDist, 30.0)` rejection (:49-56).
+ *
+ *   q [nq x 32], t [nt x 32]  descriptors
+ *   out_q/out_t/out_dist      cross-check matches in ascending query index,
+ *                             capacity >= min(nq,nt) each; dist is the integer
+ *                             Hamming distance (cv::DMatch::distance is that
+ *                             value as float)
+ *   out_keep                  1 iff the match survives the max(2*minDist,30) test
+ *   n_matches                 number of cross-check matches written
+ *   n_kept                    number with out_keep==1  (the reference's return value)
+ *   min_dist                  smallest distance over the matches, -1 if none
+ */
+int lorb_match_bf_crosscheck(lorb_ctx* ctx, const uint8_t* q, int nq, const uint8_t* t, int nt,
+                             int mode, int* out_q, int* out_t, int* out_dist, uint8_t* out_keep,
+                             int* n_matches, int* n_kept, int* min_dist);
+
+/*
+ * kNN-2 Hamming search with Lowe ratio + absolute threshold (north_star asks
+ * for it; the reference has no caller — cv::BFMatcher::knnMatch(k=2) is the
+ * oracle: neighbours ordered by (distance, train index)).
+ *   out_idx/out_dist [nq x 2]  best and second best (-1 / 256 when nt < 2 or 1)
+ *   out_pass [nq]              1 iff dist0 <= max_dist && dist0 < ratio * dist1
+ *                              (float compare, a missing second neighbour passes)
+ */
+int lorb_match_knn2(lorb_ctx* ctx, const uint8_t* q, int nq, const uint8_t* t, int nt, float ratio,
+                    int max_dist, int* out_idx, int* out_dist, uint8_t* out_pass);
+
+/*
+ * Keyframe-pair matching sweep (BASELINE config 5): a bank of n_kf keyframes,
+ * each with n_desc descriptors, and a list of (a,b) keyframe pairs.  For every
+ * pair the kernel runs the same cross-check + max(2*minDist,30) rule as
+ * lorb_match_bf_crosscheck(query = bank[a], train = bank[b]) and returns
+ *   out_kept[p]    number of kept matches
+ *   out_matches[p] number of cross-check matches  (may be NULL)
+ *   out_min[p]     minDist (-1 if no match)       (may be NULL)
+ * Host-buffer form: uploads bank, runs, downloads (the e2e path).
+ */
+int lorb_match_sweep(lorb_ctx* ctx, const uint8_t* bank, int n_kf, int n_desc, const int* pair_a,
+                     const int* pair_b, int n_pairs, int* out_kept, int* out_matches, int* out_min);
+
+/* Resident form: upload the bank once, then sweep pair lists against it. */
+int lorb_bank_upload(lorb_ctx* ctx, const uint8_t* bank, int n_kf, int n_desc);
+/* Pair lists / outputs are host pointers; only the bank stays in HBM. */
+int lorb_match_sweep_resident(lorb_ctx* ctx, const int* pair_a, const int* pair_b, int n_pairs,
+                              int* out_kept, int* out_matches, int* out_min);
+/* Fully device-resident variant used to time the kernel alone: pair list is
+ * uploaded once with lorb_sweep_plan_upload, each call only launches kernels;
+ * results stay on the device until lorb_sweep_plan_download. */
+int lorb_sweep_plan_upload(lorb_ctx* ctx, const int* pair_a, const int* pair_b, int n_pairs);
+int lorb_sweep_plan_run(lorb_ctx* ctx);
+int lorb_sweep_plan_download(lorb_ctx* ctx, int* out_kept, int* out_matches, int* out_min);
+
+/* ------------------------------------------- projection-guided search (a5/a6) */
+
+/* Current-frame view: what Matcher reads from a Frame through public members
+ * (reference include/frame.h:76-110) plus the descriptor matrix. */
+typedef struct lorb_frame_view {
+  int n_kp;
+  const float* kp_x;      /* mvKeysUn[i].pt.x */
+  const float* kp_y;      /* mvKeysUn[i].pt.y */
+  const int* kp_octave;   /* mvKeysUn[i].octave */
+  const float* kp_angle;  /* mvKeysUn[i].angle (degrees) */
+  const float* kp_uright; /* mvuRight[i]; <= 0 means "no stereo" */
+  const uint8_t* desc;    /* [n_kp x 32] */
+  /* claim state of mvpMapPoints[i] on entry: -1 = NULL, otherwise the mnObs of
+   * the map point currently held (0 = held but unprotected, >0 = protected:
+   * reference src/matcher.cpp:149-151, 273-275) */
+  const int* kp_claim_obs;
+  float min_x, max_x, min_y, max_y; /* mnMinX..mnMaxY (src/frame.cpp:79-82) */
+  int n_levels;
+  const float* scale_factors; /* mvScaleFactors[n_levels] */
+} lorb_frame_view;
+
+/*
+ * Matcher::SearchByProjection(Frame* F, const std::set<MapPoint*>&, float th)
+ * (reference src/matcher.cpp:220-316).  Points are given in the set's
+ * iteration order (that order IS the semantics: earlier points claim first).
+ *   active[k]    mbTrackInView && !IsBad()
+ *   level[k]     mnTrackScaleLevel (must index scale_factors)
+ *   mp_nobs[k]   the map point's mnObs (decides whether its claim protects)
+ * Outputs:
+ *   out_kp_for_point[n_pts]  keypoint assigned at that point's turn, -1 if none
+ *   out_point_for_kp[n_kp]   index of the point that finally holds the keypoint
+ *                            (last writer), -1 if this call did not touch it
+ *   n_matches                the reference's return value (assignments made)
+ *   n_candidates             optional (may be NULL): sum over points of the
+ *                            GetFeaturesInArea window sizes (work measure)
+ */
+int lorb_search_proj_points(lorb_ctx* ctx, const lorb_frame_view* frame, int n_pts,
+                            const float* proj_x, const float* proj_y, const float* proj_xr,
+                            const int* level, const float* view_cos, const uint8_t* active,
+                            const uint8_t* mp_desc, const int* mp_nobs, float th,
+                            int* out_kp_for_point, int* out_point_for_kp, int* n_matches,
+                            long long* n_candidates);
+
+typedef struct lorb_intrinsics {
+  float fx, fy, cx, cy, mbf, mb; /* Frame::fx.. (src/frame.cpp:70-77); mb = mbf/fx */
+} lorb_intrinsics;
+
+/*
+ * Matcher::SearchByProjection(Frame* Cur, Frame* Last, float th)
+ * (reference src/matcher.cpp:64-218): project Last's map points with Cur's
+ * pose, octave-dependent window, best Hamming <= TH_HIGH, rotation histogram.
+ *   tcw_cur/tcw_last [16]  row-major 4x4 float mTcw
+ *   last_valid[i]          mvpMapPoints[i] != NULL && !mvbOutlier[i]
+ *   last_xw [n_last x 3]   MapPoint::GetPos()
+ *   last_octave[i]         LastFrame->mvKeys[i].octave
+ *   last_angle[i]          LastFrame->mvKeysUn[i].angle
+ * Outputs:
+ *   out_kp_for_item[n_last]  keypoint chosen at that item's turn (-1 none)
+ *   out_state_for_kp[n_kp]   -1 untouched, -2 set to NULL by the rotation
+ *                            check, >=0 index of the Last item finally held
+ *   n_matches                the reference's return value
+ */
+int lorb_search_proj_frame(lorb_ctx* ctx, const lorb_frame_view* cur, const float* tcw_cur,
+                           const float* tcw_last, const lorb_intrinsics* K, int n_last,
+                           const uint8_t* last_valid, const float* last_xw, const int* last_octave,
+                           const float* last_angle, const uint8_t* mp_desc, const int* mp_nobs,
+                           float th, int* out_kp_for_item, int* out_state_for_kp, int* n_matches,
+                           long long* n_candidates);
+
+/* ------------------------------------------------------- bundle adjustment */
+
+/* Solver options: the Ceres Solver::Options fields that shape the LM
+ * trajectory.  lorb_ba_default_options fills Ceres'
+ * defaults; the reference sets nothing but DENSE_SCHUR
+ * (src/bundle_adjust.cpp:189-191, 308-310). */
+typedef struct lorb_ba_options {
+  int max_num_iterations;           /* 50 */
+  int jacobi_scaling;               /* 1 */
+  int max_consecutive_invalid_steps;/* 5 */
+  int reserved0;
+  double function_tolerance;        /* 1e-6 */
+  double gradient_tolerance;        /* 1e-10 */
+  double parameter_tolerance;       /* 1e-8 */
+  double initial_trust_region_radius; /* 1e4 */
+  double max_trust_region_radius;   /* 1e16 */
+  double min_trust_region_radius;   /* 1e-32 */
+  double min_relative_decrease;     /* 1e-3 */
+  double min_lm_diagonal;           /* 1e-6 */
+  double max_lm_diagonal;           /* 1e32 */
+} lorb_ba_options;
+
+enum {
+  LORB_BA_NO_CONVERGENCE = 0,   /* iteration budget exhausted */
+  LORB_BA_CONV_FUNCTION = 1,
+  LORB_BA_CONV_GRADIENT = 2,
+  LORB_BA_CONV_PARAMETER = 3,
+  LORB_BA_CONV_RADIUS = 4,      /* trust region radius below minimum */
+  LORB_BA_FAILURE = 5           /* too many consecutive invalid steps */
+};
+
+typedef struct lorb_ba_summary {
+  double initial_cost;  /* 1/2 sum r^2 at the input */
+  double final_cost;
+  double final_radius;
+  double final_gradient_max_norm;
+  int iterations;       /* LM steps attempted (Ceres' iteration index at exit) */
+  int num_successful_steps;
+  int num_unsuccessful_steps;
+  int termination;      /* LORB_BA_* */
+} lorb_ba_summary;
+
+void lorb_ba_default_options(lorb_ba_options* opt);
+
+/*
+ * BA::ProjectPoseOptimization (reference src/bundle_adjust.cpp:158-202):
+ * 6-dof pose (angle-axis R, translation T) of one frame against fixed 3-D
+ * points, PoseCost residuals (src/bundle_adjust.cpp:22-64 — including its use
+ * of fx for the v coordinate, :51).
+ *   xw [n x 3] float   MapPoint::GetPos()
+ *   uv [n x 2] float   Frame::GetKp2d(i)
+ *   K = {fx, fy, cx, cy} float (fy is unused by PoseCost; kept for symmetry)
+ *   rt [6] double in/out: (R0,R1,R2,T0,T1,T2)
+ */
+int lorb_ba_pose_only(lorb_ctx* ctx, int n, const float* xw, const float* uv, const float* K,
+                      double* rt, const lorb_ba_options* opt, lorb_ba_summary* summary);
+
+/*
+ * BA::LocalPoseOptimization (reference src/bundle_adjust.cpp:207-330).
+ *   cams [C x 6] double in/out   (w0,w1,w2,t0,t1,t2) per window frame (:250-255)
+ *   pts  [P x 3] double in/out   (:262-264)
+ *   obs_*  [O]   PoseMPCost residuals (point, pose) (:116-151, :299-300)
+ *   fix_*  [F]   MPCost residuals: point seen from an out-of-window frame whose
+ *                float pose fix_rt[f] = (r0,r1,r2,t0,t1,t2) stays constant
+ *                (:68-113, :288-289)
+ *   K = {fx, fy, cx, cy} of pCurrFrame->mpCamera
+ * No parameter block is held constant (the reference holds none).
+ */
+int lorb_ba_local(lorb_ctx* ctx, int C, double* cams, int P, double* pts, int O, const int* obs_cam,
+                  const int* obs_pt, const float* obs_uv, int F, const int* fix_pt,
+                  const float* fix_uv, const float* fix_rt, const float* K,
+                  const lorb_ba_options* opt, lorb_ba_summary* summary);
+
+/*
+ * Batched independent windows (BASELINE config 4).  Window w owns
+ *   cams[cam_off[w] .. cam_off[w+1]), pts[pt_off[w] .. pt_off[w+1]),
+ *   obs[obs_off[w] .. obs_off[w+1])  with obs_cam / obs_pt LOCAL to the window,
+ *   fixed observations [fix_off[w] .. fix_off[w+1]) likewise (fix_off may be
+ *   NULL when there are none).
+ * Every window runs its own LM loop (own trust region, own termination).
+ */
+int lorb_ba_local_batched(lorb_ctx* ctx, int n_windows, const int* cam_off, double* cams,
+                          const int* pt_off, double* pts, const int* obs_off, const int* obs_cam,
+                          const int* obs_pt, const float* obs_uv, const int* fix_off,
+                          const int* fix_pt, const float* fix_uv, const float* fix_rt,
+                          const float* K, const lorb_ba_options* opt, lorb_ba_summary* summaries);
+
+/* Device-resident local BA problem, for timing the solver without the
+ * host<->device copies and for the multi-GPU sharded solve. */
+typedef struct lorb_ba_problem lorb_ba_problem; /* opaque */
+int lorb_ba_problem_create(lorb_ctx* ctx, int C, const double* cams, int P, const double* pts, int O,
+                           const int* obs_cam, const int* obs_pt, const float* obs_uv, int F,
+                           const int* fix_pt, const float* fix_uv, const float* fix_rt,
+                           const float* K, lorb_ba_problem** out);
+/* Restore the parameters uploaded at creation (so a bench can re-solve). */
+int lorb_ba_problem_reset(lorb_ba_problem* p);
+/* Run LM on the resident problem.  If the ctx has a distributed group
+ * (lorb_dist_init) and `sharded` != 0, the points/observations given to this
+ * rank are its shard, cameras are replicated, and the reduced camera system is
+ * all-reduced over NCCL every iteration. */
+int lorb_ba_problem_solve(lorb_ba_problem* p, const lorb_ba_options* opt, int sharded,
+                          lorb_ba_summary* summary);
+int lorb_ba_problem_download(lorb_ba_problem* p, double* cams, double* pts);
+int lorb_ba_problem_destroy(lorb_ba_problem* p);
+
+/* ------------------------------------------------------------- multi-GPU */
+
+#define LORB_NCCL_UNIQUE_ID_BYTES 128
+/* Rank 0 calls this and broadcasts the 128 bytes by any host channel
+ * (torch.distributed, MPI, a file). */
+int lorb_dist_get_unique_id(uint8_t id[LORB_NCCL_UNIQUE_ID_BYTES]);
+/* Create the NCCL communicator of this ctx (one ctx = one rank = one GPU). */
+int lorb_dist_init(lorb_ctx* ctx, const uint8_t id[LORB_NCCL_UNIQUE_ID_BYTES], int rank, int world);
+int lorb_dist_finalize(lorb_ctx* ctx);
+/* Sum-allreduce `n` doubles in place on the host through the ctx communicator
+ * (used by tests and to gather tiny per-rank results). */
+int lorb_dist_allreduce_f64(lorb_ctx* ctx, double* data, int n);
+
+/* ------------------------------------------------------------ diagnostics */
+
+/* Integer-pipe micro-benchmark used for the matching roofline denominator
+ * (SURVEY §8(d)): runs `iters` dependent-free popc/xor word operations per
+ * thread on the whole GPU and returns 32-bit words processed per second.
+ * kind 0 = xor+popc+add per word; kind 1 = the carry-save (4 popc / 8 words)
+ * distance kernel body on register operands. */
+int lorb_microbench_popc(lorb_ctx* ctx, int kind, int iters, double* words_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LORB_CUDA_H */

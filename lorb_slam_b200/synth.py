@@ -1,0 +1,329 @@
+"""Seeded synthetic inputs of the shapes BASELINE.json names.
+
+Pure numpy; no oracle, no CUDA.  Used by bench.py and the tests to feed the
+C-ABI with Frame/MapPoint-shaped SoA arrays (the layout lorb_cuda.h documents).
+"""
+import numpy as np
+
+GRID_COLS, GRID_ROWS = 64, 48
+
+
+def scale_factors(n_levels=8, scale=1.2):
+    """mvScaleFactor as reference src/ORBextractor.cpp:428-436 builds it: the
+    factor is a float parameter held in a double member, the vector is float."""
+    sf = np.zeros(n_levels, np.float32)
+    sf[0] = 1.0
+    f = float(np.float32(scale))
+    for i in range(1, n_levels):
+        sf[i] = np.float32(float(sf[i - 1]) * f)
+    return sf
+
+
+# ----------------------------------------------------------------- descriptors
+
+def descriptors_uniform(n, rng):
+    return rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+
+
+def descriptors_tie_stress(n, rng, nbytes=2, nvals=4):
+    """Low-entropy descriptors: only the first `nbytes` bytes non-zero, values in
+    [0, nvals) -> many equal distances, exercises the lowest-index tie-breaks."""
+    d = np.zeros((n, 32), np.uint8)
+    d[:, :nbytes] = rng.integers(0, nvals, size=(n, nbytes), dtype=np.uint8)
+    return d
+
+
+def descriptors_noisy_copy(src, rng, p_flip=0.08):
+    """Each bit of `src` flipped with probability p_flip (a re-observed feature)."""
+    bits = np.unpackbits(src, axis=1)
+    flip = rng.random(bits.shape) < p_flip
+    return np.packbits(bits ^ flip.astype(np.uint8), axis=1)
+
+
+def kf_bank(n_kf, n_desc, seed=0, shared_frac=0.5, p_flip=0.08):
+    """Keyframe descriptor bank for the pair sweep: consecutive keyframes share
+    `shared_frac` of their features (noisy copies), the rest is uniform."""
+    rng = np.random.default_rng(seed)
+    bank = rng.integers(0, 256, size=(n_kf, n_desc, 32), dtype=np.uint8)
+    ns = int(n_desc * shared_frac)
+    if ns > 0 and n_kf <= 512:  # only worth the time for small banks
+        for k in range(1, n_kf):
+            idx = rng.permutation(n_desc)[:ns]
+            bank[k, idx] = descriptors_noisy_copy(bank[k - 1, idx], rng, p_flip)
+    return bank
+
+
+def all_pairs(n_kf):
+    a, b = np.triu_indices(n_kf, k=1)
+    return a.astype(np.int32), b.astype(np.int32)
+
+
+# ------------------------------------------------------------ frames / points
+
+def make_frame(n_kp=2000, seed=0, width=640, height=480, stereo=False, n_levels=8,
+               claimed_frac=0.0, claimed_protected_frac=0.5):
+    """Current-frame SoA (lorb_frame_view).  Octaves drawn proportional to
+    1.2^-l as mnFeaturesPerLevel does (reference src/ORBextractor.cpp:448-461)."""
+    rng = np.random.default_rng(seed)
+    w = (1.0 / 1.2) ** np.arange(n_levels)
+    octave = rng.choice(n_levels, size=n_kp, p=w / w.sum()).astype(np.int32)
+    fr = dict(
+        n_kp=n_kp,
+        kp_x=(rng.random(n_kp) * width).astype(np.float32),
+        kp_y=(rng.random(n_kp) * height).astype(np.float32),
+        kp_octave=octave,
+        kp_angle=(rng.random(n_kp) * 360.0).astype(np.float32),
+        kp_uright=np.full(n_kp, -1.0, np.float32),
+        desc=descriptors_uniform(n_kp, rng),
+        kp_claim_obs=np.full(n_kp, -1, np.int32),
+        min_x=0.0, max_x=float(width), min_y=0.0, max_y=float(height),
+        n_levels=n_levels, scale_factors=scale_factors(n_levels),
+    )
+    if stereo:
+        has = rng.random(n_kp) < 0.7
+        disp = (rng.random(n_kp) * 40.0 + 1.0).astype(np.float32)
+        fr["kp_uright"] = np.where(has, fr["kp_x"] - disp, -1.0).astype(np.float32)
+    if claimed_frac > 0:
+        cl = rng.random(n_kp) < claimed_frac
+        prot = rng.random(n_kp) < claimed_protected_frac
+        fr["kp_claim_obs"] = np.where(cl, np.where(prot, 3, 0), -1).astype(np.int32)
+    return fr
+
+
+def make_proj_points(fr, n_pts=5000, seed=0, true_frac=0.6, nobs=1, sigma_px=2.0, p_flip=0.08,
+                     inactive_frac=0.0):
+    """Map points already projected into `fr` (what Frame::IsInFrustum leaves in
+    MapPoint::mTrack*, reference src/frame.cpp:484-491)."""
+    rng = np.random.default_rng(seed + 7919)
+    n_kp = fr["n_kp"]
+    n_true = int(n_pts * true_frac)
+    src = rng.integers(0, n_kp, size=n_true)
+    px = np.empty(n_pts, np.float32)
+    py = np.empty(n_pts, np.float32)
+    lvl = np.empty(n_pts, np.int32)
+    desc = descriptors_uniform(n_pts, rng)
+    px[:n_true] = fr["kp_x"][src] + rng.normal(0, sigma_px, n_true).astype(np.float32)
+    py[:n_true] = fr["kp_y"][src] + rng.normal(0, sigma_px, n_true).astype(np.float32)
+    lvl[:n_true] = np.minimum(fr["kp_octave"][src] + rng.integers(0, 2, n_true), fr["n_levels"] - 1)
+    desc[:n_true] = descriptors_noisy_copy(fr["desc"][src], rng, p_flip)
+    px[n_true:] = (rng.random(n_pts - n_true) * fr["max_x"]).astype(np.float32)
+    py[n_true:] = (rng.random(n_pts - n_true) * fr["max_y"]).astype(np.float32)
+    lvl[n_true:] = rng.integers(0, fr["n_levels"], n_pts - n_true)
+    perm = rng.permutation(n_pts)  # processing order = array index
+    px, py, lvl, desc = px[perm], py[perm], lvl[perm], desc[perm]
+    disp = (rng.random(n_pts) * 40.0 + 1.0).astype(np.float32)
+    if np.isscalar(nobs):
+        mp_nobs = np.full(n_pts, nobs, np.int32)
+    else:
+        mp_nobs = rng.choice(np.asarray(nobs, np.int32), size=n_pts).astype(np.int32)
+    active = (rng.random(n_pts) >= inactive_frac).astype(np.uint8)
+    return dict(
+        n_pts=n_pts, proj_x=np.ascontiguousarray(px), proj_y=np.ascontiguousarray(py),
+        proj_xr=np.ascontiguousarray(px - disp), level=np.ascontiguousarray(lvl),
+        view_cos=(0.5 + 0.5 * rng.random(n_pts)).astype(np.float32), active=active,
+        mp_desc=np.ascontiguousarray(desc), mp_nobs=mp_nobs,
+    )
+
+
+def rodrigues(rvec):
+    """Angle-axis -> rotation matrices, vectorised ([...,3] -> [...,3,3])."""
+    rvec = np.asarray(rvec, np.float64)
+    th = np.linalg.norm(rvec, axis=-1)[..., None, None]
+    k = rvec / np.maximum(th[..., 0], 1e-300)
+    K = np.zeros(rvec.shape[:-1] + (3, 3))
+    K[..., 0, 1], K[..., 0, 2] = -k[..., 2], k[..., 1]
+    K[..., 1, 0], K[..., 1, 2] = k[..., 2], -k[..., 0]
+    K[..., 2, 0], K[..., 2, 1] = -k[..., 1], k[..., 0]
+    I = np.broadcast_to(np.eye(3), K.shape)
+    return I + np.sin(th) * K + (1 - np.cos(th)) * (K @ K)
+
+
+def make_frame_pair(n_kp=2000, seed=0, width=640, height=480, motion="forward", stereo=True,
+                    nobs=(0, 1, 2), valid_frac=0.9, sigma_px=1.5, p_flip=0.06):
+    """Inputs of Matcher::SearchByProjection(Cur, Last, th) (reference
+    src/matcher.cpp:64-218): Last's map points re-observed in Cur after a small
+    camera motion, plus clutter keypoints in Cur."""
+    rng = np.random.default_rng(seed + 104729)
+    fx = fy = np.float32(458.0)
+    cx, cy = np.float32(width / 2), np.float32(height / 2)
+    mbf = np.float32(47.9)
+    mb = np.float32(mbf / fx)
+    n_levels = 8
+    sf = scale_factors(n_levels)
+    # Last frame at identity; points in front of it
+    u = rng.random(n_kp) * width
+    v = rng.random(n_kp) * height
+    z = 2.0 + rng.random(n_kp) * 18.0
+    xw = np.stack([(u - cx) / fx * z, (v - cy) / fy * z, z], 1).astype(np.float32)
+    w = (1.0 / 1.2) ** np.arange(n_levels)
+    last_oct = rng.choice(n_levels, size=n_kp, p=w / w.sum()).astype(np.int32)
+    last_angle = (rng.random(n_kp) * 360.0).astype(np.float32)
+    last_desc = descriptors_uniform(n_kp, rng)
+    tz = {"forward": 0.4, "backward": -0.4, "still": 0.02}[motion]
+    rv = rng.normal(0, 0.01, 3)
+    Rcl = rodrigues(rv)
+    tcl = np.array([0.03, -0.02, -tz])  # x_cur = Rcl x_last + tcl (camera moved +tz)
+    tcw_last = np.eye(4, dtype=np.float32)
+    tcw_cur = np.eye(4, dtype=np.float32)
+    tcw_cur[:3, :3] = Rcl.astype(np.float32)
+    tcw_cur[:3, 3] = tcl.astype(np.float32)
+    xc = (Rcl @ xw.astype(np.float64).T).T + tcl
+    uc = fx * xc[:, 0] / xc[:, 2] + cx
+    vc = fy * xc[:, 1] / xc[:, 2] + cy
+    cur = make_frame(n_kp, seed + 1, width, height, stereo=False, n_levels=n_levels)
+    n_re = int(0.7 * n_kp)  # re-observed features occupy the first slots of Cur (shuffled below)
+    src = rng.permutation(n_kp)[:n_re]
+    ok = (uc[src] > 0) & (uc[src] < width) & (vc[src] > 0) & (vc[src] < height) & (xc[src, 2] > 0.1)
+    src = src[ok]
+    slot = rng.permutation(n_kp)[:len(src)]
+    cur["kp_x"][slot] = (uc[src] + rng.normal(0, sigma_px, len(src))).astype(np.float32)
+    cur["kp_y"][slot] = (vc[src] + rng.normal(0, sigma_px, len(src))).astype(np.float32)
+    cur["kp_x"] = np.clip(cur["kp_x"], 0, width - 1e-3).astype(np.float32)
+    cur["kp_y"] = np.clip(cur["kp_y"], 0, height - 1e-3).astype(np.float32)
+    d_oct = {"forward": rng.integers(0, 2, len(src)), "backward": -rng.integers(0, 2, len(src)),
+             "still": rng.integers(-1, 2, len(src))}[motion]
+    cur["kp_octave"][slot] = np.clip(last_oct[src] + d_oct, 0, n_levels - 1)
+    # most re-observations keep their orientation (+ a common rotation), some do not
+    rot = np.where(rng.random(len(src)) < 0.85, 12.0 + rng.normal(0, 2.0, len(src)),
+                   rng.random(len(src)) * 360.0)
+    cur["kp_angle"][slot] = np.mod(last_angle[src] - rot, 360.0).astype(np.float32)
+    cur["desc"][slot] = descriptors_noisy_copy(last_desc[src], rng, p_flip)
+    if stereo:
+        has = rng.random(n_kp) < 0.7
+        ur = cur["kp_x"] - mbf / np.maximum(2.0 + rng.random(n_kp) * 18.0, 1e-3)
+        ur[slot] = (cur["kp_x"][slot] - mbf / xc[src, 2] + rng.normal(0, 1.0, len(src)))
+        cur["kp_uright"] = np.where(has, ur, -1.0).astype(np.float32)
+    last = dict(
+        n_last=n_kp, valid=(rng.random(n_kp) < valid_frac).astype(np.uint8),
+        xw=np.ascontiguousarray(xw), octave=last_oct, angle=last_angle,
+        mp_desc=np.ascontiguousarray(last_desc),
+        mp_nobs=rng.choice(np.asarray(nobs, np.int32), size=n_kp).astype(np.int32),
+        tcw_cur=np.ascontiguousarray(tcw_cur.reshape(16)),
+        tcw_last=np.ascontiguousarray(tcw_last.reshape(16)),
+        K=dict(fx=float(fx), fy=float(fy), cx=float(cx), cy=float(cy), mbf=float(mbf),
+               mb=float(mb)),
+    )
+    return cur, last
+
+
+# --------------------------------------------------------------------- BA
+
+K_DEFAULT = np.array([458.0, 458.0, 320.0, 240.0], np.float32)
+
+
+def _project(rv, tv, X, K):
+    R = rodrigues(rv)
+    q = np.einsum("...ij,...j->...i", R, X) + tv
+    u = q[..., 0] / q[..., 2] * K[0] + K[2]
+    v = q[..., 1] / q[..., 2] * K[1] + K[3]
+    return u, v, q[..., 2]
+
+
+def make_ba_problem(seed=0, C=10, P=5000, obs_per_point=(6,), traj_len=5.0, fixed_frac=0.0,
+                    width=640, height=480, pose_noise=(0.01, 0.05), point_noise=0.05,
+                    pixel_noise=1.0):
+    """Local-BA window (SURVEY §8(d) cfg 3 / cfg 5).  Cameras on a gentle arc of
+    length `traj_len` looking down +z at a cloud 4-20 m ahead; every point is
+    observed by k in `obs_per_point` cameras drawn among those that see it.
+    Initial parameters = truth + noise, rounded through fp32 (the reference
+    stores poses and points as float, src/bundle_adjust.cpp:250-264).
+    Observations sorted by point.  `fixed_frac` of each point's observers are
+    turned into out-of-window MPCost observations with a fixed float pose."""
+    rng = np.random.default_rng(seed)
+    K = K_DEFAULT
+    s = np.linspace(0.0, 1.0, C) if C > 1 else np.zeros(1)
+    cam_c = np.stack([s * traj_len, 0.15 * np.sin(2 * np.pi * s), 0.1 * s], 1)  # centres
+    cam_rv = np.stack([0.02 * np.sin(3 * s), 0.08 * (s - 0.5), 0.01 * s], 1)     # small rotations
+    R = rodrigues(cam_rv)
+    cam_t = -np.einsum("cij,cj->ci", R, cam_c)  # x_c = R x_w + t
+    half = max(5.0, traj_len / 2 + 5.0)
+    pts = np.empty((P, 3))
+    obs_cam, obs_pt = [], []
+    ks = rng.choice(np.asarray(obs_per_point), size=P)
+    todo = np.arange(P)
+    chunk = 20000
+    while len(todo):
+        n = len(todo)
+        cand = np.stack([rng.uniform(traj_len / 2 - half, traj_len / 2 + half, n),
+                         rng.uniform(-3.0, 3.0, n), rng.uniform(4.0, 20.0, n)], 1)
+        done = np.zeros(n, bool)
+        kmax = int(np.max(obs_per_point))
+        for a in range(0, n, chunk):
+            X = cand[a:a + chunk]
+            u, v, z = _project(cam_rv[None], cam_t[None], X[:, None, :], K)
+            vis = (z > 0.5) & (u > 1) & (u < width - 1) & (v > 1) & (v < height - 1)
+            kk = ks[todo[a:a + chunk]]
+            good = vis.sum(1) >= kk
+            # k random visible cameras per point: smallest random scores among the visible
+            score = np.where(vis, rng.random(vis.shape), 2.0)
+            pick = np.argsort(score, axis=1)[:, :kmax]
+            use = (np.arange(kmax)[None, :] < kk[:, None]) & good[:, None]
+            rows = np.nonzero(good)[0]
+            pts[todo[a + rows]] = X[rows]
+            sel_cam = np.sort(np.where(use, pick, C + 1), axis=1)
+            m = sel_cam <= C
+            obs_cam.append(sel_cam[m])
+            obs_pt.append(np.broadcast_to(todo[a:a + chunk][:, None], sel_cam.shape)[m])
+            done[a + rows] = True
+        todo = todo[~done]
+    obs_cam = np.concatenate(obs_cam).astype(np.int32)
+    obs_pt = np.concatenate(obs_pt).astype(np.int32)
+    order = np.argsort(obs_pt, kind="stable")
+    obs_cam, obs_pt = obs_cam[order], obs_pt[order]
+    u, v, _ = _project(cam_rv[obs_cam], cam_t[obs_cam], pts[obs_pt], K)
+    uv = np.stack([u, v], 1) + rng.normal(0, pixel_noise, (len(u), 2))
+    uv = uv.astype(np.float32)
+    cams0 = np.concatenate([cam_rv + rng.normal(0, pose_noise[0], (C, 3)),
+                            cam_t + rng.normal(0, pose_noise[1], (C, 3))], 1)
+    cams0 = cams0.astype(np.float32).astype(np.float64)
+    pts0 = (pts + rng.normal(0, point_noise, (P, 3))).astype(np.float32).astype(np.float64)
+    pb = dict(C=C, P=P, K=K.copy(), cams=cams0, pts=pts0,
+              cams_true=np.concatenate([cam_rv, cam_t], 1), pts_true=pts.copy())
+    if fixed_frac > 0:
+        fx = rng.random(len(obs_cam)) < fixed_frac
+        truth = np.concatenate([cam_rv, cam_t], 1).astype(np.float32)
+        pb["fix_pt"] = obs_pt[fx].copy()
+        pb["fix_uv"] = uv[fx].copy()
+        pb["fix_rt"] = np.ascontiguousarray(truth[obs_cam[fx]])
+        obs_cam, obs_pt, uv = obs_cam[~fx], obs_pt[~fx], uv[~fx]
+    else:
+        pb["fix_pt"] = np.zeros(0, np.int32)
+        pb["fix_uv"] = np.zeros((0, 2), np.float32)
+        pb["fix_rt"] = np.zeros((0, 6), np.float32)
+    pb["obs_cam"] = np.ascontiguousarray(obs_cam)
+    pb["obs_pt"] = np.ascontiguousarray(obs_pt)
+    pb["obs_uv"] = np.ascontiguousarray(uv)
+    pb["O"] = len(obs_cam)
+    pb["F"] = len(pb["fix_pt"])
+    return pb
+
+
+def make_pose_only(seed=0, n=500, pixel_noise=1.0, pose_noise=(0.02, 0.1)):
+    """Inputs of BA::ProjectPoseOptimization (reference src/bundle_adjust.cpp:158-202).
+    fx = fy so the reference's fx-for-v quirk (:51) is consistent with the data."""
+    rng = np.random.default_rng(seed + 15485863)
+    K = K_DEFAULT
+    rv = rng.normal(0, 0.1, 3)
+    tv = rng.normal(0, 0.3, 3)
+    Xc = np.stack([rng.uniform(-4, 4, n), rng.uniform(-3, 3, n), rng.uniform(3, 20, n)], 1)
+    R = rodrigues(rv)
+    xw = ((Xc - tv) @ R).astype(np.float32)  # R^T (Xc - t)
+    u, v, _ = _project(rv, tv, xw.astype(np.float64), np.array([K[0], K[0], K[2], K[3]]))
+    uv = (np.stack([u, v], 1) + rng.normal(0, pixel_noise, (n, 2))).astype(np.float32)
+    rt0 = np.concatenate([rv + rng.normal(0, pose_noise[0], 3), tv + rng.normal(0, pose_noise[1], 3)])
+    rt0 = rt0.astype(np.float32).astype(np.float64)
+    return dict(n=n, xw=xw, uv=uv, K=K.copy(), rt=rt0, rt_true=np.concatenate([rv, tv]))
+
+
+def batch_windows(pbs):
+    """Concatenate independent windows into the offset-array form of
+    lorb_ba_local_batched (observation indices stay window-local)."""
+    cam_off = np.cumsum([0] + [p["C"] for p in pbs]).astype(np.int32)
+    pt_off = np.cumsum([0] + [p["P"] for p in pbs]).astype(np.int32)
+    obs_off = np.cumsum([0] + [p["O"] for p in pbs]).astype(np.int32)
+    return dict(
+        n_windows=len(pbs), cam_off=cam_off, pt_off=pt_off, obs_off=obs_off,
+        cams=np.concatenate([p["cams"] for p in pbs]), pts=np.concatenate([p["pts"] for p in pbs]),
+        obs_cam=np.concatenate([p["obs_cam"] for p in pbs]),
+        obs_pt=np.concatenate([p["obs_pt"] for p in pbs]),
+        obs_uv=np.concatenate([p["obs_uv"] for p in pbs]), K=pbs[0]["K"].copy())

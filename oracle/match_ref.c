@@ -1,0 +1,540 @@
+/*
+ * oracle/match_ref.c — CPU restatement of the reference's descriptor matching.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing in the product path (lorb_slam_b200/,
+ * include/) may call, link or import this file.  It is the checker that the
+ * CUDA path is compared against (tests/, __graft_entry__.smoke(), and the
+ * cpu_baseline / --impl reference legs of bench.py).
+ *
+ * Parity status
+ *   - brute-force cross-check + knn2: PINNED against cv2 4.13 BFMatcher (the
+ *     same OpenCV routine the reference calls, src/matcher.cpp:36-39) through
+ *     the golden vectors in tests/golden/ (tests/golden/make_golden.py).
+ *   - fp32 projection arithmetic: PINNED against cv2.gemm through golden vectors.
+ *   - projection-guided searches as a whole: restated line by line from the
+ *     reference (cited below); the reference has no tests or fixtures for them
+ *      and cannot be built here -> "parity unpinned" beyond the
+ *     citations.
+ *
+ * All citations are file:line in /root/reference.
+ * Build: gcc -O2 -ffp-contract=off -fno-fast-math -fPIC -shared (oracle/Makefile).
+ * The reference itself builds -O0 on baseline x86-64 (CMakeLists.txt:5-6), so
+ * no FMA contraction may happen in the float code below.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define GRID_COLS 64 /* include/frame.h:14 */
+#define GRID_ROWS 48 /* include/frame.h:13 */
+#define TH_HIGH 100  /* src/matcher.cpp:6 */
+#define HISTO_LENGTH 30 /* src/matcher.cpp:8 */
+
+/* ---- a2: Matcher::DescriptorDistance, src/matcher.cpp:369-385 (SWAR popcount
+ * over eight 32-bit words). */
+int orc_hamming256(const uint8_t* a, const uint8_t* b) {
+  int dist = 0;
+  for (int i = 0; i < 8; i++) {
+    uint32_t wa, wb;
+    memcpy(&wa, a + 4 * i, 4);
+    memcpy(&wb, b + 4 * i, 4);
+    uint32_t v = wa ^ wb;
+    v = v - ((v >> 1) & 0x55555555u);
+    v = (v & 0x33333333u) + ((v >> 2) & 0x33333333u);
+    dist += (int)((((v + (v >> 4)) & 0x0F0F0F0Fu) * 0x01010101u) >> 24);
+  }
+  return dist;
+}
+
+/* Faster equivalent used for the big distance matrices (same value; the test
+ * suite checks it against orc_hamming256). */
+static inline int ham_fast(const uint8_t* a, const uint8_t* b) {
+  uint64_t x[4], y[4];
+  memcpy(x, a, 32);
+  memcpy(y, b, 32);
+  return __builtin_popcountll(x[0] ^ y[0]) + __builtin_popcountll(x[1] ^ y[1]) +
+         __builtin_popcountll(x[2] ^ y[2]) + __builtin_popcountll(x[3] ^ y[3]);
+}
+
+/* Nearest neighbour both ways: fwd[i] = argmin_t d(i,t), bwd[t] = argmin_i d(i,t),
+ * lowest index on ties (cv::batchDistance keeps the first strict minimum). */
+static void nn_both(const uint8_t* q, int nq, const uint8_t* t, int nt, int* fwd, int* fwd_d,
+                    int* bwd, int* bwd_d) {
+  for (int j = 0; j < nt; j++) {
+    bwd[j] = -1;
+    bwd_d[j] = 1 << 30;
+  }
+  for (int i = 0; i < nq; i++) {
+    int best = -1, bd = 1 << 30;
+    const uint8_t* qi = q + 32 * (size_t)i;
+    for (int j = 0; j < nt; j++) {
+      int d = ham_fast(qi, t + 32 * (size_t)j);
+      if (d < bd) {
+        bd = d;
+        best = j;
+      }
+      if (d < bwd_d[j]) {
+        bwd_d[j] = d;
+        bwd[j] = i;
+      }
+    }
+    fwd[i] = best;
+    fwd_d[i] = bd;
+  }
+}
+
+/*
+ * a3/a4: cv::BFMatcher(NORM_HAMMING, crossCheck=true).match(query, train)
+ * as called at src/matcher.cpp:36-39 and :342-345.
+ * mode 0 (mutual): OpenCV >= 3.4 semantics, pinned against cv2 4.13.
+ * mode 1 (legacy): OpenCV 3.1 batchDistance cross-check as recalled (for every
+ *   train t, idx = its nearest query; dist[idx] takes the strictly smaller d,
+ *   scanning t ascending).  Unpinned: OpenCV 3.1 is not executable here.
+ * Emits matches in ascending query index (the order knnMatch's result is
+ * flattened in).  Returns the number of matches.
+ */
+int orc_bf_crosscheck(const uint8_t* q, int nq, const uint8_t* t, int nt, int mode, int* out_q,
+                      int* out_t, int* out_d) {
+  if (nq <= 0 || nt <= 0) return 0;
+  int* fwd = (int*)malloc(sizeof(int) * (size_t)nq * 2);
+  int* fwd_d = fwd + nq;
+  int* bwd = (int*)malloc(sizeof(int) * (size_t)nt * 2);
+  int* bwd_d = bwd + nt;
+  nn_both(q, nq, t, nt, fwd, fwd_d, bwd, bwd_d);
+  int n = 0;
+  if (mode == 0) {
+    for (int i = 0; i < nq; i++) {
+      int j = fwd[i];
+      if (j >= 0 && bwd[j] == i) {
+        out_q[n] = i;
+        out_t[n] = j;
+        out_d[n] = fwd_d[i];
+        n++;
+      }
+    }
+  } else {
+    int* nidx = (int*)malloc(sizeof(int) * (size_t)nq * 2);
+    int* dist = nidx + nq;
+    for (int i = 0; i < nq; i++) {
+      nidx[i] = -1;
+      dist[i] = 0x7fffffff;
+    }
+    for (int j = 0; j < nt; j++) {
+      int idx = bwd[j];
+      int d = bwd_d[j];
+      if (d < dist[idx]) {
+        dist[idx] = d;
+        nidx[idx] = j;
+      }
+    }
+    for (int i = 0; i < nq; i++)
+      if (nidx[i] >= 0) {
+        out_q[n] = i;
+        out_t[n] = nidx[i];
+        out_d[n] = dist[i];
+        n++;
+      }
+    free(nidx);
+  }
+  free(fwd);
+  free(bwd);
+  return n;
+}
+
+/* src/matcher.cpp:42-56: minDist scan, then keep iff !(distance > max(2*minDist, 30.0))
+ * evaluated in double.  Returns the kept count (the reference's return value). */
+int orc_bf_filter(const int* d, int n, int* min_dist_out, uint8_t* keep) {
+  double minDist = 1.7976931348623157e308; /* DBL_MAX */
+  for (int i = 0; i < n; i++)
+    if ((double)(float)d[i] < minDist) minDist = (double)(float)d[i];
+  int kept = 0;
+  for (int i = 0; i < n; i++) {
+    double thr = 2 * minDist > 30.0 ? 2 * minDist : 30.0;
+    int k = !((double)(float)d[i] > thr);
+    keep[i] = (uint8_t)k;
+    kept += k;
+  }
+  *min_dist_out = n > 0 ? (int)minDist : -1;
+  return kept;
+}
+
+/* kNN-2 (cv::BFMatcher::knnMatch k=2, crossCheck=false): neighbours sorted by
+ * (distance, train index).  idx = -1 / dist = 256 where there is no neighbour. */
+void orc_knn2(const uint8_t* q, int nq, const uint8_t* t, int nt, int* idx, int* dist) {
+  for (int i = 0; i < nq; i++) {
+    int b0 = -1, d0 = 256 + 1, b1 = -1, d1 = 256 + 1;
+    const uint8_t* qi = q + 32 * (size_t)i;
+    for (int j = 0; j < nt; j++) {
+      int d = ham_fast(qi, t + 32 * (size_t)j);
+      if (d < d0) {
+        d1 = d0;
+        b1 = b0;
+        d0 = d;
+        b0 = j;
+      } else if (d < d1) {
+        d1 = d;
+        b1 = j;
+      }
+    }
+    idx[2 * i] = b0;
+    dist[2 * i] = b0 >= 0 ? d0 : 256;
+    idx[2 * i + 1] = b1;
+    dist[2 * i + 1] = b1 >= 0 ? d1 : 256;
+  }
+}
+
+/* Sweep unit (BASELINE config 5): one keyframe pair -> (kept, matches, minDist). */
+void orc_sweep_pair(const uint8_t* a, const uint8_t* b, int n_desc, int* kept, int* matches,
+                    int* min_dist) {
+  int* oq = (int*)malloc(sizeof(int) * (size_t)n_desc * 3);
+  int* ot = oq + n_desc;
+  int* od = ot + n_desc;
+  uint8_t* keep = (uint8_t*)malloc((size_t)n_desc + 1);
+  int n = orc_bf_crosscheck(a, n_desc, b, n_desc, 0, oq, ot, od);
+  *kept = orc_bf_filter(od, n, min_dist, keep);
+  *matches = n;
+  free(oq);
+  free(keep);
+}
+
+/* ------------------------------------------------------------------ a7: grid */
+
+typedef struct {
+  int n_kp;
+  const float *x, *y;
+  const int* octave;
+  float min_x, min_y, inv_w, inv_h;
+  int* cell_start; /* GRID_COLS*GRID_ROWS + 1, cell id = ix*GRID_ROWS + iy */
+  int* cell_items; /* keypoint indices, ascending inside a cell */
+} grid_t;
+
+/* ComputeImageBounds src/frame.cpp:83-84, AssignFeaturesToGrid :87-103,
+ * PosInGrid :105-115 (round(), not floor; out-of-range cells drop the keypoint). */
+static void grid_build(grid_t* g, int n_kp, const float* x, const float* y, const int* octave,
+                       float min_x, float max_x, float min_y, float max_y) {
+  g->n_kp = n_kp;
+  g->x = x;
+  g->y = y;
+  g->octave = octave;
+  g->min_x = min_x;
+  g->min_y = min_y;
+  g->inv_w = (float)GRID_COLS / (max_x - min_x);
+  g->inv_h = (float)GRID_ROWS / (max_y - min_y);
+  int ncell = GRID_COLS * GRID_ROWS;
+  g->cell_start = (int*)calloc((size_t)ncell + 1, sizeof(int));
+  g->cell_items = (int*)malloc(sizeof(int) * (size_t)(n_kp > 0 ? n_kp : 1));
+  int* cell_of = (int*)malloc(sizeof(int) * (size_t)(n_kp > 0 ? n_kp : 1));
+  for (int i = 0; i < n_kp; i++) {
+    int px = (int)roundf((x[i] - min_x) * g->inv_w);
+    int py = (int)roundf((y[i] - min_y) * g->inv_h);
+    if (px < 0 || px >= GRID_COLS || py < 0 || py >= GRID_ROWS) {
+      cell_of[i] = -1;
+      continue;
+    }
+    cell_of[i] = px * GRID_ROWS + py;
+    g->cell_start[cell_of[i] + 1]++;
+  }
+  for (int c = 0; c < ncell; c++) g->cell_start[c + 1] += g->cell_start[c];
+  int* fill = (int*)malloc(sizeof(int) * (size_t)ncell);
+  memcpy(fill, g->cell_start, sizeof(int) * (size_t)ncell);
+  for (int i = 0; i < n_kp; i++)
+    if (cell_of[i] >= 0) g->cell_items[fill[cell_of[i]]++] = i;
+  free(fill);
+  free(cell_of);
+}
+
+static void grid_free(grid_t* g) {
+  free(g->cell_start);
+  free(g->cell_items);
+}
+
+/* Frame::GetFeaturesInArea src/frame.cpp:370-423.  Writes indices in the
+ * reference's iteration order (ix outer, iy inner, cell order); returns count. */
+static int grid_query(const grid_t* g, float x, float y, float r, int minLevel, int maxLevel,
+                      int* out) {
+  int n = 0;
+  int nMinCellX = (int)floorf((x - g->min_x - r) * g->inv_w);
+  if (nMinCellX < 0) nMinCellX = 0;
+  if (nMinCellX >= GRID_COLS) return 0;
+  int nMaxCellX = (int)ceilf((x - g->min_x + r) * g->inv_w);
+  if (nMaxCellX > GRID_COLS - 1) nMaxCellX = GRID_COLS - 1;
+  if (nMaxCellX < 0) return 0;
+  int nMinCellY = (int)floorf((y - g->min_y - r) * g->inv_h);
+  if (nMinCellY < 0) nMinCellY = 0;
+  if (nMinCellY >= GRID_ROWS) return 0;
+  int nMaxCellY = (int)ceilf((y - g->min_y + r) * g->inv_h);
+  if (nMaxCellY > GRID_ROWS - 1) nMaxCellY = GRID_ROWS - 1;
+  if (nMaxCellY < 0) return 0;
+  const int bCheckLevels = (minLevel > 0) || (maxLevel >= 0);
+  for (int ix = nMinCellX; ix <= nMaxCellX; ix++)
+    for (int iy = nMinCellY; iy <= nMaxCellY; iy++) {
+      int c = ix * GRID_ROWS + iy;
+      for (int j = g->cell_start[c]; j < g->cell_start[c + 1]; j++) {
+        int k = g->cell_items[j];
+        if (bCheckLevels) {
+          if (g->octave[k] < minLevel) continue;
+          if (maxLevel >= 0)
+            if (g->octave[k] > maxLevel) continue;
+        }
+        const float distx = g->x[k] - x;
+        const float disty = g->y[k] - y;
+        if (fabsf(distx) < r && fabsf(disty) < r) out[n++] = k;
+      }
+    }
+  return n;
+}
+
+/* Exposed for tests: candidate list of one window query. */
+int orc_features_in_area(int n_kp, const float* kx, const float* ky, const int* octave, float min_x,
+                         float max_x, float min_y, float max_y, float x, float y, float r,
+                         int minLevel, int maxLevel, int* out) {
+  grid_t g;
+  grid_build(&g, n_kp, kx, ky, octave, min_x, max_x, min_y, max_y);
+  int n = grid_query(&g, x, y, r, minLevel, maxLevel, out);
+  grid_free(&g);
+  return n;
+}
+
+/* ---- a6: Matcher::SearchByProjection(Frame*, const set<MapPoint*>&, th),
+ * src/matcher.cpp:220-316.  Points arrive in set-iteration order. */
+int orc_search_proj_points(int n_kp, const float* kx, const float* ky, const int* koct,
+                           const float* kuright, const uint8_t* kdesc, const int* kclaim_obs,
+                           float min_x, float max_x, float min_y, float max_y,
+                           const float* scale_factors, int n_pts, const float* proj_x,
+                           const float* proj_y, const float* proj_xr, const int* level,
+                           const float* view_cos, const uint8_t* active, const uint8_t* mp_desc,
+                           const int* mp_nobs, float th, int* out_kp_for_point,
+                           int* out_point_for_kp, long long* n_candidates) {
+  grid_t g;
+  grid_build(&g, n_kp, kx, ky, koct, min_x, max_x, min_y, max_y);
+  int* holder_obs = (int*)malloc(sizeof(int) * (size_t)(n_kp > 0 ? n_kp : 1));
+  int* cand = (int*)malloc(sizeof(int) * (size_t)(n_kp > 0 ? n_kp : 1));
+  for (int i = 0; i < n_kp; i++) {
+    holder_obs[i] = kclaim_obs[i];
+    out_point_for_kp[i] = -1;
+  }
+  long long ncand = 0;
+  int nmatches = 0;
+  const int bFactor = th != 1.0; /* :224 (float promoted to double) */
+  for (int k = 0; k < n_pts; k++) {
+    out_kp_for_point[k] = -1;
+    if (!active[k]) continue; /* :231-235 */
+    const int lvl = level[k];
+    float r = ((double)view_cos[k] > 0.998) ? 2.5f : 4.0f; /* :430-436 */
+    if (bFactor) r *= th;                                   /* :244 */
+    const float rs = r * scale_factors[lvl];
+    int nc = grid_query(&g, proj_x[k], proj_y[k], rs, lvl - 1, lvl, cand); /* :252-253 */
+    ncand += nc;
+    if (nc == 0) continue;
+    const uint8_t* d_mp = mp_desc + 32 * (size_t)k;
+    int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+    for (int c = 0; c < nc; c++) {
+      const int idx = cand[c];
+      if (holder_obs[idx] > 0) continue; /* :273-275 */
+      if (kuright[idx] > 0) {            /* :277-282 */
+        const float er = fabsf(proj_xr[k] - kuright[idx]);
+        if (er > r * scale_factors[lvl]) continue;
+      }
+      const int dist = orc_hamming256(d_mp, kdesc + 32 * (size_t)idx);
+      if (dist < bestDist) { /* :289-301 */
+        bestDist2 = bestDist;
+        bestDist = dist;
+        bestLevel2 = bestLevel;
+        bestLevel = koct[idx];
+        bestIdx = idx;
+      } else if (dist < bestDist2) {
+        bestLevel2 = koct[idx];
+        bestDist2 = dist;
+      }
+    }
+    if (bestDist <= TH_HIGH) { /* :305-312 */
+      if (bestLevel == bestLevel2 && (double)bestDist > 0.8 * (double)bestDist2) continue;
+      holder_obs[bestIdx] = mp_nobs[k];
+      out_point_for_kp[bestIdx] = k;
+      out_kp_for_point[k] = bestIdx;
+      nmatches++;
+    }
+  }
+  if (n_candidates) *n_candidates = ncand;
+  free(holder_obs);
+  free(cand);
+  grid_free(&g);
+  return nmatches;
+}
+
+/* cv::Mat 3x3 * 3x1 (+ c) float product as OpenCV's small-matrix gemm path
+ * evaluates it: sequential fp32 multiply/add, k ascending, then + c
+ * (pinned against cv2.gemm in tests/golden). */
+static inline float dot3_seq(const float* a, int sa, const float* b, int sb) {
+  float t = a[0] * b[0];
+  t = t + a[sa] * b[sb];
+  t = t + a[2 * sa] * b[2 * sb];
+  return t;
+}
+
+/* Exposed for the golden test of the fp32 projection: xc = R*x + t. */
+void orc_project_rt(const float* tcw, const float* xw, float* xc) {
+  for (int r = 0; r < 3; r++) xc[r] = dot3_seq(tcw + 4 * r, 1, xw, 1) + tcw[4 * r + 3];
+}
+
+/* tlc of src/matcher.cpp:74-83: twc = -Rcw^T tcw ; tlc = Rlw*twc + tlw. */
+void orc_tlc(const float* tcw_cur, const float* tcw_last, float* tlc) {
+  float twc[3];
+  float tc[3] = {tcw_cur[3], tcw_cur[7], tcw_cur[11]};
+  for (int i = 0; i < 3; i++) twc[i] = -dot3_seq(tcw_cur + i, 4, tc, 1);
+  for (int r = 0; r < 3; r++) tlc[r] = dot3_seq(tcw_last + 4 * r, 1, twc, 1) + tcw_last[4 * r + 3];
+}
+
+/* a8: Matcher::ComputeThreeMaxima src/matcher.cpp:387-428 on bin counts. */
+void orc_three_maxima(const int* histo, int L, int* ind1, int* ind2, int* ind3) {
+  int max1 = 0, max2 = 0, max3 = 0;
+  int i1 = -1, i2 = -1, i3 = -1;
+  for (int i = 0; i < L; i++) {
+    const int s = histo[i];
+    if (s > max1) {
+      max3 = max2;
+      max2 = max1;
+      max1 = s;
+      i3 = i2;
+      i2 = i1;
+      i1 = i;
+    } else if (s > max2) {
+      max3 = max2;
+      max2 = s;
+      i3 = i2;
+      i2 = i;
+    } else if (s > max3) {
+      max3 = s;
+      i3 = i;
+    }
+  }
+  if ((float)max2 < 0.1f * (float)max1) {
+    i2 = -1;
+    i3 = -1;
+  } else if ((float)max3 < 0.1f * (float)max1) {
+    i3 = -1;
+  }
+  *ind1 = i1;
+  *ind2 = i2;
+  *ind3 = i3;
+}
+
+/* ---- a5: Matcher::SearchByProjection(Frame* Cur, Frame* Last, th),
+ * src/matcher.cpp:64-218. */
+int orc_search_proj_frame(int n_kp, const float* kx, const float* ky, const int* koct,
+                          const float* kangle, const float* kuright, const uint8_t* kdesc,
+                          const int* kclaim_obs, float min_x, float max_x, float min_y,
+                          float max_y, const float* scale_factors, const float* tcw_cur,
+                          const float* tcw_last, float fx, float fy, float cx, float cy, float mbf,
+                          float mb, int n_last, const uint8_t* last_valid, const float* last_xw,
+                          const int* last_octave, const float* last_angle, const uint8_t* mp_desc,
+                          const int* mp_nobs, float th, int* out_kp_for_item,
+                          int* out_state_for_kp, long long* n_candidates) {
+  grid_t g;
+  grid_build(&g, n_kp, kx, ky, koct, min_x, max_x, min_y, max_y);
+  int* holder_obs = (int*)malloc(sizeof(int) * (size_t)(n_kp > 0 ? n_kp : 1));
+  int* cand = (int*)malloc(sizeof(int) * (size_t)(n_kp > 0 ? n_kp : 1));
+  for (int i = 0; i < n_kp; i++) {
+    holder_obs[i] = kclaim_obs[i];
+    out_state_for_kp[i] = -1;
+  }
+  /* rotation histogram :69-72 — entries are keypoint indices */
+  int* hist_items = (int*)malloc(sizeof(int) * (size_t)(n_last > 0 ? n_last : 1));
+  int* hist_bin = (int*)malloc(sizeof(int) * (size_t)(n_last > 0 ? n_last : 1));
+  int hist_count[HISTO_LENGTH];
+  memset(hist_count, 0, sizeof(hist_count));
+  int n_hist = 0;
+  const float factor = HISTO_LENGTH / 360.0f;
+
+  float tlc[3];
+  orc_tlc(tcw_cur, tcw_last, tlc);
+  const int bForward = tlc[2] > mb;   /* :86 */
+  const int bBackward = -tlc[2] > mb; /* :87 */
+
+  long long ncand = 0;
+  int nmatches = 0;
+  for (int i = 0; i < n_last; i++) {
+    out_kp_for_item[i] = -1;
+    if (!last_valid[i]) continue; /* :91-95 */
+    float x3Dc[3];
+    orc_project_rt(tcw_cur, last_xw + 3 * (size_t)i, x3Dc); /* :99-101 */
+    const float xc = x3Dc[0];
+    const float yc = x3Dc[1];
+    const float invzc = (float)(1.0 / (double)x3Dc[2]); /* :105 */
+    if (invzc < 0) continue;                            /* :107 */
+    float u = fx * xc * invzc + cx;                     /* :110 */
+    float v = fy * yc * invzc + cy;                     /* :111 */
+    if (u < min_x || u > max_x) continue;               /* :113 */
+    if (v < min_y || v > max_y) continue;               /* :115 */
+    const int nLastOctave = last_octave[i];
+    const float radius = th * scale_factors[nLastOctave]; /* :121 */
+    int nc;
+    if (bForward) /* :129-134; default maxLevel = -1 (include/frame.h:73) */
+      nc = grid_query(&g, u, v, radius, nLastOctave, -1, cand);
+    else if (bBackward)
+      nc = grid_query(&g, u, v, radius, 0, nLastOctave, cand);
+    else
+      nc = grid_query(&g, u, v, radius, nLastOctave - 1, nLastOctave + 1, cand);
+    ncand += nc;
+    if (nc == 0) continue;
+    const uint8_t* dMP = mp_desc + 32 * (size_t)i;
+    int bestDist = 256, bestIdx2 = -1;
+    for (int c = 0; c < nc; c++) {
+      const int i2 = cand[c];
+      if (holder_obs[i2] > 0) continue; /* :149-151 */
+      if (kuright[i2] > 0) {            /* :153-160 */
+        const float ur = u - mbf * invzc;
+        const float er = fabsf(ur - kuright[i2]);
+        if (er > radius) continue;
+      }
+      const int dist = orc_hamming256(dMP, kdesc + 32 * (size_t)i2);
+      if (dist < bestDist) {
+        bestDist = dist;
+        bestIdx2 = i2;
+      }
+    }
+    if (bestDist <= TH_HIGH) { /* :174-191 */
+      holder_obs[bestIdx2] = mp_nobs[i];
+      out_state_for_kp[bestIdx2] = i;
+      out_kp_for_item[i] = bestIdx2;
+      nmatches++;
+      float rot = last_angle[i] - kangle[bestIdx2];
+      if (rot < 0.0) rot += 360.0f;
+      int bin = (int)roundf(rot * factor);
+      if (bin == HISTO_LENGTH) bin = 0;
+      hist_items[n_hist] = bestIdx2;
+      hist_bin[n_hist] = bin;
+      n_hist++;
+      hist_count[bin]++;
+    }
+  }
+  int ind1, ind2, ind3;
+  orc_three_maxima(hist_count, HISTO_LENGTH, &ind1, &ind2, &ind3); /* :196-202 */
+  for (int b = 0; b < HISTO_LENGTH; b++) {
+    if (b != ind1 && b != ind2 && b != ind3) {
+      for (int j = 0; j < n_hist; j++)
+        if (hist_bin[j] == b) { /* :204-214 */
+          out_state_for_kp[hist_items[j]] = -2;
+          nmatches--;
+        }
+    }
+  }
+  if (n_candidates) *n_candidates = ncand;
+  free(hist_items);
+  free(hist_bin);
+  free(holder_obs);
+  free(cand);
+  grid_free(&g);
+  return nmatches;
+}
+
+/* ---- multi-threaded driver for the CPU baseline of the sweep (bench.py
+ * --impl reference): pairs are split over OpenMP threads. */
+void orc_sweep(const uint8_t* bank, int n_desc, const int* pair_a, const int* pair_b, int n_pairs,
+               int* kept, int* matches, int* min_dist) {
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int p = 0; p < n_pairs; p++)
+    orc_sweep_pair(bank + (size_t)pair_a[p] * n_desc * 32, bank + (size_t)pair_b[p] * n_desc * 32,
+                   n_desc, &kept[p], &matches[p], &min_dist[p]);
+}
