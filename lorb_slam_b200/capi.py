@@ -1,0 +1,382 @@
+"""ctypes binding of include/lorb_cuda.h — the call a Python user (tests,
+bench.py) makes.  It is a thin, copy-free view over the C ABI: numpy arrays go
+in as host pointers, exactly as the C++ Matcher/BA wrappers pass them.
+
+There is no fallback: if liblorb_cuda.so is missing or a call fails, this
+raises (LorbError); nothing here computes on the CPU.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "liblorb_cuda.so")
+
+OK = 0
+CROSSCHECK_MUTUAL, CROSSCHECK_LEGACY = 0, 1
+TERMINATION = {0: "NO_CONVERGENCE", 1: "CONV_FUNCTION", 2: "CONV_GRADIENT", 3: "CONV_PARAMETER",
+               4: "CONV_RADIUS", 5: "FAILURE"}
+
+# every symbol include/lorb_cuda.h declares (tests check the .so exports all of them)
+EXPORTS = [
+    "lorb_ctx_create", "lorb_ctx_destroy", "lorb_ctx_sync", "lorb_ctx_stream",
+    "lorb_ctx_launch_count", "lorb_last_error", "lorb_version",
+    "lorb_match_bf_crosscheck", "lorb_match_knn2", "lorb_match_sweep", "lorb_bank_upload",
+    "lorb_match_sweep_resident", "lorb_sweep_plan_upload", "lorb_sweep_plan_run",
+    "lorb_sweep_plan_download", "lorb_search_proj_points", "lorb_search_proj_frame",
+    "lorb_ba_default_options", "lorb_ba_pose_only", "lorb_ba_local", "lorb_ba_local_batched",
+    "lorb_ba_problem_create", "lorb_ba_problem_reset", "lorb_ba_problem_solve",
+    "lorb_ba_problem_download", "lorb_ba_problem_destroy", "lorb_dist_get_unique_id",
+    "lorb_dist_init", "lorb_dist_finalize", "lorb_dist_allreduce_f64", "lorb_microbench_popc",
+]
+
+
+class LorbError(RuntimeError):
+    pass
+
+
+class BAOptions(C.Structure):
+    _fields_ = [("max_num_iterations", C.c_int), ("jacobi_scaling", C.c_int),
+                ("max_consecutive_invalid_steps", C.c_int), ("reserved0", C.c_int),
+                ("function_tolerance", C.c_double), ("gradient_tolerance", C.c_double),
+                ("parameter_tolerance", C.c_double), ("initial_trust_region_radius", C.c_double),
+                ("max_trust_region_radius", C.c_double), ("min_trust_region_radius", C.c_double),
+                ("min_relative_decrease", C.c_double), ("min_lm_diagonal", C.c_double),
+                ("max_lm_diagonal", C.c_double)]
+
+
+class BASummary(C.Structure):
+    _fields_ = [("initial_cost", C.c_double), ("final_cost", C.c_double),
+                ("final_radius", C.c_double), ("final_gradient_max_norm", C.c_double),
+                ("iterations", C.c_int), ("num_successful_steps", C.c_int),
+                ("num_unsuccessful_steps", C.c_int), ("termination", C.c_int)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class FrameView(C.Structure):
+    _fields_ = [("n_kp", C.c_int), ("kp_x", C.c_void_p), ("kp_y", C.c_void_p),
+                ("kp_octave", C.c_void_p), ("kp_angle", C.c_void_p), ("kp_uright", C.c_void_p),
+                ("desc", C.c_void_p), ("kp_claim_obs", C.c_void_p), ("min_x", C.c_float),
+                ("max_x", C.c_float), ("min_y", C.c_float), ("max_y", C.c_float),
+                ("n_levels", C.c_int), ("scale_factors", C.c_void_p)]
+
+
+class Intrinsics(C.Structure):
+    _fields_ = [("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float),
+                ("mbf", C.c_float), ("mb", C.c_float)]
+
+
+_lib = None
+
+
+def load_library():
+    """dlopen the C-ABI library; raise if it was not built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise LorbError(
+                "liblorb_cuda.so is not built (%s). Run `python -m lorb_slam_b200.build`; "
+                "this package has no CPU fallback." % LIB_PATH)
+        _lib = C.CDLL(LIB_PATH)
+        _lib.lorb_last_error.restype = C.c_char_p
+        _lib.lorb_version.restype = C.c_char_p
+        _lib.lorb_ctx_stream.restype = C.c_void_p
+        _lib.lorb_ctx_stream.argtypes = [C.c_void_p]
+        _lib.lorb_ctx_launch_count.restype = C.c_longlong
+        _lib.lorb_ctx_launch_count.argtypes = [C.c_void_p]
+    return _lib
+
+
+def _check(rc):
+    if rc != OK:
+        raise LorbError("lorb error %d: %s" % (rc, load_library().lorb_last_error().decode()))
+
+
+def _ptr(a):
+    return C.c_void_p(a.ctypes.data) if a is not None and a.size else C.c_void_p(0)
+
+
+def _arr(a, dt, shape=None):
+    a = np.ascontiguousarray(a, dtype=dt)
+    return a.reshape(shape) if shape is not None else a
+
+
+def ba_options(**kw):
+    o = BAOptions()
+    load_library().lorb_ba_default_options(C.byref(o))
+    for k, v in kw.items():
+        if not hasattr(o, k):
+            raise AttributeError(k)
+        setattr(o, k, v)
+    return o
+
+
+def _frame_view(fr):
+    keep = [_arr(fr["kp_x"], np.float32), _arr(fr["kp_y"], np.float32),
+            _arr(fr["kp_octave"], np.int32), _arr(fr["kp_angle"], np.float32),
+            _arr(fr["kp_uright"], np.float32), _arr(fr["desc"], np.uint8),
+            _arr(fr["kp_claim_obs"], np.int32), _arr(fr["scale_factors"], np.float32)]
+    v = FrameView(int(fr["n_kp"]), _ptr(keep[0]), _ptr(keep[1]), _ptr(keep[2]), _ptr(keep[3]),
+                  _ptr(keep[4]), _ptr(keep[5]), _ptr(keep[6]), float(fr["min_x"]),
+                  float(fr["max_x"]), float(fr["min_y"]), float(fr["max_y"]),
+                  int(fr["n_levels"]), _ptr(keep[7]))
+    return v, keep
+
+
+class Context:
+    """One lorb_ctx: a CUDA stream plus device/pinned scratch.  Not thread-safe;
+    make one per calling thread (the reference runs Matcher on the tracking
+    thread and local BA on the mapper thread, example/main.cpp:36-37)."""
+
+    def __init__(self, device=0):
+        self._lib = load_library()
+        h = C.c_void_p()
+        _check(self._lib.lorb_ctx_create(int(device), C.byref(h)))
+        self._h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.lorb_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- plumbing
+    def sync(self):
+        _check(self._lib.lorb_ctx_sync(self._h))
+
+    @property
+    def stream(self):
+        return self._lib.lorb_ctx_stream(self._h)
+
+    @property
+    def launch_count(self):
+        return int(self._lib.lorb_ctx_launch_count(self._h))
+
+    # -- brute force
+    def match_bf_crosscheck(self, q, t, mode=CROSSCHECK_MUTUAL):
+        q, t = _arr(q, np.uint8).reshape(-1, 32), _arr(t, np.uint8).reshape(-1, 32)
+        cap = max(1, min(len(q), len(t)))
+        oq, ot, od = (np.zeros(cap, np.int32) for _ in range(3))
+        keep = np.zeros(cap, np.uint8)
+        n, nk, md = C.c_int(), C.c_int(), C.c_int()
+        _check(self._lib.lorb_match_bf_crosscheck(
+            self._h, _ptr(q), len(q), _ptr(t), len(t), int(mode), _ptr(oq), _ptr(ot), _ptr(od),
+            _ptr(keep), C.byref(n), C.byref(nk), C.byref(md)))
+        k = n.value
+        return dict(q=oq[:k], t=ot[:k], dist=od[:k], keep=keep[:k], n_kept=nk.value,
+                    min_dist=md.value)
+
+    def match_knn2(self, q, t, ratio=0.8, max_dist=100):
+        q, t = _arr(q, np.uint8).reshape(-1, 32), _arr(t, np.uint8).reshape(-1, 32)
+        n = max(1, len(q))
+        idx, dist = np.zeros((n, 2), np.int32), np.zeros((n, 2), np.int32)
+        ok = np.zeros(n, np.uint8)
+        _check(self._lib.lorb_match_knn2(self._h, _ptr(q), len(q), _ptr(t), len(t),
+                                         C.c_float(ratio), int(max_dist), _ptr(idx), _ptr(dist),
+                                         _ptr(ok)))
+        return idx[:len(q)], dist[:len(q)], ok[:len(q)]
+
+    def bank_upload(self, bank):
+        bank = _arr(bank, np.uint8)
+        assert bank.ndim == 3 and bank.shape[2] == 32
+        _check(self._lib.lorb_bank_upload(self._h, _ptr(bank), bank.shape[0], bank.shape[1]))
+
+    def match_sweep(self, bank, pair_a, pair_b):
+        bank = _arr(bank, np.uint8)
+        pa, pb = _arr(pair_a, np.int32), _arr(pair_b, np.int32)
+        n = len(pa)
+        kept, mt, md = (np.zeros(max(1, n), np.int32) for _ in range(3))
+        _check(self._lib.lorb_match_sweep(self._h, _ptr(bank), bank.shape[0], bank.shape[1],
+                                          _ptr(pa), _ptr(pb), n, _ptr(kept), _ptr(mt), _ptr(md)))
+        return kept[:n], mt[:n], md[:n]
+
+    def match_sweep_resident(self, pair_a, pair_b):
+        pa, pb = _arr(pair_a, np.int32), _arr(pair_b, np.int32)
+        n = len(pa)
+        kept, mt, md = (np.zeros(max(1, n), np.int32) for _ in range(3))
+        _check(self._lib.lorb_match_sweep_resident(self._h, _ptr(pa), _ptr(pb), n, _ptr(kept),
+                                                   _ptr(mt), _ptr(md)))
+        return kept[:n], mt[:n], md[:n]
+
+    def sweep_plan_upload(self, pair_a, pair_b):
+        pa, pb = _arr(pair_a, np.int32), _arr(pair_b, np.int32)
+        self._plan_n = len(pa)
+        _check(self._lib.lorb_sweep_plan_upload(self._h, _ptr(pa), _ptr(pb), len(pa)))
+
+    def sweep_plan_run(self):
+        _check(self._lib.lorb_sweep_plan_run(self._h))
+
+    def sweep_plan_download(self):
+        n = self._plan_n
+        kept, mt, md = (np.zeros(max(1, n), np.int32) for _ in range(3))
+        _check(self._lib.lorb_sweep_plan_download(self._h, _ptr(kept), _ptr(mt), _ptr(md)))
+        return kept[:n], mt[:n], md[:n]
+
+    # -- projection-guided search
+    def search_proj_points(self, fr, pts, th):
+        v, keep = _frame_view(fr)
+        n_pts = int(pts["n_pts"])
+        a = [_arr(pts["proj_x"], np.float32), _arr(pts["proj_y"], np.float32),
+             _arr(pts["proj_xr"], np.float32), _arr(pts["level"], np.int32),
+             _arr(pts["view_cos"], np.float32), _arr(pts["active"], np.uint8),
+             _arr(pts["mp_desc"], np.uint8), _arr(pts["mp_nobs"], np.int32)]
+        kfp = np.full(max(1, n_pts), -1, np.int32)
+        pfk = np.full(max(1, v.n_kp), -1, np.int32)
+        nm, nc = C.c_int(), C.c_longlong()
+        _check(self._lib.lorb_search_proj_points(
+            self._h, C.byref(v), n_pts, *[_ptr(x) for x in a], C.c_float(th), _ptr(kfp), _ptr(pfk),
+            C.byref(nm), C.byref(nc)))
+        return dict(kp_for_point=kfp[:n_pts], point_for_kp=pfk[:v.n_kp], n_matches=nm.value,
+                    n_candidates=nc.value)
+
+    def search_proj_frame(self, cur, last, th):
+        v, keep = _frame_view(cur)
+        n_last = int(last["n_last"])
+        K = last["K"]
+        Ks = Intrinsics(K["fx"], K["fy"], K["cx"], K["cy"], K["mbf"], K["mb"])
+        tc, tl = _arr(last["tcw_cur"], np.float32), _arr(last["tcw_last"], np.float32)
+        a = [_arr(last["valid"], np.uint8), _arr(last["xw"], np.float32),
+             _arr(last["octave"], np.int32), _arr(last["angle"], np.float32),
+             _arr(last["mp_desc"], np.uint8), _arr(last["mp_nobs"], np.int32)]
+        kfi = np.full(max(1, n_last), -1, np.int32)
+        sfk = np.full(max(1, v.n_kp), -1, np.int32)
+        nm, nc = C.c_int(), C.c_longlong()
+        _check(self._lib.lorb_search_proj_frame(
+            self._h, C.byref(v), _ptr(tc), _ptr(tl), C.byref(Ks), n_last, *[_ptr(x) for x in a],
+            C.c_float(th), _ptr(kfi), _ptr(sfk), C.byref(nm), C.byref(nc)))
+        return dict(kp_for_item=kfi[:n_last], state_for_kp=sfk[:v.n_kp], n_matches=nm.value,
+                    n_candidates=nc.value)
+
+    # -- bundle adjustment
+    def ba_pose_only(self, xw, uv, K, rt, opt=None):
+        xw, uv = _arr(xw, np.float32).reshape(-1, 3), _arr(uv, np.float32).reshape(-1, 2)
+        K = _arr(K, np.float32).reshape(4)
+        rt = _arr(rt, np.float64).reshape(6).copy()
+        opt = opt or ba_options()
+        s = BASummary()
+        _check(self._lib.lorb_ba_pose_only(self._h, len(xw), _ptr(xw), _ptr(uv), _ptr(K), _ptr(rt),
+                                           C.byref(opt), C.byref(s)))
+        return rt, s.as_dict()
+
+    def ba_local(self, pb, opt=None):
+        cams = _arr(pb["cams"], np.float64).copy()
+        pts = _arr(pb["pts"], np.float64).copy()
+        oc, op = _arr(pb["obs_cam"], np.int32), _arr(pb["obs_pt"], np.int32)
+        ouv = _arr(pb["obs_uv"], np.float32)
+        fp = _arr(pb.get("fix_pt", np.zeros(0)), np.int32)
+        fuv = _arr(pb.get("fix_uv", np.zeros((0, 2))), np.float32)
+        frt = _arr(pb.get("fix_rt", np.zeros((0, 6))), np.float32)
+        K = _arr(pb["K"], np.float32).reshape(4)
+        opt = opt or ba_options()
+        s = BASummary()
+        _check(self._lib.lorb_ba_local(self._h, len(cams), _ptr(cams), len(pts), _ptr(pts), len(oc),
+                                       _ptr(oc), _ptr(op), _ptr(ouv), len(fp), _ptr(fp), _ptr(fuv),
+                                       _ptr(frt), _ptr(K), C.byref(opt), C.byref(s)))
+        return cams, pts, s.as_dict()
+
+    def ba_local_batched(self, bt, opt=None):
+        cams = _arr(bt["cams"], np.float64).copy()
+        pts = _arr(bt["pts"], np.float64).copy()
+        co, po, oo = (_arr(bt[k], np.int32) for k in ("cam_off", "pt_off", "obs_off"))
+        oc, op = _arr(bt["obs_cam"], np.int32), _arr(bt["obs_pt"], np.int32)
+        ouv = _arr(bt["obs_uv"], np.float32)
+        K = _arr(bt["K"], np.float32).reshape(4)
+        nw = int(bt["n_windows"])
+        opt = opt or ba_options()
+        sums = (BASummary * nw)()
+        _check(self._lib.lorb_ba_local_batched(
+            self._h, nw, _ptr(co), _ptr(cams), _ptr(po), _ptr(pts), _ptr(oo), _ptr(oc), _ptr(op),
+            _ptr(ouv), C.c_void_p(0), C.c_void_p(0), C.c_void_p(0), C.c_void_p(0), _ptr(K),
+            C.byref(opt), sums))
+        return cams, pts, [s.as_dict() for s in sums]
+
+    def ba_problem(self, pb):
+        return BAProblem(self, pb)
+
+    # -- multi-GPU
+    @staticmethod
+    def dist_unique_id():
+        buf = (C.c_uint8 * 128)()
+        _check(load_library().lorb_dist_get_unique_id(buf))
+        return bytes(buf)
+
+    def dist_init(self, uid, rank, world):
+        buf = (C.c_uint8 * 128).from_buffer_copy(uid)
+        _check(self._lib.lorb_dist_init(self._h, buf, int(rank), int(world)))
+
+    def dist_finalize(self):
+        _check(self._lib.lorb_dist_finalize(self._h))
+
+    def dist_allreduce_f64(self, a):
+        a = _arr(a, np.float64).copy()
+        _check(self._lib.lorb_dist_allreduce_f64(self._h, _ptr(a), a.size))
+        return a
+
+    # -- diagnostics
+    def microbench_popc(self, kind=0, iters=4096):
+        r = C.c_double()
+        _check(self._lib.lorb_microbench_popc(self._h, int(kind), int(iters), C.byref(r)))
+        return r.value
+
+
+class BAProblem:
+    """Device-resident local-BA problem (lorb_ba_problem_*)."""
+
+    def __init__(self, ctx, pb):
+        self._ctx = ctx
+        self._lib = ctx._lib
+        cams, pts = _arr(pb["cams"], np.float64), _arr(pb["pts"], np.float64)
+        oc, op = _arr(pb["obs_cam"], np.int32), _arr(pb["obs_pt"], np.int32)
+        ouv = _arr(pb["obs_uv"], np.float32)
+        fp = _arr(pb.get("fix_pt", np.zeros(0)), np.int32)
+        fuv = _arr(pb.get("fix_uv", np.zeros((0, 2))), np.float32)
+        frt = _arr(pb.get("fix_rt", np.zeros((0, 6))), np.float32)
+        K = _arr(pb["K"], np.float32).reshape(4)
+        self.C, self.P = len(cams), len(pts)
+        h = C.c_void_p()
+        _check(self._lib.lorb_ba_problem_create(
+            ctx._h, len(cams), _ptr(cams), len(pts), _ptr(pts), len(oc), _ptr(oc), _ptr(op),
+            _ptr(ouv), len(fp), _ptr(fp), _ptr(fuv), _ptr(frt), _ptr(K), C.byref(h)))
+        self._h = h
+
+    def reset(self):
+        _check(self._lib.lorb_ba_problem_reset(self._h))
+
+    def solve(self, opt=None, sharded=False):
+        opt = opt or ba_options()
+        s = BASummary()
+        _check(self._lib.lorb_ba_problem_solve(self._h, C.byref(opt), int(bool(sharded)),
+                                               C.byref(s)))
+        return s.as_dict()
+
+    def download(self):
+        cams = np.zeros((self.C, 6), np.float64)
+        pts = np.zeros((self.P, 3), np.float64)
+        _check(self._lib.lorb_ba_problem_download(self._h, _ptr(cams), _ptr(pts)))
+        return cams, pts
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.lorb_ba_problem_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

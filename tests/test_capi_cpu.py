@@ -1,0 +1,55 @@
+"""CPU-only checks of the C-ABI boundary: the library builds, loads, and
+exports every symbol include/lorb_cuda.h declares.  No compute calls."""
+import ctypes
+import os
+import re
+
+from lorb_slam_b200 import build, capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    txt = open(os.path.join(ROOT, "include", "lorb_cuda.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(lorb_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    lib_path = build.build_library()
+    assert os.path.exists(lib_path)
+    lib = ctypes.CDLL(lib_path)
+    declared = _declared_symbols()
+    assert len(declared) >= 25
+    for name in declared:
+        assert hasattr(lib, name), "missing export: " + name
+    # the python binding's list is the same set
+    assert sorted(capi.EXPORTS) == declared
+
+
+def test_version_and_default_options():
+    lib = capi.load_library()
+    assert b"sm_100a" in lib.lorb_version()
+    o = capi.ba_options()
+    assert o.max_num_iterations == 50 and o.jacobi_scaling == 1
+    assert o.function_tolerance == 1e-6 and o.initial_trust_region_radius == 1e4
+    assert o.min_lm_diagonal == 1e-6 and o.max_lm_diagonal == 1e32
+
+
+def test_no_cpu_fallback_without_device():
+    """On a box without a GPU the context refuses to exist (and says why)."""
+    import torch
+    if torch.cuda.is_available():
+        return
+    try:
+        capi.Context(0)
+    except capi.LorbError as e:
+        assert "no usable CUDA device" in str(e) or "CUDA" in str(e)
+    else:
+        raise AssertionError("context creation must fail without a CUDA device")
+
+
+def test_struct_layouts_match_header():
+    assert ctypes.sizeof(capi.BAOptions) == 16 + 9 * 8
+    assert ctypes.sizeof(capi.BASummary) == 4 * 8 + 4 * 4
+    assert ctypes.sizeof(capi.Intrinsics) == 24

@@ -1,0 +1,130 @@
+"""GPU parity: brute-force Hamming matching through the C ABI vs the oracle,
+the cv2-pinned golden vectors, and size-independent properties.
+Bar: bit-exact (indices, distances, tie-break order)."""
+import numpy as np
+import pytest
+
+from lorb_slam_b200 import synth
+from oracle import ref
+
+pytestmark = pytest.mark.gpu
+
+
+def _same(r, o):
+    assert np.array_equal(r["q"], o["q"])
+    assert np.array_equal(r["t"], o["t"])
+    assert np.array_equal(r["dist"], o["dist"])
+    assert np.array_equal(r["keep"], o["keep"])
+    assert r["n_kept"] == o["n_kept"] and r["min_dist"] == o["min_dist"]
+
+
+def test_golden_cv2(ctx, golden_dir):
+    g = np.load(golden_dir + "/bf_golden.npz")
+    for name in g["names"]:
+        r = ctx.match_bf_crosscheck(g[f"{name}_q"], g[f"{name}_t"])
+        assert np.array_equal(r["q"], g[f"{name}_mq"]), name
+        assert np.array_equal(r["t"], g[f"{name}_mt"]), name
+        assert np.array_equal(r["dist"], g[f"{name}_md"]), name
+        idx, dist, _ = ctx.match_knn2(g[f"{name}_q"], g[f"{name}_t"])
+        assert np.array_equal(idx, g[f"{name}_ki"]), name
+        assert np.array_equal(dist, g[f"{name}_kd"]), name
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("shape", [(1, 1), (1, 77), (77, 1), (31, 33), (128, 256), (129, 257),
+                                   (1000, 1000), (2000, 2000), (300, 5000), (5000, 300)])
+def test_crosscheck_vs_oracle(ctx, shape, mode):
+    rng = np.random.default_rng(hash(shape) % 2**32 + mode)
+    for kind in ("uniform", "tie"):
+        if kind == "uniform":
+            q, t = synth.descriptors_uniform(shape[0], rng), synth.descriptors_uniform(shape[1], rng)
+        else:
+            q = synth.descriptors_tie_stress(shape[0], rng, 2, 3)
+            t = synth.descriptors_tie_stress(shape[1], rng, 2, 3)
+        _same(ctx.match_bf_crosscheck(q, t, mode), ref.bf_crosscheck(q, t, mode))
+
+
+def test_empty_sides(ctx):
+    rng = np.random.default_rng(0)
+    q = synth.descriptors_uniform(10, rng)
+    e = np.zeros((0, 32), np.uint8)
+    for a, b in ((q, e), (e, q), (e, e)):
+        r = ctx.match_bf_crosscheck(a, b)
+        assert len(r["q"]) == 0 and r["n_kept"] == 0 and r["min_dist"] == -1
+    idx, dist, ok = ctx.match_knn2(q, e)
+    assert (idx == -1).all() and (dist == 256).all() and not ok.any()
+
+
+def test_wide_tile_path(ctx):
+    """Large enough that the 4-queries-per-thread tile variant is chosen."""
+    rng = np.random.default_rng(5)
+    q, t = synth.descriptors_uniform(9000, rng), synth.descriptors_uniform(9000, rng)
+    t[:3000] = synth.descriptors_noisy_copy(q[rng.permutation(9000)[:3000]], rng, 0.05)
+    _same(ctx.match_bf_crosscheck(q, t), ref.bf_crosscheck(q, t))
+    idx, dist, ok = ctx.match_knn2(q[:4500], t)
+    oi, od = ref.knn2(q[:4500], t)
+    assert np.array_equal(idx, oi) and np.array_equal(dist, od)
+
+
+def test_knn2_ratio(ctx):
+    rng = np.random.default_rng(3)
+    t = synth.descriptors_uniform(700, rng)
+    q = synth.descriptors_noisy_copy(t[rng.permutation(700)[:400]], rng, 0.1)
+    idx, dist, ok = ctx.match_knn2(q, t, ratio=0.8, max_dist=100)
+    oi, od = ref.knn2(q, t)
+    assert np.array_equal(idx, oi) and np.array_equal(dist, od)
+    exp = (od[:, 0] <= 100) & (od[:, 0].astype(np.float32) < np.float32(0.8) * od[:, 1].astype(np.float32))
+    assert np.array_equal(ok.astype(bool), exp)
+
+
+def test_properties_full_size(ctx):
+    """Size-independent properties at BASELINE config-5 descriptor counts."""
+    rng = np.random.default_rng(11)
+    a = synth.descriptors_uniform(2000, rng)
+    # identical sets: every descriptor matches itself at distance 0
+    r = ctx.match_bf_crosscheck(a, a.copy())
+    assert np.array_equal(r["q"], np.arange(2000)) and np.array_equal(r["t"], np.arange(2000))
+    assert (r["dist"] == 0).all() and r["n_kept"] == 2000 and r["min_dist"] == 0
+    # permuted train set: matches follow the permutation
+    perm = rng.permutation(2000)
+    r = ctx.match_bf_crosscheck(a, a[perm])
+    inv = np.argsort(perm)
+    assert np.array_equal(r["t"], inv)
+    # symmetry of mutual cross-check: swapping sides transposes the match set
+    b = synth.descriptors_noisy_copy(a[rng.permutation(2000)], rng, 0.2)
+    r1, r2 = ctx.match_bf_crosscheck(a, b), ctx.match_bf_crosscheck(b, a)
+    s1 = set(zip(r1["q"].tolist(), r1["t"].tolist()))
+    s2 = set(zip(r2["t"].tolist(), r2["q"].tolist()))
+    assert s1 == s2 and r1["min_dist"] == r2["min_dist"]
+
+
+@pytest.mark.parametrize("n_desc", [100, 512, 513, 1000, 2000, 2048])
+def test_sweep_vs_oracle(ctx, n_desc):
+    n_kf = 6
+    bank = synth.kf_bank(n_kf, n_desc, seed=n_desc)
+    pa, pb = synth.all_pairs(n_kf)
+    # also unordered / repeated pairs and a self pair
+    pa = np.concatenate([pa, [3, 5, 2]]).astype(np.int32)
+    pb = np.concatenate([pb, [1, 5, 0]]).astype(np.int32)
+    kept, mt, md = ctx.match_sweep(bank, pa, pb)
+    ok, om, od = ref.sweep(bank, pa, pb)
+    assert np.array_equal(kept, ok) and np.array_equal(mt, om) and np.array_equal(md, od)
+    # per-pair equality with the single-pair entry point
+    r = ctx.match_bf_crosscheck(bank[pa[1]], bank[pb[1]])
+    assert r["n_kept"] == kept[1] and len(r["q"]) == mt[1] and r["min_dist"] == md[1]
+
+
+def test_sweep_many_pairs_resident(ctx):
+    """More pairs than SMs, exercising the persistent loop, A reuse and B double buffering."""
+    n_kf, n_desc = 24, 700
+    bank = synth.kf_bank(n_kf, n_desc, seed=1)
+    pa, pb = synth.all_pairs(n_kf)
+    ctx.bank_upload(bank)
+    kept, mt, md = ctx.match_sweep_resident(pa, pb)
+    ok, om, od = ref.sweep(bank, pa, pb)
+    assert np.array_equal(kept, ok) and np.array_equal(mt, om) and np.array_equal(md, od)
+    ctx.sweep_plan_upload(pa[:50], pb[:50])
+    ctx.sweep_plan_run()
+    ctx.sweep_plan_run()
+    k2, m2, d2 = ctx.sweep_plan_download()
+    assert np.array_equal(k2, ok[:50]) and np.array_equal(m2, om[:50]) and np.array_equal(d2, od[:50])
