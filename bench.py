@@ -1,0 +1,481 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the LORB-SLAM hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload NAME]
+
+Headline workload (default, `sweep`): BASELINE.json config 5's keyframe-pair
+matching sweep — a bank of 4096 keyframes x 2000 ORB descriptors (262 MB, larger
+than the 126 MB L2) resident in HBM.  One step = every pair among one block of
+128 consecutive keyframes (8128 keyframe pairs x 2000 x 2000 descriptor pairs),
+a different block every step; rank r of N takes blocks r, r+N, ... (weak
+scaling: per-GPU work fixed, no data-path collective).  metric =
+descriptor-pairs/s (cross-checked Hamming match incl. the max(2*minDist,30)
+filter), exact same result as the reference's BFMatcher path.
+
+  value  whole-job pairs/s, bank and pair plan already in HBM, CUDA events on the
+         library's stream, max over ranks.
+  e2e    same step through the host-buffer C-ABI call (lorb_match_sweep): pinned
+         host descriptors -> H2D -> kernels -> D2H of the per-pair results.
+
+Other workloads (`--workload ba_batched | ba_large | ba_local | bf | proj`) put
+another BASELINE config under the same contract; their short versions are also
+reported in `extra` of the default line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_KF, N_DESC, BLOCK_KF = 4096, 2000, 128
+PAIRS_PER_KF_PAIR = N_DESC * N_DESC
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1]))
+                smax = float(r[2])
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if r[5 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        # median of the upper half = clock under load (the sampler also sees idle edges)
+        sm.sort()
+        load = sm[len(sm) // 2:] if sm else []
+        med = load[len(load) // 2] if load else None
+        return {"sm_mhz": med, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def _dist_setup(n_gpus):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return rank, world, local
+
+
+def _barrier(world):
+    import torch
+    import torch.distributed as dist
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def _max_over_ranks(x, world, local):
+    import torch
+    import torch.distributed as dist
+    if world == 1:
+        return x
+    t = torch.tensor([x], dtype=torch.float64, device=torch.device("cuda", local))
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def _sum_over_ranks(x, world, local):
+    import torch
+    import torch.distributed as dist
+    if world == 1:
+        return x
+    t = torch.tensor([x], dtype=torch.float64, device=torch.device("cuda", local))
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+def _events(ctx, local):
+    import torch
+    st = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))
+    return st, torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+
+# ----------------------------------------------------------------------- sweep
+def _block_pairs():
+    a, b = np.triu_indices(BLOCK_KF, k=1)
+    return a.astype(np.int32), b.astype(np.int32)
+
+
+def _make_bank(seed=0):
+    rng = np.random.default_rng(seed)
+    return rng.integers(0, 256, size=(N_KF, N_DESC, 32), dtype=np.uint8)
+
+
+def cpu_baseline_sweep(bank, target_s=12.0):
+    """Oracle (CPU restatement, OpenMP over keyframe pairs) on a bounded sample."""
+    from oracle import ref
+    cores = os.cpu_count() or 1
+    pa, pb = _block_pairs()
+    n0 = max(cores, 8)
+    t0 = time.time()
+    ref.sweep(bank, pa[:n0], pb[:n0])
+    dt = time.time() - t0
+    n = int(min(len(pa), max(n0, n0 * target_s / max(dt, 1e-3))))
+    t0 = time.time()
+    ref.sweep(bank, pa[:n], pb[:n])
+    dt = time.time() - t0
+    out = {"value": n * PAIRS_PER_KF_PAIR / dt, "unit": "descriptor-pairs/s", "cores": cores,
+           "kind": "port",
+           "sample": "%d keyframe pairs (2000x2000 each) of the first block, oracle/match_ref.c "
+                     "-O2 -mpopcnt, OpenMP over pairs" % n}
+    try:  # the library routine the reference itself calls, for context
+        import cv2
+        cv2.setNumThreads(cores)
+        m = cv2.BFMatcher(cv2.NORM_HAMMING, True)
+        t0 = time.time()
+        reps = 6
+        for i in range(reps):
+            m.match(bank[pa[i]], bank[pb[i]])
+        out["cv2_bfmatcher_value"] = reps * PAIRS_PER_KF_PAIR / (time.time() - t0)
+        out["cv2_threads"] = cores
+    except Exception:
+        pass
+    return out
+
+
+def run_sweep(args, rank, world, local):
+    import torch
+    from lorb_slam_b200 import capi
+    ctx = capi.Context(local)
+    bank = _make_bank(0)
+    n_blocks = N_KF // BLOCK_KF
+    pa, pb = _block_pairs()
+    n_pairs = len(pa)
+    ctx.bank_upload(bank)
+    ctx.sweep_plan_upload(pa, pb)
+    my_blocks = [(rank + i * world) % n_blocks for i in range(args.warmup + args.steps)]
+    st, ev0, ev1 = _events(ctx, local)
+    for i in range(args.warmup):
+        ctx.sweep_plan_run(my_blocks[i] * BLOCK_KF)
+    ctx.sync()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    _barrier(world)
+    l0 = ctx.launch_count
+    ev0.record(st)
+    for i in range(args.steps):
+        ctx.sweep_plan_run(my_blocks[args.warmup + i] * BLOCK_KF)
+    ev1.record(st)
+    ctx.sync()
+    _barrier(world)
+    launches = ctx.launch_count - l0
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_max = _max_over_ranks(ms, world, local)
+    kernel_ms = ms / args.steps  # one kernel launch per step on this rank
+    # sanity: the last block's result equals the host-buffer path's
+    kept_dev = ctx.sweep_plan_download()[0]
+
+    # ---- e2e through the host-buffer entry point, pinned host inputs
+    pinned = torch.empty((BLOCK_KF, N_DESC, 32), dtype=torch.uint8).pin_memory()
+    host_blk = pinned.numpy()
+    e2e_steps = args.steps
+    for i in range(min(2, args.warmup)):
+        host_blk[...] = bank[my_blocks[i] * BLOCK_KF:(my_blocks[i] + 1) * BLOCK_KF]
+        ctx.match_sweep(host_blk, pa, pb)
+    _barrier(world)
+    t_e2e = 0.0
+    kept_e2e = None
+    for i in range(e2e_steps):
+        b = my_blocks[args.warmup + i]
+        host_blk[...] = bank[b * BLOCK_KF:(b + 1) * BLOCK_KF]  # staging of the step's input (untimed)
+        t0 = time.perf_counter()
+        kept_e2e, _, _ = ctx.match_sweep(host_blk, pa, pb)
+        t_e2e += time.perf_counter() - t0
+    assert np.array_equal(kept_e2e, kept_dev), "device-resident and host-buffer paths disagree"
+    e2e_max = _max_over_ranks(t_e2e, world, local)
+    # restore the full bank for anything that follows
+    total_pairs = float(world) * args.steps * n_pairs * PAIRS_PER_KF_PAIR
+    value = total_pairs / (ms_max * 1e-3)
+    e2e_value = total_pairs / e2e_max
+
+    res = None
+    if rank == 0:
+        hbm_peak, peak_src = _peaks()
+        ctx.bank_upload(bank[:BLOCK_KF])  # small bank is enough for the micro-benchmarks
+        peak_words = ctx.microbench_popc(1, 4096)
+        peak_words_popc8 = ctx.microbench_popc(0, 4096)
+        words = n_pairs * PAIRS_PER_KF_PAIR * 8.0
+        achieved = words / (kernel_ms * 1e-3)
+        alg_bytes = n_pairs * 2 * N_DESC * 32.0  # both descriptor blocks of every keyframe pair
+        res = {
+            "metric": "descriptor-pairs/s Hamming match", "value": value,
+            "unit": "descriptor-pairs/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u32 (xor/popc on 256-bit strings)",
+            "data": "synthetic (uniform random 256-bit descriptors, seed 0)",
+            "config": {"workload": "kf_pair_sweep: 4096 keyframes x 2000 descriptors resident "
+                                   "(262 MB > 126 MB L2); step = all 8128 pairs of one 128-keyframe "
+                                   "block, cross-check + max(2*minDist,30) filter",
+                       "keyframe_pairs_per_step_per_gpu": n_pairs,
+                       "descriptor_pairs_per_step_per_gpu": n_pairs * PAIRS_PER_KF_PAIR,
+                       "l2": "bank larger than L2; a different 8 MB block every step",
+                       "sharding": "blocks round-robin over ranks, no collective"},
+            "e2e": {"value": e2e_value, "unit": "descriptor-pairs/s",
+                    "h2d_bytes_per_step": int(host_blk.nbytes + 2 * pa.nbytes),
+                    "d2h_bytes_per_step": int(3 * 4 * n_pairs)},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "int-pipe (LOP3/POPC issue; operands live in smem/registers)",
+                         "achieved": achieved / 1e9, "peak": peak_words / 1e9,
+                         "unit": "G 32-bit words/s (1 descriptor pair = 8 words)",
+                         "frac": achieved / peak_words,
+                         "peak_source": "measured in this run: lorb_microbench_popc(kind=1), the "
+                                        "carry-save distance body on register operands, whole GPU",
+                         "peak_plain_popc8": peak_words_popc8 / 1e9,
+                         "frac_of_plain_popc8": achieved / peak_words_popc8,
+                         "traffic": None},
+            "roofline_hbm": {"bound": "hbm", "achieved": alg_bytes / (kernel_ms * 1e-3) / 1e9,
+                             "peak": hbm_peak, "unit": "GB/s",
+                             "frac": alg_bytes / (kernel_ms * 1e-3) / 1e9 / hbm_peak,
+                             "peak_source": peak_src,
+                             "note": "algorithmic bytes = 2 x 64 KB descriptor blocks per keyframe "
+                                     "pair; the kernel is not HBM-bound"},
+        }
+    ctx.close()
+    return res, bank
+
+
+# ------------------------------------------------------------------- BA extras
+def _ba_opts_fixed_iters(mod, iters=10):
+    """Exactly `iters` LM attempts: tolerances disabled (negative), as BASELINE's
+    '10 LM iterations' asks."""
+    return mod.ba_options(max_num_iterations=iters, function_tolerance=-1.0,
+                          parameter_tolerance=-1.0, gradient_tolerance=-1.0,
+                          max_consecutive_invalid_steps=1 << 30)
+
+
+def extras(ctx, local):
+    """Short versions of the other BASELINE configs (device-timed with CUDA
+    events where a resident form exists, else wall clock through the C ABI)."""
+    from lorb_slam_b200 import capi, synth
+    out = {}
+    rng = np.random.default_rng(0)
+    # cfg 1: 1000 x 1000 brute force through the host-buffer call
+    q, t = synth.descriptors_uniform(1000, rng), synth.descriptors_uniform(1000, rng)
+    ctx.match_bf_crosscheck(q, t)
+    t0 = time.perf_counter()
+    reps = 200
+    for _ in range(reps):
+        ctx.match_bf_crosscheck(q, t)
+    dt = (time.perf_counter() - t0) / reps
+    out["bf_1000x1000_e2e"] = {"us_per_call": dt * 1e6, "descriptor_pairs_per_s": 1e6 / dt}
+    # cfg 2: projection-guided search
+    fr = synth.make_frame(2000, 0)
+    pts = synth.make_proj_points(fr, 5000, 0)
+    for th in (1.0, 15.0):
+        r = ctx.search_proj_points(fr, pts, th)
+        t0 = time.perf_counter()
+        reps = 30
+        for _ in range(reps):
+            ctx.search_proj_points(fr, pts, th)
+        dt = (time.perf_counter() - t0) / reps
+        out["proj_5000pts_2000kp_th%g_e2e" % th] = {
+            "us_per_call": dt * 1e6, "map_points_per_s": 5000 / dt,
+            "candidate_pairs": r["n_candidates"], "candidate_pairs_per_s": r["n_candidates"] / dt}
+    # cfg 3: local BA, 10 LM iterations
+    pb = synth.make_ba_problem(0, C=10, P=5000)
+    opt = _ba_opts_fixed_iters(capi)
+    prob = ctx.ba_problem(pb)
+    prob.solve(opt)
+    best = 1e9
+    for _ in range(3):
+        prob.reset()
+        ctx.sync()
+        t0 = time.perf_counter()
+        s = prob.solve(opt)
+        best = min(best, time.perf_counter() - t0)
+    prob.close()
+    t0 = time.perf_counter()
+    ctx.ba_local(pb, opt)
+    e2e = time.perf_counter() - t0
+    out["ba_local_10kf_5kpts_30kobs"] = {
+        "ms_per_local_ba_resident": best * 1e3, "ms_per_local_ba_e2e": e2e * 1e3,
+        "lm_iterations": s["iterations"],
+        "obs_per_s_per_lm_iter": pb["O"] * s["iterations"] / best}
+    return out
+
+
+def run_ba_batched(args, rank, world, local):
+    """BASELINE config 4: 512 independent 10-keyframe windows sharded over ranks
+    (weak scaling variant: `--windows` per GPU, default 512/8 = 64)."""
+    from lorb_slam_b200 import capi, synth
+    ctx = capi.Context(local)
+    nw = args.windows
+    pbs = [synth.make_ba_problem(rank * nw + i, C=10, P=5000) for i in range(nw)]
+    bt = synth.batch_windows(pbs)
+    opt = _ba_opts_fixed_iters(capi)
+    obs = int(bt["obs_off"][-1])
+    for _ in range(args.warmup):
+        ctx.ba_local_batched(bt, opt)
+    _barrier(world)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = ctx.launch_count
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        _, _, sums = ctx.ba_local_batched(bt, opt)
+    dt = time.perf_counter() - t0
+    launches = ctx.launch_count - l0
+    clocks = sampler.stop() if rank == 0 else None
+    dt_max = _max_over_ranks(dt, world, local)
+    iters = sum(s["iterations"] for s in sums) / len(sums)
+    value = world * args.steps * obs * iters / dt_max
+    res = None
+    if rank == 0:
+        res = {"metric": "BA observations/s per LM iter", "value": value,
+               "unit": "observations*iterations/s", "n_gpus": world, "steps": args.steps,
+               "warmup": args.warmup, "ms_per_step": dt_max / args.steps * 1e3,
+               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+               "data": "synthetic (SURVEY 8(d) cfg 3 generator, seeds rank*W+i)",
+               "config": {"workload": "batched local BA: %d independent windows per GPU, each 10 "
+                                      "keyframes / 5000 points / 30000 observations, 10 LM "
+                                      "iterations, through lorb_ba_local_batched (host buffers)" % nw,
+                          "l2": "per-step inputs re-uploaded from host"},
+               "e2e": {"value": value, "unit": "observations*iterations/s",
+                       "h2d_bytes_per_step": int(bt["cams"].nbytes + bt["pts"].nbytes +
+                                                 bt["obs_uv"].nbytes + 2 * bt["obs_cam"].nbytes),
+                       "d2h_bytes_per_step": int(bt["cams"].nbytes + bt["pts"].nbytes)},
+               "gpu_launches": int(launches), "clocks": clocks,
+               "ms_per_local_ba": dt_max / args.steps / nw * 1e3, "lm_iterations": iters}
+    ctx.close()
+    return res, None
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="lorb", choices=["lorb", "reference"])
+    ap.add_argument("--workload", default="sweep", choices=["sweep", "ba_batched"])
+    ap.add_argument("--windows", type=int, default=64)
+    ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "lorb" else args.warmup
+
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    rank, world, local = _dist_setup(args.gpus)
+    if args.workload == "ba_batched":
+        res, bank = run_ba_batched(args, rank, world, local)
+    else:
+        res, bank = run_sweep(args, rank, world, local)
+    if rank == 0:
+        if args.workload == "sweep":
+            if not args.no_extras:
+                from lorb_slam_b200 import capi
+                ctx = capi.Context(local)
+                try:
+                    res["extra"] = extras(ctx, local)
+                finally:
+                    ctx.close()
+            if world == 1 and not args.no_cpu_baseline:
+                res["cpu_baseline"] = cpu_baseline_sweep(bank)
+        print(json.dumps(res), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def reference_arm(args):
+    """The reference's own CPU path for the same metric/config, on the host
+    cores of this box.  The reference cannot be compiled here (OpenCV-C++ and
+    Ceres are absent), so this times the oracle port — the one other place
+    bench.py may execute oracle/ — with all host threads; each step is a bounded
+    sample of the workload.  Rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import ref
+    cores = os.cpu_count() or 1
+    bank = _make_bank(0)[:BLOCK_KF]
+    pa, pb = _block_pairs()
+    n = max(cores, 8) * 16  # keyframe pairs per step (bounded sample, ~0.1-0.3 s of all-core work)
+    for _ in range(args.warmup):
+        ref.sweep(bank, pa[:n], pb[:n])
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        o = (s * n) % (len(pa) - n)
+        ref.sweep(bank, pa[o:o + n], pb[o:o + n])
+    dt = time.perf_counter() - t0
+    value = args.steps * n * PAIRS_PER_KF_PAIR / dt
+    sample = ("%d keyframe pairs (2000x2000 descriptors each) per step out of the 8128 of a block; "
+              "oracle/match_ref.c (-O2 -mpopcnt), OpenMP over pairs" % n)
+    print(json.dumps({
+        "impl": "reference", "metric": "descriptor-pairs/s Hamming match", "value": value,
+        "unit": "descriptor-pairs/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u64 popcnt", "data": "synthetic",
+        "config": {"workload": "kf_pair_sweep (bounded sample): " + sample},
+        "cpu_baseline": {"value": value, "unit": "descriptor-pairs/s", "cores": cores,
+                         "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "descriptor-pairs/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0}}), flush=True)
+
+
+if __name__ == "__main__":
+    main()

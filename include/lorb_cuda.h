@@ -132,6 +132,9 @@ int lorb_match_sweep_resident(lorb_ctx* ctx, const int* pair_a, const int* pair_
  * results stay on the device until lorb_sweep_plan_download. */
 int lorb_sweep_plan_upload(lorb_ctx* ctx, const int* pair_a, const int* pair_b, int n_pairs);
 int lorb_sweep_plan_run(lorb_ctx* ctx);
+/* Same plan, keyframe indices shifted by kf_base (sweeps block after block of a
+ * resident bank with one uploaded pair pattern). */
+int lorb_sweep_plan_run_at(lorb_ctx* ctx, int kf_base);
 int lorb_sweep_plan_download(lorb_ctx* ctx, int* out_kept, int* out_matches, int* out_min);
 
 /* ------------------------------------------- projection-guided search (a5/a6) */

@@ -24,7 +24,7 @@ EXPORTS = [
     "lorb_ctx_launch_count", "lorb_last_error", "lorb_version",
     "lorb_match_bf_crosscheck", "lorb_match_knn2", "lorb_match_sweep", "lorb_bank_upload",
     "lorb_match_sweep_resident", "lorb_sweep_plan_upload", "lorb_sweep_plan_run",
-    "lorb_sweep_plan_download", "lorb_search_proj_points", "lorb_search_proj_frame",
+    "lorb_sweep_plan_download", "lorb_sweep_plan_run_at", "lorb_search_proj_points", "lorb_search_proj_frame",
     "lorb_ba_default_options", "lorb_ba_pose_only", "lorb_ba_local", "lorb_ba_local_batched",
     "lorb_ba_problem_create", "lorb_ba_problem_reset", "lorb_ba_problem_solve",
     "lorb_ba_problem_download", "lorb_ba_problem_destroy", "lorb_dist_get_unique_id",
@@ -218,8 +218,8 @@ class Context:
         self._plan_n = len(pa)
         _check(self._lib.lorb_sweep_plan_upload(self._h, _ptr(pa), _ptr(pb), len(pa)))
 
-    def sweep_plan_run(self):
-        _check(self._lib.lorb_sweep_plan_run(self._h))
+    def sweep_plan_run(self, kf_base=0):
+        _check(self._lib.lorb_sweep_plan_run_at(self._h, int(kf_base)))
 
     def sweep_plan_download(self):
         n = self._plan_n

@@ -60,7 +60,7 @@ struct lorb_ctx {
   lorb::Buf bank;
   int bank_n_kf = 0, bank_n_desc = 0;
   lorb::Buf plan_pairs, plan_out;
-  int plan_n_pairs = 0;
+  int plan_n_pairs = 0, plan_max_kf = 0;
   lorb::Dist* dist = nullptr;
 };
 

@@ -294,6 +294,7 @@ template <int QPT, bool CSA>
 __global__ void __launch_bounds__(SWEEP_THREADS, 1)
     sweep_kernel(const uint4* __restrict__ bank, int n_desc, const int2* __restrict__ pairs,
                  int n_pairs, int* __restrict__ out /* [n_pairs][3] kept, matches, min */) {
+  // `bank` already points at keyframe kf_base (lorb_sweep_plan_run_at)
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int desc_bytes = n_desc * 32;
   const int buf_bytes = (desc_bytes + 127) & ~127;
@@ -631,6 +632,8 @@ int lorb_sweep_plan_upload(lorb_ctx* c, const int* pa, const int* pb, int n_pair
   LORB_TRY(check_pairs(c, pa, pb, n_pairs));
   LORB_CUDA_TRY(cudaSetDevice(c->device));
   c->plan_n_pairs = n_pairs;
+  c->plan_max_kf = 0;
+  for (int i = 0; i < n_pairs; i++) c->plan_max_kf = std::max(c->plan_max_kf, std::max(pa[i], pb[i]));
   if (n_pairs == 0) return LORB_OK;
   LORB_TRY(c->plan_pairs.reserve((size_t)n_pairs * 8));
   LORB_TRY(c->plan_out.reserve((size_t)n_pairs * 12));
@@ -643,13 +646,17 @@ int lorb_sweep_plan_upload(lorb_ctx* c, const int* pa, const int* pb, int n_pair
   return LORB_OK;
 }
 
-int lorb_sweep_plan_run(lorb_ctx* c) {
+int lorb_sweep_plan_run_at(lorb_ctx* c, int kf_base) {
   LORB_REQUIRE(c, "ctx");
   LORB_REQUIRE(c->bank_n_kf > 0, "no bank uploaded");
+  LORB_REQUIRE(kf_base >= 0 && kf_base + c->plan_max_kf < c->bank_n_kf, "kf_base out of range");
   LORB_CUDA_TRY(cudaSetDevice(c->device));
-  return launch_sweep(c, c->bank.as<uint4>(), c->bank_n_desc, c->plan_pairs.as<int2>(),
-                      c->plan_n_pairs, c->plan_out.as<int>());
+  return launch_sweep(c, c->bank.as<uint4>() + (size_t)kf_base * c->bank_n_desc * 2,
+                      c->bank_n_desc, c->plan_pairs.as<int2>(), c->plan_n_pairs,
+                      c->plan_out.as<int>());
 }
+
+int lorb_sweep_plan_run(lorb_ctx* c) { return lorb_sweep_plan_run_at(c, 0); }
 
 int lorb_sweep_plan_download(lorb_ctx* c, int* out_kept, int* out_matches, int* out_min) {
   LORB_REQUIRE(c, "ctx");

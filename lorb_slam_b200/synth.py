@@ -239,7 +239,7 @@ def make_ba_problem(seed=0, C=10, P=5000, obs_per_point=(6,), traj_len=5.0, fixe
     half = max(5.0, traj_len / 2 + 5.0)
     pts = np.empty((P, 3))
     obs_cam, obs_pt = [], []
-    ks = rng.choice(np.asarray(obs_per_point), size=P)
+    ks = np.minimum(rng.choice(np.asarray(obs_per_point), size=P), C)
     todo = np.arange(P)
     chunk = 20000
     while len(todo):
@@ -247,7 +247,7 @@ def make_ba_problem(seed=0, C=10, P=5000, obs_per_point=(6,), traj_len=5.0, fixe
         cand = np.stack([rng.uniform(traj_len / 2 - half, traj_len / 2 + half, n),
                          rng.uniform(-3.0, 3.0, n), rng.uniform(4.0, 20.0, n)], 1)
         done = np.zeros(n, bool)
-        kmax = int(np.max(obs_per_point))
+        kmax = min(int(np.max(obs_per_point)), C)
         for a in range(0, n, chunk):
             X = cand[a:a + chunk]
             u, v, z = _project(cam_rv[None], cam_t[None], X[:, None, :], K)
