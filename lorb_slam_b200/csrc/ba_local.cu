@@ -134,7 +134,11 @@ __device__ __forceinline__ double block_max(double v, double* red) {
 // Build pass.  Eight lanes per point, one observation per lane per round.
 // FULL = false: initial pass (scales are 1): cost, H_cc / g_c, point column
 // norms -> scale_p, |x|^2, gradient max.  FULL = true: one LM attempt.
-template <bool FULL>
+// SMALL = true: windows with few cameras (n = 6C <= 96).  All blocks of such a
+// window hit the same few hundred H_cc / S addresses, and same-address fp64
+// atomics serialise in L2 (profiles/ba_launches_r01.md), so every CTA first
+// accumulates into a private copy of `lin` in shared memory and flushes it once.
+template <bool FULL, bool SMALL>
 __global__ void __launch_bounds__(BA_THREADS)
     ba_build_kernel(const BADev* __restrict__ probs, lorb_ba_options opt, int force) {
   const BADev p = probs[blockIdx.y];
@@ -143,6 +147,16 @@ __global__ void __launch_bounds__(BA_THREADS)
   __shared__ double Wsm[BA_THREADS][18];
   __shared__ int Csm[BA_THREADS];
   __shared__ double red[BA_THREADS / 32];
+  extern __shared__ double slin[];  // SMALL: [S n*n | Hcc 21C | gc 6C | rhs_corr 6C]
+  const int lin_n = p.n * p.n + (HCC + 12) * p.C;
+  if (SMALL) {
+    for (int i = threadIdx.x; i < lin_n; i += BA_THREADS) slin[i] = 0.0;
+    __syncthreads();
+  }
+  double* const accS = SMALL ? slin : p.S;
+  double* const accH = SMALL ? slin + (size_t)p.n * p.n : p.Hcc;
+  double* const accG = SMALL ? slin + (size_t)p.n * p.n + HCC * p.C : p.gc;
+  double* const accR = SMALL ? slin + (size_t)p.n * p.n + (HCC + 6) * p.C : p.rhs_corr;
   const int cur = st->cur;
   const double* cams = p.cams[cur];
   const double* pts = p.pts[cur];
@@ -187,13 +201,13 @@ __global__ void __launch_bounds__(BA_THREADS)
 #pragma unroll
         for (int a = 0; a < 3; a++) g[a] += Jp[a] * r[0] + Jp[3 + a] * r[1];
         if (cam >= 0) {
-          double* H = p.Hcc + HCC * (size_t)cam;
+          double* H = accH + HCC * (size_t)cam;
           int k = 0;
 #pragma unroll
           for (int a = 0; a < 6; a++) {
 #pragma unroll
             for (int b = a; b < 6; b++) atomicAdd(&H[k++], Jc[a] * Jc[b] + Jc[6 + a] * Jc[6 + b]);
-            atomicAdd(&p.gc[6 * cam + a], Jc[a] * r[0] + Jc[6 + a] * r[1]);
+            atomicAdd(&accG[6 * cam + a], Jc[a] * r[0] + Jc[6 + a] * r[1]);
           }
         }
       }
@@ -257,7 +271,7 @@ __global__ void __launch_bounds__(BA_THREADS)
           Yi[3 * a + 0] = w0 * hi[0] + w1 * hi[1] + w2 * hi[2];
           Yi[3 * a + 1] = w0 * hi[1] + w1 * hi[3] + w2 * hi[4];
           Yi[3 * a + 2] = w0 * hi[2] + w1 * hi[4] + w2 * hi[5];
-          atomicAdd(&p.rhs_corr[6 * ci + a],
+          atomicAdd(&accR[6 * ci + a],
                     Yi[3 * a] * g[0] + Yi[3 * a + 1] * g[1] + Yi[3 * a + 2] * g[2]);
         }
       }
@@ -291,7 +305,7 @@ __global__ void __launch_bounds__(BA_THREADS)
           // upper block triangle only (finish mirrors); equal cameras keep both orders
           if (act_i && cj >= ci) {
             const double* Wj = Wsm[src];
-            double* Sblk = p.S + (size_t)(6 * ci) * n + 6 * cj;
+            double* Sblk = accS + (size_t)(6 * ci) * n + 6 * cj;
 #pragma unroll
             for (int a = 0; a < 6; a++)
 #pragma unroll
@@ -304,6 +318,13 @@ __global__ void __launch_bounds__(BA_THREADS)
         }
         __syncwarp();
       }
+    }
+  }
+  if (SMALL) {
+    __syncthreads();
+    for (int i = tid; i < lin_n; i += BA_THREADS) {
+      const double v = slin[i];
+      if (v != 0.0) atomicAdd(&p.lin[i], v);
     }
   }
   double t = block_sum(cost_acc, red);
@@ -451,6 +472,116 @@ __global__ void __launch_bounds__(256) ba_chol_small_kernel(const BADev* __restr
   __syncthreads();
   for (int i = tid; i < n; i += blockDim.x) p.rhs[i] = b[i];
   if (tid == 0 && !s_ok) st->solve_ok = 0;
+}
+
+// Small windows: one CTA does everything between the build pass and the
+// back-substitution: gradient-tolerance test, assembly of the damped reduced
+// camera system in shared memory, Cholesky, both triangular solves, candidate
+// cameras and their rotation blocks.  L is kept transposed in the (unused) upper
+// triangle so a column step needs a single barrier.
+__global__ void __launch_bounds__(256)
+    ba_solve_small_kernel(const BADev* __restrict__ probs, lorb_ba_options opt) {
+  const BADev p = probs[blockIdx.y];
+  LMState* st = p.st;
+  if (st->done) return;
+  extern __shared__ double A[];  // n*n | b[n] | diag[n]
+  __shared__ double red[8];
+  __shared__ int s_ok, s_done;
+  const int n = p.n, tid = threadIdx.x;
+  double* b = A + (size_t)n * n;
+  double* dg = b + n;
+  // gradient tolerance of the point accepted by the previous attempt
+  double gm = 0;
+  for (int i = tid; i < n; i += blockDim.x) gm = fmax(gm, fabs(p.gc[i] / p.scale_c[i]));
+  const double gmx = block_max(gm, red);
+  if (tid == 0) {
+    s_done = 0;
+    s_ok = (p.tail[2] == 0.0) ? 1 : 0;
+    if (st->check_gradient) {
+      st->gmax = fmax(gmx, st->acc_gmax);
+      st->check_gradient = 0;
+      if (st->gmax <= opt.gradient_tolerance) {
+        st->termination = LORB_BA_CONV_GRADIENT;
+        st->done = 1;
+        s_done = 1;
+      }
+    }
+  }
+  __syncthreads();
+  if (s_done) return;
+  const double radius = st->radius;
+  for (int idx = tid; idx < n * n; idx += blockDim.x) {
+    const int i = idx / n, j = idx % n;
+    const int ci = i / 6, cj = j / 6;
+    double v;
+    if (ci == cj) {
+      const int a = i % 6, c = j % 6;
+      const double h = p.Hcc[HCC * (size_t)ci + (a <= c ? upper_idx(a, c) : upper_idx(c, a))];
+      v = p.S[idx] + h;
+      if (a == c) v += clamp_diag(h, opt.min_lm_diagonal, opt.max_lm_diagonal) / radius;
+    } else {
+      v = ci < cj ? p.S[idx] : p.S[(size_t)j * n + i];
+    }
+    A[idx] = v;
+  }
+  for (int i = tid; i < n; i += blockDim.x) b[i] = p.gc[i] - p.rhs_corr[i];
+  __syncthreads();
+  const int ty = tid >> 4, tx = tid & 15;
+  for (int j = 0; j < n; j++) {
+    double d = A[j * n + j];
+    if (!(d > 0.0)) {
+      if (tid == 0) s_ok = 0;
+      d = 1.0;
+    }
+    const double inv_d = 1.0 / d, inv_s = 1.0 / sqrt(d);
+    if (tid == 0) dg[j] = sqrt(d);
+    for (int i = j + 1 + tid; i < n; i += 256) A[j * n + i] = A[i * n + j] * inv_s;  // L_ij at [j][i]
+    for (int i = j + 1 + ty; i < n; i += 16) {
+      const double aij = A[i * n + j] * inv_d;
+      for (int k = j + 1 + tx; k <= i; k += 16) A[i * n + k] -= aij * A[k * n + j];
+    }
+    __syncthreads();
+  }
+  if (tid < 32) {  // L y = b ; L^T x = y   (L_ik = A[k][i] for k < i)
+    for (int i = 0; i < n; i++) {
+      double sacc = 0;
+      for (int k = tid; k < i; k += 32) sacc += A[k * n + i] * b[k];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
+      if (tid == 0) b[i] = (b[i] - sacc) / dg[i];
+      __syncwarp();
+    }
+    for (int i = n - 1; i >= 0; i--) {
+      double sacc = 0;
+      for (int k = i + 1 + tid; k < n; k += 32) sacc += A[i * n + k] * b[k];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
+      if (tid == 0) b[i] = (b[i] - sacc) / dg[i];
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  // candidate cameras + rotation blocks
+  const int cur = st->cur;
+  double step2 = 0, xc2 = 0;
+  for (int i = tid; i < n; i += blockDim.x) {
+    p.rhs[i] = b[i];
+    const double dlt = -b[i] * p.scale_c[i];
+    const double x = p.cams[cur][i] + dlt;
+    p.cams[cur ^ 1][i] = x;
+    step2 += dlt * dlt;
+    xc2 += x * x;
+  }
+  const double s2 = block_sum(step2, red);
+  const double x2 = block_sum(xc2, red);
+  if (tid == 0) {
+    p.tail[3] = s2;
+    p.tail[4] = x2;
+    st->solve_ok = s_ok;
+  }
+  __syncthreads();
+  for (int c = tid; c < p.C; c += blockDim.x)
+    cam_rotation(p.cams[cur ^ 1] + 6 * c, p.camrot[cur ^ 1] + CAMROT * c, true);
 }
 
 // Large systems: right-looking blocked Cholesky in global memory, NB = 32.
@@ -634,7 +765,28 @@ __global__ void ba_candcam_kernel(const BADev* __restrict__ probs) {
 }
 
 // Back-substitution, model decrease, candidate points and candidate cost.
-__global__ void __launch_bounds__(BA_THREADS) ba_backsub_kernel(const BADev* __restrict__ probs) {
+__device__ __forceinline__ void lm_control(const BADev& p, const lorb_ba_options& opt, int* n_active) {
+  // volatile copy: accumulators were written by other CTAs through L2 atomics
+  LMState loc;
+  {
+    const volatile long long* src = reinterpret_cast<const volatile long long*>(p.st);
+    long long* dst = reinterpret_cast<long long*>(&loc);
+    for (int i = 0; i < (int)(sizeof(LMState) / 8); i++) dst[i] = src[i];
+  }
+  const volatile double* tail = p.tail;
+  loc.acc_step2 += tail[3];
+  loc.acc_xcand2 += tail[4];
+  const int acc = lm_decide(&loc, opt);
+  if (acc) loc.cur ^= 1;
+  lm_zero_acc(&loc);
+  loc.blocks_done = 0;
+  if (!loc.done) atomicAdd(n_active, 1);
+  *p.st = loc;
+}
+
+__global__ void __launch_bounds__(BA_THREADS)
+    ba_backsub_kernel(const BADev* __restrict__ probs, lorb_ba_options opt, int fuse_control,
+                      int* __restrict__ n_active) {
   const BADev p = probs[blockIdx.y];
   LMState* st = p.st;
   if (st->done) return;
@@ -748,18 +900,21 @@ __global__ void __launch_bounds__(BA_THREADS) ba_backsub_kernel(const BADev* __r
   if (tid == 0 && t != 0.0) atomicAdd(&st->acc_step2, t);
   t = block_sum(xn_acc, red);
   if (tid == 0 && t != 0.0) atomicAdd(&st->acc_xcand2, t);
+  if (fuse_control && tid == 0) {
+    __threadfence();
+    const int prev = atomicAdd(&st->blocks_done, 1);
+    if (prev == (int)gridDim.x - 1) {
+      __threadfence();
+      lm_control(p, opt, n_active);
+    }
+  }
 }
 
 __global__ void ba_control_kernel(const BADev* __restrict__ probs, lorb_ba_options opt, int* __restrict__ n_active) {
   const BADev p = probs[blockIdx.x];
   LMState* st = p.st;
   if (st->done) return;
-  st->acc_step2 += p.tail[3];
-  st->acc_xcand2 += p.tail[4];
-  const int acc = lm_decide(st, opt);
-  if (acc) st->cur ^= 1;
-  lm_zero_acc(st);
-  if (!st->done) atomicAdd(n_active, 1);
+  lm_control(p, opt, n_active);
 }
 
 }  // namespace lorb
@@ -1031,13 +1186,39 @@ static int problem_solve(lorb_ba_problem* pb, const lorb_ba_options* optp, int s
   cudaStream_t s = c->stream;
   int* d_active = pb->counter.as<int>();
   int* h_active = reinterpret_cast<int*>(pb->hstate.as<uint8_t>() + sizeof(LMState) * (size_t)nw);
+  // small windows: shared-memory privatised accumulation + one fused solve kernel
+  const bool small = nmax <= 96;
+  const size_t smem_lin = small ? ((size_t)nmax * nmax + (size_t)(HCC + 12) * pb->maxC) * 8 : 0;
+  const size_t smem_solve = ((size_t)nmax * nmax + 2 * (size_t)nmax) * 8;
+  if (small) {
+    LORB_CUDA_TRY(cudaFuncSetAttribute(ba_build_kernel<true, true>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_lin));
+    LORB_CUDA_TRY(cudaFuncSetAttribute(ba_build_kernel<false, true>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_lin));
+    LORB_CUDA_TRY(cudaFuncSetAttribute(ba_solve_small_kernel,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_solve));
+  }
+  auto launch_build = [&](bool full, int force) -> int {
+    if (small) {
+      if (full)
+        LORB_LAUNCH(c, (ba_build_kernel<true, true>), grid_pts, BA_THREADS, smem_lin, dp, opt, force);
+      else
+        LORB_LAUNCH(c, (ba_build_kernel<false, true>), grid_pts, BA_THREADS, smem_lin, dp, opt, force);
+    } else {
+      if (full)
+        LORB_LAUNCH(c, (ba_build_kernel<true, false>), grid_pts, BA_THREADS, 0, dp, opt, force);
+      else
+        LORB_LAUNCH(c, (ba_build_kernel<false, false>), grid_pts, BA_THREADS, 0, dp, opt, force);
+    }
+    return LORB_OK;
+  };
   // ---- initial evaluation (iteration 0)
   LORB_CUDA_TRY(cudaMemsetAsync(pb->d_states, 0, sizeof(LMState) * (size_t)nw, s));
   LORB_CUDA_TRY(cudaMemsetAsync(pb->lin_base, 0, pb->lin_bytes_total, s));
   LORB_LAUNCH(c, fill_ones_kernel, 128, 256, 0, d0.scale_c, pb->cam_doubles);
   LORB_LAUNCH(c, fill_ones_kernel, 512, 256, 0, d0.scale_p, pb->pt_doubles);
   LORB_LAUNCH(c, ba_camrot_kernel, grid_cam, 128, 0, dp, 0, 1);
-  LORB_LAUNCH(c, ba_build_kernel<false>, grid_pts, BA_THREADS, 0, dp, opt, 1);
+  LORB_TRY(launch_build(false, 1));
   if (sharded) {
     LORB_TRY(dist_allreduce_sum(c, d0.Hcc, (size_t)HCC * d0.C + 12 * (size_t)d0.C + 8));
     LORB_TRY(dist_allreduce_max_u64(c, &d0.st->acc_gmax, 1));
@@ -1045,21 +1226,28 @@ static int problem_solve(lorb_ba_problem* pb, const lorb_ba_options* optp, int s
   LORB_LAUNCH(c, ba_init_finish_kernel, dim3(1, nw), 1024, 0, dp, opt);
   // ---- LM attempts; the device decides, the host polls a counter every few attempts
   const int poll_every = 4;
+  const int fuse_control = sharded ? 0 : 1;
   for (int it = 0; it < opt.max_num_iterations; it++) {
     LORB_CUDA_TRY(cudaMemsetAsync(pb->lin_base, 0, pb->lin_bytes_total, s));
     LORB_CUDA_TRY(cudaMemsetAsync(d_active, 0, 4, s));
-    LORB_LAUNCH(c, ba_build_kernel<true>, grid_pts, BA_THREADS, 0, dp, opt, 0);
+    LORB_TRY(launch_build(true, 0));
     if (sharded) {
       LORB_TRY(dist_allreduce_sum(c, d0.lin, pb->lin_doubles_max));
       LORB_TRY(dist_allreduce_max_u64(c, &d0.st->acc_gmax, 1));
     }
-    LORB_LAUNCH(c, ba_gradcheck_kernel, dim3(1, nw), 256, 0, dp, opt, 0);
-    LORB_LAUNCH(c, ba_finish_kernel, grid_fin, 256, 0, dp, opt);
-    LORB_TRY(run_cholesky(pb));
-    LORB_LAUNCH(c, ba_candcam_kernel, grid_cam, 128, 0, dp);
-    LORB_LAUNCH(c, ba_backsub_kernel, grid_pts, BA_THREADS, 0, dp);
-    if (sharded) LORB_TRY(dist_allreduce_sum(c, &d0.st->acc_cost2, 4));
-    LORB_LAUNCH(c, ba_control_kernel, nw, 1, 0, dp, opt, d_active);
+    if (small) {
+      LORB_LAUNCH(c, ba_solve_small_kernel, dim3(1, nw), 256, smem_solve, dp, opt);
+    } else {
+      LORB_LAUNCH(c, ba_gradcheck_kernel, dim3(1, nw), 256, 0, dp, opt, 0);
+      LORB_LAUNCH(c, ba_finish_kernel, grid_fin, 256, 0, dp, opt);
+      LORB_TRY(run_cholesky(pb));
+      LORB_LAUNCH(c, ba_candcam_kernel, grid_cam, 128, 0, dp);
+    }
+    LORB_LAUNCH(c, ba_backsub_kernel, grid_pts, BA_THREADS, 0, dp, opt, fuse_control, d_active);
+    if (sharded) {
+      LORB_TRY(dist_allreduce_sum(c, &d0.st->acc_cost2, 4));
+      LORB_LAUNCH(c, ba_control_kernel, nw, 1, 0, dp, opt, d_active);
+    }
     if ((it + 1) % poll_every == 0 && it + 1 < opt.max_num_iterations) {
       LORB_CUDA_TRY(cudaMemcpyAsync(h_active, d_active, 4, cudaMemcpyDeviceToHost, s));
       LORB_CUDA_TRY(cudaStreamSynchronize(s));
@@ -1076,7 +1264,7 @@ static int problem_solve(lorb_ba_problem* pb, const lorb_ba_options* optp, int s
   if (pending) {
     LORB_CUDA_TRY(cudaMemsetAsync(pb->lin_base, 0, pb->lin_bytes_total, s));
     LORB_LAUNCH(c, ba_camrot_kernel, grid_cam, 128, 0, dp, 0, 2);
-    LORB_LAUNCH(c, ba_build_kernel<false>, grid_pts, BA_THREADS, 0, dp, opt, 2);
+    LORB_TRY(launch_build(false, 2));
     if (sharded) {
       LORB_TRY(dist_allreduce_sum(c, d0.Hcc, (size_t)HCC * d0.C + 12 * (size_t)d0.C + 8));
       LORB_TRY(dist_allreduce_max_u64(c, &d0.st->acc_gmax, 1));

@@ -196,6 +196,8 @@ struct LMState {
   int termination, done, solve_ok, cur;  // cur: which parameter buffer is current (0/1)
   int check_gradient;  // a step was just accepted: test gradient tolerance after the next build
   int pad;
+  int blocks_done;     // CTAs of this window that finished the back-substitution pass
+  int pad2;
 };
 
 __device__ __forceinline__ void lm_zero_acc(LMState* s) {

@@ -1,0 +1,239 @@
+// harness.cpp — test-only C entry points that build Frame / MapPoint objects
+// (shim versions here, the real ones in a LORB-SLAM checkout) from flat arrays,
+// call the drop-in Matcher / BA classes exactly as VisualOdometry / LocalMapping
+// do, and hand the mutated object state back as arrays.  tests/test_host_dropin_gpu.py
+// compares those with the oracle.
+#include <cstring>
+#include <deque>
+
+#include "../include/bundle_adjust.h"
+#include "../include/matcher.h"
+
+using namespace Simple_ORB_SLAM;
+
+namespace
+{
+cv::Mat DescMat(const uint8_t* d, int n)
+{
+	cv::Mat m(n, 32, CV_8U);
+	if(n) std::memcpy(m.ptr<uint8_t>(), d, (size_t)n*32);
+	return m;
+}
+
+void FillFrame(Frame& F, int n, const float* x, const float* y, const int* oct, const float* ang,
+               const float* ur, const uint8_t* desc, float minx, float maxx, float miny, float maxy,
+               int nlev, const float* sf)
+{
+	F.mnMapPoints = n;
+	F.mvpMapPoints.assign(n, static_cast<MapPoint*>(NULL));
+	F.mvKeysUn.resize(n);
+	for(int i=0;i<n;i++)
+	{
+		F.mvKeysUn[i].pt = cv::Point2f(x[i], y[i]);
+		F.mvKeysUn[i].octave = oct[i];
+		F.mvKeysUn[i].angle = ang[i];
+	}
+	F.mvKeys = F.mvKeysUn;
+	F.mvuRight.assign(ur, ur+n);
+	F.mvbOutlier.assign(n, false);
+	F.mDescriptors = DescMat(desc, n);
+	F.mnMinX = minx; F.mnMaxX = maxx; F.mnMinY = miny; F.mnMaxY = maxy;
+	F.mvScaleFactors.assign(sf, sf+nlev);
+	F.mnScaleLevels = nlev;
+}
+}
+
+extern "C" {
+
+// Matcher::SearchByProjection(curr, prev) [which=0] / Matcher::SearchLocalPoints [which=1]
+// prev_has[j] == 0 leaves a NULL slot in prev->mvpMapPoints.  out_assign[i] = index j of the
+// map point now held by curr keypoint i, -1 if none.
+int harness_bf(int which, int nq, const uint8_t* qdesc, int nt, const uint8_t* tdesc,
+               const uint8_t* prev_has, int* out_assign)
+{
+	Frame curr, prev;
+	std::vector<float> z(nq, 0.f);
+	std::vector<int> zi(nq, 0);
+	float sf = 1.f;
+	FillFrame(curr, nq, z.data(), z.data(), zi.data(), z.data(), z.data(), qdesc, 0, 640, 0, 480, 1, &sf);
+	std::vector<MapPoint> mps(nt);  // contiguous: pointer order == index order (std::set iteration)
+	prev.mnMapPoints = nt;
+	prev.mvpMapPoints.assign(nt, static_cast<MapPoint*>(NULL));
+	std::set<MapPoint*> local;
+	for(int j=0;j<nt;j++)
+	{
+		mps[j].mDescriptor = DescMat(tdesc + (size_t)j*32, 1);
+		if(prev_has[j]) { prev.mvpMapPoints[j] = &mps[j]; local.insert(&mps[j]); }
+	}
+	const size_t n = which == 0 ? Matcher::SearchByProjection(&curr, &prev)
+	                            : Matcher::SearchLocalPoints(&curr, local);
+	for(int i=0;i<nq;i++)
+		out_assign[i] = curr.mvpMapPoints[i] ? (int)(curr.mvpMapPoints[i] - &mps[0]) : -1;
+	return (int)n;
+}
+
+// Matcher::SearchByProjection(F, set<MapPoint*>, th)
+int harness_proj_points(int n_kp, const float* x, const float* y, const int* oct, const float* ang,
+                        const float* ur, const uint8_t* desc, const int* claim_obs, float minx,
+                        float maxx, float miny, float maxy, int nlev, const float* sf, int n_pts,
+                        const float* px, const float* py, const float* pxr, const int* level,
+                        const float* vcos, const uint8_t* active, const uint8_t* mpdesc,
+                        const int* nobs, float th, int* out_assign)
+{
+	Frame F;
+	FillFrame(F, n_kp, x, y, oct, ang, ur, desc, minx, maxx, miny, maxy, nlev, sf);
+	std::deque<MapPoint> holders;  // pre-existing claims
+	for(int i=0;i<n_kp;i++)
+		if(claim_obs[i] >= 0)
+		{
+			holders.emplace_back();
+			holders.back().mnObs = (size_t)claim_obs[i];
+			F.mvpMapPoints[i] = &holders.back();
+		}
+	std::vector<MapPoint> mps(n_pts);
+	std::set<MapPoint*> local;
+	for(int k=0;k<n_pts;k++)
+	{
+		MapPoint& m = mps[k];
+		m.mDescriptor = DescMat(mpdesc + (size_t)k*32, 1);
+		m.mnObs = (size_t)nobs[k];
+		m.mbTrackInView = active[k] != 0;
+		m.mTrackProjX = px[k]; m.mTrackProjY = py[k]; m.mTrackProjXR = pxr[k];
+		m.mnTrackScaleLevel = level[k]; m.mTrackViewCos = vcos[k];
+		local.insert(&m);
+	}
+	const size_t n = Matcher::SearchByProjection(&F, local, th);
+	for(int i=0;i<n_kp;i++)
+	{
+		MapPoint* h = F.mvpMapPoints[i];
+		out_assign[i] = (h && n_pts && h >= &mps[0] && h <= &mps[n_pts-1]) ? (int)(h - &mps[0]) : -1;
+	}
+	return (int)n;
+}
+
+// Matcher::SearchByProjection(Cur, Last, th).  out_state: >=0 last item held, -2 NULL (was
+// touched and cleared or never held), -1 still holding its pre-existing claim.
+int harness_proj_frame(int n_kp, const float* x, const float* y, const int* oct, const float* ang,
+                       const float* ur, const uint8_t* desc, const int* claim_obs, float minx,
+                       float maxx, float miny, float maxy, int nlev, const float* sf,
+                       const float* tcw_cur, const float* tcw_last, const float* K6, int n_last,
+                       const uint8_t* valid, const float* xw, const int* loct, const float* lang,
+                       const uint8_t* mpdesc, const int* nobs, float th, int* out_state)
+{
+	Frame Cur, Last;
+	FillFrame(Cur, n_kp, x, y, oct, ang, ur, desc, minx, maxx, miny, maxy, nlev, sf);
+	Cur.fx = K6[0]; Cur.fy = K6[1]; Cur.cx = K6[2]; Cur.cy = K6[3]; Cur.mbf = K6[4]; Cur.mb = K6[5];
+	for(int r=0;r<4;r++) for(int c=0;c<4;c++)
+	{
+		Cur.mTcw.at<float>(r,c) = tcw_cur[4*r+c];
+		Last.mTcw.at<float>(r,c) = tcw_last[4*r+c];
+	}
+	std::deque<MapPoint> holders;
+	for(int i=0;i<n_kp;i++)
+		if(claim_obs[i] >= 0)
+		{
+			holders.emplace_back();
+			holders.back().mnObs = (size_t)claim_obs[i];
+			Cur.mvpMapPoints[i] = &holders.back();
+		}
+	std::vector<MapPoint> mps(n_last);
+	Last.mnMapPoints = n_last;
+	Last.mvpMapPoints.assign(n_last, static_cast<MapPoint*>(NULL));
+	Last.mvbOutlier.assign(n_last, false);
+	Last.mvKeys.resize(n_last);
+	Last.mvKeysUn.resize(n_last);
+	for(int i=0;i<n_last;i++)
+	{
+		Last.mvKeys[i].octave = loct[i];
+		Last.mvKeysUn[i].octave = loct[i];
+		Last.mvKeysUn[i].angle = lang[i];
+		if(valid[i])
+		{
+			mps[i].mWorldPos = cv::Point3f(xw[3*i], xw[3*i+1], xw[3*i+2]);
+			mps[i].mDescriptor = DescMat(mpdesc + (size_t)i*32, 1);
+			mps[i].mnObs = (size_t)nobs[i];
+			Last.mvpMapPoints[i] = &mps[i];
+		}
+	}
+	const size_t n = Matcher::SearchByProjection(&Cur, &Last, th);
+	for(int i=0;i<n_kp;i++)
+	{
+		MapPoint* h = Cur.mvpMapPoints[i];
+		if(h == NULL) out_state[i] = -2;
+		else if(n_last && h >= &mps[0] && h <= &mps[n_last-1]) out_state[i] = (int)(h - &mps[0]);
+		else out_state[i] = -1;
+	}
+	return (int)n;
+}
+
+// BA::ProjectPoseOptimization: rt (float[6]: R then T) in/out
+void harness_pose_opt(int n, const float* xw, const float* uv, const float* K4, float* rt)
+{
+	Camera cam;
+	cam.fx = K4[0]; cam.fy = K4[1]; cam.cx = K4[2]; cam.cy = K4[3];
+	Frame F;
+	F.mpCamera = &cam;
+	F.mnMapPoints = n;
+	F.mvKeysUn.resize(n);
+	std::vector<MapPoint> mps(n);
+	F.mvpMapPoints.assign(n, static_cast<MapPoint*>(NULL));
+	for(int i=0;i<n;i++)
+	{
+		F.mvKeysUn[i].pt = cv::Point2f(uv[2*i], uv[2*i+1]);
+		mps[i].mWorldPos = cv::Point3f(xw[3*i], xw[3*i+1], xw[3*i+2]);
+		F.mvpMapPoints[i] = &mps[i];
+	}
+	for(int k=0;k<3;k++) { F.mRvec.at<float>(k) = rt[k]; F.mTvec.at<float>(k) = rt[3+k]; }
+	BA::ProjectPoseOptimization(&F);
+	for(int k=0;k<3;k++) { rt[k] = F.mRvec.at<float>(k); rt[3+k] = F.mTvec.at<float>(k); }
+}
+
+// BA::LocalPoseOptimization on a window of C frames (frame 0 = current, the rest covisible)
+// plus n_fix out-of-window observers.  cams / fix_rt are float (R then T); points float.
+void harness_local_ba(int C, float* cams, int P, float* pts, int O, const int* obs_cam,
+                      const int* obs_pt, const float* obs_uv, int n_fix, const int* fix_pt,
+                      const float* fix_uv, const float* fix_rt, const float* K4)
+{
+	Camera cam;
+	cam.fx = K4[0]; cam.fy = K4[1]; cam.cx = K4[2]; cam.cy = K4[3];
+	// frames live in one array so that std::map<Frame*,...> iterates window frames by index and
+	// the fixed observers (allocated after them) last — the order the flat arrays are given in
+	std::vector<Frame> frames(C + n_fix);
+	std::vector<MapPoint> mps(P);
+	for(int p=0;p<P;p++) mps[p].mWorldPos = cv::Point3f(pts[3*p], pts[3*p+1], pts[3*p+2]);
+	for(int c=0;c<C+n_fix;c++)
+	{
+		Frame& F = frames[c];
+		F.mpCamera = &cam;
+		const float* rt = c < C ? cams + 6*c : fix_rt + 6*(c-C);
+		cv::Mat R(3,1,CV_32F), T(3,1,CV_32F);
+		for(int k=0;k<3;k++) { R.at<float>(k) = rt[k]; T.at<float>(k) = rt[3+k]; }
+		F.SetPose(T, R);
+	}
+	auto add_obs = [&](Frame& F, int p, float u, float v)
+	{
+		cv::KeyPoint kp;
+		kp.pt = cv::Point2f(u, v);
+		F.mvKeysUn.push_back(kp);
+		F.mvpMapPoints.push_back(&mps[p]);
+		F.mnMapPoints = F.mvKeysUn.size();
+		mps[p].AddObservation(&F, F.mvKeysUn.size()-1);
+	};
+	for(int i=0;i<O;i++) add_obs(frames[obs_cam[i]], obs_pt[i], obs_uv[2*i], obs_uv[2*i+1]);
+	for(int i=0;i<n_fix;i++) add_obs(frames[C+i], fix_pt[i], fix_uv[2*i], fix_uv[2*i+1]);
+	for(int c=1;c<C;c++) frames[0].mvpOrderedKeyFrames.push_back(&frames[c]);
+	BA::LocalPoseOptimization(&frames[0]);
+	for(int c=0;c<C;c++)
+		for(int k=0;k<3;k++)
+		{
+			cams[6*c+k] = frames[c].mRvec.at<float>(k);
+			cams[6*c+3+k] = frames[c].mTvec.at<float>(k);
+		}
+	for(int p=0;p<P;p++)
+	{
+		const cv::Point3f q = mps[p].GetPos();
+		pts[3*p] = q.x; pts[3*p+1] = q.y; pts[3*p+2] = q.z;
+	}
+}
+
+}

@@ -53,3 +53,26 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(capi.BAOptions) == 16 + 9 * 8
     assert ctypes.sizeof(capi.BASummary) == 4 * 8 + 4 * 4
     assert ctypes.sizeof(capi.Intrinsics) == 24
+
+
+def test_cpp_dropin_layer_compiles_with_reference_interfaces():
+    """The drop-in Matcher / BA sources compile (against the shim headers here)
+    and export the reference's member functions with the reference's signatures."""
+    import subprocess
+    from lorb_slam_b200.host import build_host
+    so = build_host.build()
+    syms = subprocess.run(["nm", "-DC", so], capture_output=True, text=True).stdout
+    for want in [
+        "Simple_ORB_SLAM::Matcher::SearchByProjection(Simple_ORB_SLAM::Frame*, Simple_ORB_SLAM::Frame*)",
+        "Simple_ORB_SLAM::Matcher::SearchByProjection(Simple_ORB_SLAM::Frame*, Simple_ORB_SLAM::Frame*, float)",
+        "Simple_ORB_SLAM::Matcher::SearchLocalPoints(Simple_ORB_SLAM::Frame*, std::set<",
+        "Simple_ORB_SLAM::Matcher::SearchByProjection(Simple_ORB_SLAM::Frame*, std::set<",
+        "Simple_ORB_SLAM::Matcher::DescriptorDistance(cv::Mat const&, cv::Mat const&)",
+        "Simple_ORB_SLAM::Matcher::RadiusByViewingCos(float const&)",
+        "Simple_ORB_SLAM::Matcher::ComputeThreeMaxima(std::vector<int",
+        "Simple_ORB_SLAM::Matcher::TH_HIGH", "Simple_ORB_SLAM::Matcher::TH_LOW",
+        "Simple_ORB_SLAM::Matcher::HISTO_LENGTH",
+        "Simple_ORB_SLAM::BA::ProjectPoseOptimization(Simple_ORB_SLAM::Frame*)",
+        "Simple_ORB_SLAM::BA::LocalPoseOptimization(Simple_ORB_SLAM::Frame*)",
+    ]:
+        assert want in syms, want

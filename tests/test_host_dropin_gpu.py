@@ -1,0 +1,100 @@
+"""GPU: the C++ drop-in classes (Matcher / BA with the reference's interfaces,
+lorb_slam_b200/host) driven through real Frame / MapPoint objects, compared
+with the oracle.  This is the path a LORB-SLAM caller takes:
+VisualOdometry -> Matcher::* / BA::* -> C ABI -> sm_100a kernels."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from lorb_slam_b200 import synth
+from lorb_slam_b200.host import build_host
+from oracle import ref
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def H():
+    return C.CDLL(build_host.build())
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _frame_args(fr):
+    return [fr["n_kp"], _p(fr["kp_x"]), _p(fr["kp_y"]), _p(fr["kp_octave"]), _p(fr["kp_angle"]),
+            _p(fr["kp_uright"]), _p(fr["desc"]), _p(fr["kp_claim_obs"]), C.c_float(fr["min_x"]),
+            C.c_float(fr["max_x"]), C.c_float(fr["min_y"]), C.c_float(fr["max_y"]), fr["n_levels"],
+            _p(fr["scale_factors"])]
+
+
+@pytest.mark.parametrize("which", [0, 1])
+def test_bruteforce_entry_points(H, which):
+    rng = np.random.default_rng(which)
+    q = synth.descriptors_uniform(700, rng)
+    t = synth.descriptors_uniform(900, rng)
+    t[:400] = synth.descriptors_noisy_copy(q[rng.permutation(700)[:400]], rng, 0.05)
+    has = (rng.random(900) < 0.8).astype(np.uint8)
+    out = np.full(700, -1, np.int32)
+    n = H.harness_bf(which, 700, _p(q), 900, _p(t), _p(has), _p(out))
+    idx = np.flatnonzero(has)
+    o = ref.bf_crosscheck(q, t[idx])
+    exp = np.full(700, -1, np.int32)
+    k = o["keep"].astype(bool)
+    exp[o["q"][k]] = idx[o["t"][k]]
+    assert n == o["n_kept"] > 100
+    assert np.array_equal(out, exp)
+
+
+@pytest.mark.parametrize("th,nobs", [(1.0, 1), (1.0, 0), (15.0, (0, 1, 2))])
+def test_search_by_projection_points(H, th, nobs):
+    fr = synth.make_frame(2000, seed=3, stereo=True, claimed_frac=0.1)
+    pts = synth.make_proj_points(fr, 5000, seed=3, nobs=nobs, inactive_frac=0.05)
+    out = np.full(2000, -1, np.int32)
+    n = H.harness_proj_points(*_frame_args(fr), 5000, _p(pts["proj_x"]), _p(pts["proj_y"]),
+                              _p(pts["proj_xr"]), _p(pts["level"]), _p(pts["view_cos"]),
+                              _p(pts["active"]), _p(pts["mp_desc"]), _p(pts["mp_nobs"]),
+                              C.c_float(th), _p(out))
+    o = ref.search_proj_points(fr, pts, th)
+    assert n == o["n_matches"] > 100
+    assert np.array_equal(out, o["point_for_kp"])
+
+
+@pytest.mark.parametrize("motion", ["forward", "still"])
+def test_search_by_projection_frame(H, motion):
+    cur, last = synth.make_frame_pair(2000, seed=2, motion=motion)
+    K = last["K"]
+    K6 = np.array([K["fx"], K["fy"], K["cx"], K["cy"], K["mbf"], K["mb"]], np.float32)
+    out = np.full(2000, -1, np.int32)
+    n = H.harness_proj_frame(*_frame_args(cur), _p(last["tcw_cur"]), _p(last["tcw_last"]), _p(K6),
+                             2000, _p(last["valid"]), _p(last["xw"]), _p(last["octave"]),
+                             _p(last["angle"]), _p(last["mp_desc"]), _p(last["mp_nobs"]),
+                             C.c_float(15.0), _p(out))
+    o = ref.search_proj_frame(cur, last, 15.0)
+    assert n == o["n_matches"] > 200
+    exp = o["state_for_kp"].copy()
+    exp[exp == -1] = -2  # the frame had no earlier claims: untouched keypoints hold NULL
+    assert np.array_equal(out, exp)
+
+
+def test_project_pose_optimization(H):
+    po = synth.make_pose_only(1, 600)
+    rt = po["rt"].astype(np.float32)
+    H.harness_pose_opt(600, _p(po["xw"]), _p(po["uv"]), _p(po["K"]), _p(rt))
+    ort, _ = ref.ba_pose_only(po["xw"], po["uv"], po["K"], po["rt"])
+    np.testing.assert_allclose(rt, ort.astype(np.float32), rtol=2e-6, atol=1e-7)
+
+
+def test_local_pose_optimization(H):
+    pb = synth.make_ba_problem(5, C=6, P=400, obs_per_point=(4, 5), fixed_frac=0.1)
+    cams = pb["cams"].astype(np.float32)
+    pts = pb["pts"].astype(np.float32)
+    H.harness_local_ba(6, _p(cams), 400, _p(pts), pb["O"], _p(pb["obs_cam"]), _p(pb["obs_pt"]),
+                       _p(pb["obs_uv"]), pb["F"], _p(pb["fix_pt"]), _p(pb["fix_uv"]),
+                       _p(pb["fix_rt"]), _p(pb["K"]))
+    oc, op, s = ref.ba_local(pb)
+    assert s["final_cost"] < s["initial_cost"]
+    np.testing.assert_allclose(cams, oc.astype(np.float32), rtol=3e-6, atol=1e-6)
+    np.testing.assert_allclose(pts, op.astype(np.float32), rtol=3e-6, atol=1e-6)
