@@ -275,7 +275,9 @@ def run_sweep(args, rank, world, local):
                     "d2h_bytes_per_step": int(3 * 4 * n_pairs)},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "int-pipe (LOP3/POPC issue; operands live in smem/registers)",
+            "roofline": {"bound": "alu",
+                         "bound_detail": "integer pipes (LOP3 on ALU 86%, POPC on XU 74% per ncu); "
+                                         "operands live in shared memory / registers",
                          "achieved": achieved / 1e9, "peak": peak_words / 1e9,
                          "unit": "G 32-bit words/s (1 descriptor pair = 8 words)",
                          "frac": achieved / peak_words,
@@ -283,7 +285,9 @@ def run_sweep(args, rank, world, local):
                                         "carry-save distance body on register operands, whole GPU",
                          "peak_plain_popc8": peak_words_popc8 / 1e9,
                          "frac_of_plain_popc8": achieved / peak_words_popc8,
-                         "traffic": None},
+                         "traffic": 8295424,
+                         "traffic_source": "dram__bytes_read+write per launch, ncu --set full, "
+                                           "profiles/r01_sweep_kernel_ncu_full.csv"},
             "roofline_hbm": {"bound": "hbm", "achieved": alg_bytes / (kernel_ms * 1e-3) / 1e9,
                              "peak": hbm_peak, "unit": "GB/s",
                              "frac": alg_bytes / (kernel_ms * 1e-3) / 1e9 / hbm_peak,
@@ -402,14 +406,90 @@ def run_ba_batched(args, rank, world, local):
     return res, None
 
 
+def run_ba_large(args, rank, world, local):
+    """BASELINE config 5 BA: 200 keyframes / 200k points / 1.5M observations,
+    points sharded over the ranks, reduced camera system all-reduced over NCCL
+    every LM attempt.  Strong scaling (the problem is fixed)."""
+    import torch
+    import torch.distributed as dist
+    from lorb_slam_b200 import capi, sharding, synth
+    ctx = capi.Context(local)
+    if world > 1:
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid = torch.tensor(list(capi.Context.dist_unique_id()), dtype=torch.uint8, device="cuda")
+        dist.broadcast(uid, 0)
+        ctx.dist_init(bytes(uid.cpu().tolist()), rank, world)
+    pb = synth.make_ba_problem(0, C=args.large_cams, P=args.large_points, obs_per_point=(7, 8),
+                               traj_len=100.0 * args.large_cams / 200.0)
+    sh = sharding.shard_ba_by_point(pb, rank, world)
+    opt = _ba_opts_fixed_iters(capi)
+    prob = ctx.ba_problem(sh)
+    for _ in range(args.warmup):
+        prob.reset()
+        prob.solve(opt, sharded=world > 1)
+    _barrier(world)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = ctx.launch_count
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        prob.reset()
+        s = prob.solve(opt, sharded=world > 1)
+    ctx.sync()
+    dt = time.perf_counter() - t0
+    launches = ctx.launch_count - l0
+    clocks = sampler.stop() if rank == 0 else None
+    dt_max = _max_over_ranks(dt, world, local)
+    prob.close()
+    # e2e: create (upload) + solve + download every step
+    _barrier(world)
+    t0 = time.perf_counter()
+    for _ in range(max(1, args.steps // 2)):
+        p2 = ctx.ba_problem(sh)
+        p2.solve(opt, sharded=world > 1)
+        p2.download()
+        p2.close()
+    e2e = _max_over_ranks((time.perf_counter() - t0) / max(1, args.steps // 2), world, local)
+    O = pb["O"]
+    value = args.steps * O * s["iterations"] / dt_max
+    res = None
+    if rank == 0:
+        res = {"metric": "BA observations/s per LM iter", "value": value,
+               "unit": "observations*iterations/s", "n_gpus": world, "steps": args.steps,
+               "warmup": args.warmup, "ms_per_step": dt_max / args.steps * 1e3,
+               "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+               "data": "synthetic (SURVEY 8(d) cfg 5 generator, seed 0)",
+               "config": {"workload": "large BA: %d keyframes / %d points / %d observations, 10 LM "
+                                      "attempts, points sharded over ranks, NCCL all-reduce of the "
+                                      "%dx%d reduced camera system per attempt"
+                                      % (args.large_cams, args.large_points, O, 6 * args.large_cams,
+                                         6 * args.large_cams),
+                          "l2": "observations + points (%.0f MB) streamed per pass" % (O * 12 / 1e6)},
+               "e2e": {"value": O * s["iterations"] / e2e, "unit": "observations*iterations/s",
+                       "h2d_bytes_per_step": int(sh["obs_uv"].nbytes + 2 * sh["obs_cam"].nbytes +
+                                                 sh["pts"].nbytes + sh["cams"].nbytes),
+                       "d2h_bytes_per_step": int(sh["pts"].nbytes + sh["cams"].nbytes)},
+               "gpu_launches": int(launches), "clocks": clocks,
+               "ms_per_lm_iteration": dt_max / args.steps / s["iterations"] * 1e3,
+               "lm_iterations": s["iterations"], "final_cost": s["final_cost"]}
+    if world > 1:
+        ctx.dist_finalize()
+    ctx.close()
+    return res, None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="lorb", choices=["lorb", "reference"])
-    ap.add_argument("--workload", default="sweep", choices=["sweep", "ba_batched"])
+    ap.add_argument("--workload", default="sweep", choices=["sweep", "ba_batched", "ba_large"])
     ap.add_argument("--windows", type=int, default=64)
+    ap.add_argument("--large-cams", type=int, default=200)
+    ap.add_argument("--large-points", type=int, default=200000)
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -421,6 +501,8 @@ def main():
     rank, world, local = _dist_setup(args.gpus)
     if args.workload == "ba_batched":
         res, bank = run_ba_batched(args, rank, world, local)
+    elif args.workload == "ba_large":
+        res, bank = run_ba_large(args, rank, world, local)
     else:
         res, bank = run_sweep(args, rank, world, local)
     if rank == 0:

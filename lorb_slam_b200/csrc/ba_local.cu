@@ -18,6 +18,8 @@
 //                -> back-substitution + model decrease + candidate cost
 //                -> [allreduce] -> control (accept / reject, radius update).
 // The trust-region state lives on the device; the host only enqueues.
+#include <stdlib.h>
+
 #include <algorithm>
 #include <new>
 #include <vector>
@@ -49,9 +51,17 @@ struct BADev {
   double* rhs_corr;
   double* tail;          // acc_cur2, acc_xcur2, bad, spare
   double* rhs;           // n (becomes y_c after the solve)
+  double* dinv;          // 1/L_jj of the Cholesky factor, padded to ceil(n/32)*32 (blocked path)
   double* pt_hinv;       // P x 6
   double* pt_gp;         // P x 3
   LMState* st;
+  // large path only: camera-major / block-pair-major work lists (host built)
+  const int* obs_pt;      // point of each observation (point-sorted observation order)
+  const int* cam_obs;     // observations grouped by camera
+  const int4* cam_items;  // (camera, start in cam_obs, length, 0)
+  const int2* pairs;      // (observation i, observation j) grouped by camera block
+  const int4* pair_items; // (ci, cj, start in pairs, length)
+  int n_cam_items, n_pair_items;
 };
 
 __device__ __forceinline__ int upper_idx(int a, int b) {  // a <= b, 6x6
@@ -134,40 +144,70 @@ __device__ __forceinline__ double block_max(double v, double* red) {
 // Build pass.  Eight lanes per point, one observation per lane per round.
 // FULL = false: initial pass (scales are 1): cost, H_cc / g_c, point column
 // norms -> scale_p, |x|^2, gradient max.  FULL = true: one LM attempt.
-// SMALL = true: windows with few cameras (n = 6C <= 96).  All blocks of such a
-// window hit the same few hundred H_cc / S addresses, and same-address fp64
-// atomics serialise in L2 (profiles/ba_launches_r01.md), so every CTA first
-// accumulates into a private copy of `lin` in shared memory and flushes it once.
-template <bool FULL, bool SMALL>
+// Accumulation strategy of the build pass (template ACC):
+//   0  global fp64 atomics straight into `lin` (many cameras: addresses are spread)
+//   1  windows with n = 6C <= 96: every block of such a window hits the same few
+//      hundred H_cc / S addresses and same-address fp64 atomics serialise in L2
+//      (profiles/r01_ba_local_launches_before_opt.csv), so each CTA accumulates
+//      into a private copy of `lin` in shared memory and flushes it once
+//   3  many cameras (n > 96, BASELINE config 5): this kernel only does the
+//      point side (H_pp, g_p, damped inverse, cost); the camera side runs in
+//      ba_cam_rows_kernel and the Schur products in ba_schur_pairs_kernel, both
+//      segmented reductions in registers over host-built lists - no atomics in
+//      any inner loop
+//   2  n <= 64 (the 10-keyframe windows of BASELINE configs 3/4): H_cc / g_c / rhs
+//      as in 1, but the Schur products are a dense contraction per CTA:
+//      Y = W H_pp^-1 and W of 32 points are staged as dense 64 x 96 tiles in
+//      shared memory and S -= Y W^T is accumulated in registers (4x4 per thread),
+//      flushed once per CTA.  No per-block atomics at all in the inner loop.
+constexpr int DENSE_N = 64;   // padded reduced-system size of the dense path
+constexpr int DENSE_K = 96;   // 32 points x 3 per block round
+
+template <bool FULL, int ACC>
 __global__ void __launch_bounds__(BA_THREADS)
     ba_build_kernel(const BADev* __restrict__ probs, lorb_ba_options opt, int force) {
   const BADev p = probs[blockIdx.y];
   LMState* st = p.st;
   if (st->done && !force) return;
-  __shared__ double Wsm[BA_THREADS][18];
   __shared__ int Csm[BA_THREADS];
   __shared__ double red[BA_THREADS / 32];
-  extern __shared__ double slin[];  // SMALL: [S n*n | Hcc 21C | gc 6C | rhs_corr 6C]
+  extern __shared__ __align__(16) double dsm[];
+  // dynamic shared memory carve-up
+  //   ACC 0: [Wsm 256x18]   ACC 1: [lin copy][Wsm 256x18]   ACC 2: [Hcc|gc|rhs][Yd 96x64][Wd 96x64]
   const int lin_n = p.n * p.n + (HCC + 12) * p.C;
-  if (SMALL) {
-    for (int i = threadIdx.x; i < lin_n; i += BA_THREADS) slin[i] = 0.0;
-    __syncthreads();
+  const int small_n = (HCC + 12) * p.C;
+  double* slin = dsm;
+  double (*Wsm)[18] = reinterpret_cast<double (*)[18]>(ACC == 1 ? dsm + lin_n : dsm);
+  double* Yd = dsm + ((small_n + 1) & ~1);  // 16-byte aligned for the double2 tile loads
+  double* Wd = Yd + DENSE_K * DENSE_N;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, gl = lane & 7, gw = lane >> 3;
+  if (ACC == 1) {
+    for (int i = tid; i < lin_n; i += BA_THREADS) slin[i] = 0.0;
+  } else if (ACC == 2) {
+    for (int i = tid; i < ((small_n + 1) & ~1) + (FULL ? 2 * DENSE_K * DENSE_N : 0); i += BA_THREADS)
+      slin[i] = 0.0;
   }
-  double* const accS = SMALL ? slin : p.S;
-  double* const accH = SMALL ? slin + (size_t)p.n * p.n : p.Hcc;
-  double* const accG = SMALL ? slin + (size_t)p.n * p.n + HCC * p.C : p.gc;
-  double* const accR = SMALL ? slin + (size_t)p.n * p.n + (HCC + 6) * p.C : p.rhs_corr;
+  if (ACC != 0) __syncthreads();
+  double* const accS = ACC == 1 ? slin : p.S;
+  double* const accH = ACC == 1 ? slin + (size_t)p.n * p.n : (ACC == 2 ? slin : p.Hcc);
+  double* const accG = accH + HCC * p.C;
+  double* const accR = accG + 6 * p.C;
   const int cur = st->cur;
   const double* cams = p.cams[cur];
   const double* pts = p.pts[cur];
   const double* camrot = p.camrot[cur];
   const double radius = st->radius;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, gl = lane & 7, gw = lane >> 3;
   const int n = p.n;
   double cost_acc = 0, gmax_acc = 0, xn_acc = 0, bad_acc = 0;
-  for (int base = (blockIdx.x * (BA_THREADS / 32) + warp) * 4; base < p.P;
-       base += gridDim.x * (BA_THREADS / 8)) {
-    const int pt = base + gw;
+  double sacc[4][4];  // ACC 2: this thread's 4x4 tile of Y W^T
+#pragma unroll
+  for (int a = 0; a < 4; a++)
+#pragma unroll
+    for (int c = 0; c < 4; c++) sacc[a][c] = 0.0;
+  // block-uniform trip count (the dense path has block barriers inside)
+  for (int blk = blockIdx.x * (BA_THREADS / 8); blk < p.P; blk += gridDim.x * (BA_THREADS / 8)) {
+    const int pt = blk + warp * 4 + gw;
+    const int slot = warp * 4 + gw;
     const bool pv = pt < p.P;
     int s = 0, e = 0;
     double X[3] = {0, 0, 0}, sp[3] = {1, 1, 1};
@@ -200,13 +240,13 @@ __global__ void __launch_bounds__(BA_THREADS)
         h[5] += Jp[2] * Jp[2] + Jp[5] * Jp[5];
 #pragma unroll
         for (int a = 0; a < 3; a++) g[a] += Jp[a] * r[0] + Jp[3 + a] * r[1];
-        if (cam >= 0) {
+        if (ACC != 3 && cam >= 0) {
           double* H = accH + HCC * (size_t)cam;
           int k = 0;
 #pragma unroll
           for (int a = 0; a < 6; a++) {
 #pragma unroll
-            for (int b = a; b < 6; b++) atomicAdd(&H[k++], Jc[a] * Jc[b] + Jc[6 + a] * Jc[6 + b]);
+            for (int c2 = a; c2 < 6; c2++) atomicAdd(&H[k++], Jc[a] * Jc[c2] + Jc[6 + a] * Jc[6 + c2]);
             atomicAdd(&accG[6 * cam + a], Jc[a] * r[0] + Jc[6 + a] * r[1]);
           }
         }
@@ -249,6 +289,77 @@ __global__ void __launch_bounds__(BA_THREADS)
       for (int a = 0; a < 6; a++) hi[a] = 0.0;
     }
     // ---- phase 2: Schur products  S -= W_i Hinv W_j^T ,  rhs_corr += W_i Hinv g_p
+    if (ACC == 3) continue;  // done by ba_cam_rows_kernel / ba_schur_pairs_kernel
+    if (ACC == 2) {
+      // dense path: scatter W_i and Y_i = W_i Hinv into the block's 64 x 96 tiles
+      for (int ri = 0; ri < rounds; ri++) {
+        const int oi = s + ri * 8 + gl;
+        const bool has_i = oi < e;
+        int ci = -1;
+        if (rounds > 1 || ri > 0) {
+          if (has_i) ci = eval_obs(p, cams, camrot, oi, X, sp, r, Jc, Jp);
+        } else {
+          ci = has ? cam : -1;
+        }
+        if (has_i && ci >= 0) {
+#pragma unroll
+          for (int a = 0; a < 6; a++) {
+            const double w0 = Jc[a] * Jp[0] + Jc[6 + a] * Jp[3];
+            const double w1 = Jc[a] * Jp[1] + Jc[6 + a] * Jp[4];
+            const double w2 = Jc[a] * Jp[2] + Jc[6 + a] * Jp[5];
+            const double y0 = w0 * hi[0] + w1 * hi[1] + w2 * hi[2];
+            const double y1 = w0 * hi[1] + w1 * hi[3] + w2 * hi[4];
+            const double y2 = w0 * hi[2] + w1 * hi[4] + w2 * hi[5];
+            const int row = 6 * ci + a;
+            // atomicAdd (not a store): tolerates a point observed twice by one camera
+            atomicAdd(&Wd[(slot * 3 + 0) * DENSE_N + row], w0);
+            atomicAdd(&Wd[(slot * 3 + 1) * DENSE_N + row], w1);
+            atomicAdd(&Wd[(slot * 3 + 2) * DENSE_N + row], w2);
+            atomicAdd(&Yd[(slot * 3 + 0) * DENSE_N + row], y0);
+            atomicAdd(&Yd[(slot * 3 + 1) * DENSE_N + row], y1);
+            atomicAdd(&Yd[(slot * 3 + 2) * DENSE_N + row], y2);
+            atomicAdd(&accR[row], y0 * g[0] + y1 * g[1] + y2 * g[2]);
+          }
+        }
+      }
+      __syncthreads();
+      {
+        const int ty = tid >> 4, tx = tid & 15;
+        const double* yp = Yd + 4 * ty;
+        const double* wp = Wd + 4 * tx;
+#pragma unroll 4
+        for (int k = 0; k < DENSE_K; k++) {
+          const double2 ya = *reinterpret_cast<const double2*>(yp + k * DENSE_N);
+          const double2 yb = *reinterpret_cast<const double2*>(yp + k * DENSE_N + 2);
+          const double2 wa = *reinterpret_cast<const double2*>(wp + k * DENSE_N);
+          const double2 wb = *reinterpret_cast<const double2*>(wp + k * DENSE_N + 2);
+          const double yv[4] = {ya.x, ya.y, yb.x, yb.y}, wv[4] = {wa.x, wa.y, wb.x, wb.y};
+#pragma unroll
+          for (int a = 0; a < 4; a++)
+#pragma unroll
+            for (int c2 = 0; c2 < 4; c2++) sacc[a][c2] += yv[a] * wv[c2];
+        }
+      }
+      __syncthreads();
+      // clear exactly what this lane wrote
+      for (int ri = 0; ri < rounds; ri++) {
+        const int oi = s + ri * 8 + gl;
+        if (oi < e) {
+          const int ci = p.obs_cam[oi];
+          if (ci >= 0) {
+#pragma unroll
+            for (int a = 0; a < 6; a++)
+#pragma unroll
+              for (int c2 = 0; c2 < 3; c2++) {
+                Wd[(slot * 3 + c2) * DENSE_N + 6 * ci + a] = 0.0;
+                Yd[(slot * 3 + c2) * DENSE_N + 6 * ci + a] = 0.0;
+              }
+          }
+        }
+      }
+      __syncwarp();
+      continue;
+    }
     for (int ri = 0; ri < rounds; ri++) {
       const int oi = s + ri * 8 + gl;
       const bool has_i = oi < e;
@@ -264,7 +375,7 @@ __global__ void __launch_bounds__(BA_THREADS)
 #pragma unroll
         for (int a = 0; a < 6; a++)
 #pragma unroll
-          for (int b = 0; b < 3; b++) Wi[3 * a + b] = Jc[a] * Jp[b] + Jc[6 + a] * Jp[3 + b];
+          for (int c2 = 0; c2 < 3; c2++) Wi[3 * a + c2] = Jc[a] * Jp[c2] + Jc[6 + a] * Jp[3 + c2];
 #pragma unroll
         for (int a = 0; a < 6; a++) {
           const double w0 = Wi[3 * a], w1 = Wi[3 * a + 1], w2 = Wi[3 * a + 2];
@@ -292,8 +403,8 @@ __global__ void __launch_bounds__(BA_THREADS)
 #pragma unroll
               for (int a = 0; a < 6; a++)
 #pragma unroll
-                for (int b = 0; b < 3; b++)
-                  Wsm[tid][3 * a + b] = Jc2[a] * Jp2[b] + Jc2[6 + a] * Jp2[3 + b];
+                for (int c2 = 0; c2 < 3; c2++)
+                  Wsm[tid][3 * a + c2] = Jc2[a] * Jp2[c2] + Jc2[6 + a] * Jp2[3 + c2];
             }
           }
           Csm[tid] = cj;
@@ -309,10 +420,10 @@ __global__ void __launch_bounds__(BA_THREADS)
 #pragma unroll
             for (int a = 0; a < 6; a++)
 #pragma unroll
-              for (int b = 0; b < 6; b++) {
-                const double v = Yi[3 * a] * Wj[3 * b] + Yi[3 * a + 1] * Wj[3 * b + 1] +
-                                 Yi[3 * a + 2] * Wj[3 * b + 2];
-                atomicAdd(&Sblk[(size_t)a * n + b], -v);
+              for (int c2 = 0; c2 < 6; c2++) {
+                const double v = Yi[3 * a] * Wj[3 * c2] + Yi[3 * a + 1] * Wj[3 * c2 + 1] +
+                                 Yi[3 * a + 2] * Wj[3 * c2 + 2];
+                atomicAdd(&Sblk[(size_t)a * n + c2], -v);
               }
           }
         }
@@ -320,11 +431,29 @@ __global__ void __launch_bounds__(BA_THREADS)
       }
     }
   }
-  if (SMALL) {
+  if (ACC == 1) {
     __syncthreads();
     for (int i = tid; i < lin_n; i += BA_THREADS) {
       const double v = slin[i];
       if (v != 0.0) atomicAdd(&p.lin[i], v);
+    }
+  } else if (ACC == 2) {
+    __syncthreads();
+    for (int i = tid; i < small_n; i += BA_THREADS) {
+      const double v = slin[i];
+      if (v != 0.0) atomicAdd(&p.Hcc[i], v);  // Hcc | gc | rhs_corr are contiguous in lin
+    }
+    if (FULL) {
+      const int ty = tid >> 4, tx = tid & 15;
+#pragma unroll
+      for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int c2 = 0; c2 < 4; c2++) {
+          const int row = 4 * ty + a, col = 4 * tx + c2;
+          // diagonal and upper camera blocks only (the solve mirrors the rest)
+          if (row < n && col < n && col / 6 >= row / 6 && sacc[a][c2] != 0.0)
+            atomicAdd(&p.S[(size_t)row * n + col], -sacc[a][c2]);
+        }
     }
   }
   double t = block_sum(cost_acc, red);
@@ -335,6 +464,143 @@ __global__ void __launch_bounds__(BA_THREADS)
   if (tid == 0 && t != 0.0) atomicAdd(&p.tail[2], t);
   t = block_max(gmax_acc, red);
   if (tid == 0 && t > 0.0) atomic_max_nonneg(&st->acc_gmax, t);
+}
+
+// ---- large path, camera side.  Work item = (camera, slice of its observation
+// list): one warp accumulates H_cc (21), g_c (6) and the Schur right-hand side
+// W H_pp^-1 g_p (6) of its slice in registers, reduces by shuffles and issues 33
+// atomics per item.
+__global__ void __launch_bounds__(256)
+    ba_cam_rows_kernel(const BADev* __restrict__ probs, int full, int force) {
+  const BADev p = probs[blockIdx.y];
+  LMState* st = p.st;
+  if (st->done && !force) return;
+  const int lane = threadIdx.x & 31;
+  const int item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (item >= p.n_cam_items) return;
+  const int4 it = p.cam_items[item];  // camera, start, length
+  const int cur = st->cur;
+  const double* cams = p.cams[cur];
+  const double* pts = p.pts[cur];
+  const double* camrot = p.camrot[cur];
+  double acc[33];
+#pragma unroll
+  for (int a = 0; a < 33; a++) acc[a] = 0.0;
+  for (int e = lane; e < it.z; e += 32) {
+    const int o = p.cam_obs[it.y + e];
+    const int pt = p.obs_pt[o];
+    double X[3], sp[3], r[2], Jc[12], Jp[6];
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      X[a] = pts[3 * (size_t)pt + a];
+      sp[a] = p.scale_p[3 * (size_t)pt + a];
+    }
+    eval_obs(p, cams, camrot, o, X, sp, r, Jc, Jp);
+    int k = 0;
+#pragma unroll
+    for (int a = 0; a < 6; a++) {
+#pragma unroll
+      for (int c2 = a; c2 < 6; c2++) acc[k++] += Jc[a] * Jc[c2] + Jc[6 + a] * Jc[6 + c2];
+      acc[21 + a] += Jc[a] * r[0] + Jc[6 + a] * r[1];
+    }
+    if (full) {
+      const double* hi = p.pt_hinv + 6 * (size_t)pt;
+      const double* gp = p.pt_gp + 3 * (size_t)pt;
+      // t = Hinv g_p ; rhs_corr += W t = Jc^T (Jp t)
+      const double t0 = hi[0] * gp[0] + hi[1] * gp[1] + hi[2] * gp[2];
+      const double t1 = hi[1] * gp[0] + hi[3] * gp[1] + hi[4] * gp[2];
+      const double t2 = hi[2] * gp[0] + hi[4] * gp[1] + hi[5] * gp[2];
+      const double q0 = Jp[0] * t0 + Jp[1] * t1 + Jp[2] * t2;
+      const double q1 = Jp[3] * t0 + Jp[4] * t1 + Jp[5] * t2;
+#pragma unroll
+      for (int a = 0; a < 6; a++) acc[27 + a] += Jc[a] * q0 + Jc[6 + a] * q1;
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 33; a++) {
+    double v = acc[a];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    acc[a] = v;
+  }
+  if (lane == 0) {
+    const int cam = it.x;
+#pragma unroll
+    for (int a = 0; a < 21; a++) atomicAdd(&p.Hcc[HCC * (size_t)cam + a], acc[a]);
+#pragma unroll
+    for (int a = 0; a < 6; a++) {
+      atomicAdd(&p.gc[6 * cam + a], acc[21 + a]);
+      if (full) atomicAdd(&p.rhs_corr[6 * cam + a], acc[27 + a]);
+    }
+  }
+}
+
+// ---- large path, Schur products.  Work item = (camera block (ci,cj), slice of
+// the pair records of that block); a record is (observation i, observation j)
+// of one point with camera(i) = ci, camera(j) = cj.  One warp accumulates
+// sum Y_i W_j^T (6x6) in registers over its slice, reduces by shuffles and
+// subtracts it from S with 36 atomics per item (an item is <= 2048 records).
+__global__ void __launch_bounds__(256)
+    ba_schur_pairs_kernel(const BADev* __restrict__ probs) {
+  const BADev p = probs[blockIdx.y];
+  LMState* st = p.st;
+  if (st->done) return;
+  const int lane = threadIdx.x & 31;
+  const int item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (item >= p.n_pair_items) return;
+  const int4 it = p.pair_items[item];  // ci, cj, start, length
+  const int cur = st->cur;
+  const double* cams = p.cams[cur];
+  const double* pts = p.pts[cur];
+  const double* camrot = p.camrot[cur];
+  double acc[36];
+#pragma unroll
+  for (int a = 0; a < 36; a++) acc[a] = 0.0;
+  for (int e = lane; e < it.w; e += 32) {
+    const int2 rec = p.pairs[it.z + e];
+    const int pt = p.obs_pt[rec.x];
+    double X[3], sp[3], r[2], Jc[12], Jp[6], Y[18];
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      X[a] = pts[3 * (size_t)pt + a];
+      sp[a] = p.scale_p[3 * (size_t)pt + a];
+    }
+    const double* hi = p.pt_hinv + 6 * (size_t)pt;
+    const double h0 = hi[0], h1 = hi[1], h2 = hi[2], h3 = hi[3], h4 = hi[4], h5 = hi[5];
+    eval_obs(p, cams, camrot, rec.x, X, sp, r, Jc, Jp);
+#pragma unroll
+    for (int a = 0; a < 6; a++) {
+      const double w0 = Jc[a] * Jp[0] + Jc[6 + a] * Jp[3];
+      const double w1 = Jc[a] * Jp[1] + Jc[6 + a] * Jp[4];
+      const double w2 = Jc[a] * Jp[2] + Jc[6 + a] * Jp[5];
+      Y[3 * a + 0] = w0 * h0 + w1 * h1 + w2 * h2;
+      Y[3 * a + 1] = w0 * h1 + w1 * h3 + w2 * h4;
+      Y[3 * a + 2] = w0 * h2 + w1 * h4 + w2 * h5;
+    }
+    if (rec.y != rec.x) eval_obs(p, cams, camrot, rec.y, X, sp, r, Jc, Jp);
+#pragma unroll
+    for (int b = 0; b < 6; b++) {
+      const double w0 = Jc[b] * Jp[0] + Jc[6 + b] * Jp[3];
+      const double w1 = Jc[b] * Jp[1] + Jc[6 + b] * Jp[4];
+      const double w2 = Jc[b] * Jp[2] + Jc[6 + b] * Jp[5];
+#pragma unroll
+      for (int a = 0; a < 6; a++) acc[6 * a + b] += Y[3 * a] * w0 + Y[3 * a + 1] * w1 + Y[3 * a + 2] * w2;
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 36; a++) {
+    double v = acc[a];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    acc[a] = v;
+  }
+  if (lane == 0) {
+    double* Sblk = p.S + (size_t)(6 * it.x) * p.n + 6 * it.y;
+#pragma unroll
+    for (int a = 0; a < 6; a++)
+#pragma unroll
+      for (int b = 0; b < 6; b++) atomicAdd(&Sblk[(size_t)a * p.n + b], -acc[6 * a + b]);
+  }
 }
 
 // After the initial pass: camera column scales, |x|, cost, gradient test.
@@ -533,8 +799,8 @@ __global__ void __launch_bounds__(256)
       if (tid == 0) s_ok = 0;
       d = 1.0;
     }
-    const double inv_d = 1.0 / d, inv_s = 1.0 / sqrt(d);
-    if (tid == 0) dg[j] = sqrt(d);
+    const double inv_s = rsqrt(d), inv_d = inv_s * inv_s;
+    if (tid == 0) dg[j] = inv_s;  // 1 / L_jj
     for (int i = j + 1 + tid; i < n; i += 256) A[j * n + i] = A[i * n + j] * inv_s;  // L_ij at [j][i]
     for (int i = j + 1 + ty; i < n; i += 16) {
       const double aij = A[i * n + j] * inv_d;
@@ -542,23 +808,41 @@ __global__ void __launch_bounds__(256)
     }
     __syncthreads();
   }
-  if (tid < 32) {  // L y = b ; L^T x = y   (L_ik = A[k][i] for k < i)
-    for (int i = 0; i < n; i++) {
-      double sacc = 0;
-      for (int k = tid; k < i; k += 32) sacc += A[k * n + i] * b[k];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
-      if (tid == 0) b[i] = (b[i] - sacc) / dg[i];
-      __syncwarp();
+  // L y = b then L^T x = y by warp 0, right-looking with the vector in registers
+  // (lane owns rows lane, lane+32, lane+64): per step one shuffle broadcast and one
+  // FMA per owned row, no reductions and no divides.  L_ik (k<i) sits at A[k][i].
+  if (tid < 32) {
+    double v0 = tid < n ? b[tid] : 0.0, v1 = tid + 32 < n ? b[tid + 32] : 0.0,
+           v2 = tid + 64 < n ? b[tid + 64] : 0.0;
+    for (int j = 0; j < n; j++) {
+      const int own = j & 31, slot = j >> 5;
+      double yj = slot == 0 ? v0 : (slot == 1 ? v1 : v2);
+      yj = __shfl_sync(0xffffffffu, yj, own) * dg[j];
+      if (tid == own) {
+        if (slot == 0) v0 = yj; else if (slot == 1) v1 = yj; else v2 = yj;
+      }
+      const double* Lj = A + (size_t)j * n;  // L_ij = Lj[i] for i > j
+      if (tid > j && tid < n) v0 -= Lj[tid] * yj;
+      if (tid + 32 > j && tid + 32 < n) v1 -= Lj[tid + 32] * yj;
+      if (tid + 64 > j && tid + 64 < n) v2 -= Lj[tid + 64] * yj;
     }
-    for (int i = n - 1; i >= 0; i--) {
-      double sacc = 0;
-      for (int k = i + 1 + tid; k < n; k += 32) sacc += A[i * n + k] * b[k];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
-      if (tid == 0) b[i] = (b[i] - sacc) / dg[i];
-      __syncwarp();
+    for (int j = n - 1; j >= 0; j--) {
+      const int own = j & 31, slot = j >> 5;
+      // x_j = (y_j - sum_{k>j} L_kj x_k) / L_jj with L_kj = A[j][k]: gather form needs a
+      // reduction, so use the column form: after x_j is known, y_i -= L_ji x_j for i < j
+      double xj = slot == 0 ? v0 : (slot == 1 ? v1 : v2);
+      xj = __shfl_sync(0xffffffffu, xj, own) * dg[j];
+      if (tid == own) {
+        if (slot == 0) v0 = xj; else if (slot == 1) v1 = xj; else v2 = xj;
+      }
+      // L_ji for i < j is stored at A[i][j] (column j of the upper triangle)
+      if (tid < j) v0 -= A[(size_t)tid * n + j] * xj;
+      if (tid + 32 < j) v1 -= A[(size_t)(tid + 32) * n + j] * xj;
+      if (tid + 64 < j) v2 -= A[(size_t)(tid + 64) * n + j] * xj;
     }
+    if (tid < n) b[tid] = v0;
+    if (tid + 32 < n) b[tid + 32] = v1;
+    if (tid + 64 < n) b[tid + 64] = v2;
   }
   __syncthreads();
   // candidate cameras + rotation blocks
@@ -587,70 +871,209 @@ __global__ void __launch_bounds__(256)
 // Large systems: right-looking blocked Cholesky in global memory, NB = 32.
 constexpr int NB = 32;
 
-// Panel: every CTA factors the diagonal block in smem; CTA b>0 then solves its
-// row block  L_ik = A_ik L_kk^-T.
+// Panel: every CTA factors the 32x32 diagonal block in shared memory with all
+// 256 threads (one barrier per column, rsqrt instead of sqrt + divides; L_ij,
+// i>j, is kept transposed at D[j][i]); CTA 0 writes L_kk and 1/L_jj, CTA b>0
+// solves its 32-row block  X L_kk^T = A_ik  with 8 threads per row.
 __global__ void __launch_bounds__(NB * NB / 4)
     ba_chol_panel_kernel(const BADev* __restrict__ probs, int kb) {
   const BADev p = probs[blockIdx.y];
   LMState* st = p.st;
   if (st->done) return;
   __shared__ double D[NB][NB + 1];
-  __shared__ double Ablk[NB][NB + 1];
+  __shared__ double X[NB][NB + 1];
+  __shared__ double idg[NB];  // 1 / L_jj
   __shared__ int s_ok;
   const int n = p.n, tid = threadIdx.x;
   const int k0 = kb * NB, kn = min(NB, n - k0);
   if (k0 >= n || (kb + (int)blockIdx.x) * NB >= n) return;
+  const int ib = kb + blockIdx.x;
+  const int i0 = ib * NB, in = min(NB, n - i0);
   for (int e = tid; e < NB * NB; e += blockDim.x) {
     const int i = e / NB, j = e % NB;
     D[i][j] = (i < kn && j < kn) ? p.S[(size_t)(k0 + i) * n + k0 + j] : (i == j ? 1.0 : 0.0);
+    X[i][j] = (blockIdx.x > 0 && i < in && j < kn) ? p.S[(size_t)(i0 + i) * n + k0 + j] : 0.0;
   }
   if (tid == 0) s_ok = 1;
   __syncthreads();
-  if (tid < 32) {  // one warp, lane = row
-    for (int j = 0; j < kn; j++) {
-      double d = D[j][j];
-      if (!(d > 0.0)) {
-        if (tid == 0) s_ok = 0;
-        d = 1.0;
-      }
-      const double dj = sqrt(d);
-      __syncwarp();
-      if (tid == j) D[j][j] = dj;
-      if (tid > j && tid < kn) D[tid][j] /= dj;
-      __syncwarp();
-      if (tid > j && tid < kn)
-        for (int k = j + 1; k <= tid; k++) D[tid][k] -= D[tid][j] * D[k][j];
-      __syncwarp();
+  const int ty = tid >> 4, tx = tid & 15;
+  for (int j = 0; j < NB; j++) {
+    double d = D[j][j];
+    if (!(d > 0.0)) {
+      if (tid == 0) s_ok = 0;
+      d = 1.0;
     }
+    const double is = rsqrt(d), inv_d = is * is;
+    if (tid == 0) idg[j] = is;
+    if (tid > j && tid < NB) D[j][tid] = D[tid][j] * is;  // L_ij at [j][i]
+    for (int i = j + 1 + ty; i < NB; i += 16) {
+      const double aij = D[i][j] * inv_d;
+      for (int k = j + 1 + tx; k <= i; k += 16) D[i][k] -= aij * D[k][j];
+    }
+    __syncthreads();
   }
-  __syncthreads();
-  const int ib = kb + blockIdx.x;
-  const int i0 = ib * NB, in = min(NB, n - i0);
   if (blockIdx.x == 0) {
     for (int e = tid; e < NB * NB; e += blockDim.x) {
       const int i = e / NB, j = e % NB;
-      if (i < kn && j <= i) p.S[(size_t)(k0 + i) * n + k0 + j] = D[i][j];
+      if (i < kn && j < i) p.S[(size_t)(k0 + i) * n + k0 + j] = D[j][i];
+    }
+    if (tid < NB) {
+      if (tid < kn) p.S[(size_t)(k0 + tid) * n + k0 + tid] = 1.0 / idg[tid];
+      p.dinv[(size_t)kb * NB + tid] = idg[tid];
     }
     if (tid == 0 && !s_ok) st->solve_ok = 0;
     return;
   }
-  for (int e = tid; e < NB * NB; e += blockDim.x) {
-    const int i = e / NB, j = e % NB;
-    Ablk[i][j] = (i < in && j < kn) ? p.S[(size_t)(i0 + i) * n + k0 + j] : 0.0;
-  }
-  __syncthreads();
-  if (tid < in) {  // x L^T = a, one row per thread
-    for (int c = 0; c < kn; c++) {
-      double v = Ablk[tid][c];
-      for (int m = 0; m < c; m++) v -= Ablk[tid][m] * D[c][m];
-      Ablk[tid][c] = v / D[c][c];
+  // row r (8 threads): x_c = (a_c - sum_{m<c} x_m L_cm) / L_cc ,  L_cm = D[m][c]
+  {
+    const int r = tid >> 3, sub = tid & 7;
+    for (int c = 0; c < NB; c++) {
+      double part = 0;
+      for (int m = sub; m < c; m += 8) part += X[r][m] * D[m][c];
+      part += __shfl_xor_sync(0xffffffffu, part, 4);
+      part += __shfl_xor_sync(0xffffffffu, part, 2);
+      part += __shfl_xor_sync(0xffffffffu, part, 1);
+      if (sub == 0) X[r][c] = (X[r][c] - part) * idg[c];
+      __syncwarp();
     }
   }
   __syncthreads();
   for (int e = tid; e < NB * NB; e += blockDim.x) {
     const int i = e / NB, j = e % NB;
-    if (i < in && j < kn) p.S[(size_t)(i0 + i) * n + k0 + j] = Ablk[i][j];
+    if (i < in && j < kn) p.S[(size_t)(i0 + i) * n + k0 + j] = X[i][j];
   }
+}
+
+// ---- dataflow tiled Cholesky (n > 96, one window): ONE cooperative launch.
+// Lower-triangular 32x32 tiles are numbered column-major and dealt round-robin to
+// co-resident CTAs; a CTA handles its tiles in increasing order.  Tile (i,j) is
+// computed left-looking: A_ij -= sum_{k<j} L_ik L_jk^T as soon as the two source
+// tiles are flagged ready, then POTRF (i == j) or TRSM against L_jj, then its own
+// ready flag.  Every dependency of a tile has a smaller number, so the smallest
+// unfinished tile can always proceed: no deadlock while all CTAs are resident
+// (cooperative launch guarantees that).  Replaces 2 launches per block column.
+__device__ __forceinline__ void flag_wait(const int* flag) {
+  if (threadIdx.x == 0) {
+    while (*reinterpret_cast<const volatile int*>(flag) == 0) {
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256)
+    ba_chol_dataflow_kernel(const BADev* __restrict__ probs, int* __restrict__ flags, int T) {
+  const BADev p = probs[0];
+  LMState* st = p.st;
+  if (st->done) return;
+  __shared__ double A[NB][NB + 1];   // source tile L_ik, then the tile being finished
+  __shared__ double B[NB][NB + 1];   // source tile L_jk, then L_jj (transposed-slot form)
+  __shared__ double idg[NB];
+  __shared__ int s_ok;
+  const int n = p.n, tid = threadIdx.x;
+  const int ty = tid >> 4, tx = tid & 15;
+  const int n_tiles = T * (T + 1) / 2;
+  if (tid == 0) s_ok = 1;
+  int j = 0, col_start = 0;  // column of the current tile and the number of its first tile
+  for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    while (t >= col_start + (T - j)) {
+      col_start += T - j;
+      j++;
+    }
+    const int i = j + (t - col_start);
+    const int i0 = i * NB, j0 = j * NB;
+    // this thread's 2x2 patch of the tile
+    double acc[2][2];
+#pragma unroll
+    for (int a = 0; a < 2; a++)
+#pragma unroll
+      for (int b = 0; b < 2; b++) {
+        const int r = i0 + 2 * ty + a, c = j0 + 2 * tx + b;
+        acc[a][b] = (r < n && c < n) ? __ldcg(&p.S[(size_t)r * n + c]) : (r == c ? 1.0 : 0.0);
+      }
+    for (int k = 0; k < j; k++) {
+      flag_wait(&flags[i * T + k]);
+      if (i != j) flag_wait(&flags[j * T + k]);
+      const int k0 = k * NB;
+      for (int e = tid; e < NB * NB; e += 256) {
+        const int r = e >> 5, c = e & 31;
+        A[r][c] = (i0 + r < n) ? __ldcg(&p.S[(size_t)(i0 + r) * n + k0 + c]) : 0.0;
+        B[r][c] = (j0 + r < n) ? __ldcg(&p.S[(size_t)(j0 + r) * n + k0 + c]) : 0.0;
+      }
+      __syncthreads();
+#pragma unroll 8
+      for (int m = 0; m < NB; m++) {
+        const double a0 = A[2 * ty][m], a1 = A[2 * ty + 1][m];
+        const double b0 = B[2 * tx][m], b1 = B[2 * tx + 1][m];
+        acc[0][0] -= a0 * b0;
+        acc[0][1] -= a0 * b1;
+        acc[1][0] -= a1 * b0;
+        acc[1][1] -= a1 * b1;
+      }
+      __syncthreads();
+    }
+#pragma unroll
+    for (int a = 0; a < 2; a++)
+#pragma unroll
+      for (int b = 0; b < 2; b++) A[2 * ty + a][2 * tx + b] = acc[a][b];
+    __syncthreads();
+    if (i == j) {
+      // POTRF in shared memory, L_rc (r>c) kept at A[c][r]
+      for (int c = 0; c < NB; c++) {
+        double d = A[c][c];
+        if (!(d > 0.0)) {
+          if (tid == 0) s_ok = 0;
+          d = 1.0;
+        }
+        const double is = rsqrt(d), inv_d = is * is;
+        if (tid == 0) idg[c] = is;
+        if (tid > c && tid < NB) A[c][tid] = A[tid][c] * is;
+        for (int r = c + 1 + ty; r < NB; r += 16) {
+          const double arc = A[r][c] * inv_d;
+          for (int q = c + 1 + tx; q <= r; q += 16) A[r][q] -= arc * A[q][c];
+        }
+        __syncthreads();
+      }
+      for (int e = tid; e < NB * NB; e += 256) {
+        const int r = e >> 5, c = e & 31;
+        if (i0 + r < n && c < r) p.S[(size_t)(i0 + r) * n + j0 + c] = A[c][r];
+      }
+      if (tid < NB) {
+        if (i0 + tid < n) p.S[(size_t)(i0 + tid) * n + j0 + tid] = 1.0 / idg[tid];
+        p.dinv[(size_t)j * NB + tid] = idg[tid];
+      }
+    } else {
+      flag_wait(&flags[j * T + j]);
+      for (int e = tid; e < NB * NB; e += 256) {
+        const int r = e >> 5, c = e & 31;  // B[m][c] = L_cm for m < c
+        B[c][r] = (r > c && j0 + r < n) ? __ldcg(&p.S[(size_t)(j0 + r) * n + j0 + c]) : 0.0;
+      }
+      if (tid < NB) idg[tid] = __ldcg(&p.dinv[(size_t)j * NB + tid]);
+      __syncthreads();
+      {
+        const int r = tid >> 3, sub = tid & 7;
+        for (int c = 0; c < NB; c++) {
+          double part = 0;
+          for (int m = sub; m < c; m += 8) part += A[r][m] * B[m][c];
+          part += __shfl_xor_sync(0xffffffffu, part, 4);
+          part += __shfl_xor_sync(0xffffffffu, part, 2);
+          part += __shfl_xor_sync(0xffffffffu, part, 1);
+          if (sub == 0) A[r][c] = (A[r][c] - part) * idg[c];
+          __syncwarp();
+        }
+      }
+      __syncthreads();
+      for (int e = tid; e < NB * NB; e += 256) {
+        const int r = e >> 5, c = e & 31;
+        if (i0 + r < n && j0 + c < n) p.S[(size_t)(i0 + r) * n + j0 + c] = A[r][c];
+      }
+    }
+    __threadfence();  // every thread publishes its part of the tile before the flag goes up
+    __syncthreads();
+    if (tid == 0) atomicExch(&flags[i * T + j], 1);
+  }
+  __syncthreads();
+  if (tid == 0 && !s_ok) st->solve_ok = 0;
 }
 
 // Trailing update A_ij -= L_ik L_jk^T for block pairs i >= j > kb (lower triangle).
@@ -692,48 +1115,93 @@ __global__ void __launch_bounds__(256) ba_chol_update_kernel(const BADev* __rest
 }
 
 // Triangular solves with the factor in global memory; one CTA, vector in smem.
+// Per 32-wide block: the diagonal block is staged in shared memory and solved by
+// one warp with the vector in registers (one shuffle + one FMA per column, the
+// stored 1/L_jj instead of divides); then all threads update the remaining rows
+// with register-staged loads.
 __global__ void __launch_bounds__(1024) ba_chol_solve_kernel(const BADev* __restrict__ probs) {
   const BADev p = probs[blockIdx.y];
   LMState* st = p.st;
   if (st->done) return;
   extern __shared__ double y[];
+  __shared__ double Lb[NB][NB + 1];
+  __shared__ double yk[NB];
+  __shared__ double idg[NB];
   const int n = p.n, tid = threadIdx.x;
   const int nblk = (n + NB - 1) / NB;
   for (int i = tid; i < n; i += blockDim.x) y[i] = p.rhs[i];
   __syncthreads();
   for (int kb = 0; kb < nblk; kb++) {  // L y = b
     const int k0 = kb * NB, kn = min(NB, n - k0);
-    if (tid < 32) {
-      for (int j = 0; j < kn; j++) {
-        if (tid == j) y[k0 + j] /= p.S[(size_t)(k0 + j) * n + k0 + j];
-        __syncwarp();
-        if (tid > j && tid < kn) y[k0 + tid] -= p.S[(size_t)(k0 + tid) * n + k0 + j] * y[k0 + j];
-        __syncwarp();
-      }
+    {
+      const int i = tid >> 5, j = tid & 31;
+      Lb[i][j] = (i < kn && j < i) ? p.S[(size_t)(k0 + i) * n + k0 + j] : 0.0;
+      if (tid < NB) idg[tid] = p.dinv[(size_t)kb * NB + tid];
     }
     __syncthreads();
-    for (int i = k0 + kn + tid; i < n; i += blockDim.x) {
-      const double* Lrow = p.S + (size_t)i * n + k0;
-      double acc = 0;
-      for (int m = 0; m < kn; m++) acc += Lrow[m] * y[k0 + m];
-      y[i] -= acc;
+    if (tid < 32) {
+      double v = tid < kn ? y[k0 + tid] : 0.0;
+      for (int j = 0; j < kn; j++) {
+        const double yj = __shfl_sync(0xffffffffu, v, j) * idg[j];
+        if (tid == j) v = yj;
+        if (tid > j) v -= Lb[tid][j] * yj;
+      }
+      yk[tid] = tid < kn ? v : 0.0;
+      if (tid < kn) y[k0 + tid] = v;
+    }
+    __syncthreads();
+    {
+      // rows below the block: one warp per row, lane = column (coalesced 256 B),
+      // four rows in flight per warp
+      const int lane = tid & 31, warp = tid >> 5;
+      const double ykl = yk[lane];
+      for (int i = k0 + kn + warp; i < n; i += 32 * 4) {
+        double a[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const int r = i + 32 * q;
+          a[q] = (r < n && lane < kn) ? p.S[(size_t)r * n + k0 + lane] * ykl : 0.0;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+          for (int q = 0; q < 4; q++) a[q] += __shfl_xor_sync(0xffffffffu, a[q], o);
+        }
+        if (lane < 4) {
+          const int r = i + 32 * lane;
+          const double v = lane == 0 ? a[0] : (lane == 1 ? a[1] : (lane == 2 ? a[2] : a[3]));
+          if (r < n) y[r] -= v;
+        }
+      }
     }
     __syncthreads();
   }
   for (int kb = nblk - 1; kb >= 0; kb--) {  // L^T x = y
     const int k0 = kb * NB, kn = min(NB, n - k0);
+    {
+      const int i = tid >> 5, j = tid & 31;
+      Lb[i][j] = (i < kn && j < i) ? p.S[(size_t)(k0 + i) * n + k0 + j] : 0.0;
+      if (tid < NB) idg[tid] = p.dinv[(size_t)kb * NB + tid];
+    }
+    __syncthreads();
     if (tid < 32) {
+      double v = tid < kn ? y[k0 + tid] : 0.0;
       for (int j = kn - 1; j >= 0; j--) {
-        if (tid == j) y[k0 + j] /= p.S[(size_t)(k0 + j) * n + k0 + j];
-        __syncwarp();
-        if (tid < j) y[k0 + tid] -= p.S[(size_t)(k0 + j) * n + k0 + tid] * y[k0 + j];
-        __syncwarp();
+        const double xj = __shfl_sync(0xffffffffu, v, j) * idg[j];
+        if (tid == j) v = xj;
+        if (tid < j) v -= Lb[j][tid] * xj;  // (L^T)_{tid,j} = L_{j,tid}
       }
+      yk[tid] = tid < kn ? v : 0.0;
+      if (tid < kn) y[k0 + tid] = v;
     }
     __syncthreads();
     for (int i = tid; i < k0; i += blockDim.x) {
+      double v[NB];
+#pragma unroll
+      for (int m = 0; m < NB; m++) v[m] = m < kn ? p.S[(size_t)(k0 + m) * n + i] : 0.0;
       double acc = 0;
-      for (int m = 0; m < kn; m++) acc += p.S[(size_t)(k0 + m) * n + i] * y[k0 + m];
+#pragma unroll
+      for (int m = 0; m < NB; m++) acc += v[m] * yk[m];
       y[i] -= acc;
     }
     __syncthreads();
@@ -930,7 +1398,8 @@ struct lorb_ba_problem {
   int nw = 0;
   std::vector<lorb::BADev> h_dev;     // host copies of the per-window descriptors
   std::vector<int> h_cam_off, h_pt_off;
-  lorb::Buf params, topo, work, descs, hstate, counter;
+  lorb::Buf params, topo, work, descs, hstate, counter, lists;
+  int max_cam_items = 0, max_pair_items = 0;
   double *cams0 = nullptr, *pts0 = nullptr;  // initial parameters of all windows
   size_t cam_doubles = 0, pt_doubles = 0;
   int maxC = 0, maxP = 0;
@@ -979,10 +1448,12 @@ static int problem_build(lorb_ba_problem* pb, lorb_ctx* c, const std::vector<Win
   pb->ctx = c;
   const int nw = (int)ws.size();
   pb->nw = nw;
+  pb->maxC = pb->maxP = 0;
+  pb->lin_doubles_max = 0;
   pb->h_dev.resize(nw);
   pb->h_cam_off.assign(nw + 1, 0);
   pb->h_pt_off.assign(nw + 1, 0);
-  size_t tot_obs = 0, tot_fix = 0, tot_ptr = 0, tot_lin = 0, tot_rot = 0;
+  size_t tot_obs = 0, tot_fix = 0, tot_ptr = 0, tot_lin = 0, tot_rot = 0, tot_dinv = 0;
   for (int w = 0; w < nw; w++) {
     const WindowSpec& W = ws[w];
     LORB_REQUIRE(W.C > 0 && W.P >= 0 && W.O >= 0 && W.F >= 0, "window sizes");
@@ -998,6 +1469,7 @@ static int problem_build(lorb_ba_problem* pb, lorb_ctx* c, const std::vector<Win
     tot_fix += W.F;
     tot_ptr += (size_t)W.P + 1;
     tot_rot += (size_t)W.C * CAMROT;
+    tot_dinv += (size_t)((n + NB - 1) / NB) * NB;
   }
   const size_t totC = pb->h_cam_off[nw], totP = pb->h_pt_off[nw];
   pb->cam_doubles = totC * 6;
@@ -1008,6 +1480,13 @@ static int problem_build(lorb_ba_problem* pb, lorb_ctx* c, const std::vector<Win
   std::vector<double> h_fix(std::max<size_t>(tot_fix, 1) * 12);
   std::vector<double> h_cams(pb->cam_doubles), h_pts(std::max<size_t>(pb->pt_doubles, 1));
   std::vector<size_t> o_ptr(nw), o_obs(nw), o_fix(nw);
+  // large-path work lists (windows with 6C > 96), concatenated over windows
+  std::vector<int> h_obs_pt, h_cam_obs;
+  std::vector<int4> h_cam_items, h_pair_items;
+  std::vector<int2> h_pairs;
+  struct ListOff { size_t obs_pt, cam_obs, cam_items, pairs, pair_items; int n_cam_items, n_pair_items; };
+  std::vector<ListOff> lo(nw, ListOff{0, 0, 0, 0, 0, 0, 0});
+  pb->max_cam_items = pb->max_pair_items = 0;
   {
     size_t a = 0, b = 0, f = 0;
     for (int w = 0; w < nw; w++) {
@@ -1039,6 +1518,63 @@ static int problem_build(lorb_ba_problem* pb, lorb_ctx* c, const std::vector<Win
         h_uv[b + d] = make_float2(W.fix_uv[2 * i], W.fix_uv[2 * i + 1]);
         host_fix_rotation(W.fix_rt + 6 * (size_t)i, &h_fix[12 * (f + i)]);
       }
+      if (6 * W.C > 96) {
+        const int OT = W.O + W.F;
+        const int* cam = &h_cam[b];
+        ListOff& L = lo[w];
+        L.obs_pt = h_obs_pt.size();
+        h_obs_pt.resize(L.obs_pt + OT);
+        for (int pp = 0; pp < W.P; pp++)
+          for (int e = ptr[pp]; e < ptr[pp + 1]; e++) h_obs_pt[L.obs_pt + e] = pp;
+        // observations grouped by camera (counting sort), sliced into items of <= 1024
+        std::vector<int> cnt((size_t)W.C + 1, 0);
+        for (int e = 0; e < OT; e++)
+          if (cam[e] >= 0) cnt[cam[e] + 1]++;
+        for (int c2 = 0; c2 < W.C; c2++) cnt[c2 + 1] += cnt[c2];
+        L.cam_obs = h_cam_obs.size();
+        h_cam_obs.resize(L.cam_obs + cnt[W.C]);
+        {
+          std::vector<int> cur(cnt.begin(), cnt.end() - 1);
+          for (int e = 0; e < OT; e++)
+            if (cam[e] >= 0) h_cam_obs[L.cam_obs + cur[cam[e]]++] = e;
+        }
+        L.cam_items = h_cam_items.size();
+        for (int c2 = 0; c2 < W.C; c2++)
+          for (int st0 = cnt[c2]; st0 < cnt[c2 + 1]; st0 += 1024)
+            h_cam_items.push_back(make_int4(c2, st0, std::min(1024, cnt[c2 + 1] - st0), 0));
+        L.n_cam_items = (int)(h_cam_items.size() - L.cam_items);
+        // pair records grouped by camera block (ci <= cj; equal cameras keep both orders)
+        std::vector<long long> kcnt((size_t)W.C * W.C + 1, 0);
+        for (int pp = 0; pp < W.P; pp++)
+          for (int e1 = ptr[pp]; e1 < ptr[pp + 1]; e1++) {
+            if (cam[e1] < 0) continue;
+            for (int e2 = ptr[pp]; e2 < ptr[pp + 1]; e2++)
+              if (cam[e2] >= cam[e1]) kcnt[(size_t)cam[e1] * W.C + cam[e2] + 1]++;
+          }
+        for (size_t k2 = 0; k2 < (size_t)W.C * W.C; k2++) kcnt[k2 + 1] += kcnt[k2];
+        L.pairs = h_pairs.size();
+        h_pairs.resize(L.pairs + (size_t)kcnt[(size_t)W.C * W.C]);
+        {
+          std::vector<long long> cur(kcnt.begin(), kcnt.end() - 1);
+          for (int pp = 0; pp < W.P; pp++)
+            for (int e1 = ptr[pp]; e1 < ptr[pp + 1]; e1++) {
+              if (cam[e1] < 0) continue;
+              for (int e2 = ptr[pp]; e2 < ptr[pp + 1]; e2++)
+                if (cam[e2] >= cam[e1])
+                  h_pairs[L.pairs + (size_t)cur[(size_t)cam[e1] * W.C + cam[e2]]++] = make_int2(e1, e2);
+            }
+        }
+        L.pair_items = h_pair_items.size();
+        for (int ci = 0; ci < W.C; ci++)
+          for (int cj = ci; cj < W.C; cj++) {
+            const long long s0 = kcnt[(size_t)ci * W.C + cj], s1 = kcnt[(size_t)ci * W.C + cj + 1];
+            for (long long st0 = s0; st0 < s1; st0 += 2048)
+              h_pair_items.push_back(make_int4(ci, cj, (int)st0, (int)std::min<long long>(2048, s1 - st0)));
+          }
+        L.n_pair_items = (int)(h_pair_items.size() - L.pair_items);
+        pb->max_cam_items = std::max(pb->max_cam_items, L.n_cam_items);
+        pb->max_pair_items = std::max(pb->max_pair_items, L.n_pair_items);
+      }
       memcpy(&h_cams[6 * (size_t)pb->h_cam_off[w]], W.cams, (size_t)W.C * 48);
       if (W.P) memcpy(&h_pts[3 * (size_t)pb->h_pt_off[w]], W.pts, (size_t)W.P * 24);
       a += (size_t)W.P + 1;
@@ -1064,8 +1600,8 @@ static int problem_build(lorb_ba_problem* pb, lorb_ctx* c, const std::vector<Win
   double* d_fix = (double*)(t + t_ptr + t_cam + t_uv);
   const size_t w_rot = al(tot_rot * 8), w_sc = cb, w_sp = pbts, w_lin = al(tot_lin * 8), w_rhs = cb,
                w_hinv = al(std::max<size_t>(totP, 1) * 48), w_gp = pbts,
-               w_st = al(sizeof(LMState) * (size_t)nw);
-  LORB_TRY(pb->work.reserve(2 * w_rot + w_sc + w_sp + w_lin + w_rhs + w_hinv + w_gp + w_st));
+               w_st = al(sizeof(LMState) * (size_t)nw), w_dinv = al(tot_dinv * 8);
+  LORB_TRY(pb->work.reserve(2 * w_rot + w_sc + w_sp + w_lin + w_rhs + w_hinv + w_gp + w_st + w_dinv));
   uint8_t* wk = pb->work.as<uint8_t>();
   double* d_rot[2] = {(double*)wk, (double*)(wk + w_rot)};
   wk += 2 * w_rot;
@@ -1075,11 +1611,12 @@ static int problem_build(lorb_ba_problem* pb, lorb_ctx* c, const std::vector<Win
   double* d_rhs = (double*)wk;  wk += w_rhs;
   double* d_hinv = (double*)wk; wk += w_hinv;
   double* d_gp = (double*)wk;   wk += w_gp;
-  pb->d_states = (LMState*)wk;
+  pb->d_states = (LMState*)wk;  wk += w_st;
+  double* d_dinv = (double*)wk;
   pb->lin_base = d_lin;
   pb->lin_bytes_total = tot_lin * 8;
   {
-    size_t lin_off = 0, rot_off = 0;
+    size_t lin_off = 0, rot_off = 0, dinv_off = 0;
     for (int w = 0; w < nw; w++) {
       const WindowSpec& W = ws[w];
       BADev& d = pb->h_dev[w];
@@ -1112,8 +1649,37 @@ static int problem_build(lorb_ba_problem* pb, lorb_ctx* c, const std::vector<Win
       d.pt_hinv = d_hinv + 2 * po;
       d.pt_gp = d_gp + po;
       d.st = pb->d_states + w;
+      d.dinv = d_dinv + dinv_off;
+      dinv_off += (size_t)((d.n + NB - 1) / NB) * NB;
       lin_off += (size_t)d.n * d.n + (size_t)HCC * W.C + 12 * (size_t)W.C + 8;
       rot_off += (size_t)W.C * CAMROT;
+    }
+  }
+  {
+    const size_t b0 = al(h_obs_pt.size() * 4), b1 = al(h_cam_obs.size() * 4),
+                 b2 = al(h_cam_items.size() * 16), b3 = al(h_pairs.size() * 8),
+                 b4 = al(h_pair_items.size() * 16);
+    LORB_TRY(pb->lists.reserve(b0 + b1 + b2 + b3 + b4 + 256));
+    uint8_t* lb = pb->lists.as<uint8_t>();
+    cudaStream_t s2 = c->stream;
+    if (!h_obs_pt.empty()) {
+      LORB_CUDA_TRY(cudaMemcpyAsync(lb, h_obs_pt.data(), h_obs_pt.size() * 4, cudaMemcpyHostToDevice, s2));
+      LORB_CUDA_TRY(cudaMemcpyAsync(lb + b0, h_cam_obs.data(), h_cam_obs.size() * 4, cudaMemcpyHostToDevice, s2));
+      LORB_CUDA_TRY(cudaMemcpyAsync(lb + b0 + b1, h_cam_items.data(), h_cam_items.size() * 16, cudaMemcpyHostToDevice, s2));
+      LORB_CUDA_TRY(cudaMemcpyAsync(lb + b0 + b1 + b2, h_pairs.data(), h_pairs.size() * 8, cudaMemcpyHostToDevice, s2));
+      LORB_CUDA_TRY(cudaMemcpyAsync(lb + b0 + b1 + b2 + b3, h_pair_items.data(), h_pair_items.size() * 16, cudaMemcpyHostToDevice, s2));
+      LORB_CUDA_TRY(cudaStreamSynchronize(s2));
+    }
+    for (int w = 0; w < nw; w++) {
+      BADev& d = pb->h_dev[w];
+      const ListOff& L = lo[w];
+      d.obs_pt = reinterpret_cast<const int*>(lb) + L.obs_pt;
+      d.cam_obs = reinterpret_cast<const int*>(lb + b0) + L.cam_obs;
+      d.cam_items = reinterpret_cast<const int4*>(lb + b0 + b1) + L.cam_items;
+      d.pairs = reinterpret_cast<const int2*>(lb + b0 + b1 + b2) + L.pairs;
+      d.pair_items = reinterpret_cast<const int4*>(lb + b0 + b1 + b2 + b3) + L.pair_items;
+      d.n_cam_items = L.n_cam_items;
+      d.n_pair_items = L.n_pair_items;
     }
   }
   LORB_TRY(pb->descs.reserve(sizeof(BADev) * (size_t)nw));
@@ -1158,10 +1724,32 @@ static int run_cholesky(lorb_ba_problem* pb) {
     return LORB_OK;
   }
   const int nblk = (n + NB - 1) / NB;
-  for (int kb = 0; kb < nblk; kb++) {
-    LORB_LAUNCH(c, ba_chol_panel_kernel, dim3(nblk - kb, nw), NB * NB / 4, 0, dp, kb);
-    const int m = nblk - kb - 1;
-    if (m > 0) LORB_LAUNCH(c, ba_chol_update_kernel, dim3(m * (m + 1) / 2, nw), 256, 0, dp, kb, nblk);
+  static int coop_ok = -1, coop_blocks = 0;
+  if (coop_ok < 0) {
+    int dev_coop = 0, per_sm = 0;
+    cudaDeviceGetAttribute(&dev_coop, cudaDevAttrCooperativeLaunch, c->device);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ba_chol_dataflow_kernel, 256, 0);
+    const char* e = getenv("LORB_CHOL_DATAFLOW");
+    coop_ok = (dev_coop && per_sm > 0 && !(e && atoi(e) == 0)) ? 1 : 0;
+    coop_blocks = per_sm * c->sm_count;
+  }
+  if (coop_ok && nw == 1) {
+    const int n_tiles = nblk * (nblk + 1) / 2;
+    LORB_TRY(dev_reserve(c, 14, (size_t)nblk * nblk * 4));
+    int* flags = c->d[14].as<int>();
+    LORB_CUDA_TRY(cudaMemsetAsync(flags, 0, (size_t)nblk * nblk * 4, c->stream));
+    int T = nblk;
+    void* args[] = {(void*)&dp, (void*)&flags, (void*)&T};
+    LORB_CUDA_TRY(cudaLaunchCooperativeKernel((void*)ba_chol_dataflow_kernel,
+                                              dim3(std::min(n_tiles, coop_blocks)), dim3(256), args, 0,
+                                              c->stream));
+    c->launches++;
+  } else {
+    for (int kb = 0; kb < nblk; kb++) {
+      LORB_LAUNCH(c, ba_chol_panel_kernel, dim3(nblk - kb, nw), NB * NB / 4, 0, dp, kb);
+      const int m = nblk - kb - 1;
+      if (m > 0) LORB_LAUNCH(c, ba_chol_update_kernel, dim3(m * (m + 1) / 2, nw), 256, 0, dp, kb, nblk);
+    }
   }
   LORB_REQUIRE((size_t)n * 8 <= 200 * 1024, "reduced camera system too large for the solve kernel");
   LORB_CUDA_TRY(cudaFuncSetAttribute(ba_chol_solve_kernel,
@@ -1188,28 +1776,49 @@ static int problem_solve(lorb_ba_problem* pb, const lorb_ba_options* optp, int s
   int* h_active = reinterpret_cast<int*>(pb->hstate.as<uint8_t>() + sizeof(LMState) * (size_t)nw);
   // small windows: shared-memory privatised accumulation + one fused solve kernel
   const bool small = nmax <= 96;
-  const size_t smem_lin = small ? ((size_t)nmax * nmax + (size_t)(HCC + 12) * pb->maxC) * 8 : 0;
+  const int acc_mode = nmax <= DENSE_N ? 2 : (small ? 1 : 3);
+  const size_t wsm_bytes = (size_t)BA_THREADS * 18 * 8;
+  const size_t lin_small = (size_t)(HCC + 12) * pb->maxC;
+  const size_t smem_build_full =
+      acc_mode == 2 ? (lin_small + 2 + 2 * (size_t)DENSE_K * DENSE_N) * 8
+                    : (acc_mode == 1 ? ((size_t)nmax * nmax + lin_small) * 8 + wsm_bytes : 0);
+  const size_t smem_build_init =
+      acc_mode == 2 ? lin_small * 8 + 16
+                    : (acc_mode == 1 ? ((size_t)nmax * nmax + lin_small) * 8 + wsm_bytes : 0);
   const size_t smem_solve = ((size_t)nmax * nmax + 2 * (size_t)nmax) * 8;
-  if (small) {
-    LORB_CUDA_TRY(cudaFuncSetAttribute(ba_build_kernel<true, true>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_lin));
-    LORB_CUDA_TRY(cudaFuncSetAttribute(ba_build_kernel<false, true>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_lin));
+#define LORB_BUILD_ATTR(FULL_, ACC_, BYTES_)                                                  \
+  LORB_CUDA_TRY(cudaFuncSetAttribute(ba_build_kernel<FULL_, ACC_>,                             \
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BYTES_)))
+  if (acc_mode == 2) {
+    LORB_BUILD_ATTR(true, 2, smem_build_full);
+    LORB_BUILD_ATTR(false, 2, smem_build_init);
+  } else if (acc_mode == 1) {
+    LORB_BUILD_ATTR(true, 1, smem_build_full);
+    LORB_BUILD_ATTR(false, 1, smem_build_init);
+  }
+#undef LORB_BUILD_ATTR
+  if (small)
     LORB_CUDA_TRY(cudaFuncSetAttribute(ba_solve_small_kernel,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_solve));
-  }
   auto launch_build = [&](bool full, int force) -> int {
-    if (small) {
-      if (full)
-        LORB_LAUNCH(c, (ba_build_kernel<true, true>), grid_pts, BA_THREADS, smem_lin, dp, opt, force);
-      else
-        LORB_LAUNCH(c, (ba_build_kernel<false, true>), grid_pts, BA_THREADS, smem_lin, dp, opt, force);
+    const size_t sm = full ? smem_build_full : smem_build_init;
+#define LORB_BUILD(FULL_, ACC_) \
+  LORB_LAUNCH(c, (ba_build_kernel<FULL_, ACC_>), grid_pts, BA_THREADS, sm, dp, opt, force)
+    if (acc_mode == 2) {
+      if (full) LORB_BUILD(true, 2); else LORB_BUILD(false, 2);
+    } else if (acc_mode == 1) {
+      if (full) LORB_BUILD(true, 1); else LORB_BUILD(false, 1);
     } else {
-      if (full)
-        LORB_LAUNCH(c, (ba_build_kernel<true, false>), grid_pts, BA_THREADS, 0, dp, opt, force);
-      else
-        LORB_LAUNCH(c, (ba_build_kernel<false, false>), grid_pts, BA_THREADS, 0, dp, opt, force);
+      // large path: point side, then camera side and Schur products from the work lists
+      if (full) LORB_LAUNCH(c, (ba_build_kernel<true, 3>), grid_pts, BA_THREADS, 0, dp, opt, force);
+      else      LORB_LAUNCH(c, (ba_build_kernel<false, 3>), grid_pts, BA_THREADS, 0, dp, opt, force);
+      if (pb->max_cam_items > 0)
+        LORB_LAUNCH(c, ba_cam_rows_kernel, dim3((pb->max_cam_items + 7) / 8, nw), 256, 0, dp,
+                    full ? 1 : 0, force);
+      if (full && pb->max_pair_items > 0)
+        LORB_LAUNCH(c, ba_schur_pairs_kernel, dim3((pb->max_pair_items + 7) / 8, nw), 256, 0, dp);
     }
+#undef LORB_BUILD
     return LORB_OK;
   };
   // ---- initial evaluation (iteration 0)
@@ -1296,6 +1905,14 @@ static int problem_solve(lorb_ba_problem* pb, const lorb_ba_options* optp, int s
   return LORB_OK;
 }
 
+// The host-buffer entry points (lorb_ba_local, lorb_ba_local_batched) reuse one
+// problem object per ctx: its device / pinned buffers only ever grow, so a
+// steady stream of windows allocates nothing.
+static lorb_ba_problem* cached_problem(lorb_ctx* c) {
+  if (!c->ba_cache) c->ba_cache = new (std::nothrow) lorb_ba_problem();
+  return static_cast<lorb_ba_problem*>(c->ba_cache);
+}
+
 static void problem_free(lorb_ba_problem* pb) {
   if (!pb) return;
   if (pb->ctx) {
@@ -1306,9 +1923,17 @@ static void problem_free(lorb_ba_problem* pb) {
   pb->topo.release();
   pb->work.release();
   pb->descs.release();
+  pb->lists.release();
   pb->hstate.release();
   pb->counter.release();
   delete pb;
+}
+
+void ba_cache_free(lorb_ctx* c) {
+  if (c && c->ba_cache) {
+    problem_free(static_cast<lorb_ba_problem*>(c->ba_cache));
+    c->ba_cache = nullptr;
+  }
 }
 
 }  // namespace lorb
@@ -1374,14 +1999,20 @@ int lorb_ba_local(lorb_ctx* c, int C, double* cams, int P, double* pts, int O, c
                   const int* obs_pt, const float* obs_uv, int F, const int* fix_pt,
                   const float* fix_uv, const float* fix_rt, const float* K,
                   const lorb_ba_options* opt, lorb_ba_summary* summary) {
-  LORB_REQUIRE(opt, "options");
-  lorb_ba_problem* pb = nullptr;
-  LORB_TRY(lorb_ba_problem_create(c, C, cams, P, pts, O, obs_cam, obs_pt, obs_uv, F, fix_pt, fix_uv,
-                                  fix_rt, K, &pb));
-  int rc = lorb_ba_problem_solve(pb, opt, 0, summary);
-  if (rc == LORB_OK) rc = lorb_ba_problem_download(pb, cams, pts);
-  problem_free(pb);
-  return rc;
+  LORB_REQUIRE(c && opt && K, "ctx / options / K");
+  LORB_REQUIRE(C > 0 && P >= 0 && O >= 0 && F >= 0, "sizes");
+  LORB_REQUIRE(cams && (P == 0 || pts), "parameters");
+  LORB_REQUIRE(O == 0 || (obs_cam && obs_pt && obs_uv), "observations");
+  LORB_REQUIRE(F == 0 || (fix_pt && fix_uv && fix_rt), "fixed observations");
+  LORB_CUDA_TRY(cudaSetDevice(c->device));
+  lorb_ba_problem* pb = cached_problem(c);
+  if (!pb) return LORB_ERR_NOMEM;
+  std::vector<WindowSpec> ws(1);
+  ws[0] = WindowSpec{C, P, O, F, cams, pts, obs_cam, obs_pt, obs_uv, fix_pt, fix_uv, fix_rt};
+  LORB_TRY(problem_build(pb, c, ws, K));
+  LORB_TRY(problem_reset(pb));
+  LORB_TRY(problem_solve(pb, opt, 0, summary));
+  return lorb_ba_problem_download(pb, cams, pts);
 }
 
 int lorb_ba_local_batched(lorb_ctx* c, int n_windows, const int* cam_off, double* cams,
@@ -1408,14 +2039,12 @@ int lorb_ba_local_batched(lorb_ctx* c, int n_windows, const int* cam_off, double
     W.fix_uv = fix_off ? fix_uv + 2 * (size_t)fix_off[w] : nullptr;
     W.fix_rt = fix_off ? fix_rt + 6 * (size_t)fix_off[w] : nullptr;
   }
-  lorb_ba_problem* pb = new (std::nothrow) lorb_ba_problem();
+  lorb_ba_problem* pb = cached_problem(c);
   if (!pb) return LORB_ERR_NOMEM;
-  int rc = problem_build(pb, c, ws, K);
-  if (rc == LORB_OK) rc = problem_reset(pb);
-  if (rc == LORB_OK) rc = problem_solve(pb, opt, 0, summaries);
-  if (rc == LORB_OK) rc = lorb_ba_problem_download(pb, cams, pts);
-  problem_free(pb);
-  return rc;
+  LORB_TRY(problem_build(pb, c, ws, K));
+  LORB_TRY(problem_reset(pb));
+  LORB_TRY(problem_solve(pb, opt, 0, summaries));
+  return lorb_ba_problem_download(pb, cams, pts);
 }
 
 }  // extern "C"

@@ -62,6 +62,7 @@ struct lorb_ctx {
   lorb::Buf plan_pairs, plan_out;
   int plan_n_pairs = 0, plan_max_kf = 0;
   lorb::Dist* dist = nullptr;
+  void* ba_cache = nullptr;  // reusable lorb_ba_problem of the host-buffer BA calls (ba_local.cu)
 };
 
 namespace lorb {

@@ -1,0 +1,72 @@
+"""Launched by torchrun (one rank per GPU): the point-sharded large-BA path with
+the NCCL all-reduce of the reduced camera system against the
+single-GPU solve and the oracle.  Prints SHARDED_BA_OK on rank 0."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from lorb_slam_b200 import capi, sharding, synth  # noqa: E402
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = capi.Context(local)
+    uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        uid = torch.tensor(list(capi.Context.dist_unique_id()), dtype=torch.uint8, device="cuda")
+    dist.broadcast(uid, 0)
+    ctx.dist_init(bytes(uid.cpu().tolist()), rank, world)
+    # the communicator itself
+    r = ctx.dist_allreduce_f64(np.array([rank + 1.0, 2.0]))
+    assert np.allclose(r, [world * (world + 1) / 2, 2.0 * world])
+
+    for case, kw in (("blocked", dict(C=24, P=3000, obs_per_point=(5, 6, 7), traj_len=8.0)),
+                     ("small", dict(C=8, P=1500, obs_per_point=(4, 5)))):
+        pb = synth.make_ba_problem(31, **kw)
+        sh = sharding.shard_ba_by_point(pb, rank, world)
+        opt = capi.ba_options(max_num_iterations=8)
+        prob = ctx.ba_problem(sh)
+        s = prob.solve(opt, sharded=True)
+        cams, pts = prob.download()
+        prob.close()
+        # gather the point shards on rank 0
+        lo_hi = [sharding.window_slice(r_, world, len(pb["pts"])) for r_ in range(world)]
+        mx = max(h - l for l, h in lo_hi)
+        buf = torch.zeros((mx, 3), dtype=torch.float64, device="cuda")
+        buf[:len(pts)] = torch.from_numpy(pts).cuda()
+        allb = [torch.zeros_like(buf) for _ in range(world)]
+        dist.all_gather(allb, buf)
+        camt = torch.from_numpy(cams).cuda()
+        cam0 = camt.clone()
+        dist.broadcast(cam0, 0)
+        assert torch.equal(camt, cam0), "replicated cameras diverged between ranks"
+        if rank == 0:
+            full_pts = np.concatenate([allb[r_][:h - l].cpu().numpy() for r_, (l, h) in enumerate(lo_hi)])
+            c1, p1, s1 = ctx.ba_local(pb, opt)
+            np.testing.assert_allclose(cams, c1, rtol=1e-6, atol=1e-8)
+            np.testing.assert_allclose(full_pts, p1, rtol=1e-6, atol=1e-8)
+            assert s["iterations"] == s1["iterations"] and s["termination"] == s1["termination"]
+            np.testing.assert_allclose(s["final_cost"], s1["final_cost"], rtol=1e-9)
+            from oracle import ref
+            oc, op, so = ref.ba_local(pb, ref.ba_options(max_num_iterations=8))
+            np.testing.assert_allclose(cams, oc, rtol=1e-6, atol=1e-8)
+            np.testing.assert_allclose(full_pts, op, rtol=1e-6, atol=1e-8)
+            print("case", case, "ok", s)
+    dist.barrier()
+    ctx.dist_finalize()
+    ctx.close()
+    if rank == 0:
+        print("SHARDED_BA_OK")
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
