@@ -206,6 +206,28 @@ int lorb_search_proj_frame(lorb_ctx* ctx, const lorb_frame_view* cur, const floa
                            float th, int* out_kp_for_item, int* out_state_for_kp, int* n_matches,
                            long long* n_candidates);
 
+/*
+ * Frame::IsInFrustum (reference src/frame.cpp:425-494) with
+ * MapPoint::PredictScale (src/map_point.cpp:267-284) for n map points at once —
+ * the step that fills MapPoint::mTrack* before the local-map search
+ * (src/visual_odometry.cpp:176-195).
+ *   tcw [16]      row-major float mTcw
+ *   ow [3]        camera centre = translation column of mTcw.inv() (the caller
+ *                 computes it with the same cv::Mat::inv() the reference uses)
+ *   xw, normal    [n x 3] GetPos() / GetNormal()
+ *   min_dist/max_dist [n]  mfMinDistance / mfMaxDistance (0.8 / 1.2 applied inside)
+ *   log_scale_factor       Frame::mfLogScaleFactor, n_levels = mnScaleLevels
+ * Outputs (what IsInFrustum leaves in the MapPoint): in_view (mbTrackInView),
+ * proj_x/proj_y/proj_xr, level (mnTrackScaleLevel), view_cos.  Entries of
+ * points that are not in view are left untouched except in_view = 0.
+ */
+int lorb_frustum_project(lorb_ctx* ctx, const float* tcw, const float* ow, const lorb_intrinsics* K,
+                         float min_x, float max_x, float min_y, float max_y, int n, const float* xw,
+                         const float* normal, const float* min_dist, const float* max_dist,
+                         float viewing_cos_limit, float log_scale_factor, int n_levels,
+                         uint8_t* in_view, float* proj_x, float* proj_y, float* proj_xr, int* level,
+                         float* view_cos);
+
 /* ------------------------------------------------------- bundle adjustment */
 
 /* Solver options: the Ceres Solver::Options fields that shape the LM

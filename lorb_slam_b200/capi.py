@@ -24,7 +24,7 @@ EXPORTS = [
     "lorb_ctx_launch_count", "lorb_last_error", "lorb_version",
     "lorb_match_bf_crosscheck", "lorb_match_knn2", "lorb_match_sweep", "lorb_bank_upload",
     "lorb_match_sweep_resident", "lorb_sweep_plan_upload", "lorb_sweep_plan_run",
-    "lorb_sweep_plan_download", "lorb_sweep_plan_run_at", "lorb_search_proj_points", "lorb_search_proj_frame",
+    "lorb_sweep_plan_download", "lorb_sweep_plan_run_at", "lorb_search_proj_points", "lorb_search_proj_frame", "lorb_frustum_project",
     "lorb_ba_default_options", "lorb_ba_pose_only", "lorb_ba_local", "lorb_ba_local_batched",
     "lorb_ba_problem_create", "lorb_ba_problem_reset", "lorb_ba_problem_solve",
     "lorb_ba_problem_download", "lorb_ba_problem_destroy", "lorb_dist_get_unique_id",
@@ -261,6 +261,26 @@ class Context:
             C.c_float(th), _ptr(kfi), _ptr(sfk), C.byref(nm), C.byref(nc)))
         return dict(kp_for_item=kfi[:n_last], state_for_kp=sfk[:v.n_kp], n_matches=nm.value,
                     n_candidates=nc.value)
+
+    def frustum_project(self, fp):
+        n = int(fp["n"])
+        K = fp["K"]
+        Ks = Intrinsics(K["fx"], K["fy"], K["cx"], K["cy"], K["mbf"], K.get("mb", 0.0))
+        a = [_arr(fp["tcw"], np.float32), _arr(fp["ow"], np.float32), _arr(fp["xw"], np.float32),
+             _arr(fp["normal"], np.float32), _arr(fp["min_dist"], np.float32),
+             _arr(fp["max_dist"], np.float32)]
+        out = dict(in_view=np.zeros(max(1, n), np.uint8), proj_x=np.full(max(1, n), -7.0, np.float32),
+                   proj_y=np.full(max(1, n), -7.0, np.float32),
+                   proj_xr=np.full(max(1, n), -7.0, np.float32),
+                   level=np.full(max(1, n), -7, np.int32),
+                   view_cos=np.full(max(1, n), -7.0, np.float32))
+        _check(self._lib.lorb_frustum_project(
+            self._h, _ptr(a[0]), _ptr(a[1]), C.byref(Ks), C.c_float(fp["min_x"]),
+            C.c_float(fp["max_x"]), C.c_float(fp["min_y"]), C.c_float(fp["max_y"]), n, _ptr(a[2]),
+            _ptr(a[3]), _ptr(a[4]), _ptr(a[5]), C.c_float(fp["cos_limit"]), C.c_float(fp["log_sf"]),
+            int(fp["n_levels"]), _ptr(out["in_view"]), _ptr(out["proj_x"]), _ptr(out["proj_y"]),
+            _ptr(out["proj_xr"]), _ptr(out["level"]), _ptr(out["view_cos"])))
+        return {k: v[:n] for k, v in out.items()}
 
     # -- bundle adjustment
     def ba_pose_only(self, xw, uv, K, rt, opt=None):

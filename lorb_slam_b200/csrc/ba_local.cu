@@ -1076,6 +1076,121 @@ __global__ void __launch_bounds__(256)
   if (tid == 0 && !s_ok) st->solve_ok = 0;
 }
 
+// ---- dataflow triangular solves (one cooperative launch, one CTA per block row).
+// Forward: CTA k accumulates b_k - sum_{j<k} L_kj y_j as the y_j are flagged ready
+// (tile loads are issued before the flag wait: the factor is complete), solves its
+// diagonal block with one warp (vector in registers) and publishes y_k.  Backward
+// likewise from the last block row up with the transposed tiles.  The chain is
+// T sequential publish/consume hops instead of 2T block steps of a single CTA.
+__global__ void __launch_bounds__(256)
+    ba_trisolve_dataflow_kernel(const BADev* __restrict__ probs, int* __restrict__ flags, int T) {
+  const BADev p = probs[0];
+  LMState* st = p.st;
+  if (st->done) return;
+  __shared__ double Lt[2][NB][NB + 1];
+  __shared__ double vec[NB];   // the consumed y_j / x_i
+  __shared__ double part[8][NB];
+  __shared__ double sk[NB];    // running right-hand side of this block row
+  __shared__ double idg[NB];
+  const int n = p.n, tid = threadIdx.x;
+  const int k = blockIdx.x, k0 = k * NB;
+  if (k >= T) return;
+  const int kn = min(NB, n - k0);
+  int* yflag = flags;
+  int* xflag = flags + T;
+  double* yv = p.rhs;  // y overwrites b block by block; x overwrites y
+  auto load_tile = [&](int buf, int rb, int cb) {  // Lt[buf][r][c] = L[rb*32 + r][cb*32 + c]
+    for (int e = tid; e < NB * NB; e += 256) {
+      const int r = e >> 5, c = e & 31;
+      const int gr = rb * NB + r, gc = cb * NB + c;
+      Lt[buf][r][c] = (gr < n && gc < n && gc <= gr) ? __ldcg(&p.S[(size_t)gr * n + gc]) : 0.0;
+    }
+  };
+  if (tid < NB) {
+    sk[tid] = tid < kn ? __ldcg(&p.rhs[k0 + tid]) : 0.0;
+    idg[tid] = __ldcg(&p.dinv[(size_t)k * NB + tid]);
+  }
+  // ---------------- forward: L y = b
+  if (k > 0) load_tile(0, k, 0);
+  __syncthreads();
+  for (int j = 0; j < k; j++) {
+    if (j + 1 < k) load_tile((j + 1) & 1, k, j + 1);
+    flag_wait(&yflag[j]);
+    if (tid < NB) vec[tid] = __ldcg(&yv[j * NB + tid]);
+    __syncthreads();
+    {
+      const int r = tid & 31, q = tid >> 5;  // 8 column slices of 4
+      double a = 0;
+#pragma unroll
+      for (int c = 0; c < 4; c++) a += Lt[j & 1][r][4 * q + c] * vec[4 * q + c];
+      part[q][r] = a;
+    }
+    __syncthreads();
+    if (tid < NB) {
+      double a = 0;
+#pragma unroll
+      for (int q = 0; q < 8; q++) a += part[q][tid];
+      sk[tid] -= a;
+    }
+    __syncthreads();
+  }
+  load_tile(0, k, k);
+  __syncthreads();
+  if (tid < 32) {
+    double v = sk[tid];
+    for (int j = 0; j < kn; j++) {
+      const double yj = __shfl_sync(0xffffffffu, v, j) * idg[j];
+      if (tid == j) v = yj;
+      if (tid > j) v -= Lt[0][tid][j] * yj;
+    }
+    if (tid < kn) yv[k0 + tid] = v;
+    sk[tid] = tid < kn ? v : 0.0;
+    __threadfence();
+    __syncwarp();
+    if (tid == 0) atomicExch(&yflag[k], 1);
+  }
+  __syncthreads();
+  // ---------------- backward: L^T x = y   (sk holds y_k)
+  if (k + 1 < T) load_tile(1, T - 1, k);
+  __syncthreads();
+  for (int i = T - 1; i > k; i--) {
+    const int buf = (T - i) & 1;  // T-1 -> 1, T-2 -> 0, ...
+    if (i - 1 > k) load_tile(buf ^ 1, i - 1, k);
+    flag_wait(&xflag[i]);
+    if (tid < NB) vec[tid] = (i * NB + tid < n) ? __ldcg(&yv[i * NB + tid]) : 0.0;
+    __syncthreads();
+    {
+      const int c = tid & 31, q = tid >> 5;  // (L_ik^T x_i)[c] = sum_r L_ik[r][c] x_i[r]
+      double a = 0;
+#pragma unroll
+      for (int r = 0; r < 4; r++) a += Lt[buf][4 * q + r][c] * vec[4 * q + r];
+      part[q][c] = a;
+    }
+    __syncthreads();
+    if (tid < NB) {
+      double a = 0;
+#pragma unroll
+      for (int q = 0; q < 8; q++) a += part[q][tid];
+      sk[tid] -= a;
+    }
+    __syncthreads();
+  }
+  load_tile(0, k, k);
+  __syncthreads();
+  if (tid < 32) {
+    double v = sk[tid];
+    for (int j = kn - 1; j >= 0; j--) {
+      const double xj = __shfl_sync(0xffffffffu, v, j) * idg[j];
+      if (tid == j) v = xj;
+      if (tid < j) v -= Lt[0][j][tid] * xj;
+    }
+    if (tid < kn) yv[k0 + tid] = v;
+    __threadfence();
+    __syncwarp();
+    if (tid == 0) atomicExch(&xflag[k], 1);
+  }
+}
+
 // Trailing update A_ij -= L_ik L_jk^T for block pairs i >= j > kb (lower triangle).
 __global__ void __launch_bounds__(256) ba_chol_update_kernel(const BADev* __restrict__ probs, int kb, int nblk) {
   const BADev p = probs[blockIdx.y];
@@ -1733,17 +1848,24 @@ static int run_cholesky(lorb_ba_problem* pb) {
     coop_ok = (dev_coop && per_sm > 0 && !(e && atoi(e) == 0)) ? 1 : 0;
     coop_blocks = per_sm * c->sm_count;
   }
-  if (coop_ok && nw == 1) {
+  // (one CTA per block row of the solve must be co-resident as well)
+  if (coop_ok && nw == 1 && nblk <= c->sm_count) {
     const int n_tiles = nblk * (nblk + 1) / 2;
-    LORB_TRY(dev_reserve(c, 14, (size_t)nblk * nblk * 4));
+    LORB_TRY(dev_reserve(c, 14, ((size_t)nblk * nblk + 2 * (size_t)nblk) * 4));
     int* flags = c->d[14].as<int>();
-    LORB_CUDA_TRY(cudaMemsetAsync(flags, 0, (size_t)nblk * nblk * 4, c->stream));
+    LORB_CUDA_TRY(cudaMemsetAsync(flags, 0, ((size_t)nblk * nblk + 2 * (size_t)nblk) * 4, c->stream));
     int T = nblk;
     void* args[] = {(void*)&dp, (void*)&flags, (void*)&T};
     LORB_CUDA_TRY(cudaLaunchCooperativeKernel((void*)ba_chol_dataflow_kernel,
                                               dim3(std::min(n_tiles, coop_blocks)), dim3(256), args, 0,
                                               c->stream));
     c->launches++;
+    int* sflags = flags + (size_t)nblk * nblk;
+    void* args2[] = {(void*)&dp, (void*)&sflags, (void*)&T};
+    LORB_CUDA_TRY(cudaLaunchCooperativeKernel((void*)ba_trisolve_dataflow_kernel, dim3(nblk),
+                                              dim3(256), args2, 0, c->stream));
+    c->launches++;
+    return LORB_OK;
   } else {
     for (int kb = 0; kb < nblk; kb++) {
       LORB_LAUNCH(c, ba_chol_panel_kernel, dim3(nblk - kb, nw), NB * NB / 4, 0, dp, kb);

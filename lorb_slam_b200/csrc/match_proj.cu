@@ -520,6 +520,63 @@ __global__ void __launch_bounds__(1024)
   }
 }
 
+// ---- Frame::IsInFrustum + MapPoint::PredictScale, one thread per map point
+struct FrustumDev {
+  float tcw[16];
+  float ow[3];
+  float fx, fy, cx, cy, mbf;
+  float min_x, max_x, min_y, max_y;
+  float cos_limit, log_sf;
+  int n_levels;
+};
+
+__global__ void frustum_kernel(FrustumDev F, int n, const float* __restrict__ xw,
+                               const float* __restrict__ nrm, const float* __restrict__ dmin,
+                               const float* __restrict__ dmax, uint8_t* __restrict__ in_view,
+                               float* __restrict__ px, float* __restrict__ py, float* __restrict__ pxr,
+                               int* __restrict__ level, float* __restrict__ vcos) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  in_view[i] = 0;
+  const float P0 = xw[3 * i], P1 = xw[3 * i + 1], P2 = xw[3 * i + 2];
+  // Pc = mTcw * (P,1): OpenCV small gemm = sequential fp32 multiply-add, no FMA (frame.cpp:434-440)
+  float c[3];
+#pragma unroll
+  for (int r = 0; r < 3; r++) {
+    float t = __fmul_rn(F.tcw[4 * r], P0);
+    t = __fadd_rn(t, __fmul_rn(F.tcw[4 * r + 1], P1));
+    t = __fadd_rn(t, __fmul_rn(F.tcw[4 * r + 2], P2));
+    c[r] = __fadd_rn(t, __fmul_rn(F.tcw[4 * r + 3], 1.0f));
+  }
+  if (c[2] < 0.0f) return;                                                        // :443
+  const float invz = __fdiv_rn(1.0f, c[2]);                                       // :446
+  const float u = __fadd_rn(__fmul_rn(__fmul_rn(F.fx, c[0]), invz), F.cx);        // :447
+  const float v = __fadd_rn(__fmul_rn(__fmul_rn(F.fy, c[1]), invz), F.cy);        // :448
+  if (u < F.min_x || u > F.max_x) return;                                         // :450
+  if (v < F.min_y || v > F.max_y) return;                                         // :452
+  const float maxd = __fmul_rn(1.2f, dmax[i]), mind = __fmul_rn(0.8f, dmin[i]);   // map_point.cpp:209-217
+  const float o0 = __fsub_rn(P0, F.ow[0]), o1 = __fsub_rn(P1, F.ow[1]), o2 = __fsub_rn(P2, F.ow[2]);
+  // cv::norm(Point3f) accumulates in double (:462)
+  const float dist = (float)sqrt((double)o0 * o0 + (double)o1 * o1 + (double)o2 * o2);
+  if (dist < mind || dist > maxd) return;                                         // :464
+  const float dot = __fadd_rn(__fadd_rn(__fmul_rn(o0, nrm[3 * i]), __fmul_rn(o1, nrm[3 * i + 1])),
+                              __fmul_rn(o2, nrm[3 * i + 2]));
+  const float vc = __fdiv_rn(dot, dist);                                          // :472
+  if (vc < F.cos_limit) return;                                                   // :474
+  // PredictScale (map_point.cpp:267-284): ceil(log(mfMaxDistance/dist) / mfLogScaleFactor)
+  const float ratio = __fdiv_rn(dmax[i], dist);
+  const float lg = (float)log((double)ratio);  // logf; double log rounded = correctly rounded float
+  int ns = (int)ceilf(__fdiv_rn(lg, F.log_sf));
+  if (ns < 0) ns = 0;
+  else if (ns >= F.n_levels) ns = F.n_levels - 1;
+  in_view[i] = 1;
+  px[i] = u;
+  pxr[i] = __fsub_rn(u, __fmul_rn(F.mbf, invz));                                  // :487
+  py[i] = v;
+  level[i] = ns;
+  vcos[i] = vc;
+}
+
 // ------------------------------------------------------------------ host side
 struct Packer {  // lays host arrays out in one pinned block / one device block
   size_t off = 0;
@@ -672,6 +729,66 @@ static int run_search(lorb_ctx* c, const lorb_frame_view* fv, int n_pts, const u
 using namespace lorb;
 
 extern "C" {
+
+int lorb_frustum_project(lorb_ctx* c, const float* tcw, const float* ow, const lorb_intrinsics* K,
+                         float min_x, float max_x, float min_y, float max_y, int n, const float* xw,
+                         const float* normal, const float* min_dist, const float* max_dist,
+                         float viewing_cos_limit, float log_scale_factor, int n_levels,
+                         uint8_t* in_view, float* proj_x, float* proj_y, float* proj_xr, int* level,
+                         float* view_cos) {
+  LORB_REQUIRE(c && tcw && ow && K, "ctx / pose / intrinsics");
+  LORB_REQUIRE(n >= 0 && n_levels > 0, "sizes");
+  if (n == 0) return LORB_OK;
+  LORB_REQUIRE(xw && normal && min_dist && max_dist, "point arrays");
+  LORB_REQUIRE(in_view && proj_x && proj_y && proj_xr && level && view_cos, "outputs");
+  LORB_CUDA_TRY(cudaSetDevice(c->device));
+  Packer in, out;
+  const size_t i_xw = in.add((size_t)n * 12), i_n = in.add((size_t)n * 12), i_dmin = in.add((size_t)n * 4),
+               i_dmax = in.add((size_t)n * 4);
+  const size_t o_px = out.add((size_t)n * 4), o_py = out.add((size_t)n * 4), o_pxr = out.add((size_t)n * 4),
+               o_lvl = out.add((size_t)n * 4), o_vc = out.add((size_t)n * 4), o_in = out.add((size_t)n);
+  LORB_TRY(pin_reserve(c, 0, in.off));
+  LORB_TRY(pin_reserve(c, 1, out.off));
+  LORB_TRY(dev_reserve(c, 0, in.off));
+  LORB_TRY(dev_reserve(c, 2, out.off));
+  uint8_t* h = c->h[0].as<uint8_t>();
+  memcpy(h + i_xw, xw, (size_t)n * 12);
+  memcpy(h + i_n, normal, (size_t)n * 12);
+  memcpy(h + i_dmin, min_dist, (size_t)n * 4);
+  memcpy(h + i_dmax, max_dist, (size_t)n * 4);
+  // outputs of points that fail a test keep the caller's values: stage them too
+  uint8_t* ho = c->h[1].as<uint8_t>();
+  memcpy(ho + o_px, proj_x, (size_t)n * 4);
+  memcpy(ho + o_py, proj_y, (size_t)n * 4);
+  memcpy(ho + o_pxr, proj_xr, (size_t)n * 4);
+  memcpy(ho + o_lvl, level, (size_t)n * 4);
+  memcpy(ho + o_vc, view_cos, (size_t)n * 4);
+  uint8_t* d = c->d[0].as<uint8_t>();
+  uint8_t* dout = c->d[2].as<uint8_t>();
+  LORB_CUDA_TRY(cudaMemcpyAsync(d, h, in.off, cudaMemcpyHostToDevice, c->stream));
+  LORB_CUDA_TRY(cudaMemcpyAsync(dout, ho, out.off, cudaMemcpyHostToDevice, c->stream));
+  FrustumDev F;
+  memcpy(F.tcw, tcw, sizeof(F.tcw));
+  memcpy(F.ow, ow, sizeof(F.ow));
+  F.fx = K->fx; F.fy = K->fy; F.cx = K->cx; F.cy = K->cy; F.mbf = K->mbf;
+  F.min_x = min_x; F.max_x = max_x; F.min_y = min_y; F.max_y = max_y;
+  F.cos_limit = viewing_cos_limit;
+  F.log_sf = log_scale_factor;
+  F.n_levels = n_levels;
+  LORB_LAUNCH(c, frustum_kernel, (n + 255) / 256, 256, 0, F, n, (const float*)(d + i_xw),
+              (const float*)(d + i_n), (const float*)(d + i_dmin), (const float*)(d + i_dmax),
+              dout + o_in, (float*)(dout + o_px), (float*)(dout + o_py), (float*)(dout + o_pxr),
+              (int*)(dout + o_lvl), (float*)(dout + o_vc));
+  LORB_CUDA_TRY(cudaMemcpyAsync(ho, dout, out.off, cudaMemcpyDeviceToHost, c->stream));
+  LORB_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  memcpy(proj_x, ho + o_px, (size_t)n * 4);
+  memcpy(proj_y, ho + o_py, (size_t)n * 4);
+  memcpy(proj_xr, ho + o_pxr, (size_t)n * 4);
+  memcpy(level, ho + o_lvl, (size_t)n * 4);
+  memcpy(view_cos, ho + o_vc, (size_t)n * 4);
+  memcpy(in_view, ho + o_in, (size_t)n);
+  return LORB_OK;
+}
 
 int lorb_search_proj_points(lorb_ctx* c, const lorb_frame_view* frame, int n_pts,
                             const float* proj_x, const float* proj_y, const float* proj_xr,

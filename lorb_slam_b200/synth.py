@@ -206,6 +206,44 @@ def make_frame_pair(n_kp=2000, seed=0, width=640, height=480, motion="forward", 
     return cur, last
 
 
+def make_frustum_points(n=5000, seed=0, width=640, height=480):
+    """Inputs of Frame::IsInFrustum for n local map points (reference
+    src/frame.cpp:425-494): a camera pose, 3-D points in and around its frustum,
+    mean viewing directions and scale-invariance distance ranges."""
+    rng = np.random.default_rng(seed + 611953)
+    fx = fy = np.float32(458.0)
+    cx, cy = np.float32(width / 2), np.float32(height / 2)
+    mbf = np.float32(47.9)
+    rv = rng.normal(0, 0.2, 3)
+    R = rodrigues(rv)
+    t = rng.normal(0, 1.0, 3)
+    tcw = np.eye(4, dtype=np.float32)
+    tcw[:3, :3] = R.astype(np.float32)
+    tcw[:3, 3] = t.astype(np.float32)
+    ow = (-R.T @ t).astype(np.float32)
+    # points: 75 % inside a widened frustum, the rest anywhere (behind, outside, far)
+    u = rng.uniform(-0.3 * width, 1.3 * width, n)
+    v = rng.uniform(-0.3 * height, 1.3 * height, n)
+    z = np.where(rng.random(n) < 0.9, rng.uniform(0.5, 30.0, n), rng.uniform(-5.0, 0.5, n))
+    xc = np.stack([(u - cx) / fx * z, (v - cy) / fy * z, z], 1)
+    xw = ((xc - t) @ R).astype(np.float32)
+    d = np.linalg.norm(xw - ow, axis=1)
+    ref_d = d * rng.uniform(0.4, 2.5, n)               # distance at which the point was created
+    lvl = rng.integers(0, 8, n)
+    sf = scale_factors(8)
+    max_dist = (ref_d * sf[lvl]).astype(np.float32)     # UpdateNormalAndDepth, map_point.cpp:263-264
+    min_dist = (max_dist / sf[7]).astype(np.float32)
+    to_pt = (xw - ow) / np.maximum(d, 1e-6)[:, None]
+    nrm = to_pt + rng.normal(0, 0.5, (n, 3))
+    nrm = (nrm / np.linalg.norm(nrm, axis=1)[:, None]).astype(np.float32)
+    return dict(n=n, tcw=np.ascontiguousarray(tcw.reshape(16)), ow=ow,
+                K=dict(fx=float(fx), fy=float(fy), cx=float(cx), cy=float(cy), mbf=float(mbf)),
+                min_x=0.0, max_x=float(width), min_y=0.0, max_y=float(height),
+                xw=np.ascontiguousarray(xw), normal=np.ascontiguousarray(nrm), min_dist=min_dist,
+                max_dist=max_dist, cos_limit=0.5, log_sf=float(np.log(np.float32(1.2)).astype(np.float32)),
+                n_levels=8)
+
+
 # --------------------------------------------------------------------- BA
 
 K_DEFAULT = np.array([458.0, 458.0, 320.0, 240.0], np.float32)

@@ -529,6 +529,56 @@ int orc_search_proj_frame(int n_kp, const float* kx, const float* ky, const int*
   return nmatches;
 }
 
+/* ---- Frame::IsInFrustum src/frame.cpp:425-494 with
+ * MapPoint::PredictScale src/map_point.cpp:267-284, GetMin/MaxDistanceInvariance :209-217.
+ * ow = camera centre (translation of mTcw.inv(), given by the caller). */
+void orc_frustum_project(const float* tcw, const float* ow, float fx, float fy, float cx, float cy,
+                         float mbf, float min_x, float max_x, float min_y, float max_y, int n,
+                         const float* xw, const float* normal, const float* min_dist,
+                         const float* max_dist, float cos_limit, float log_sf, int n_levels,
+                         uint8_t* in_view, float* proj_x, float* proj_y, float* proj_xr, int* level,
+                         float* view_cos) {
+  for (int i = 0; i < n; i++) {
+    in_view[i] = 0;
+    const float* P = xw + 3 * (size_t)i;
+    float Pc[3];
+    for (int r = 0; r < 3; r++) { /* 4x4 * 4x1 float gemm, sequential, no FMA */
+      float t = tcw[4 * r] * P[0];
+      t = t + tcw[4 * r + 1] * P[1];
+      t = t + tcw[4 * r + 2] * P[2];
+      t = t + tcw[4 * r + 3] * 1.0f;
+      Pc[r] = t;
+    }
+    if (Pc[2] < 0.0f) continue;
+    const float invz = 1.0f / Pc[2];
+    const float u = fx * Pc[0] * invz + cx;
+    const float v = fy * Pc[1] * invz + cy;
+    if (u < min_x || u > max_x) continue;
+    if (v < min_y || v > max_y) continue;
+    const float maxDistance = 1.2f * max_dist[i];
+    const float minDistance = 0.8f * min_dist[i];
+    const float PO[3] = {P[0] - ow[0], P[1] - ow[1], P[2] - ow[2]};
+    const float dist =
+        (float)sqrt((double)PO[0] * PO[0] + (double)PO[1] * PO[1] + (double)PO[2] * PO[2]);
+    if (dist < minDistance || dist > maxDistance) continue;
+    const float* Pn = normal + 3 * (size_t)i;
+    const float viewCos = (PO[0] * Pn[0] + PO[1] * Pn[1] + PO[2] * Pn[2]) / dist;
+    if (viewCos < cos_limit) continue;
+    const float ratio = max_dist[i] / dist;
+    int nScale = (int)ceilf(logf(ratio) / log_sf);
+    if (nScale < 0)
+      nScale = 0;
+    else if (nScale >= n_levels)
+      nScale = n_levels - 1;
+    in_view[i] = 1;
+    proj_x[i] = u;
+    proj_xr[i] = u - mbf * invz;
+    proj_y[i] = v;
+    level[i] = nScale;
+    view_cos[i] = viewCos;
+  }
+}
+
 /* ---- multi-threaded driver for the CPU baseline of the sweep (bench.py
  * --impl reference): pairs are split over OpenMP threads. */
 void orc_sweep(const uint8_t* bank, int n_desc, const int* pair_a, const int* pair_b, int n_pairs,

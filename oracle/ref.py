@@ -169,6 +169,25 @@ def search_proj_frame(cur, last, th):
                 n_candidates=int(nc.value))
 
 
+def frustum_project(fp):
+    """fp: dict from lorb_slam_b200.synth.make_frustum_points."""
+    n = fp["n"]
+    K = fp["K"]
+    out = dict(in_view=np.zeros(n, np.uint8), proj_x=np.full(n, -7.0, np.float32),
+               proj_y=np.full(n, -7.0, np.float32), proj_xr=np.full(n, -7.0, np.float32),
+               level=np.full(n, -7, np.int32), view_cos=np.full(n, -7.0, np.float32))
+    _match().orc_frustum_project(
+        _p(fp["tcw"], C.c_float), _p(fp["ow"], C.c_float), C.c_float(K["fx"]), C.c_float(K["fy"]),
+        C.c_float(K["cx"]), C.c_float(K["cy"]), C.c_float(K["mbf"]), C.c_float(fp["min_x"]),
+        C.c_float(fp["max_x"]), C.c_float(fp["min_y"]), C.c_float(fp["max_y"]), n,
+        _p(fp["xw"], C.c_float), _p(fp["normal"], C.c_float), _p(fp["min_dist"], C.c_float),
+        _p(fp["max_dist"], C.c_float), C.c_float(fp["cos_limit"]), C.c_float(fp["log_sf"]),
+        int(fp["n_levels"]), _p(out["in_view"], C.c_uint8), _p(out["proj_x"], C.c_float),
+        _p(out["proj_y"], C.c_float), _p(out["proj_xr"], C.c_float), _p(out["level"], C.c_int),
+        _p(out["view_cos"], C.c_float))
+    return out
+
+
 def project_rt(tcw, xw):
     tcw, xw = _f32(tcw).reshape(16), _f32(xw).reshape(3)
     out = np.zeros(3, np.float32)

@@ -97,3 +97,22 @@ def test_frame_search_unprotected_overwrites(ctx):
     assert r["n_matches"] == o["n_matches"]
     taken = o["kp_for_item"][o["kp_for_item"] >= 0]
     assert len(taken) > len(np.unique(taken))  # some keypoint was taken twice
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_frustum_project(ctx, seed):
+    """SURVEY 8(f) rank 1: Frame::IsInFrustum + PredictScale, bit-exact vs the oracle."""
+    fp = synth.make_frustum_points(20000, seed)
+    g, o = ctx.frustum_project(fp), ref.frustum_project(fp)
+    assert 2000 < o["in_view"].sum() < 19000
+    for k in ("in_view", "proj_x", "proj_y", "proj_xr", "level", "view_cos"):
+        assert np.array_equal(g[k], o[k]), k
+    # its outputs feed the local-map search unchanged
+    fr = synth.make_frame(2000, seed=seed)
+    m = int(min(5000, fp["n"]))
+    pts = synth.make_proj_points(fr, m, seed=seed)
+    pts["proj_x"], pts["proj_y"], pts["proj_xr"] = g["proj_x"][:m], g["proj_y"][:m], g["proj_xr"][:m]
+    pts["level"] = np.clip(g["level"][:m], 0, 7).astype(np.int32)
+    pts["view_cos"], pts["active"] = g["view_cos"][:m], g["in_view"][:m]
+    r, q = ctx.search_proj_points(fr, pts, 1.0), ref.search_proj_points(fr, pts, 1.0)
+    assert np.array_equal(r["kp_for_point"], q["kp_for_point"]) and r["n_matches"] == q["n_matches"]
