@@ -228,6 +228,20 @@ int lorb_frustum_project(lorb_ctx* ctx, const float* tcw, const float* ow, const
                          uint8_t* in_view, float* proj_x, float* proj_y, float* proj_xr, int* level,
                          float* view_cos);
 
+/*
+ * MapPoint::ComputeDescriptor (reference src/map_point.cpp:69-129) for a batch
+ * of map points: point k owns the observation descriptors
+ * desc[offsets[k] .. offsets[k+1]) (in the iteration order of its observation
+ * map, bad frames already dropped); all pairwise Hamming distances, per row the
+ * element (int)(0.5*(m-1)) of the sorted row, the row with the smallest such
+ * median wins (first one on ties).  At most 128 observations per point.
+ *   out_best[k]    index (0-based inside the point's slice) of the chosen
+ *                  descriptor, -1 for a point without observations
+ *   out_median[k]  its median distance (may be NULL)
+ */
+int lorb_compute_descriptors(lorb_ctx* ctx, int n_points, const int* offsets, const uint8_t* desc,
+                             int* out_best, int* out_median);
+
 /* ------------------------------------------------------- bundle adjustment */
 
 /* Solver options: the Ceres Solver::Options fields that shape the LM

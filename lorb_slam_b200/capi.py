@@ -24,7 +24,7 @@ EXPORTS = [
     "lorb_ctx_launch_count", "lorb_last_error", "lorb_version",
     "lorb_match_bf_crosscheck", "lorb_match_knn2", "lorb_match_sweep", "lorb_bank_upload",
     "lorb_match_sweep_resident", "lorb_sweep_plan_upload", "lorb_sweep_plan_run",
-    "lorb_sweep_plan_download", "lorb_sweep_plan_run_at", "lorb_search_proj_points", "lorb_search_proj_frame", "lorb_frustum_project",
+    "lorb_sweep_plan_download", "lorb_sweep_plan_run_at", "lorb_search_proj_points", "lorb_search_proj_frame", "lorb_frustum_project", "lorb_compute_descriptors",
     "lorb_ba_default_options", "lorb_ba_pose_only", "lorb_ba_local", "lorb_ba_local_batched",
     "lorb_ba_problem_create", "lorb_ba_problem_reset", "lorb_ba_problem_solve",
     "lorb_ba_problem_download", "lorb_ba_problem_destroy", "lorb_dist_get_unique_id",
@@ -261,6 +261,15 @@ class Context:
             C.c_float(th), _ptr(kfi), _ptr(sfk), C.byref(nm), C.byref(nc)))
         return dict(kp_for_item=kfi[:n_last], state_for_kp=sfk[:v.n_kp], n_matches=nm.value,
                     n_candidates=nc.value)
+
+    def compute_descriptors(self, offsets, desc):
+        offsets = _arr(offsets, np.int32)
+        desc = _arr(desc, np.uint8).reshape(-1, 32)
+        n = len(offsets) - 1
+        best, med = np.zeros(max(1, n), np.int32), np.zeros(max(1, n), np.int32)
+        _check(self._lib.lorb_compute_descriptors(self._h, n, _ptr(offsets), _ptr(desc), _ptr(best),
+                                                  _ptr(med)))
+        return best[:n], med[:n]
 
     def frustum_project(self, fp):
         n = int(fp["n"])

@@ -287,6 +287,66 @@ __global__ void knn2_finalize_kernel(const uint32_t* __restrict__ part, int nq, 
   out_pass[qi] = pass ? 1 : 0;
 }
 
+// ---- MapPoint::ComputeDescriptor (reference src/map_point.cpp:69-129), one CTA per map point
+constexpr int CD_MAX = 128;
+__global__ void __launch_bounds__(128)
+    compute_descriptor_kernel(int n_points, const int* __restrict__ offsets,
+                              const uint4* __restrict__ desc, int* __restrict__ out_best,
+                              int* __restrict__ out_median) {
+  extern __shared__ __align__(16) unsigned char cd_raw[];
+  __shared__ uint32_t s_key[4];
+  const int k = blockIdx.x;
+  if (k >= n_points) return;
+  const int s0 = offsets[k], m = offsets[k + 1] - s0, tid = threadIdx.x;
+  if (m <= 0) {
+    if (tid == 0) {
+      out_best[k] = -1;
+      if (out_median) out_median[k] = -1;
+    }
+    return;
+  }
+  uint4* D = reinterpret_cast<uint4*>(cd_raw);                       // m x 2 uint4
+  uint16_t* dist = reinterpret_cast<uint16_t*>(cd_raw + CD_MAX * 32);  // m x m
+  for (int e = tid; e < 2 * m; e += 128) D[e] = desc[2 * (size_t)s0 + e];
+  __syncthreads();
+  for (int e = tid; e < m * m; e += 128) {
+    const int i = e / m, j = e % m;
+    const uint4 a0 = D[2 * i], a1 = D[2 * i + 1], b0 = D[2 * j], b1 = D[2 * j + 1];
+    const uint32_t q[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    const uint32_t t[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    dist[e] = (uint16_t)hamming256_popc8(q, t);
+  }
+  __syncthreads();
+  // row i: element (int)(0.5*(m-1)) of the sorted row, by counting selection
+  const int kth = (int)(0.5 * (double)(m - 1));
+  uint32_t key = KEY_NONE;
+  if (tid < m) {
+    const uint16_t* row = dist + (size_t)tid * m;
+    int median = 0;
+    for (int j = 0; j < m; j++) {
+      const int v = row[j];
+      int less = 0, eq = 0;
+      for (int j2 = 0; j2 < m; j2++) {
+        less += row[j2] < v;
+        eq += row[j2] == v;
+      }
+      if (less <= kth && kth < less + eq) {
+        median = v;
+        break;
+      }
+    }
+    key = ((uint32_t)median << KEY_IDX_BITS) | (uint32_t)tid;  // min = smallest median, first row
+  }
+  key = __reduce_min_sync(0xffffffffu, key);
+  if ((tid & 31) == 0) s_key[tid >> 5] = key;
+  __syncthreads();
+  if (tid == 0) {
+    const uint32_t best = min(min(s_key[0], s_key[1]), min(s_key[2], s_key[3]));
+    out_best[k] = (int)(best & KEY_IDX_MASK);
+    if (out_median) out_median[k] = (int)(best >> KEY_IDX_BITS);
+  }
+}
+
 // ------------------------------------------------------------------ sweep
 constexpr int SWEEP_THREADS = 512;
 
@@ -600,6 +660,47 @@ int lorb_match_knn2(lorb_ctx* c, const uint8_t* q, int nq, const uint8_t* t, int
   memcpy(out_idx, res, (size_t)nq * 8);
   memcpy(out_dist, res + 2 * (size_t)nq, (size_t)nq * 8);
   memcpy(out_pass, reinterpret_cast<const uint8_t*>(res + 4 * (size_t)nq), (size_t)nq);
+  return LORB_OK;
+}
+
+int lorb_compute_descriptors(lorb_ctx* c, int n_points, const int* offsets, const uint8_t* desc,
+                             int* out_best, int* out_median) {
+  LORB_REQUIRE(c, "ctx");
+  LORB_REQUIRE(n_points >= 0, "n_points");
+  if (n_points == 0) return LORB_OK;
+  LORB_REQUIRE(offsets && out_best, "offsets / out_best");
+  LORB_REQUIRE(offsets[0] == 0, "offsets[0] must be 0");
+  int mmax = 0;
+  for (int k = 0; k < n_points; k++) {
+    const int m = offsets[k + 1] - offsets[k];
+    LORB_REQUIRE(m >= 0, "offsets must be non-decreasing");
+    LORB_REQUIRE(m <= CD_MAX, "more than 128 observations for one map point");
+    mmax = std::max(mmax, m);
+  }
+  const int total = offsets[n_points];
+  LORB_REQUIRE(total == 0 || desc, "desc");
+  LORB_CUDA_TRY(cudaSetDevice(c->device));
+  const size_t b_off = ((size_t)(n_points + 1) * 4 + 255) & ~(size_t)255;
+  const size_t up = b_off + (size_t)total * 32, down = (size_t)n_points * 8;
+  LORB_TRY(pin_reserve(c, 0, up));
+  LORB_TRY(pin_reserve(c, 1, down));
+  LORB_TRY(dev_reserve(c, 0, up));
+  LORB_TRY(dev_reserve(c, 2, down));
+  uint8_t* h = c->h[0].as<uint8_t>();
+  memcpy(h, offsets, (size_t)(n_points + 1) * 4);
+  if (total) memcpy(h + b_off, desc, (size_t)total * 32);
+  uint8_t* d = c->d[0].as<uint8_t>();
+  LORB_CUDA_TRY(cudaMemcpyAsync(d, h, up, cudaMemcpyHostToDevice, c->stream));
+  const size_t smem = (size_t)CD_MAX * 32 + (size_t)mmax * mmax * 2 + 16;
+  LORB_CUDA_TRY(cudaFuncSetAttribute(compute_descriptor_kernel,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int* d_best = c->d[2].as<int>();
+  LORB_LAUNCH(c, compute_descriptor_kernel, n_points, 128, smem, n_points, (const int*)d,
+              (const uint4*)(d + b_off), d_best, d_best + n_points);
+  LORB_CUDA_TRY(cudaMemcpyAsync(c->h[1].p, c->d[2].p, down, cudaMemcpyDeviceToHost, c->stream));
+  LORB_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  memcpy(out_best, c->h[1].p, (size_t)n_points * 4);
+  if (out_median) memcpy(out_median, c->h[1].as<int>() + n_points, (size_t)n_points * 4);
   return LORB_OK;
 }
 

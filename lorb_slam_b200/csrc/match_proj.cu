@@ -21,6 +21,9 @@
 //                            reached in <= n+1 sweeps, in practice 3-6.
 // Float arithmetic that decides candidate sets uses explicit _rn intrinsics so
 // nothing is contracted into FMA (the reference is -O0 x86-64 code).
+#include <cooperative_groups.h>
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "common.cuh"
@@ -357,41 +360,71 @@ __global__ void __launch_bounds__(256)
 
 // ---- 3. claim resolution.  MODE 0: points (best/second + ratio, :265-312);
 // MODE 1: frame (best only + rotation histogram, :139-215).
+//
+// One warp evaluates one point: lanes read consecutive candidates (coalesced),
+// keys (dist << 32 | position) are min-reduced over the warp.  The reference's
+// sequential best/second bookkeeping (:289-301) is reproduced exactly from
+// three order statistics.  Let c* be the FIRST position of the minimum distance
+// (strict '<' keeps the first).  When c* arrived it demoted the best of the
+// prefix A = [0,c*) into the "second" slot; afterwards only a strictly smaller
+// distance from the suffix Z = (c*,m) can replace it.  Hence
+//     second = first-min(Z) if dist(first-min(Z)) < dist(first-min(A)) else first-min(A)
+// (with (256, level -1) for an empty A), and bestLevel2 is that element's octave.
+constexpr int RG = 8;  // lanes per point in the claim resolution (4 points per warp in flight)
+__device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v) {
+#pragma unroll
+  for (int o = RG / 2; o > 0; o >>= 1) {
+    const unsigned long long u = __shfl_xor_sync(0xffffffffu, v, o);
+    v = u < v ? u : v;
+  }
+  return v;
+}
+
 template <int MODE>
-__device__ __forceinline__ int choose(const uint32_t* __restrict__ cand, int s, int n,
-                                      const int* __restrict__ fp, int k,
-                                      const int* __restrict__ kp_octave) {
-  int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
-  for (int c = 0; c < n; c++) {
+__device__ __forceinline__ int choose_warp(const uint32_t* __restrict__ cand, int s, int n,
+                                           const int* fp /* rewritten between sweeps: no .nc loads */, int k,
+                                           const int* __restrict__ kp_octave, int lane) {
+  const unsigned long long NONE = ~0ull;
+  unsigned long long kbest = NONE;
+  for (int c = lane; c < n; c += RG) {
     const uint32_t rec = cand[s + c];
-    const int kp = (int)(rec & KEY_IDX_MASK);
-    if (fp[kp] < k) continue;  // held by a map point with mnObs>0 at this point's turn
-    const int dist = (int)(rec >> KEY_IDX_BITS);
-    if (MODE == 0) {
-      if (dist < bestDist) {
-        bestDist2 = bestDist;
-        bestDist = dist;
-        bestLevel2 = bestLevel;
-        bestLevel = kp_octave[kp];
-        bestIdx = kp;
-      } else if (dist < bestDist2) {
-        bestLevel2 = kp_octave[kp];
-        bestDist2 = dist;
-      }
-    } else {
-      if (dist < bestDist) {
-        bestDist = dist;
-        bestIdx = kp;
-      }
-    }
+    if (fp[rec & KEY_IDX_MASK] < k) continue;  // held by a map point with mnObs>0 at this point's turn
+    if ((rec >> KEY_IDX_BITS) >= 256u) continue;  // 256 never beats the initial bestDist / bestDist2
+    const unsigned long long key = ((unsigned long long)(rec >> KEY_IDX_BITS) << 32) | (unsigned)c;
+    kbest = key < kbest ? key : kbest;
   }
-  if (bestDist <= LORB_TH_HIGH) {
-    if (MODE == 0) {
-      if (bestLevel == bestLevel2 && (double)bestDist > 0.8 * (double)bestDist2) return -1;  // :307
-    }
-    return bestIdx;
+  kbest = warp_min_u64(kbest);
+  // (no early return before the last shuffle: the other groups of the warp still need this one)
+  const bool none = kbest == NONE || (int)(kbest >> 32) > LORB_TH_HIGH;
+  const int bestDist = none ? 256 : (int)(kbest >> 32);
+  const int cstar = none ? -1 : (int)(kbest & 0xffffffffu);
+  const int bestIdx = none ? -1 : (int)(cand[s + cstar] & KEY_IDX_MASK);
+  if (MODE == 1) return bestIdx;
+  unsigned long long ka = NONE, kz = NONE;
+  for (int c = lane; c < n; c += RG) {
+    if (c == cstar) continue;
+    const uint32_t rec = cand[s + c];
+    if (fp[rec & KEY_IDX_MASK] < k) continue;
+    if ((rec >> KEY_IDX_BITS) >= 256u) continue;
+    const unsigned long long key = ((unsigned long long)(rec >> KEY_IDX_BITS) << 32) | (unsigned)c;
+    if (c < cstar) ka = key < ka ? key : ka;
+    else kz = key < kz ? key : kz;
   }
-  return -1;
+  ka = warp_min_u64(ka);
+  kz = warp_min_u64(kz);
+  if (none) return -1;
+  int bestDist2 = 256, bestLevel2 = -1;
+  if (ka != NONE) {
+    bestDist2 = (int)(ka >> 32);
+    bestLevel2 = kp_octave[cand[s + (int)(ka & 0xffffffffu)] & KEY_IDX_MASK];
+  }
+  if (kz != NONE && (int)(kz >> 32) < bestDist2) {
+    bestDist2 = (int)(kz >> 32);
+    bestLevel2 = kp_octave[cand[s + (int)(kz & 0xffffffffu)] & KEY_IDX_MASK];
+  }
+  const int bestLevel = kp_octave[bestIdx];
+  if (bestLevel == bestLevel2 && (double)bestDist > 0.8 * (double)bestDist2) return -1;  // :307
+  return bestIdx;
 }
 
 // SMEM = true: the two claim arrays and the octaves live in shared memory
@@ -431,14 +464,21 @@ __global__ void __launch_bounds__(1024)
     for (int i = tid; i < n_kp; i += blockDim.x) fp_new[i] = claim_obs[i] > 0 ? -1 : INF;
     __syncthreads();
     int changed = 0;
-    for (int k = tid; k < n_pts; k += blockDim.x) {
-      const int n = seg_len[k];
-      const int c = n > 0 ? choose<MODE>(cand, seg_start[k], n, fp_cur, k, kp_octave) : -1;
-      if (c != choice[k]) {
-        choice[k] = c;
-        changed = 1;
+    {
+      // RG lanes per point; the loop is warp-uniform so every lane reaches the shuffles
+      const int lane = tid & (RG - 1), ngroups = blockDim.x / RG, per_warp = 32 / RG;
+      for (int base = (tid >> 5) * per_warp; base < n_pts; base += ngroups) {
+        const int k = base + ((tid & 31) / RG);
+        const int n = k < n_pts ? seg_len[k] : 0;
+        const int c = choose_warp<MODE>(cand, n > 0 ? seg_start[k] : 0, n, fp_cur, k, kp_octave, lane);
+        if (lane == 0 && k < n_pts) {
+          if (c != choice[k]) {
+            choice[k] = c;
+            changed = 1;
+          }
+          if (c >= 0 && mp_nobs[k] > 0) atomicMin(&fp_new[c], k);
+        }
       }
-      if (c >= 0 && mp_nobs[k] > 0) atomicMin(&fp_new[c], k);
     }
     if (changed) s_changed = 1;
     __syncthreads();
@@ -577,6 +617,131 @@ __global__ void frustum_kernel(FrustumDev F, int n, const float* __restrict__ xw
   vcos[i] = vc;
 }
 
+// ---- 3b. the same claim resolution as one COOPERATIVE multi-CTA launch: the
+// per-sweep evaluation is latency-bound (a handful of dependent loads per
+// point), so it is spread over all SMs (8 lanes per point, every point in
+// flight at once) with a grid-wide barrier between the phases of a sweep.
+// scratch: int[8] = {changed[3], count, ind1, ind2, ind3, sweeps} + int hist[30]
+template <int MODE>
+__global__ void __launch_bounds__(256)
+    resolve_coop_kernel(int n_kp, int n_pts, const int* __restrict__ claim_obs,
+                        const int* __restrict__ kp_octave, const float* __restrict__ kp_angle,
+                        const int* __restrict__ mp_nobs, const float* __restrict__ last_angle,
+                        const int* __restrict__ seg_start, const int* __restrict__ seg_len,
+                        const uint32_t* __restrict__ cand, int* fp_a, int* fp_b, int* choice,
+                        int* out_for_kp, int* res, int* scratch) {
+  namespace cg = cooperative_groups;
+  cg::grid_group grid = cg::this_grid();
+  const int INF = 0x7fffffff;
+  const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
+  int* changed = scratch;       // [3]
+  int* count = scratch + 3;
+  int* ind = scratch + 4;       // [3]
+  int* hist = scratch + 8;      // [30]
+  for (int i = gtid; i < n_kp; i += gsize) {
+    fp_a[i] = claim_obs[i] > 0 ? -1 : INF;
+    out_for_kp[i] = -1;
+  }
+  for (int k = gtid; k < n_pts; k += gsize) choice[k] = -2;
+  if (gtid < 8 + LORB_HISTO_LENGTH) scratch[gtid] = 0;
+  int* fp_cur = fp_a;
+  int* fp_new = fp_b;
+  int sweeps = 0;
+  for (;;) {
+    for (int i = gtid; i < n_kp; i += gsize) fp_new[i] = claim_obs[i] > 0 ? -1 : INF;
+    if (gtid == 0) changed[(sweeps + 1) % 3] = 0;
+    grid.sync();
+    {
+      const int lane = gtid & (RG - 1), ngroups = gsize / RG, per_warp = 32 / RG;
+      for (int base = (gtid >> 5) * per_warp; base < n_pts; base += ngroups) {
+        const int k = base + ((gtid & 31) / RG);
+        const int n = k < n_pts ? seg_len[k] : 0;
+        const int c = choose_warp<MODE>(cand, n > 0 ? seg_start[k] : 0, n, fp_cur, k, kp_octave, lane);
+        if (lane == 0 && k < n_pts) {
+          if (c != choice[k]) {
+            choice[k] = c;
+            changed[sweeps % 3] = 1;
+          }
+          if (c >= 0 && mp_nobs[k] > 0) atomicMin(&fp_new[c], k);
+        }
+      }
+    }
+    grid.sync();
+    const int any = *reinterpret_cast<volatile int*>(&changed[sweeps % 3]);
+    sweeps++;
+    int* t = fp_cur;
+    fp_cur = fp_new;
+    fp_new = t;
+    if (!any) break;
+  }
+  // final holder of a keypoint = last point that took it
+  auto bin_of = [&](int k, int c) {
+    float rot = __fsub_rn(last_angle[k], kp_angle[c]);  // :181-188
+    if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+    int bin = (int)roundf(__fmul_rn(rot, (float)LORB_HISTO_LENGTH / 360.0f));
+    if (bin == LORB_HISTO_LENGTH) bin = 0;
+    return bin;
+  };
+  int cnt = 0;
+  for (int k = gtid; k < n_pts; k += gsize) {
+    const int c = choice[k];
+    if (c >= 0) {
+      cnt++;
+      atomicMax(&out_for_kp[c], k);
+      if (MODE == 1) atomicAdd(&hist[bin_of(k, c)], 1);
+    }
+  }
+  cnt = __reduce_add_sync(0xffffffffu, cnt);
+  if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(count, cnt);
+  grid.sync();
+  if (MODE == 1) {
+    if (gtid == 0) {  // ComputeThreeMaxima :387-428
+      int max1 = 0, max2 = 0, max3 = 0, i1 = -1, i2 = -1, i3 = -1;
+      for (int i = 0; i < LORB_HISTO_LENGTH; i++) {
+        const int sz = hist[i];
+        if (sz > max1) {
+          max3 = max2; max2 = max1; max1 = sz;
+          i3 = i2; i2 = i1; i1 = i;
+        } else if (sz > max2) {
+          max3 = max2; max2 = sz;
+          i3 = i2; i2 = i;
+        } else if (sz > max3) {
+          max3 = sz;
+          i3 = i;
+        }
+      }
+      if ((float)max2 < __fmul_rn(0.1f, (float)max1)) {
+        i2 = -1;
+        i3 = -1;
+      } else if ((float)max3 < __fmul_rn(0.1f, (float)max1)) {
+        i3 = -1;
+      }
+      ind[0] = i1; ind[1] = i2; ind[2] = i3;
+    }
+    grid.sync();
+    const int i1 = *reinterpret_cast<volatile int*>(&ind[0]), i2 = *reinterpret_cast<volatile int*>(&ind[1]),
+              i3 = *reinterpret_cast<volatile int*>(&ind[2]);
+    int dropped = 0;
+    for (int k = gtid; k < n_pts; k += gsize) {
+      const int c = choice[k];
+      if (c >= 0) {
+        const int bin = bin_of(k, c);
+        if (bin != i1 && bin != i2 && bin != i3) {
+          out_for_kp[c] = -2;  // :204-214
+          dropped++;
+        }
+      }
+    }
+    dropped = __reduce_add_sync(0xffffffffu, dropped);
+    if ((threadIdx.x & 31) == 0 && dropped) atomicSub(count, dropped);
+    grid.sync();
+  }
+  if (gtid == 0) {
+    res[0] = *reinterpret_cast<volatile int*>(count);
+    res[1] = sweeps;
+  }
+}
+
 // ------------------------------------------------------------------ host side
 struct Packer {  // lays host arrays out in one pinned block / one device block
   size_t off = 0;
@@ -630,7 +795,7 @@ static int run_search(lorb_ctx* c, const lorb_frame_view* fv, int n_pts, const u
   const size_t w_cellof = ws.add((size_t)n_kp * 4), w_cstart = ws.add((size_t)(NCELL + 1) * 4),
                w_citems = ws.add((size_t)n_kp * 4), w_segs = ws.add((size_t)n_pts * 4),
                w_segl = ws.add((size_t)n_pts * 4), w_fpa = ws.add((size_t)n_kp * 4),
-               w_fpb = ws.add((size_t)n_kp * 4), w_counter = ws.add(16);
+               w_fpb = ws.add((size_t)n_kp * 4), w_counter = ws.add(16), w_scratch = ws.add(256);
   // outputs (one D2H): res[4] | choice[n_pts] | out_for_kp[n_kp] | counter
   Packer op;
   const size_t r_res = op.add(16), r_choice = op.add((size_t)n_pts * 4),
@@ -690,18 +855,45 @@ static int run_search(lorb_ctx* c, const lorb_frame_view* fv, int n_pts, const u
       LORB_TRY(launch_cand.launch(c, f, up.d + o_extra, d_mpd, d_segs, d_segl, d_cand,
                                   (int)std::min<size_t>(cand_cap, 0x7fffffff), d_counter));
     }
-    const size_t res_smem = (size_t)n_kp * 12;
-    if (res_smem <= 160 * 1024) {
-      LORB_CUDA_TRY(cudaFuncSetAttribute(resolve_kernel<MODE, true>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)std::max<size_t>(res_smem, 16)));
-      LORB_LAUNCH(c, (resolve_kernel<MODE, true>), 1, 1024, res_smem, n_kp, n_pts, f.claim_obs,
-                  f.octave, f.angle, d_nobs, d_lang, d_segs, d_segl, d_cand, d_fpa, d_fpb, d_choice,
-                  d_forkp, d_res);
+    static int coop_blocks[2] = {-1, -1};  // per MODE: co-resident CTAs of the cooperative kernel
+    if (coop_blocks[MODE] < 0) {
+      int dev_coop = 0, per_sm = 0;
+      cudaDeviceGetAttribute(&dev_coop, cudaDevAttrCooperativeLaunch, c->device);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, resolve_coop_kernel<MODE>, 256, 0);
+      const char* e = getenv("LORB_RESOLVE_COOP");
+      coop_blocks[MODE] = (dev_coop && per_sm > 0 && !(e && atoi(e) == 0)) ? per_sm * c->sm_count : 0;
+    }
+    if (coop_blocks[MODE] > 0) {
+      int* d_scratch = reinterpret_cast<int*>(wsd + w_scratch);
+      const int want = std::max(1, (int)(((size_t)std::max(n_pts, 1) * RG + 255) / 256));
+      const int grid = std::min(want, coop_blocks[MODE]);
+      int a_nkp = n_kp, a_npts = n_pts;
+      const int* a_claim = f.claim_obs;
+      const int* a_oct = f.octave;
+      const float* a_ang = f.angle;
+      const uint32_t* a_cand = d_cand;
+      const int* a_segs = d_segs;
+      const int* a_segl = d_segl;
+      void* args[] = {&a_nkp, &a_npts, &a_claim, &a_oct, &a_ang, (void*)&d_nobs, (void*)&d_lang,
+                      &a_segs, &a_segl, &a_cand, &d_fpa, &d_fpb, &d_choice, &d_forkp, &d_res,
+                      &d_scratch};
+      LORB_CUDA_TRY(cudaLaunchCooperativeKernel((void*)resolve_coop_kernel<MODE>, dim3(grid),
+                                                dim3(256), args, 0, c->stream));
+      c->launches++;
     } else {
-      LORB_LAUNCH(c, (resolve_kernel<MODE, false>), 1, 1024, 0, n_kp, n_pts, f.claim_obs, f.octave,
-                  f.angle, d_nobs, d_lang, d_segs, d_segl, d_cand, d_fpa, d_fpb, d_choice, d_forkp,
-                  d_res);
+      const size_t res_smem = (size_t)n_kp * 12;
+      if (res_smem <= 160 * 1024) {
+        LORB_CUDA_TRY(cudaFuncSetAttribute(resolve_kernel<MODE, true>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)std::max<size_t>(res_smem, 16)));
+        LORB_LAUNCH(c, (resolve_kernel<MODE, true>), 1, 1024, res_smem, n_kp, n_pts, f.claim_obs,
+                    f.octave, f.angle, d_nobs, d_lang, d_segs, d_segl, d_cand, d_fpa, d_fpb, d_choice,
+                    d_forkp, d_res);
+      } else {
+        LORB_LAUNCH(c, (resolve_kernel<MODE, false>), 1, 1024, 0, n_kp, n_pts, f.claim_obs, f.octave,
+                    f.angle, d_nobs, d_lang, d_segs, d_segl, d_cand, d_fpa, d_fpb, d_choice, d_forkp,
+                    d_res);
+      }
     }
     LORB_CUDA_TRY(cudaMemcpyAsync(outd + r_cnt, d_counter, 16, cudaMemcpyDeviceToDevice, c->stream));
     LORB_CUDA_TRY(cudaMemcpyAsync(c->h[1].p, outd, op.off, cudaMemcpyDeviceToHost, c->stream));
@@ -714,6 +906,7 @@ static int run_search(lorb_ctx* c, const lorb_frame_view* fv, int n_pts, const u
     }
     const int* res = reinterpret_cast<const int*>(ho + r_res);
     *n_matches = res[0];
+    if (getenv("LORB_DEBUG")) fprintf(stderr, "[lorb] projection search: %d claim sweeps\n", res[1]);
     if (n_candidates)
       *n_candidates = (long long)reinterpret_cast<const unsigned long long*>(ho + r_cnt)[1];
     if (n_pts) memcpy(out_for_point, ho + r_choice, (size_t)n_pts * 4);

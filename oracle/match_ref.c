@@ -579,6 +579,40 @@ void orc_frustum_project(const float* tcw, const float* ow, float fx, float fy, 
   }
 }
 
+/* ---- MapPoint::ComputeDescriptor src/map_point.cpp:69-129 for one
+ * map point with m observation descriptors.  Returns the chosen index, writes its median. */
+static int cmp_int(const void* a, const void* b) { return *(const int*)a - *(const int*)b; }
+int orc_compute_descriptor(const uint8_t* desc, int m, int* median_out) {
+  if (m <= 0) {
+    *median_out = -1;
+    return -1;
+  }
+  int* distances = (int*)malloc(sizeof(int) * (size_t)m * m);
+  int* v = (int*)malloc(sizeof(int) * (size_t)m);
+  for (int i = 0; i < m; i++) {
+    distances[i * m + i] = 0;
+    for (int j = i + 1; j < m; j++) {
+      const int d = orc_hamming256(desc + 32 * (size_t)i, desc + 32 * (size_t)j); /* :88-100 */
+      distances[i * m + j] = d;
+      distances[j * m + i] = d;
+    }
+  }
+  int bestIdx = 0, bestMedian = 0x7fffffff;
+  for (int i = 0; i < m; i++) {
+    memcpy(v, distances + (size_t)i * m, sizeof(int) * (size_t)m);
+    qsort(v, (size_t)m, sizeof(int), cmp_int);
+    const int median = v[(size_t)(0.5 * (m - 1))]; /* :115 */
+    if (median < bestMedian) {
+      bestMedian = median;
+      bestIdx = i;
+    }
+  }
+  free(distances);
+  free(v);
+  *median_out = bestMedian;
+  return bestIdx;
+}
+
 /* ---- multi-threaded driver for the CPU baseline of the sweep (bench.py
  * --impl reference): pairs are split over OpenMP threads. */
 void orc_sweep(const uint8_t* bank, int n_desc, const int* pair_a, const int* pair_b, int n_pairs,

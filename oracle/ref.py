@@ -188,6 +188,19 @@ def frustum_project(fp):
     return out
 
 
+def compute_descriptors(offsets, desc):
+    offsets, desc = _i32(offsets), _u8(desc).reshape(-1, 32)
+    n = len(offsets) - 1
+    best, med = np.zeros(n, np.int32), np.zeros(n, np.int32)
+    for k in range(n):
+        m = C.c_int(0)
+        sl = np.ascontiguousarray(desc[offsets[k]:offsets[k + 1]])
+        best[k] = _match().orc_compute_descriptor(_p(sl, C.c_uint8) if len(sl) else None, len(sl),
+                                                  C.byref(m))
+        med[k] = m.value
+    return best, med
+
+
 def project_rt(tcw, xw):
     tcw, xw = _f32(tcw).reshape(16), _f32(xw).reshape(3)
     out = np.zeros(3, np.float32)

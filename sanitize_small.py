@@ -1,0 +1,24 @@
+"""Small pass over every C-ABI entry point (for compute-sanitizer memcheck)."""
+import sys
+sys.path.insert(0, ".")
+import numpy as np
+from lorb_slam_b200 import capi, synth
+c = capi.Context(0)
+rng = np.random.default_rng(0)
+q, t = synth.descriptors_uniform(300, rng), synth.descriptors_uniform(421, rng)
+c.match_bf_crosscheck(q, t); c.match_bf_crosscheck(q, t, 1); c.match_knn2(q, t)
+bank = synth.kf_bank(5, 333, seed=1); pa, pb = synth.all_pairs(5)
+c.match_sweep(bank, pa, pb)
+fr = synth.make_frame(700, 1, stereo=True, claimed_frac=0.1); pts = synth.make_proj_points(fr, 900, 1, nobs=(0, 1))
+c.search_proj_points(fr, pts, 1.0); c.search_proj_points(fr, pts, 15.0)
+cur, last = synth.make_frame_pair(600, 1); c.search_proj_frame(cur, last, 15.0)
+c.frustum_project(synth.make_frustum_points(1000, 1))
+po = synth.make_pose_only(1, 200); c.ba_pose_only(po["xw"], po["uv"], po["K"], po["rt"])
+opt = capi.ba_options(max_num_iterations=4)
+c.ba_local(synth.make_ba_problem(1, C=4, P=150, obs_per_point=(3, 4), fixed_frac=0.1), opt)   # dense path
+c.ba_local(synth.make_ba_problem(2, C=14, P=300, obs_per_point=(4, 5, 9)), opt)                # privatised path
+c.ba_local(synth.make_ba_problem(3, C=20, P=400, obs_per_point=(4, 5, 11), traj_len=6.0), opt)  # work lists + dataflow
+pbs = [synth.make_ba_problem(10 + i, C=3 + i, P=60 + 10 * i, obs_per_point=(3,)) for i in range(3)]
+c.ba_local_batched(synth.batch_windows(pbs), opt)
+c.close()
+print("SANITIZE_PASS_DONE")

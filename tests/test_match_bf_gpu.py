@@ -128,3 +128,25 @@ def test_sweep_many_pairs_resident(ctx):
     ctx.sweep_plan_run()
     k2, m2, d2 = ctx.sweep_plan_download()
     assert np.array_equal(k2, ok[:50]) and np.array_equal(m2, om[:50]) and np.array_equal(d2, od[:50])
+
+
+def test_compute_descriptors(ctx):
+    """SURVEY 8(f) rank 4: MapPoint::ComputeDescriptor batched, bit-exact vs the oracle."""
+    rng = np.random.default_rng(17)
+    sizes = np.concatenate([[0, 1, 2, 3, 128], rng.integers(1, 40, 400)]).astype(np.int32)
+    offsets = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    desc = np.zeros((offsets[-1], 32), np.uint8)
+    for k, m in enumerate(sizes):
+        if m == 0:
+            continue
+        base = synth.descriptors_uniform(1, rng)
+        if k % 3 == 0:   # tie-heavy points
+            desc[offsets[k]:offsets[k + 1]] = synth.descriptors_tie_stress(m, rng, 1, 3)
+        else:
+            desc[offsets[k]:offsets[k + 1]] = synth.descriptors_noisy_copy(np.repeat(base, m, 0), rng, 0.1)
+    best, med = ctx.compute_descriptors(offsets, desc)
+    ob, om = ref.compute_descriptors(offsets, desc)
+    assert np.array_equal(best, ob) and np.array_equal(med, om)
+    assert best[0] == -1 and best[1] == 0
+    with pytest.raises(Exception):
+        ctx.compute_descriptors(np.array([0, 129], np.int32), np.zeros((129, 32), np.uint8))
