@@ -336,6 +336,16 @@ int lorb_ba_problem_create(lorb_ctx* ctx, int C, const double* cams, int P, cons
                            const int* obs_cam, const int* obs_pt, const float* obs_uv, int F,
                            const int* fix_pt, const float* fix_uv, const float* fix_rt,
                            const float* K, lorb_ba_problem** out);
+/* Batched form of the above: n_windows independent windows in the offset-array
+ * layout of lorb_ba_local_batched; lorb_ba_problem_solve then fills
+ * summary[0..n_windows) and lorb_ba_problem_download returns the concatenated
+ * cameras / points. */
+int lorb_ba_problem_create_batched(lorb_ctx* ctx, int n_windows, const int* cam_off,
+                                   const double* cams, const int* pt_off, const double* pts,
+                                   const int* obs_off, const int* obs_cam, const int* obs_pt,
+                                   const float* obs_uv, const int* fix_off, const int* fix_pt,
+                                   const float* fix_uv, const float* fix_rt, const float* K,
+                                   lorb_ba_problem** out);
 /* Restore the parameters uploaded at creation (so a bench can re-solve). */
 int lorb_ba_problem_reset(lorb_ba_problem* p);
 /* Run LM on the resident problem.  If the ctx has a distributed group

@@ -26,7 +26,7 @@ EXPORTS = [
     "lorb_match_sweep_resident", "lorb_sweep_plan_upload", "lorb_sweep_plan_run",
     "lorb_sweep_plan_download", "lorb_sweep_plan_run_at", "lorb_search_proj_points", "lorb_search_proj_frame", "lorb_frustum_project", "lorb_compute_descriptors",
     "lorb_ba_default_options", "lorb_ba_pose_only", "lorb_ba_local", "lorb_ba_local_batched",
-    "lorb_ba_problem_create", "lorb_ba_problem_reset", "lorb_ba_problem_solve",
+    "lorb_ba_problem_create", "lorb_ba_problem_create_batched", "lorb_ba_problem_reset", "lorb_ba_problem_solve",
     "lorb_ba_problem_download", "lorb_ba_problem_destroy", "lorb_dist_get_unique_id",
     "lorb_dist_init", "lorb_dist_finalize", "lorb_dist_allreduce_f64", "lorb_microbench_popc",
 ]
@@ -337,6 +337,9 @@ class Context:
     def ba_problem(self, pb):
         return BAProblem(self, pb)
 
+    def ba_problem_batched(self, bt):
+        return BAProblem(self, None, batch=bt)
+
     # -- multi-GPU
     @staticmethod
     def dist_unique_id():
@@ -366,9 +369,25 @@ class Context:
 class BAProblem:
     """Device-resident local-BA problem (lorb_ba_problem_*)."""
 
-    def __init__(self, ctx, pb):
+    def __init__(self, ctx, pb, batch=None):
         self._ctx = ctx
         self._lib = ctx._lib
+        self.nw = 1
+        if batch is not None:
+            bt = batch
+            cams, pts = _arr(bt["cams"], np.float64), _arr(bt["pts"], np.float64)
+            co, po, oo = (_arr(bt[k], np.int32) for k in ("cam_off", "pt_off", "obs_off"))
+            oc, op = _arr(bt["obs_cam"], np.int32), _arr(bt["obs_pt"], np.int32)
+            ouv = _arr(bt["obs_uv"], np.float32)
+            K = _arr(bt["K"], np.float32).reshape(4)
+            self.C, self.P, self.nw = len(cams), len(pts), int(bt["n_windows"])
+            h = C.c_void_p()
+            _check(self._lib.lorb_ba_problem_create_batched(
+                ctx._h, self.nw, _ptr(co), _ptr(cams), _ptr(po), _ptr(pts), _ptr(oo), _ptr(oc),
+                _ptr(op), _ptr(ouv), C.c_void_p(0), C.c_void_p(0), C.c_void_p(0), C.c_void_p(0),
+                _ptr(K), C.byref(h)))
+            self._h = h
+            return
         cams, pts = _arr(pb["cams"], np.float64), _arr(pb["pts"], np.float64)
         oc, op = _arr(pb["obs_cam"], np.int32), _arr(pb["obs_pt"], np.int32)
         ouv = _arr(pb["obs_uv"], np.float32)
@@ -388,6 +407,10 @@ class BAProblem:
 
     def solve(self, opt=None, sharded=False):
         opt = opt or ba_options()
+        if self.nw > 1:
+            sums = (BASummary * self.nw)()
+            _check(self._lib.lorb_ba_problem_solve(self._h, C.byref(opt), 0, sums))
+            return [x.as_dict() for x in sums]
         s = BASummary()
         _check(self._lib.lorb_ba_problem_solve(self._h, C.byref(opt), int(bool(sharded)),
                                                C.byref(s)))

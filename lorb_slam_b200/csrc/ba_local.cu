@@ -1513,7 +1513,7 @@ struct lorb_ba_problem {
   int nw = 0;
   std::vector<lorb::BADev> h_dev;     // host copies of the per-window descriptors
   std::vector<int> h_cam_off, h_pt_off;
-  lorb::Buf params, topo, work, descs, hstate, counter, lists;
+  lorb::Buf params, topo, work, descs, hstate, counter, lists, stage;
   int max_cam_items = 0, max_pair_items = 0;
   double *cams0 = nullptr, *pts0 = nullptr;  // initial parameters of all windows
   size_t cam_doubles = 0, pt_doubles = 0;
@@ -1590,10 +1590,21 @@ static int problem_build(lorb_ba_problem* pb, lorb_ctx* c, const std::vector<Win
   pb->cam_doubles = totC * 6;
   pb->pt_doubles = totP * 3;
   // ---- host staging of the topology (CSR by point per window)
-  std::vector<int> h_ptr(tot_ptr), h_cam(std::max<size_t>(tot_obs, 1));
-  std::vector<float2> h_uv(std::max<size_t>(tot_obs, 1));
-  std::vector<double> h_fix(std::max<size_t>(tot_fix, 1) * 12);
-  std::vector<double> h_cams(pb->cam_doubles), h_pts(std::max<size_t>(pb->pt_doubles, 1));
+  // staged in pinned memory owned by the problem (grow-only): the uploads below are
+  // true async DMA and a cached problem allocates nothing in steady state
+  const size_t sb_ptr = al(tot_ptr * 4), sb_cam = al(std::max<size_t>(tot_obs, 1) * 4),
+               sb_uv = al(std::max<size_t>(tot_obs, 1) * 8), sb_fix = al(std::max<size_t>(tot_fix, 1) * 96),
+               sb_cams = al(std::max<size_t>(pb->cam_doubles, 1) * 8),
+               sb_pts = al(std::max<size_t>(pb->pt_doubles, 1) * 8);
+  pb->stage.pinned = true;
+  LORB_TRY(pb->stage.reserve(sb_ptr + sb_cam + sb_uv + sb_fix + sb_cams + sb_pts));
+  uint8_t* sg = pb->stage.as<uint8_t>();
+  int* h_ptr = reinterpret_cast<int*>(sg);
+  int* h_cam = reinterpret_cast<int*>(sg + sb_ptr);
+  float2* h_uv = reinterpret_cast<float2*>(sg + sb_ptr + sb_cam);
+  double* h_fix = reinterpret_cast<double*>(sg + sb_ptr + sb_cam + sb_uv);
+  double* h_cams = reinterpret_cast<double*>(sg + sb_ptr + sb_cam + sb_uv + sb_fix);
+  double* h_pts = reinterpret_cast<double*>(sg + sb_ptr + sb_cam + sb_uv + sb_fix + sb_cams);
   std::vector<size_t> o_ptr(nw), o_obs(nw), o_fix(nw);
   // large-path work lists (windows with 6C > 96), concatenated over windows
   std::vector<int> h_obs_pt, h_cam_obs;
@@ -1611,21 +1622,31 @@ static int problem_build(lorb_ba_problem* pb, lorb_ctx* c, const std::vector<Win
       o_fix[w] = f;
       int* ptr = &h_ptr[a];
       for (int i = 0; i <= W.P; i++) ptr[i] = 0;
+      bool sorted = W.F == 0;  // fast path: window observations already grouped by ascending point
       for (int i = 0; i < W.O; i++) {
         LORB_REQUIRE(W.obs_pt[i] >= 0 && W.obs_pt[i] < W.P && W.obs_cam[i] >= 0 && W.obs_cam[i] < W.C,
                      "observation index out of range");
         ptr[W.obs_pt[i] + 1]++;
+        if (i > 0 && W.obs_pt[i] < W.obs_pt[i - 1]) sorted = false;
       }
       for (int i = 0; i < W.F; i++) {
         LORB_REQUIRE(W.fix_pt[i] >= 0 && W.fix_pt[i] < W.P, "fixed observation point out of range");
         ptr[W.fix_pt[i] + 1]++;
       }
       for (int i = 0; i < W.P; i++) ptr[i + 1] += ptr[i];
-      std::vector<int> fill(ptr, ptr + W.P);
-      for (int i = 0; i < W.O; i++) {
-        const int d = fill[W.obs_pt[i]]++;
-        h_cam[b + d] = W.obs_cam[i];
-        h_uv[b + d] = make_float2(W.obs_uv[2 * i], W.obs_uv[2 * i + 1]);
+      std::vector<int> fill;
+      if (sorted) {  // the CSR order is the input order: two block copies
+        if (W.O) {
+          memcpy(&h_cam[b], W.obs_cam, (size_t)W.O * 4);
+          memcpy(&h_uv[b], W.obs_uv, (size_t)W.O * 8);
+        }
+      } else {
+        fill.assign(ptr, ptr + W.P);
+        for (int i = 0; i < W.O; i++) {
+          const int d = fill[W.obs_pt[i]]++;
+          h_cam[b + d] = W.obs_cam[i];
+          h_uv[b + d] = make_float2(W.obs_uv[2 * i], W.obs_uv[2 * i + 1]);
+        }
       }
       for (int i = 0; i < W.F; i++) {
         const int d = fill[W.fix_pt[i]]++;
@@ -1803,12 +1824,12 @@ static int problem_build(lorb_ba_problem* pb, lorb_ctx* c, const std::vector<Win
   LORB_TRY(pb->hstate.reserve(sizeof(LMState) * (size_t)nw + 64));
   cudaStream_t s = c->stream;
   LORB_CUDA_TRY(cudaMemcpyAsync(pb->descs.p, pb->h_dev.data(), sizeof(BADev) * (size_t)nw, cudaMemcpyHostToDevice, s));
-  LORB_CUDA_TRY(cudaMemcpyAsync(pb->cams0, h_cams.data(), pb->cam_doubles * 8, cudaMemcpyHostToDevice, s));
-  LORB_CUDA_TRY(cudaMemcpyAsync(pb->pts0, h_pts.data(), pb->pt_doubles * 8, cudaMemcpyHostToDevice, s));
-  LORB_CUDA_TRY(cudaMemcpyAsync(d_ptr, h_ptr.data(), tot_ptr * 4, cudaMemcpyHostToDevice, s));
-  LORB_CUDA_TRY(cudaMemcpyAsync(d_ocam, h_cam.data(), tot_obs * 4, cudaMemcpyHostToDevice, s));
-  LORB_CUDA_TRY(cudaMemcpyAsync(d_uv, h_uv.data(), tot_obs * 8, cudaMemcpyHostToDevice, s));
-  LORB_CUDA_TRY(cudaMemcpyAsync(d_fix, h_fix.data(), tot_fix * 96, cudaMemcpyHostToDevice, s));
+  LORB_CUDA_TRY(cudaMemcpyAsync(pb->cams0, h_cams, pb->cam_doubles * 8, cudaMemcpyHostToDevice, s));
+  LORB_CUDA_TRY(cudaMemcpyAsync(pb->pts0, h_pts, pb->pt_doubles * 8, cudaMemcpyHostToDevice, s));
+  LORB_CUDA_TRY(cudaMemcpyAsync(d_ptr, h_ptr, tot_ptr * 4, cudaMemcpyHostToDevice, s));
+  LORB_CUDA_TRY(cudaMemcpyAsync(d_ocam, h_cam, tot_obs * 4, cudaMemcpyHostToDevice, s));
+  LORB_CUDA_TRY(cudaMemcpyAsync(d_uv, h_uv, tot_obs * 8, cudaMemcpyHostToDevice, s));
+  LORB_CUDA_TRY(cudaMemcpyAsync(d_fix, h_fix, tot_fix * 96, cudaMemcpyHostToDevice, s));
   LORB_CUDA_TRY(cudaStreamSynchronize(s));  // host staging vectors go out of scope
   return LORB_OK;
 }
@@ -2046,6 +2067,7 @@ static void problem_free(lorb_ba_problem* pb) {
   pb->work.release();
   pb->descs.release();
   pb->lists.release();
+  pb->stage.release();
   pb->hstate.release();
   pb->counter.release();
   delete pb;
@@ -2137,15 +2159,13 @@ int lorb_ba_local(lorb_ctx* c, int C, double* cams, int P, double* pts, int O, c
   return lorb_ba_problem_download(pb, cams, pts);
 }
 
-int lorb_ba_local_batched(lorb_ctx* c, int n_windows, const int* cam_off, double* cams,
-                          const int* pt_off, double* pts, const int* obs_off, const int* obs_cam,
-                          const int* obs_pt, const float* obs_uv, const int* fix_off,
-                          const int* fix_pt, const float* fix_uv, const float* fix_rt,
-                          const float* K, const lorb_ba_options* opt, lorb_ba_summary* summaries) {
-  LORB_REQUIRE(c && opt && K, "ctx / options / K");
+static int batched_specs(std::vector<WindowSpec>& ws, int n_windows, const int* cam_off,
+                         const double* cams, const int* pt_off, const double* pts,
+                         const int* obs_off, const int* obs_cam, const int* obs_pt,
+                         const float* obs_uv, const int* fix_off, const int* fix_pt,
+                         const float* fix_uv, const float* fix_rt) {
   LORB_REQUIRE(n_windows > 0 && cam_off && pt_off && obs_off && cams, "window offsets");
-  LORB_CUDA_TRY(cudaSetDevice(c->device));
-  std::vector<WindowSpec> ws((size_t)n_windows);
+  ws.resize((size_t)n_windows);
   for (int w = 0; w < n_windows; w++) {
     WindowSpec& W = ws[w];
     W.C = cam_off[w + 1] - cam_off[w];
@@ -2161,6 +2181,42 @@ int lorb_ba_local_batched(lorb_ctx* c, int n_windows, const int* cam_off, double
     W.fix_uv = fix_off ? fix_uv + 2 * (size_t)fix_off[w] : nullptr;
     W.fix_rt = fix_off ? fix_rt + 6 * (size_t)fix_off[w] : nullptr;
   }
+  return LORB_OK;
+}
+
+int lorb_ba_problem_create_batched(lorb_ctx* c, int n_windows, const int* cam_off,
+                                   const double* cams, const int* pt_off, const double* pts,
+                                   const int* obs_off, const int* obs_cam, const int* obs_pt,
+                                   const float* obs_uv, const int* fix_off, const int* fix_pt,
+                                   const float* fix_uv, const float* fix_rt, const float* K,
+                                   lorb_ba_problem** out) {
+  LORB_REQUIRE(c && out && K, "ctx / out / K");
+  LORB_CUDA_TRY(cudaSetDevice(c->device));
+  std::vector<WindowSpec> ws;
+  LORB_TRY(batched_specs(ws, n_windows, cam_off, cams, pt_off, pts, obs_off, obs_cam, obs_pt, obs_uv,
+                         fix_off, fix_pt, fix_uv, fix_rt));
+  lorb_ba_problem* pb = new (std::nothrow) lorb_ba_problem();
+  if (!pb) return LORB_ERR_NOMEM;
+  int rc = problem_build(pb, c, ws, K);
+  if (rc == LORB_OK) rc = problem_reset(pb);
+  if (rc != LORB_OK) {
+    problem_free(pb);
+    return rc;
+  }
+  *out = pb;
+  return LORB_OK;
+}
+
+int lorb_ba_local_batched(lorb_ctx* c, int n_windows, const int* cam_off, double* cams,
+                          const int* pt_off, double* pts, const int* obs_off, const int* obs_cam,
+                          const int* obs_pt, const float* obs_uv, const int* fix_off,
+                          const int* fix_pt, const float* fix_uv, const float* fix_rt,
+                          const float* K, const lorb_ba_options* opt, lorb_ba_summary* summaries) {
+  LORB_REQUIRE(c && opt && K, "ctx / options / K");
+  LORB_CUDA_TRY(cudaSetDevice(c->device));
+  std::vector<WindowSpec> ws;
+  LORB_TRY(batched_specs(ws, n_windows, cam_off, cams, pt_off, pts, obs_off, obs_cam, obs_pt, obs_uv,
+                         fix_off, fix_pt, fix_uv, fix_rt));
   lorb_ba_problem* pb = cached_problem(c);
   if (!pb) return LORB_ERR_NOMEM;
   LORB_TRY(problem_build(pb, c, ws, K));

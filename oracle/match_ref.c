@@ -22,6 +22,7 @@
  * no FMA contraction may happen in the float code below.
  */
 #include <math.h>
+#include <omp.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -612,6 +613,11 @@ int orc_compute_descriptor(const uint8_t* desc, int m, int* median_out) {
   *median_out = bestMedian;
   return bestIdx;
 }
+
+/* Launchers such as torchrun export OMP_NUM_THREADS=1; the CPU baseline must use every host
+ * thread it can, so the caller sets the count explicitly. */
+void orc_set_num_threads(int n) { omp_set_num_threads(n > 0 ? n : 1); }
+int orc_get_max_threads(void) { return omp_get_max_threads(); }
 
 /* ---- multi-threaded driver for the CPU baseline of the sweep (bench.py
  * --impl reference): pairs are split over OpenMP threads. */

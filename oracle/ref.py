@@ -102,6 +102,12 @@ def knn2(q, t):
     return idx[:len(q)], dist[:len(q)]
 
 
+def set_num_threads(n):
+    """Thread count of the OpenMP loops (sweep, batched BA); torchrun exports OMP_NUM_THREADS=1."""
+    _match().orc_set_num_threads(int(n))
+    return int(_match().orc_get_max_threads())
+
+
 def sweep(bank, pair_a, pair_b):
     """bank [n_kf, n_desc, 32] -> (kept, matches, min_dist) per pair; OpenMP over pairs."""
     bank = _u8(bank)
