@@ -156,12 +156,19 @@ __device__ __forceinline__ double block_max(double v, double* red) {
 //      segmented reductions in registers over host-built lists - no atomics in
 //      any inner loop
 //   2  n <= 64 (the 10-keyframe windows of BASELINE configs 3/4): H_cc / g_c / rhs
-//      as in 1, but the Schur products are a dense contraction per CTA:
-//      Y = W H_pp^-1 and W of 32 points are staged as dense 64 x 96 tiles in
-//      shared memory and S -= Y W^T is accumulated in registers (4x4 per thread),
-//      flushed once per CTA.  No per-block atomics at all in the inner loop.
+//      and the Schur products are dense contractions per CTA, with NO atomics in
+//      the inner loop: the Jacobian rows of 32 points are stored into a dense
+//      64 x 64 tile (H_cc entries = dot products of its columns, g_c against a
+//      residual tile), then Y = W H_pp^-1 and W into dense 64 x 96 tiles and
+//      S -= Y W^T accumulates in registers (4x4 per thread); every thread owns
+//      its outputs for the whole kernel and flushes them once.  (Windows in
+//      which a point is observed twice by the same camera take variant 1.)
 constexpr int DENSE_N = 64;   // padded reduced-system size of the dense path
 constexpr int DENSE_K = 96;   // 32 points x 3 per block round
+constexpr int DENSE_K2 = 64;  // 32 points x 2 residual rows per block round
+constexpr int DENSE_RC = 16;  // padded camera count of the residual tile
+__constant__ int c_up_a[21] = {0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 4, 4, 5};
+__constant__ int c_up_b[21] = {0, 1, 2, 3, 4, 5, 1, 2, 3, 4, 5, 2, 3, 4, 5, 3, 4, 5, 4, 5, 5};
 
 template <bool FULL, int ACC>
 __global__ void __launch_bounds__(BA_THREADS)
@@ -173,23 +180,25 @@ __global__ void __launch_bounds__(BA_THREADS)
   __shared__ double red[BA_THREADS / 32];
   extern __shared__ __align__(16) double dsm[];
   // dynamic shared memory carve-up
-  //   ACC 0: [Wsm 256x18]   ACC 1: [lin copy][Wsm 256x18]   ACC 2: [Hcc|gc|rhs][Yd 96x64][Wd 96x64]
+  //   ACC 0: [Wsm 256x18]   ACC 1: [lin copy][Wsm 256x18]
+  //   ACC 2: [Yd 96x64 (aliased by the J tile 64x64)][Wd 96x64][Rd 64x16][gv 96]
   const int lin_n = p.n * p.n + (HCC + 12) * p.C;
-  const int small_n = (HCC + 12) * p.C;
   double* slin = dsm;
   double (*Wsm)[18] = reinterpret_cast<double (*)[18]>(ACC == 1 ? dsm + lin_n : dsm);
-  double* Yd = dsm + ((small_n + 1) & ~1);  // 16-byte aligned for the double2 tile loads
+  double* Yd = dsm;
   double* Wd = Yd + DENSE_K * DENSE_N;
+  double* Rd = Wd + DENSE_K * DENSE_N;
+  double* gv = Rd + DENSE_K2 * DENSE_RC;
+  constexpr int DENSE_SMEM = 2 * DENSE_K * DENSE_N + DENSE_K2 * DENSE_RC + DENSE_K;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, gl = lane & 7, gw = lane >> 3;
   if (ACC == 1) {
     for (int i = tid; i < lin_n; i += BA_THREADS) slin[i] = 0.0;
   } else if (ACC == 2) {
-    for (int i = tid; i < ((small_n + 1) & ~1) + (FULL ? 2 * DENSE_K * DENSE_N : 0); i += BA_THREADS)
-      slin[i] = 0.0;
+    for (int i = tid; i < DENSE_SMEM; i += BA_THREADS) dsm[i] = 0.0;
   }
   if (ACC != 0) __syncthreads();
   double* const accS = ACC == 1 ? slin : p.S;
-  double* const accH = ACC == 1 ? slin + (size_t)p.n * p.n : (ACC == 2 ? slin : p.Hcc);
+  double* const accH = ACC == 1 ? slin + (size_t)p.n * p.n : p.Hcc;
   double* const accG = accH + HCC * p.C;
   double* const accR = accG + 6 * p.C;
   const int cur = st->cur;
@@ -199,6 +208,30 @@ __global__ void __launch_bounds__(BA_THREADS)
   const double radius = st->radius;
   const int n = p.n;
   double cost_acc = 0, gmax_acc = 0, xn_acc = 0, bad_acc = 0;
+  // ACC 2: outputs owned by this thread for the whole kernel: two entries of
+  // [H_cc (21 per camera) | g_c (6 per camera)], one row of the Schur rhs, a 4x4 tile of Y W^T
+  double hown[2] = {0.0, 0.0}, rown = 0.0;
+  int own_col_a[2] = {-1, -1}, own_col_b[2] = {0, 0};  // tile columns to multiply (b = -1: residual tile)
+  int own_cam[2] = {0, 0};
+  if (ACC == 2) {
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+      const int ent = tid + q * BA_THREADS;
+      if (ent < (HCC + 6) * p.C) {
+        if (ent < HCC * p.C) {
+          const int c2 = ent / HCC, idx = ent % HCC;
+          own_cam[q] = c2;
+          own_col_a[q] = 6 * c2 + c_up_a[idx];
+          own_col_b[q] = 6 * c2 + c_up_b[idx];
+        } else {
+          const int e2 = ent - HCC * p.C;
+          own_cam[q] = e2 / 6;
+          own_col_a[q] = e2;
+          own_col_b[q] = -1;
+        }
+      }
+    }
+  }
   double sacc[4][4];  // ACC 2: this thread's 4x4 tile of Y W^T
 #pragma unroll
   for (int a = 0; a < 4; a++)
@@ -240,7 +273,7 @@ __global__ void __launch_bounds__(BA_THREADS)
         h[5] += Jp[2] * Jp[2] + Jp[5] * Jp[5];
 #pragma unroll
         for (int a = 0; a < 3; a++) g[a] += Jp[a] * r[0] + Jp[3 + a] * r[1];
-        if (ACC != 3 && cam >= 0) {
+        if (ACC != 3 && ACC != 2 && cam >= 0) {
           double* H = accH + HCC * (size_t)cam;
           int k = 0;
 #pragma unroll
@@ -256,6 +289,62 @@ __global__ void __launch_bounds__(BA_THREADS)
     for (int a = 0; a < 6; a++) h[a] = group_sum8(h[a]);
 #pragma unroll
     for (int a = 0; a < 3; a++) g[a] = group_sum8(g[a]);
+    if (ACC == 2) {
+      // camera side without atomics: Jacobian rows / residuals of the block's 32 points
+      // into dense tiles, then every thread reduces the entries it owns
+      double* Jd = Yd;  // 64 x 64, row = (slot, residual component), column = camera parameter
+      for (int ri = 0; ri < rounds; ri++) {
+        const int oi = s + ri * 8 + gl;
+        const bool has_i = oi < e;
+        int ci = -1;
+        if (rounds > 1) {
+          if (has_i) ci = eval_obs(p, cams, camrot, oi, X, sp, r, Jc, Jp);
+        } else {
+          ci = has ? cam : -1;
+        }
+        if (has_i && ci >= 0) {
+#pragma unroll
+          for (int comp = 0; comp < 2; comp++) {
+#pragma unroll
+            for (int a = 0; a < 6; a++) Jd[(slot * 2 + comp) * DENSE_N + 6 * ci + a] = Jc[6 * comp + a];
+            Rd[(slot * 2 + comp) * DENSE_RC + ci] = r[comp];
+          }
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int q = 0; q < 2; q++) {
+        if (own_col_a[q] >= 0) {
+          double a2 = 0;
+          if (own_col_b[q] >= 0) {
+#pragma unroll 8
+            for (int k2 = 0; k2 < DENSE_K2; k2++)
+              a2 += Jd[k2 * DENSE_N + own_col_a[q]] * Jd[k2 * DENSE_N + own_col_b[q]];
+          } else {
+#pragma unroll 8
+            for (int k2 = 0; k2 < DENSE_K2; k2++)
+              a2 += Jd[k2 * DENSE_N + own_col_a[q]] * Rd[k2 * DENSE_RC + own_cam[q]];
+          }
+          hown[q] += a2;
+        }
+      }
+      __syncthreads();
+      for (int ri = 0; ri < rounds; ri++) {
+        const int oi = s + ri * 8 + gl;
+        if (oi < e) {
+          const int ci = p.obs_cam[oi];
+          if (ci >= 0) {
+#pragma unroll
+            for (int comp = 0; comp < 2; comp++) {
+#pragma unroll
+              for (int a = 0; a < 6; a++) Jd[(slot * 2 + comp) * DENSE_N + 6 * ci + a] = 0.0;
+              Rd[(slot * 2 + comp) * DENSE_RC + ci] = 0.0;
+            }
+          }
+        }
+      }
+      __syncthreads();
+    }
     if (!FULL) {
       if (pv && gl == 0) {
         if (opt.jacobi_scaling && force == 1) {
@@ -291,12 +380,17 @@ __global__ void __launch_bounds__(BA_THREADS)
     // ---- phase 2: Schur products  S -= W_i Hinv W_j^T ,  rhs_corr += W_i Hinv g_p
     if (ACC == 3) continue;  // done by ba_cam_rows_kernel / ba_schur_pairs_kernel
     if (ACC == 2) {
-      // dense path: scatter W_i and Y_i = W_i Hinv into the block's 64 x 96 tiles
+      // dense path: store W_i and Y_i = W_i Hinv into the block's 64 x 96 tiles (plain stores:
+      // the (point, camera) pairs of a window are unique on this path)
+      if (gl == 0) {
+#pragma unroll
+        for (int b2 = 0; b2 < 3; b2++) gv[slot * 3 + b2] = pv ? g[b2] : 0.0;
+      }
       for (int ri = 0; ri < rounds; ri++) {
         const int oi = s + ri * 8 + gl;
         const bool has_i = oi < e;
         int ci = -1;
-        if (rounds > 1 || ri > 0) {
+        if (rounds > 1) {
           if (has_i) ci = eval_obs(p, cams, camrot, oi, X, sp, r, Jc, Jp);
         } else {
           ci = has ? cam : -1;
@@ -307,18 +401,13 @@ __global__ void __launch_bounds__(BA_THREADS)
             const double w0 = Jc[a] * Jp[0] + Jc[6 + a] * Jp[3];
             const double w1 = Jc[a] * Jp[1] + Jc[6 + a] * Jp[4];
             const double w2 = Jc[a] * Jp[2] + Jc[6 + a] * Jp[5];
-            const double y0 = w0 * hi[0] + w1 * hi[1] + w2 * hi[2];
-            const double y1 = w0 * hi[1] + w1 * hi[3] + w2 * hi[4];
-            const double y2 = w0 * hi[2] + w1 * hi[4] + w2 * hi[5];
             const int row = 6 * ci + a;
-            // atomicAdd (not a store): tolerates a point observed twice by one camera
-            atomicAdd(&Wd[(slot * 3 + 0) * DENSE_N + row], w0);
-            atomicAdd(&Wd[(slot * 3 + 1) * DENSE_N + row], w1);
-            atomicAdd(&Wd[(slot * 3 + 2) * DENSE_N + row], w2);
-            atomicAdd(&Yd[(slot * 3 + 0) * DENSE_N + row], y0);
-            atomicAdd(&Yd[(slot * 3 + 1) * DENSE_N + row], y1);
-            atomicAdd(&Yd[(slot * 3 + 2) * DENSE_N + row], y2);
-            atomicAdd(&accR[row], y0 * g[0] + y1 * g[1] + y2 * g[2]);
+            Wd[(slot * 3 + 0) * DENSE_N + row] = w0;
+            Wd[(slot * 3 + 1) * DENSE_N + row] = w1;
+            Wd[(slot * 3 + 2) * DENSE_N + row] = w2;
+            Yd[(slot * 3 + 0) * DENSE_N + row] = w0 * hi[0] + w1 * hi[1] + w2 * hi[2];
+            Yd[(slot * 3 + 1) * DENSE_N + row] = w0 * hi[1] + w1 * hi[3] + w2 * hi[4];
+            Yd[(slot * 3 + 2) * DENSE_N + row] = w0 * hi[2] + w1 * hi[4] + w2 * hi[5];
           }
         }
       }
@@ -339,6 +428,12 @@ __global__ void __launch_bounds__(BA_THREADS)
 #pragma unroll
             for (int c2 = 0; c2 < 4; c2++) sacc[a][c2] += yv[a] * wv[c2];
         }
+        if (tid < n) {  // Schur right-hand side row owned by this thread
+          double a2 = 0;
+#pragma unroll 8
+          for (int k = 0; k < DENSE_K; k++) a2 += Yd[k * DENSE_N + tid] * gv[k];
+          rown += a2;
+        }
       }
       __syncthreads();
       // clear exactly what this lane wrote
@@ -357,7 +452,7 @@ __global__ void __launch_bounds__(BA_THREADS)
           }
         }
       }
-      __syncwarp();
+      __syncthreads();
       continue;
     }
     for (int ri = 0; ri < rounds; ri++) {
@@ -438,11 +533,12 @@ __global__ void __launch_bounds__(BA_THREADS)
       if (v != 0.0) atomicAdd(&p.lin[i], v);
     }
   } else if (ACC == 2) {
-    __syncthreads();
-    for (int i = tid; i < small_n; i += BA_THREADS) {
-      const double v = slin[i];
-      if (v != 0.0) atomicAdd(&p.Hcc[i], v);  // Hcc | gc | rhs_corr are contiguous in lin
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+      const int ent = tid + q * BA_THREADS;  // Hcc | gc are contiguous in lin
+      if (own_col_a[q] >= 0 && hown[q] != 0.0) atomicAdd(&p.Hcc[ent], hown[q]);
     }
+    if (FULL && tid < n && rown != 0.0) atomicAdd(&p.rhs_corr[tid], rown);
     if (FULL) {
       const int ty = tid >> 4, tx = tid & 15;
 #pragma unroll
@@ -1515,6 +1611,7 @@ struct lorb_ba_problem {
   std::vector<int> h_cam_off, h_pt_off;
   lorb::Buf params, topo, work, descs, hstate, counter, lists, stage;
   int max_cam_items = 0, max_pair_items = 0;
+  bool has_dup = false;  // some point is observed twice by the same window camera
   double *cams0 = nullptr, *pts0 = nullptr;  // initial parameters of all windows
   size_t cam_doubles = 0, pt_doubles = 0;
   int maxC = 0, maxP = 0;
@@ -1613,6 +1710,7 @@ static int problem_build(lorb_ba_problem* pb, lorb_ctx* c, const std::vector<Win
   struct ListOff { size_t obs_pt, cam_obs, cam_items, pairs, pair_items; int n_cam_items, n_pair_items; };
   std::vector<ListOff> lo(nw, ListOff{0, 0, 0, 0, 0, 0, 0});
   pb->max_cam_items = pb->max_pair_items = 0;
+  pb->has_dup = false;
   {
     size_t a = 0, b = 0, f = 0;
     for (int w = 0; w < nw; w++) {
@@ -1653,6 +1751,17 @@ static int problem_build(lorb_ba_problem* pb, lorb_ctx* c, const std::vector<Win
         h_cam[b + d] = -1 - i;
         h_uv[b + d] = make_float2(W.fix_uv[2 * i], W.fix_uv[2 * i + 1]);
         host_fix_rotation(W.fix_rt + 6 * (size_t)i, &h_fix[12 * (f + i)]);
+      }
+      if (6 * W.C <= DENSE_N && !pb->has_dup) {
+        // the atomic-free dense path stores (point, camera) tiles: needs unique pairs
+        const int* cam2 = &h_cam[b];
+        for (int pp = 0; pp < W.P && !pb->has_dup; pp++)
+          for (int e1 = ptr[pp]; e1 < ptr[pp + 1] && !pb->has_dup; e1++)
+            for (int e2 = e1 + 1; e2 < ptr[pp + 1]; e2++)
+              if (cam2[e1] >= 0 && cam2[e1] == cam2[e2]) {
+                pb->has_dup = true;
+                break;
+              }
       }
       if (6 * W.C > 96) {
         const int OT = W.O + W.F;
@@ -1919,14 +2028,14 @@ static int problem_solve(lorb_ba_problem* pb, const lorb_ba_options* optp, int s
   int* h_active = reinterpret_cast<int*>(pb->hstate.as<uint8_t>() + sizeof(LMState) * (size_t)nw);
   // small windows: shared-memory privatised accumulation + one fused solve kernel
   const bool small = nmax <= 96;
-  const int acc_mode = nmax <= DENSE_N ? 2 : (small ? 1 : 3);
+  const int acc_mode = (nmax <= DENSE_N && !pb->has_dup) ? 2 : (small ? 1 : 3);
   const size_t wsm_bytes = (size_t)BA_THREADS * 18 * 8;
   const size_t lin_small = (size_t)(HCC + 12) * pb->maxC;
   const size_t smem_build_full =
-      acc_mode == 2 ? (lin_small + 2 + 2 * (size_t)DENSE_K * DENSE_N) * 8
+      acc_mode == 2 ? (2 * (size_t)DENSE_K * DENSE_N + DENSE_K2 * DENSE_RC + DENSE_K) * 8
                     : (acc_mode == 1 ? ((size_t)nmax * nmax + lin_small) * 8 + wsm_bytes : 0);
   const size_t smem_build_init =
-      acc_mode == 2 ? lin_small * 8 + 16
+      acc_mode == 2 ? (2 * (size_t)DENSE_K * DENSE_N + DENSE_K2 * DENSE_RC + DENSE_K) * 8
                     : (acc_mode == 1 ? ((size_t)nmax * nmax + lin_small) * 8 + wsm_bytes : 0);
   const size_t smem_solve = ((size_t)nmax * nmax + 2 * (size_t)nmax) * 8;
 #define LORB_BUILD_ATTR(FULL_, ACC_, BYTES_)                                                  \

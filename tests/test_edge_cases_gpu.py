@@ -92,3 +92,20 @@ def test_pose_only_too_few_observations(ctx):
     np.testing.assert_allclose(rt, ort, rtol=1e-6, atol=1e-8)
     rt0, s0 = ctx.ba_pose_only(np.zeros((0, 3), np.float32), np.zeros((0, 2), np.float32), po["K"], po["rt"])
     assert np.array_equal(rt0, po["rt"]) and s0["initial_cost"] == 0.0
+
+
+def test_ba_point_observed_twice_by_one_camera(ctx):
+    """Two residual blocks on the same (point, pose) pair — legal for Ceres; the
+    atomic-free dense path must hand such windows to the accumulating variant."""
+    pb = synth.make_ba_problem(14, C=5, P=120, obs_per_point=(3, 4))
+    dup = np.flatnonzero(pb["obs_pt"] < 10)
+    pb2 = dict(pb)
+    pb2["obs_cam"] = np.concatenate([pb["obs_cam"], pb["obs_cam"][dup]]).astype(np.int32)
+    pb2["obs_pt"] = np.concatenate([pb["obs_pt"], pb["obs_pt"][dup]]).astype(np.int32)
+    pb2["obs_uv"] = np.concatenate([pb["obs_uv"], pb["obs_uv"][dup] + np.float32(0.5)]).astype(np.float32)
+    kw = dict(max_num_iterations=6)
+    cams, pts, s = ctx.ba_local(pb2, capi.ba_options(**kw))
+    oc, op, o = ref.ba_local(pb2, ref.ba_options(**kw))
+    np.testing.assert_allclose(cams, oc, rtol=1e-6, atol=1e-8)
+    np.testing.assert_allclose(pts, op, rtol=1e-6, atol=1e-8)
+    assert s["iterations"] == o["iterations"]
