@@ -240,8 +240,9 @@ def make_frustum_points(n=5000, seed=0, width=640, height=480):
                 K=dict(fx=float(fx), fy=float(fy), cx=float(cx), cy=float(cy), mbf=float(mbf)),
                 min_x=0.0, max_x=float(width), min_y=0.0, max_y=float(height),
                 xw=np.ascontiguousarray(xw), normal=np.ascontiguousarray(nrm), min_dist=min_dist,
-                max_dist=max_dist, cos_limit=0.5, log_sf=float(np.log(np.float32(1.2)).astype(np.float32)),
-                n_levels=8)
+                max_dist=max_dist, cos_limit=0.5, n_levels=8,
+                # = logf(1.2f) of reference src/frame.cpp:35 (numpy's float32 log is 1 ulp off here)
+                log_sf=float(np.float32(np.log(np.float64(np.float32(1.2))))))
 
 
 # --------------------------------------------------------------------- BA

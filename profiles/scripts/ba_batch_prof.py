@@ -1,5 +1,6 @@
+import os
 import sys
-sys.path.insert(0, ".")
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
 from lorb_slam_b200 import capi, synth
 c = capi.Context(0)
 pbs = [synth.make_ba_problem(i, C=10, P=5000) for i in range(64)]

@@ -1,6 +1,7 @@
 """Small pass over every C-ABI entry point (for compute-sanitizer memcheck)."""
+import os
 import sys
-sys.path.insert(0, ".")
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
 import numpy as np
 from lorb_slam_b200 import capi, synth
 c = capi.Context(0)
