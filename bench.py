@@ -159,24 +159,47 @@ def _make_bank(seed=0):
     return rng.integers(0, 256, size=(N_KF, N_DESC, 32), dtype=np.uint8)
 
 
+def _cpu_sweepers(bank_block):
+    """-> [(kind, description, run(pa, pb), set_threads)], the reference's own compiled code first.
+
+    "reference" = oracle/_ref: Matcher::SearchByProjection(curr, prev) of /root/reference's
+    src/matcher.cpp compiled unmodified (descriptor gathering, minDist / max(2*minDist,30) filter)
+    over the OpenCV stand-in's BFMatcher, OpenMP over keyframe pairs (the reference is
+    single-threaded; OpenCV-C++ is not in the image).  "port" = oracle/match_ref.c."""
+    from oracle import ref, reflib
+    out = []
+    if reflib.available():
+        sw = reflib.Sweep(bank_block)
+        out.append(("reference", "oracle/_ref (reference src/matcher.cpp compiled unmodified, -O2 -mpopcnt, "
+                    "OpenCV stand-in BFMatcher), OpenMP over pairs", sw.run))
+    out.append(("port", "oracle/match_ref.c -O2 -mpopcnt, OpenMP over pairs",
+                lambda pa, pb: ref.sweep(bank_block, pa, pb)))
+    return out
+
+
 def cpu_baseline_sweep(bank, target_s=12.0):
-    """Oracle (CPU restatement, OpenMP over keyframe pairs) on a bounded sample."""
+    """The reference's CPU path on a bounded sample of the same workload, all host threads."""
     from oracle import ref
     cores = os.cpu_count() or 1
-    cores = ref.set_num_threads(cores)
+    cores = ref.set_num_threads(cores)  # one libgomp: also sets the team size of oracle/_ref
     pa, pb = _block_pairs()
-    n0 = max(cores, 8)
-    t0 = time.time()
-    ref.sweep(bank, pa[:n0], pb[:n0])
-    dt = time.time() - t0
-    n = int(min(len(pa), max(n0, n0 * target_s / max(dt, 1e-3))))
-    t0 = time.time()
-    ref.sweep(bank, pa[:n], pb[:n])
-    dt = time.time() - t0
-    out = {"value": n * PAIRS_PER_KF_PAIR / dt, "unit": "descriptor-pairs/s", "cores": cores,
-           "kind": "port",
-           "sample": "%d keyframe pairs (2000x2000 each) of the first block, oracle/match_ref.c "
-                     "-O2 -mpopcnt, OpenMP over pairs" % n}
+    res = []
+    for kind, desc, run in _cpu_sweepers(bank[:BLOCK_KF]):
+        n0 = max(cores, 8)
+        t0 = time.time()
+        run(pa[:n0], pb[:n0])
+        dt = time.time() - t0
+        n = int(min(len(pa), max(n0, n0 * target_s / max(dt, 1e-3))))
+        t0 = time.time()
+        run(pa[:n], pb[:n])
+        dt = time.time() - t0
+        res.append({"value": n * PAIRS_PER_KF_PAIR / dt, "unit": "descriptor-pairs/s", "cores": cores,
+                    "kind": kind,
+                    "sample": "%d keyframe pairs (2000x2000 each) of the first block, %s" % (n, desc)})
+    out = res[0]
+    if len(res) > 1:
+        out["port_value"] = res[1]["value"]
+        out["port_sample"] = res[1]["sample"]
     try:  # the library routine the reference itself calls, for context
         import cv2
         cv2.setNumThreads(cores)
@@ -543,11 +566,11 @@ def main():
 
 
 def reference_arm(args):
-    """The reference's own CPU path for the same metric/config, on the host
-    cores of this box.  The reference cannot be compiled here (OpenCV-C++ and
-    Ceres are absent), so this times the oracle port — the one other place
-    bench.py may execute oracle/ — with all host threads; each step is a bounded
-    sample of the workload.  Rank 0 only."""
+    """The reference's own CPU path for the same metric/config, on the host cores of this box:
+    oracle/_ref (the reference's src/matcher.cpp compiled unmodified over the OpenCV stand-in; see
+    oracle/ref_harness.cpp) when its library is present, else the oracle port -- the one other
+    place bench.py may execute oracle/ -- with all host threads; each step is a bounded sample of
+    the workload.  Rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -556,17 +579,18 @@ def reference_arm(args):
     cores = ref.set_num_threads(cores)  # torchrun exports OMP_NUM_THREADS=1: use every host thread
     bank = _make_bank(0)[:BLOCK_KF]
     pa, pb = _block_pairs()
-    n = max(cores, 8) * 16  # keyframe pairs per step (bounded sample, ~0.1-0.3 s of all-core work)
+    kind, desc, run = _cpu_sweepers(bank)[0]
+    n = max(cores, 8) * (4 if kind == "reference" else 16)  # keyframe pairs per step (bounded sample)
     for _ in range(args.warmup):
-        ref.sweep(bank, pa[:n], pb[:n])
+        run(pa[:n], pb[:n])
     t0 = time.perf_counter()
     for s in range(args.steps):
         o = (s * n) % (len(pa) - n)
-        ref.sweep(bank, pa[o:o + n], pb[o:o + n])
+        run(pa[o:o + n], pb[o:o + n])
     dt = time.perf_counter() - t0
     value = args.steps * n * PAIRS_PER_KF_PAIR / dt
-    sample = ("%d keyframe pairs (2000x2000 descriptors each) per step out of the 8128 of a block; "
-              "oracle/match_ref.c (-O2 -mpopcnt), OpenMP over pairs" % n)
+    sample = ("%d keyframe pairs (2000x2000 descriptors each) per step out of the 8128 of a block; %s"
+              % (n, desc))
     print(json.dumps({
         "impl": "reference", "metric": "descriptor-pairs/s Hamming match", "value": value,
         "unit": "descriptor-pairs/s", "n_gpus": args.gpus, "steps": args.steps,
@@ -574,7 +598,7 @@ def reference_arm(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "u64 popcnt", "data": "synthetic",
         "config": {"workload": "kf_pair_sweep (bounded sample): " + sample},
         "cpu_baseline": {"value": value, "unit": "descriptor-pairs/s", "cores": cores,
-                         "kind": "port", "sample": sample},
+                         "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "descriptor-pairs/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0}}), flush=True)
 

@@ -229,6 +229,38 @@ int lorb_frustum_project(lorb_ctx* ctx, const float* tcw, const float* ow, const
                          float* view_cos);
 
 /*
+ * Frame::ComputeStereoMatches (reference src/frame.cpp:125-333): for every
+ * left keypoint, the best right keypoint in its row band by Hamming distance (octave within
+ * +-1, disparity in [0, mbf/mb]), 11x11 SAD refinement over 11 shifts at the keypoint's pyramid
+ * level with a parabola fit, then removal of matches whose SAD is >= 1.5*1.4*median.
+ *   left / right       image pyramids as ORBextractor::mvImagePyramid holds them
+ *                      (reference include/ORBextractor.h:85): 8-bit, data[l] -> pixel (0,0),
+ *                      step[l] bytes between rows, width[l] x height[l]
+ *   scale_factors / inv_scale_factors [n_levels]   Frame::mvScaleFactors / mvInvScaleFactors
+ *   mbf, mb            Frame::mbf, Frame::mb
+ *   lx, ly, loct, ldesc   left  mvKeys[i].pt.x / .pt.y / .octave, mDescriptors rows
+ *   rx, ry, roct, rdesc   right mvKeysRight / mDescriptorsRight
+ * Outputs: out_uright[n_left] (mvuRight), out_depth[n_left] (mvDepth), -1 where unmatched;
+ * n_matched = matches left after the outlier step (may be NULL).
+ * A keypoint whose correlation patch would leave its level image is left unmatched (in the
+ * reference cv::Mat::rowRange/colRange would throw there).
+ */
+typedef struct lorb_pyramid_view {
+  int n_levels;
+  const int* width;          /* [n_levels] */
+  const int* height;         /* [n_levels] */
+  const int* step;           /* [n_levels] bytes per row */
+  const uint8_t* const* data;/* [n_levels] host pointers */
+} lorb_pyramid_view;
+
+int lorb_stereo_matches(lorb_ctx* ctx, const lorb_pyramid_view* left, const lorb_pyramid_view* right,
+                        int n_levels, const float* scale_factors, const float* inv_scale_factors,
+                        float mbf, float mb, int n_left, const float* lx, const float* ly,
+                        const int* loct, const uint8_t* ldesc, int n_right, const float* rx,
+                        const float* ry, const int* roct, const uint8_t* rdesc, float* out_uright,
+                        float* out_depth, int* n_matched);
+
+/*
  * MapPoint::ComputeDescriptor (reference src/map_point.cpp:69-129) for a batch
  * of map points: point k owns the observation descriptors
  * desc[offsets[k] .. offsets[k+1]) (in the iteration order of its observation

@@ -25,6 +25,7 @@ EXPORTS = [
     "lorb_match_bf_crosscheck", "lorb_match_knn2", "lorb_match_sweep", "lorb_bank_upload",
     "lorb_match_sweep_resident", "lorb_sweep_plan_upload", "lorb_sweep_plan_run",
     "lorb_sweep_plan_download", "lorb_sweep_plan_run_at", "lorb_search_proj_points", "lorb_search_proj_frame", "lorb_frustum_project", "lorb_compute_descriptors",
+    "lorb_stereo_matches",
     "lorb_ba_default_options", "lorb_ba_pose_only", "lorb_ba_local", "lorb_ba_local_batched",
     "lorb_ba_problem_create", "lorb_ba_problem_create_batched", "lorb_ba_problem_reset", "lorb_ba_problem_solve",
     "lorb_ba_problem_download", "lorb_ba_problem_destroy", "lorb_dist_get_unique_id",
@@ -62,6 +63,21 @@ class FrameView(C.Structure):
                 ("desc", C.c_void_p), ("kp_claim_obs", C.c_void_p), ("min_x", C.c_float),
                 ("max_x", C.c_float), ("min_y", C.c_float), ("max_y", C.c_float),
                 ("n_levels", C.c_int), ("scale_factors", C.c_void_p)]
+
+
+class PyramidView(C.Structure):
+    _fields_ = [("n_levels", C.c_int), ("width", C.c_void_p), ("height", C.c_void_p),
+                ("step", C.c_void_p), ("data", C.c_void_p)]
+
+
+def _pyramid_view(pyr):
+    lv = [np.ascontiguousarray(a, dtype=np.uint8) for a in pyr]
+    w = np.array([a.shape[1] for a in lv], np.int32)
+    h = np.array([a.shape[0] for a in lv], np.int32)
+    st = np.array([a.strides[0] for a in lv], np.int32)
+    ptrs = (C.c_void_p * len(lv))(*[a.ctypes.data for a in lv])
+    v = PyramidView(len(lv), _ptr(w), _ptr(h), _ptr(st), C.cast(ptrs, C.c_void_p))
+    return v, (lv, w, h, st, ptrs)
 
 
 class Intrinsics(C.Structure):
@@ -270,6 +286,23 @@ class Context:
         _check(self._lib.lorb_compute_descriptors(self._h, n, _ptr(offsets), _ptr(desc), _ptr(best),
                                                   _ptr(med)))
         return best[:n], med[:n]
+
+    def stereo_matches(self, st):
+        """Frame::ComputeStereoMatches; st as produced by synth.make_stereo_pair."""
+        vl, kl = _pyramid_view(st["pyr_left"])
+        vr, kr = _pyramid_view(st["pyr_right"])
+        n, nr = int(st["n_left"]), int(st["n_right"])
+        a = [_arr(st["scale_factors"], np.float32), _arr(st["inv_scale_factors"], np.float32),
+             _arr(st["lx"], np.float32), _arr(st["ly"], np.float32), _arr(st["loct"], np.int32),
+             _arr(st["ldesc"], np.uint8), _arr(st["rx"], np.float32), _arr(st["ry"], np.float32),
+             _arr(st["roct"], np.int32), _arr(st["rdesc"], np.uint8)]
+        ur, dp = np.zeros(max(1, n), np.float32), np.zeros(max(1, n), np.float32)
+        nm = C.c_int(0)
+        _check(self._lib.lorb_stereo_matches(
+            self._h, C.byref(vl), C.byref(vr), int(st["n_levels"]), _ptr(a[0]), _ptr(a[1]),
+            C.c_float(st["mbf"]), C.c_float(st["mb"]), n, _ptr(a[2]), _ptr(a[3]), _ptr(a[4]), _ptr(a[5]),
+            nr, _ptr(a[6]), _ptr(a[7]), _ptr(a[8]), _ptr(a[9]), _ptr(ur), _ptr(dp), C.byref(nm)))
+        return dict(uright=ur[:n], depth=dp[:n], n_matched=nm.value)
 
     def frustum_project(self, fp):
         n = int(fp["n"])

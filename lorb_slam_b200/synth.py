@@ -366,3 +366,95 @@ def batch_windows(pbs):
         obs_cam=np.concatenate([p["obs_cam"] for p in pbs]),
         obs_pt=np.concatenate([p["obs_pt"] for p in pbs]),
         obs_uv=np.concatenate([p["obs_uv"] for p in pbs]), K=pbs[0]["K"].copy())
+
+
+# ------------------------------------------------------------- stereo matches
+
+def _blur(img, k):
+    ker = np.ones(k) / k
+    img = np.apply_along_axis(lambda r: np.convolve(r, ker, mode="same"), 1, img)
+    return np.apply_along_axis(lambda c: np.convolve(c, ker, mode="same"), 0, img)
+
+
+def _resample(img, w, h):
+    """Bilinear resize (the pyramid is an INPUT of the path; any resampler will do)."""
+    H, W = img.shape
+    xs = (np.arange(w) + 0.5) * W / w - 0.5
+    ys = (np.arange(h) + 0.5) * H / h - 0.5
+    x0 = np.clip(np.floor(xs).astype(int), 0, W - 2)
+    y0 = np.clip(np.floor(ys).astype(int), 0, H - 2)
+    fx = np.clip(xs - x0, 0, 1)[None, :]
+    fy = np.clip(ys - y0, 0, 1)[:, None]
+    a = img[y0][:, x0]
+    b = img[y0][:, x0 + 1]
+    c = img[y0 + 1][:, x0]
+    d = img[y0 + 1][:, x0 + 1]
+    return (a * (1 - fx) + b * fx) * (1 - fy) + (c * (1 - fx) + d * fx) * fy
+
+
+def make_stereo_pair(n_kp=1000, seed=0, width=640, height=480, n_levels=8, matched_frac=0.75,
+                     p_flip=0.05, border=19):
+    """Inputs of Frame::ComputeStereoMatches (reference src/frame.cpp:125-333): rectified left /
+    right image pyramids (the right image is the left one shifted by a per-band disparity), left and
+    right keypoints at least `border` px from the border of their pyramid level (what
+    ORBextractor's EDGE_THRESHOLD guarantees, reference src/ORBextractor.cpp:808-811) and their
+    descriptors."""
+    rng = np.random.default_rng(seed + 424243)
+    sf = scale_factors(n_levels)
+    inv_sf = (np.float32(1.0) / sf).astype(np.float32)  # mvInvScaleFactor, src/ORBextractor.cpp:434
+    tex = rng.random((height, width)) * 255.0
+    img = 0.5 * _blur(tex, 3) + 0.5 * _blur(tex, 9)
+    for _ in range(300):
+        x, y = int(rng.integers(0, width - 10)), int(rng.integers(0, height - 10))
+        w, h = int(rng.integers(4, 50)), int(rng.integers(4, 50))
+        img[y:y + h, x:x + w] = 0.6 * img[y:y + h, x:x + w] + 0.4 * rng.integers(0, 256)
+    left0 = np.clip(img, 0, 255)
+    n_bands = 8
+    band_d = rng.uniform(3.0, 60.0, n_bands)
+    row_d = band_d[np.minimum(np.arange(height) * n_bands // height, n_bands - 1)]
+    xs = np.arange(width)[None, :] + row_d[:, None]  # right(x, y) = left(x + d(y), y)
+    x0 = np.clip(np.floor(xs).astype(int), 0, width - 2)
+    fx = np.clip(xs - x0, 0, 1)
+    rows = np.arange(height)[:, None]
+    right0 = left0[rows, x0] * (1 - fx) + left0[rows, x0 + 1] * fx
+    right0 = np.clip(right0 + rng.normal(0, 1.0, right0.shape), 0, 255)
+    dims = [(int(np.rint(np.float32(width) * inv_sf[l])), int(np.rint(np.float32(height) * inv_sf[l])))
+            for l in range(n_levels)]
+    pyr_l = [np.ascontiguousarray(np.rint(_resample(left0, w, h)).astype(np.uint8)) for (w, h) in dims]
+    pyr_r = [np.ascontiguousarray(np.rint(_resample(right0, w, h)).astype(np.uint8)) for (w, h) in dims]
+    wgt = (1.0 / 1.2) ** np.arange(n_levels)
+    loct = rng.choice(n_levels, size=n_kp, p=wgt / wgt.sum()).astype(np.int32)
+    lw = np.array([dims[o][0] for o in loct])
+    lh = np.array([dims[o][1] for o in loct])
+    lx = ((border + rng.random(n_kp) * (lw - 2 * border)) * sf[loct]).astype(np.float32)
+    ly = ((border + rng.random(n_kp) * (lh - 2 * border)) * sf[loct]).astype(np.float32)
+    ldesc = descriptors_uniform(n_kp, rng)
+    # right keypoints: re-detections of a part of the left ones + clutter
+    d_at = row_d[np.clip(ly.astype(int), 0, height - 1)]
+    is_m = rng.random(n_kp) < matched_frac
+    rx = lx - d_at + rng.normal(0, 0.3, n_kp)
+    ry = ly + rng.normal(0, 0.5, n_kp)
+    roct = np.clip(loct + np.where(rng.random(n_kp) < 0.1, rng.integers(-1, 2, n_kp), 0), 0, n_levels - 1)
+    flip = np.where(rng.random(n_kp) < 0.85, p_flip, 0.3)  # some re-detections look different
+    rdesc = ldesc.copy()
+    for p in np.unique(flip):
+        m = flip == p
+        rdesc[m] = descriptors_noisy_copy(ldesc[m], rng, float(p))
+    clutter = ~is_m
+    rw_ = np.array([dims[o][0] for o in roct])
+    rh_ = np.array([dims[o][1] for o in roct])
+    rx = np.where(clutter, (border + rng.random(n_kp) * (rw_ - 2 * border)) * sf[roct], rx)
+    ry = np.where(clutter, (border + rng.random(n_kp) * (rh_ - 2 * border)) * sf[roct], ry)
+    rdesc[clutter] = descriptors_uniform(int(clutter.sum()), rng)
+    ok = ((rx * inv_sf[roct] >= border) & (rx * inv_sf[roct] <= rw_ - border) &
+          (ry * inv_sf[roct] >= border) & (ry * inv_sf[roct] <= rh_ - border))
+    perm = rng.permutation(np.nonzero(ok)[0])
+    fxc = np.float32(458.0)
+    mbf = np.float32(47.9)
+    return dict(
+        n_levels=n_levels, scale_factors=sf, inv_scale_factors=inv_sf, pyr_left=pyr_l, pyr_right=pyr_r,
+        fx=float(fxc), mbf=float(mbf), mb=float(np.float32(mbf / fxc)),
+        n_left=n_kp, lx=lx, ly=ly, loct=loct, ldesc=np.ascontiguousarray(ldesc),
+        n_right=len(perm), rx=np.ascontiguousarray(rx[perm].astype(np.float32)),
+        ry=np.ascontiguousarray(ry[perm].astype(np.float32)),
+        roct=np.ascontiguousarray(roct[perm].astype(np.int32)), rdesc=np.ascontiguousarray(rdesc[perm]))

@@ -21,6 +21,7 @@
  * The reference itself builds -O0 on baseline x86-64 (CMakeLists.txt:5-6), so
  * no FMA contraction may happen in the float code below.
  */
+#include <limits.h>
 #include <math.h>
 #include <omp.h>
 #include <stdint.h>
@@ -30,6 +31,7 @@
 #define GRID_COLS 64 /* include/frame.h:14 */
 #define GRID_ROWS 48 /* include/frame.h:13 */
 #define TH_HIGH 100  /* src/matcher.cpp:6 */
+#define TH_LOW 50    /* src/matcher.cpp:7 */
 #define HISTO_LENGTH 30 /* src/matcher.cpp:8 */
 
 /* ---- a2: Matcher::DescriptorDistance, src/matcher.cpp:369-385 (SWAR popcount
@@ -627,4 +629,146 @@ void orc_sweep(const uint8_t* bank, int n_desc, const int* pair_a, const int* pa
   for (int p = 0; p < n_pairs; p++)
     orc_sweep_pair(bank + (size_t)pair_a[p] * n_desc * 32, bank + (size_t)pair_b[p] * n_desc * 32,
                    n_desc, &kept[p], &matches[p], &min_dist[p]);
+}
+
+/* ---- Frame::ComputeStereoMatches src/frame.cpp:125-333, line by line on
+ * flat arrays.  pyr_*[l] -> pixel (0,0) of level l (8-bit, `step` bytes per row), as
+ * ORBextractor::mvImagePyramid holds them.  Returns the number of matches left after the
+ * outlier step.  A correlation patch that would leave its level image makes the reference's
+ * cv::Mat::rowRange/colRange throw; here that keypoint is skipped (same rule as the CUDA path). */
+typedef struct { int first, second; } orc_pair_t;
+static int cmp_pair(const void* a, const void* b) {
+  const orc_pair_t* x = (const orc_pair_t*)a; const orc_pair_t* y = (const orc_pair_t*)b;
+  if (x->first != y->first) return x->first < y->first ? -1 : 1;
+  return (x->second > y->second) - (x->second < y->second);
+}
+int orc_stereo_matches(int n_levels, const int* lw, const int* lh, const int* lstep,
+                       const uint8_t* const* pyr_left, const int* rw, const int* rh, const int* rstep,
+                       const uint8_t* const* pyr_right, const float* mvScaleFactors,
+                       const float* mvInvScaleFactors, float mbf, float mb, int N, const float* lx,
+                       const float* ly, const int* loct, const uint8_t* ldesc, int Nr, const float* rx,
+                       const float* ry, const int* roct, const uint8_t* rdesc, float* mvuRight,
+                       float* mvDepth) {
+  (void)n_levels; (void)rh;
+  for (int i = 0; i < N; i++) { mvuRight[i] = -1.0f; mvDepth[i] = -1.0f; } /* :127-128 */
+  const int thOrbDist = (TH_HIGH + TH_LOW) / 2;                              /* :130 */
+  const int nRows = lh[0];                                                   /* :132 */
+  /* :141-160 row table, right keypoints appended in ascending iR */
+  int* rowCount = (int*)calloc((size_t)nRows + 1, sizeof(int));
+  for (int iR = 0; iR < Nr; iR++) {
+    const float kpY = ry[iR];
+    const float r = 2.0f * mvScaleFactors[roct[iR]];
+    const int maxr = (int)ceil(kpY + r), minr = (int)floor(kpY - r);
+    for (int yi = minr; yi <= maxr; yi++)
+      if (yi >= 0 && yi < nRows) rowCount[yi + 1]++;
+  }
+  for (int y = 0; y < nRows; y++) rowCount[y + 1] += rowCount[y];
+  int* rowItems = (int*)malloc(sizeof(int) * (size_t)(rowCount[nRows] > 0 ? rowCount[nRows] : 1));
+  int* fill = (int*)malloc(sizeof(int) * (size_t)(nRows > 0 ? nRows : 1));
+  for (int y = 0; y < nRows; y++) fill[y] = rowCount[y];
+  for (int iR = 0; iR < Nr; iR++) {
+    const float kpY = ry[iR];
+    const float r = 2.0f * mvScaleFactors[roct[iR]];
+    const int maxr = (int)ceil(kpY + r), minr = (int)floor(kpY - r);
+    for (int yi = minr; yi <= maxr; yi++)
+      if (yi >= 0 && yi < nRows) rowItems[fill[yi]++] = iR;
+  }
+  const float minZ = mb, minD = 0;       /* :164-165 */
+  const float maxD = mbf / minZ;         /* :166 */
+  orc_pair_t* vDistIdx = (orc_pair_t*)malloc(sizeof(orc_pair_t) * (size_t)(N > 0 ? N : 1));
+  int nDist = 0;
+  for (int iL = 0; iL < N; iL++) {
+    const int levelL = loct[iL];
+    const float vL = ly[iL], uL = lx[iL];
+    if (vL < 0.0f || (int)vL >= nRows) continue; /* vRowIndices[vL] would be out of range */
+    const int row = (int)vL;                     /* :185 */
+    if (rowCount[row + 1] == rowCount[row]) continue; /* :187 */
+    const float minU = uL - maxD, maxU = uL - minD;   /* :190-191 */
+    if (maxU < 0) continue;                           /* :193 */
+    int bestDist = TH_HIGH;
+    int bestIdxR = 0;
+    const uint8_t* dL = ldesc + 32 * (size_t)iL;
+    for (int c = rowCount[row]; c < rowCount[row + 1]; c++) {
+      const int iR = rowItems[c];
+      if (roct[iR] < levelL - 1 || roct[iR] > levelL + 1) continue; /* :209 */
+      const float uR = rx[iR];
+      if (uR >= minU && uR <= maxU) {
+        const int dist = orc_hamming256(dL, rdesc + 32 * (size_t)iR);
+        if (dist < bestDist) { bestDist = dist; bestIdxR = iR; }
+      }
+    }
+    if (bestDist < thOrbDist) { /* :231 */
+      const float uR0 = rx[bestIdxR];
+      const float scaleFactor = mvInvScaleFactors[levelL];
+      const float scaleduL = roundf(uL * scaleFactor);
+      const float scaledvL = roundf(vL * scaleFactor);
+      const float scaleduR0 = roundf(uR0 * scaleFactor);
+      const int w = 5, L = 5;
+      const int cu = (int)scaleduL, cv = (int)scaledvL, cr = (int)scaleduR0;
+      const uint8_t* IL = pyr_left[levelL];
+      const uint8_t* IR = pyr_right[levelL];
+      /* where cv::Mat::rowRange/colRange of the left patch would assert (:240) */
+      if (cv - w < 0 || cv + w >= lh[levelL] || cu - w < 0 || cu + w >= lw[levelL]) continue;
+      float ILn[11][11];
+      const float cL = (float)IL[(size_t)cv * lstep[levelL] + cu];
+      for (int a = 0; a < 11; a++)
+        for (int b = 0; b < 11; b++)
+          ILn[a][b] = (float)IL[(size_t)(cv - w + a) * lstep[levelL] + cu - w + b] - cL; /* :241-242 */
+      int bestDistS = INT_MAX, bestincR = 0;
+      float vDists[11];
+      const float iniu = scaleduR0 + L - w;     /* :252 */
+      const float endu = scaleduR0 + L + w + 1; /* :253 */
+      if (iniu < 0 || endu >= rw[levelL]) continue; /* :254 */
+      if (cv + w >= rh[levelL] || cr - L - w < 0 || cr + L + w >= rw[levelL]) continue; /* asserts of :260 */
+      for (int incR = -L; incR <= +L; incR++) {
+        const float cR = (float)IR[(size_t)cv * rstep[levelL] + cr + incR];
+        double s = 0;
+        for (int a = 0; a < 11; a++)
+          for (int b = 0; b < 11; b++) {
+            const float v = (float)IR[(size_t)(cv - w + a) * rstep[levelL] + cr + incR - w + b] - cR;
+            s += fabs((double)ILn[a][b] - (double)v); /* cv::norm(IL, IR, NORM_L1) :264 */
+          }
+        const float dist = (float)s;
+        if (dist < bestDistS) { bestDistS = (int)dist; bestincR = incR; } /* :265-269 */
+        vDists[L + incR] = dist;
+      }
+      if (bestincR == -L || bestincR == L) continue; /* :276 */
+      const float dist1 = vDists[L + bestincR - 1];
+      const float dist2 = vDists[L + bestincR];
+      const float dist3 = vDists[L + bestincR + 1];
+      const float deltaR = (dist1 - dist3) / (2.0f * (dist1 + dist3 - 2.0f * dist2)); /* :287 */
+      if (deltaR < -1 || deltaR > 1) continue;                                        /* :290 */
+      float bestuR = mvScaleFactors[levelL] * ((float)scaleduR0 + (float)bestincR + deltaR); /* :297 */
+      float disparity = (uL - bestuR);                                                /* :300 */
+      if (disparity >= minD && disparity < maxD) {
+        if (disparity <= 0) {
+          disparity = 0.01;
+          bestuR = uL - 0.01;
+        }
+        mvDepth[iL] = mbf / disparity;
+        mvuRight[iL] = bestuR;
+        vDistIdx[nDist].first = bestDistS;
+        vDistIdx[nDist].second = iL;
+        nDist++;
+      }
+    }
+  }
+  int kept = 0;
+  if (nDist > 0) { /* :320-337 (the reference reads vDistIdx[0] of an empty vector otherwise) */
+    qsort(vDistIdx, (size_t)nDist, sizeof(orc_pair_t), cmp_pair);
+    const float median = vDistIdx[nDist / 2].first;
+    const float thDist = 1.5f * 1.4f * median;
+    kept = nDist;
+    for (int i = nDist - 1; i >= 0; i--) {
+      if (vDistIdx[i].first < thDist) break;
+      mvuRight[vDistIdx[i].second] = -1;
+      mvDepth[vDistIdx[i].second] = -1;
+      kept--;
+    }
+  }
+  free(vDistIdx);
+  free(fill);
+  free(rowItems);
+  free(rowCount);
+  return kept;
 }

@@ -207,6 +207,33 @@ def compute_descriptors(offsets, desc):
     return best, med
 
 
+def _pyr_args(pyr):
+    """list of 2-D uint8 arrays -> (keepalive, w[], h[], step[], uint8** )"""
+    lv = [np.ascontiguousarray(a, dtype=np.uint8) for a in pyr]
+    w = np.array([a.shape[1] for a in lv], np.int32)
+    h = np.array([a.shape[0] for a in lv], np.int32)
+    st = np.array([a.strides[0] for a in lv], np.int32)
+    ptrs = (C.POINTER(C.c_uint8) * len(lv))(*[_p(a, C.c_uint8) for a in lv])
+    return lv, w, h, st, ptrs
+
+
+def stereo_matches(st):
+    """st: dict from lorb_slam_b200.synth.make_stereo_pair -> dict(uright, depth, n_matched)."""
+    kl, lw, lh, ls, lp = _pyr_args(st["pyr_left"])
+    kr, rw, rh, rs, rp = _pyr_args(st["pyr_right"])
+    n = st["n_left"]
+    ur, dp = np.zeros(max(1, n), np.float32), np.zeros(max(1, n), np.float32)
+    _match().orc_stereo_matches.restype = C.c_int
+    k = _match().orc_stereo_matches(
+        int(st["n_levels"]), _p(lw, C.c_int), _p(lh, C.c_int), _p(ls, C.c_int), lp, _p(rw, C.c_int),
+        _p(rh, C.c_int), _p(rs, C.c_int), rp, _p(_f32(st["scale_factors"]), C.c_float),
+        _p(_f32(st["inv_scale_factors"]), C.c_float), C.c_float(st["mbf"]), C.c_float(st["mb"]), n,
+        _p(st["lx"], C.c_float), _p(st["ly"], C.c_float), _p(st["loct"], C.c_int),
+        _p(st["ldesc"], C.c_uint8), st["n_right"], _p(st["rx"], C.c_float), _p(st["ry"], C.c_float),
+        _p(st["roct"], C.c_int), _p(st["rdesc"], C.c_uint8), _p(ur, C.c_float), _p(dp, C.c_float))
+    return dict(uright=ur[:n], depth=dp[:n], n_matched=int(k))
+
+
 def project_rt(tcw, xw):
     tcw, xw = _f32(tcw).reshape(16), _f32(xw).reshape(3)
     out = np.zeros(3, np.float32)

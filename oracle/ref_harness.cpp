@@ -240,6 +240,62 @@ int ref_search_bf(int use_set, int n_q, const uint8_t* q_desc, int n_t, const ui
   return (int)n;
 }
 
+// ---- the keyframe-pair sweep of BASELINE config 5 run through the reference's own entry point:
+// for every pair (a, b), Matcher::SearchByProjection(curr = keyframe a, prev = keyframe b), i.e. its
+// descriptor gathering (GetDescriptors clone, row-by-row push_back), the stand-in BFMatcher and its
+// minDist / max(2*minDist, 30) filter.  Used by bench.py's reference arm (all host threads: OpenMP
+// over pairs; the reference itself is single-threaded) and checked against the oracle's sweep.
+struct RefSweep {
+  Camera* cam = nullptr;
+  int n_kf = 0, n_desc = 0;
+  const uint8_t* bank = nullptr;
+  std::vector<Frame*> prev;        // one per keyframe: every keypoint holds a map point
+  std::vector<PointBlock*> pts;
+};
+void* ref_sweep_create(const uint8_t* bank, int n_kf, int n_desc) {
+  RefSweep* S = new RefSweep();
+  S->cam = make_camera(458, 458, 320, 240, 47.9f);
+  S->n_kf = n_kf;
+  S->n_desc = n_desc;
+  S->bank = bank;
+  const float sf[8] = {1, 1, 1, 1, 1, 1, 1, 1};
+  std::vector<float> z(n_desc > 0 ? n_desc : 1, 1.0f);
+  std::vector<int> zi(z.size(), 0);
+  for (int k = 0; k < n_kf; k++) {
+    const uint8_t* d = bank + (size_t)k * n_desc * 32;
+    Frame* F = make_search_frame(S->cam, n_desc, z.data(), z.data(), zi.data(), nullptr, nullptr, d, 0, 640, 0, 480, sf, 8);
+    PointBlock* P = new PointBlock(n_desc, S->cam);
+    for (int j = 0; j < n_desc; j++) {
+      P->p[j].mDescriptor = desc_row(d + 32 * (size_t)j);
+      F->mvpMapPoints[j] = &P->p[j];
+    }
+    S->prev.push_back(F);
+    S->pts.push_back(P);
+  }
+  return S;
+}
+void ref_sweep_run(void* h, const int* pair_a, const int* pair_b, int n_pairs, int* kept) {
+  RefSweep* S = static_cast<RefSweep*>(h);
+  const float sf[8] = {1, 1, 1, 1, 1, 1, 1, 1};
+  std::vector<float> z(S->n_desc > 0 ? S->n_desc : 1, 1.0f);
+  std::vector<int> zi(z.size(), 0);
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int i = 0; i < n_pairs; i++) {
+    // a private current frame per pair: SearchByProjection writes curr->mvpMapPoints
+    Frame* cur = make_search_frame(S->cam, S->n_desc, z.data(), z.data(), zi.data(), nullptr, nullptr,
+                                   S->bank + (size_t)pair_a[i] * S->n_desc * 32, 0, 640, 0, 480, sf, 8);
+    kept[i] = (int)Matcher::SearchByProjection(cur, S->prev[pair_b[i]]);
+    delete cur;
+  }
+}
+void ref_sweep_destroy(void* h) {
+  RefSweep* S = static_cast<RefSweep*>(h);
+  for (Frame* F : S->prev) delete F;
+  for (PointBlock* P : S->pts) delete P;
+  std::free(S->cam);
+  delete S;
+}
+
 // ---- a6: Matcher::SearchByProjection(F, set, th).  Same arguments as orc_search_proj_points;
 // out_point_for_kp = what F->mvpMapPoints holds at exit (-1 entry state, k = map point k).
 int ref_search_proj_points(int n_kp, const float* kx, const float* ky, const int* koct,
@@ -344,6 +400,53 @@ void ref_frustum_project(const float* tcw, float fx, float fy, float cx, float c
   }
   delete F;
   std::free(cam);
+}
+
+// ---- 8(f) rank 2: Frame::ComputeStereoMatches (private; src/frame.cpp:125-333) on given pyramids.
+// ORBextractor's constructor is not on the path (aborting stub): its two instances are zeroed
+// blocks (an all-zero std::vector is the empty vector) that only carry mvImagePyramid.
+int ref_stereo_matches(int n_levels, const int* lw, const int* lh, const int* lstep,
+                       const uint8_t* const* pyr_left, const int* rw, const int* rh, const int* rstep,
+                       const uint8_t* const* pyr_right, const float* sf, const float* inv_sf, float fx,
+                       float mbf, int N, const float* lx, const float* ly, const int* loct,
+                       const uint8_t* ldesc, int Nr, const float* rx, const float* ry, const int* roct,
+                       const uint8_t* rdesc, float* out_uright, float* out_depth, float* out_mb) {
+  Camera* cam = make_camera(fx, fx, lw[0] / 2.0f, lh[0] / 2.0f, mbf);
+  Frame* F = make_search_frame(cam, N, lx, ly, loct, nullptr, nullptr, ldesc, 0, (float)lw[0], 0, (float)lh[0], sf, n_levels);
+  F->mvInvScaleFactors.assign(inv_sf, inv_sf + n_levels);
+  F->mvKeysRight.resize(Nr);
+  for (int i = 0; i < Nr; i++) {
+    F->mvKeysRight[i].pt.x = rx[i];
+    F->mvKeysRight[i].pt.y = ry[i];
+    F->mvKeysRight[i].octave = roct[i];
+  }
+  F->mDescriptorsRight = cv::Mat(Nr, 32, CV_8U);
+  for (int i = 0; i < Nr; i++) std::memcpy(F->mDescriptorsRight.ptr<uint8_t>(i), rdesc + 32 * (size_t)i, 32);
+  ORBextractor* ex[2];
+  for (int s = 0; s < 2; s++) {
+    ex[s] = static_cast<ORBextractor*>(std::calloc(1, sizeof(ORBextractor)));
+    const int* w = s ? rw : lw; const int* h = s ? rh : lh; const int* st = s ? rstep : lstep;
+    const uint8_t* const* img = s ? pyr_right : pyr_left;
+    for (int l = 0; l < n_levels; l++) {
+      cv::Mat m(h[l], w[l], CV_8U);
+      for (int r = 0; r < h[l]; r++) std::memcpy(m.ptr<uint8_t>(r), img[l] + (size_t)r * st[l], w[l]);
+      ex[s]->mvImagePyramid.push_back(m);
+    }
+  }
+  F->mpORBextractorLeft = ex[0];
+  F->mpORBextractorRight = ex[1];
+  if (out_mb) *out_mb = F->mb;
+  F->ComputeStereoMatches();
+  int kept = 0;
+  for (int i = 0; i < N; i++) {
+    out_uright[i] = F->mvuRight[i];
+    out_depth[i] = F->mvDepth[i];
+    kept += F->mvuRight[i] != -1.0f || F->mvDepth[i] != -1.0f;
+  }
+  for (int s = 0; s < 2; s++) { ex[s]->mvImagePyramid.clear(); std::free(ex[s]); }
+  delete F;
+  std::free(cam);
+  return kept;
 }
 
 // ---- 8(f) rank 4: MapPoint::ComputeDescriptor over m observing frames (one descriptor each).

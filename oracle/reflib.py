@@ -135,6 +135,26 @@ def search_bf(q, t, present=None, use_set=False):
     return int(n), out[:len(q)].copy()
 
 
+class Sweep:
+    """Keyframe-pair sweep through Matcher::SearchByProjection(curr, prev); OpenMP over pairs."""
+
+    def __init__(self, bank):
+        self.bank = _u8(bank)
+        lib().ref_sweep_create.restype = C.c_void_p
+        self.h = C.c_void_p(lib().ref_sweep_create(_p(self.bank, C.c_uint8), self.bank.shape[0], self.bank.shape[1]))
+
+    def run(self, pair_a, pair_b):
+        pa, pb = _i32(pair_a), _i32(pair_b)
+        kept = np.zeros(max(1, len(pa)), np.int32)
+        lib().ref_sweep_run(self.h, _p(pa, C.c_int), _p(pb, C.c_int), len(pa), _p(kept, C.c_int))
+        return kept[:len(pa)]
+
+    def close(self):
+        if self.h:
+            lib().ref_sweep_destroy(self.h)
+            self.h = None
+
+
 def search_proj_points(fr, pts, th):
     n_kp, n_pts = fr["n_kp"], pts["n_pts"]
     pfk = np.full(max(1, n_kp), -1, np.int32)
@@ -196,6 +216,24 @@ def frustum_project(fp, scale_factor=np.float32(1.2)):
         _p(out["proj_xr"], C.c_float), _p(out["level"], C.c_int), _p(out["view_cos"], C.c_float),
         _p(ow, C.c_float), C.byref(lsf))
     return out, ow, float(lsf.value)
+
+
+def stereo_matches(st):
+    """Frame::ComputeStereoMatches of the compiled reference on the given pyramids."""
+    kl, lw, lh, ls, lp = _orc._pyr_args(st["pyr_left"])
+    kr, rw, rh, rs, rp = _orc._pyr_args(st["pyr_right"])
+    n = st["n_left"]
+    ur, dp = np.zeros(max(1, n), np.float32), np.zeros(max(1, n), np.float32)
+    mb = C.c_float(0)
+    k = lib().ref_stereo_matches(
+        int(st["n_levels"]), _p(lw, C.c_int), _p(lh, C.c_int), _p(ls, C.c_int), lp, _p(rw, C.c_int),
+        _p(rh, C.c_int), _p(rs, C.c_int), rp, _p(_f32(st["scale_factors"]), C.c_float),
+        _p(_f32(st["inv_scale_factors"]), C.c_float), C.c_float(st["fx"]), C.c_float(st["mbf"]), n,
+        _p(st["lx"], C.c_float), _p(st["ly"], C.c_float), _p(st["loct"], C.c_int),
+        _p(st["ldesc"], C.c_uint8), st["n_right"], _p(st["rx"], C.c_float), _p(st["ry"], C.c_float),
+        _p(st["roct"], C.c_int), _p(st["rdesc"], C.c_uint8), _p(ur, C.c_float), _p(dp, C.c_float),
+        C.byref(mb))
+    return dict(uright=ur[:n], depth=dp[:n], n_matched=int(k), mb=float(mb.value))
 
 
 def compute_descriptor(desc):

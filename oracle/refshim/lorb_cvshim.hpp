@@ -188,6 +188,8 @@ class Mat {
       for (int c = 0; c < cols; c++) out.set(r, c, get(r, c));
     dst = out;
   }
+  // amortised growth like cv::Mat::push_back (reserve 1.5x), so that the reference's
+  // row-by-row descriptor gathering (src/matcher.cpp:30) costs what it costs with OpenCV
   void push_back(const Mat& m) {
     if (m.empty()) return;
     if (empty()) {
@@ -195,11 +197,20 @@ class Mat {
       return;
     }
     assert(m.cols == cols && m.type_ == type_);
-    Mat out(rows + m.rows, cols, type_);
-    for (int r = 0; r < rows; r++) std::memcpy(out.raw(r), raw(r), (size_t)cols * esz(type_));
-    for (int r = 0; r < m.rows; r++)
-      std::memcpy(out.raw(rows + r), m.raw(r), (size_t)cols * esz(type_));
-    *this = out;
+    const size_t need = off_ + (size_t)(rows + m.rows) * step_ + 8;
+    if (!isContinuous() || buf_.use_count() != 1 || buf_->capacity() < need) {
+      auto nb = std::make_shared<std::vector<unsigned char>>();
+      nb->reserve(std::max(need, (size_t)((rows + m.rows) * 3 / 2 + 4) * cols * esz(type_) + 8));
+      nb->resize((size_t)(rows + m.rows) * cols * esz(type_) + 8);
+      for (int r = 0; r < rows; r++) std::memcpy(nb->data() + (size_t)r * cols * esz(type_), raw(r), (size_t)cols * esz(type_));
+      buf_ = nb;
+      off_ = 0;
+      step_ = (size_t)cols * esz(type_);
+    } else {
+      if (buf_->size() < need) buf_->resize(need);  // within capacity: no reallocation
+    }
+    for (int r = 0; r < m.rows; r++) std::memcpy(raw(rows + r), m.raw(r), (size_t)cols * esz(type_));
+    rows += m.rows;
   }
   Mat t() const {
     Mat out(cols, rows, type_);

@@ -65,6 +65,14 @@ def make_ref():
         out[k + "/digest"] = np.array(RC.digest(q, t, present, use_set))
         out[k + "/assign"] = assign
         out[k + "/n_kept"] = np.array(n)
+    for c in RC.STEREO:
+        st = RC.stereo_case(c)
+        r = R.stereo_matches(st)
+        k = "st/" + c[0]
+        out[k + "/digest"] = np.array(RC.digest(st))
+        out[k + "/uright"] = r["uright"]
+        out[k + "/depth"] = r["depth"]
+        out[k + "/n_matched"] = np.array(r["n_matched"])
     offs, desc = RC.compute_descriptor_case()
     chosen = np.array([R.compute_descriptor(desc[offs[i]:offs[i + 1]]) for i in range(len(offs) - 1)], np.int32)
     out["cd/digest"] = np.array(RC.digest(offs, desc))

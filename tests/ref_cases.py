@@ -21,6 +21,9 @@ def digest(*objs):
             for k in sorted(o):
                 h.update(str(k).encode())
                 feed(o[k])
+        elif isinstance(o, (list, tuple)):
+            for x in o:
+                feed(x)
         elif isinstance(o, np.ndarray):
             h.update(str(o.dtype).encode() + str(o.shape).encode())
             h.update(np.ascontiguousarray(o).tobytes())
@@ -103,6 +106,14 @@ def search_bf_case(c):
     present = (rng.random(n_t) < pf).astype(np.uint8)
     present[0] = 1
     return q, t, present, use_set
+
+
+# ---- 8(f) rank 2: Frame::ComputeStereoMatches
+STEREO = [("n1000_s0", 0, 1000), ("n2000_s1", 1, 2000), ("n2000_s2", 2, 2000), ("n300_s3", 3, 300)]
+
+
+def stereo_case(c):
+    return synth.make_stereo_pair(c[2], c[1])
 
 
 # ---- 8(f) rank 4: MapPoint::ComputeDescriptor

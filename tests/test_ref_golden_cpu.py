@@ -30,6 +30,11 @@ def test_oracle_search_bf(c):
     CK.check_search_bf(ref, c)
 
 
+@pytest.mark.parametrize("c", RC.STEREO, ids=[c[0] for c in RC.STEREO])
+def test_oracle_stereo(c):
+    CK.check_stereo(ref, c)
+
+
 def test_oracle_compute_descriptor():
     CK.check_compute_descriptor(ref)
 

@@ -49,6 +49,11 @@ def test_cuda_search_bf(impl, c):
     CK.check_search_bf(impl, c)
 
 
+@pytest.mark.parametrize("c", RC.STEREO, ids=[c[0] for c in RC.STEREO])
+def test_cuda_stereo(impl, c):
+    CK.check_stereo(impl, c)
+
+
 def test_cuda_compute_descriptor(impl):
     CK.check_compute_descriptor(impl)
 
