@@ -164,11 +164,22 @@ __device__ __forceinline__ double block_max(double v, double* red) {
 //      its outputs for the whole kernel and flushes them once.  (Windows in
 //      which a point is observed twice by the same camera take variant 1.)
 constexpr int DENSE_N = 64;   // padded reduced-system size of the dense path
+constexpr int DENSE_DS = 68;  // row stride (doubles) of the Y / W tiles: == 4 mod 16, so the four k-rows of
+                              // a DMMA fragment load (lanes: k = lane % 4, row = lane / 4) hit 16 distinct banks
+constexpr int DENSE_MAXT = 5; // 8x8 output tiles per warp: 36 upper tiles of the 64x64 product over 8 warps
 constexpr int DENSE_K = 96;   // 32 points x 3 per block round
 constexpr int DENSE_K2 = 64;  // 32 points x 2 residual rows per block round
 constexpr int DENSE_RC = 16;  // padded camera count of the residual tile
 __constant__ int c_up_a[21] = {0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 4, 4, 5};
 __constant__ int c_up_b[21] = {0, 1, 2, 3, 4, 5, 1, 2, 3, 4, 5, 2, 3, 4, 5, 3, 4, 5, 4, 5, 5};
+
+// D (8x8, fp64) += A (8x4, row) * B (4x8, col) on the tensor cores (SASS DMMA).  Fragments:
+// a = A[lane/4][lane%4], b = B[lane%4][lane/4], c0/c1 = C[lane/4][2*(lane%4) + 0/1].
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
 
 template <bool FULL, int ACC>
 __global__ void __launch_bounds__(BA_THREADS)
@@ -181,15 +192,15 @@ __global__ void __launch_bounds__(BA_THREADS)
   extern __shared__ __align__(16) double dsm[];
   // dynamic shared memory carve-up
   //   ACC 0: [Wsm 256x18]   ACC 1: [lin copy][Wsm 256x18]
-  //   ACC 2: [Yd 96x64 (aliased by the J tile 64x64)][Wd 96x64][Rd 64x16][gv 96]
+  //   ACC 2: [Yd 96x68 (aliased by the J tile 64x64)][Wd 96x68][Rd 64x16][gv 96]
   const int lin_n = p.n * p.n + (HCC + 12) * p.C;
   double* slin = dsm;
   double (*Wsm)[18] = reinterpret_cast<double (*)[18]>(ACC == 1 ? dsm + lin_n : dsm);
   double* Yd = dsm;
-  double* Wd = Yd + DENSE_K * DENSE_N;
-  double* Rd = Wd + DENSE_K * DENSE_N;
+  double* Wd = Yd + DENSE_K * DENSE_DS;
+  double* Rd = Wd + DENSE_K * DENSE_DS;
   double* gv = Rd + DENSE_K2 * DENSE_RC;
-  constexpr int DENSE_SMEM = 2 * DENSE_K * DENSE_N + DENSE_K2 * DENSE_RC + DENSE_K;
+  constexpr int DENSE_SMEM = 2 * DENSE_K * DENSE_DS + DENSE_K2 * DENSE_RC + DENSE_K;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, gl = lane & 7, gw = lane >> 3;
   if (ACC == 1) {
     for (int i = tid; i < lin_n; i += BA_THREADS) slin[i] = 0.0;
@@ -232,11 +243,30 @@ __global__ void __launch_bounds__(BA_THREADS)
       }
     }
   }
-  double sacc[4][4];  // ACC 2: this thread's 4x4 tile of Y W^T
+  // ACC 2: Y W^T (64x64, symmetric) as 36 upper 8x8 tiles, row-major, dealt contiguously to the
+  // 8 warps (4 or 5 each, so a warp's tiles mostly share the A fragment); lane holds 2 entries per tile
+  double sacc[DENSE_MAXT][2];
+  int tile_i[DENSE_MAXT], tile_j[DENSE_MAXT];
+  int ntile = 0;
 #pragma unroll
-  for (int a = 0; a < 4; a++)
+  for (int t = 0; t < DENSE_MAXT; t++) {
+    sacc[t][0] = sacc[t][1] = 0.0;
+    tile_i[t] = tile_j[t] = 0;
+  }
+  if (ACC == 2) {
+    const int t0 = (warp * 36) / 8, t1 = ((warp + 1) * 36) / 8;
+    ntile = t1 - t0;
 #pragma unroll
-    for (int c = 0; c < 4; c++) sacc[a][c] = 0.0;
+    for (int t = 0; t < DENSE_MAXT; t++) {
+      int rem = t0 + (t < ntile ? t : 0), r0 = 0;
+      while (rem >= 8 - r0) {
+        rem -= 8 - r0;
+        r0++;
+      }
+      tile_i[t] = r0;
+      tile_j[t] = r0 + rem;
+    }
+  }
   // block-uniform trip count (the dense path has block barriers inside)
   for (int blk = blockIdx.x * (BA_THREADS / 8); blk < p.P; blk += gridDim.x * (BA_THREADS / 8)) {
     const int pt = blk + warp * 4 + gw;
@@ -402,36 +432,36 @@ __global__ void __launch_bounds__(BA_THREADS)
             const double w1 = Jc[a] * Jp[1] + Jc[6 + a] * Jp[4];
             const double w2 = Jc[a] * Jp[2] + Jc[6 + a] * Jp[5];
             const int row = 6 * ci + a;
-            Wd[(slot * 3 + 0) * DENSE_N + row] = w0;
-            Wd[(slot * 3 + 1) * DENSE_N + row] = w1;
-            Wd[(slot * 3 + 2) * DENSE_N + row] = w2;
-            Yd[(slot * 3 + 0) * DENSE_N + row] = w0 * hi[0] + w1 * hi[1] + w2 * hi[2];
-            Yd[(slot * 3 + 1) * DENSE_N + row] = w0 * hi[1] + w1 * hi[3] + w2 * hi[4];
-            Yd[(slot * 3 + 2) * DENSE_N + row] = w0 * hi[2] + w1 * hi[4] + w2 * hi[5];
+            Wd[(slot * 3 + 0) * DENSE_DS + row] = w0;
+            Wd[(slot * 3 + 1) * DENSE_DS + row] = w1;
+            Wd[(slot * 3 + 2) * DENSE_DS + row] = w2;
+            Yd[(slot * 3 + 0) * DENSE_DS + row] = w0 * hi[0] + w1 * hi[1] + w2 * hi[2];
+            Yd[(slot * 3 + 1) * DENSE_DS + row] = w0 * hi[1] + w1 * hi[3] + w2 * hi[4];
+            Yd[(slot * 3 + 2) * DENSE_DS + row] = w0 * hi[2] + w1 * hi[4] + w2 * hi[5];
           }
         }
       }
       __syncthreads();
       {
-        const int ty = tid >> 4, tx = tid & 15;
-        const double* yp = Yd + 4 * ty;
-        const double* wp = Wd + 4 * tx;
-#pragma unroll 4
-        for (int k = 0; k < DENSE_K; k++) {
-          const double2 ya = *reinterpret_cast<const double2*>(yp + k * DENSE_N);
-          const double2 yb = *reinterpret_cast<const double2*>(yp + k * DENSE_N + 2);
-          const double2 wa = *reinterpret_cast<const double2*>(wp + k * DENSE_N);
-          const double2 wb = *reinterpret_cast<const double2*>(wp + k * DENSE_N + 2);
-          const double yv[4] = {ya.x, ya.y, yb.x, yb.y}, wv[4] = {wa.x, wa.y, wb.x, wb.y};
+        // S_tile += Y^T W over the block's 96 point coordinates, 4 at a time per DMMA
+        const double* yrow = Yd + (lane & 3) * DENSE_DS + (lane >> 2);
+        const double* wrow = Wd + (lane & 3) * DENSE_DS + (lane >> 2);
+#pragma unroll 2
+        for (int k0 = 0; k0 < DENSE_K; k0 += 4) {
+          double af[DENSE_MAXT], bf[DENSE_MAXT];
 #pragma unroll
-          for (int a = 0; a < 4; a++)
+          for (int t = 0; t < DENSE_MAXT; t++) {
+            af[t] = yrow[k0 * DENSE_DS + 8 * tile_i[t]];
+            bf[t] = wrow[k0 * DENSE_DS + 8 * tile_j[t]];
+          }
 #pragma unroll
-            for (int c2 = 0; c2 < 4; c2++) sacc[a][c2] += yv[a] * wv[c2];
+          for (int t = 0; t < DENSE_MAXT; t++)
+            if (t < ntile) dmma884(sacc[t][0], sacc[t][1], af[t], bf[t]);
         }
         if (tid < n) {  // Schur right-hand side row owned by this thread
           double a2 = 0;
 #pragma unroll 8
-          for (int k = 0; k < DENSE_K; k++) a2 += Yd[k * DENSE_N + tid] * gv[k];
+          for (int k = 0; k < DENSE_K; k++) a2 += Yd[k * DENSE_DS + tid] * gv[k];
           rown += a2;
         }
       }
@@ -446,8 +476,8 @@ __global__ void __launch_bounds__(BA_THREADS)
             for (int a = 0; a < 6; a++)
 #pragma unroll
               for (int c2 = 0; c2 < 3; c2++) {
-                Wd[(slot * 3 + c2) * DENSE_N + 6 * ci + a] = 0.0;
-                Yd[(slot * 3 + c2) * DENSE_N + 6 * ci + a] = 0.0;
+                Wd[(slot * 3 + c2) * DENSE_DS + 6 * ci + a] = 0.0;
+                Yd[(slot * 3 + c2) * DENSE_DS + 6 * ci + a] = 0.0;
               }
           }
         }
@@ -540,16 +570,21 @@ __global__ void __launch_bounds__(BA_THREADS)
     }
     if (FULL && tid < n && rown != 0.0) atomicAdd(&p.rhs_corr[tid], rown);
     if (FULL) {
-      const int ty = tid >> 4, tx = tid & 15;
 #pragma unroll
-      for (int a = 0; a < 4; a++)
+      for (int t = 0; t < DENSE_MAXT; t++) {
+        if (t >= ntile) continue;
 #pragma unroll
-        for (int c2 = 0; c2 < 4; c2++) {
-          const int row = 4 * ty + a, col = 4 * tx + c2;
-          // diagonal and upper camera blocks only (the solve mirrors the rest)
-          if (row < n && col < n && col / 6 >= row / 6 && sacc[a][c2] != 0.0)
-            atomicAdd(&p.S[(size_t)row * n + col], -sacc[a][c2]);
+        for (int q = 0; q < 2; q++) {
+          const int row = 8 * tile_i[t] + (lane >> 2), col = 8 * tile_j[t] + 2 * (lane & 3) + q;
+          const double v = sacc[t][q];
+          if (row >= n || col >= n || v == 0.0) continue;
+          // diagonal and upper camera blocks only (the solve mirrors the rest).  A diagonal tile
+          // holds both triangles; an off-diagonal tile that cuts through a 6x6 diagonal block
+          // supplies that block's lower entries by symmetry of W H^-1 W^T.
+          if (col / 6 >= row / 6) atomicAdd(&p.S[(size_t)row * n + col], -v);
+          if (tile_j[t] != tile_i[t] && col / 6 == row / 6) atomicAdd(&p.S[(size_t)col * n + row], -v);
         }
+      }
     }
   }
   double t = block_sum(cost_acc, red);
@@ -2032,15 +2067,18 @@ static int problem_solve(lorb_ba_problem* pb, const lorb_ba_options* optp, int s
   const size_t wsm_bytes = (size_t)BA_THREADS * 18 * 8;
   const size_t lin_small = (size_t)(HCC + 12) * pb->maxC;
   const size_t smem_build_full =
-      acc_mode == 2 ? (2 * (size_t)DENSE_K * DENSE_N + DENSE_K2 * DENSE_RC + DENSE_K) * 8
+      acc_mode == 2 ? (2 * (size_t)DENSE_K * DENSE_DS + DENSE_K2 * DENSE_RC + DENSE_K) * 8
                     : (acc_mode == 1 ? ((size_t)nmax * nmax + lin_small) * 8 + wsm_bytes : 0);
   const size_t smem_build_init =
-      acc_mode == 2 ? (2 * (size_t)DENSE_K * DENSE_N + DENSE_K2 * DENSE_RC + DENSE_K) * 8
+      acc_mode == 2 ? (2 * (size_t)DENSE_K * DENSE_DS + DENSE_K2 * DENSE_RC + DENSE_K) * 8
                     : (acc_mode == 1 ? ((size_t)nmax * nmax + lin_small) * 8 + wsm_bytes : 0);
   const size_t smem_solve = ((size_t)nmax * nmax + 2 * (size_t)nmax) * 8;
 #define LORB_BUILD_ATTR(FULL_, ACC_, BYTES_)                                                  \
   LORB_CUDA_TRY(cudaFuncSetAttribute(ba_build_kernel<FULL_, ACC_>,                             \
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BYTES_)))
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BYTES_))); \
+  LORB_CUDA_TRY(cudaFuncSetAttribute(ba_build_kernel<FULL_, ACC_>,                             \
+                                     cudaFuncAttributePreferredSharedMemoryCarveout,           \
+                                     (int)cudaSharedmemCarveoutMaxShared))
   if (acc_mode == 2) {
     LORB_BUILD_ATTR(true, 2, smem_build_full);
     LORB_BUILD_ATTR(false, 2, smem_build_init);
