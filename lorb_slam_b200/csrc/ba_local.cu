@@ -597,6 +597,346 @@ __global__ void __launch_bounds__(BA_THREADS)
   if (tid == 0 && t > 0.0) atomic_max_nonneg(&st->acc_gmax, t);
 }
 
+// ---- dense path, n = 6C <= 64 and unique (point, camera) pairs (BASELINE configs 3 / 4).
+// H_cc, g_c, the Schur right-hand side and the Schur products of a window are dense contractions
+// over its points.  The CTA is four independent WARP PAIRS; a pair owns 8 points per round and
+// keeps private dense tiles of them in shared memory:
+//     J  [16 x 64]  rows (point slot, residual component), columns camera parameters
+//     R  [16 x 16]  residual of that row per camera
+//     W, Y = W H_pp^-1  [24 x 64]  rows (point slot, point coordinate)
+// After one 64-thread named barrier the pair contracts its own tiles on the fp64 tensor cores
+// (DMMA m8n8k4): S_pair += Y^T W as 36 upper 8x8 tiles (18 per warp, compile-time lists, so a
+// k-step loads <= 11 fragments for 18 DMMAs) and H_cc += J^T J on the 13 tiles that meet a 6x6
+// diagonal block; g_c and the Schur rhs are one column dot product per thread.  A second pair
+// barrier, then every lane clears exactly what it stored.  No block-wide barrier and no atomic
+// in the round loop; the pairs are reduced through shared memory once at the end and the CTA
+// flushes one partial result.
+constexpr int DP_PTS = 8;                 // points per warp pair and round
+constexpr int DP_KW = 3 * DP_PTS;         // rows of the W / Y tiles
+constexpr int DP_KJ = 2 * DP_PTS;         // rows of the J / R tiles
+constexpr int DP_PAIR = 2 * DP_KW * DENSE_DS + DP_KJ * DENSE_DS + DP_KJ * DENSE_RC + DP_KW;  // doubles
+constexpr int DP_THREADS = 256;           // 4 warp pairs (384 threads = 6 pairs fit in smem but spill: measured slower)
+constexpr int DP_NPAIR = DP_THREADS / 64;
+constexpr int DP_SMEM_DOUBLES = DP_NPAIR * DP_PAIR;
+static_assert(DP_SMEM_DOUBLES >= DENSE_N * DENSE_N + HCC * 10 + 2 * DENSE_N + 16, "reduction buffer fits");
+
+__device__ __forceinline__ void pair_barrier(int pair) {
+  asm volatile("bar.sync %0, 64;" ::"r"(pair + 1) : "memory");
+}
+
+// Upper 8x8 tiles of the 64x64 product, split between the two warps of a pair.
+template <int HALF>
+struct DenseTiles {
+  static constexpr int NS = 18;
+  static constexpr int NH = HALF == 0 ? 7 : 6;
+  __device__ static constexpr int si(int t) {
+    constexpr int a0[18] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 1, 1, 2, 2, 2};
+    constexpr int a1[18] = {2, 2, 2, 3, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 6, 6, 7};
+    return HALF == 0 ? a0[t] : a1[t];
+  }
+  __device__ static constexpr int sj(int t) {
+    constexpr int a0[18] = {0, 1, 2, 3, 4, 5, 6, 7, 1, 2, 3, 4, 5, 6, 7, 2, 3, 4};
+    constexpr int a1[18] = {5, 6, 7, 3, 4, 5, 6, 7, 4, 5, 6, 7, 5, 6, 7, 6, 7, 7};
+    return HALF == 0 ? a0[t] : a1[t];
+  }
+  // tiles of J^T J that intersect a diagonal 6x6 block (block boundaries 24 and 48 are tile aligned)
+  __device__ static constexpr int hi(int t) {
+    constexpr int a0[7] = {0, 0, 1, 1, 2, 3, 3};
+    constexpr int a1[7] = {4, 4, 5, 6, 6, 7, 7};
+    return HALF == 0 ? a0[t] : a1[t];
+  }
+  __device__ static constexpr int hj(int t) {
+    constexpr int a0[7] = {0, 1, 1, 2, 2, 3, 4};
+    constexpr int a1[7] = {4, 5, 5, 6, 7, 7, 7};
+    return HALF == 0 ? a0[t] : a1[t];
+  }
+};
+
+template <int HALF, bool FULL>
+__device__ __forceinline__ void dense_contract(const double* __restrict__ Yt, const double* __restrict__ Wt,
+                                               const double* __restrict__ Jt, int lane,
+                                               double (&sacc)[18][2], double (&hacc)[7][2]) {
+  using T = DenseTiles<HALF>;
+  const int fo = (lane & 3) * DENSE_DS + (lane >> 2);
+#pragma unroll
+  for (int k0 = 0; k0 < DP_KJ; k0 += 4) {
+    double f[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) f[i] = Jt[fo + k0 * DENSE_DS + 8 * i];  // unused ones are eliminated
+#pragma unroll
+    for (int t = 0; t < T::NH; t++) dmma884(hacc[t][0], hacc[t][1], f[T::hi(t)], f[T::hj(t)]);
+  }
+  if (FULL) {
+#pragma unroll
+    for (int k0 = 0; k0 < DP_KW; k0 += 4) {
+      double a[8], b[8];
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        a[i] = Yt[fo + k0 * DENSE_DS + 8 * i];
+        b[i] = Wt[fo + k0 * DENSE_DS + 8 * i];
+      }
+#pragma unroll
+      for (int t = 0; t < T::NS; t++) dmma884(sacc[t][0], sacc[t][1], a[T::si(t)], b[T::sj(t)]);
+    }
+  }
+}
+
+// Adds this warp's accumulators into the CTA's reduction buffers (called by one pair at a time).
+template <int HALF, bool FULL>
+__device__ __forceinline__ void dense_reduce(double* __restrict__ Sbuf, double* __restrict__ Hbuf, int lane,
+                                             int n, const double (&sacc)[18][2], const double (&hacc)[7][2]) {
+  using T = DenseTiles<HALF>;
+#pragma unroll
+  for (int t = 0; t < T::NH; t++)
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+      const int row = 8 * T::hi(t) + (lane >> 2), col = 8 * T::hj(t) + 2 * (lane & 3) + q;
+      if (col < n && row / 6 == col / 6 && row <= col)
+        Hbuf[HCC * (row / 6) + upper_idx(row % 6, col % 6)] += hacc[t][q];
+    }
+  if (FULL) {
+#pragma unroll
+    for (int t = 0; t < T::NS; t++)
+#pragma unroll
+      for (int q = 0; q < 2; q++) {
+        const int row = 8 * T::si(t) + (lane >> 2), col = 8 * T::sj(t) + 2 * (lane & 3) + q;
+        Sbuf[row * DENSE_N + col] += sacc[t][q];
+      }
+  }
+}
+
+template <bool FULL>
+__global__ void __launch_bounds__(DP_THREADS)
+    ba_build_dense_kernel(const BADev* __restrict__ probs, lorb_ba_options opt, int force) {
+  const BADev p = probs[blockIdx.y];
+  LMState* st = p.st;
+  if (st->done && !force) return;
+  __shared__ double red[DP_THREADS / 32];
+  extern __shared__ __align__(16) double dsm[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, gl = lane & 7, gw = lane >> 3;
+  const int pair = warp >> 1, half = warp & 1, ptid = tid & 63;
+  double* const Yt = dsm + pair * DP_PAIR;
+  double* const Wt = Yt + DP_KW * DENSE_DS;
+  double* const Jt = Wt + DP_KW * DENSE_DS;
+  double* const Rt = Jt + DP_KJ * DENSE_DS;
+  double* const gv = Rt + DP_KJ * DENSE_RC;
+  for (int i = tid; i < DP_SMEM_DOUBLES; i += DP_THREADS) dsm[i] = 0.0;
+  __syncthreads();
+  const int cur = st->cur;
+  const double* cams = p.cams[cur];
+  const double* pts = p.pts[cur];
+  const double* camrot = p.camrot[cur];
+  const double radius = st->radius;
+  const int n = p.n;
+  double cost_acc = 0, gmax_acc = 0, xn_acc = 0, bad_acc = 0;
+  double sacc[18][2], hacc[7][2], gown = 0.0, rown = 0.0;
+#pragma unroll
+  for (int t = 0; t < 18; t++) sacc[t][0] = sacc[t][1] = 0.0;
+#pragma unroll
+  for (int t = 0; t < 7; t++) hacc[t][0] = hacc[t][1] = 0.0;
+  const int ps = half * 4 + gw;  // point slot inside the pair
+  // block-uniform trip count (pair barriers inside)
+  for (int blk = blockIdx.x * (DP_THREADS / 8); blk < p.P; blk += gridDim.x * (DP_THREADS / 8)) {
+    const int pt = blk + warp * 4 + gw;
+    const bool pv = pt < p.P;
+    int s = 0, e = 0;
+    double X[3] = {0, 0, 0}, sp[3] = {1, 1, 1};
+    if (pv) {
+      s = p.pt_ptr[pt];
+      e = p.pt_ptr[pt + 1];
+#pragma unroll
+      for (int a = 0; a < 3; a++) {
+        X[a] = pts[3 * (size_t)pt + a];
+        sp[a] = p.scale_p[3 * (size_t)pt + a];
+      }
+    }
+    const int rounds = __reduce_max_sync(0xffffffffu, (e - s + 7) >> 3);
+    // ---- phase 1: Jacobians -> J / R tiles, H_pp, g_p, cost
+    double h[6] = {0, 0, 0, 0, 0, 0}, g[3] = {0, 0, 0};
+    double r[2], Jc[12], Jp[6];
+    int cam = -1;
+    bool has = false;
+    for (int rd = 0; rd < rounds; rd++) {
+      const int o = s + rd * 8 + gl;
+      has = o < e;
+      if (has) {
+        cam = eval_obs(p, cams, camrot, o, X, sp, r, Jc, Jp);
+        cost_acc += r[0] * r[0] + r[1] * r[1];
+        h[0] += Jp[0] * Jp[0] + Jp[3] * Jp[3];
+        h[1] += Jp[0] * Jp[1] + Jp[3] * Jp[4];
+        h[2] += Jp[0] * Jp[2] + Jp[3] * Jp[5];
+        h[3] += Jp[1] * Jp[1] + Jp[4] * Jp[4];
+        h[4] += Jp[1] * Jp[2] + Jp[4] * Jp[5];
+        h[5] += Jp[2] * Jp[2] + Jp[5] * Jp[5];
+#pragma unroll
+        for (int a = 0; a < 3; a++) g[a] += Jp[a] * r[0] + Jp[3 + a] * r[1];
+        if (cam >= 0) {
+#pragma unroll
+          for (int comp = 0; comp < 2; comp++) {
+#pragma unroll
+            for (int a = 0; a < 6; a++) Jt[(ps * 2 + comp) * DENSE_DS + 6 * cam + a] = Jc[6 * comp + a];
+            Rt[(ps * 2 + comp) * DENSE_RC + cam] = r[comp];
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < 6; a++) h[a] = group_sum8(h[a]);
+#pragma unroll
+    for (int a = 0; a < 3; a++) g[a] = group_sum8(g[a]);
+    if (pv && gl == 0)
+      gmax_acc = fmax(gmax_acc, fmax(fabs(g[0] / sp[0]), fmax(fabs(g[1] / sp[1]), fabs(g[2] / sp[2]))));
+    if (!FULL) {
+      if (pv && gl == 0) {
+        if (opt.jacobi_scaling && force == 1) {
+          p.scale_p[3 * (size_t)pt + 0] = 1.0 / (1.0 + sqrt(h[0]));
+          p.scale_p[3 * (size_t)pt + 1] = 1.0 / (1.0 + sqrt(h[3]));
+          p.scale_p[3 * (size_t)pt + 2] = 1.0 / (1.0 + sqrt(h[5]));
+        }
+        xn_acc += X[0] * X[0] + X[1] * X[1] + X[2] * X[2];
+      }
+    } else {
+      // LM diagonal on the scaled columns, clamped (LevenbergMarquardtStrategy)
+      double hd[6] = {h[0], h[1], h[2], h[3], h[4], h[5]}, hi[6];
+      hd[0] += clamp_diag(h[0], opt.min_lm_diagonal, opt.max_lm_diagonal) / radius;
+      hd[3] += clamp_diag(h[3], opt.min_lm_diagonal, opt.max_lm_diagonal) / radius;
+      hd[5] += clamp_diag(h[5], opt.min_lm_diagonal, opt.max_lm_diagonal) / radius;
+      const bool ok = inv3_spd(hd, hi);
+      if (pv && gl == 0) {
+        if (!ok) bad_acc += 1.0;
+#pragma unroll
+        for (int a = 0; a < 6; a++) p.pt_hinv[6 * (size_t)pt + a] = ok ? hi[a] : 0.0;
+#pragma unroll
+        for (int a = 0; a < 3; a++) p.pt_gp[3 * (size_t)pt + a] = g[a];
+      }
+      if (!ok) {
+#pragma unroll
+        for (int a = 0; a < 6; a++) hi[a] = 0.0;
+      }
+      // ---- phase 2: W_i and Y_i = W_i H_pp^-1 into the pair's tiles
+      if (gl == 0) {
+#pragma unroll
+        for (int b2 = 0; b2 < 3; b2++) gv[ps * 3 + b2] = pv ? g[b2] : 0.0;
+      }
+      for (int ri = 0; ri < rounds; ri++) {
+        const int oi = s + ri * 8 + gl;
+        const bool has_i = oi < e;
+        int ci = -1;
+        if (rounds > 1) {
+          if (has_i) ci = eval_obs(p, cams, camrot, oi, X, sp, r, Jc, Jp);
+        } else {
+          ci = has ? cam : -1;  // single round: the Jacobians of phase 1 are still live
+        }
+        if (has_i && ci >= 0) {
+#pragma unroll
+          for (int a = 0; a < 6; a++) {
+            const double w0 = Jc[a] * Jp[0] + Jc[6 + a] * Jp[3];
+            const double w1 = Jc[a] * Jp[1] + Jc[6 + a] * Jp[4];
+            const double w2 = Jc[a] * Jp[2] + Jc[6 + a] * Jp[5];
+            const int col = 6 * ci + a;
+            Wt[(ps * 3 + 0) * DENSE_DS + col] = w0;
+            Wt[(ps * 3 + 1) * DENSE_DS + col] = w1;
+            Wt[(ps * 3 + 2) * DENSE_DS + col] = w2;
+            Yt[(ps * 3 + 0) * DENSE_DS + col] = w0 * hi[0] + w1 * hi[1] + w2 * hi[2];
+            Yt[(ps * 3 + 1) * DENSE_DS + col] = w0 * hi[1] + w1 * hi[3] + w2 * hi[4];
+            Yt[(ps * 3 + 2) * DENSE_DS + col] = w0 * hi[2] + w1 * hi[4] + w2 * hi[5];
+          }
+        }
+      }
+    }
+    pair_barrier(pair);
+    // ---- contractions over the pair's 8 points
+    if (half == 0)
+      dense_contract<0, FULL>(Yt, Wt, Jt, lane, sacc, hacc);
+    else
+      dense_contract<1, FULL>(Yt, Wt, Jt, lane, sacc, hacc);
+    if (ptid < n) {  // one column of g_c (and of the Schur right-hand side) per thread of the pair
+      const int c2 = ptid / 6;
+      double a2 = 0;
+#pragma unroll
+      for (int k2 = 0; k2 < DP_KJ; k2++) a2 += Jt[k2 * DENSE_DS + ptid] * Rt[k2 * DENSE_RC + c2];
+      gown += a2;
+      if (FULL) {
+        double a3 = 0;
+#pragma unroll
+        for (int k = 0; k < DP_KW; k++) a3 += Yt[k * DENSE_DS + ptid] * gv[k];
+        rown += a3;
+      }
+    }
+    pair_barrier(pair);
+    // ---- clear exactly what this lane stored
+    for (int ri = 0; ri < rounds; ri++) {
+      const int oi = s + ri * 8 + gl;
+      if (oi < e) {
+        const int ci = p.obs_cam[oi];
+        if (ci >= 0) {
+#pragma unroll
+          for (int a = 0; a < 6; a++) {
+            Jt[(ps * 2 + 0) * DENSE_DS + 6 * ci + a] = 0.0;
+            Jt[(ps * 2 + 1) * DENSE_DS + 6 * ci + a] = 0.0;
+            if (FULL) {
+#pragma unroll
+              for (int c2 = 0; c2 < 3; c2++) {
+                Wt[(ps * 3 + c2) * DENSE_DS + 6 * ci + a] = 0.0;
+                Yt[(ps * 3 + c2) * DENSE_DS + 6 * ci + a] = 0.0;
+              }
+            }
+          }
+          Rt[(ps * 2 + 0) * DENSE_RC + ci] = 0.0;
+          Rt[(ps * 2 + 1) * DENSE_RC + ci] = 0.0;
+        }
+      }
+    }
+  }
+  // ---- reduce the four pairs through shared memory, flush once per CTA
+  __syncthreads();
+  double* const Sbuf = dsm;                        // 64 x 64
+  double* const Hbuf = Sbuf + DENSE_N * DENSE_N;   // 21 per camera
+  double* const Gbuf = Hbuf + HCC * 10 + 6;        // g_c
+  double* const Rbuf = Gbuf + DENSE_N;             // Schur rhs
+  for (int i = tid; i < DENSE_N * DENSE_N + HCC * 10 + 6 + 2 * DENSE_N; i += DP_THREADS) dsm[i] = 0.0;
+  __syncthreads();
+  for (int pp = 0; pp < DP_NPAIR; pp++) {
+    if (pair == pp) {
+      if (half == 0)
+        dense_reduce<0, FULL>(Sbuf, Hbuf, lane, n, sacc, hacc);
+      else
+        dense_reduce<1, FULL>(Sbuf, Hbuf, lane, n, sacc, hacc);
+      if (ptid < n) {
+        Gbuf[ptid] += gown;
+        if (FULL) Rbuf[ptid] += rown;
+      }
+    }
+    __syncthreads();
+  }
+  for (int i = tid; i < HCC * p.C; i += DP_THREADS)
+    if (Hbuf[i] != 0.0) atomicAdd(&p.Hcc[i], Hbuf[i]);
+  if (tid < n) {
+    if (Gbuf[tid] != 0.0) atomicAdd(&p.gc[tid], Gbuf[tid]);
+    if (FULL && Rbuf[tid] != 0.0) atomicAdd(&p.rhs_corr[tid], Rbuf[tid]);
+  }
+  if (FULL) {
+    for (int i = tid; i < DENSE_N * DENSE_N; i += DP_THREADS) {
+      const int row = i / DENSE_N, col = i % DENSE_N;
+      const double v = Sbuf[i];
+      if (row >= n || col >= n || v == 0.0) continue;
+      // diagonal and upper camera blocks only (the solve mirrors the rest).  Only upper TILES were
+      // computed: a tile that cuts through a 6x6 diagonal block supplies that block's lower
+      // entries by symmetry of W H^-1 W^T.
+      if (col / 6 >= row / 6) atomicAdd(&p.S[(size_t)row * n + col], -v);
+      if (row / 8 != col / 8 && col / 6 == row / 6) atomicAdd(&p.S[(size_t)col * n + row], -v);
+    }
+  }
+  double t = block_sum(cost_acc, red);
+  if (tid == 0 && t != 0.0) atomicAdd(&p.tail[0], t);
+  t = block_sum(xn_acc, red);
+  if (tid == 0 && t != 0.0) atomicAdd(&p.tail[1], t);
+  t = block_sum(bad_acc, red);
+  if (tid == 0 && t != 0.0) atomicAdd(&p.tail[2], t);
+  t = block_max(gmax_acc, red);
+  if (tid == 0 && t > 0.0) atomic_max_nonneg(&st->acc_gmax, t);
+}
+
 // ---- large path, camera side.  Work item = (camera, slice of its observation
 // list): one warp accumulates H_cc (21), g_c (6) and the Schur right-hand side
 // W H_pp^-1 g_p (6) of its slice in registers, reduces by shuffles and issues 33
@@ -1498,7 +1838,7 @@ __device__ __forceinline__ void lm_control(const BADev& p, const lorb_ba_options
   *p.st = loc;
 }
 
-__global__ void __launch_bounds__(BA_THREADS)
+__global__ void __launch_bounds__(BA_THREADS, 2)  // latency-bound gathers: two CTAs per SM (ncu: long_scoreboard)
     ba_backsub_kernel(const BADev* __restrict__ probs, lorb_ba_options opt, int fuse_control,
                       int* __restrict__ n_active) {
   const BADev p = probs[blockIdx.y];
@@ -2055,6 +2395,8 @@ static int problem_solve(lorb_ba_problem* pb, const lorb_ba_options* optp, int s
   LORB_REQUIRE(!sharded || (dist_ready(c) && nw == 1), "sharded solve needs lorb_dist_init and one window");
   const int gx_pts = std::max(1, std::min((pb->maxP + 31) / 32, std::max(1, c->sm_count * 8 / nw)));
   const dim3 grid_pts(gx_pts, nw);
+  const int ppc = DP_THREADS / 8;  // points per CTA round of the dense path
+  const dim3 grid_dense(std::max(1, std::min((pb->maxP + ppc - 1) / ppc, std::max(1, c->sm_count * 8 / nw))), nw);
   const dim3 grid_cam((pb->maxC + 127) / 128, nw);
   const int nmax = 6 * pb->maxC;
   const dim3 grid_fin(std::max(1, std::min(c->sm_count * 2 / std::min(nw, c->sm_count) + 1, (nmax * nmax + 255) / 256)), nw);
@@ -2080,8 +2422,10 @@ static int problem_solve(lorb_ba_problem* pb, const lorb_ba_options* optp, int s
                                      cudaFuncAttributePreferredSharedMemoryCarveout,           \
                                      (int)cudaSharedmemCarveoutMaxShared))
   if (acc_mode == 2) {
-    LORB_BUILD_ATTR(true, 2, smem_build_full);
-    LORB_BUILD_ATTR(false, 2, smem_build_init);
+    LORB_CUDA_TRY(cudaFuncSetAttribute(ba_build_dense_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)(DP_SMEM_DOUBLES * 8)));
+    LORB_CUDA_TRY(cudaFuncSetAttribute(ba_build_dense_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)(DP_SMEM_DOUBLES * 8)));
   } else if (acc_mode == 1) {
     LORB_BUILD_ATTR(true, 1, smem_build_full);
     LORB_BUILD_ATTR(false, 1, smem_build_init);
@@ -2095,7 +2439,8 @@ static int problem_solve(lorb_ba_problem* pb, const lorb_ba_options* optp, int s
 #define LORB_BUILD(FULL_, ACC_) \
   LORB_LAUNCH(c, (ba_build_kernel<FULL_, ACC_>), grid_pts, BA_THREADS, sm, dp, opt, force)
     if (acc_mode == 2) {
-      if (full) LORB_BUILD(true, 2); else LORB_BUILD(false, 2);
+      if (full) LORB_LAUNCH(c, ba_build_dense_kernel<true>, grid_dense, DP_THREADS, DP_SMEM_DOUBLES * 8, dp, opt, force);
+      else      LORB_LAUNCH(c, ba_build_dense_kernel<false>, grid_dense, DP_THREADS, DP_SMEM_DOUBLES * 8, dp, opt, force);
     } else if (acc_mode == 1) {
       if (full) LORB_BUILD(true, 1); else LORB_BUILD(false, 1);
     } else {

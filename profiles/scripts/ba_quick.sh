@@ -17,3 +17,5 @@ for _ in range(5):
     prob.reset(); c.sync(); t0 = time.perf_counter(); s = prob.solve(opt); best = min(best, time.perf_counter() - t0)
 print('cfg3 resident solve: %.3f ms, iters %d' % (best * 1e3, s['iterations']))
 PY
+python profiles/scripts/ba_batch_prof.py > /dev/null 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches_bab_q.csv python profiles/scripts/ba_batch_prof.py > /dev/null 2>&1
+python profiles/scripts/launch_summary.py gpurun_out/launches_bab_q.csv
