@@ -360,6 +360,15 @@ def extras(ctx, local):
         out["proj_5000pts_2000kp_th%g_e2e" % th] = {
             "us_per_call": dt * 1e6, "map_points_per_s": 5000 / dt,
             "candidate_pairs": r["n_candidates"], "candidate_pairs_per_s": r["n_candidates"] / dt}
+    # next row: Frame::ComputeStereoMatches, 1000 features on a 640x480 stereo pair
+    st = synth.make_stereo_pair(1000, 0)
+    r = ctx.stereo_matches(st)
+    t0 = time.perf_counter()
+    reps = 30
+    for _ in range(reps):
+        ctx.stereo_matches(st)
+    dt = (time.perf_counter() - t0) / reps
+    out["stereo_matches_1000kp_640x480_e2e"] = {"us_per_call": dt * 1e6, "n_matched": r["n_matched"]}
     # cfg 3: local BA, 10 LM iterations
     pb = synth.make_ba_problem(0, C=10, P=5000)
     opt = _ba_opts_fixed_iters(capi)
@@ -383,6 +392,42 @@ def extras(ctx, local):
     return out
 
 
+def _ba_rooflines(ctx, obs_per_launch, k_obs_per_point, n_reduced, build, backsub, solve, traffic, traffic_src):
+    """roofline objects of one BA LM attempt from the library's own CUDA-event brackets
+    (lorb_ctx_profile: slot 0 build pass, 1 back-substitution, 2 reduced-system solve).
+    FLOP model of SURVEY 8(d): per observation 150 (linearise) + 216 (accumulate) + 216*k (Schur
+    products, k observations per point) in the build pass, 60 in the back-substitution; the reduced
+    solve is n^3/3 + 2 n^2.  Algorithmic bytes: 16 B per observation and pass (recompute-J design)."""
+    hbm_peak, peak_src = _peaks()
+    dfma = ctx.microbench_fp64(0, 4096)
+    dmma = ctx.microbench_fp64(1, 4096)
+    fp64_peak = max(dfma, dmma)
+    parts = {
+        "build": (build, obs_per_launch * (150.0 + 216.0 + 216.0 * k_obs_per_point), obs_per_launch * 16.0),
+        "backsub": (backsub, obs_per_launch * 60.0, obs_per_launch * 32.0),
+        "reduced_solve": (solve, n_reduced ** 3 / 3.0 + 2.0 * n_reduced ** 2, n_reduced * n_reduced * 8.0),
+    }
+    name = max(parts, key=lambda k: parts[k][0][0])
+    (ms_tot, n), flop, byt = parts[name]
+    ms = ms_tot / max(1, n)
+    shares = {k: v[0][0] for k, v in parts.items()}
+    tot = sum(shares.values()) or 1.0
+    roof = {"bound": "tensor", "bound_detail": "fp64: DMMA tensor-core contractions + DFMA Jacobians; latency-bound per ncu "
+                                               "(profiles/README.md), HBM fraction below 1 %",
+            "kernel": name, "avg_launch_ms": ms, "launches": int(n),
+            "achieved": flop / (ms * 1e-3) / 1e12, "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
+            "frac": flop / (ms * 1e-3) / fp64_peak,
+            "peak_source": "measured in this run: lorb_microbench_fp64 (DFMA %.1f, DMMA %.1f TFLOP/s), whole GPU"
+                           % (dfma / 1e12, dmma / 1e12),
+            "flop_model": "SURVEY 8(d): algorithmic flops of the kernel per launch",
+            "share_of_attempt": {k: v / tot for k, v in shares.items()},
+            "traffic": traffic, "traffic_source": traffic_src}
+    hbm = {"bound": "hbm", "kernel": name, "achieved": byt / (ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+           "frac": byt / (ms * 1e-3) / 1e9 / hbm_peak, "peak_source": peak_src,
+           "note": "algorithmic bytes of the same kernel; BA on this design is not HBM-bound"}
+    return roof, hbm
+
+
 def run_ba_batched(args, rank, world, local):
     """BASELINE config 4: 512 independent 10-keyframe windows sharded over ranks
     (weak scaling variant: `--windows` per GPU, default 512/8 = 64)."""
@@ -403,6 +448,7 @@ def run_ba_batched(args, rank, world, local):
     if rank == 0:
         sampler.start()
     l0 = ctx.launch_count
+    ctx.profile(True)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         prob.reset()
@@ -410,6 +456,8 @@ def run_ba_batched(args, rank, world, local):
     ctx.sync()
     dt = time.perf_counter() - t0
     launches = ctx.launch_count - l0
+    prof = [ctx.profile_read(k) for k in range(3)]
+    ctx.profile(False)
     clocks = sampler.stop() if rank == 0 else None
     dt_max = _max_over_ranks(dt, world, local)
     prob.close()
@@ -444,6 +492,10 @@ def run_ba_batched(args, rank, world, local):
                        "d2h_bytes_per_step": int(bt["cams"].nbytes + bt["pts"].nbytes)},
                "gpu_launches": int(launches), "clocks": clocks,
                "ms_per_local_ba": dt_max / args.steps / nw * 1e3, "lm_iterations": iters}
+        res["roofline"], res["roofline_hbm"] = _ba_rooflines(
+            ctx, obs, 6.0, 60, prof[0], prof[1], prof[2], 43960832 if nw == 64 else None,
+            "dram__bytes_read+write of ba_build_dense_kernel<1> per launch (64 windows), ncu --set full, "
+            "profiles/r01_ba_batched64_ncu_full.txt")
     ctx.close()
     return res, None
 
@@ -475,6 +527,7 @@ def run_ba_large(args, rank, world, local):
     if rank == 0:
         sampler.start()
     l0 = ctx.launch_count
+    ctx.profile(True)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         prob.reset()
@@ -482,6 +535,8 @@ def run_ba_large(args, rank, world, local):
     ctx.sync()
     dt = time.perf_counter() - t0
     launches = ctx.launch_count - l0
+    prof = [ctx.profile_read(k) for k in range(3)]
+    ctx.profile(False)
     clocks = sampler.stop() if rank == 0 else None
     dt_max = _max_over_ranks(dt, world, local)
     prob.close()
@@ -516,6 +571,9 @@ def run_ba_large(args, rank, world, local):
                "gpu_launches": int(launches), "clocks": clocks,
                "ms_per_lm_iteration": dt_max / args.steps / s["iterations"] * 1e3,
                "lm_iterations": s["iterations"], "final_cost": s["final_cost"]}
+        res["roofline"], res["roofline_hbm"] = _ba_rooflines(
+            ctx, sh["O"] if "O" in sh else len(sh["obs_cam"]), 7.5, 6 * args.large_cams, prof[0], prof[1], prof[2],
+            None, None)
     if world > 1:
         ctx.dist_finalize()
     ctx.close()

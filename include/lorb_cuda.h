@@ -411,6 +411,21 @@ int lorb_dist_allreduce_f64(lorb_ctx* ctx, double* data, int n);
  * distance kernel body on register operands. */
 int lorb_microbench_popc(lorb_ctx* ctx, int kind, int iters, double* words_per_s);
 
+/* fp64 micro-benchmark for the BA roofline denominator ("a measured fp64 FMA
+ * peak"): independent DFMA chains on register operands over the whole GPU.  kind 0 = scalar
+ * DFMA (2 flop each), kind 1 = DMMA m8n8k4 on the tensor cores (512 flop per warp instruction).
+ * Returns floating-point operations per second. */
+int lorb_microbench_fp64(lorb_ctx* ctx, int kind, int iters, double* flop_per_s);
+
+/* Device-side timing of the library's own kernels, for bench.py's roofline: while enabled,
+ * the BA solver brackets its dominant kernels with CUDA events on the ctx stream
+ * (slot 0 = build pass of an LM attempt, 1 = back-substitution, 2 = reduced-system solve).
+ * lorb_ctx_profile_read synchronises the stream and returns the accumulated milliseconds and
+ * the number of bracketed launches of a slot since the last lorb_ctx_profile(ctx, 1). */
+#define LORB_PROF_SLOTS 4
+int lorb_ctx_profile(lorb_ctx* ctx, int enable);
+int lorb_ctx_profile_read(lorb_ctx* ctx, int slot, double* total_ms, long long* count);
+
 #ifdef __cplusplus
 }
 #endif

@@ -30,6 +30,7 @@ EXPORTS = [
     "lorb_ba_problem_create", "lorb_ba_problem_create_batched", "lorb_ba_problem_reset", "lorb_ba_problem_solve",
     "lorb_ba_problem_download", "lorb_ba_problem_destroy", "lorb_dist_get_unique_id",
     "lorb_dist_init", "lorb_dist_finalize", "lorb_dist_allreduce_f64", "lorb_microbench_popc",
+    "lorb_microbench_fp64", "lorb_ctx_profile", "lorb_ctx_profile_read",
 ]
 
 
@@ -393,6 +394,21 @@ class Context:
         return a
 
     # -- diagnostics
+    def microbench_fp64(self, kind=0, iters=4096):
+        """flop/s of independent DFMA chains (kind 0) or DMMA m8n8k4 (kind 1), whole GPU."""
+        v = C.c_double()
+        _check(self._lib.lorb_microbench_fp64(self._h, int(kind), int(iters), C.byref(v)))
+        return v.value
+
+    def profile(self, enable=True):
+        _check(self._lib.lorb_ctx_profile(self._h, 1 if enable else 0))
+
+    def profile_read(self, slot):
+        """-> (total milliseconds, launches) of a bracketed kernel slot (see lorb_cuda.h)."""
+        ms, n = C.c_double(), C.c_longlong()
+        _check(self._lib.lorb_ctx_profile_read(self._h, int(slot), C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
     def microbench_popc(self, kind=0, iters=4096):
         r = C.c_double()
         _check(self._lib.lorb_microbench_popc(self._h, int(kind), int(iters), C.byref(r)))

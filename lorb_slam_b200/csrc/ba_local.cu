@@ -2474,11 +2474,14 @@ static int problem_solve(lorb_ba_problem* pb, const lorb_ba_options* optp, int s
   for (int it = 0; it < opt.max_num_iterations; it++) {
     LORB_CUDA_TRY(cudaMemsetAsync(pb->lin_base, 0, pb->lin_bytes_total, s));
     LORB_CUDA_TRY(cudaMemsetAsync(d_active, 0, 4, s));
+    prof_begin(c, 0);
     LORB_TRY(launch_build(true, 0));
+    prof_end(c, 0);
     if (sharded) {
       LORB_TRY(dist_allreduce_sum(c, d0.lin, pb->lin_doubles_max));
       LORB_TRY(dist_allreduce_max_u64(c, &d0.st->acc_gmax, 1));
     }
+    prof_begin(c, 2);
     if (small) {
       LORB_LAUNCH(c, ba_solve_small_kernel, dim3(1, nw), 256, smem_solve, dp, opt);
     } else {
@@ -2487,7 +2490,10 @@ static int problem_solve(lorb_ba_problem* pb, const lorb_ba_options* optp, int s
       LORB_TRY(run_cholesky(pb));
       LORB_LAUNCH(c, ba_candcam_kernel, grid_cam, 128, 0, dp);
     }
+    prof_end(c, 2);
+    prof_begin(c, 1);
     LORB_LAUNCH(c, ba_backsub_kernel, grid_pts, BA_THREADS, 0, dp, opt, fuse_control, d_active);
+    prof_end(c, 1);
     if (sharded) {
       LORB_TRY(dist_allreduce_sum(c, &d0.st->acc_cost2, 4));
       LORB_LAUNCH(c, ba_control_kernel, nw, 1, 0, dp, opt, d_active);

@@ -63,6 +63,9 @@ struct lorb_ctx {
   int plan_n_pairs = 0, plan_max_kf = 0;
   lorb::Dist* dist = nullptr;
   void* ba_cache = nullptr;  // reusable lorb_ba_problem of the host-buffer BA calls (ba_local.cu)
+  // optional event timing of the library's own kernels (lorb_ctx_profile)
+  int prof_on = 0;
+  void* prof = nullptr;  // lorb::Prof (ctx.cu)
 };
 
 namespace lorb {
@@ -72,6 +75,10 @@ inline int pin_reserve(lorb_ctx* c, int slot, size_t bytes) {
   c->h[slot].pinned = true;
   return c->h[slot].reserve(bytes);
 }
+
+// Event brackets around a kernel (no-ops unless lorb_ctx_profile enabled them).
+void prof_begin(lorb_ctx* c, int slot);
+void prof_end(lorb_ctx* c, int slot);
 
 #define LORB_TRY(expr)          \
   do {                          \

@@ -3,6 +3,7 @@
 #include <stdarg.h>
 
 #include <new>
+#include <vector>
 
 #include "common.cuh"
 
@@ -72,11 +73,138 @@ __global__ void __launch_bounds__(256) popc_bench_kernel(uint32_t* sink, int ite
   if (r == 0x12345u) sink[0] = r;  // practically never; keeps the loop alive
 }
 
+// kind 0: 8 independent DFMA chains per thread; kind 1: 8 independent DMMA accumulators per warp.
+template <int KIND>
+__global__ void __launch_bounds__(256) fp64_bench_kernel(double* sink, int iters, double seed) {
+  double acc[8][2];
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    acc[k][0] = seed * (threadIdx.x + k);
+    acc[k][1] = seed * (blockIdx.x + k + 1);
+  }
+  const double a = 1.0 + seed * 1e-9 * threadIdx.x, b = 1.0 - seed * 1e-9;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      if (KIND == 0) {
+        acc[k][0] = fma(acc[k][0], a, b);
+        acc[k][1] = fma(acc[k][1], b, a);
+      } else {
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                     : "+d"(acc[k][0]), "+d"(acc[k][1])
+                     : "d"(a), "d"(b));
+      }
+    }
+  }
+  double r = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) r += acc[k][0] + acc[k][1];
+  if (r == 0.12345) sink[0] = r;
+}
+
+struct Prof {
+  struct Ev { cudaEvent_t a, b; int slot; };
+  std::vector<Ev> ev;
+  size_t used = 0;
+  double total[LORB_PROF_SLOTS] = {0, 0, 0, 0};
+  long long count[LORB_PROF_SLOTS] = {0, 0, 0, 0};
+};
+
+void prof_begin(lorb_ctx* c, int slot) {
+  if (!c->prof_on) return;
+  Prof* P = static_cast<Prof*>(c->prof);
+  if (P->used == P->ev.size()) {
+    Prof::Ev e;
+    if (cudaEventCreate(&e.a) != cudaSuccess || cudaEventCreate(&e.b) != cudaSuccess) return;
+    P->ev.push_back(e);
+  }
+  P->ev[P->used].slot = slot;
+  cudaEventRecord(P->ev[P->used].a, c->stream);
+}
+
+void prof_end(lorb_ctx* c, int slot) {
+  if (!c->prof_on) return;
+  Prof* P = static_cast<Prof*>(c->prof);
+  if (P->used >= P->ev.size() || P->ev[P->used].slot != slot) return;
+  cudaEventRecord(P->ev[P->used].b, c->stream);
+  P->used++;
+}
+
+static void prof_collect(lorb_ctx* c) {
+  Prof* P = static_cast<Prof*>(c->prof);
+  if (!P) return;
+  cudaStreamSynchronize(c->stream);
+  for (size_t i = 0; i < P->used; i++) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, P->ev[i].a, P->ev[i].b) == cudaSuccess) {
+      P->total[P->ev[i].slot] += ms;
+      P->count[P->ev[i].slot]++;
+    }
+  }
+  P->used = 0;
+}
+
 }  // namespace lorb
 
 using namespace lorb;
 
 extern "C" {
+
+int lorb_ctx_profile(lorb_ctx* c, int enable) {
+  LORB_REQUIRE(c, "ctx");
+  LORB_CUDA_TRY(cudaSetDevice(c->device));
+  if (!c->prof) c->prof = new (std::nothrow) Prof();
+  LORB_REQUIRE(c->prof, "profile state");
+  Prof* P = static_cast<Prof*>(c->prof);
+  prof_collect(c);
+  if (enable) {
+    for (int s = 0; s < LORB_PROF_SLOTS; s++) {
+      P->total[s] = 0;
+      P->count[s] = 0;
+    }
+  }
+  c->prof_on = enable ? 1 : 0;
+  return LORB_OK;
+}
+
+int lorb_ctx_profile_read(lorb_ctx* c, int slot, double* total_ms, long long* count) {
+  LORB_REQUIRE(c && c->prof && total_ms && count, "ctx / outputs (call lorb_ctx_profile first)");
+  LORB_REQUIRE(slot >= 0 && slot < LORB_PROF_SLOTS, "slot");
+  LORB_CUDA_TRY(cudaSetDevice(c->device));
+  prof_collect(c);
+  Prof* P = static_cast<Prof*>(c->prof);
+  *total_ms = P->total[slot];
+  *count = P->count[slot];
+  return LORB_OK;
+}
+
+int lorb_microbench_fp64(lorb_ctx* c, int kind, int iters, double* flop_per_s) {
+  LORB_REQUIRE(c && flop_per_s, "ctx/out");
+  LORB_REQUIRE(iters > 0 && (kind == 0 || kind == 1), "iters / kind");
+  LORB_CUDA_TRY(cudaSetDevice(c->device));
+  LORB_TRY(dev_reserve(c, 0, 256));
+  const int grid = c->sm_count * 8, block = 256;
+  cudaEvent_t e0, e1;
+  LORB_CUDA_TRY(cudaEventCreate(&e0));
+  LORB_CUDA_TRY(cudaEventCreate(&e1));
+  for (int rep = 0; rep < 2; rep++) {  // first pass warms up
+    LORB_CUDA_TRY(cudaEventRecord(e0, c->stream));
+    if (kind == 0)
+      LORB_LAUNCH(c, fp64_bench_kernel<0>, grid, block, 0, c->d[0].as<double>(), iters, 1.000001);
+    else
+      LORB_LAUNCH(c, fp64_bench_kernel<1>, grid, block, 0, c->d[0].as<double>(), iters, 1.000001);
+    LORB_CUDA_TRY(cudaEventRecord(e1, c->stream));
+    LORB_CUDA_TRY(cudaEventSynchronize(e1));
+  }
+  float ms = 0;
+  LORB_CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  // kind 0: 16 DFMA (2 flop) per thread and iteration; kind 1: 8 DMMA (512 flop) per warp and iteration
+  const double per_iter = kind == 0 ? (double)grid * block * 16.0 * 2.0 : (double)grid * (block / 32) * 8.0 * 512.0;
+  *flop_per_s = per_iter * iters / (ms * 1e-3);
+  return LORB_OK;
+}
 
 const char* lorb_last_error(void) { return g_err; }
 const char* lorb_version(void) { return "lorb-b200 0.1 (sm_100a)"; }
@@ -123,6 +251,14 @@ int lorb_ctx_destroy(lorb_ctx* c) {
   c->bank.release();
   c->plan_pairs.release();
   c->plan_out.release();
+  if (c->prof) {
+    Prof* P = static_cast<Prof*>(c->prof);
+    for (auto& e : P->ev) {
+      cudaEventDestroy(e.a);
+      cudaEventDestroy(e.b);
+    }
+    delete P;
+  }
   cudaStreamDestroy(c->stream);
   delete c;
   return LORB_OK;
