@@ -155,23 +155,12 @@ __device__ __forceinline__ double block_max(double v, double* red) {
 //      ba_cam_rows_kernel and the Schur products in ba_schur_pairs_kernel, both
 //      segmented reductions in registers over host-built lists - no atomics in
 //      any inner loop
-//   2  n <= 64 (the 10-keyframe windows of BASELINE configs 3/4): H_cc / g_c / rhs
-//      and the Schur products are dense contractions per CTA, with NO atomics in
-//      the inner loop: the Jacobian rows of 32 points are stored into a dense
-//      64 x 64 tile (H_cc entries = dot products of its columns, g_c against a
-//      residual tile), then Y = W H_pp^-1 and W into dense 64 x 96 tiles and
-//      S -= Y W^T accumulates in registers (4x4 per thread); every thread owns
-//      its outputs for the whole kernel and flushes them once.  (Windows in
-//      which a point is observed twice by the same camera take variant 1.)
+//   (n <= 64 with unique (point, camera) pairs - the 10-keyframe windows of BASELINE
+//   configs 3/4 - do not come here: ba_build_dense_kernel below.)
 constexpr int DENSE_N = 64;   // padded reduced-system size of the dense path
 constexpr int DENSE_DS = 68;  // row stride (doubles) of the Y / W tiles: == 4 mod 16, so the four k-rows of
                               // a DMMA fragment load (lanes: k = lane % 4, row = lane / 4) hit 16 distinct banks
-constexpr int DENSE_MAXT = 5; // 8x8 output tiles per warp: 36 upper tiles of the 64x64 product over 8 warps
-constexpr int DENSE_K = 96;   // 32 points x 3 per block round
-constexpr int DENSE_K2 = 64;  // 32 points x 2 residual rows per block round
 constexpr int DENSE_RC = 16;  // padded camera count of the residual tile
-__constant__ int c_up_a[21] = {0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 4, 4, 5};
-__constant__ int c_up_b[21] = {0, 1, 2, 3, 4, 5, 1, 2, 3, 4, 5, 2, 3, 4, 5, 3, 4, 5, 4, 5, 5};
 
 // D (8x8, fp64) += A (8x4, row) * B (4x8, col) on the tensor cores (SASS DMMA).  Fragments:
 // a = A[lane/4][lane%4], b = B[lane%4][lane/4], c0/c1 = C[lane/4][2*(lane%4) + 0/1].
@@ -192,22 +181,14 @@ __global__ void __launch_bounds__(BA_THREADS)
   extern __shared__ __align__(16) double dsm[];
   // dynamic shared memory carve-up
   //   ACC 0: [Wsm 256x18]   ACC 1: [lin copy][Wsm 256x18]
-  //   ACC 2: [Yd 96x68 (aliased by the J tile 64x64)][Wd 96x68][Rd 64x16][gv 96]
   const int lin_n = p.n * p.n + (HCC + 12) * p.C;
   double* slin = dsm;
   double (*Wsm)[18] = reinterpret_cast<double (*)[18]>(ACC == 1 ? dsm + lin_n : dsm);
-  double* Yd = dsm;
-  double* Wd = Yd + DENSE_K * DENSE_DS;
-  double* Rd = Wd + DENSE_K * DENSE_DS;
-  double* gv = Rd + DENSE_K2 * DENSE_RC;
-  constexpr int DENSE_SMEM = 2 * DENSE_K * DENSE_DS + DENSE_K2 * DENSE_RC + DENSE_K;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, gl = lane & 7, gw = lane >> 3;
   if (ACC == 1) {
     for (int i = tid; i < lin_n; i += BA_THREADS) slin[i] = 0.0;
-  } else if (ACC == 2) {
-    for (int i = tid; i < DENSE_SMEM; i += BA_THREADS) dsm[i] = 0.0;
+    __syncthreads();
   }
-  if (ACC != 0) __syncthreads();
   double* const accS = ACC == 1 ? slin : p.S;
   double* const accH = ACC == 1 ? slin + (size_t)p.n * p.n : p.Hcc;
   double* const accG = accH + HCC * p.C;
@@ -219,55 +200,6 @@ __global__ void __launch_bounds__(BA_THREADS)
   const double radius = st->radius;
   const int n = p.n;
   double cost_acc = 0, gmax_acc = 0, xn_acc = 0, bad_acc = 0;
-  // ACC 2: outputs owned by this thread for the whole kernel: two entries of
-  // [H_cc (21 per camera) | g_c (6 per camera)], one row of the Schur rhs, a 4x4 tile of Y W^T
-  double hown[2] = {0.0, 0.0}, rown = 0.0;
-  int own_col_a[2] = {-1, -1}, own_col_b[2] = {0, 0};  // tile columns to multiply (b = -1: residual tile)
-  int own_cam[2] = {0, 0};
-  if (ACC == 2) {
-#pragma unroll
-    for (int q = 0; q < 2; q++) {
-      const int ent = tid + q * BA_THREADS;
-      if (ent < (HCC + 6) * p.C) {
-        if (ent < HCC * p.C) {
-          const int c2 = ent / HCC, idx = ent % HCC;
-          own_cam[q] = c2;
-          own_col_a[q] = 6 * c2 + c_up_a[idx];
-          own_col_b[q] = 6 * c2 + c_up_b[idx];
-        } else {
-          const int e2 = ent - HCC * p.C;
-          own_cam[q] = e2 / 6;
-          own_col_a[q] = e2;
-          own_col_b[q] = -1;
-        }
-      }
-    }
-  }
-  // ACC 2: Y W^T (64x64, symmetric) as 36 upper 8x8 tiles, row-major, dealt contiguously to the
-  // 8 warps (4 or 5 each, so a warp's tiles mostly share the A fragment); lane holds 2 entries per tile
-  double sacc[DENSE_MAXT][2];
-  int tile_i[DENSE_MAXT], tile_j[DENSE_MAXT];
-  int ntile = 0;
-#pragma unroll
-  for (int t = 0; t < DENSE_MAXT; t++) {
-    sacc[t][0] = sacc[t][1] = 0.0;
-    tile_i[t] = tile_j[t] = 0;
-  }
-  if (ACC == 2) {
-    const int t0 = (warp * 36) / 8, t1 = ((warp + 1) * 36) / 8;
-    ntile = t1 - t0;
-#pragma unroll
-    for (int t = 0; t < DENSE_MAXT; t++) {
-      int rem = t0 + (t < ntile ? t : 0), r0 = 0;
-      while (rem >= 8 - r0) {
-        rem -= 8 - r0;
-        r0++;
-      }
-      tile_i[t] = r0;
-      tile_j[t] = r0 + rem;
-    }
-  }
-  // block-uniform trip count (the dense path has block barriers inside)
   for (int blk = blockIdx.x * (BA_THREADS / 8); blk < p.P; blk += gridDim.x * (BA_THREADS / 8)) {
     const int pt = blk + warp * 4 + gw;
     const int slot = warp * 4 + gw;
@@ -303,7 +235,7 @@ __global__ void __launch_bounds__(BA_THREADS)
         h[5] += Jp[2] * Jp[2] + Jp[5] * Jp[5];
 #pragma unroll
         for (int a = 0; a < 3; a++) g[a] += Jp[a] * r[0] + Jp[3 + a] * r[1];
-        if (ACC != 3 && ACC != 2 && cam >= 0) {
+        if (ACC != 3 && cam >= 0) {
           double* H = accH + HCC * (size_t)cam;
           int k = 0;
 #pragma unroll
@@ -319,62 +251,6 @@ __global__ void __launch_bounds__(BA_THREADS)
     for (int a = 0; a < 6; a++) h[a] = group_sum8(h[a]);
 #pragma unroll
     for (int a = 0; a < 3; a++) g[a] = group_sum8(g[a]);
-    if (ACC == 2) {
-      // camera side without atomics: Jacobian rows / residuals of the block's 32 points
-      // into dense tiles, then every thread reduces the entries it owns
-      double* Jd = Yd;  // 64 x 64, row = (slot, residual component), column = camera parameter
-      for (int ri = 0; ri < rounds; ri++) {
-        const int oi = s + ri * 8 + gl;
-        const bool has_i = oi < e;
-        int ci = -1;
-        if (rounds > 1) {
-          if (has_i) ci = eval_obs(p, cams, camrot, oi, X, sp, r, Jc, Jp);
-        } else {
-          ci = has ? cam : -1;
-        }
-        if (has_i && ci >= 0) {
-#pragma unroll
-          for (int comp = 0; comp < 2; comp++) {
-#pragma unroll
-            for (int a = 0; a < 6; a++) Jd[(slot * 2 + comp) * DENSE_N + 6 * ci + a] = Jc[6 * comp + a];
-            Rd[(slot * 2 + comp) * DENSE_RC + ci] = r[comp];
-          }
-        }
-      }
-      __syncthreads();
-#pragma unroll
-      for (int q = 0; q < 2; q++) {
-        if (own_col_a[q] >= 0) {
-          double a2 = 0;
-          if (own_col_b[q] >= 0) {
-#pragma unroll 8
-            for (int k2 = 0; k2 < DENSE_K2; k2++)
-              a2 += Jd[k2 * DENSE_N + own_col_a[q]] * Jd[k2 * DENSE_N + own_col_b[q]];
-          } else {
-#pragma unroll 8
-            for (int k2 = 0; k2 < DENSE_K2; k2++)
-              a2 += Jd[k2 * DENSE_N + own_col_a[q]] * Rd[k2 * DENSE_RC + own_cam[q]];
-          }
-          hown[q] += a2;
-        }
-      }
-      __syncthreads();
-      for (int ri = 0; ri < rounds; ri++) {
-        const int oi = s + ri * 8 + gl;
-        if (oi < e) {
-          const int ci = p.obs_cam[oi];
-          if (ci >= 0) {
-#pragma unroll
-            for (int comp = 0; comp < 2; comp++) {
-#pragma unroll
-              for (int a = 0; a < 6; a++) Jd[(slot * 2 + comp) * DENSE_N + 6 * ci + a] = 0.0;
-              Rd[(slot * 2 + comp) * DENSE_RC + ci] = 0.0;
-            }
-          }
-        }
-      }
-      __syncthreads();
-    }
     if (!FULL) {
       if (pv && gl == 0) {
         if (opt.jacobi_scaling && force == 1) {
@@ -409,82 +285,6 @@ __global__ void __launch_bounds__(BA_THREADS)
     }
     // ---- phase 2: Schur products  S -= W_i Hinv W_j^T ,  rhs_corr += W_i Hinv g_p
     if (ACC == 3) continue;  // done by ba_cam_rows_kernel / ba_schur_pairs_kernel
-    if (ACC == 2) {
-      // dense path: store W_i and Y_i = W_i Hinv into the block's 64 x 96 tiles (plain stores:
-      // the (point, camera) pairs of a window are unique on this path)
-      if (gl == 0) {
-#pragma unroll
-        for (int b2 = 0; b2 < 3; b2++) gv[slot * 3 + b2] = pv ? g[b2] : 0.0;
-      }
-      for (int ri = 0; ri < rounds; ri++) {
-        const int oi = s + ri * 8 + gl;
-        const bool has_i = oi < e;
-        int ci = -1;
-        if (rounds > 1) {
-          if (has_i) ci = eval_obs(p, cams, camrot, oi, X, sp, r, Jc, Jp);
-        } else {
-          ci = has ? cam : -1;
-        }
-        if (has_i && ci >= 0) {
-#pragma unroll
-          for (int a = 0; a < 6; a++) {
-            const double w0 = Jc[a] * Jp[0] + Jc[6 + a] * Jp[3];
-            const double w1 = Jc[a] * Jp[1] + Jc[6 + a] * Jp[4];
-            const double w2 = Jc[a] * Jp[2] + Jc[6 + a] * Jp[5];
-            const int row = 6 * ci + a;
-            Wd[(slot * 3 + 0) * DENSE_DS + row] = w0;
-            Wd[(slot * 3 + 1) * DENSE_DS + row] = w1;
-            Wd[(slot * 3 + 2) * DENSE_DS + row] = w2;
-            Yd[(slot * 3 + 0) * DENSE_DS + row] = w0 * hi[0] + w1 * hi[1] + w2 * hi[2];
-            Yd[(slot * 3 + 1) * DENSE_DS + row] = w0 * hi[1] + w1 * hi[3] + w2 * hi[4];
-            Yd[(slot * 3 + 2) * DENSE_DS + row] = w0 * hi[2] + w1 * hi[4] + w2 * hi[5];
-          }
-        }
-      }
-      __syncthreads();
-      {
-        // S_tile += Y^T W over the block's 96 point coordinates, 4 at a time per DMMA
-        const double* yrow = Yd + (lane & 3) * DENSE_DS + (lane >> 2);
-        const double* wrow = Wd + (lane & 3) * DENSE_DS + (lane >> 2);
-#pragma unroll 2
-        for (int k0 = 0; k0 < DENSE_K; k0 += 4) {
-          double af[DENSE_MAXT], bf[DENSE_MAXT];
-#pragma unroll
-          for (int t = 0; t < DENSE_MAXT; t++) {
-            af[t] = yrow[k0 * DENSE_DS + 8 * tile_i[t]];
-            bf[t] = wrow[k0 * DENSE_DS + 8 * tile_j[t]];
-          }
-#pragma unroll
-          for (int t = 0; t < DENSE_MAXT; t++)
-            if (t < ntile) dmma884(sacc[t][0], sacc[t][1], af[t], bf[t]);
-        }
-        if (tid < n) {  // Schur right-hand side row owned by this thread
-          double a2 = 0;
-#pragma unroll 8
-          for (int k = 0; k < DENSE_K; k++) a2 += Yd[k * DENSE_DS + tid] * gv[k];
-          rown += a2;
-        }
-      }
-      __syncthreads();
-      // clear exactly what this lane wrote
-      for (int ri = 0; ri < rounds; ri++) {
-        const int oi = s + ri * 8 + gl;
-        if (oi < e) {
-          const int ci = p.obs_cam[oi];
-          if (ci >= 0) {
-#pragma unroll
-            for (int a = 0; a < 6; a++)
-#pragma unroll
-              for (int c2 = 0; c2 < 3; c2++) {
-                Wd[(slot * 3 + c2) * DENSE_DS + 6 * ci + a] = 0.0;
-                Yd[(slot * 3 + c2) * DENSE_DS + 6 * ci + a] = 0.0;
-              }
-          }
-        }
-      }
-      __syncthreads();
-      continue;
-    }
     for (int ri = 0; ri < rounds; ri++) {
       const int oi = s + ri * 8 + gl;
       const bool has_i = oi < e;
@@ -561,30 +361,6 @@ __global__ void __launch_bounds__(BA_THREADS)
     for (int i = tid; i < lin_n; i += BA_THREADS) {
       const double v = slin[i];
       if (v != 0.0) atomicAdd(&p.lin[i], v);
-    }
-  } else if (ACC == 2) {
-#pragma unroll
-    for (int q = 0; q < 2; q++) {
-      const int ent = tid + q * BA_THREADS;  // Hcc | gc are contiguous in lin
-      if (own_col_a[q] >= 0 && hown[q] != 0.0) atomicAdd(&p.Hcc[ent], hown[q]);
-    }
-    if (FULL && tid < n && rown != 0.0) atomicAdd(&p.rhs_corr[tid], rown);
-    if (FULL) {
-#pragma unroll
-      for (int t = 0; t < DENSE_MAXT; t++) {
-        if (t >= ntile) continue;
-#pragma unroll
-        for (int q = 0; q < 2; q++) {
-          const int row = 8 * tile_i[t] + (lane >> 2), col = 8 * tile_j[t] + 2 * (lane & 3) + q;
-          const double v = sacc[t][q];
-          if (row >= n || col >= n || v == 0.0) continue;
-          // diagonal and upper camera blocks only (the solve mirrors the rest).  A diagonal tile
-          // holds both triangles; an off-diagonal tile that cuts through a 6x6 diagonal block
-          // supplies that block's lower entries by symmetry of W H^-1 W^T.
-          if (col / 6 >= row / 6) atomicAdd(&p.S[(size_t)row * n + col], -v);
-          if (tile_j[t] != tile_i[t] && col / 6 == row / 6) atomicAdd(&p.S[(size_t)col * n + row], -v);
-        }
-      }
     }
   }
   double t = block_sum(cost_acc, red);
@@ -2409,10 +2185,10 @@ static int problem_solve(lorb_ba_problem* pb, const lorb_ba_options* optp, int s
   const size_t wsm_bytes = (size_t)BA_THREADS * 18 * 8;
   const size_t lin_small = (size_t)(HCC + 12) * pb->maxC;
   const size_t smem_build_full =
-      acc_mode == 2 ? (2 * (size_t)DENSE_K * DENSE_DS + DENSE_K2 * DENSE_RC + DENSE_K) * 8
+      acc_mode == 2 ? (size_t)DP_SMEM_DOUBLES * 8
                     : (acc_mode == 1 ? ((size_t)nmax * nmax + lin_small) * 8 + wsm_bytes : 0);
   const size_t smem_build_init =
-      acc_mode == 2 ? (2 * (size_t)DENSE_K * DENSE_DS + DENSE_K2 * DENSE_RC + DENSE_K) * 8
+      acc_mode == 2 ? (size_t)DP_SMEM_DOUBLES * 8
                     : (acc_mode == 1 ? ((size_t)nmax * nmax + lin_small) * 8 + wsm_bytes : 0);
   const size_t smem_solve = ((size_t)nmax * nmax + 2 * (size_t)nmax) * 8;
 #define LORB_BUILD_ATTR(FULL_, ACC_, BYTES_)                                                  \

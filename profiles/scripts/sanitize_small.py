@@ -14,6 +14,9 @@ fr = synth.make_frame(700, 1, stereo=True, claimed_frac=0.1); pts = synth.make_p
 c.search_proj_points(fr, pts, 1.0); c.search_proj_points(fr, pts, 15.0)
 cur, last = synth.make_frame_pair(600, 1); c.search_proj_frame(cur, last, 15.0)
 c.frustum_project(synth.make_frustum_points(1000, 1))
+c.stereo_matches(synth.make_stereo_pair(300, 1))
+offs = np.array([0, 3, 3, 10, 30], np.int32); c.compute_descriptors(offs, synth.descriptors_uniform(30, rng))
+c.profile(True)
 po = synth.make_pose_only(1, 200); c.ba_pose_only(po["xw"], po["uv"], po["K"], po["rt"])
 opt = capi.ba_options(max_num_iterations=4)
 c.ba_local(synth.make_ba_problem(1, C=4, P=150, obs_per_point=(3, 4), fixed_frac=0.1), opt)   # dense path
@@ -21,5 +24,6 @@ c.ba_local(synth.make_ba_problem(2, C=14, P=300, obs_per_point=(4, 5, 9)), opt) 
 c.ba_local(synth.make_ba_problem(3, C=20, P=400, obs_per_point=(4, 5, 11), traj_len=6.0), opt)  # work lists + dataflow
 pbs = [synth.make_ba_problem(10 + i, C=3 + i, P=60 + 10 * i, obs_per_point=(3,)) for i in range(3)]
 c.ba_local_batched(synth.batch_windows(pbs), opt)
+print(c.profile_read(0), c.microbench_fp64(0, 16), c.microbench_fp64(1, 16))
 c.close()
 print("SANITIZE_PASS_DONE")

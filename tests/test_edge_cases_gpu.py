@@ -109,3 +109,19 @@ def test_ba_point_observed_twice_by_one_camera(ctx):
     np.testing.assert_allclose(cams, oc, rtol=1e-6, atol=1e-8)
     np.testing.assert_allclose(pts, op, rtol=1e-6, atol=1e-8)
     assert s["iterations"] == o["iterations"]
+
+
+def test_profile_brackets_and_fp64_microbench(ctx):
+    """lorb_ctx_profile / lorb_microbench_fp64 (bench.py's roofline inputs)."""
+    from lorb_slam_b200 import capi
+    pb = synth.make_ba_problem(5, C=5, P=200, obs_per_point=(4,))
+    ctx.profile(True)
+    _, _, s = ctx.ba_local(pb, capi.ba_options(max_num_iterations=3, function_tolerance=-1.0,
+                                               parameter_tolerance=-1.0, gradient_tolerance=-1.0))
+    for slot in range(3):
+        ms, n = ctx.profile_read(slot)
+        assert n == s["iterations"] and ms > 0
+    ctx.profile(False)
+    ctx.ba_local(pb, capi.ba_options(max_num_iterations=2))
+    assert ctx.profile_read(0)[1] == s["iterations"]  # nothing recorded while disabled
+    assert ctx.microbench_fp64(0, 64) > 1e12 and ctx.microbench_fp64(1, 64) > 1e12
