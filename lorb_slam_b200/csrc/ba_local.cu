@@ -1199,6 +1199,55 @@ __global__ void __launch_bounds__(NB * NB / 4)
 // ready flag.  Every dependency of a tile has a smaller number, so the smallest
 // unfinished tile can always proceed: no deadlock while all CTAs are resident
 // (cooperative launch guarantees that).  Replaces 2 launches per block column.
+// 32x32 POTRF by ONE warp with the tile in registers (lane = row, fully unrolled): per column one
+// broadcast of the pivot, rsqrt, and 31-c shuffle + FMA pairs; no barriers.  The 256-thread
+// shared-memory version took 11.3 us per tile on the critical path of the dataflow factorisation
+// (globaltimer trace, profiles/README.md); this one is bound by ~150 dependent cycles per column.
+// In: A[r][c] (lower part valid).  Out: L_rc (r > c) at A[c][r], idg[c] = 1 / L_cc.
+__device__ __forceinline__ void potrf32_warp(double (*A)[NB + 1], double* idg, int* s_ok, int lane) {
+  double a[NB];
+#pragma unroll
+  for (int c = 0; c < NB; c++) a[c] = A[lane][c];
+#pragma unroll
+  for (int c = 0; c < NB; c++) {
+    double d = __shfl_sync(0xffffffffu, a[c], c);
+    if (!(d > 0.0)) {
+      if (lane == 0) *s_ok = 0;
+      d = 1.0;
+    }
+    const double is = rsqrt(d);
+    const double l = a[c] * is;  // L_rc for r >= c
+    a[c] = l;
+    if (lane == c) idg[c] = is;
+#pragma unroll
+    for (int q = c + 1; q < NB; q++) {
+      const double lq = __shfl_sync(0xffffffffu, l, q);  // L_qc
+      a[q] -= l * lq;  // meaningful for r >= q; the unused upper part may hold anything
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < NB; c++)
+    if (lane > c) A[c][lane] = a[c];
+}
+
+// X L^T = A for one 32x32 tile by ONE warp (lane = row of X, registers, right-looking):
+// B[m][c] = L_cm (m < c) is read as a shared-memory broadcast, idg[m] = 1 / L_mm.
+__device__ __forceinline__ void trsm32_warp(double (*A)[NB + 1], const double (*B)[NB + 1], const double* idg,
+                                            int lane) {
+  double a[NB];
+#pragma unroll
+  for (int c = 0; c < NB; c++) a[c] = A[lane][c];
+#pragma unroll
+  for (int m = 0; m < NB; m++) {
+    const double x = a[m] * idg[m];
+    a[m] = x;
+#pragma unroll
+    for (int c = m + 1; c < NB; c++) a[c] -= x * B[m][c];
+  }
+#pragma unroll
+  for (int c = 0; c < NB; c++) A[lane][c] = a[c];
+}
+
 __device__ __forceinline__ void flag_wait(const int* flag) {
   if (threadIdx.x == 0) {
     while (*reinterpret_cast<const volatile int*>(flag) == 0) {
@@ -1265,22 +1314,9 @@ __global__ void __launch_bounds__(256)
       for (int b = 0; b < 2; b++) A[2 * ty + a][2 * tx + b] = acc[a][b];
     __syncthreads();
     if (i == j) {
-      // POTRF in shared memory, L_rc (r>c) kept at A[c][r]
-      for (int c = 0; c < NB; c++) {
-        double d = A[c][c];
-        if (!(d > 0.0)) {
-          if (tid == 0) s_ok = 0;
-          d = 1.0;
-        }
-        const double is = rsqrt(d), inv_d = is * is;
-        if (tid == 0) idg[c] = is;
-        if (tid > c && tid < NB) A[c][tid] = A[tid][c] * is;
-        for (int r = c + 1 + ty; r < NB; r += 16) {
-          const double arc = A[r][c] * inv_d;
-          for (int q = c + 1 + tx; q <= r; q += 16) A[r][q] -= arc * A[q][c];
-        }
-        __syncthreads();
-      }
+      // POTRF: warp 0, tile in registers; L_rc (r>c) comes back at A[c][r]
+      if (tid < 32) potrf32_warp(A, idg, &s_ok, tid);
+      __syncthreads();
       for (int e = tid; e < NB * NB; e += 256) {
         const int r = e >> 5, c = e & 31;
         if (i0 + r < n && c < r) p.S[(size_t)(i0 + r) * n + j0 + c] = A[c][r];
@@ -1297,18 +1333,7 @@ __global__ void __launch_bounds__(256)
       }
       if (tid < NB) idg[tid] = __ldcg(&p.dinv[(size_t)j * NB + tid]);
       __syncthreads();
-      {
-        const int r = tid >> 3, sub = tid & 7;
-        for (int c = 0; c < NB; c++) {
-          double part = 0;
-          for (int m = sub; m < c; m += 8) part += A[r][m] * B[m][c];
-          part += __shfl_xor_sync(0xffffffffu, part, 4);
-          part += __shfl_xor_sync(0xffffffffu, part, 2);
-          part += __shfl_xor_sync(0xffffffffu, part, 1);
-          if (sub == 0) A[r][c] = (A[r][c] - part) * idg[c];
-          __syncwarp();
-        }
-      }
+      if (tid < 32) trsm32_warp(A, B, idg, tid);
       __syncthreads();
       for (int e = tid; e < NB * NB; e += 256) {
         const int r = e >> 5, c = e & 31;
