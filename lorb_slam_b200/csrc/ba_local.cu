@@ -1258,13 +1258,14 @@ __device__ __forceinline__ void flag_wait(const int* flag) {
 }
 
 __global__ void __launch_bounds__(256)
-    ba_chol_dataflow_kernel(const BADev* __restrict__ probs, int* __restrict__ flags, int T) {
+    ba_chol_dataflow_kernel(const BADev* __restrict__ probs, int* __restrict__ flags, int* __restrict__ yflag, int T) {
   const BADev p = probs[0];
   LMState* st = p.st;
   if (st->done) return;
   __shared__ double A[NB][NB + 1];   // source tile L_ik, then the tile being finished
   __shared__ double B[NB][NB + 1];   // source tile L_jk, then L_jj (transposed-slot form)
   __shared__ double idg[NB];
+  __shared__ double sk[NB], vec[NB];  // diagonal tiles: running right-hand side b_j - sum L_jk y_k, and y_k
   __shared__ int s_ok;
   const int n = p.n, tid = threadIdx.x;
   const int ty = tid >> 4, tx = tid & 15;
@@ -1278,6 +1279,9 @@ __global__ void __launch_bounds__(256)
     }
     const int i = j + (t - col_start);
     const int i0 = i * NB, j0 = j * NB;
+    // diagonal tiles: warp 1 carries the forward substitution (its lane r owns row r of b_j - sum L_jk y_k)
+    const bool ywarp = (i == j) && (tid >> 5) == 1;
+    double skreg = (ywarp && i0 + (tid & 31) < n) ? __ldcg(&p.rhs[i0 + (tid & 31)]) : 0.0, yreg = 0.0;
     // this thread's 2x2 patch of the tile
     double acc[2][2];
 #pragma unroll
@@ -1291,12 +1295,41 @@ __global__ void __launch_bounds__(256)
       flag_wait(&flags[i * T + k]);
       if (i != j) flag_wait(&flags[j * T + k]);
       const int k0 = k * NB;
-      for (int e = tid; e < NB * NB; e += 256) {
-        const int r = e >> 5, c = e & 31;
-        A[r][c] = (i0 + r < n) ? __ldcg(&p.S[(size_t)(i0 + r) * n + k0 + c]) : 0.0;
-        B[r][c] = (j0 + r < n) ? __ldcg(&p.S[(size_t)(j0 + r) * n + k0 + c]) : 0.0;
+      if (ywarp) {  // y_k was published right after POTRF(k): normally no wait; its load overlaps the tile loads
+        if ((tid & 31) == 0) {
+          while (*reinterpret_cast<const volatile int*>(&yflag[k]) == 0) {
+          }
+          __threadfence();
+        }
+        __syncwarp();
+        yreg = __ldcg(&p.rhs[k0 + (tid & 31)]);
+      }
+      {
+        // both source tiles in flight at once (8 independent loads per thread), then to shared memory
+        double ta[4], tb[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const int e = tid + 256 * q, r = e >> 5, c = e & 31;
+          ta[q] = (i0 + r < n) ? __ldcg(&p.S[(size_t)(i0 + r) * n + k0 + c]) : 0.0;
+          tb[q] = (j0 + r < n) ? __ldcg(&p.S[(size_t)(j0 + r) * n + k0 + c]) : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const int e = tid + 256 * q, r = e >> 5, c = e & 31;
+          A[r][c] = ta[q];
+          B[r][c] = tb[q];
+        }
       }
       __syncthreads();
+      if (ywarp) {
+        vec[tid & 31] = yreg;
+        __syncwarp();
+        double a2 = 0;
+#pragma unroll 8
+        for (int m = 0; m < NB; m++) a2 += A[tid & 31][m] * vec[m];
+        skreg -= a2;
+        __syncwarp();
+      }
 #pragma unroll 8
       for (int m = 0; m < NB; m++) {
         const double a0 = A[2 * ty][m], a1 = A[2 * ty + 1][m];
@@ -1312,6 +1345,7 @@ __global__ void __launch_bounds__(256)
     for (int a = 0; a < 2; a++)
 #pragma unroll
       for (int b = 0; b < 2; b++) A[2 * ty + a][2 * tx + b] = acc[a][b];
+    if (ywarp) sk[tid & 31] = skreg;
     __syncthreads();
     if (i == j) {
       // POTRF: warp 0, tile in registers; L_rc (r>c) comes back at A[c][r]
@@ -1343,6 +1377,21 @@ __global__ void __launch_bounds__(256)
     __threadfence();  // every thread publishes its part of the tile before the flag goes up
     __syncthreads();
     if (tid == 0) atomicExch(&flags[i * T + j], 1);
+    if (i == j && tid < 32) {
+      // L_jj y_j = b_j - sum_k L_jk y_k (off the factorisation's critical path: L_jj is already out).
+      // L_rc (r > c) sits at A[c][r], idg[c] = 1 / L_cc.
+      double v = sk[tid];
+#pragma unroll 8
+      for (int c = 0; c < NB; c++) {
+        const double yc = __shfl_sync(0xffffffffu, v, c) * idg[c];
+        if (tid == c) v = yc;
+        if (tid > c) v -= A[c][tid] * yc;
+      }
+      if (i0 + tid < n) p.rhs[i0 + tid] = v;
+      __threadfence();
+      __syncwarp();
+      if (tid == 0) atomicExch(&yflag[j], 1);
+    }
   }
   __syncthreads();
   if (tid == 0 && !s_ok) st->solve_ok = 0;
@@ -1355,11 +1404,11 @@ __global__ void __launch_bounds__(256)
 // likewise from the last block row up with the transposed tiles.  The chain is
 // T sequential publish/consume hops instead of 2T block steps of a single CTA.
 __global__ void __launch_bounds__(256)
-    ba_trisolve_dataflow_kernel(const BADev* __restrict__ probs, int* __restrict__ flags, int T) {
+    ba_trisolve_dataflow_kernel(const BADev* __restrict__ probs, int* __restrict__ flags, int T, int fwd_done) {
   const BADev p = probs[0];
   LMState* st = p.st;
   if (st->done) return;
-  __shared__ double Lt[2][NB][NB + 1];
+  __shared__ double Lt[3][NB][NB + 1];  // two streaming buffers + the diagonal tile (loaded once, up front)
   __shared__ double vec[NB];   // the consumed y_j / x_i
   __shared__ double part[8][NB];
   __shared__ double sk[NB];    // running right-hand side of this block row
@@ -1382,10 +1431,11 @@ __global__ void __launch_bounds__(256)
     sk[tid] = tid < kn ? __ldcg(&p.rhs[k0 + tid]) : 0.0;
     idg[tid] = __ldcg(&p.dinv[(size_t)k * NB + tid]);
   }
-  // ---------------- forward: L y = b
-  if (k > 0) load_tile(0, k, 0);
+  load_tile(2, k, k);
+  // ---------------- forward: L y = b (already done inside ba_chol_dataflow_kernel when fwd_done)
+  if (!fwd_done && k > 0) load_tile(0, k, 0);
   __syncthreads();
-  for (int j = 0; j < k; j++) {
+  for (int j = 0; j < (fwd_done ? 0 : k); j++) {
     if (j + 1 < k) load_tile((j + 1) & 1, k, j + 1);
     flag_wait(&yflag[j]);
     if (tid < NB) vec[tid] = __ldcg(&yv[j * NB + tid]);
@@ -1406,22 +1456,22 @@ __global__ void __launch_bounds__(256)
     }
     __syncthreads();
   }
-  load_tile(0, k, k);
-  __syncthreads();
-  if (tid < 32) {
-    double v = sk[tid];
-    for (int j = 0; j < kn; j++) {
-      const double yj = __shfl_sync(0xffffffffu, v, j) * idg[j];
-      if (tid == j) v = yj;
-      if (tid > j) v -= Lt[0][tid][j] * yj;
+  if (!fwd_done) {
+    if (tid < 32) {
+      double v = sk[tid];
+      for (int j = 0; j < kn; j++) {
+        const double yj = __shfl_sync(0xffffffffu, v, j) * idg[j];
+        if (tid == j) v = yj;
+        if (tid > j) v -= Lt[2][tid][j] * yj;
+      }
+      if (tid < kn) yv[k0 + tid] = v;
+      sk[tid] = tid < kn ? v : 0.0;
+      __threadfence();
+      __syncwarp();
+      if (tid == 0) atomicExch(&yflag[k], 1);
     }
-    if (tid < kn) yv[k0 + tid] = v;
-    sk[tid] = tid < kn ? v : 0.0;
-    __threadfence();
-    __syncwarp();
-    if (tid == 0) atomicExch(&yflag[k], 1);
+    __syncthreads();
   }
-  __syncthreads();
   // ---------------- backward: L^T x = y   (sk holds y_k)
   if (k + 1 < T) load_tile(1, T - 1, k);
   __syncthreads();
@@ -1447,14 +1497,12 @@ __global__ void __launch_bounds__(256)
     }
     __syncthreads();
   }
-  load_tile(0, k, k);
-  __syncthreads();
   if (tid < 32) {
     double v = sk[tid];
     for (int j = kn - 1; j >= 0; j--) {
       const double xj = __shfl_sync(0xffffffffu, v, j) * idg[j];
       if (tid == j) v = xj;
-      if (tid < j) v -= Lt[0][j][tid] * xj;
+      if (tid < j) v -= Lt[2][j][tid] * xj;
     }
     if (tid < kn) yv[k0 + tid] = v;
     __threadfence();
@@ -2161,13 +2209,14 @@ static int run_cholesky(lorb_ba_problem* pb) {
     int* flags = c->d[14].as<int>();
     LORB_CUDA_TRY(cudaMemsetAsync(flags, 0, ((size_t)nblk * nblk + 2 * (size_t)nblk) * 4, c->stream));
     int T = nblk;
-    void* args[] = {(void*)&dp, (void*)&flags, (void*)&T};
+    int* sflags = flags + (size_t)nblk * nblk;  // y flags [T], x flags [T]
+    void* args[] = {(void*)&dp, (void*)&flags, (void*)&sflags, (void*)&T};
     LORB_CUDA_TRY(cudaLaunchCooperativeKernel((void*)ba_chol_dataflow_kernel,
                                               dim3(std::min(n_tiles, coop_blocks)), dim3(256), args, 0,
                                               c->stream));
     c->launches++;
-    int* sflags = flags + (size_t)nblk * nblk;
-    void* args2[] = {(void*)&dp, (void*)&sflags, (void*)&T};
+    int fwd_done = 1;  // the factorisation kernel also ran the forward substitution
+    void* args2[] = {(void*)&dp, (void*)&sflags, (void*)&T, (void*)&fwd_done};
     LORB_CUDA_TRY(cudaLaunchCooperativeKernel((void*)ba_trisolve_dataflow_kernel, dim3(nblk),
                                               dim3(256), args2, 0, c->stream));
     c->launches++;
