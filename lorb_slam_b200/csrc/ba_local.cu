@@ -57,9 +57,9 @@ struct BADev {
   LMState* st;
   // large path only: camera-major / block-pair-major work lists (host built)
   const int* obs_pt;      // point of each observation (point-sorted observation order)
-  const int* cam_obs;     // observations grouped by camera
+  const int2* cam_obs;    // (observation, its point) grouped by camera
   const int4* cam_items;  // (camera, start in cam_obs, length, 0)
-  const int2* pairs;      // (observation i, observation j) grouped by camera block
+  const int4* pairs;      // (point, observation i, observation j, 0) grouped by camera block
   const int4* pair_items; // (ci, cj, start in pairs, length)
   int n_cam_items, n_pair_items;
 };
@@ -78,6 +78,27 @@ __global__ void ba_camrot_kernel(const BADev* __restrict__ probs, int which /*0 
   cam_rotation(p.cams[buf] + 6 * c, p.camrot[buf] + CAMROT * c, true);
 }
 
+// Observation of point X by window camera `cam` (>= 0) at pixel uv, with scaled Jacobians.
+__device__ __forceinline__ void eval_obs_cam(const BADev& p, const double* __restrict__ cams,
+                                             const double* __restrict__ camrot, int cam, float2 uv,
+                                             const double X[3], const double sp[3], double r[2], double Jc[12],
+                                             double Jp[6]) {
+  const double* t = cams + 6 * cam + 3;
+  const double tt[3] = {t[0], t[1], t[2]};
+  obs_eval<true, true>(camrot + CAMROT * cam, tt, X, p.K, (double)uv.x, (double)uv.y, r, Jc, Jp);
+  const double* sc = p.scale_c + 6 * cam;
+#pragma unroll
+  for (int a = 0; a < 6; a++) {
+    Jc[a] *= sc[a];
+    Jc[6 + a] *= sc[a];
+  }
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+    Jp[a] *= sp[a];
+    Jp[3 + a] *= sp[a];
+  }
+}
+
 // Evaluate observation `o` of point X with scaled Jacobians.
 __device__ __forceinline__ int eval_obs(const BADev& p, const double* __restrict__ cams,
                                         const double* __restrict__ camrot, int o, const double X[3],
@@ -86,20 +107,12 @@ __device__ __forceinline__ int eval_obs(const BADev& p, const double* __restrict
   const int cam = p.obs_cam[o];
   const float2 uv = p.obs_uv[o];
   if (cam >= 0) {
-    const double* t = cams + 6 * cam + 3;
-    const double tt[3] = {t[0], t[1], t[2]};
-    obs_eval<true, true>(camrot + CAMROT * cam, tt, X, p.K, (double)uv.x, (double)uv.y, r, Jc, Jp);
-    const double* sc = p.scale_c + 6 * cam;
-#pragma unroll
-    for (int a = 0; a < 6; a++) {
-      Jc[a] *= sc[a];
-      Jc[6 + a] *= sc[a];
-    }
-  } else {
-    const double* f = p.fixrt + 12 * (size_t)(-1 - cam);
-    const double tt[3] = {f[9], f[10], f[11]};
-    obs_eval<false, true>(f, tt, X, p.K, (double)uv.x, (double)uv.y, r, Jc, Jp);
+    eval_obs_cam(p, cams, camrot, cam, uv, X, sp, r, Jc, Jp);
+    return cam;
   }
+  const double* f = p.fixrt + 12 * (size_t)(-1 - cam);
+  const double tt[3] = {f[9], f[10], f[11]};
+  obs_eval<false, true>(f, tt, X, p.K, (double)uv.x, (double)uv.y, r, Jc, Jp);
 #pragma unroll
   for (int a = 0; a < 3; a++) {
     Jp[a] *= sp[a];
@@ -733,16 +746,19 @@ __global__ void __launch_bounds__(256)
   double acc[33];
 #pragma unroll
   for (int a = 0; a < 33; a++) acc[a] = 0.0;
+  // records are streamed one step ahead so that only one gather level (the point's data) is exposed
+  int2 rec = lane < it.z ? p.cam_obs[it.y + lane] : make_int2(0, 0);
   for (int e = lane; e < it.z; e += 32) {
-    const int o = p.cam_obs[it.y + e];
-    const int pt = p.obs_pt[o];
+    const int o = rec.x, pt = rec.y;
+    if (e + 32 < it.z) rec = p.cam_obs[it.y + e + 32];
+    const float2 uv = p.obs_uv[o];
     double X[3], sp[3], r[2], Jc[12], Jp[6];
 #pragma unroll
     for (int a = 0; a < 3; a++) {
       X[a] = pts[3 * (size_t)pt + a];
       sp[a] = p.scale_p[3 * (size_t)pt + a];
     }
-    eval_obs(p, cams, camrot, o, X, sp, r, Jc, Jp);
+    eval_obs_cam(p, cams, camrot, it.x, uv, X, sp, r, Jc, Jp);
     int k = 0;
 #pragma unroll
     for (int a = 0; a < 6; a++) {
@@ -803,9 +819,13 @@ __global__ void __launch_bounds__(256)
   double acc[36];
 #pragma unroll
   for (int a = 0; a < 36; a++) acc[a] = 0.0;
+  // records are streamed one step ahead: only the gathers of the point's data and the two pixels
+  // (one level, all independent) are exposed per step
+  int4 rec = lane < it.w ? p.pairs[it.z + lane] : make_int4(0, 0, 0, 0);
   for (int e = lane; e < it.w; e += 32) {
-    const int2 rec = p.pairs[it.z + e];
-    const int pt = p.obs_pt[rec.x];
+    const int pt = rec.x, oi = rec.y, oj = rec.z;
+    if (e + 32 < it.w) rec = p.pairs[it.z + e + 32];
+    const float2 uvi = p.obs_uv[oi], uvj = p.obs_uv[oj];
     double X[3], sp[3], r[2], Jc[12], Jp[6], Y[18];
 #pragma unroll
     for (int a = 0; a < 3; a++) {
@@ -814,7 +834,7 @@ __global__ void __launch_bounds__(256)
     }
     const double* hi = p.pt_hinv + 6 * (size_t)pt;
     const double h0 = hi[0], h1 = hi[1], h2 = hi[2], h3 = hi[3], h4 = hi[4], h5 = hi[5];
-    eval_obs(p, cams, camrot, rec.x, X, sp, r, Jc, Jp);
+    eval_obs_cam(p, cams, camrot, it.x, uvi, X, sp, r, Jc, Jp);
 #pragma unroll
     for (int a = 0; a < 6; a++) {
       const double w0 = Jc[a] * Jp[0] + Jc[6 + a] * Jp[3];
@@ -824,7 +844,7 @@ __global__ void __launch_bounds__(256)
       Y[3 * a + 1] = w0 * h1 + w1 * h3 + w2 * h4;
       Y[3 * a + 2] = w0 * h2 + w1 * h4 + w2 * h5;
     }
-    if (rec.y != rec.x) eval_obs(p, cams, camrot, rec.y, X, sp, r, Jc, Jp);
+    if (oj != oi) eval_obs_cam(p, cams, camrot, it.y, uvj, X, sp, r, Jc, Jp);
 #pragma unroll
     for (int b = 0; b < 6; b++) {
       const double w0 = Jc[b] * Jp[0] + Jc[6 + b] * Jp[3];
@@ -1928,9 +1948,10 @@ static int problem_build(lorb_ba_problem* pb, lorb_ctx* c, const std::vector<Win
   double* h_pts = reinterpret_cast<double*>(sg + sb_ptr + sb_cam + sb_uv + sb_fix + sb_cams);
   std::vector<size_t> o_ptr(nw), o_obs(nw), o_fix(nw);
   // large-path work lists (windows with 6C > 96), concatenated over windows
-  std::vector<int> h_obs_pt, h_cam_obs;
+  std::vector<int> h_obs_pt;
+  std::vector<int2> h_cam_obs;
   std::vector<int4> h_cam_items, h_pair_items;
-  std::vector<int2> h_pairs;
+  std::vector<int4> h_pairs;
   struct ListOff { size_t obs_pt, cam_obs, cam_items, pairs, pair_items; int n_cam_items, n_pair_items; };
   std::vector<ListOff> lo(nw, ListOff{0, 0, 0, 0, 0, 0, 0});
   pb->max_cam_items = pb->max_pair_items = 0;
@@ -2005,7 +2026,7 @@ static int problem_build(lorb_ba_problem* pb, lorb_ctx* c, const std::vector<Win
         {
           std::vector<int> cur(cnt.begin(), cnt.end() - 1);
           for (int e = 0; e < OT; e++)
-            if (cam[e] >= 0) h_cam_obs[L.cam_obs + cur[cam[e]]++] = e;
+            if (cam[e] >= 0) h_cam_obs[L.cam_obs + cur[cam[e]]++] = make_int2(e, h_obs_pt[L.obs_pt + e]);
         }
         L.cam_items = h_cam_items.size();
         for (int c2 = 0; c2 < W.C; c2++)
@@ -2030,7 +2051,7 @@ static int problem_build(lorb_ba_problem* pb, lorb_ctx* c, const std::vector<Win
               if (cam[e1] < 0) continue;
               for (int e2 = ptr[pp]; e2 < ptr[pp + 1]; e2++)
                 if (cam[e2] >= cam[e1])
-                  h_pairs[L.pairs + (size_t)cur[(size_t)cam[e1] * W.C + cam[e2]]++] = make_int2(e1, e2);
+                  h_pairs[L.pairs + (size_t)cur[(size_t)cam[e1] * W.C + cam[e2]]++] = make_int4(pp, e1, e2, 0);
             }
         }
         L.pair_items = h_pair_items.size();
@@ -2125,17 +2146,17 @@ static int problem_build(lorb_ba_problem* pb, lorb_ctx* c, const std::vector<Win
     }
   }
   {
-    const size_t b0 = al(h_obs_pt.size() * 4), b1 = al(h_cam_obs.size() * 4),
-                 b2 = al(h_cam_items.size() * 16), b3 = al(h_pairs.size() * 8),
+    const size_t b0 = al(h_obs_pt.size() * 4), b1 = al(h_cam_obs.size() * 8),
+                 b2 = al(h_cam_items.size() * 16), b3 = al(h_pairs.size() * 16),
                  b4 = al(h_pair_items.size() * 16);
     LORB_TRY(pb->lists.reserve(b0 + b1 + b2 + b3 + b4 + 256));
     uint8_t* lb = pb->lists.as<uint8_t>();
     cudaStream_t s2 = c->stream;
     if (!h_obs_pt.empty()) {
       LORB_CUDA_TRY(cudaMemcpyAsync(lb, h_obs_pt.data(), h_obs_pt.size() * 4, cudaMemcpyHostToDevice, s2));
-      LORB_CUDA_TRY(cudaMemcpyAsync(lb + b0, h_cam_obs.data(), h_cam_obs.size() * 4, cudaMemcpyHostToDevice, s2));
+      LORB_CUDA_TRY(cudaMemcpyAsync(lb + b0, h_cam_obs.data(), h_cam_obs.size() * 8, cudaMemcpyHostToDevice, s2));
       LORB_CUDA_TRY(cudaMemcpyAsync(lb + b0 + b1, h_cam_items.data(), h_cam_items.size() * 16, cudaMemcpyHostToDevice, s2));
-      LORB_CUDA_TRY(cudaMemcpyAsync(lb + b0 + b1 + b2, h_pairs.data(), h_pairs.size() * 8, cudaMemcpyHostToDevice, s2));
+      LORB_CUDA_TRY(cudaMemcpyAsync(lb + b0 + b1 + b2, h_pairs.data(), h_pairs.size() * 16, cudaMemcpyHostToDevice, s2));
       LORB_CUDA_TRY(cudaMemcpyAsync(lb + b0 + b1 + b2 + b3, h_pair_items.data(), h_pair_items.size() * 16, cudaMemcpyHostToDevice, s2));
       LORB_CUDA_TRY(cudaStreamSynchronize(s2));
     }
@@ -2143,9 +2164,9 @@ static int problem_build(lorb_ba_problem* pb, lorb_ctx* c, const std::vector<Win
       BADev& d = pb->h_dev[w];
       const ListOff& L = lo[w];
       d.obs_pt = reinterpret_cast<const int*>(lb) + L.obs_pt;
-      d.cam_obs = reinterpret_cast<const int*>(lb + b0) + L.cam_obs;
+      d.cam_obs = reinterpret_cast<const int2*>(lb + b0) + L.cam_obs;
       d.cam_items = reinterpret_cast<const int4*>(lb + b0 + b1) + L.cam_items;
-      d.pairs = reinterpret_cast<const int2*>(lb + b0 + b1 + b2) + L.pairs;
+      d.pairs = reinterpret_cast<const int4*>(lb + b0 + b1 + b2) + L.pairs;
       d.pair_items = reinterpret_cast<const int4*>(lb + b0 + b1 + b2 + b3) + L.pair_items;
       d.n_cam_items = L.n_cam_items;
       d.n_pair_items = L.n_pair_items;
