@@ -15,7 +15,7 @@ LIB = os.path.join(LIBDIR, "liblorb_cuda.so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-fopenmp", "-shared",
     # float code of the projection search must not contract a*b+c into FMA
     # (reference builds -O0 on baseline x86-64, CMakeLists.txt:5-6); the
     # kernels that need it use __fmul_rn/__fadd_rn explicitly, this is a belt.
@@ -41,7 +41,7 @@ def build_library(force=False, verbose=False):
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB] + sources() + ["-ldl"]
+    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB] + sources() + ["-ldl", "-lgomp"]
     env = dict(os.environ)
     # the image exports CC/CXX pointing at a gcc without OpenMP specs; nvcc only
     # needs a host compiler, use the system one

@@ -1957,24 +1957,52 @@ static int problem_build(lorb_ba_problem* pb, lorb_ctx* c, const std::vector<Win
   pb->max_cam_items = pb->max_pair_items = 0;
   pb->has_dup = false;
   {
-    size_t a = 0, b = 0, f = 0;
+    bool any_large = false;
+    {
+      size_t a = 0, b = 0, f = 0;
+      for (int w = 0; w < nw; w++) {
+        o_ptr[w] = a;
+        o_obs[w] = b;
+        o_fix[w] = f;
+        a += (size_t)ws[w].P + 1;
+        b += (size_t)ws[w].O + ws[w].F;
+        f += ws[w].F;
+        any_large = any_large || 6 * ws[w].C > 96;
+      }
+    }
+    // Staging one window touches only its own slices, so a batch of small windows is staged by
+    // all host threads; windows that need the large-path work lists (shared vectors) go serially.
+    int bad_obs = 0, bad_fix = 0, dup_any = 0;
+#pragma omp parallel for schedule(dynamic, 1) reduction(| : bad_obs, bad_fix, dup_any) if (nw > 3 && !any_large)
     for (int w = 0; w < nw; w++) {
       const WindowSpec& W = ws[w];
-      o_ptr[w] = a;
-      o_obs[w] = b;
-      o_fix[w] = f;
+      const size_t a = o_ptr[w], b = o_obs[w], f = o_fix[w];
       int* ptr = &h_ptr[a];
       for (int i = 0; i <= W.P; i++) ptr[i] = 0;
       bool sorted = W.F == 0;  // fast path: window observations already grouped by ascending point
+      bool bad = false;
       for (int i = 0; i < W.O; i++) {
-        LORB_REQUIRE(W.obs_pt[i] >= 0 && W.obs_pt[i] < W.P && W.obs_cam[i] >= 0 && W.obs_cam[i] < W.C,
-                     "observation index out of range");
+        if (!(W.obs_pt[i] >= 0 && W.obs_pt[i] < W.P && W.obs_cam[i] >= 0 && W.obs_cam[i] < W.C)) {
+          bad = true;
+          break;
+        }
         ptr[W.obs_pt[i] + 1]++;
         if (i > 0 && W.obs_pt[i] < W.obs_pt[i - 1]) sorted = false;
       }
+      if (bad) {
+        bad_obs |= 1;
+        continue;
+      }
       for (int i = 0; i < W.F; i++) {
-        LORB_REQUIRE(W.fix_pt[i] >= 0 && W.fix_pt[i] < W.P, "fixed observation point out of range");
+        if (!(W.fix_pt[i] >= 0 && W.fix_pt[i] < W.P)) {
+          bad = true;
+          break;
+        }
         ptr[W.fix_pt[i] + 1]++;
+      }
+      if (bad) {
+        bad_fix |= 1;
+        continue;
       }
       for (int i = 0; i < W.P; i++) ptr[i + 1] += ptr[i];
       std::vector<int> fill;
@@ -1997,16 +2025,18 @@ static int problem_build(lorb_ba_problem* pb, lorb_ctx* c, const std::vector<Win
         h_uv[b + d] = make_float2(W.fix_uv[2 * i], W.fix_uv[2 * i + 1]);
         host_fix_rotation(W.fix_rt + 6 * (size_t)i, &h_fix[12 * (f + i)]);
       }
-      if (6 * W.C <= DENSE_N && !pb->has_dup) {
+      if (6 * W.C <= DENSE_N) {
         // the atomic-free dense path stores (point, camera) tiles: needs unique pairs
         const int* cam2 = &h_cam[b];
-        for (int pp = 0; pp < W.P && !pb->has_dup; pp++)
-          for (int e1 = ptr[pp]; e1 < ptr[pp + 1] && !pb->has_dup; e1++)
+        bool dup = false;
+        for (int pp = 0; pp < W.P && !dup; pp++)
+          for (int e1 = ptr[pp]; e1 < ptr[pp + 1] && !dup; e1++)
             for (int e2 = e1 + 1; e2 < ptr[pp + 1]; e2++)
               if (cam2[e1] >= 0 && cam2[e1] == cam2[e2]) {
-                pb->has_dup = true;
+                dup = true;
                 break;
               }
+        if (dup) dup_any |= 1;
       }
       if (6 * W.C > 96) {
         const int OT = W.O + W.F;
@@ -2067,10 +2097,10 @@ static int problem_build(lorb_ba_problem* pb, lorb_ctx* c, const std::vector<Win
       }
       memcpy(&h_cams[6 * (size_t)pb->h_cam_off[w]], W.cams, (size_t)W.C * 48);
       if (W.P) memcpy(&h_pts[3 * (size_t)pb->h_pt_off[w]], W.pts, (size_t)W.P * 24);
-      a += (size_t)W.P + 1;
-      b += (size_t)W.O + W.F;
-      f += W.F;
     }
+    LORB_REQUIRE(!bad_obs, "observation index out of range");
+    LORB_REQUIRE(!bad_fix, "fixed observation point out of range");
+    pb->has_dup = dup_any != 0;
   }
   // ---- device layout
   const size_t cb = al(pb->cam_doubles * 8), pbts = al(std::max<size_t>(pb->pt_doubles, 1) * 8);
