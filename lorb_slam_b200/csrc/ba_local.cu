@@ -1007,6 +1007,59 @@ __global__ void __launch_bounds__(256) ba_chol_small_kernel(const BADev* __restr
   if (tid == 0 && !s_ok) st->solve_ok = 0;
 }
 
+constexpr int NB = 32;  // tile size of the dense factorisations
+
+// The same two warp-level tile operations on a shared-memory matrix with leading dimension ld that
+// keeps L transposed in its upper triangle (L_ij, i > j, at M[j*ld + i]; dg[j] = 1 / L_jj): the
+// layout of ba_solve_small_kernel.  kn / rn < 32 pad with identity / zero rows.
+__device__ __forceinline__ void potrf_tile_ld(double* M, int ld, int k0, int kn, double* dg, int* s_ok, int lane) {
+  double a[NB];
+#pragma unroll
+  for (int c = 0; c < NB; c++)
+    a[c] = (lane < kn && c < kn) ? M[(size_t)(k0 + lane) * ld + k0 + c] : (c == lane ? 1.0 : 0.0);
+#pragma unroll
+  for (int c = 0; c < NB; c++) {
+    double d = __shfl_sync(0xffffffffu, a[c], c);
+    if (!(d > 0.0)) {
+      if (lane == 0) *s_ok = 0;
+      d = 1.0;
+    }
+    const double is = rsqrt(d);
+    const double l = a[c] * is;
+    a[c] = l;
+    if (lane == c && c < kn) dg[k0 + c] = is;
+#pragma unroll
+    for (int q = c + 1; q < NB; q++) {
+      const double lq = __shfl_sync(0xffffffffu, l, q);
+      a[q] -= l * lq;
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < NB; c++)
+    if (lane > c && lane < kn) M[(size_t)(k0 + c) * ld + k0 + lane] = a[c];
+}
+
+// rows r0 .. r0+rn of the panel below the diagonal tile at k0: X L_kk^T = A_rk
+__device__ __forceinline__ void trsm_tile_ld(double* M, int ld, int r0, int rn, int k0, int kn, const double* dg,
+                                             int lane) {
+  double a[NB];
+#pragma unroll
+  for (int c = 0; c < NB; c++) a[c] = (lane < rn && c < kn) ? M[(size_t)(r0 + lane) * ld + k0 + c] : 0.0;
+#pragma unroll
+  for (int m = 0; m < NB; m++) {
+    if (m < kn) {  // uniform
+      const double x = a[m] * dg[k0 + m];
+      a[m] = x;
+#pragma unroll
+      for (int c = m + 1; c < NB; c++)
+        if (c < kn) a[c] -= x * M[(size_t)(k0 + m) * ld + k0 + c];  // L_cm, broadcast
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < NB; c++)
+    if (lane < rn && c < kn) M[(size_t)(k0 + c) * ld + r0 + lane] = a[c];
+}
+
 // Small windows: one CTA does everything between the build pass and the
 // back-substitution: gradient-tolerance test, assembly of the damped reduced
 // camera system in shared memory, Cholesky, both triangular solves, candidate
@@ -1017,12 +1070,14 @@ __global__ void __launch_bounds__(256)
   const BADev p = probs[blockIdx.y];
   LMState* st = p.st;
   if (st->done) return;
-  extern __shared__ double A[];  // n*n | b[n] | diag[n]
+  extern __shared__ double A[];  // n*n | b[n] | diag[n] | tmp[32] | Linv[nb][32][33]
   __shared__ double red[8];
   __shared__ int s_ok, s_done;
   const int n = p.n, tid = threadIdx.x;
   double* b = A + (size_t)n * n;
   double* dg = b + n;
+  double* tmp = dg + n;
+  double* Linv = tmp + NB;  // inverses of the diagonal tiles of L (lower triangular, [tile][r][c], stride 33)
   // gradient tolerance of the point accepted by the previous attempt
   double gm = 0;
   for (int i = tid; i < n; i += blockDim.x) gm = fmax(gm, fabs(p.gc[i] / p.scale_c[i]));
@@ -1043,73 +1098,126 @@ __global__ void __launch_bounds__(256)
   __syncthreads();
   if (s_done) return;
   const double radius = st->radius;
-  for (int idx = tid; idx < n * n; idx += blockDim.x) {
-    const int i = idx / n, j = idx % n;
-    const int ci = i / 6, cj = j / 6;
-    double v;
-    if (ci == cj) {
-      const int a = i % 6, c = j % 6;
-      const double h = p.Hcc[HCC * (size_t)ci + (a <= c ? upper_idx(a, c) : upper_idx(c, a))];
-      v = p.S[idx] + h;
-      if (a == c) v += clamp_diag(h, opt.min_lm_diagonal, opt.max_lm_diagonal) / radius;
-    } else {
-      v = ci < cj ? p.S[idx] : p.S[(size_t)j * n + i];
+  // (the loads of four elements per thread are issued together: the loop was one exposed L2
+  //  round trip per element, 8.5 us of the 50 us this kernel took)
+  for (int base = 0; base < n * n; base += 4 * 256) {
+    double vs[4], vh[4];
+    int dcase[4];  // 0 off-diagonal block, 1 diagonal block, 2 diagonal element
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const int idx = base + tid + 256 * q;
+      vs[q] = vh[q] = 0.0;
+      dcase[q] = -1;
+      if (idx < n * n) {
+        const int i = idx / n, j = idx % n;
+        const int ci = i / 6, cj = j / 6;
+        if (ci == cj) {
+          const int a2 = i % 6, c2 = j % 6;
+          vh[q] = p.Hcc[HCC * (size_t)ci + (a2 <= c2 ? upper_idx(a2, c2) : upper_idx(c2, a2))];
+          vs[q] = p.S[idx];
+          dcase[q] = a2 == c2 ? 2 : 1;
+        } else {
+          vs[q] = ci < cj ? p.S[idx] : p.S[(size_t)j * n + i];
+          dcase[q] = 0;
+        }
+      }
     }
-    A[idx] = v;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const int idx = base + tid + 256 * q;
+      if (dcase[q] < 0) continue;
+      double v = vs[q] + vh[q];
+      if (dcase[q] == 2) v += clamp_diag(vh[q], opt.min_lm_diagonal, opt.max_lm_diagonal) / radius;
+      A[idx] = v;
+    }
   }
   for (int i = tid; i < n; i += blockDim.x) b[i] = p.gc[i] - p.rhs_corr[i];
   __syncthreads();
-  const int ty = tid >> 4, tx = tid & 15;
-  for (int j = 0; j < n; j++) {
-    double d = A[j * n + j];
-    if (!(d > 0.0)) {
-      if (tid == 0) s_ok = 0;
-      d = 1.0;
+  // Blocked right-looking Cholesky on 32-wide tiles: the diagonal tile by warp 0 and each panel
+  // tile by one warp, both with the tile in registers (no barrier inside), then the trailing
+  // update by the whole CTA: 3 block barriers per tile column instead of one per column.
+  {
+    const int lane = tid & 31, warp = tid >> 5;
+    const int nb = (n + NB - 1) / NB;
+    for (int kb = 0; kb < nb; kb++) {
+      const int k0 = kb * NB, kn = min(NB, n - k0);
+      if (warp == 0) potrf_tile_ld(A, n, k0, kn, dg, &s_ok, lane);
+      __syncthreads();
+      const int rb = kb + warp;  // warps 1.. take the panel tiles below
+      if (warp >= 1 && rb < nb) trsm_tile_ld(A, n, rb * NB, min(NB, n - rb * NB), k0, kn, dg, lane);
+      __syncthreads();
+      const int t0 = k0 + NB, tn = max(0, n - t0);  // trailing block (lower triangle incl. diagonal)
+      for (int idx = tid; idx < tn * tn; idx += 256) {
+        const int r = idx / tn, q = idx % tn;
+        if (q > r) continue;
+        double acc = 0;
+#pragma unroll 8
+        for (int m = 0; m < kn; m++) acc += A[(k0 + m) * n + t0 + r] * A[(k0 + m) * n + t0 + q];
+        A[(t0 + r) * n + t0 + q] -= acc;
+      }
+      __syncthreads();
     }
-    const double inv_s = rsqrt(d), inv_d = inv_s * inv_s;
-    if (tid == 0) dg[j] = inv_s;  // 1 / L_jj
-    for (int i = j + 1 + tid; i < n; i += 256) A[j * n + i] = A[i * n + j] * inv_s;  // L_ij at [j][i]
-    for (int i = j + 1 + ty; i < n; i += 16) {
-      const double aij = A[i * n + j] * inv_d;
-      for (int k = j + 1 + tx; k <= i; k += 16) A[i * n + k] -= aij * A[k * n + j];
+  }
+  // Triangular solves without a per-column dependency chain: warps 0..nb-1 invert the diagonal
+  // tiles of L (lane c solves L x = e_c with the column in registers; L_rm is a shared-memory
+  // broadcast), then warp 0 runs both substitutions block-wise as matrix-vector products:
+  // y_k = Linv_kk (b_k - sum_{j<k} L_kj y_j),  x_k = Linv_kk^T (y_k - sum_{i>k} L_ik^T x_i).
+  // (The register-vector column sweep this replaces took 24 k cycles of the kernel's 98 k.)
+  {
+    const int lane = tid & 31, warp = tid >> 5;
+    const int nb = (n + NB - 1) / NB;
+    if (warp < nb) {
+      const int k0 = warp * NB, kn = min(NB, n - k0);
+      double x[NB];
+#pragma unroll
+      for (int r = 0; r < NB; r++) {
+        double acc = (r == lane) ? 1.0 : 0.0;
+        if (r < kn) {
+#pragma unroll
+          for (int m = 0; m < r; m++) acc -= A[(size_t)(k0 + m) * n + k0 + r] * x[m];  // L_rm
+          x[r] = acc * dg[k0 + r];
+        } else {
+          x[r] = 0.0;
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < NB; r++) Linv[(warp * NB + r) * (NB + 1) + lane] = x[r];
     }
     __syncthreads();
-  }
-  // L y = b then L^T x = y by warp 0, right-looking with the vector in registers
-  // (lane owns rows lane, lane+32, lane+64): per step one shuffle broadcast and one
-  // FMA per owned row, no reductions and no divides.  L_ik (k<i) sits at A[k][i].
-  if (tid < 32) {
-    double v0 = tid < n ? b[tid] : 0.0, v1 = tid + 32 < n ? b[tid + 32] : 0.0,
-           v2 = tid + 64 < n ? b[tid + 64] : 0.0;
-    for (int j = 0; j < n; j++) {
-      const int own = j & 31, slot = j >> 5;
-      double yj = slot == 0 ? v0 : (slot == 1 ? v1 : v2);
-      yj = __shfl_sync(0xffffffffu, yj, own) * dg[j];
-      if (tid == own) {
-        if (slot == 0) v0 = yj; else if (slot == 1) v1 = yj; else v2 = yj;
+    if (warp == 0) {
+      for (int kb = 0; kb < nb; kb++) {  // forward
+        const int k0 = kb * NB, kn = min(NB, n - k0);
+        double t = 0.0;
+        if (lane < kn) {
+          t = b[k0 + lane];
+          for (int j = 0; j < k0; j++) t -= A[(size_t)j * n + k0 + lane] * b[j];  // L_{k0+lane, j} y_j
+        }
+        tmp[lane] = t;
+        __syncwarp();
+        double y = 0.0;
+#pragma unroll 8
+        for (int c2 = 0; c2 < NB; c2++) y += Linv[(kb * NB + lane) * (NB + 1) + c2] * tmp[c2];
+        __syncwarp();
+        if (lane < kn) b[k0 + lane] = y;
+        __syncwarp();
       }
-      const double* Lj = A + (size_t)j * n;  // L_ij = Lj[i] for i > j
-      if (tid > j && tid < n) v0 -= Lj[tid] * yj;
-      if (tid + 32 > j && tid + 32 < n) v1 -= Lj[tid + 32] * yj;
-      if (tid + 64 > j && tid + 64 < n) v2 -= Lj[tid + 64] * yj;
-    }
-    for (int j = n - 1; j >= 0; j--) {
-      const int own = j & 31, slot = j >> 5;
-      // x_j = (y_j - sum_{k>j} L_kj x_k) / L_jj with L_kj = A[j][k]: gather form needs a
-      // reduction, so use the column form: after x_j is known, y_i -= L_ji x_j for i < j
-      double xj = slot == 0 ? v0 : (slot == 1 ? v1 : v2);
-      xj = __shfl_sync(0xffffffffu, xj, own) * dg[j];
-      if (tid == own) {
-        if (slot == 0) v0 = xj; else if (slot == 1) v1 = xj; else v2 = xj;
+      for (int kb = nb - 1; kb >= 0; kb--) {  // backward
+        const int k0 = kb * NB, kn = min(NB, n - k0);
+        double t = 0.0;
+        if (lane < kn) {
+          t = b[k0 + lane];
+          for (int i = k0 + NB; i < n; i++) t -= A[(size_t)(k0 + lane) * n + i] * b[i];  // L_{i, k0+lane} x_i
+        }
+        tmp[lane] = t;
+        __syncwarp();
+        double xv = 0.0;
+#pragma unroll 8
+        for (int c2 = 0; c2 < NB; c2++) xv += Linv[(kb * NB + c2) * (NB + 1) + lane] * tmp[c2];
+        __syncwarp();
+        if (lane < kn) b[k0 + lane] = xv;
+        __syncwarp();
       }
-      // L_ji for i < j is stored at A[i][j] (column j of the upper triangle)
-      if (tid < j) v0 -= A[(size_t)tid * n + j] * xj;
-      if (tid + 32 < j) v1 -= A[(size_t)(tid + 32) * n + j] * xj;
-      if (tid + 64 < j) v2 -= A[(size_t)(tid + 64) * n + j] * xj;
     }
-    if (tid < n) b[tid] = v0;
-    if (tid + 32 < n) b[tid + 32] = v1;
-    if (tid + 64 < n) b[tid + 64] = v2;
   }
   __syncthreads();
   // candidate cameras + rotation blocks
@@ -1136,7 +1244,6 @@ __global__ void __launch_bounds__(256)
 }
 
 // Large systems: right-looking blocked Cholesky in global memory, NB = 32.
-constexpr int NB = 32;
 
 // Panel: every CTA factors the 32x32 diagonal block in shared memory with all
 // 256 threads (one barrier per column, rsqrt instead of sqrt + divides; L_ij,
@@ -2315,7 +2422,7 @@ static int problem_solve(lorb_ba_problem* pb, const lorb_ba_options* optp, int s
   const size_t smem_build_init =
       acc_mode == 2 ? (size_t)DP_SMEM_DOUBLES * 8
                     : (acc_mode == 1 ? ((size_t)nmax * nmax + lin_small) * 8 + wsm_bytes : 0);
-  const size_t smem_solve = ((size_t)nmax * nmax + 2 * (size_t)nmax) * 8;
+  const size_t smem_solve = ((size_t)nmax * nmax + 2 * (size_t)nmax + NB + (size_t)((nmax + NB - 1) / NB) * NB * (NB + 1)) * 8;
 #define LORB_BUILD_ATTR(FULL_, ACC_, BYTES_)                                                  \
   LORB_CUDA_TRY(cudaFuncSetAttribute(ba_build_kernel<FULL_, ACC_>,                             \
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BYTES_))); \
