@@ -20,6 +20,8 @@
 // The trust-region state lives on the device; the host only enqueues.
 #include <stdlib.h>
 
+#include <omp.h>
+
 #include <algorithm>
 #include <new>
 #include <vector>
@@ -1961,6 +1963,7 @@ struct lorb_ba_problem {
   std::vector<lorb::BADev> h_dev;     // host copies of the per-window descriptors
   std::vector<int> h_cam_off, h_pt_off;
   lorb::Buf params, topo, work, descs, hstate, counter, lists, stage;
+  lorb::Buf pairs_stage;  // pinned host copy of the pair records (grow-only: no per-call allocation or zero fill)
   int max_cam_items = 0, max_pair_items = 0;
   bool has_dup = false;  // some point is observed twice by the same window camera
   double *cams0 = nullptr, *pts0 = nullptr;  // initial parameters of all windows
@@ -2058,7 +2061,8 @@ static int problem_build(lorb_ba_problem* pb, lorb_ctx* c, const std::vector<Win
   std::vector<int> h_obs_pt;
   std::vector<int2> h_cam_obs;
   std::vector<int4> h_cam_items, h_pair_items;
-  std::vector<int4> h_pairs;
+  int4* h_pairs = nullptr;  // in pb->pairs_stage
+  size_t n_pairs_total = 0;
   struct ListOff { size_t obs_pt, cam_obs, cam_items, pairs, pair_items; int n_cam_items, n_pair_items; };
   std::vector<ListOff> lo(nw, ListOff{0, 0, 0, 0, 0, 0, 0});
   pb->max_cam_items = pb->max_pair_items = 0;
@@ -2170,20 +2174,55 @@ static int problem_build(lorb_ba_problem* pb, lorb_ctx* c, const std::vector<Win
           for (int st0 = cnt[c2]; st0 < cnt[c2 + 1]; st0 += 1024)
             h_cam_items.push_back(make_int4(c2, st0, std::min(1024, cnt[c2 + 1] - st0), 0));
         L.n_cam_items = (int)(h_cam_items.size() - L.cam_items);
-        // pair records grouped by camera block (ci <= cj; equal cameras keep both orders)
-        std::vector<long long> kcnt((size_t)W.C * W.C + 1, 0);
-        for (int pp = 0; pp < W.P; pp++)
-          for (int e1 = ptr[pp]; e1 < ptr[pp + 1]; e1++) {
-            if (cam[e1] < 0) continue;
-            for (int e2 = ptr[pp]; e2 < ptr[pp + 1]; e2++)
-              if (cam[e2] >= cam[e1]) kcnt[(size_t)cam[e1] * W.C + cam[e2] + 1]++;
+        // pair records grouped by camera block (ci <= cj; equal cameras keep both orders), points
+        // ascending inside a block.  Counting sort over the points with one histogram per host thread
+        // (static point ranges), so the order does not depend on the thread count.
+        const int nth = std::max(1, std::min(omp_get_max_threads(), 64));
+        const size_t nblkC = (size_t)W.C * W.C;
+        std::vector<long long> kcnt(nblkC + 1, 0);
+        std::vector<long long> tcnt((size_t)nth * nblkC, 0);
+        auto p_lo = [&](int t) { return (int)((long long)W.P * t / nth); };
+#pragma omp parallel for schedule(static, 1) num_threads(nth)
+        for (int t = 0; t < nth; t++) {
+          long long* mine = &tcnt[(size_t)t * nblkC];
+          for (int pp = p_lo(t); pp < p_lo(t + 1); pp++)
+            for (int e1 = ptr[pp]; e1 < ptr[pp + 1]; e1++) {
+              if (cam[e1] < 0) continue;
+              for (int e2 = ptr[pp]; e2 < ptr[pp + 1]; e2++)
+                if (cam[e2] >= cam[e1]) mine[(size_t)cam[e1] * W.C + cam[e2]]++;
+            }
+        }
+        for (size_t k2 = 0; k2 < nblkC; k2++) {
+          long long run = kcnt[k2];
+          for (int t = 0; t < nth; t++) {  // exclusive offsets of thread t inside block k2
+            const long long c2 = tcnt[(size_t)t * nblkC + k2];
+            tcnt[(size_t)t * nblkC + k2] = run;
+            run += c2;
           }
-        for (size_t k2 = 0; k2 < (size_t)W.C * W.C; k2++) kcnt[k2 + 1] += kcnt[k2];
-        L.pairs = h_pairs.size();
-        h_pairs.resize(L.pairs + (size_t)kcnt[(size_t)W.C * W.C]);
+          kcnt[k2 + 1] = run;
+        }
+        L.pairs = n_pairs_total;
         {
-          std::vector<long long> cur(kcnt.begin(), kcnt.end() - 1);
-          for (int pp = 0; pp < W.P; pp++)
+          const size_t need = (n_pairs_total + (size_t)kcnt[nblkC]) * sizeof(int4);
+          pb->pairs_stage.pinned = true;
+          if (need > pb->pairs_stage.cap) {  // grow, keeping the records of earlier windows
+            lorb::Buf nb2;
+            nb2.pinned = true;
+            if (nb2.reserve(need) != LORB_OK) {  // (no return from inside the OpenMP loop)
+              bad_obs |= 2;
+              continue;
+            }
+            if (n_pairs_total) memcpy(nb2.p, pb->pairs_stage.p, n_pairs_total * sizeof(int4));
+            pb->pairs_stage.release();
+            pb->pairs_stage = nb2;
+          }
+          h_pairs = pb->pairs_stage.as<int4>();
+          n_pairs_total += (size_t)kcnt[nblkC];
+        }
+#pragma omp parallel for schedule(static, 1) num_threads(nth)
+        for (int t = 0; t < nth; t++) {
+          long long* cur = &tcnt[(size_t)t * nblkC];
+          for (int pp = p_lo(t); pp < p_lo(t + 1); pp++)
             for (int e1 = ptr[pp]; e1 < ptr[pp + 1]; e1++) {
               if (cam[e1] < 0) continue;
               for (int e2 = ptr[pp]; e2 < ptr[pp + 1]; e2++)
@@ -2205,6 +2244,7 @@ static int problem_build(lorb_ba_problem* pb, lorb_ctx* c, const std::vector<Win
       memcpy(&h_cams[6 * (size_t)pb->h_cam_off[w]], W.cams, (size_t)W.C * 48);
       if (W.P) memcpy(&h_pts[3 * (size_t)pb->h_pt_off[w]], W.pts, (size_t)W.P * 24);
     }
+    if (bad_obs & 2) return LORB_ERR_NOMEM;
     LORB_REQUIRE(!bad_obs, "observation index out of range");
     LORB_REQUIRE(!bad_fix, "fixed observation point out of range");
     pb->has_dup = dup_any != 0;
@@ -2284,7 +2324,7 @@ static int problem_build(lorb_ba_problem* pb, lorb_ctx* c, const std::vector<Win
   }
   {
     const size_t b0 = al(h_obs_pt.size() * 4), b1 = al(h_cam_obs.size() * 8),
-                 b2 = al(h_cam_items.size() * 16), b3 = al(h_pairs.size() * 16),
+                 b2 = al(h_cam_items.size() * 16), b3 = al(n_pairs_total * 16),
                  b4 = al(h_pair_items.size() * 16);
     LORB_TRY(pb->lists.reserve(b0 + b1 + b2 + b3 + b4 + 256));
     uint8_t* lb = pb->lists.as<uint8_t>();
@@ -2293,7 +2333,8 @@ static int problem_build(lorb_ba_problem* pb, lorb_ctx* c, const std::vector<Win
       LORB_CUDA_TRY(cudaMemcpyAsync(lb, h_obs_pt.data(), h_obs_pt.size() * 4, cudaMemcpyHostToDevice, s2));
       LORB_CUDA_TRY(cudaMemcpyAsync(lb + b0, h_cam_obs.data(), h_cam_obs.size() * 8, cudaMemcpyHostToDevice, s2));
       LORB_CUDA_TRY(cudaMemcpyAsync(lb + b0 + b1, h_cam_items.data(), h_cam_items.size() * 16, cudaMemcpyHostToDevice, s2));
-      LORB_CUDA_TRY(cudaMemcpyAsync(lb + b0 + b1 + b2, h_pairs.data(), h_pairs.size() * 16, cudaMemcpyHostToDevice, s2));
+      if (n_pairs_total)
+        LORB_CUDA_TRY(cudaMemcpyAsync(lb + b0 + b1 + b2, h_pairs, n_pairs_total * 16, cudaMemcpyHostToDevice, s2));
       LORB_CUDA_TRY(cudaMemcpyAsync(lb + b0 + b1 + b2 + b3, h_pair_items.data(), h_pair_items.size() * 16, cudaMemcpyHostToDevice, s2));
       LORB_CUDA_TRY(cudaStreamSynchronize(s2));
     }
@@ -2574,6 +2615,7 @@ static void problem_free(lorb_ba_problem* pb) {
   pb->descs.release();
   pb->lists.release();
   pb->stage.release();
+  pb->pairs_stage.release();
   pb->hstate.release();
   pb->counter.release();
   delete pb;
