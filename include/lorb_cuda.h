@@ -261,6 +261,36 @@ int lorb_stereo_matches(lorb_ctx* ctx, const lorb_pyramid_view* left, const lorb
                         float* out_depth, int* n_matched);
 
 /*
+ * Orientation and steered-BRIEF stages of ORBextractor (reference src/ORBextractor.cpp:79-149 =
+ * IC_Angle + computeOrbDescriptor, driven by computeOrientation :487-494 and computeDescriptors
+ * :1078-1085) for keypoints given in the coordinates of their pyramid level.
+ *   raw        the image pyramid (ORBextractor::mvImagePyramid): orientation reads it (:1105)
+ *   blurred    the same levels after cv::GaussianBlur(7x7, sigma 2) (:1131-1132): the descriptor
+ *              reads it
+ *   pattern    [512 x 2] int, the sampling pattern the ORBextractor constructor holds
+ *              (ORBextractor::pattern, :464-467); every point inside radius 19
+ *   kx, ky     keypoint position in level coordinates (before the scale-back of :1142-1147),
+ *              klevel its pyramid level; each keypoint at least EDGE_THRESHOLD = 19 px inside its
+ *              level, which the extractor guarantees (:76, :820-823) -- LORB_ERR_ARG otherwise
+ *   angle_in   NULL: compute the orientation (out_angle receives KeyPoint::angle, degrees);
+ *              non-NULL: describe with these angles (raw may then be NULL)
+ *   out_desc   [n_kp x 32] descriptor rows (Frame::mDescriptors layout, row a1 of SURVEY 8(a))
+ * cos/sin of the angle carry the bits of the host libm the reference links (glibc >= 2.28 on an
+ * FMA-capable x86-64), see lorb_slam_b200/csrc/libm_sincosf.cuh.
+ */
+int lorb_orb_describe(lorb_ctx* ctx, const lorb_pyramid_view* raw, const lorb_pyramid_view* blurred,
+                      int n_levels, const int* pattern, int n_kp, const float* kx, const float* ky,
+                      const int* klevel, const float* angle_in, float* out_angle, uint8_t* out_desc);
+
+/* ORBextractor::umax (:469-482): half widths of the rows 0..15 of the orientation disc. */
+void lorb_orb_umax(int* umax16);
+
+/* Arithmetic pins for the tests: the device's sinf / cosf (host-libm bits) of a[i] and
+ * cv::fastAtan2(a[i], b[i]). */
+int lorb_orb_selftest(lorb_ctx* ctx, int n, const float* a, const float* b, float* out_sin,
+                      float* out_cos, float* out_atan2);
+
+/*
  * MapPoint::ComputeDescriptor (reference src/map_point.cpp:69-129) for a batch
  * of map points: point k owns the observation descriptors
  * desc[offsets[k] .. offsets[k+1]) (in the iteration order of its observation

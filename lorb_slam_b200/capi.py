@@ -25,7 +25,7 @@ EXPORTS = [
     "lorb_match_bf_crosscheck", "lorb_match_knn2", "lorb_match_sweep", "lorb_bank_upload",
     "lorb_match_sweep_resident", "lorb_sweep_plan_upload", "lorb_sweep_plan_run",
     "lorb_sweep_plan_download", "lorb_sweep_plan_run_at", "lorb_search_proj_points", "lorb_search_proj_frame", "lorb_frustum_project", "lorb_compute_descriptors",
-    "lorb_stereo_matches",
+    "lorb_stereo_matches", "lorb_orb_describe", "lorb_orb_umax", "lorb_orb_selftest",
     "lorb_ba_default_options", "lorb_ba_pose_only", "lorb_ba_local", "lorb_ba_local_batched",
     "lorb_ba_problem_create", "lorb_ba_problem_create_batched", "lorb_ba_problem_reset", "lorb_ba_problem_solve",
     "lorb_ba_problem_download", "lorb_ba_problem_destroy", "lorb_dist_get_unique_id",
@@ -304,6 +304,29 @@ class Context:
             C.c_float(st["mbf"]), C.c_float(st["mb"]), n, _ptr(a[2]), _ptr(a[3]), _ptr(a[4]), _ptr(a[5]),
             nr, _ptr(a[6]), _ptr(a[7]), _ptr(a[8]), _ptr(a[9]), _ptr(ur), _ptr(dp), C.byref(nm)))
         return dict(uright=ur[:n], depth=dp[:n], n_matched=nm.value)
+
+    def orb_describe(self, oi, pattern, angle_in=None):
+        """IC_Angle + computeOrbDescriptor; oi as produced by synth.make_orb_inputs, pattern
+        [512, 2] int32 -> (angle[n], desc[n, 32])."""
+        vb, kb = _pyramid_view(oi["pyr_blur"])
+        vr, kr = _pyramid_view(oi["pyr_raw"])
+        n = int(oi["n_kp"])
+        a = [_arr(pattern, np.int32).reshape(-1), _arr(oi["kx"], np.float32), _arr(oi["ky"], np.float32),
+             _arr(oi["klevel"], np.int32)]
+        ang = np.zeros(max(1, n), np.float32)
+        desc = np.zeros((max(1, n), 32), np.uint8)
+        ain = None if angle_in is None else _arr(angle_in, np.float32)
+        _check(self._lib.lorb_orb_describe(
+            self._h, C.byref(vr), C.byref(vb), int(oi["n_levels"]), _ptr(a[0]), n, _ptr(a[1]), _ptr(a[2]),
+            _ptr(a[3]), None if ain is None else _ptr(ain), _ptr(ang), _ptr(desc)))
+        return ang[:n], desc[:n]
+
+    def orb_selftest(self, a, b):
+        a, b = _arr(a, np.float32), _arr(b, np.float32)
+        n = len(a)
+        s, c, t = np.zeros(n, np.float32), np.zeros(n, np.float32), np.zeros(n, np.float32)
+        _check(self._lib.lorb_orb_selftest(self._h, n, _ptr(a), _ptr(b), _ptr(s), _ptr(c), _ptr(t)))
+        return s, c, t
 
     def frustum_project(self, fp):
         n = int(fp["n"])

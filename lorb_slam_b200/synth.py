@@ -458,3 +458,34 @@ def make_stereo_pair(n_kp=1000, seed=0, width=640, height=480, n_levels=8, match
         n_right=len(perm), rx=np.ascontiguousarray(rx[perm].astype(np.float32)),
         ry=np.ascontiguousarray(ry[perm].astype(np.float32)),
         roct=np.ascontiguousarray(roct[perm].astype(np.int32)), rdesc=np.ascontiguousarray(rdesc[perm]))
+
+
+# ------------------------------------------------------- ORB descriptor stage
+
+def make_orb_inputs(n_kp=1000, seed=0, width=640, height=480, n_levels=8, border=19):
+    """Inputs of the orientation + steered-BRIEF stage of ORBextractor (reference
+    src/ORBextractor.cpp:79-149): a raw and a blurred image pyramid (the blur is an input of the
+    stage: the extractor applies cv::GaussianBlur 7x7 / sigma 2 per level, :1131-1132) and keypoints
+    in the coordinates of their level, at least `border` px inside it (EDGE_THRESHOLD, :76)."""
+    rng = np.random.default_rng(seed + 90001)
+    st = make_stereo_pair(8, seed, width, height, n_levels)  # reuse its textured left pyramid
+    raw = st["pyr_left"]
+    ker = np.array([1, 6, 15, 20, 15, 6, 1], np.float64) / 64.0  # binomial 7-tap stand-in for the blur
+
+    def blur(img):
+        f = np.pad(img.astype(np.float64), 3, mode="reflect")
+        f = sum(ker[k] * f[:, k:k + img.shape[1]] for k in range(7))
+        f = sum(ker[k] * f[k:k + img.shape[0], :] for k in range(7))
+        return np.ascontiguousarray(np.rint(f).astype(np.uint8))
+
+    blurred = [blur(a) for a in raw]
+    wgt = (1.0 / 1.2) ** np.arange(n_levels)
+    lvl = rng.choice(n_levels, size=n_kp, p=wgt / wgt.sum()).astype(np.int32)
+    lw = np.array([raw[o].shape[1] for o in lvl])
+    lh = np.array([raw[o].shape[0] for o in lvl])
+    kx = (border + rng.random(n_kp) * (lw - 2 * border - 1)).astype(np.float32)
+    ky = (border + rng.random(n_kp) * (lh - 2 * border - 1)).astype(np.float32)
+    half = rng.random(n_kp) < 0.3  # FAST keypoints are integer pixels; refined ones are not: keep both
+    kx = np.where(half, kx, np.rint(kx)).astype(np.float32)
+    ky = np.where(half, ky, np.rint(ky)).astype(np.float32)
+    return dict(n_levels=n_levels, pyr_raw=raw, pyr_blur=blurred, n_kp=n_kp, kx=kx, ky=ky, klevel=lvl)

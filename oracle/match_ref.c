@@ -772,3 +772,76 @@ int orc_stereo_matches(int n_levels, const int* lw, const int* lh, const int* ls
   free(rowCount);
   return kept;
 }
+
+/* ---- SURVEY 8(f) rank 5 (descriptor stage): IC_Angle + computeOrbDescriptor of
+ * src/ORBextractor.cpp:79-149 for keypoints given in the coordinates of their pyramid level.
+ * `pattern` (512 x,y pairs = bit_pattern_31_) and `umax` (16 entries) are the tables the
+ * reference's ORBextractor constructor builds (:464-482); they are inputs here. */
+static float orc_fast_atan2(float y, float x) { /* cv::fastAtan2, no FMA (pinned against cv2) */
+  const float PI_F = (float)(180 / 3.1415926535897932384626433832795);
+  const float p1 = 0.9997878412794807f * PI_F, p3 = -0.3258083974640975f * PI_F,
+              p5 = 0.1555786518463281f * PI_F, p7 = -0.04432655554792128f * PI_F;
+  const float ax = fabsf(x), ay = fabsf(y);
+  float a, c, c2;
+  if (ax >= ay) {
+    c = ay / (ax + (float)2.2204460492503131e-16);
+    c2 = c * c;
+    a = (((p7 * c2 + p5) * c2 + p3) * c2 + p1) * c;
+  } else {
+    c = ax / (ay + (float)2.2204460492503131e-16);
+    c2 = c * c;
+    a = 90.f - (((p7 * c2 + p5) * c2 + p3) * c2 + p1) * c;
+  }
+  if (x < 0) a = 180.f - a;
+  if (y < 0) a = 360.f - a;
+  return a;
+}
+float orc_fast_atan2_export(float y, float x) { return orc_fast_atan2(y, x); }
+
+void orc_orb_describe(int n_levels, const int* w, const int* h, const int* step_raw,
+                      const uint8_t* const* raw, const int* step_blur, const uint8_t* const* blurred,
+                      int n_kp, const float* kx, const float* ky, const int* klevel, const int* pattern,
+                      const int* umax, float* out_angle, uint8_t* out_desc) {
+  (void)n_levels; (void)w; (void)h;
+  const int HALF_PATCH_SIZE = 15;
+  const float factorPI = (float)(3.1415926535897932384626433832795 / 180.f); /* :109 */
+  for (int i = 0; i < n_kp; i++) {
+    const int l = klevel[i];
+    /* IC_Angle :79-106 */
+    {
+      int m_01 = 0, m_10 = 0;
+      const int step = step_raw[l];
+      const uint8_t* center = raw[l] + (size_t)lrintf(ky[i]) * step + lrintf(kx[i]);
+      for (int u = -HALF_PATCH_SIZE; u <= HALF_PATCH_SIZE; ++u) m_10 += u * center[u];
+      for (int v = 1; v <= HALF_PATCH_SIZE; ++v) {
+        int v_sum = 0;
+        const int d = umax[v];
+        for (int u = -d; u <= d; ++u) {
+          const int val_plus = center[u + v * step], val_minus = center[u - v * step];
+          v_sum += (val_plus - val_minus);
+          m_10 += u * (val_plus + val_minus);
+        }
+        m_01 += v * v_sum;
+      }
+      out_angle[i] = orc_fast_atan2((float)m_01, (float)m_10);
+    }
+    /* computeOrbDescriptor :110-149 */
+    {
+      const float angle = out_angle[i] * factorPI;
+      const float a = cosf(angle), b = sinf(angle); /* (float)cos(float): std::cos(float) overload */
+      const int step = step_blur[l];
+      const uint8_t* center = blurred[l] + (size_t)lrintf(ky[i]) * step + lrintf(kx[i]);
+      const int* pat = pattern;
+      for (int k = 0; k < 32; ++k, pat += 32) {
+        int val = 0;
+        for (int bit = 0; bit < 8; bit++) {
+          const int x0 = pat[4 * bit], y0 = pat[4 * bit + 1], x1 = pat[4 * bit + 2], y1 = pat[4 * bit + 3];
+          const int t0 = center[lrintf(x0 * b + y0 * a) * step + lrintf(x0 * a - y0 * b)];
+          const int t1 = center[lrintf(x1 * b + y1 * a) * step + lrintf(x1 * a - y1 * b)];
+          val |= (t0 < t1) << bit;
+        }
+        out_desc[32 * (size_t)i + k] = (uint8_t)val;
+      }
+    }
+  }
+}

@@ -14,16 +14,21 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIBDIR = os.path.join(_HERE, "lib")
 
 
+_LIBS = ("liborc_match.so", "liborc_ba.so", "liborc_orb.so")
+
+
 def build(force=False):
     """Compile the oracle shared objects with the committed Makefile."""
     need = force or not all(
-        os.path.exists(os.path.join(_LIBDIR, n)) for n in ("liborc_match.so", "liborc_ba.so"))
+        os.path.exists(os.path.join(_LIBDIR, n)) for n in _LIBS)
     if not need:
         srcs = [os.path.join(_HERE, "match_ref.c"), os.path.join(_HERE, "ba_ref.cpp"),
+                os.path.join(_HERE, "orb_ref.cpp"), os.path.join(_HERE, "Makefile"),
+                os.path.join(_HERE, "..", "lorb_slam_b200", "csrc", "libm_sincosf.cuh"),
                 os.path.join(_HERE, "..", "include", "lorb_cuda.h")]
         newest = max(os.path.getmtime(s) for s in srcs)
         oldest = min(os.path.getmtime(os.path.join(_LIBDIR, n))
-                     for n in ("liborc_match.so", "liborc_ba.so"))
+                     for n in _LIBS)
         need = newest > oldest
     if need:
         subprocess.run(["make", "-C", _HERE, "-B"], check=True, capture_output=True)
@@ -31,6 +36,7 @@ def build(force=False):
 
 _m = None
 _b = None
+_o = None
 
 
 def _match():
@@ -39,6 +45,16 @@ def _match():
         build()
         _m = C.CDLL(os.path.join(_LIBDIR, "liborc_match.so"))
     return _m
+
+
+def _orb():
+    global _o
+    if _o is None:
+        build()
+        _o = C.CDLL(os.path.join(_LIBDIR, "liborc_orb.so"))
+        _o.orc_sincosf_mismatches.restype = C.c_longlong
+        _o.orc_sincosf_mismatches.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32]
+    return _o
 
 
 def _ba():
@@ -232,6 +248,41 @@ def stereo_matches(st):
         _p(st["ldesc"], C.c_uint8), st["n_right"], _p(st["rx"], C.c_float), _p(st["ry"], C.c_float),
         _p(st["roct"], C.c_int), _p(st["rdesc"], C.c_uint8), _p(ur, C.c_float), _p(dp, C.c_float))
     return dict(uright=ur[:n], depth=dp[:n], n_matched=int(k))
+
+
+def orb_describe(oi, pattern, umax):
+    """oi: dict from synth.make_orb_inputs; pattern [512,2] int32, umax [16] int32 (the tables of
+    the reference's ORBextractor constructor) -> (angle[n], desc[n,32])."""
+    kr, w, h, sr, pr = _pyr_args(oi["pyr_raw"])
+    kb, _, _, sb, pb = _pyr_args(oi["pyr_blur"])
+    n = oi["n_kp"]
+    pattern, umax = _i32(pattern).reshape(-1), _i32(umax)
+    ang, desc = np.zeros(max(1, n), np.float32), np.zeros((max(1, n), 32), np.uint8)
+    _match().orc_orb_describe(int(oi["n_levels"]), _p(w, C.c_int), _p(h, C.c_int), _p(sr, C.c_int), pr,
+                              _p(sb, C.c_int), pb, n, _p(oi["kx"], C.c_float), _p(oi["ky"], C.c_float),
+                              _p(oi["klevel"], C.c_int), _p(pattern, C.c_int), _p(umax, C.c_int),
+                              _p(ang, C.c_float), _p(desc, C.c_uint8))
+    return ang[:n], desc[:n]
+
+
+def libm_sincosf(x, restated=False):
+    """sinf/cosf of the process's libm (or of the host instantiation of the device restatement)."""
+    x = _f32(x)
+    s, c = np.zeros(len(x), np.float32), np.zeros(len(x), np.float32)
+    f = _orb().orc_restated_sincosf if restated else _orb().orc_libm_sincosf
+    f(len(x), _p(x, C.c_float), _p(s, C.c_float), _p(c, C.c_float))
+    return s, c
+
+
+def sincosf_mismatches(lo_bits, hi_bits, stride):
+    return int(_orb().orc_sincosf_mismatches(lo_bits, hi_bits, stride))
+
+
+def fast_atan2(y, x):
+    f = _match().orc_fast_atan2_export
+    f.restype = C.c_float
+    f.argtypes = [C.c_float, C.c_float]
+    return float(f(y, x))
 
 
 def project_rt(tcw, xw):

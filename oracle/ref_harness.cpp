@@ -646,11 +646,13 @@ int waitKey(int) { LORB_OFF_PATH("cv::waitKey"); }
 Ptr<ORB> ORB::create() { LORB_OFF_PATH("cv::ORB::create"); }
 void Feature2D::detect(const Mat&, std::vector<KeyPoint>&) { LORB_OFF_PATH("cv::Feature2D::detect"); }
 void Feature2D::compute(const Mat&, std::vector<KeyPoint>&, Mat&) { LORB_OFF_PATH("cv::Feature2D::compute"); }
+void resize(const Mat&, Mat&, Size, double, double, int) { LORB_OFF_PATH("cv::resize"); }
+void copyMakeBorder(const Mat&, Mat&, int, int, int, int, int) { LORB_OFF_PATH("cv::copyMakeBorder"); }
+void GaussianBlur(const Mat&, Mat&, Size, double, double, int) { LORB_OFF_PATH("cv::GaussianBlur"); }
+void FAST(const Mat&, std::vector<KeyPoint>&, int, bool) { LORB_OFF_PATH("cv::FAST"); }
+void KeyPointsFilter::retainBest(std::vector<KeyPoint>&, int) { LORB_OFF_PATH("cv::KeyPointsFilter::retainBest"); }
 }  // namespace cv
 namespace Simple_ORB_SLAM {
-ORBextractor::ORBextractor(int, float, int, int, int) { LORB_OFF_PATH("ORBextractor"); }
-void ORBextractor::operator()(cv::InputArray, cv::InputArray, std::vector<cv::KeyPoint>&, cv::OutputArray) {
-  LORB_OFF_PATH("ORBextractor::operator()");
-}
+// (ORBextractor itself is compiled from the reference in ref_orb_harness.cpp)
 bool Camera::Project(const Point3f&, Point2f&) { LORB_OFF_PATH("Camera::Project"); }
 }  // namespace Simple_ORB_SLAM

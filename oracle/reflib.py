@@ -30,7 +30,8 @@ def build(force=False):
     if not can_build():
         return False
     srcs = [os.path.join(_HERE, "ref_harness.cpp"), os.path.join(_HERE, "refshim", "lorb_cvshim.hpp"),
-            os.path.join(_HERE, "refshim", "lorb_ceresshim.hpp"), os.path.join(_HERE, "Makefile")]
+            os.path.join(_HERE, "refshim", "lorb_ceresshim.hpp"), os.path.join(_HERE, "Makefile"),
+            os.path.join(_HERE, "ref_orb_harness.cpp")]
     if force or not os.path.exists(_LIB) or max(map(os.path.getmtime, srcs)) > os.path.getmtime(_LIB):
         subprocess.run(["make", "-C", _HERE, "ref", "REFERENCE=" + REFERENCE_ROOT], check=True,
                        capture_output=True)
@@ -234,6 +235,22 @@ def stereo_matches(st):
         _p(st["roct"], C.c_int), _p(st["rdesc"], C.c_uint8), _p(ur, C.c_float), _p(dp, C.c_float),
         C.byref(mb))
     return dict(uright=ur[:n], depth=dp[:n], n_matched=int(k), mb=float(mb.value))
+
+
+def orb_describe(oi):
+    """IC_Angle + computeOrbDescriptor of the compiled reference (src/ORBextractor.cpp:79-149)
+    -> (angle[n], desc[n,32], pattern[512,2], umax[16]); the two tables are the ones its
+    ORBextractor constructor builds."""
+    kr, w, h, sr, pr = _orc._pyr_args(oi["pyr_raw"])
+    kb, _, _, sb, pb = _orc._pyr_args(oi["pyr_blur"])
+    n = oi["n_kp"]
+    ang, desc = np.zeros(max(1, n), np.float32), np.zeros((max(1, n), 32), np.uint8)
+    umax, pattern = np.zeros(16, np.int32), np.zeros(1024, np.int32)
+    lib().ref_orb_describe(int(oi["n_levels"]), _p(w, C.c_int), _p(h, C.c_int), _p(sr, C.c_int), pr,
+                           _p(sb, C.c_int), pb, n, _p(oi["kx"], C.c_float), _p(oi["ky"], C.c_float),
+                           _p(oi["klevel"], C.c_int), _p(ang, C.c_float), _p(desc, C.c_uint8),
+                           _p(umax, C.c_int), _p(pattern, C.c_int))
+    return ang[:n], desc[:n], pattern.reshape(512, 2), umax
 
 
 def compute_descriptor(desc):

@@ -35,11 +35,66 @@
 #include <vector>
 
 #define CV_8U 0
+#define CV_8UC1 0
+#define CV_PI 3.1415926535897932384626433832795
 #define CV_32S 4
 #define CV_32F 5
 #define CV_64F 6
 
+typedef unsigned char uchar;
+
+// cvRound: round to nearest, ties to even (OpenCV: _mm_cvtsd_si32 / lrint)
+inline int cvRound(double v) { return (int)lrint(v); }
+inline int cvRound(float v) { return (int)lrintf(v); }
+inline int cvRound(int v) { return v; }
+inline int cvFloor(double v) { return (int)std::floor(v); }
+inline int cvCeil(double v) { return (int)std::ceil(v); }
+
 namespace cv {
+
+using ::cvRound;
+using ::cvFloor;
+using ::cvCeil;
+using ::uchar;
+
+enum InterpolationFlags { INTER_NEAREST = 0, INTER_LINEAR = 1 };
+enum BorderTypes { BORDER_CONSTANT = 0, BORDER_REPLICATE = 1, BORDER_REFLECT = 2, BORDER_REFLECT_101 = 4, BORDER_ISOLATED = 16 };
+
+// cv::fastAtan2 (degrees, polynomial of core/src/mathfuncs_core): restated without FMA and pinned
+// bit-exactly against cv2.fastAtan2 (tests/golden/cvshim_golden.npz)
+inline float fastAtan2(float y, float x) {
+  const float p1 = 0.9997878412794807f * (float)(180 / CV_PI), p3 = -0.3258083974640975f * (float)(180 / CV_PI),
+              p5 = 0.1555786518463281f * (float)(180 / CV_PI), p7 = -0.04432655554792128f * (float)(180 / CV_PI);
+  const float ax = std::abs(x), ay = std::abs(y);
+  float a, c, c2;
+  if (ax >= ay) {
+    c = ay / (ax + (float)DBL_EPSILON);
+    c2 = c * c;
+    a = (((p7 * c2 + p5) * c2 + p3) * c2 + p1) * c;
+  } else {
+    c = ax / (ay + (float)DBL_EPSILON);
+    c2 = c * c;
+    a = 90.f - (((p7 * c2 + p5) * c2 + p3) * c2 + p1) * c;
+  }
+  if (x < 0) a = 180.f - a;
+  if (y < 0) a = 360.f - a;
+  return a;
+}
+
+template <typename T>
+struct Size_ {
+  T width, height;
+  Size_() : width(0), height(0) {}
+  Size_(T w, T h) : width(w), height(h) {}
+};
+typedef Size_<int> Size;
+template <typename T>
+struct Rect_ {
+  T x, y, width, height;
+  Rect_() : x(0), y(0), width(0), height(0) {}
+  Rect_(T a, T b, T w, T h) : x(a), y(b), width(w), height(h) {}
+};
+typedef Rect_<int> Rect;
 
 enum NormTypes { NORM_INF = 1, NORM_L1 = 2, NORM_L2 = 4, NORM_HAMMING = 6 };
 
@@ -49,6 +104,12 @@ struct Point_ {
   T x, y;
   Point_() : x(0), y(0) {}
   Point_(T a, T b) : x(a), y(b) {}
+  template <typename S>
+  Point_& operator*=(S s) {
+    x = (T)(x * s);
+    y = (T)(y * s);
+    return *this;
+  }
 };
 template <typename T>
 struct Point3_ {
@@ -103,6 +164,7 @@ class Mat {
   int rows = 0, cols = 0;
   Mat() {}
   Mat(int r, int c, int type) { create(r, c, type); }
+  Mat(Size sz, int type) { create(sz.height, sz.width, type); }
   template <typename T>
   explicit Mat(const Point3_<T>& p) {
     create(3, 1, sizeof(T) == 4 ? CV_32F : CV_64F);
@@ -114,8 +176,8 @@ class Mat {
     rows = r;
     cols = c;
     type_ = type;
-    step_ = (size_t)c * esz(type);
-    buf_ = std::make_shared<std::vector<unsigned char>>((size_t)r * step_ + 8, 0);
+    step = (size_t)c * esz(type);
+    buf_ = std::make_shared<std::vector<unsigned char>>((size_t)r * step + 8, 0);
     off_ = 0;
   }
   static Mat zeros(int r, int c, int type) { return Mat(r, c, type); }
@@ -130,12 +192,20 @@ class Mat {
     for (int i = 0; i < std::min(r, c); i++) m.set(i, i, 1.0);
     return m;
   }
+  size_t step = 0;  // bytes per row (public like cv::Mat::step)
+  size_t step1() const { return step / esz(type_); }
+  Size size() const { return Size(cols, rows); }
+  Mat operator()(const Rect& r) const { return view(r.y, r.y + r.height, r.x, r.x + r.width); }
+  Mat getMat() const { return *this; }
+  void release() { *this = Mat(); }
+  uchar* ptr(int r = 0) { return raw(r); }
+  const uchar* ptr(int r = 0) const { return raw(r); }
   int type() const { return type_; }
   bool empty() const { return rows == 0 || cols == 0 || !buf_; }
   size_t elemSize() const { return esz(type_); }
-  bool isContinuous() const { return step_ == (size_t)cols * esz(type_); }
+  bool isContinuous() const { return step == (size_t)cols * esz(type_); }
 
-  unsigned char* raw(int r) const { return buf_->data() + off_ + (size_t)r * step_; }
+  unsigned char* raw(int r) const { return buf_->data() + off_ + (size_t)r * step; }
   template <typename T>
   T* ptr(int r = 0) { return reinterpret_cast<T*>(raw(r)); }
   template <typename T>
@@ -155,9 +225,9 @@ class Mat {
     m.rows = r1 - r0;
     m.cols = c1 - c0;
     m.type_ = type_;
-    m.step_ = step_;
+    m.step = step;
     m.buf_ = buf_;
-    m.off_ = off_ + (size_t)r0 * step_ + (size_t)c0 * esz(type_);
+    m.off_ = off_ + (size_t)r0 * step + (size_t)c0 * esz(type_);
     return m;
   }
   Mat row(int r) const { return view(r, r + 1, 0, cols); }
@@ -197,7 +267,7 @@ class Mat {
       return;
     }
     assert(m.cols == cols && m.type_ == type_);
-    const size_t need = off_ + (size_t)(rows + m.rows) * step_ + 8;
+    const size_t need = off_ + (size_t)(rows + m.rows) * step + 8;
     if (!isContinuous() || buf_.use_count() != 1 || buf_->capacity() < need) {
       auto nb = std::make_shared<std::vector<unsigned char>>();
       nb->reserve(std::max(need, (size_t)((rows + m.rows) * 3 / 2 + 4) * cols * esz(type_) + 8));
@@ -205,7 +275,7 @@ class Mat {
       for (int r = 0; r < rows; r++) std::memcpy(nb->data() + (size_t)r * cols * esz(type_), raw(r), (size_t)cols * esz(type_));
       buf_ = nb;
       off_ = 0;
-      step_ = (size_t)cols * esz(type_);
+      step = (size_t)cols * esz(type_);
     } else {
       if (buf_->size() < need) buf_->resize(need);  // within capacity: no reallocation
     }
@@ -243,7 +313,7 @@ class Mat {
 
  private:
   int type_ = CV_8U;
-  size_t step_ = 0, off_ = 0;
+  size_t off_ = 0;
   std::shared_ptr<std::vector<unsigned char>> buf_;
 };
 
@@ -523,6 +593,13 @@ typedef Feature2D FeatureDetector;
 typedef Feature2D DescriptorExtractor;
 struct ORB : Feature2D {
   static Ptr<ORB> create();
+};
+void resize(const Mat& src, Mat& dst, Size dsize, double fx = 0, double fy = 0, int interpolation = INTER_LINEAR);
+void copyMakeBorder(const Mat& src, Mat& dst, int top, int bottom, int left, int right, int borderType);
+void GaussianBlur(const Mat& src, Mat& dst, Size ksize, double sigmaX, double sigmaY = 0, int borderType = BORDER_REFLECT_101);
+void FAST(const Mat& image, std::vector<KeyPoint>& keypoints, int threshold, bool nonmaxSuppression = true);
+struct KeyPointsFilter {
+  static void retainBest(std::vector<KeyPoint>& keypoints, int npoints);
 };
 void imshow(const std::string& name, const Mat& img);
 int waitKey(int delay = 0);

@@ -158,3 +158,11 @@ def ba_local_case(c):
 
 def ba_case_options(c, ba_options):
     return None if c[-1] is None else ba_options(max_num_iterations=c[-1])
+
+
+# ---- 8(f) rank 5 (descriptor side): IC_Angle + computeOrbDescriptor of ORBextractor.cpp
+ORB_DESCRIBE = [("n1000_s0", 0, 1000), ("n2000_s1", 1, 2000), ("n3000_s2", 2, 3000), ("n64_s3", 3, 64)]
+
+
+def orb_describe_case(c):
+    return synth.make_orb_inputs(c[2], c[1])

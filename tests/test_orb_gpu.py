@@ -1,0 +1,66 @@
+"""GPU parity of the ORBextractor stages through the C ABI: bit-exact against
+the compiled reference's outputs (tests/golden/orb_golden.npz) and against the oracle on fresh
+inputs; the device's sinf/cosf/fastAtan2 against the host's."""
+import numpy as np
+import pytest
+
+import orb_checks as OC
+import ref_cases as RC
+from lorb_slam_b200 import capi, synth
+from oracle import ref
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("c", RC.ORB_DESCRIBE, ids=[c[0] for c in RC.ORB_DESCRIBE])
+def test_cuda_orb_describe_golden(ctx, c):
+    OC.check_orb_describe(ctx.orb_describe, c)
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_cuda_orb_describe_fresh(ctx, seed):
+    g = OC.golden()
+    oi = synth.make_orb_inputs(4000 + 500 * seed, 100 + seed, width=752 if seed % 2 else 640)
+    a, d = ctx.orb_describe(oi, OC.pattern())
+    oa, od = ref.orb_describe(oi, OC.pattern(), g["orb/umax"])
+    assert np.array_equal(a.view(np.uint32), oa.view(np.uint32)) and np.array_equal(d, od)
+    # describing with given angles (computeDescriptors after computeOrientation) is the same thing
+    _, d2 = ctx.orb_describe(oi, OC.pattern(), angle_in=oa)
+    assert np.array_equal(d2, od)
+
+
+def test_cuda_orb_describe_edges(ctx):
+    oi = synth.make_orb_inputs(0, 5)
+    a, d = ctx.orb_describe(oi, OC.pattern())
+    assert a.shape == (0,) and d.shape == (0, 32)
+    oi = synth.make_orb_inputs(10, 6)
+    oi["kx"][3] = 5.0  # closer than EDGE_THRESHOLD to the border
+    with pytest.raises(capi.LorbError):
+        ctx.orb_describe(oi, OC.pattern())
+    # keypoints exactly on the EDGE_THRESHOLD ring of every level: the patch touches the border
+    oi = synth.make_orb_inputs(64, 7)
+    w = np.array([oi["pyr_raw"][l].shape[1] for l in oi["klevel"]])
+    h = np.array([oi["pyr_raw"][l].shape[0] for l in oi["klevel"]])
+    oi["kx"] = np.where(np.arange(64) % 2 == 0, 19, w - 20).astype(np.float32)
+    oi["ky"] = np.where(np.arange(64) % 4 < 2, 19, h - 20).astype(np.float32)
+    a, d = ctx.orb_describe(oi, OC.pattern())
+    oa, od = ref.orb_describe(oi, OC.pattern(), OC.golden()["orb/umax"])
+    assert np.array_equal(a.view(np.uint32), oa.view(np.uint32)) and np.array_equal(d, od)
+
+
+def test_device_sincosf_and_atan2_bits(ctx):
+    rng = np.random.default_rng(3)
+    # every float of [0, 2*pi] that a degree angle times factorPI can produce is a float: sample
+    # 8 M of them uniformly in bit pattern plus a dense linear sweep
+    hi = int(np.float32(6.3).view(np.uint32))
+    x = np.concatenate([rng.integers(0, hi, 6_000_000).astype(np.uint32).view(np.float32),
+                        np.linspace(0, 6.3, 2_000_000).astype(np.float32),
+                        -np.linspace(0, 100.0, 100_000).astype(np.float32)])
+    y = rng.integers(-2700000, 2700000, len(x)).astype(np.float32)
+    s, c, _ = ctx.orb_selftest(x, y)
+    hs, hc = ref.libm_sincosf(x)
+    assert np.array_equal(s.view(np.uint32), hs.view(np.uint32))
+    assert np.array_equal(c.view(np.uint32), hc.view(np.uint32))
+    g = OC.golden()
+    _, _, t = ctx.orb_selftest(g["atan2/y"], g["atan2/x"])
+    assert np.array_equal(t.view(np.uint32), g["atan2/deg"].view(np.uint32))
