@@ -282,6 +282,55 @@ int lorb_orb_describe(lorb_ctx* ctx, const lorb_pyramid_view* raw, const lorb_py
                       int n_levels, const int* pattern, int n_kp, const float* kx, const float* ky,
                       const int* klevel, const float* angle_in, float* out_angle, uint8_t* out_desc);
 
+/*
+ * ORBextractor::operator() (reference src/ORBextractor.cpp:1087-1151): scale
+ * pyramid (ComputePyramid :1157-1184, cv::resize INTER_LINEAR level from level), FAST-9 with
+ * non-maximum suppression per ~30x30 cell at iniThFAST, else minThFAST (ComputeKeyPointsOctTree
+ * :799-880), quadtree selection of about nfeatures keypoints (DistributeOctTree :554-797),
+ * orientation, cv::GaussianBlur(7x7, 2) and the steered-BRIEF descriptors, keypoints scaled back
+ * to level-0 coordinates.  The OpenCV operations follow OpenCV 4.x (pinned to cv2 4.13; the
+ * reference's CMakeLists.txt:10 names 3.1).  The quadtree's tie-break among equally filled nodes
+ * (the reference compares node addresses, :695) is creation order: last created first.
+ *   params       the ORBextractor constructor arguments (:412-415)
+ *   pattern      as lorb_orb_describe
+ *   cap          capacity of the output arrays; the extractor returns slightly more than
+ *                nfeatures (each level stops at >= its share), nfeatures + 64 is safe
+ * Outputs in the reference's order (level by level, nodes in list order): KeyPoint pt.x, pt.y,
+ * octave, angle, response (may be NULL), size (may be NULL), descriptor rows; *n_out keypoints.
+ */
+typedef struct lorb_orb_params {
+  int nfeatures;
+  float scale_factor;
+  int nlevels;
+  int ini_th_fast;
+  int min_th_fast;
+} lorb_orb_params;
+
+int lorb_orb_extract(lorb_ctx* ctx, const uint8_t* image, int width, int height, int step,
+                     const lorb_orb_params* params, const int* pattern, int cap, float* kp_x,
+                     float* kp_y, int* kp_octave, float* kp_angle, float* kp_response, float* kp_size,
+                     uint8_t* desc, int* n_out);
+
+/* Level geometry of the extractor: sizes of the pyramid levels (:1161-1163), mnFeaturesPerLevel
+ * (:448-461, may be NULL) and mvScaleFactor (:428-436, may be NULL). */
+int lorb_orb_level_sizes(const lorb_orb_params* params, int width, int height, int* level_w,
+                         int* level_h, int* n_features_per_level, float* scale_factors);
+
+/*
+ * The intermediate products of the extractor, any of them optional (NULL):
+ *   raw_levels / blur_levels  [nlevels] host buffers of level_w*level_h bytes: mvImagePyramid and
+ *                             its blurred copy (what Frame::ComputeStereoMatches and
+ *                             lorb_orb_describe take)
+ *   cand_*                    the keypoints handed to DistributeOctTree (vToDistributeKeys :813),
+ *                             level after level in the reference's order (cell row, cell column,
+ *                             row-major inside the cell), coordinates relative to the 16-px
+ *                             margin; cand_level_start [nlevels + 1]
+ */
+int lorb_orb_stages(lorb_ctx* ctx, const uint8_t* image, int width, int height, int step,
+                    const lorb_orb_params* params, uint8_t* const* raw_levels,
+                    uint8_t* const* blur_levels, int cand_cap, float* cand_x, float* cand_y,
+                    float* cand_response, int* cand_level_start);
+
 /* ORBextractor::umax (:469-482): half widths of the rows 0..15 of the orientation disc. */
 void lorb_orb_umax(int* umax16);
 

@@ -26,6 +26,7 @@ EXPORTS = [
     "lorb_match_sweep_resident", "lorb_sweep_plan_upload", "lorb_sweep_plan_run",
     "lorb_sweep_plan_download", "lorb_sweep_plan_run_at", "lorb_search_proj_points", "lorb_search_proj_frame", "lorb_frustum_project", "lorb_compute_descriptors",
     "lorb_stereo_matches", "lorb_orb_describe", "lorb_orb_umax", "lorb_orb_selftest",
+    "lorb_orb_extract", "lorb_orb_level_sizes", "lorb_orb_stages",
     "lorb_ba_default_options", "lorb_ba_pose_only", "lorb_ba_local", "lorb_ba_local_batched",
     "lorb_ba_problem_create", "lorb_ba_problem_create_batched", "lorb_ba_problem_reset", "lorb_ba_problem_solve",
     "lorb_ba_problem_download", "lorb_ba_problem_destroy", "lorb_dist_get_unique_id",
@@ -64,6 +65,11 @@ class FrameView(C.Structure):
                 ("desc", C.c_void_p), ("kp_claim_obs", C.c_void_p), ("min_x", C.c_float),
                 ("max_x", C.c_float), ("min_y", C.c_float), ("max_y", C.c_float),
                 ("n_levels", C.c_int), ("scale_factors", C.c_void_p)]
+
+
+class OrbParams(C.Structure):
+    _fields_ = [("nfeatures", C.c_int), ("scale_factor", C.c_float), ("nlevels", C.c_int),
+                ("ini_th_fast", C.c_int), ("min_th_fast", C.c_int)]
 
 
 class PyramidView(C.Structure):
@@ -320,6 +326,49 @@ class Context:
             self._h, C.byref(vr), C.byref(vb), int(oi["n_levels"]), _ptr(a[0]), n, _ptr(a[1]), _ptr(a[2]),
             _ptr(a[3]), None if ain is None else _ptr(ain), _ptr(ang), _ptr(desc)))
         return ang[:n], desc[:n]
+
+    def orb_level_sizes(self, width, height, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7):
+        prm = OrbParams(nfeatures, scale_factor, nlevels, ini_th, min_th)
+        w, h, nf = np.zeros(nlevels, np.int32), np.zeros(nlevels, np.int32), np.zeros(nlevels, np.int32)
+        sf = np.zeros(nlevels, np.float32)
+        _check(self._lib.lorb_orb_level_sizes(C.byref(prm), width, height, _ptr(w), _ptr(h), _ptr(nf), _ptr(sf)))
+        return w, h, nf, sf
+
+    def orb_extract(self, img, pattern, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7):
+        """ORBextractor::operator() on one 8-bit image -> dict like oracle.reflib.orb_extract."""
+        img = _arr(img, np.uint8)
+        prm = OrbParams(nfeatures, scale_factor, nlevels, ini_th, min_th)
+        pat = _arr(pattern, np.int32).reshape(-1)
+        cap = nfeatures + 64
+        kx, ky = np.zeros(cap, np.float32), np.zeros(cap, np.float32)
+        ko, ka = np.zeros(cap, np.int32), np.zeros(cap, np.float32)
+        kr, ks = np.zeros(cap, np.float32), np.zeros(cap, np.float32)
+        desc = np.zeros((cap, 32), np.uint8)
+        n = C.c_int(0)
+        _check(self._lib.lorb_orb_extract(
+            self._h, _ptr(img), img.shape[1], img.shape[0], img.strides[0], C.byref(prm), _ptr(pat), cap,
+            _ptr(kx), _ptr(ky), _ptr(ko), _ptr(ka), _ptr(kr), _ptr(ks), _ptr(desc), C.byref(n)))
+        n = n.value
+        return dict(n=n, x=kx[:n], y=ky[:n], octave=ko[:n], angle=ka[:n], response=kr[:n], size=ks[:n],
+                    desc=desc[:n], n_per_level=np.bincount(ko[:n], minlength=nlevels).astype(np.int32))
+
+    def orb_stages(self, img, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7):
+        """Pyramid, blurred pyramid and the candidate keypoints handed to the quadtree."""
+        img = _arr(img, np.uint8)
+        prm = OrbParams(nfeatures, scale_factor, nlevels, ini_th, min_th)
+        w, h, _, _ = self.orb_level_sizes(img.shape[1], img.shape[0], nfeatures, scale_factor, nlevels, ini_th, min_th)
+        raw = [np.zeros((h[l], w[l]), np.uint8) for l in range(nlevels)]
+        blur = [np.zeros((h[l], w[l]), np.uint8) for l in range(nlevels)]
+        pr = (C.c_void_p * nlevels)(*[a.ctypes.data for a in raw])
+        pb = (C.c_void_p * nlevels)(*[a.ctypes.data for a in blur])
+        cap = int(sum(int(w[l]) * int(h[l]) for l in range(nlevels)) // 4 + 1024)
+        cx, cy, cr = np.zeros(cap, np.float32), np.zeros(cap, np.float32), np.zeros(cap, np.float32)
+        ls = np.zeros(nlevels + 1, np.int32)
+        _check(self._lib.lorb_orb_stages(
+            self._h, _ptr(img), img.shape[1], img.shape[0], img.strides[0], C.byref(prm), pr, pb, cap,
+            _ptr(cx), _ptr(cy), _ptr(cr), _ptr(ls)))
+        t = int(ls[-1])
+        return dict(raw=raw, blur=blur, cand_x=cx[:t], cand_y=cy[:t], cand_response=cr[:t], level_start=ls)
 
     def orb_selftest(self, a, b):
         a, b = _arr(a, np.float32), _arr(b, np.float32)

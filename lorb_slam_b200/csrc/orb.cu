@@ -9,6 +9,10 @@
 // points; the rotation uses sinf/cosf with the bits of the host's libm (libm_sincosf.cuh) and
 // separate fp32 multiply / add (the reference is compiled without FMA), each coordinate rounded
 // half-to-even as cvRound does.  The pattern (512 points, int8 pairs) sits in shared memory.
+#include <algorithm>
+#include <utility>
+#include <vector>
+
 #include "common.cuh"
 #include "libm_sincosf.cuh"
 
@@ -122,8 +126,9 @@ __global__ void orb_selftest_kernel(int n, const float* __restrict__ a, const fl
                                     float* __restrict__ o_sin, float* __restrict__ o_cos,
                                     float* __restrict__ o_atan2) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    o_sin[i] = lorb_libm::sinf_libm(a[i]);
-    o_cos[i] = lorb_libm::cosf_libm(a[i]);
+    const bool in_domain = fabsf(a[i]) < 120.0f;  // outside it the restatement traps by design
+    o_sin[i] = in_domain ? lorb_libm::sinf_libm(a[i]) : nanf("");
+    o_cos[i] = in_domain ? lorb_libm::cosf_libm(a[i]) : nanf("");
     o_atan2[i] = fast_atan2_cv(a[i], b[i]);
   }
 }
@@ -163,6 +168,478 @@ static void make_umax(int* umax) {
     while (umax[v0] == umax[v0 + 1]) ++v0;
     umax[v] = v0;
     ++v0;
+  }
+}
+
+
+// =====================================================================================
+// The detection side: pyramid, FAST per cell, blur (ORBextractor::operator() :1087-1151).
+// =====================================================================================
+//
+// ComputePyramid (:1157-1184): level l = cv::resize(level l-1, INTER_LINEAR).  8-bit INTER_LINEAR
+// is OpenCV's 11-bit fixed-point bilinear: coefficients round(2048*(1-f)), round(2048*f) from a
+// float fraction f of (d+0.5)*scale-0.5, horizontal pass in int, vertical pass
+// (((b0*(h0>>4))>>16) + ((b1*(h1>>4))>>16) + 2) >> 2.  One thread per output pixel; the source
+// level (<= 300 KB) is read through L1/L2.
+__global__ void __launch_bounds__(256)
+    orb_resize_kernel(const uint8_t* __restrict__ src, int sw, int sh, uint8_t* __restrict__ dst, int dw, int dh,
+                      double scale_x, double scale_y) {
+  const int dx = blockIdx.x * blockDim.x + threadIdx.x, dy = blockIdx.y * blockDim.y + threadIdx.y;
+  if (dx >= dw || dy >= dh) return;
+  float fx = (float)__dsub_rn(__dmul_rn((double)dx + 0.5, scale_x), 0.5);
+  int sx = __float2int_rd(fx);
+  fx = __fsub_rn(fx, (float)sx);
+  if (sx < 0) fx = 0.f, sx = 0;
+  if (sx >= sw - 1) fx = 0.f, sx = sw - 1;
+  float fy = (float)__dsub_rn(__dmul_rn((double)dy + 0.5, scale_y), 0.5);
+  const int sy = __float2int_rd(fy);
+  fy = __fsub_rn(fy, (float)sy);
+  const int a0 = __float2int_rn(__fmul_rn(__fsub_rn(1.f, fx), 2048.f)), a1 = __float2int_rn(__fmul_rn(fx, 2048.f));
+  const int b0 = __float2int_rn(__fmul_rn(__fsub_rn(1.f, fy), 2048.f)), b1 = __float2int_rn(__fmul_rn(fy, 2048.f));
+  const int sx1 = min(sx + 1, sw - 1);
+  const uint8_t* r0 = src + (size_t)min(max(sy, 0), sh - 1) * sw;
+  const uint8_t* r1 = src + (size_t)min(max(sy + 1, 0), sh - 1) * sw;
+  const int h0 = r0[sx] * a0 + r0[sx1] * a1, h1 = r1[sx] * a0 + r1[sx1] * a1;
+  dst[(size_t)dy * dw + dx] = (uint8_t)((((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2);
+}
+
+// Everything the multi-level kernels need to find their level from blockIdx.x.
+struct OrbPlanDev {
+  int n_levels;
+  int w[ORB_MAX_LEVELS], h[ORB_MAX_LEVELS];
+  uint8_t* raw[ORB_MAX_LEVELS];
+  uint8_t* blur[ORB_MAX_LEVELS];
+  int tile_start[ORB_MAX_LEVELS + 1];  // blur tiles
+  int tiles_x[ORB_MAX_LEVELS];
+  int cell_start[ORB_MAX_LEVELS + 1];  // FAST cells
+  int n_cols[ORB_MAX_LEVELS], w_cell[ORB_MAX_LEVELS], h_cell[ORB_MAX_LEVELS];
+  int slot_cap;                        // candidate slots per cell
+  int ini_th, min_th;
+};
+
+// cv::GaussianBlur(7x7, sigma 2, BORDER_REFLECT_101) of an 8-bit image in OpenCV 4's fixed-point
+// form: taps {18,34,48,56,48,34,18}/256 in both directions, exact integer accumulation, one
+// rounding (+2^15)>>16.  64x16 output tile per CTA, separable through shared memory.
+constexpr int BLUR_TX = 64, BLUR_TY = 16;
+
+__device__ __forceinline__ int reflect101(int p, int n) {
+  if (n == 1) return 0;
+  while (p < 0 || p >= n) p = p < 0 ? -p : 2 * n - 2 - p;
+  return p;
+}
+
+__global__ void __launch_bounds__(256) orb_blur_kernel(OrbPlanDev P) {
+  __shared__ uint8_t s_in[BLUR_TY + 6][BLUR_TX + 6 + 2];
+  __shared__ uint16_t s_h[BLUR_TY + 6][BLUR_TX];
+  int l = 0;
+  while (l + 1 < P.n_levels && (int)blockIdx.x >= P.tile_start[l + 1]) ++l;
+  const int t = blockIdx.x - P.tile_start[l];
+  const int w = P.w[l], h = P.h[l];
+  const int x0 = (t % P.tiles_x[l]) * BLUR_TX, y0 = (t / P.tiles_x[l]) * BLUR_TY;
+  const uint8_t* __restrict__ src = P.raw[l];
+  for (int p = threadIdx.x; p < (BLUR_TY + 6) * (BLUR_TX + 6); p += blockDim.x) {
+    const int ty = p / (BLUR_TX + 6), tx = p % (BLUR_TX + 6);
+    s_in[ty][tx] = src[(size_t)reflect101(y0 + ty - 3, h) * w + reflect101(x0 + tx - 3, w)];
+  }
+  __syncthreads();
+  for (int p = threadIdx.x; p < (BLUR_TY + 6) * BLUR_TX; p += blockDim.x) {
+    const int ty = p / BLUR_TX, tx = p % BLUR_TX;
+    const uint8_t* r = &s_in[ty][tx];
+    s_h[ty][tx] = (uint16_t)(18 * (r[0] + r[6]) + 34 * (r[1] + r[5]) + 48 * (r[2] + r[4]) + 56 * r[3]);
+  }
+  __syncthreads();
+  uint8_t* __restrict__ dst = P.blur[l];
+  for (int p = threadIdx.x; p < BLUR_TY * BLUR_TX; p += blockDim.x) {
+    const int ty = p / BLUR_TX, tx = p % BLUR_TX;
+    const int x = x0 + tx, y = y0 + ty;
+    if (x >= w || y >= h) continue;
+    const uint32_t v = 18u * (s_h[ty][tx] + s_h[ty + 6][tx]) + 34u * (s_h[ty + 1][tx] + s_h[ty + 5][tx]) +
+                       48u * (s_h[ty + 2][tx] + s_h[ty + 4][tx]) + 56u * s_h[ty + 3][tx];
+    dst[(size_t)y * w + x] = (uint8_t)((v + (1u << 15)) >> 16);
+  }
+}
+
+// ComputeKeyPointsOctTree's detection loop (:799-880): the level is cut into ~30x30 cells, each
+// cell image (cell + 6 px, clipped to 16 px inside the level) goes through cv::FAST(iniThFAST,
+// nonmax) and, if that finds nothing, cv::FAST(minThFAST, nonmax).
+//
+// FAST-9/16 restated: with A = the largest, over the 16 arcs of 9 ring pixels and both
+// polarities, of the smallest |centre - ring| on the arc, a pixel is a corner at threshold T iff
+// A > T and its OpenCV score (cornerScore<16>) is A - 1, independent of T.  cv::FAST only scores
+// pixels 3 px inside the image it is given and suppresses against the scores of that image, so a
+// keypoint of a cell is: score >= T, strictly greater than its 8 neighbours' scores, all taken
+// inside the cell interior.  One score map per cell therefore serves both thresholds.
+//
+// One CTA per cell: cell image in shared memory, A by a doubling sliding minimum over the ring,
+// suppression flags, block vote for "iniThFAST found something", ordered (row-major, as cv::FAST
+// emits) compaction into the cell's slot.  Candidates are packed score<<24 | y<<12 | x with x, y
+// relative to the level's 16-px margin (what the reference hands to DistributeOctTree).
+constexpr int CELL_MAX = 68;  // cell image side: wCell + 6 < 60 + 6
+
+__device__ __forceinline__ int arc9_min_max(const int (&d)[16]) {
+  int m2[16], m4[16], best = -256;
+#pragma unroll
+  for (int k = 0; k < 16; k++) m2[k] = min(d[k], d[(k + 1) & 15]);
+#pragma unroll
+  for (int k = 0; k < 16; k++) m4[k] = min(m2[k], m2[(k + 2) & 15]);
+#pragma unroll
+  for (int k = 0; k < 16; k++) best = max(best, min(min(m4[k], m4[(k + 4) & 15]), d[(k + 8) & 15]));
+  return best;
+}
+
+__global__ void __launch_bounds__(256)
+    orb_fast_cells_kernel(OrbPlanDev P, uint32_t* __restrict__ slots, int* __restrict__ cell_count) {
+  __shared__ uint8_t s_img[CELL_MAX * CELL_MAX];
+  __shared__ int16_t s_score[CELL_MAX * CELL_MAX];
+  __shared__ uint8_t s_keep[CELL_MAX * CELL_MAX];
+  __shared__ int s_warp[8];
+  __shared__ int s_base;
+  int l = 0;
+  while (l + 1 < P.n_levels && (int)blockIdx.x >= P.cell_start[l + 1]) ++l;
+  const int c = blockIdx.x - P.cell_start[l];
+  const int ci = c / P.n_cols[l], cj = c % P.n_cols[l];
+  const int w = P.w[l], h = P.h[l];
+  const int min_b = ORB_EDGE - 3, max_bx = w - ORB_EDGE + 3, max_by = h - ORB_EDGE + 3;
+  const int ini_y = min_b + ci * P.h_cell[l], ini_x = min_b + cj * P.w_cell[l];
+  const int max_y = min(ini_y + P.h_cell[l] + 6, max_by), max_x = min(ini_x + P.w_cell[l] + 6, max_bx);
+  const int sw = max_x - ini_x, sh = max_y - ini_y;
+  // the reference skips these cells (:832-833, :841-842); cv::FAST returns nothing below 7 px
+  if (ini_y >= max_by - 3 || ini_x >= max_bx - 6 || sw < 7 || sh < 7) {
+    if (threadIdx.x == 0) cell_count[blockIdx.x] = 0;
+    return;
+  }
+  const uint8_t* __restrict__ img = P.raw[l];
+  for (int p = threadIdx.x; p < sw * sh; p += blockDim.x) {
+    const int y = p / sw, x = p - y * sw;
+    s_img[y * CELL_MAX + x] = img[(size_t)(ini_y + y) * w + ini_x + x];
+    s_score[y * CELL_MAX + x] = 0;
+    s_keep[y * CELL_MAX + x] = 0;
+  }
+  __syncthreads();
+  const int iw = sw - 6, ih = sh - 6, n_in = iw * ih;
+  const int th_lo = min(P.ini_th, P.min_th);
+  for (int q = threadIdx.x; q < n_in; q += blockDim.x) {
+    const int y = q / iw + 3, x = q % iw + 3;
+    const uint8_t* p = &s_img[y * CELL_MAX + x];
+    const int v = p[0];
+    int d[16];
+    d[0] = v - p[3 * CELL_MAX];
+    d[1] = v - p[3 * CELL_MAX + 1];
+    d[2] = v - p[2 * CELL_MAX + 2];
+    d[3] = v - p[CELL_MAX + 3];
+    d[4] = v - p[3];
+    d[5] = v - p[-CELL_MAX + 3];
+    d[6] = v - p[-2 * CELL_MAX + 2];
+    d[7] = v - p[-3 * CELL_MAX + 1];
+    d[8] = v - p[-3 * CELL_MAX];
+    d[9] = v - p[-3 * CELL_MAX - 1];
+    d[10] = v - p[-2 * CELL_MAX - 2];
+    d[11] = v - p[-CELL_MAX - 3];
+    d[12] = v - p[-3];
+    d[13] = v - p[CELL_MAX - 3];
+    d[14] = v - p[2 * CELL_MAX - 2];
+    d[15] = v - p[3 * CELL_MAX - 1];
+    const int dark = arc9_min_max(d);  // ring darker than the centre
+#pragma unroll
+    for (int k = 0; k < 16; k++) d[k] = -d[k];
+    const int a = max(dark, arc9_min_max(d));
+    if (a > th_lo) s_score[y * CELL_MAX + x] = (int16_t)(a - 1);
+  }
+  __syncthreads();
+  int any_ini = 0;
+  for (int q = threadIdx.x; q < n_in; q += blockDim.x) {
+    const int y = q / iw + 3, x = q % iw + 3;
+    const int16_t* s = &s_score[y * CELL_MAX + x];
+    const int v = s[0];
+    const bool keep = v > 0 && v > s[-1] && v > s[1] && v > s[-CELL_MAX - 1] && v > s[-CELL_MAX] &&
+                      v > s[-CELL_MAX + 1] && v > s[CELL_MAX - 1] && v > s[CELL_MAX] && v > s[CELL_MAX + 1];
+    s_keep[y * CELL_MAX + x] = keep;
+    any_ini |= keep && v >= P.ini_th;
+  }
+  if (threadIdx.x == 0) s_base = 0;
+  const int th = __syncthreads_or(any_ini) ? P.ini_th : P.min_th;
+  uint32_t* __restrict__ slot = slots + (size_t)blockIdx.x * P.slot_cap;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int q0 = 0; q0 < n_in; q0 += blockDim.x) {
+    const int q = q0 + threadIdx.x;
+    bool keep = false;
+    int x = 0, y = 0, v = 0;
+    if (q < n_in) {
+      y = q / iw + 3;
+      x = q % iw + 3;
+      v = s_score[y * CELL_MAX + x];
+      keep = s_keep[y * CELL_MAX + x] && v >= th;
+    }
+    const uint32_t ballot = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) s_warp[warp] = __popc(ballot);
+    __syncthreads();
+    int off = s_base + __popc(ballot & ((1u << lane) - 1));
+    for (int k = 0; k < warp; k++) off += s_warp[k];
+    if (keep && off < P.slot_cap)
+      slot[off] = ((uint32_t)v << 24) | ((uint32_t)(ini_y + y - min_b) << 12) | (uint32_t)(ini_x + x - min_b);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int tot = 0;
+      for (int k = 0; k < 8; k++) tot += s_warp[k];
+      s_base += tot;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) cell_count[blockIdx.x] = s_base;
+}
+
+// Cells in (level, row, column) order -> one dense candidate list (written straight into mapped
+// pinned host memory) and the per-level start offsets.  Single CTA: <= a few thousand cells.
+__global__ void __launch_bounds__(1024)
+    orb_compact_kernel(OrbPlanDev P, const uint32_t* __restrict__ slots, const int* __restrict__ cell_count,
+                       int* __restrict__ cell_offset, uint32_t* __restrict__ dense, int dense_cap,
+                       int* __restrict__ level_start) {
+  __shared__ int s_part[1024];
+  const int n_cells = P.cell_start[P.n_levels];
+  const int per = (n_cells + blockDim.x - 1) / blockDim.x;
+  const int lo = min((int)threadIdx.x * per, n_cells), hi = min(lo + per, n_cells);
+  int sum = 0;
+  for (int k = lo; k < hi; k++) sum += min(cell_count[k], P.slot_cap);
+  s_part[threadIdx.x] = sum;
+  __syncthreads();
+  for (int o = 1; o < (int)blockDim.x; o <<= 1) {
+    const int v = threadIdx.x >= o ? s_part[threadIdx.x - o] : 0;
+    __syncthreads();
+    s_part[threadIdx.x] += v;
+    __syncthreads();
+  }
+  int run = s_part[threadIdx.x] - sum;
+  for (int k = lo; k < hi; k++) {
+    cell_offset[k] = run;
+    run += min(cell_count[k], P.slot_cap);
+  }
+  if (threadIdx.x == blockDim.x - 1) level_start[P.n_levels] = s_part[threadIdx.x];
+  __syncthreads();
+  if (threadIdx.x < P.n_levels) level_start[threadIdx.x] = cell_offset[P.cell_start[threadIdx.x]];
+  // overflow flag: a cell that produced more than its slot holds (cannot happen for slot_cap =
+  // ceil(w/2)*ceil(h/2) of the interior, kept as a loud check)
+  if (threadIdx.x == 0) level_start[P.n_levels + 1] = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+  for (int k = warp; k < n_cells; k += n_warps) {
+    const int cnt = cell_count[k], off = cell_offset[k];
+    if (cnt > P.slot_cap && lane == 0) level_start[P.n_levels + 1] = 1;
+    for (int e = lane; e < min(cnt, P.slot_cap); e += 32)
+      if (off + e < dense_cap) dense[off + e] = slots[(size_t)k * P.slot_cap + e];
+  }
+}
+
+// ------------------------------------------------------------------ host: level plan + quadtree
+struct OrbLevelPlan {
+  int n_levels;
+  float scale[ORB_MAX_LEVELS], inv_scale[ORB_MAX_LEVELS];
+  int w[ORB_MAX_LEVELS], h[ORB_MAX_LEVELS];
+  int n_features[ORB_MAX_LEVELS];
+  int n_cols[ORB_MAX_LEVELS], n_rows[ORB_MAX_LEVELS], w_cell[ORB_MAX_LEVELS], h_cell[ORB_MAX_LEVELS];
+};
+
+// The ORBextractor constructor (:412-461) and the level sizes of ComputePyramid (:1161-1163), in
+// the reference's float arithmetic.
+static int make_level_plan(const lorb_orb_params* p, int width, int height, OrbLevelPlan* L) {
+  LORB_REQUIRE(p->nlevels >= 1 && p->nlevels <= ORB_MAX_LEVELS, "nlevels");
+  LORB_REQUIRE(p->scale_factor > 1.0f, "scale_factor");
+  LORB_REQUIRE(p->nfeatures >= 1, "nfeatures");
+  LORB_REQUIRE(p->min_th_fast >= 1 && p->ini_th_fast >= 1 && p->min_th_fast <= 254 && p->ini_th_fast <= 254,
+               "FAST thresholds");
+  const int n = L->n_levels = p->nlevels;
+  L->scale[0] = 1.0f;
+  for (int i = 1; i < n; i++) L->scale[i] = L->scale[i - 1] * p->scale_factor;
+  for (int i = 0; i < n; i++) L->inv_scale[i] = 1.0f / L->scale[i];
+  const float factor = 1.0f / p->scale_factor;
+  float per_scale = p->nfeatures * (1 - factor) / (1 - (float)pow((double)factor, (double)n));
+  int sum = 0;
+  for (int l = 0; l < n - 1; l++) {
+    L->n_features[l] = (int)lrintf(per_scale);
+    sum += L->n_features[l];
+    per_scale *= factor;
+  }
+  L->n_features[n - 1] = std::max(p->nfeatures - sum, 0);
+  for (int l = 0; l < n; l++) {
+    L->w[l] = (int)lrintf((float)width * L->inv_scale[l]);
+    L->h[l] = (int)lrintf((float)height * L->inv_scale[l]);
+    const float bw = (float)(L->w[l] - 2 * ORB_EDGE + 6), bh = (float)(L->h[l] - 2 * ORB_EDGE + 6);
+    L->n_cols[l] = (int)(bw / 30.f);  // W = 30 (:803)
+    L->n_rows[l] = (int)(bh / 30.f);
+    // below one cell the reference divides by zero (:821-822)
+    LORB_REQUIRE(L->n_cols[l] >= 1 && L->n_rows[l] >= 1, "pyramid level smaller than one 30 px cell + margins");
+    L->w_cell[l] = (int)ceilf(bw / L->n_cols[l]);
+    L->h_cell[l] = (int)ceilf(bh / L->n_rows[l]);
+    LORB_REQUIRE(L->w[l] - 2 * ORB_EDGE + 6 < 4096 && L->h[l] - 2 * ORB_EDGE + 6 < 4096, "image larger than 4096 px");
+  }
+  return LORB_OK;
+}
+
+struct QKey {
+  float x, y, response;
+};
+
+// ORBextractor::DistributeOctTree (:554-797) on an index-linked node list.
+//   * the node list keeps the reference's order: children are pushed to the FRONT in the order
+//     n1..n4 as their parent is erased, a pass walks from the (old) front to the back;
+//   * a pass expands every node with more than one key; when the next pass could overshoot N
+//     (size + 3*expandable > N) the nodes are expanded largest first instead (:687-753).  The
+//     reference orders equal sizes by node ADDRESS (std::sort of (size, pointer) pairs); under an
+//     allocator that never reuses memory that is creation order, which is the rule here (and how
+//     oracle/_ref runs the reference): among equal sizes the node created LAST goes first;
+//   * each surviving node yields its first key of maximal response (:776-794).
+// Keys of a node are a contiguous run of `perm`, children are a stable 4-way partition of it.
+struct QNode {
+  int x0, x1, y0, y1;
+  int k0, k1;      // keys perm[k0 .. k1)
+  int prev, next;  // list links (-1 = none)
+  bool no_more;
+};
+
+static void distribute_quadtree(const std::vector<QKey>& keys, int min_x, int max_x, int min_y, int max_y, int N,
+                                std::vector<int>* result) {
+  result->clear();
+  const int n_keys = (int)keys.size();
+  const int n_ini = (int)roundf((float)(max_x - min_x) / (max_y - min_y));
+  if (n_ini < 1 || n_keys == 0) return;  // (the reference divides by zero for n_ini == 0)
+  const float h_x = (float)(max_x - min_x) / n_ini;
+  std::vector<QNode> nodes;
+  nodes.reserve((size_t)4 * n_keys + n_ini + 16);
+  std::vector<int> perm(n_keys), tmp(n_keys);
+  int head = -1, tail = -1, size = 0;
+  auto push_back = [&](int id) {
+    nodes[id].prev = tail;
+    nodes[id].next = -1;
+    if (tail >= 0) nodes[tail].next = id; else head = id;
+    tail = id;
+    ++size;
+  };
+  auto push_front = [&](int id) {
+    nodes[id].prev = -1;
+    nodes[id].next = head;
+    if (head >= 0) nodes[head].prev = id; else tail = id;
+    head = id;
+    ++size;
+  };
+  auto erase = [&](int id) {  // returns the next node
+    const int p = nodes[id].prev, nx = nodes[id].next;
+    if (p >= 0) nodes[p].next = nx; else head = nx;
+    if (nx >= 0) nodes[nx].prev = p; else tail = p;
+    --size;
+    return nx;
+  };
+  // initial nodes (:571-594): keys go to column (int)(x / hX), in input order
+  {
+    std::vector<int> cnt(n_ini + 1, 0), col(n_keys);
+    for (int i = 0; i < n_keys; i++) {
+      col[i] = std::min((int)(keys[i].x / h_x), n_ini - 1);
+      cnt[col[i] + 1]++;
+    }
+    for (int i = 0; i < n_ini; i++) cnt[i + 1] += cnt[i];
+    std::vector<int> fill(cnt.begin(), cnt.end() - 1);
+    for (int i = 0; i < n_keys; i++) perm[fill[col[i]]++] = i;
+    for (int i = 0; i < n_ini; i++) {
+      QNode nd;
+      nd.x0 = (int)(h_x * (float)i);
+      nd.x1 = (int)(h_x * (float)(i + 1));
+      nd.y0 = 0;
+      nd.y1 = max_y - min_y;
+      nd.k0 = cnt[i];
+      nd.k1 = cnt[i + 1];
+      nd.no_more = false;
+      nodes.push_back(nd);
+      push_back((int)nodes.size() - 1);
+    }
+  }
+  for (int id = head; id >= 0;) {  // :598-609
+    const int nk = nodes[id].k1 - nodes[id].k0;
+    if (nk == 1) {
+      nodes[id].no_more = true;
+      id = nodes[id].next;
+    } else if (nk == 0) {
+      id = erase(id);
+    } else {
+      id = nodes[id].next;
+    }
+  }
+  // DivideNode (:496-551) + the four push_front blocks; appends children with > 1 keys to `grown`
+  std::vector<std::pair<int, int>> grown, prev_grown;  // (size, node id = creation order)
+  auto divide = [&](int id) {
+    const QNode nd = nodes[id];
+    const int half_x = (int)ceilf((float)(nd.x1 - nd.x0) / 2), half_y = (int)ceilf((float)(nd.y1 - nd.y0) / 2);
+    const int xm = nd.x0 + half_x, ym = nd.y0 + half_y;
+    int cnt[4] = {0, 0, 0, 0};
+    for (int k = nd.k0; k < nd.k1; k++) {
+      const QKey& kp = keys[perm[k]];
+      const int q = kp.x < xm ? (kp.y < ym ? 0 : 2) : (kp.y < ym ? 1 : 3);
+      tmp[k] = q;
+      cnt[q]++;
+    }
+    int start[4], fill[4];
+    start[0] = nd.k0;
+    for (int q = 1; q < 4; q++) start[q] = start[q - 1] + cnt[q - 1];
+    for (int q = 0; q < 4; q++) fill[q] = start[q];
+    std::vector<int> moved(nd.k1 - nd.k0);
+    for (int k = nd.k0; k < nd.k1; k++) moved[fill[tmp[k]]++ - nd.k0] = perm[k];
+    std::copy(moved.begin(), moved.end(), perm.begin() + nd.k0);
+    const int bx0[4] = {nd.x0, xm, nd.x0, xm}, bx1[4] = {xm, nd.x1, xm, nd.x1};
+    const int by0[4] = {nd.y0, nd.y0, ym, ym}, by1[4] = {ym, ym, nd.y1, nd.y1};
+    int expandable = 0;
+    for (int q = 0; q < 4; q++) {
+      if (cnt[q] == 0) continue;
+      QNode ch;
+      ch.x0 = bx0[q];
+      ch.x1 = bx1[q];
+      ch.y0 = by0[q];
+      ch.y1 = by1[q];
+      ch.k0 = start[q];
+      ch.k1 = start[q] + cnt[q];
+      ch.no_more = cnt[q] == 1;
+      nodes.push_back(ch);
+      const int cid = (int)nodes.size() - 1;
+      push_front(cid);
+      if (cnt[q] > 1) {
+        ++expandable;
+        grown.emplace_back(cnt[q], cid);
+      }
+    }
+    return expandable;
+  };
+  bool finish = false;
+  while (!finish) {
+    const int prev_size = size;
+    int to_expand = 0;
+    grown.clear();
+    for (int id = head; id >= 0;) {
+      if (nodes[id].no_more) {
+        id = nodes[id].next;
+        continue;
+      }
+      to_expand += divide(id);
+      id = erase(id);
+    }
+    if (size >= N || size == prev_size) {
+      finish = true;
+    } else if (size + to_expand * 3 > N) {
+      while (!finish) {
+        const int prev_size2 = size;
+        prev_grown = grown;
+        grown.clear();
+        std::sort(prev_grown.begin(), prev_grown.end());  // (size, creation order) ascending
+        for (int j = (int)prev_grown.size() - 1; j >= 0; j--) {
+          divide(prev_grown[j].second);
+          erase(prev_grown[j].second);
+          if (size >= N) break;
+        }
+        if (size >= N || size == prev_size2) finish = true;
+      }
+    }
+  }
+  result->reserve(size);
+  for (int id = head; id >= 0; id = nodes[id].next) {
+    int best = perm[nodes[id].k0];
+    for (int k = nodes[id].k0 + 1; k < nodes[id].k1; k++)
+      if (keys[perm[k]].response > keys[best].response) best = perm[k];
+    result->push_back(best);
   }
 }
 
@@ -252,6 +729,282 @@ int lorb_orb_describe(lorb_ctx* c, const lorb_pyramid_view* raw, const lorb_pyra
   if (out_angle) memcpy(out_angle, ho + o_ang, (size_t)n_kp * 4);
   memcpy(out_desc, ho + o_desc, (size_t)n_kp * 32);
   return LORB_OK;
+}
+
+// Shared body of lorb_orb_extract / lorb_orb_stages.
+namespace {
+
+struct ExtractOut {
+  // stages (all optional)
+  uint8_t* const* raw_levels = nullptr;   // [n_levels] host buffers w*h
+  uint8_t* const* blur_levels = nullptr;  // [n_levels]
+  int cand_cap = 0;
+  float *cand_x = nullptr, *cand_y = nullptr, *cand_resp = nullptr;
+  int* cand_level_start = nullptr;  // [n_levels + 1]
+  // final keypoints
+  int cap = 0;
+  float *kx = nullptr, *ky = nullptr, *kangle = nullptr, *kresp = nullptr, *ksize = nullptr;
+  int* koct = nullptr;
+  uint8_t* desc = nullptr;
+  int* n_out = nullptr;
+  int* n_per_level = nullptr;
+  int* level_w = nullptr;
+  int* level_h = nullptr;
+};
+
+int orb_run(lorb_ctx* c, const uint8_t* image, int width, int height, int step, const lorb_orb_params* prm,
+            const int* pattern, const ExtractOut& O) {
+  LORB_REQUIRE(c && image && prm, "ctx / image / params");
+  LORB_REQUIRE(width > 0 && height > 0 && step >= width, "image shape");
+  OrbLevelPlan L;
+  LORB_TRY(make_level_plan(prm, width, height, &L));
+  const int nl = L.n_levels;
+  const bool want_desc = O.desc != nullptr;
+  if (want_desc) {
+    LORB_REQUIRE(pattern, "pattern");
+    for (int k = 0; k < 512; k++)
+      LORB_REQUIRE(pattern[2 * k] * pattern[2 * k] + pattern[2 * k + 1] * pattern[2 * k + 1] < ORB_EDGE * ORB_EDGE,
+                   "pattern radius");
+  }
+  LORB_CUDA_TRY(cudaSetDevice(c->device));
+
+  // ---- device layout: raw + blurred levels, cell slots, counts
+  OPacker dv;
+  size_t o_raw[ORB_MAX_LEVELS], o_blur[ORB_MAX_LEVELS];
+  for (int l = 0; l < nl; l++) o_raw[l] = dv.add((size_t)L.w[l] * L.h[l]);
+  for (int l = 0; l < nl; l++) o_blur[l] = dv.add((size_t)L.w[l] * L.h[l]);
+  OrbPlanDev P;
+  memset(&P, 0, sizeof(P));
+  P.n_levels = nl;
+  P.ini_th = prm->ini_th_fast;
+  P.min_th = prm->min_th_fast;
+  int n_cells = 0, n_tiles = 0, slot_cap = 0;
+  for (int l = 0; l < nl; l++) {
+    P.w[l] = L.w[l];
+    P.h[l] = L.h[l];
+    P.tile_start[l] = n_tiles;
+    P.tiles_x[l] = (L.w[l] + BLUR_TX - 1) / BLUR_TX;
+    n_tiles += P.tiles_x[l] * ((L.h[l] + BLUR_TY - 1) / BLUR_TY);
+    P.cell_start[l] = n_cells;
+    P.n_cols[l] = L.n_cols[l];
+    P.w_cell[l] = L.w_cell[l];
+    P.h_cell[l] = L.h_cell[l];
+    n_cells += L.n_cols[l] * L.n_rows[l];
+    LORB_REQUIRE(L.w_cell[l] + 6 <= CELL_MAX && L.h_cell[l] + 6 <= CELL_MAX, "cell size");
+    // suppression leaves no two adjacent survivors: at most ceil(w/2)*ceil(h/2) per interior
+    slot_cap = std::max(slot_cap, ((L.w_cell[l] + 1) / 2) * ((L.h_cell[l] + 1) / 2));
+  }
+  P.tile_start[nl] = n_tiles;
+  P.cell_start[nl] = n_cells;
+  P.slot_cap = slot_cap;
+  const size_t o_slots = dv.add((size_t)n_cells * slot_cap * 4), o_cnt = dv.add((size_t)n_cells * 4),
+               o_off = dv.add((size_t)n_cells * 4);
+  LORB_TRY(dev_reserve(c, 3, dv.off));
+  uint8_t* d = c->d[3].as<uint8_t>();
+  for (int l = 0; l < nl; l++) {
+    P.raw[l] = d + o_raw[l];
+    P.blur[l] = d + o_blur[l];
+  }
+
+  // ---- host staging (pinned): image in; candidates + level starts out (written by the GPU)
+  const int dense_cap = n_cells * slot_cap;
+  OPacker hs;
+  const size_t h_img = hs.add((size_t)width * height), h_lvl = hs.add((size_t)(nl + 2) * 4),
+               h_dense = hs.add((size_t)dense_cap * 4);
+  LORB_TRY(pin_reserve(c, 2, hs.off));
+  uint8_t* hp = c->h[2].as<uint8_t>();
+  if (step == width) {
+    memcpy(hp + h_img, image, (size_t)width * height);
+  } else {
+    for (int r = 0; r < height; r++) memcpy(hp + h_img + (size_t)r * width, image + (size_t)r * step, width);
+  }
+  LORB_CUDA_TRY(cudaMemcpyAsync(P.raw[0], hp + h_img, (size_t)width * height, cudaMemcpyHostToDevice, c->stream));
+  for (int l = 1; l < nl; l++) {
+    // scale = 1 / (dsize / ssize) in double, as cv::resize derives it from the two sizes
+    const double sx = 1. / ((double)L.w[l] / L.w[l - 1]), sy = 1. / ((double)L.h[l] / L.h[l - 1]);
+    const dim3 blk(32, 8), grd((L.w[l] + 31) / 32, (L.h[l] + 7) / 8);
+    LORB_LAUNCH(c, orb_resize_kernel, grd, blk, 0, P.raw[l - 1], L.w[l - 1], L.h[l - 1], P.raw[l], L.w[l], L.h[l], sx,
+                sy);
+  }
+  int* lvl_host = (int*)(hp + h_lvl);
+  uint32_t* dense_host = (uint32_t*)(hp + h_dense);
+  LORB_LAUNCH(c, orb_fast_cells_kernel, n_cells, 256, 0, P, (uint32_t*)(d + o_slots), (int*)(d + o_cnt));
+  LORB_LAUNCH(c, orb_compact_kernel, 1, 1024, 0, P, (const uint32_t*)(d + o_slots), (const int*)(d + o_cnt),
+              (int*)(d + o_off), dense_host, dense_cap, lvl_host);
+  cudaEvent_t ev;
+  LORB_CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  LORB_CUDA_TRY(cudaEventRecord(ev, c->stream));
+  // the blur of all levels runs while the host distributes the keypoints
+  if (want_desc || O.blur_levels) LORB_LAUNCH(c, orb_blur_kernel, n_tiles, 256, 0, P);
+  cudaError_t ee = cudaEventSynchronize(ev);
+  cudaEventDestroy(ev);
+  LORB_CUDA_TRY(ee);
+  LORB_REQUIRE(lvl_host[nl + 1] == 0 && lvl_host[nl] <= dense_cap, "candidate slot overflow (internal)");
+
+  if (O.cand_level_start) {
+    const int total = lvl_host[nl];
+    LORB_REQUIRE(total <= O.cand_cap, "candidate capacity");
+    for (int l = 0; l <= nl; l++) O.cand_level_start[l] = lvl_host[l];
+    for (int i = 0; i < total; i++) {
+      const uint32_t e = dense_host[i];
+      O.cand_x[i] = (float)(e & 0xfff);
+      O.cand_y[i] = (float)((e >> 12) & 0xfff);
+      O.cand_resp[i] = (float)(e >> 24);
+    }
+  }
+
+  // ---- DistributeOctTree per level (:865-866), levels are independent
+  std::vector<std::vector<int>> chosen(nl);
+  std::vector<std::vector<QKey>> keys(nl);
+  int n_total = 0;
+  if (O.n_out || want_desc) {
+#pragma omp parallel for schedule(dynamic, 1) num_threads(std::min(nl, 8))
+    for (int l = 0; l < nl; l++) {
+      const int a = lvl_host[l], b = lvl_host[l + 1];
+      keys[l].resize(b - a);
+      for (int i = a; i < b; i++) {
+        const uint32_t e = dense_host[i];
+        keys[l][i - a] = QKey{(float)(e & 0xfff), (float)((e >> 12) & 0xfff), (float)(e >> 24)};
+      }
+      const int min_b = ORB_EDGE - 3;
+      distribute_quadtree(keys[l], min_b, L.w[l] - ORB_EDGE + 3, min_b, L.h[l] - ORB_EDGE + 3, L.n_features[l],
+                          &chosen[l]);
+    }
+    for (int l = 0; l < nl; l++) n_total += (int)chosen[l].size();
+    if (O.n_out) *O.n_out = n_total;
+    LORB_REQUIRE(n_total <= O.cap, "keypoint capacity (nfeatures + a few: the quadtree stops at >= N per level)");
+  }
+
+  // ---- orientation + descriptors of the chosen keypoints (level coordinates)
+  if (n_total > 0 && (want_desc || O.kangle)) {
+    OPacker in, out;
+    const size_t i_kx = in.add((size_t)n_total * 4), i_ky = in.add((size_t)n_total * 4),
+                 i_kl = in.add((size_t)n_total * 4), i_tab = in.add(sizeof(OrbTables));
+    const size_t o_ang = out.add((size_t)n_total * 4), o_desc = out.add((size_t)n_total * 32);
+    LORB_TRY(pin_reserve(c, 0, in.off));
+    LORB_TRY(pin_reserve(c, 1, out.off));
+    LORB_TRY(dev_reserve(c, 0, in.off));
+    LORB_TRY(dev_reserve(c, 2, out.off));
+    uint8_t* h = c->h[0].as<uint8_t>();
+    float *hx = (float*)(h + i_kx), *hy = (float*)(h + i_ky);
+    int* hl = (int*)(h + i_kl);
+    int k = 0;
+    for (int l = 0; l < nl; l++)
+      for (int id : chosen[l]) {
+        hx[k] = keys[l][id].x + (float)(ORB_EDGE - 3);  // pt += minBorder (:873-874)
+        hy[k] = keys[l][id].y + (float)(ORB_EDGE - 3);
+        hl[k] = l;
+        k++;
+      }
+    OrbTables* t = (OrbTables*)(h + i_tab);
+    memset(t, 0, sizeof(OrbTables));
+    if (pattern)
+      for (int q = 0; q < 512; q++)
+        t->pattern[q] = make_char2((signed char)pattern[2 * q], (signed char)pattern[2 * q + 1]);
+    make_umax(t->umax);
+    uint8_t* din = c->d[0].as<uint8_t>();
+    uint8_t* dout = c->d[2].as<uint8_t>();
+    LORB_CUDA_TRY(cudaMemcpyAsync(din, h, in.off, cudaMemcpyHostToDevice, c->stream));
+    OrbLevelsDev LV;
+    for (int l = 0; l < nl; l++) {
+      LV.raw[l] = P.raw[l];
+      LV.blur[l] = P.blur[l];
+      LV.w[l] = L.w[l];
+      LV.h[l] = L.h[l];
+    }
+    const int warps_per_cta = 8;
+    LORB_LAUNCH(c, orb_describe_kernel, (n_total + warps_per_cta - 1) / warps_per_cta, warps_per_cta * 32, 0, LV,
+                n_total, (const float*)(din + i_kx), (const float*)(din + i_ky), (const int*)(din + i_kl),
+                (const OrbTables*)(din + i_tab), (float*)(dout + o_ang), (uint32_t*)(dout + o_desc), 0);
+    uint8_t* ho = c->h[1].as<uint8_t>();
+    LORB_CUDA_TRY(cudaMemcpyAsync(ho, dout, out.off, cudaMemcpyDeviceToHost, c->stream));
+    if (O.raw_levels || O.blur_levels)
+      for (int l = 0; l < nl; l++) {
+        if (O.raw_levels) LORB_CUDA_TRY(cudaMemcpyAsync(O.raw_levels[l], P.raw[l], (size_t)L.w[l] * L.h[l], cudaMemcpyDeviceToHost, c->stream));
+        if (O.blur_levels) LORB_CUDA_TRY(cudaMemcpyAsync(O.blur_levels[l], P.blur[l], (size_t)L.w[l] * L.h[l], cudaMemcpyDeviceToHost, c->stream));
+      }
+    LORB_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    k = 0;
+    for (int l = 0; l < nl; l++) {
+      const float scale = L.scale[l];
+      const float patch = (float)(int)(31 * scale);  // scaledPatchSize = PATCH_SIZE*mvScaleFactor (:868)
+      for (int id : chosen[l]) {
+        float x = hx[k], y = hy[k];
+        if (l != 0) x = x * scale, y = y * scale;  // keypoint->pt *= scale (:1142-1147)
+        if (O.kx) O.kx[k] = x;
+        if (O.ky) O.ky[k] = y;
+        if (O.koct) O.koct[k] = l;
+        if (O.kangle) O.kangle[k] = ((const float*)(ho + o_ang))[k];
+        if (O.kresp) O.kresp[k] = keys[l][id].response;
+        if (O.ksize) O.ksize[k] = patch;
+        k++;
+      }
+    }
+    if (want_desc) memcpy(O.desc, ho + o_desc, (size_t)n_total * 32);
+  } else {
+    if (O.raw_levels || O.blur_levels)
+      for (int l = 0; l < nl; l++) {
+        if (O.raw_levels) LORB_CUDA_TRY(cudaMemcpyAsync(O.raw_levels[l], P.raw[l], (size_t)L.w[l] * L.h[l], cudaMemcpyDeviceToHost, c->stream));
+        if (O.blur_levels) LORB_CUDA_TRY(cudaMemcpyAsync(O.blur_levels[l], P.blur[l], (size_t)L.w[l] * L.h[l], cudaMemcpyDeviceToHost, c->stream));
+      }
+    LORB_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  }
+  if (O.n_per_level)
+    for (int l = 0; l < nl; l++) O.n_per_level[l] = (int)chosen[l].size();
+  if (O.level_w)
+    for (int l = 0; l < nl; l++) O.level_w[l] = L.w[l], O.level_h[l] = L.h[l];
+  return LORB_OK;
+}
+
+}  // namespace
+
+int lorb_orb_level_sizes(const lorb_orb_params* prm, int width, int height, int* level_w, int* level_h,
+                         int* n_features_per_level, float* scale_factors) {
+  LORB_REQUIRE(prm && level_w && level_h, "arguments");
+  OrbLevelPlan L;
+  LORB_TRY(make_level_plan(prm, width, height, &L));
+  for (int l = 0; l < L.n_levels; l++) {
+    level_w[l] = L.w[l];
+    level_h[l] = L.h[l];
+    if (n_features_per_level) n_features_per_level[l] = L.n_features[l];
+    if (scale_factors) scale_factors[l] = L.scale[l];
+  }
+  return LORB_OK;
+}
+
+int lorb_orb_extract(lorb_ctx* c, const uint8_t* image, int width, int height, int step,
+                     const lorb_orb_params* prm, const int* pattern, int cap, float* kp_x, float* kp_y,
+                     int* kp_octave, float* kp_angle, float* kp_response, float* kp_size, uint8_t* desc,
+                     int* n_out) {
+  LORB_REQUIRE(cap >= 0 && kp_x && kp_y && kp_octave && kp_angle && desc && n_out, "output arrays");
+  ExtractOut O;
+  O.cap = cap;
+  O.kx = kp_x;
+  O.ky = kp_y;
+  O.koct = kp_octave;
+  O.kangle = kp_angle;
+  O.kresp = kp_response;
+  O.ksize = kp_size;
+  O.desc = desc;
+  O.n_out = n_out;
+  return orb_run(c, image, width, height, step, prm, pattern, O);
+}
+
+int lorb_orb_stages(lorb_ctx* c, const uint8_t* image, int width, int height, int step,
+                    const lorb_orb_params* prm, uint8_t* const* raw_levels, uint8_t* const* blur_levels,
+                    int cand_cap, float* cand_x, float* cand_y, float* cand_response, int* cand_level_start) {
+  ExtractOut O;
+  O.raw_levels = raw_levels;
+  O.blur_levels = blur_levels;
+  if (cand_level_start) {
+    LORB_REQUIRE(cand_cap >= 0 && cand_x && cand_y && cand_response, "candidate arrays");
+    O.cand_cap = cand_cap;
+    O.cand_x = cand_x;
+    O.cand_y = cand_y;
+    O.cand_resp = cand_response;
+    O.cand_level_start = cand_level_start;
+  }
+  return orb_run(c, image, width, height, step, prm, nullptr, O);
 }
 
 int lorb_orb_selftest(lorb_ctx* c, int n, const float* a, const float* b, float* out_sin, float* out_cos,

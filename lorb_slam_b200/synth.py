@@ -489,3 +489,40 @@ def make_orb_inputs(n_kp=1000, seed=0, width=640, height=480, n_levels=8, border
     kx = np.where(half, kx, np.rint(kx)).astype(np.float32)
     ky = np.where(half, ky, np.rint(ky)).astype(np.float32)
     return dict(n_levels=n_levels, pyr_raw=raw, pyr_blur=blurred, n_kp=n_kp, kx=kx, ky=ky, klevel=lvl)
+
+
+# ------------------------------------------------------- ORB extractor images (BASELINE config 0)
+
+def make_orb_image(seed=0, width=640, height=480):
+    """A synthetic 8-bit frame for ORBextractor::operator() (reference src/ORBextractor.cpp:1087):
+    blurred noise with random filled rectangles (corners at every contrast), a low-contrast band
+    where only minThFAST finds anything, and a flat patch where nothing does."""
+    rng = np.random.default_rng(seed + 515151)
+    tex = rng.random((height, width)) * 255.0
+    img = 0.5 * _blur(tex, 3) + 0.5 * _blur(tex, 9)
+    for _ in range(400):
+        x, y = int(rng.integers(0, width - 10)), int(rng.integers(0, height - 10))
+        w, h = int(rng.integers(4, 60)), int(rng.integers(4, 60))
+        img[y:y + h, x:x + w] = 0.5 * img[y:y + h, x:x + w] + 0.5 * rng.integers(0, 256)
+    y0 = height // 3
+    band = img[y0:y0 + height // 6]
+    img[y0:y0 + height // 6] = 128 + (band - band.mean()) * 0.12  # weak corners only
+    img[height - height // 5:height - height // 10, width // 8:width // 2] = 90.0  # flat
+    return np.ascontiguousarray(np.clip(np.rint(img), 0, 255).astype(np.uint8))
+
+
+def warp_orb_image(img, angle_deg=3.0, scale=1.02, shift=(4.0, -3.0)):
+    """The second frame of the config-0 pair: `img` under a small similarity (bilinear sampling,
+    border replicated)."""
+    h, w = img.shape
+    a = np.deg2rad(angle_deg)
+    ca, sa = np.cos(a) / scale, np.sin(a) / scale
+    ys, xs = np.mgrid[0:h, 0:w].astype(np.float64)
+    xc, yc = xs - w / 2 - shift[0], ys - h / 2 - shift[1]
+    sx = np.clip(ca * xc + sa * yc + w / 2, 0, w - 1.001)
+    sy = np.clip(-sa * xc + ca * yc + h / 2, 0, h - 1.001)
+    x0, y0 = np.floor(sx).astype(int), np.floor(sy).astype(int)
+    fx, fy = sx - x0, sy - y0
+    f = img.astype(np.float64)
+    out = (f[y0, x0] * (1 - fx) + f[y0, x0 + 1] * fx) * (1 - fy) + (f[y0 + 1, x0] * (1 - fx) + f[y0 + 1, x0 + 1] * fx) * fy
+    return np.ascontiguousarray(np.clip(np.rint(out), 0, 255).astype(np.uint8))

@@ -278,6 +278,53 @@ def sincosf_mismatches(lo_bits, hi_bits, stride):
     return int(_orb().orc_sincosf_mismatches(lo_bits, hi_bits, stride))
 
 
+def resize_linear(img, dw, dh):
+    """cv::resize(img, (dw, dh), INTER_LINEAR) restated (oracle/orb_ref.cpp)."""
+    img = _u8(img)
+    out = np.zeros((dh, dw), np.uint8)
+    _orb().orc_resize_linear_u8(_p(img, C.c_uint8), img.shape[1], img.shape[0], img.strides[0],
+                                _p(out, C.c_uint8), dw, dh, dw)
+    return out
+
+
+def gaussian7(img):
+    """cv::GaussianBlur(img, (7, 7), 2, 2, BORDER_REFLECT_101) restated."""
+    img = _u8(img)
+    out = np.zeros_like(img)
+    _orb().orc_gaussian7_u8(_p(img, C.c_uint8), img.shape[1], img.shape[0], img.strides[0],
+                            _p(out, C.c_uint8), img.shape[1])
+    return out
+
+
+def fast9_nms(img, threshold):
+    """cv::FAST(img, kps, threshold, true) restated -> (x[n], y[n], score[n]) in OpenCV's order."""
+    img = _u8(img)
+    cap = img.size
+    x, y, s = np.zeros(cap, np.int32), np.zeros(cap, np.int32), np.zeros(cap, np.int32)
+    n = _orb().orc_fast9_nms(_p(img, C.c_uint8), img.shape[1], img.shape[0], img.strides[0], int(threshold),
+                             _p(x, C.c_int), _p(y, C.c_int), _p(s, C.c_int), cap)
+    return x[:n], y[:n], s[:n]
+
+
+def orb_level_candidates(img, ini_th=20, min_th=7):
+    """vToDistributeKeys of one pyramid level (src/ORBextractor.cpp:808-862) -> (x, y, response)."""
+    img = _u8(img)
+    cap = img.size // 4 + 1024
+    x, y, r = np.zeros(cap, np.float32), np.zeros(cap, np.float32), np.zeros(cap, np.float32)
+    n = _orb().orc_orb_level_candidates(_p(img, C.c_uint8), img.shape[1], img.shape[0], img.strides[0], ini_th,
+                                        min_th, _p(x, C.c_float), _p(y, C.c_float), _p(r, C.c_float), cap)
+    assert 0 <= n <= cap
+    return x[:n], y[:n], r[:n]
+
+
+def orb_pyramid(img, sizes):
+    """ComputePyramid (:1157-1184): level l = resize(level l-1) to sizes[l] = (w, h)."""
+    pyr = [_u8(img)]
+    for (w, h) in sizes[1:]:
+        pyr.append(resize_linear(pyr[-1], int(w), int(h)))
+    return pyr
+
+
 def fast_atan2(y, x):
     f = _match().orc_fast_atan2_export
     f.restype = C.c_float

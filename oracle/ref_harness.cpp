@@ -646,10 +646,59 @@ int waitKey(int) { LORB_OFF_PATH("cv::waitKey"); }
 Ptr<ORB> ORB::create() { LORB_OFF_PATH("cv::ORB::create"); }
 void Feature2D::detect(const Mat&, std::vector<KeyPoint>&) { LORB_OFF_PATH("cv::Feature2D::detect"); }
 void Feature2D::compute(const Mat&, std::vector<KeyPoint>&, Mat&) { LORB_OFF_PATH("cv::Feature2D::compute"); }
-void resize(const Mat&, Mat&, Size, double, double, int) { LORB_OFF_PATH("cv::resize"); }
-void copyMakeBorder(const Mat&, Mat&, int, int, int, int, int) { LORB_OFF_PATH("cv::copyMakeBorder"); }
-void GaussianBlur(const Mat&, Mat&, Size, double, double, int) { LORB_OFF_PATH("cv::GaussianBlur"); }
-void FAST(const Mat&, std::vector<KeyPoint>&, int, bool) { LORB_OFF_PATH("cv::FAST"); }
+// The four image operations of ORBextractor: the cv2-pinned restatements of oracle/orb_ref.cpp
+// (linked into this library).  Only the forms ORBextractor.cpp uses are accepted.
+}  // namespace cv
+namespace orc {
+void resize_linear_u8(const uint8_t* src, int sw, int sh, int sstep, uint8_t* dst, int dw, int dh, int dstep);
+void gaussian7_u8(const uint8_t* src, int w, int h, int sstep, uint8_t* dst, int dstep);
+int fast9_nms(const uint8_t* img, int w, int h, int step, int threshold, int* out_x, int* out_y, int* out_score,
+              int cap);
+}  // namespace orc
+namespace cv {
+void resize(const Mat& src, Mat& dst, Size dsize, double fx, double fy, int interpolation) {
+  if (src.type() != CV_8U || fx != 0 || fy != 0 || interpolation != INTER_LINEAR) LORB_OFF_PATH("cv::resize form");
+  if (dst.rows != dsize.height || dst.cols != dsize.width || dst.type() != CV_8U) dst.create(dsize.height, dsize.width, CV_8U);
+  orc::resize_linear_u8(src.ptr(0), src.cols, src.rows, (int)src.step, dst.ptr(0), dst.cols, dst.rows, (int)dst.step);
+}
+void copyMakeBorder(const Mat& src, Mat& dst, int top, int bottom, int left, int right, int borderType) {
+  if (src.type() != CV_8U || (borderType & ~BORDER_ISOLATED) != BORDER_REFLECT_101) LORB_OFF_PATH("cv::copyMakeBorder form");
+  const int h = src.rows + top + bottom, w = src.cols + left + right;
+  const Mat s = src.clone();  // src may be the centre of dst (ORBextractor.cpp:1174)
+  if (dst.rows != h || dst.cols != w || dst.type() != CV_8U) dst.create(h, w, CV_8U);
+  auto refl = [](int p, int n) {
+    if (n == 1) return 0;
+    while (p < 0 || p >= n) p = p < 0 ? -p : 2 * n - 2 - p;
+    return p;
+  };
+  for (int y = 0; y < h; y++)
+    for (int x = 0; x < w; x++) dst.ptr(y)[x] = s.ptr(refl(y - top, s.rows))[refl(x - left, s.cols)];
+}
+void GaussianBlur(const Mat& src, Mat& dst, Size ksize, double sigmaX, double sigmaY, int borderType) {
+  if (src.type() != CV_8U || ksize.width != 7 || ksize.height != 7 || sigmaX != 2 || sigmaY != 2 ||
+      borderType != BORDER_REFLECT_101)
+    LORB_OFF_PATH("cv::GaussianBlur form");
+  const Mat s = src.clone();  // in-place call (ORBextractor.cpp:1132)
+  if (dst.rows != s.rows || dst.cols != s.cols || dst.type() != CV_8U) dst.create(s.rows, s.cols, CV_8U);
+  orc::gaussian7_u8(s.ptr(0), s.cols, s.rows, (int)s.step, dst.ptr(0), (int)dst.step);
+}
+void FAST(const Mat& image, std::vector<KeyPoint>& keypoints, int threshold, bool nonmaxSuppression) {
+  if (image.type() != CV_8U || !nonmaxSuppression) LORB_OFF_PATH("cv::FAST form");
+  keypoints.clear();
+  if (image.rows < 7 || image.cols < 7) return;
+  const int cap = image.rows * image.cols;
+  std::vector<int> x(cap), y(cap), sc(cap);
+  const int n = orc::fast9_nms(image.ptr(0), image.cols, image.rows, (int)image.step, threshold, x.data(), y.data(),
+                               sc.data(), cap);
+  for (int i = 0; i < n; i++) {  // KeyPoint((float)j, (float)(i-1), 7.f, -1, (float)score)
+    KeyPoint kp;
+    kp.pt = Point2f((float)x[i], (float)y[i]);
+    kp.size = 7.f;
+    kp.angle = -1;
+    kp.response = (float)sc[i];
+    keypoints.push_back(kp);
+  }
+}
 void KeyPointsFilter::retainBest(std::vector<KeyPoint>&, int) { LORB_OFF_PATH("cv::KeyPointsFilter::retainBest"); }
 }  // namespace cv
 namespace Simple_ORB_SLAM {

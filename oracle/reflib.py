@@ -31,7 +31,7 @@ def build(force=False):
         return False
     srcs = [os.path.join(_HERE, "ref_harness.cpp"), os.path.join(_HERE, "refshim", "lorb_cvshim.hpp"),
             os.path.join(_HERE, "refshim", "lorb_ceresshim.hpp"), os.path.join(_HERE, "Makefile"),
-            os.path.join(_HERE, "ref_orb_harness.cpp")]
+            os.path.join(_HERE, "ref_orb_harness.cpp"), os.path.join(_HERE, "orb_ref.cpp")]
     if force or not os.path.exists(_LIB) or max(map(os.path.getmtime, srcs)) > os.path.getmtime(_LIB):
         subprocess.run(["make", "-C", _HERE, "ref", "REFERENCE=" + REFERENCE_ROOT], check=True,
                        capture_output=True)
@@ -251,6 +251,24 @@ def orb_describe(oi):
                            _p(oi["klevel"], C.c_int), _p(ang, C.c_float), _p(desc, C.c_uint8),
                            _p(umax, C.c_int), _p(pattern, C.c_int))
     return ang[:n], desc[:n], pattern.reshape(512, 2), umax
+
+
+def orb_extract(img, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7):
+    """The reference's whole ORBextractor::operator() (src/ORBextractor.cpp:1087-1151) on one 8-bit
+    image, run under the bump arena of ref_orb_harness.cpp (quadtree ties = creation order)."""
+    img = np.ascontiguousarray(img, np.uint8)
+    cap = nfeatures + 64
+    kx, ky = np.zeros(cap, np.float32), np.zeros(cap, np.float32)
+    ko, ka = np.zeros(cap, np.int32), np.zeros(cap, np.float32)
+    kr, ks = np.zeros(cap, np.float32), np.zeros(cap, np.float32)
+    desc, npl = np.zeros((cap, 32), np.uint8), np.zeros(nlevels, np.int32)
+    n = lib().ref_orb_extract(_p(img, C.c_uint8), img.shape[1], img.shape[0], img.strides[0], nfeatures,
+                              C.c_float(scale_factor), nlevels, ini_th, min_th, cap, _p(kx, C.c_float),
+                              _p(ky, C.c_float), _p(ko, C.c_int), _p(ka, C.c_float), _p(kr, C.c_float),
+                              _p(ks, C.c_float), _p(desc, C.c_uint8), _p(npl, C.c_int))
+    assert 0 <= n <= cap
+    return dict(n=n, x=kx[:n], y=ky[:n], octave=ko[:n], angle=ka[:n], response=kr[:n], size=ks[:n],
+                desc=desc[:n], n_per_level=npl)
 
 
 def compute_descriptor(desc):

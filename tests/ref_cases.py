@@ -166,3 +166,19 @@ ORB_DESCRIBE = [("n1000_s0", 0, 1000), ("n2000_s1", 1, 2000), ("n3000_s2", 2, 30
 
 def orb_describe_case(c):
     return synth.make_orb_inputs(c[2], c[1])
+
+
+# ---- 8(f) rank 5 (whole extractor): ORBextractor::operator(); BASELINE config 0 shapes
+ORB_EXTRACT = [
+    # name, seed, width, height, nfeatures, warped
+    ("640x480_n1000_s0", 0, 640, 480, 1000, False),
+    ("640x480_n1000_s0_warp", 0, 640, 480, 1000, True),
+    ("752x480_n2000_s1", 1, 752, 480, 2000, False),
+    ("320x240_n500_s2", 2, 320, 240, 500, False),
+    ("640x480_n300_s3", 3, 640, 480, 300, False),
+]
+
+
+def orb_extract_case(c):
+    img = synth.make_orb_image(c[1], c[2], c[3])
+    return synth.warp_orb_image(img) if c[5] else img

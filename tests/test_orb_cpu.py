@@ -47,3 +47,38 @@ def test_umax_table():
     lib = capi.load_library()
     lib.lorb_orb_umax(umax.ctypes.data_as(C.c_void_p))
     assert np.array_equal(umax, OC.golden()["orb/umax"])
+
+
+def _oracle_stages(img):
+    w, h, _, _ = capi_level_sizes(img.shape[1], img.shape[0])
+    raw = ref.orb_pyramid(img, list(zip(w, h)))
+    return dict(raw=raw, blur=[ref.gaussian7(a) for a in raw], cand=lambda lv: ref.orb_level_candidates(raw[lv]))
+
+
+def capi_level_sizes(width, height, nfeatures=1000, nlevels=8):
+    """lorb_orb_level_sizes is host arithmetic: callable without a GPU."""
+    prm = capi.OrbParams(nfeatures, 1.2, nlevels, 20, 7)
+    w, h, nf = np.zeros(nlevels, np.int32), np.zeros(nlevels, np.int32), np.zeros(nlevels, np.int32)
+    sf = np.zeros(nlevels, np.float32)
+    rc = capi.load_library().lorb_orb_level_sizes(C.byref(prm), width, height, w.ctypes.data_as(C.c_void_p),
+                                                  h.ctypes.data_as(C.c_void_p), nf.ctypes.data_as(C.c_void_p),
+                                                  sf.ctypes.data_as(C.c_void_p))
+    assert rc == 0
+    return w, h, nf, sf
+
+
+@pytest.mark.parametrize("c", RC.ORB_EXTRACT[:3], ids=[c[0] for c in RC.ORB_EXTRACT[:3]])
+def test_oracle_image_ops_match_cv2(c):
+    """cv::resize / cv::GaussianBlur / cv::FAST restatements of oracle/orb_ref.cpp == cv2 4.13."""
+    OC.check_stages_against_cv2(_oracle_stages, c)
+
+
+def test_level_plan():
+    w, h, nf, sf = capi_level_sizes(640, 480)
+    assert list(w) == [640, 533, 444, 370, 309, 257, 214, 179] and list(h) == [480, 400, 333, 278, 231, 193, 161, 134]
+    assert nf.sum() == 1000 and list(nf[:3]) == [217, 181, 151]  # mnFeaturesPerLevel of the reference run
+    assert sf[0] == 1.0 and sf[1] == np.float32(1.2) and sf[2] == np.float32(1.2) * np.float32(1.2)
+    prm = capi.OrbParams(1000, 1.2, 8, 20, 7)
+    z = np.zeros(8, np.int32)
+    p = z.ctypes.data_as(C.c_void_p)
+    assert capi.load_library().lorb_orb_level_sizes(C.byref(prm), 100, 100, p, p, None, None) != 0  # too small

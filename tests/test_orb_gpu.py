@@ -64,3 +64,80 @@ def test_device_sincosf_and_atan2_bits(ctx):
     g = OC.golden()
     _, _, t = ctx.orb_selftest(g["atan2/y"], g["atan2/x"])
     assert np.array_equal(t.view(np.uint32), g["atan2/deg"].view(np.uint32))
+
+
+def _cuda_stages(ctx):
+    def run(img):
+        st = ctx.orb_stages(img)
+        ls = st["level_start"]
+        return dict(raw=st["raw"], blur=st["blur"],
+                    cand=lambda lv: (st["cand_x"][ls[lv]:ls[lv + 1]], st["cand_y"][ls[lv]:ls[lv + 1]],
+                                     st["cand_response"][ls[lv]:ls[lv + 1]]))
+    return run
+
+
+@pytest.mark.parametrize("c", RC.ORB_EXTRACT[:3], ids=[c[0] for c in RC.ORB_EXTRACT[:3]])
+def test_cuda_image_ops_match_cv2(ctx, c):
+    OC.check_stages_against_cv2(_cuda_stages(ctx), c)
+
+
+@pytest.mark.parametrize("c", RC.ORB_EXTRACT, ids=[c[0] for c in RC.ORB_EXTRACT])
+def test_cuda_orb_extract_golden(ctx, c):
+    OC.check_extract(lambda img, nf: ctx.orb_extract(img, OC.pattern(), nfeatures=nf), c)
+
+
+@pytest.mark.parametrize("seed,w,h", [(10, 640, 480), (11, 1241, 376), (12, 200, 150), (13, 97, 113)])
+def test_cuda_stages_fresh(ctx, seed, w, h):
+    """Every level of fresh images (odd sizes, KITTI-like aspect) against the oracle restatements."""
+    img = synth.make_orb_image(seed, w, h)
+    nl = 8 if min(w, h) >= 300 else 3
+    st = ctx.orb_stages(img, nlevels=nl)
+    lw, lh, _, _ = ctx.orb_level_sizes(w, h, nlevels=nl)
+    raw = ref.orb_pyramid(img, list(zip(lw, lh)))
+    ls = st["level_start"]
+    for lv in range(nl):
+        assert np.array_equal(st["raw"][lv], raw[lv]), lv
+        assert np.array_equal(st["blur"][lv], ref.gaussian7(raw[lv])), lv
+        x, y, r = ref.orb_level_candidates(raw[lv])
+        assert np.array_equal(st["cand_x"][ls[lv]:ls[lv + 1]], x), lv
+        assert np.array_equal(st["cand_y"][ls[lv]:ls[lv + 1]], y) and np.array_equal(st["cand_response"][ls[lv]:ls[lv + 1]], r)
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_cuda_orb_extract_fresh_vs_reference(ctx, seed):
+    """Against the compiled reference itself when its library travelled with the snapshot."""
+    from oracle import reflib
+    if not reflib.available():
+        pytest.skip("oracle/_ref not built")
+    img = synth.make_orb_image(40 + seed, 640 + 16 * seed, 480)
+    for nf in (1000, 150):
+        a, b = ctx.orb_extract(img, OC.pattern(), nfeatures=nf), reflib.orb_extract(img, nfeatures=nf)
+        assert a["n"] == b["n"]
+        for f in ("x", "y", "octave", "angle", "response", "size", "desc"):
+            assert np.array_equal(a[f], b[f]), f
+
+
+def test_cuda_orb_extract_flat_image(ctx):
+    img = np.full((480, 640), 77, np.uint8)
+    r = ctx.orb_extract(img, OC.pattern())
+    assert r["n"] == 0
+    with pytest.raises(capi.LorbError):
+        ctx.orb_extract(np.zeros((40, 40), np.uint8), OC.pattern())
+
+
+def test_config0_extract_then_match(ctx):
+    """BASELINE config 0 (reference example/test.cpp): ORB features of a frame pair, brute-force
+    Hamming match with cross-check; most matches must agree with the known warp."""
+    img = synth.make_orb_image(0)
+    a = ctx.orb_extract(img, OC.pattern())
+    b = ctx.orb_extract(synth.warp_orb_image(img), OC.pattern())
+    m = ctx.match_bf_crosscheck(a["desc"], b["desc"])
+    assert m["n_kept"] > 300
+    kept = m["keep"].astype(bool)
+    q, t = m["q"][kept], m["t"][kept]
+    ang = np.deg2rad(3.0)
+    xc, yc = a["x"][q] - 320, a["y"][q] - 240
+    px = 1.02 * (np.cos(ang) * xc - np.sin(ang) * yc) + 320 + 4.0
+    py = 1.02 * (np.sin(ang) * xc + np.cos(ang) * yc) + 240 - 3.0
+    err = np.hypot(px - b["x"][t], py - b["y"][t])
+    assert np.median(err) < 3.0
