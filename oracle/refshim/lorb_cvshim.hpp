@@ -180,7 +180,23 @@ class Mat {
     buf_ = std::make_shared<std::vector<unsigned char>>((size_t)r * step + 8, 0);
     off_ = 0;
   }
-  static Mat zeros(int r, int c, int type) { return Mat(r, c, type); }
+  // Mat::zeros is a MatExpr in OpenCV: ASSIGNING it to a matrix that already has that shape zeroes
+  // the matrix in place (Mat::create keeps the buffer), it does not rebind the header --
+  // computeDescriptors (src/ORBextractor.cpp:1081) relies on that to write into a rowRange view.
+  struct ZerosExpr {
+    int r, c, type;
+    operator Mat() const { return Mat(r, c, type); }
+  };
+  static ZerosExpr zeros(int r, int c, int type) { return ZerosExpr{r, c, type}; }
+  Mat(const ZerosExpr& z) { create(z.r, z.c, z.type); }
+  Mat& operator=(const ZerosExpr& z) {
+    if (buf_ && rows == z.r && cols == z.c && type_ == z.type) {
+      for (int i = 0; i < rows; i++) std::memset(raw(i), 0, (size_t)cols * esz(type_));
+    } else {
+      create(z.r, z.c, z.type);
+    }
+    return *this;
+  }
   static Mat ones(int r, int c, int type) {
     Mat m(r, c, type);
     for (int i = 0; i < r; i++)

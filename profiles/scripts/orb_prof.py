@@ -1,0 +1,33 @@
+"""ORB extractor: e2e time of lorb_orb_extract (host image in, keypoints + descriptors out) next to
+the compiled reference on the host; also the driver for ncu launch lists of the extractor kernels."""
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, ".")
+from lorb_slam_b200 import capi, synth  # noqa: E402
+
+g = np.load("tests/golden/orb_golden.npz")
+pattern = g["orb/pattern"].astype(np.int32)
+reps = int(sys.argv[1]) if len(sys.argv) > 1 else 50
+with capi.Context(0) as ctx:
+    for (w, h, nf) in ((640, 480, 1000), (752, 480, 2000), (1241, 376, 2000)):
+        img = synth.make_orb_image(0, w, h)
+        for _ in range(5):
+            r = ctx.orb_extract(img, pattern, nfeatures=nf)
+        t = time.perf_counter()
+        for _ in range(reps):
+            r = ctx.orb_extract(img, pattern, nfeatures=nf)
+        dt = (time.perf_counter() - t) / reps
+        line = "%dx%d nfeatures %d: %d keypoints, %.3f ms per frame (%.0f frames/s)" % (w, h, nf, r["n"], dt * 1e3, 1 / dt)
+        try:
+            from oracle import reflib
+            if reflib.available() and reps > 1:
+                t = time.perf_counter()
+                for _ in range(3):
+                    reflib.orb_extract(img, nfeatures=nf)
+                line += "; compiled reference (1 core, stand-in OpenCV) %.1f ms" % ((time.perf_counter() - t) / 3 * 1e3)
+        except Exception as e:  # noqa: BLE001
+            line += "; reference unavailable (%s)" % e
+        print(line)
