@@ -297,6 +297,8 @@ int lorb_orb_describe(lorb_ctx* ctx, const lorb_pyramid_view* raw, const lorb_py
  *                nfeatures (each level stops at >= its share), nfeatures + 64 is safe
  * Outputs in the reference's order (level by level, nodes in list order): KeyPoint pt.x, pt.y,
  * octave, angle, response (may be NULL), size (may be NULL), descriptor rows; *n_out keypoints.
+ * raw_levels (may be NULL): [nlevels] host buffers of level_w*level_h bytes (lorb_orb_level_sizes)
+ * that receive ORBextractor::mvImagePyramid, which Frame::ComputeStereoMatches reads.
  */
 typedef struct lorb_orb_params {
   int nfeatures;
@@ -309,7 +311,7 @@ typedef struct lorb_orb_params {
 int lorb_orb_extract(lorb_ctx* ctx, const uint8_t* image, int width, int height, int step,
                      const lorb_orb_params* params, const int* pattern, int cap, float* kp_x,
                      float* kp_y, int* kp_octave, float* kp_angle, float* kp_response, float* kp_size,
-                     uint8_t* desc, int* n_out);
+                     uint8_t* desc, int* n_out, uint8_t* const* raw_levels);
 
 /* Level geometry of the extractor: sizes of the pyramid levels (:1161-1163), mnFeaturesPerLevel
  * (:448-461, may be NULL) and mvScaleFactor (:428-436, may be NULL). */

@@ -19,7 +19,7 @@ NVCC_FLAGS = [
     # float code of the projection search must not contract a*b+c into FMA
     # (reference builds -O0 on baseline x86-64, CMakeLists.txt:5-6); the
     # kernels that need it use __fmul_rn/__fadd_rn explicitly, this is a belt.
-    "-Xptxas", "-v",
+    "-Xptxas", "-v", "--threads", "8",
 ]
 
 

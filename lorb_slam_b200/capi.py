@@ -347,7 +347,7 @@ class Context:
         n = C.c_int(0)
         _check(self._lib.lorb_orb_extract(
             self._h, _ptr(img), img.shape[1], img.shape[0], img.strides[0], C.byref(prm), _ptr(pat), cap,
-            _ptr(kx), _ptr(ky), _ptr(ko), _ptr(ka), _ptr(kr), _ptr(ks), _ptr(desc), C.byref(n)))
+            _ptr(kx), _ptr(ky), _ptr(ko), _ptr(ka), _ptr(kr), _ptr(ks), _ptr(desc), C.byref(n), None))
         n = n.value
         return dict(n=n, x=kx[:n], y=ky[:n], octave=ko[:n], angle=ka[:n], response=kr[:n], size=ks[:n],
                     desc=desc[:n], n_per_level=np.bincount(ko[:n], minlength=nlevels).astype(np.int32))

@@ -273,7 +273,9 @@ __global__ void __launch_bounds__(256) orb_blur_kernel(OrbPlanDev P) {
 // One CTA per cell: cell image in shared memory, A by a doubling sliding minimum over the ring,
 // suppression flags, block vote for "iniThFAST found something", ordered (row-major, as cv::FAST
 // emits) compaction into the cell's slot.  Candidates are packed score<<24 | y<<12 | x with x, y
-// relative to the level's 16-px margin (what the reference hands to DistributeOctTree).
+// relative to the level's 16-px margin (what the reference hands to DistributeOctTree).  The slots
+// and the per-cell counts live in mapped pinned host memory: the quadtree runs on the host, so the
+// few thousand 4-byte candidates go straight over PCIe and no gather kernel or copy is needed.
 constexpr int CELL_MAX = 68;  // cell image side: wCell + 6 < 60 + 6
 
 __device__ __forceinline__ int arc9_min_max(const int (&d)[16]) {
@@ -386,47 +388,6 @@ __global__ void __launch_bounds__(256)
     __syncthreads();
   }
   if (threadIdx.x == 0) cell_count[blockIdx.x] = s_base;
-}
-
-// Cells in (level, row, column) order -> one dense candidate list (written straight into mapped
-// pinned host memory) and the per-level start offsets.  Single CTA: <= a few thousand cells.
-__global__ void __launch_bounds__(1024)
-    orb_compact_kernel(OrbPlanDev P, const uint32_t* __restrict__ slots, const int* __restrict__ cell_count,
-                       int* __restrict__ cell_offset, uint32_t* __restrict__ dense, int dense_cap,
-                       int* __restrict__ level_start) {
-  __shared__ int s_part[1024];
-  const int n_cells = P.cell_start[P.n_levels];
-  const int per = (n_cells + blockDim.x - 1) / blockDim.x;
-  const int lo = min((int)threadIdx.x * per, n_cells), hi = min(lo + per, n_cells);
-  int sum = 0;
-  for (int k = lo; k < hi; k++) sum += min(cell_count[k], P.slot_cap);
-  s_part[threadIdx.x] = sum;
-  __syncthreads();
-  for (int o = 1; o < (int)blockDim.x; o <<= 1) {
-    const int v = threadIdx.x >= o ? s_part[threadIdx.x - o] : 0;
-    __syncthreads();
-    s_part[threadIdx.x] += v;
-    __syncthreads();
-  }
-  int run = s_part[threadIdx.x] - sum;
-  for (int k = lo; k < hi; k++) {
-    cell_offset[k] = run;
-    run += min(cell_count[k], P.slot_cap);
-  }
-  if (threadIdx.x == blockDim.x - 1) level_start[P.n_levels] = s_part[threadIdx.x];
-  __syncthreads();
-  if (threadIdx.x < P.n_levels) level_start[threadIdx.x] = cell_offset[P.cell_start[threadIdx.x]];
-  // overflow flag: a cell that produced more than its slot holds (cannot happen for slot_cap =
-  // ceil(w/2)*ceil(h/2) of the interior, kept as a loud check)
-  if (threadIdx.x == 0) level_start[P.n_levels + 1] = 0;
-  __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
-  for (int k = warp; k < n_cells; k += n_warps) {
-    const int cnt = cell_count[k], off = cell_offset[k];
-    if (cnt > P.slot_cap && lane == 0) level_start[P.n_levels + 1] = 1;
-    for (int e = lane; e < min(cnt, P.slot_cap); e += 32)
-      if (off + e < dense_cap) dense[off + e] = slots[(size_t)k * P.slot_cap + e];
-  }
 }
 
 // ------------------------------------------------------------------ host: level plan + quadtree
@@ -797,8 +758,6 @@ int orb_run(lorb_ctx* c, const uint8_t* image, int width, int height, int step, 
   P.tile_start[nl] = n_tiles;
   P.cell_start[nl] = n_cells;
   P.slot_cap = slot_cap;
-  const size_t o_slots = dv.add((size_t)n_cells * slot_cap * 4), o_cnt = dv.add((size_t)n_cells * 4),
-               o_off = dv.add((size_t)n_cells * 4);
   LORB_TRY(dev_reserve(c, 3, dv.off));
   uint8_t* d = c->d[3].as<uint8_t>();
   for (int l = 0; l < nl; l++) {
@@ -806,11 +765,10 @@ int orb_run(lorb_ctx* c, const uint8_t* image, int width, int height, int step, 
     P.blur[l] = d + o_blur[l];
   }
 
-  // ---- host staging (pinned): image in; candidates + level starts out (written by the GPU)
-  const int dense_cap = n_cells * slot_cap;
+  // ---- host staging (pinned, device-visible): image in; candidate slots + cell counts out
   OPacker hs;
-  const size_t h_img = hs.add((size_t)width * height), h_lvl = hs.add((size_t)(nl + 2) * 4),
-               h_dense = hs.add((size_t)dense_cap * 4);
+  const size_t h_img = hs.add((size_t)width * height), h_cnt = hs.add((size_t)n_cells * 4),
+               h_slots = hs.add((size_t)n_cells * slot_cap * 4);
   LORB_TRY(pin_reserve(c, 2, hs.off));
   uint8_t* hp = c->h[2].as<uint8_t>();
   if (step == width) {
@@ -826,11 +784,9 @@ int orb_run(lorb_ctx* c, const uint8_t* image, int width, int height, int step, 
     LORB_LAUNCH(c, orb_resize_kernel, grd, blk, 0, P.raw[l - 1], L.w[l - 1], L.h[l - 1], P.raw[l], L.w[l], L.h[l], sx,
                 sy);
   }
-  int* lvl_host = (int*)(hp + h_lvl);
-  uint32_t* dense_host = (uint32_t*)(hp + h_dense);
-  LORB_LAUNCH(c, orb_fast_cells_kernel, n_cells, 256, 0, P, (uint32_t*)(d + o_slots), (int*)(d + o_cnt));
-  LORB_LAUNCH(c, orb_compact_kernel, 1, 1024, 0, P, (const uint32_t*)(d + o_slots), (const int*)(d + o_cnt),
-              (int*)(d + o_off), dense_host, dense_cap, lvl_host);
+  const int* cnt_host = (const int*)(hp + h_cnt);
+  const uint32_t* slots_host = (const uint32_t*)(hp + h_slots);
+  LORB_LAUNCH(c, orb_fast_cells_kernel, n_cells, 256, 0, P, (uint32_t*)(hp + h_slots), (int*)(hp + h_cnt));
   cudaEvent_t ev;
   LORB_CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   LORB_CUDA_TRY(cudaEventRecord(ev, c->stream));
@@ -839,18 +795,37 @@ int orb_run(lorb_ctx* c, const uint8_t* image, int width, int height, int step, 
   cudaError_t ee = cudaEventSynchronize(ev);
   cudaEventDestroy(ev);
   LORB_CUDA_TRY(ee);
-  LORB_REQUIRE(lvl_host[nl + 1] == 0 && lvl_host[nl] <= dense_cap, "candidate slot overflow (internal)");
+  for (int k = 0; k < n_cells; k++)
+    LORB_REQUIRE(cnt_host[k] >= 0 && cnt_host[k] <= slot_cap, "candidate slot overflow (internal)");
+
+  // vToDistributeKeys of level l (:813): cells in (row, column) order, row-major inside a cell
+  auto level_keys = [&](int l, std::vector<QKey>* out) {
+    size_t n = 0;
+    for (int k = P.cell_start[l]; k < P.cell_start[l + 1]; k++) n += cnt_host[k];
+    out->resize(n);
+    n = 0;
+    for (int k = P.cell_start[l]; k < P.cell_start[l + 1]; k++)
+      for (int e = 0; e < cnt_host[k]; e++) {
+        const uint32_t v = slots_host[(size_t)k * slot_cap + e];
+        (*out)[n++] = QKey{(float)(v & 0xfff), (float)((v >> 12) & 0xfff), (float)(v >> 24)};
+      }
+  };
 
   if (O.cand_level_start) {
-    const int total = lvl_host[nl];
-    LORB_REQUIRE(total <= O.cand_cap, "candidate capacity");
-    for (int l = 0; l <= nl; l++) O.cand_level_start[l] = lvl_host[l];
-    for (int i = 0; i < total; i++) {
-      const uint32_t e = dense_host[i];
-      O.cand_x[i] = (float)(e & 0xfff);
-      O.cand_y[i] = (float)((e >> 12) & 0xfff);
-      O.cand_resp[i] = (float)(e >> 24);
+    std::vector<QKey> kk;
+    int total = 0;
+    for (int l = 0; l < nl; l++) {
+      level_keys(l, &kk);
+      O.cand_level_start[l] = total;
+      LORB_REQUIRE(total + (int)kk.size() <= O.cand_cap, "candidate capacity");
+      for (const QKey& q : kk) {
+        O.cand_x[total] = q.x;
+        O.cand_y[total] = q.y;
+        O.cand_resp[total] = q.response;
+        total++;
+      }
     }
+    O.cand_level_start[nl] = total;
   }
 
   // ---- DistributeOctTree per level (:865-866), levels are independent
@@ -860,12 +835,7 @@ int orb_run(lorb_ctx* c, const uint8_t* image, int width, int height, int step, 
   if (O.n_out || want_desc) {
 #pragma omp parallel for schedule(dynamic, 1) num_threads(std::min(nl, 8))
     for (int l = 0; l < nl; l++) {
-      const int a = lvl_host[l], b = lvl_host[l + 1];
-      keys[l].resize(b - a);
-      for (int i = a; i < b; i++) {
-        const uint32_t e = dense_host[i];
-        keys[l][i - a] = QKey{(float)(e & 0xfff), (float)((e >> 12) & 0xfff), (float)(e >> 24)};
-      }
+      level_keys(l, &keys[l]);
       const int min_b = ORB_EDGE - 3;
       distribute_quadtree(keys[l], min_b, L.w[l] - ORB_EDGE + 3, min_b, L.h[l] - ORB_EDGE + 3, L.n_features[l],
                           &chosen[l]);
@@ -975,9 +945,10 @@ int lorb_orb_level_sizes(const lorb_orb_params* prm, int width, int height, int*
 int lorb_orb_extract(lorb_ctx* c, const uint8_t* image, int width, int height, int step,
                      const lorb_orb_params* prm, const int* pattern, int cap, float* kp_x, float* kp_y,
                      int* kp_octave, float* kp_angle, float* kp_response, float* kp_size, uint8_t* desc,
-                     int* n_out) {
+                     int* n_out, uint8_t* const* raw_levels) {
   LORB_REQUIRE(cap >= 0 && kp_x && kp_y && kp_octave && kp_angle && desc && n_out, "output arrays");
   ExtractOut O;
+  O.raw_levels = raw_levels;
   O.cap = cap;
   O.kx = kp_x;
   O.ky = kp_y;

@@ -11,13 +11,14 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIBDIR = os.path.join(HERE, "..", "lib")
 OUT = os.path.join(LIBDIR, "libhost_dropin.so")
 SRCS = [os.path.join(HERE, "src", "matcher.cpp"), os.path.join(HERE, "src", "bundle_adjust.cpp"),
+        os.path.join(HERE, "src", "ORBextractor.cpp"),
         os.path.join(HERE, "test", "harness.cpp")]
 
 
 def _deps():
     d = list(SRCS)
     for root, _, files in os.walk(HERE):
-        d += [os.path.join(root, f) for f in files if f.endswith((".h", ".hpp"))]
+        d += [os.path.join(root, f) for f in files if f.endswith((".h", ".hpp", ".inc"))]
     d.append(os.path.join(HERE, "..", "..", "include", "lorb_cuda.h"))
     return d
 

@@ -50,8 +50,13 @@ class Mat {
     type_ = type;
     buf_ = std::make_shared<std::vector<unsigned char>>((size_t)r * c * esz(), 0);
     off_ = 0;
+    step = (size_t)c * esz();
   }
   int type() const { return type_; }
+  // InputArray / OutputArray surface used by the drop-in ORBextractor
+  Mat getMat() const { return *this; }
+  void release() { *this = Mat(); }
+  size_t step = 0;  // bytes per row (rows are dense in this stand-in)
   bool empty() const { return rows == 0 || cols == 0 || !buf_; }
   size_t elemSize() const { return esz(); }
   template <typename T>
@@ -107,6 +112,9 @@ class Mat {
   std::shared_ptr<std::vector<unsigned char>> buf_;
   size_t off_ = 0;
 };
+
+typedef const Mat& InputArray;
+typedef Mat& OutputArray;
 
 }  // namespace cv
 #endif

@@ -6,6 +6,7 @@
 #include <cstring>
 #include <deque>
 
+#include "../include/ORBextractor.h"
 #include "../include/bundle_adjust.h"
 #include "../include/matcher.h"
 
@@ -236,4 +237,35 @@ void harness_local_ba(int C, float* cams, int P, float* pts, int O, const int* o
 	}
 }
 
+
+// ORBextractor(nfeatures, 1.2, 8, 20, 7)(image, Mat(), keypoints, descriptors) as Frame's
+// constructor calls it (reference src/frame.cpp:34-56, 132-133); returns the keypoint count.
+// out_pyr_sum[l] = byte sum of mvImagePyramid[l] (the member ComputeStereoMatches reads).
+int harness_orb_extract(const uint8_t* img, int w, int h, int nfeatures, int cap, float* kx, float* ky, int* koct,
+                        float* kangle, float* kresp, float* ksize, uint8_t* desc, long long* out_pyr_sum)
+{
+	cv::Mat image(h, w, CV_8U);
+	std::memcpy(image.ptr<uint8_t>(), img, (size_t)w*h);
+	ORBextractor ex(nfeatures, 1.2f, 8, 20, 7);
+	std::vector<cv::KeyPoint> kps;
+	cv::Mat d;
+	ex(image, cv::Mat(), kps, d);
+	const int n = (int)kps.size();
+	for(int i = 0; i < n && i < cap; i++)
+	{
+		kx[i] = kps[i].pt.x; ky[i] = kps[i].pt.y; koct[i] = kps[i].octave; kangle[i] = kps[i].angle;
+		kresp[i] = kps[i].response; ksize[i] = kps[i].size;
+		std::memcpy(desc + 32*(size_t)i, d.ptr<uint8_t>(i), 32);
+	}
+	for(int l = 0; l < ex.GetLevels(); l++)
+	{
+		long long s = 0;
+		const cv::Mat& m = ex.mvImagePyramid[l];
+		for(int r = 0; r < m.rows; r++)
+			for(int c = 0; c < m.cols; c++) s += m.ptr<uint8_t>(r)[c];
+		out_pyr_sum[l] = s;
+	}
+	return n;
 }
+
+}  // extern "C"

@@ -98,3 +98,37 @@ def test_local_pose_optimization(H):
     assert s["final_cost"] < s["initial_cost"]
     np.testing.assert_allclose(cams, oc.astype(np.float32), rtol=3e-6, atol=1e-6)
     np.testing.assert_allclose(pts, op.astype(np.float32), rtol=3e-6, atol=1e-6)
+
+
+def test_orbextractor_class_matches_reference():
+    """The drop-in ORBextractor class (host/include/ORBextractor.h) called as Frame's constructor
+    calls it, against the compiled reference's extractor output (tests/golden/orb_golden.npz)."""
+    import orb_checks as OC
+    import ref_cases as RC
+    Hl = C.CDLL(build_host.build())
+    for c in (RC.ORB_EXTRACT[0], RC.ORB_EXTRACT[3]):
+        img = RC.orb_extract_case(c)
+        cap = c[4] + 64
+        kx, ky, ka, kr, ks = (np.zeros(cap, np.float32) for _ in range(5))
+        ko, desc, pyr = np.zeros(cap, np.int32), np.zeros((cap, 32), np.uint8), np.zeros(8, np.int64)
+        n = Hl.harness_orb_extract(_p(img), img.shape[1], img.shape[0], c[4], cap, _p(kx), _p(ky), _p(ko), _p(ka),
+                                   _p(kr), _p(ks), _p(desc), _p(pyr))
+
+        def as_result(_img, _nf):
+            return dict(n=n, x=kx[:n], y=ky[:n], octave=ko[:n], angle=ka[:n], response=kr[:n], size=ks[:n],
+                        desc=desc[:n])
+        OC.check_extract(as_result, c)
+        raw = ref.orb_pyramid(img, [(a.shape[1], a.shape[0]) for a in _ref_level_shapes(img)])
+        assert [int(a.astype(np.int64).sum()) for a in raw] == list(pyr)
+
+
+def _ref_level_shapes(img):
+    """Level shapes by the reference's rule (src/ORBextractor.cpp:1161-1163) in float32."""
+    out, sf = [], np.float32(1.0)
+    for l in range(8):
+        if l:
+            sf = np.float32(sf * np.float32(1.2))
+        isf = np.float32(1.0) / sf
+        out.append(np.zeros((int(np.rint(np.float32(img.shape[0]) * isf)), int(np.rint(np.float32(img.shape[1]) * isf))),
+                            np.uint8))
+    return out
