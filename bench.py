@@ -369,6 +369,27 @@ def extras(ctx, local):
         ctx.stereo_matches(st)
     dt = (time.perf_counter() - t0) / reps
     out["stereo_matches_1000kp_640x480_e2e"] = {"us_per_call": dt * 1e6, "n_matched": r["n_matched"]}
+    # cfg 0 / next row rank 5: ORBextractor::operator(), 1000 features on a 640x480 frame, then the
+    # brute-force match of the frame pair (reference example/test.cpp)
+    pat_path = os.path.join(ROOT, "tests", "golden", "orb_golden.npz")
+    if os.path.exists(pat_path):
+        pattern = np.load(pat_path)["orb/pattern"].astype(np.int32)
+        img = synth.make_orb_image(0)
+        img2 = synth.warp_orb_image(img)
+        a = ctx.orb_extract(img, pattern)
+        reps = 100
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            ctx.orb_extract(img, pattern)
+        dt = (time.perf_counter() - t0) / reps
+        b = ctx.orb_extract(img2, pattern)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            m = ctx.match_bf_crosscheck(a["desc"], b["desc"])
+        dtm = (time.perf_counter() - t0) / reps
+        out["orb_extract_1000f_640x480_e2e"] = {
+            "us_per_frame": dt * 1e6, "frames_per_s": 1 / dt, "keypoints": int(a["n"]),
+            "pair_match_us": dtm * 1e6, "pair_matches_kept": int(m["n_kept"])}
     # cfg 3: local BA, 10 LM iterations
     pb = synth.make_ba_problem(0, C=10, P=5000)
     opt = _ba_opts_fixed_iters(capi)

@@ -16,6 +16,10 @@ cur, last = synth.make_frame_pair(600, 1); c.search_proj_frame(cur, last, 15.0)
 c.frustum_project(synth.make_frustum_points(1000, 1))
 c.stereo_matches(synth.make_stereo_pair(300, 1))
 offs = np.array([0, 3, 3, 10, 30], np.int32); c.compute_descriptors(offs, synth.descriptors_uniform(30, rng))
+pattern = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "..", "tests", "golden", "orb_golden.npz"))["orb/pattern"].astype(np.int32)
+c.orb_describe(synth.make_orb_inputs(300, 1), pattern)
+img = synth.make_orb_image(1, 413, 307); c.orb_extract(img, pattern, nfeatures=300); c.orb_stages(img)
+c.orb_selftest(np.linspace(0, 6.3, 1000), np.linspace(-5, 5, 1000))
 c.profile(True)
 po = synth.make_pose_only(1, 200); c.ba_pose_only(po["xw"], po["uv"], po["K"], po["rt"])
 opt = capi.ba_options(max_num_iterations=4)
