@@ -403,9 +403,12 @@ def extras(ctx, local):
         s = prob.solve(opt)
         best = min(best, time.perf_counter() - t0)
     prob.close()
-    t0 = time.perf_counter()
-    ctx.ba_local(pb, opt)
-    e2e = time.perf_counter() - t0
+    ctx.ba_local(pb, opt)  # first call sizes the context's cached problem and staging
+    e2e = 1e9
+    for _ in range(3):
+        t0 = time.perf_counter()
+        ctx.ba_local(pb, opt)
+        e2e = min(e2e, time.perf_counter() - t0)
     out["ba_local_10kf_5kpts_30kobs"] = {
         "ms_per_local_ba_resident": best * 1e3, "ms_per_local_ba_e2e": e2e * 1e3,
         "lm_iterations": s["iterations"],

@@ -713,216 +713,319 @@ struct ExtractOut {
   int* level_h = nullptr;
 };
 
-int orb_run(lorb_ctx* c, const uint8_t* image, int width, int height, int step, const lorb_orb_params* prm,
-            const int* pattern, const ExtractOut& O) {
-  LORB_REQUIRE(c && image && prm, "ctx / image / params");
-  LORB_REQUIRE(width > 0 && height > 0 && step >= width, "image shape");
-  OrbLevelPlan L;
-  LORB_TRY(make_level_plan(prm, width, height, &L));
-  const int nl = L.n_levels;
-  const bool want_desc = O.desc != nullptr;
-  if (want_desc) {
-    LORB_REQUIRE(pattern, "pattern");
-    for (int k = 0; k < 512; k++)
-      LORB_REQUIRE(pattern[2 * k] * pattern[2 * k] + pattern[2 * k + 1] * pattern[2 * k + 1] < ORB_EDGE * ORB_EDGE,
-                   "pattern radius");
-  }
-  LORB_CUDA_TRY(cudaSetDevice(c->device));
-
-  // ---- device layout: raw + blurred levels, cell slots, counts
-  OPacker dv;
+// One image going through the extractor.  Two jobs (left, right) share the stream and interleave
+// so that the GPU works on one image while the host distributes the keypoints of the other.
+struct OrbJob {
+  const uint8_t* image = nullptr;
+  int step = 0;
+  ExtractOut O;
+  // layout (offsets into the shared buffers, fixed by layout())
+  size_t dev_base = 0, stage_base = 0, kin_base = 0, kout_base = 0;
   size_t o_raw[ORB_MAX_LEVELS], o_blur[ORB_MAX_LEVELS];
-  for (int l = 0; l < nl; l++) o_raw[l] = dv.add((size_t)L.w[l] * L.h[l]);
-  for (int l = 0; l < nl; l++) o_blur[l] = dv.add((size_t)L.w[l] * L.h[l]);
+  size_t h_img = 0, h_cnt = 0, h_slots = 0;
+  size_t i_kx = 0, i_ky = 0, i_kl = 0, i_sx = 0, i_sy = 0, i_tab = 0, kin_bytes = 0;
+  size_t o_ang = 0, o_desc = 0, kout_bytes = 0;
   OrbPlanDev P;
-  memset(&P, 0, sizeof(P));
-  P.n_levels = nl;
-  P.ini_th = prm->ini_th_fast;
-  P.min_th = prm->min_th_fast;
-  int n_cells = 0, n_tiles = 0, slot_cap = 0;
-  for (int l = 0; l < nl; l++) {
-    P.w[l] = L.w[l];
-    P.h[l] = L.h[l];
-    P.tile_start[l] = n_tiles;
-    P.tiles_x[l] = (L.w[l] + BLUR_TX - 1) / BLUR_TX;
-    n_tiles += P.tiles_x[l] * ((L.h[l] + BLUR_TY - 1) / BLUR_TY);
-    P.cell_start[l] = n_cells;
-    P.n_cols[l] = L.n_cols[l];
-    P.w_cell[l] = L.w_cell[l];
-    P.h_cell[l] = L.h_cell[l];
-    n_cells += L.n_cols[l] * L.n_rows[l];
-    LORB_REQUIRE(L.w_cell[l] + 6 <= CELL_MAX && L.h_cell[l] + 6 <= CELL_MAX, "cell size");
-    // suppression leaves no two adjacent survivors: at most ceil(w/2)*ceil(h/2) per interior
-    slot_cap = std::max(slot_cap, ((L.w_cell[l] + 1) / 2) * ((L.h_cell[l] + 1) / 2));
-  }
-  P.tile_start[nl] = n_tiles;
-  P.cell_start[nl] = n_cells;
-  P.slot_cap = slot_cap;
-  LORB_TRY(dev_reserve(c, 3, dv.off));
-  uint8_t* d = c->d[3].as<uint8_t>();
-  for (int l = 0; l < nl; l++) {
-    P.raw[l] = d + o_raw[l];
-    P.blur[l] = d + o_blur[l];
+  cudaEvent_t ev = nullptr;
+  std::vector<std::vector<int>> chosen;
+  std::vector<std::vector<QKey>> keys;
+  int n_total = 0;
+  // device views of the selected keypoints (valid after describe())
+  const float *d_sx = nullptr, *d_sy = nullptr;  // level-0 coordinates (KeyPoint::pt)
+  const int* d_lvl = nullptr;
+  const uint32_t* d_desc = nullptr;
+};
+
+struct OrbPipeline {
+  lorb_ctx* c;
+  OrbLevelPlan L;
+  int nl = 0, width = 0, height = 0, n_cells = 0, n_tiles = 0, slot_cap = 0, key_cap = 0;
+  bool want_desc = false;
+  const int* pattern = nullptr;
+  size_t dev_bytes = 0, stage_bytes = 0, kin_cap_bytes = 0, kout_cap_bytes = 0;
+
+  int plan(lorb_ctx* ctx, int w, int h, const lorb_orb_params* prm, const int* pat, bool desc, int cap) {
+    c = ctx;
+    width = w;
+    height = h;
+    pattern = pat;
+    want_desc = desc;
+    LORB_TRY(make_level_plan(prm, w, h, &L));
+    nl = L.n_levels;
+    if (want_desc) {
+      LORB_REQUIRE(pattern, "pattern");
+      for (int k = 0; k < 512; k++)
+        LORB_REQUIRE(pattern[2 * k] * pattern[2 * k] + pattern[2 * k + 1] * pattern[2 * k + 1] < ORB_EDGE * ORB_EDGE,
+                     "pattern radius");
+    }
+    n_cells = n_tiles = slot_cap = 0;
+    for (int l = 0; l < nl; l++) {
+      n_tiles += ((L.w[l] + BLUR_TX - 1) / BLUR_TX) * ((L.h[l] + BLUR_TY - 1) / BLUR_TY);
+      n_cells += L.n_cols[l] * L.n_rows[l];
+      LORB_REQUIRE(L.w_cell[l] + 6 <= CELL_MAX && L.h_cell[l] + 6 <= CELL_MAX, "cell size");
+      // suppression leaves no two adjacent survivors: at most ceil(w/2)*ceil(h/2) per interior
+      slot_cap = std::max(slot_cap, ((L.w_cell[l] + 1) / 2) * ((L.h_cell[l] + 1) / 2));
+    }
+    // the quadtree of a level stops at >= its share and one split adds at most 3 nodes
+    key_cap = std::max(cap, prm->nfeatures + 4 * nl);
+    return LORB_OK;
   }
 
-  // ---- host staging (pinned, device-visible): image in; candidate slots + cell counts out
-  OPacker hs;
-  const size_t h_img = hs.add((size_t)width * height), h_cnt = hs.add((size_t)n_cells * 4),
-               h_slots = hs.add((size_t)n_cells * slot_cap * 4);
-  LORB_TRY(pin_reserve(c, 2, hs.off));
-  uint8_t* hp = c->h[2].as<uint8_t>();
-  if (step == width) {
-    memcpy(hp + h_img, image, (size_t)width * height);
-  } else {
-    for (int r = 0; r < height; r++) memcpy(hp + h_img + (size_t)r * width, image + (size_t)r * step, width);
+  // Offsets of job j inside the shared device / pinned buffers.
+  void layout(OrbJob* J, int j) {
+    OPacker dv;
+    for (int l = 0; l < nl; l++) J->o_raw[l] = dv.add((size_t)L.w[l] * L.h[l]);
+    for (int l = 0; l < nl; l++) J->o_blur[l] = dv.add((size_t)L.w[l] * L.h[l]);
+    dev_bytes = dv.off;
+    J->dev_base = (size_t)j * dev_bytes;
+    OPacker hs;
+    J->h_img = hs.add((size_t)width * height);
+    J->h_cnt = hs.add((size_t)n_cells * 4);
+    J->h_slots = hs.add((size_t)n_cells * slot_cap * 4);
+    stage_bytes = hs.off;
+    J->stage_base = (size_t)j * stage_bytes;
+    OPacker in, out;
+    J->i_kx = in.add((size_t)key_cap * 4);
+    J->i_ky = in.add((size_t)key_cap * 4);
+    J->i_kl = in.add((size_t)key_cap * 4);
+    J->i_sx = in.add((size_t)key_cap * 4);
+    J->i_sy = in.add((size_t)key_cap * 4);
+    J->i_tab = in.add(sizeof(OrbTables));
+    kin_cap_bytes = in.off;
+    J->kin_base = (size_t)j * kin_cap_bytes;
+    J->o_ang = out.add((size_t)key_cap * 4);
+    J->o_desc = out.add((size_t)key_cap * 32);
+    kout_cap_bytes = out.off;
+    J->kout_base = (size_t)j * kout_cap_bytes;
   }
-  LORB_CUDA_TRY(cudaMemcpyAsync(P.raw[0], hp + h_img, (size_t)width * height, cudaMemcpyHostToDevice, c->stream));
-  for (int l = 1; l < nl; l++) {
-    // scale = 1 / (dsize / ssize) in double, as cv::resize derives it from the two sizes
-    const double sx = 1. / ((double)L.w[l] / L.w[l - 1]), sy = 1. / ((double)L.h[l] / L.h[l - 1]);
-    const dim3 blk(32, 8), grd((L.w[l] + 31) / 32, (L.h[l] + 7) / 8);
-    LORB_LAUNCH(c, orb_resize_kernel, grd, blk, 0, P.raw[l - 1], L.w[l - 1], L.h[l - 1], P.raw[l], L.w[l], L.h[l], sx,
-                sy);
+
+  int reserve(int n_jobs) {
+    LORB_TRY(dev_reserve(c, 3, dev_bytes * n_jobs));
+    LORB_TRY(pin_reserve(c, 2, stage_bytes * n_jobs));
+    LORB_TRY(pin_reserve(c, 0, kin_cap_bytes * n_jobs));
+    LORB_TRY(pin_reserve(c, 1, kout_cap_bytes * n_jobs));
+    LORB_TRY(dev_reserve(c, 0, kin_cap_bytes * n_jobs));
+    LORB_TRY(dev_reserve(c, 2, kout_cap_bytes * n_jobs));
+    return LORB_OK;
   }
-  const int* cnt_host = (const int*)(hp + h_cnt);
-  const uint32_t* slots_host = (const uint32_t*)(hp + h_slots);
-  LORB_LAUNCH(c, orb_fast_cells_kernel, n_cells, 256, 0, P, (uint32_t*)(hp + h_slots), (int*)(hp + h_cnt));
-  cudaEvent_t ev;
-  LORB_CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-  LORB_CUDA_TRY(cudaEventRecord(ev, c->stream));
-  // the blur of all levels runs while the host distributes the keypoints
-  if (want_desc || O.blur_levels) LORB_LAUNCH(c, orb_blur_kernel, n_tiles, 256, 0, P);
-  cudaError_t ee = cudaEventSynchronize(ev);
-  cudaEventDestroy(ev);
-  LORB_CUDA_TRY(ee);
-  for (int k = 0; k < n_cells; k++)
-    LORB_REQUIRE(cnt_host[k] >= 0 && cnt_host[k] <= slot_cap, "candidate slot overflow (internal)");
+
+  // H2D of the frame, pyramid chain, FAST per cell (candidates land in pinned memory), event,
+  // then the blur (it overlaps the host's quadtree).
+  int detect(OrbJob* J) {
+    OrbPlanDev& P = J->P;
+    memset(&P, 0, sizeof(P));
+    P.n_levels = nl;
+    int cells = 0, tiles = 0;
+    uint8_t* d = c->d[3].as<uint8_t>() + J->dev_base;
+    for (int l = 0; l < nl; l++) {
+      P.w[l] = L.w[l];
+      P.h[l] = L.h[l];
+      P.raw[l] = d + J->o_raw[l];
+      P.blur[l] = d + J->o_blur[l];
+      P.tile_start[l] = tiles;
+      P.tiles_x[l] = (L.w[l] + BLUR_TX - 1) / BLUR_TX;
+      tiles += P.tiles_x[l] * ((L.h[l] + BLUR_TY - 1) / BLUR_TY);
+      P.cell_start[l] = cells;
+      P.n_cols[l] = L.n_cols[l];
+      P.w_cell[l] = L.w_cell[l];
+      P.h_cell[l] = L.h_cell[l];
+      cells += L.n_cols[l] * L.n_rows[l];
+    }
+    P.tile_start[nl] = tiles;
+    P.cell_start[nl] = cells;
+    P.slot_cap = slot_cap;
+    uint8_t* hp = c->h[2].as<uint8_t>() + J->stage_base;
+    if (J->step == width) {
+      memcpy(hp + J->h_img, J->image, (size_t)width * height);
+    } else {
+      for (int r = 0; r < height; r++) memcpy(hp + J->h_img + (size_t)r * width, J->image + (size_t)r * J->step, width);
+    }
+    LORB_CUDA_TRY(cudaMemcpyAsync(P.raw[0], hp + J->h_img, (size_t)width * height, cudaMemcpyHostToDevice, c->stream));
+    for (int l = 1; l < nl; l++) {
+      // scale = 1 / (dsize / ssize) in double, as cv::resize derives it from the two sizes
+      const double sx = 1. / ((double)L.w[l] / L.w[l - 1]), sy = 1. / ((double)L.h[l] / L.h[l - 1]);
+      const dim3 blk(32, 8), grd((L.w[l] + 31) / 32, (L.h[l] + 7) / 8);
+      LORB_LAUNCH(c, orb_resize_kernel, grd, blk, 0, P.raw[l - 1], L.w[l - 1], L.h[l - 1], P.raw[l], L.w[l], L.h[l],
+                  sx, sy);
+    }
+    LORB_LAUNCH(c, orb_fast_cells_kernel, n_cells, 256, 0, P, (uint32_t*)(hp + J->h_slots), (int*)(hp + J->h_cnt));
+    LORB_CUDA_TRY(cudaEventCreateWithFlags(&J->ev, cudaEventDisableTiming));
+    LORB_CUDA_TRY(cudaEventRecord(J->ev, c->stream));
+    if (want_desc || J->O.blur_levels) LORB_LAUNCH(c, orb_blur_kernel, n_tiles, 256, 0, P);
+    return LORB_OK;
+  }
 
   // vToDistributeKeys of level l (:813): cells in (row, column) order, row-major inside a cell
-  auto level_keys = [&](int l, std::vector<QKey>* out) {
+  void level_keys(const OrbJob* J, int l, std::vector<QKey>* out) const {
+    const uint8_t* hp = c->h[2].as<uint8_t>() + J->stage_base;
+    const int* cnt = (const int*)(hp + J->h_cnt);
+    const uint32_t* slots = (const uint32_t*)(hp + J->h_slots);
     size_t n = 0;
-    for (int k = P.cell_start[l]; k < P.cell_start[l + 1]; k++) n += cnt_host[k];
+    for (int k = J->P.cell_start[l]; k < J->P.cell_start[l + 1]; k++) n += cnt[k];
     out->resize(n);
     n = 0;
-    for (int k = P.cell_start[l]; k < P.cell_start[l + 1]; k++)
-      for (int e = 0; e < cnt_host[k]; e++) {
-        const uint32_t v = slots_host[(size_t)k * slot_cap + e];
+    for (int k = J->P.cell_start[l]; k < J->P.cell_start[l + 1]; k++)
+      for (int e = 0; e < cnt[k]; e++) {
+        const uint32_t v = slots[(size_t)k * slot_cap + e];
         (*out)[n++] = QKey{(float)(v & 0xfff), (float)((v >> 12) & 0xfff), (float)(v >> 24)};
       }
-  };
+  }
 
-  if (O.cand_level_start) {
-    std::vector<QKey> kk;
-    int total = 0;
-    for (int l = 0; l < nl; l++) {
-      level_keys(l, &kk);
-      O.cand_level_start[l] = total;
-      LORB_REQUIRE(total + (int)kk.size() <= O.cand_cap, "candidate capacity");
-      for (const QKey& q : kk) {
-        O.cand_x[total] = q.x;
-        O.cand_y[total] = q.y;
-        O.cand_resp[total] = q.response;
-        total++;
+  // Wait for the candidates of this job, run DistributeOctTree per level (:865-866).
+  int select(OrbJob* J) {
+    cudaError_t ee = cudaEventSynchronize(J->ev);
+    cudaEventDestroy(J->ev);
+    J->ev = nullptr;
+    LORB_CUDA_TRY(ee);
+    const int* cnt = (const int*)(c->h[2].as<uint8_t>() + J->stage_base + J->h_cnt);
+    for (int k = 0; k < n_cells; k++)
+      LORB_REQUIRE(cnt[k] >= 0 && cnt[k] <= slot_cap, "candidate slot overflow (internal)");
+    const ExtractOut& O = J->O;
+    if (O.cand_level_start) {
+      std::vector<QKey> kk;
+      int total = 0;
+      for (int l = 0; l < nl; l++) {
+        level_keys(J, l, &kk);
+        O.cand_level_start[l] = total;
+        LORB_REQUIRE(total + (int)kk.size() <= O.cand_cap, "candidate capacity");
+        for (const QKey& q : kk) {
+          O.cand_x[total] = q.x;
+          O.cand_y[total] = q.y;
+          O.cand_resp[total] = q.response;
+          total++;
+        }
       }
+      O.cand_level_start[nl] = total;
     }
-    O.cand_level_start[nl] = total;
-  }
-
-  // ---- DistributeOctTree per level (:865-866), levels are independent
-  std::vector<std::vector<int>> chosen(nl);
-  std::vector<std::vector<QKey>> keys(nl);
-  int n_total = 0;
-  if (O.n_out || want_desc) {
+    J->chosen.assign(nl, std::vector<int>());
+    J->keys.assign(nl, std::vector<QKey>());
+    J->n_total = 0;
+    if (O.n_out || want_desc) {
 #pragma omp parallel for schedule(dynamic, 1) num_threads(std::min(nl, 8))
-    for (int l = 0; l < nl; l++) {
-      level_keys(l, &keys[l]);
-      const int min_b = ORB_EDGE - 3;
-      distribute_quadtree(keys[l], min_b, L.w[l] - ORB_EDGE + 3, min_b, L.h[l] - ORB_EDGE + 3, L.n_features[l],
-                          &chosen[l]);
+      for (int l = 0; l < nl; l++) {
+        level_keys(J, l, &J->keys[l]);
+        const int min_b = ORB_EDGE - 3;
+        distribute_quadtree(J->keys[l], min_b, L.w[l] - ORB_EDGE + 3, min_b, L.h[l] - ORB_EDGE + 3, L.n_features[l],
+                            &J->chosen[l]);
+      }
+      for (int l = 0; l < nl; l++) J->n_total += (int)J->chosen[l].size();
+      if (O.n_out) *O.n_out = J->n_total;
+      LORB_REQUIRE(J->n_total <= O.cap && J->n_total <= key_cap,
+                   "keypoint capacity (nfeatures + a few: the quadtree stops at >= N per level)");
     }
-    for (int l = 0; l < nl; l++) n_total += (int)chosen[l].size();
-    if (O.n_out) *O.n_out = n_total;
-    LORB_REQUIRE(n_total <= O.cap, "keypoint capacity (nfeatures + a few: the quadtree stops at >= N per level)");
+    return LORB_OK;
   }
 
-  // ---- orientation + descriptors of the chosen keypoints (level coordinates)
-  if (n_total > 0 && (want_desc || O.kangle)) {
-    OPacker in, out;
-    const size_t i_kx = in.add((size_t)n_total * 4), i_ky = in.add((size_t)n_total * 4),
-                 i_kl = in.add((size_t)n_total * 4), i_tab = in.add(sizeof(OrbTables));
-    const size_t o_ang = out.add((size_t)n_total * 4), o_desc = out.add((size_t)n_total * 32);
-    LORB_TRY(pin_reserve(c, 0, in.off));
-    LORB_TRY(pin_reserve(c, 1, out.off));
-    LORB_TRY(dev_reserve(c, 0, in.off));
-    LORB_TRY(dev_reserve(c, 2, out.off));
-    uint8_t* h = c->h[0].as<uint8_t>();
-    float *hx = (float*)(h + i_kx), *hy = (float*)(h + i_ky);
-    int* hl = (int*)(h + i_kl);
+  // Orientation + descriptors of the chosen keypoints; D2H of the results is queued, not awaited.
+  int describe(OrbJob* J) {
+    if (J->n_total == 0 || !(want_desc || J->O.kangle)) return LORB_OK;
+    uint8_t* h = c->h[0].as<uint8_t>() + J->kin_base;
+    float *hx = (float*)(h + J->i_kx), *hy = (float*)(h + J->i_ky);
+    float *sx = (float*)(h + J->i_sx), *sy = (float*)(h + J->i_sy);
+    int* hl = (int*)(h + J->i_kl);
     int k = 0;
-    for (int l = 0; l < nl; l++)
-      for (int id : chosen[l]) {
-        hx[k] = keys[l][id].x + (float)(ORB_EDGE - 3);  // pt += minBorder (:873-874)
-        hy[k] = keys[l][id].y + (float)(ORB_EDGE - 3);
+    for (int l = 0; l < nl; l++) {
+      const float scale = L.scale[l];
+      for (int id : J->chosen[l]) {
+        hx[k] = J->keys[l][id].x + (float)(ORB_EDGE - 3);  // pt += minBorder (:873-874)
+        hy[k] = J->keys[l][id].y + (float)(ORB_EDGE - 3);
+        sx[k] = l ? hx[k] * scale : hx[k];  // keypoint->pt *= scale (:1142-1147)
+        sy[k] = l ? hy[k] * scale : hy[k];
         hl[k] = l;
         k++;
       }
-    OrbTables* t = (OrbTables*)(h + i_tab);
+    }
+    OrbTables* t = (OrbTables*)(h + J->i_tab);
     memset(t, 0, sizeof(OrbTables));
     if (pattern)
       for (int q = 0; q < 512; q++)
         t->pattern[q] = make_char2((signed char)pattern[2 * q], (signed char)pattern[2 * q + 1]);
     make_umax(t->umax);
-    uint8_t* din = c->d[0].as<uint8_t>();
-    uint8_t* dout = c->d[2].as<uint8_t>();
-    LORB_CUDA_TRY(cudaMemcpyAsync(din, h, in.off, cudaMemcpyHostToDevice, c->stream));
+    uint8_t* din = c->d[0].as<uint8_t>() + J->kin_base;
+    uint8_t* dout = c->d[2].as<uint8_t>() + J->kout_base;
+    LORB_CUDA_TRY(cudaMemcpyAsync(din, h, kin_cap_bytes, cudaMemcpyHostToDevice, c->stream));
     OrbLevelsDev LV;
     for (int l = 0; l < nl; l++) {
-      LV.raw[l] = P.raw[l];
-      LV.blur[l] = P.blur[l];
+      LV.raw[l] = J->P.raw[l];
+      LV.blur[l] = J->P.blur[l];
       LV.w[l] = L.w[l];
       LV.h[l] = L.h[l];
     }
     const int warps_per_cta = 8;
-    LORB_LAUNCH(c, orb_describe_kernel, (n_total + warps_per_cta - 1) / warps_per_cta, warps_per_cta * 32, 0, LV,
-                n_total, (const float*)(din + i_kx), (const float*)(din + i_ky), (const int*)(din + i_kl),
-                (const OrbTables*)(din + i_tab), (float*)(dout + o_ang), (uint32_t*)(dout + o_desc), 0);
-    uint8_t* ho = c->h[1].as<uint8_t>();
-    LORB_CUDA_TRY(cudaMemcpyAsync(ho, dout, out.off, cudaMemcpyDeviceToHost, c->stream));
-    if (O.raw_levels || O.blur_levels)
-      for (int l = 0; l < nl; l++) {
-        if (O.raw_levels) LORB_CUDA_TRY(cudaMemcpyAsync(O.raw_levels[l], P.raw[l], (size_t)L.w[l] * L.h[l], cudaMemcpyDeviceToHost, c->stream));
-        if (O.blur_levels) LORB_CUDA_TRY(cudaMemcpyAsync(O.blur_levels[l], P.blur[l], (size_t)L.w[l] * L.h[l], cudaMemcpyDeviceToHost, c->stream));
-      }
-    LORB_CUDA_TRY(cudaStreamSynchronize(c->stream));
-    k = 0;
-    for (int l = 0; l < nl; l++) {
-      const float scale = L.scale[l];
-      const float patch = (float)(int)(31 * scale);  // scaledPatchSize = PATCH_SIZE*mvScaleFactor (:868)
-      for (int id : chosen[l]) {
-        float x = hx[k], y = hy[k];
-        if (l != 0) x = x * scale, y = y * scale;  // keypoint->pt *= scale (:1142-1147)
-        if (O.kx) O.kx[k] = x;
-        if (O.ky) O.ky[k] = y;
-        if (O.koct) O.koct[k] = l;
-        if (O.kangle) O.kangle[k] = ((const float*)(ho + o_ang))[k];
-        if (O.kresp) O.kresp[k] = keys[l][id].response;
-        if (O.ksize) O.ksize[k] = patch;
-        k++;
-      }
-    }
-    if (want_desc) memcpy(O.desc, ho + o_desc, (size_t)n_total * 32);
-  } else {
-    if (O.raw_levels || O.blur_levels)
-      for (int l = 0; l < nl; l++) {
-        if (O.raw_levels) LORB_CUDA_TRY(cudaMemcpyAsync(O.raw_levels[l], P.raw[l], (size_t)L.w[l] * L.h[l], cudaMemcpyDeviceToHost, c->stream));
-        if (O.blur_levels) LORB_CUDA_TRY(cudaMemcpyAsync(O.blur_levels[l], P.blur[l], (size_t)L.w[l] * L.h[l], cudaMemcpyDeviceToHost, c->stream));
-      }
-    LORB_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    LORB_LAUNCH(c, orb_describe_kernel, (J->n_total + warps_per_cta - 1) / warps_per_cta, warps_per_cta * 32, 0, LV,
+                J->n_total, (const float*)(din + J->i_kx), (const float*)(din + J->i_ky), (const int*)(din + J->i_kl),
+                (const OrbTables*)(din + J->i_tab), (float*)(dout + J->o_ang), (uint32_t*)(dout + J->o_desc), 0);
+    J->d_sx = (const float*)(din + J->i_sx);
+    J->d_sy = (const float*)(din + J->i_sy);
+    J->d_lvl = (const int*)(din + J->i_kl);
+    J->d_desc = (const uint32_t*)(dout + J->o_desc);
+    uint8_t* ho = c->h[1].as<uint8_t>() + J->kout_base;
+    LORB_CUDA_TRY(cudaMemcpyAsync(ho, dout, kout_cap_bytes, cudaMemcpyDeviceToHost, c->stream));
+    return LORB_OK;
   }
-  if (O.n_per_level)
-    for (int l = 0; l < nl; l++) O.n_per_level[l] = (int)chosen[l].size();
-  if (O.level_w)
-    for (int l = 0; l < nl; l++) O.level_w[l] = L.w[l], O.level_h[l] = L.h[l];
+
+  int queue_level_copies(OrbJob* J) {
+    const ExtractOut& O = J->O;
+    if (O.raw_levels || O.blur_levels)
+      for (int l = 0; l < nl; l++) {
+        if (O.raw_levels)
+          LORB_CUDA_TRY(cudaMemcpyAsync(O.raw_levels[l], J->P.raw[l], (size_t)L.w[l] * L.h[l], cudaMemcpyDeviceToHost,
+                                        c->stream));
+        if (O.blur_levels)
+          LORB_CUDA_TRY(cudaMemcpyAsync(O.blur_levels[l], J->P.blur[l], (size_t)L.w[l] * L.h[l],
+                                        cudaMemcpyDeviceToHost, c->stream));
+      }
+    return LORB_OK;
+  }
+
+  // After the stream has been synchronised: scatter the results into the caller's arrays.
+  void finish(OrbJob* J) {
+    const ExtractOut& O = J->O;
+    if (J->n_total > 0 && (want_desc || O.kangle)) {
+      const uint8_t* h = c->h[0].as<uint8_t>() + J->kin_base;
+      const float *sx = (const float*)(h + J->i_sx), *sy = (const float*)(h + J->i_sy);
+      const uint8_t* ho = c->h[1].as<uint8_t>() + J->kout_base;
+      int k = 0;
+      for (int l = 0; l < nl; l++) {
+        const float patch = (float)(int)(31 * L.scale[l]);  // scaledPatchSize = PATCH_SIZE*mvScaleFactor (:868)
+        for (int id : J->chosen[l]) {
+          if (O.kx) O.kx[k] = sx[k];
+          if (O.ky) O.ky[k] = sy[k];
+          if (O.koct) O.koct[k] = l;
+          if (O.kangle) O.kangle[k] = ((const float*)(ho + J->o_ang))[k];
+          if (O.kresp) O.kresp[k] = J->keys[l][id].response;
+          if (O.ksize) O.ksize[k] = patch;
+          k++;
+        }
+      }
+      if (want_desc) memcpy(O.desc, ho + J->o_desc, (size_t)J->n_total * 32);
+    }
+    if (O.n_per_level)
+      for (int l = 0; l < nl; l++) O.n_per_level[l] = (int)J->chosen[l].size();
+    if (O.level_w)
+      for (int l = 0; l < nl; l++) O.level_w[l] = L.w[l], O.level_h[l] = L.h[l];
+  }
+};
+
+int orb_run(lorb_ctx* c, const uint8_t* image, int width, int height, int step, const lorb_orb_params* prm,
+            const int* pattern, const ExtractOut& O) {
+  LORB_REQUIRE(c && image && prm, "ctx / image / params");
+  LORB_REQUIRE(width > 0 && height > 0 && step >= width, "image shape");
+  OrbPipeline pl;
+  LORB_TRY(pl.plan(c, width, height, prm, pattern, O.desc != nullptr, O.cap));
+  LORB_CUDA_TRY(cudaSetDevice(c->device));
+  OrbJob J;
+  J.image = image;
+  J.step = step;
+  J.O = O;
+  pl.layout(&J, 0);
+  LORB_TRY(pl.reserve(1));
+  LORB_TRY(pl.detect(&J));
+  LORB_TRY(pl.select(&J));
+  LORB_TRY(pl.describe(&J));
+  LORB_TRY(pl.queue_level_copies(&J));
+  LORB_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  pl.finish(&J);
   return LORB_OK;
 }
 
