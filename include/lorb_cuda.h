@@ -313,6 +313,33 @@ int lorb_orb_extract(lorb_ctx* ctx, const uint8_t* image, int width, int height,
                      float* kp_y, int* kp_octave, float* kp_angle, float* kp_response, float* kp_size,
                      uint8_t* desc, int* n_out, uint8_t* const* raw_levels);
 
+/*
+ * The device work of Frame::Frame(imgLeft, imgRight, camera) (reference src/frame.cpp:17-68) in one
+ * call: ORBextractor::operator() on both images (:42-46) and Frame::ComputeStereoMatches (:49) on
+ * the pyramids, keypoints and descriptors left on the device by the two extractions.  Results are
+ * those of lorb_orb_extract(left), lorb_orb_extract(right) and lorb_stereo_matches on their outputs.
+ *   out_left / out_right  keypoint arrays of capacity cap (response, size, raw_levels may be NULL);
+ *                         n receives the keypoint count
+ *   mbf, mb               Frame::mbf, Frame::mb
+ *   out_uright, out_depth [cap] mvuRight / mvDepth of the left keypoints (-1 where unmatched)
+ */
+typedef struct lorb_orb_keypoints {
+  int n;
+  float* x;
+  float* y;
+  int* octave;
+  float* angle;
+  float* response;
+  float* size;
+  uint8_t* desc;              /* [cap x 32] */
+  uint8_t* const* raw_levels; /* [nlevels] host buffers for mvImagePyramid, or NULL */
+} lorb_orb_keypoints;
+
+int lorb_stereo_frame(lorb_ctx* ctx, const uint8_t* left, const uint8_t* right, int width, int height,
+                      int step_left, int step_right, const lorb_orb_params* params, const int* pattern,
+                      float mbf, float mb, int cap, lorb_orb_keypoints* out_left,
+                      lorb_orb_keypoints* out_right, float* out_uright, float* out_depth, int* n_matched);
+
 /* Level geometry of the extractor: sizes of the pyramid levels (:1161-1163), mnFeaturesPerLevel
  * (:448-461, may be NULL) and mvScaleFactor (:428-436, may be NULL). */
 int lorb_orb_level_sizes(const lorb_orb_params* params, int width, int height, int* level_w,

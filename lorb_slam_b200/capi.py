@@ -26,7 +26,7 @@ EXPORTS = [
     "lorb_match_sweep_resident", "lorb_sweep_plan_upload", "lorb_sweep_plan_run",
     "lorb_sweep_plan_download", "lorb_sweep_plan_run_at", "lorb_search_proj_points", "lorb_search_proj_frame", "lorb_frustum_project", "lorb_compute_descriptors",
     "lorb_stereo_matches", "lorb_orb_describe", "lorb_orb_umax", "lorb_orb_selftest",
-    "lorb_orb_extract", "lorb_orb_level_sizes", "lorb_orb_stages",
+    "lorb_orb_extract", "lorb_orb_level_sizes", "lorb_orb_stages", "lorb_stereo_frame",
     "lorb_ba_default_options", "lorb_ba_pose_only", "lorb_ba_local", "lorb_ba_local_batched",
     "lorb_ba_problem_create", "lorb_ba_problem_create_batched", "lorb_ba_problem_reset", "lorb_ba_problem_solve",
     "lorb_ba_problem_download", "lorb_ba_problem_destroy", "lorb_dist_get_unique_id",
@@ -70,6 +70,12 @@ class FrameView(C.Structure):
 class OrbParams(C.Structure):
     _fields_ = [("nfeatures", C.c_int), ("scale_factor", C.c_float), ("nlevels", C.c_int),
                 ("ini_th_fast", C.c_int), ("min_th_fast", C.c_int)]
+
+
+class OrbKeypoints(C.Structure):
+    _fields_ = [("n", C.c_int), ("x", C.c_void_p), ("y", C.c_void_p), ("octave", C.c_void_p),
+                ("angle", C.c_void_p), ("response", C.c_void_p), ("size", C.c_void_p), ("desc", C.c_void_p),
+                ("raw_levels", C.c_void_p)]
 
 
 class PyramidView(C.Structure):
@@ -351,6 +357,37 @@ class Context:
         n = n.value
         return dict(n=n, x=kx[:n], y=ky[:n], octave=ko[:n], angle=ka[:n], response=kr[:n], size=ks[:n],
                     desc=desc[:n], n_per_level=np.bincount(ko[:n], minlength=nlevels).astype(np.int32))
+
+    def stereo_frame(self, left, right, pattern, mbf, mb, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20,
+                     min_th=7):
+        """Frame's stereo constructor on the device: both extractions + ComputeStereoMatches.
+        -> (left dict, right dict, uright, depth, n_matched)"""
+        left, right = _arr(left, np.uint8), _arr(right, np.uint8)
+        assert left.shape == right.shape
+        prm = OrbParams(nfeatures, scale_factor, nlevels, ini_th, min_th)
+        pat = _arr(pattern, np.int32).reshape(-1)
+        cap = nfeatures + 64
+        keep, views = [], []
+        for _ in range(2):
+            a = dict(x=np.zeros(cap, np.float32), y=np.zeros(cap, np.float32), octave=np.zeros(cap, np.int32),
+                     angle=np.zeros(cap, np.float32), response=np.zeros(cap, np.float32),
+                     size=np.zeros(cap, np.float32), desc=np.zeros((cap, 32), np.uint8))
+            keep.append(a)
+            views.append(OrbKeypoints(0, _ptr(a["x"]), _ptr(a["y"]), _ptr(a["octave"]), _ptr(a["angle"]),
+                                      _ptr(a["response"]), _ptr(a["size"]), _ptr(a["desc"]), None))
+        ur, dp = np.zeros(cap, np.float32), np.zeros(cap, np.float32)
+        nm = C.c_int(0)
+        _check(self._lib.lorb_stereo_frame(
+            self._h, _ptr(left), _ptr(right), left.shape[1], left.shape[0], left.strides[0], right.strides[0],
+            C.byref(prm), _ptr(pat), C.c_float(mbf), C.c_float(mb), cap, C.byref(views[0]), C.byref(views[1]),
+            _ptr(ur), _ptr(dp), C.byref(nm)))
+        res = []
+        for a, v in zip(keep, views):
+            n = v.n
+            d = {k: a[k][:n] for k in a}
+            d["n"] = n
+            res.append(d)
+        return res[0], res[1], ur[:res[0]["n"]], dp[:res[0]["n"]], nm.value
 
     def orb_stages(self, img, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7):
         """Pyramid, blurred pyramid and the candidate keypoints handed to the quadtree."""

@@ -23,27 +23,9 @@
 // Bounds: the reference relies on cv::Mat::rowRange/colRange assertions (an out-of-image patch
 // throws); here such a keypoint is simply left unmatched (documented deviation: no exception).
 #include "common.cuh"
+#include "stereo_dev.cuh"
 
 namespace lorb {
-
-constexpr int STEREO_MAX_LEVELS = 16;
-constexpr int STEREO_W = 5;  // patch half size  (:239)
-constexpr int STEREO_L = 5;  // shift half range (:246)
-
-struct PyrDev {
-  const uint8_t* lvl[STEREO_MAX_LEVELS];  // tightly packed rows, stride = w
-  int w[STEREO_MAX_LEVELS], h[STEREO_MAX_LEVELS];
-};
-
-struct StereoDev {
-  PyrDev left, right;
-  int n_left, n_right, n_levels, n_rows;
-  const float *lx, *ly, *rx, *ry;
-  const int *loct, *roct;
-  const uint4 *ldesc, *rdesc;
-  float sf[STEREO_MAX_LEVELS], inv_sf[STEREO_MAX_LEVELS];
-  float mbf, mb;
-};
 
 __global__ void __launch_bounds__(256)
     stereo_match_kernel(StereoDev S, float* __restrict__ out_uright, float* __restrict__ out_depth,
@@ -237,6 +219,14 @@ static int check_pyr(const lorb_pyramid_view* p, int n_levels) {
   return LORB_OK;
 }
 
+int stereo_launch(lorb_ctx* c, const StereoDev& S, float* d_uright, float* d_depth, int* d_sad, int* d_n_matched) {
+  const int warps_per_cta = 8;
+  LORB_LAUNCH(c, stereo_match_kernel, (S.n_left + warps_per_cta - 1) / warps_per_cta, warps_per_cta * 32, 0, S,
+              d_uright, d_depth, d_sad);
+  LORB_LAUNCH(c, stereo_finalize_kernel, 1, 1024, 0, S.n_left, (const int*)d_sad, d_uright, d_depth, d_n_matched);
+  return LORB_OK;
+}
+
 }  // namespace lorb
 
 using namespace lorb;
@@ -328,11 +318,7 @@ int lorb_stereo_matches(lorb_ctx* c, const lorb_pyramid_view* left, const lorb_p
   S.rdesc = (const uint4*)(d + i_rd);
   S.mbf = mbf;
   S.mb = mb;
-  const int warps_per_cta = 8;
-  LORB_LAUNCH(c, stereo_match_kernel, (n_left + warps_per_cta - 1) / warps_per_cta, warps_per_cta * 32, 0, S,
-              (float*)(dout + o_ur), (float*)(dout + o_dp), (int*)(dout + o_sad));
-  LORB_LAUNCH(c, stereo_finalize_kernel, 1, 1024, 0, n_left, (const int*)(dout + o_sad), (float*)(dout + o_ur),
-              (float*)(dout + o_dp), (int*)(dout + o_n));
+  LORB_TRY(stereo_launch(c, S, (float*)(dout + o_ur), (float*)(dout + o_dp), (int*)(dout + o_sad), (int*)(dout + o_n)));
   uint8_t* ho = c->h[1].as<uint8_t>();
   LORB_CUDA_TRY(cudaMemcpyAsync(ho, dout, o_sad, cudaMemcpyDeviceToHost, c->stream));
   LORB_CUDA_TRY(cudaStreamSynchronize(c->stream));

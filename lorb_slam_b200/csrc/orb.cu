@@ -15,6 +15,7 @@
 
 #include "common.cuh"
 #include "libm_sincosf.cuh"
+#include "stereo_dev.cuh"
 
 namespace lorb {
 
@@ -1062,6 +1063,104 @@ int lorb_orb_extract(lorb_ctx* c, const uint8_t* image, int width, int height, i
   O.desc = desc;
   O.n_out = n_out;
   return orb_run(c, image, width, height, step, prm, pattern, O);
+}
+
+// The device work of Frame::Frame(imgLeft, imgRight, camera) (reference src/frame.cpp:17-68):
+// ORBextractor on both images (:42-46, two host threads in the reference) and
+// ComputeStereoMatches (:49).  Both extractions share the stream: the right image's pyramid / FAST
+// run while the host distributes the left image's keypoints; the stereo matcher then reads the
+// pyramids, keypoints and descriptors where they already are -- on the device.
+int lorb_stereo_frame(lorb_ctx* c, const uint8_t* left, const uint8_t* right, int width, int height,
+                      int step_left, int step_right, const lorb_orb_params* prm, const int* pattern, float mbf,
+                      float mb, int cap, lorb_orb_keypoints* out_left, lorb_orb_keypoints* out_right,
+                      float* out_uright, float* out_depth, int* n_matched) {
+  LORB_REQUIRE(c && left && right && prm && out_left && out_right, "ctx / images / params / outputs");
+  LORB_REQUIRE(width > 0 && height > 0 && step_left >= width && step_right >= width, "image shape");
+  LORB_REQUIRE(mb > 0.0f, "baseline");
+  LORB_REQUIRE(out_uright && out_depth, "stereo outputs");
+  lorb_orb_keypoints* outs[2] = {out_left, out_right};
+  for (int j = 0; j < 2; j++)
+    LORB_REQUIRE(outs[j]->x && outs[j]->y && outs[j]->octave && outs[j]->angle && outs[j]->desc, "keypoint arrays");
+  OrbPipeline pl;
+  LORB_TRY(pl.plan(c, width, height, prm, pattern, true, cap));
+  LORB_REQUIRE(pl.nl <= STEREO_MAX_LEVELS, "levels");
+  LORB_CUDA_TRY(cudaSetDevice(c->device));
+  OrbJob J[2];
+  for (int j = 0; j < 2; j++) {
+    J[j].image = j ? right : left;
+    J[j].step = j ? step_right : step_left;
+    ExtractOut& O = J[j].O;
+    O.cap = cap;
+    O.kx = outs[j]->x;
+    O.ky = outs[j]->y;
+    O.koct = outs[j]->octave;
+    O.kangle = outs[j]->angle;
+    O.kresp = outs[j]->response;
+    O.ksize = outs[j]->size;
+    O.desc = outs[j]->desc;
+    O.n_out = &outs[j]->n;
+    O.raw_levels = outs[j]->raw_levels;
+    pl.layout(&J[j], j);
+  }
+  LORB_TRY(pl.reserve(2));
+  LORB_TRY(pl.detect(&J[0]));
+  LORB_TRY(pl.detect(&J[1]));
+  LORB_TRY(pl.select(&J[0]));
+  LORB_TRY(pl.describe(&J[0]));
+  LORB_TRY(pl.select(&J[1]));
+  LORB_TRY(pl.describe(&J[1]));
+  const int n_left = J[0].n_total, n_right = J[1].n_total;
+  if (n_matched) *n_matched = 0;
+  size_t o_ur = 0, o_dp = 0, o_n = 0;
+  if (n_left > 0) {
+    LORB_REQUIRE((unsigned)n_right < KEY_IDX_MASK, "keypoint counts");
+    OPacker so;
+    o_ur = so.add((size_t)n_left * 4);
+    o_dp = so.add((size_t)n_left * 4);
+    o_n = so.add(4);
+    const size_t o_sad = so.add((size_t)n_left * 4);
+    LORB_TRY(dev_reserve(c, 4, so.off));
+    LORB_TRY(pin_reserve(c, 3, so.off));
+    StereoDev S;
+    memset(&S, 0, sizeof(S));
+    for (int l = 0; l < pl.nl; l++) {
+      S.left.lvl[l] = J[0].P.raw[l];
+      S.right.lvl[l] = J[1].P.raw[l];
+      S.left.w[l] = S.right.w[l] = pl.L.w[l];
+      S.left.h[l] = S.right.h[l] = pl.L.h[l];
+      S.sf[l] = pl.L.scale[l];
+      S.inv_sf[l] = pl.L.inv_scale[l];
+    }
+    S.n_left = n_left;
+    S.n_right = n_right;
+    S.n_levels = pl.nl;
+    S.n_rows = pl.L.h[0];  // nRows = mvImagePyramid[0].rows (src/frame.cpp:132)
+    S.lx = J[0].d_sx;
+    S.ly = J[0].d_sy;
+    S.loct = J[0].d_lvl;
+    S.ldesc = reinterpret_cast<const uint4*>(J[0].d_desc);
+    S.rx = J[1].d_sx;
+    S.ry = J[1].d_sy;
+    S.roct = J[1].d_lvl;
+    S.rdesc = reinterpret_cast<const uint4*>(J[1].d_desc);
+    S.mbf = mbf;
+    S.mb = mb;
+    uint8_t* ds = c->d[4].as<uint8_t>();
+    LORB_TRY(stereo_launch(c, S, (float*)(ds + o_ur), (float*)(ds + o_dp), (int*)(ds + o_sad), (int*)(ds + o_n)));
+    LORB_CUDA_TRY(cudaMemcpyAsync(c->h[3].as<uint8_t>(), ds, o_sad, cudaMemcpyDeviceToHost, c->stream));
+  }
+  LORB_TRY(pl.queue_level_copies(&J[0]));
+  LORB_TRY(pl.queue_level_copies(&J[1]));
+  LORB_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  pl.finish(&J[0]);
+  pl.finish(&J[1]);
+  if (n_left > 0) {
+    const uint8_t* hs = c->h[3].as<uint8_t>();
+    memcpy(out_uright, hs + o_ur, (size_t)n_left * 4);
+    memcpy(out_depth, hs + o_dp, (size_t)n_left * 4);
+    if (n_matched) *n_matched = *(const int*)(hs + o_n);
+  }
+  return LORB_OK;
 }
 
 int lorb_orb_stages(lorb_ctx* c, const uint8_t* image, int width, int height, int step,

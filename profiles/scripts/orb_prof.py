@@ -31,3 +31,14 @@ with capi.Context(0) as ctx:
         except Exception as e:  # noqa: BLE001
             line += "; reference unavailable (%s)" % e
         print(line)
+
+    st0 = synth.make_stereo_pair(8, 0)
+    left, right = st0["pyr_left"][0], st0["pyr_right"][0]
+    for _ in range(5):
+        r = ctx.stereo_frame(left, right, pattern, float(st0["mbf"]), float(st0["mb"]))
+    t = time.perf_counter()
+    for _ in range(reps):
+        r = ctx.stereo_frame(left, right, pattern, float(st0["mbf"]), float(st0["mb"]))
+    dt = (time.perf_counter() - t) / reps
+    print("stereo frame 640x480 x2, 1000 features each: %d + %d keypoints, %d stereo matches, %.3f ms per frame pair"
+          % (r[0]["n"], r[1]["n"], r[4], dt * 1e3))

@@ -141,3 +141,35 @@ def test_config0_extract_then_match(ctx):
     py = 1.02 * (np.sin(ang) * xc + np.cos(ang) * yc) + 240 - 3.0
     err = np.hypot(px - b["x"][t], py - b["y"][t])
     assert np.median(err) < 3.0
+
+
+@pytest.mark.parametrize("seed", range(2))
+def test_stereo_frame_front_end(ctx, seed):
+    """lorb_stereo_frame (Frame's stereo constructor on the device) == the separately verified
+    pieces chained through host buffers, and == the compiled reference's extractor + its
+    Frame::ComputeStereoMatches when oracle/_ref travelled."""
+    st0 = synth.make_stereo_pair(8, 20 + seed)
+    left, right = st0["pyr_left"][0], st0["pyr_right"][0]
+    mbf, mb = float(st0["mbf"]), float(st0["mb"])
+    L, R, ur, dp, nm = ctx.stereo_frame(left, right, OC.pattern(), mbf, mb)
+    a, b = ctx.orb_extract(left, OC.pattern()), ctx.orb_extract(right, OC.pattern())
+    for got, want in ((L, a), (R, b)):
+        assert got["n"] == want["n"] > 500
+        for f in ("x", "y", "octave", "angle", "response", "size", "desc"):
+            assert np.array_equal(got[f], want[f]), f
+    _, _, _, sf = ctx.orb_level_sizes(left.shape[1], left.shape[0])
+    st = dict(n_levels=8, pyr_left=ctx.orb_stages(left)["raw"], pyr_right=ctx.orb_stages(right)["raw"],
+              scale_factors=sf, inv_scale_factors=(np.float32(1.0) / sf).astype(np.float32), mbf=mbf, mb=mb,
+              n_left=a["n"], lx=a["x"], ly=a["y"], loct=a["octave"], ldesc=a["desc"],
+              n_right=b["n"], rx=b["x"], ry=b["y"], roct=b["octave"], rdesc=b["desc"])
+    s = ctx.stereo_matches(st)
+    assert nm == s["n_matched"] and nm > 100
+    assert np.array_equal(ur, s["uright"]) and np.array_equal(dp, s["depth"])
+    o = ref.stereo_matches(st)
+    assert nm == o["n_matched"] and np.array_equal(ur, o["uright"]) and np.array_equal(dp, o["depth"])
+    from oracle import reflib
+    if reflib.available():
+        ra, rb = reflib.orb_extract(left), reflib.orb_extract(right)
+        assert np.array_equal(ra["desc"], L["desc"]) and np.array_equal(rb["x"], R["x"])
+        rs = reflib.stereo_matches(st)
+        assert nm == rs["n_matched"] and np.array_equal(ur, rs["uright"]) and np.array_equal(dp, rs["depth"])
