@@ -743,6 +743,7 @@ struct OrbPipeline {
   int nl = 0, width = 0, height = 0, n_cells = 0, n_tiles = 0, slot_cap = 0, key_cap = 0;
   bool want_desc = false;
   const int* pattern = nullptr;
+  int ini_th = 0, min_th = 0;
   size_t dev_bytes = 0, stage_bytes = 0, kin_cap_bytes = 0, kout_cap_bytes = 0;
 
   int plan(lorb_ctx* ctx, int w, int h, const lorb_orb_params* prm, const int* pat, bool desc, int cap) {
@@ -753,6 +754,8 @@ struct OrbPipeline {
     want_desc = desc;
     LORB_TRY(make_level_plan(prm, w, h, &L));
     nl = L.n_levels;
+    ini_th = prm->ini_th_fast;
+    min_th = prm->min_th_fast;
     if (want_desc) {
       LORB_REQUIRE(pattern, "pattern");
       for (int k = 0; k < 512; k++)
@@ -816,6 +819,8 @@ struct OrbPipeline {
     OrbPlanDev& P = J->P;
     memset(&P, 0, sizeof(P));
     P.n_levels = nl;
+    P.ini_th = ini_th;
+    P.min_th = min_th;
     int cells = 0, tiles = 0;
     uint8_t* d = c->d[3].as<uint8_t>() + J->dev_base;
     for (int l = 0; l < nl; l++) {
