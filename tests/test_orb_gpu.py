@@ -160,6 +160,7 @@ def test_stereo_frame_front_end(ctx, seed):
     _, _, _, sf = ctx.orb_level_sizes(left.shape[1], left.shape[0])
     st = dict(n_levels=8, pyr_left=ctx.orb_stages(left)["raw"], pyr_right=ctx.orb_stages(right)["raw"],
               scale_factors=sf, inv_scale_factors=(np.float32(1.0) / sf).astype(np.float32), mbf=mbf, mb=mb,
+              fx=float(st0["fx"]),
               n_left=a["n"], lx=a["x"], ly=a["y"], loct=a["octave"], ldesc=a["desc"],
               n_right=b["n"], rx=b["x"], ry=b["y"], roct=b["octave"], rdesc=b["desc"])
     s = ctx.stereo_matches(st)
