@@ -340,6 +340,16 @@ int lorb_stereo_frame(lorb_ctx* ctx, const uint8_t* left, const uint8_t* right, 
                       float mbf, float mb, int cap, lorb_orb_keypoints* out_left,
                       lorb_orb_keypoints* out_right, float* out_uright, float* out_depth, int* n_matched);
 
+/*
+ * ORBextractor::DistributeOctTree (:554-797) on its own (host code, no device work): from the
+ * candidate keypoints of one level (coordinates relative to min_x / min_y, in the order the
+ * detection loop produced them) pick about n_features of them, spread over the image by a
+ * quadtree.  out_index [n_keys] receives the indices of the chosen keypoints in the reference's
+ * output order, *n_out their number.  Equal-size tie-break: see lorb_orb_extract.
+ */
+int lorb_orb_distribute(int n_keys, const float* x, const float* y, const float* response, int min_x,
+                        int max_x, int min_y, int max_y, int n_features, int* out_index, int* n_out);
+
 /* Level geometry of the extractor: sizes of the pyramid levels (:1161-1163), mnFeaturesPerLevel
  * (:448-461, may be NULL) and mvScaleFactor (:428-436, may be NULL). */
 int lorb_orb_level_sizes(const lorb_orb_params* params, int width, int height, int* level_w,

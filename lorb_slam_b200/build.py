@@ -31,7 +31,7 @@ def _stale():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + [
+    deps = sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.h")) + [
         os.path.join(HERE, "..", "include", "lorb_cuda.h"), os.path.abspath(__file__)]
     return any(os.path.getmtime(d) > t for d in deps)
 

@@ -15,6 +15,7 @@
 
 #include "common.cuh"
 #include "libm_sincosf.cuh"
+#include "orb_quadtree.h"
 #include "stereo_dev.cuh"
 
 namespace lorb {
@@ -434,175 +435,6 @@ static int make_level_plan(const lorb_orb_params* p, int width, int height, OrbL
     LORB_REQUIRE(L->w[l] - 2 * ORB_EDGE + 6 < 4096 && L->h[l] - 2 * ORB_EDGE + 6 < 4096, "image larger than 4096 px");
   }
   return LORB_OK;
-}
-
-struct QKey {
-  float x, y, response;
-};
-
-// ORBextractor::DistributeOctTree (:554-797) on an index-linked node list.
-//   * the node list keeps the reference's order: children are pushed to the FRONT in the order
-//     n1..n4 as their parent is erased, a pass walks from the (old) front to the back;
-//   * a pass expands every node with more than one key; when the next pass could overshoot N
-//     (size + 3*expandable > N) the nodes are expanded largest first instead (:687-753).  The
-//     reference orders equal sizes by node ADDRESS (std::sort of (size, pointer) pairs); under an
-//     allocator that never reuses memory that is creation order, which is the rule here (and how
-//     oracle/_ref runs the reference): among equal sizes the node created LAST goes first;
-//   * each surviving node yields its first key of maximal response (:776-794).
-// Keys of a node are a contiguous run of `perm`, children are a stable 4-way partition of it.
-struct QNode {
-  int x0, x1, y0, y1;
-  int k0, k1;      // keys perm[k0 .. k1)
-  int prev, next;  // list links (-1 = none)
-  bool no_more;
-};
-
-static void distribute_quadtree(const std::vector<QKey>& keys, int min_x, int max_x, int min_y, int max_y, int N,
-                                std::vector<int>* result) {
-  result->clear();
-  const int n_keys = (int)keys.size();
-  const int n_ini = (int)roundf((float)(max_x - min_x) / (max_y - min_y));
-  if (n_ini < 1 || n_keys == 0) return;  // (the reference divides by zero for n_ini == 0)
-  const float h_x = (float)(max_x - min_x) / n_ini;
-  std::vector<QNode> nodes;
-  nodes.reserve((size_t)4 * n_keys + n_ini + 16);
-  std::vector<int> perm(n_keys), tmp(n_keys);
-  int head = -1, tail = -1, size = 0;
-  auto push_back = [&](int id) {
-    nodes[id].prev = tail;
-    nodes[id].next = -1;
-    if (tail >= 0) nodes[tail].next = id; else head = id;
-    tail = id;
-    ++size;
-  };
-  auto push_front = [&](int id) {
-    nodes[id].prev = -1;
-    nodes[id].next = head;
-    if (head >= 0) nodes[head].prev = id; else tail = id;
-    head = id;
-    ++size;
-  };
-  auto erase = [&](int id) {  // returns the next node
-    const int p = nodes[id].prev, nx = nodes[id].next;
-    if (p >= 0) nodes[p].next = nx; else head = nx;
-    if (nx >= 0) nodes[nx].prev = p; else tail = p;
-    --size;
-    return nx;
-  };
-  // initial nodes (:571-594): keys go to column (int)(x / hX), in input order
-  {
-    std::vector<int> cnt(n_ini + 1, 0), col(n_keys);
-    for (int i = 0; i < n_keys; i++) {
-      col[i] = std::min((int)(keys[i].x / h_x), n_ini - 1);
-      cnt[col[i] + 1]++;
-    }
-    for (int i = 0; i < n_ini; i++) cnt[i + 1] += cnt[i];
-    std::vector<int> fill(cnt.begin(), cnt.end() - 1);
-    for (int i = 0; i < n_keys; i++) perm[fill[col[i]]++] = i;
-    for (int i = 0; i < n_ini; i++) {
-      QNode nd;
-      nd.x0 = (int)(h_x * (float)i);
-      nd.x1 = (int)(h_x * (float)(i + 1));
-      nd.y0 = 0;
-      nd.y1 = max_y - min_y;
-      nd.k0 = cnt[i];
-      nd.k1 = cnt[i + 1];
-      nd.no_more = false;
-      nodes.push_back(nd);
-      push_back((int)nodes.size() - 1);
-    }
-  }
-  for (int id = head; id >= 0;) {  // :598-609
-    const int nk = nodes[id].k1 - nodes[id].k0;
-    if (nk == 1) {
-      nodes[id].no_more = true;
-      id = nodes[id].next;
-    } else if (nk == 0) {
-      id = erase(id);
-    } else {
-      id = nodes[id].next;
-    }
-  }
-  // DivideNode (:496-551) + the four push_front blocks; appends children with > 1 keys to `grown`
-  std::vector<std::pair<int, int>> grown, prev_grown;  // (size, node id = creation order)
-  auto divide = [&](int id) {
-    const QNode nd = nodes[id];
-    const int half_x = (int)ceilf((float)(nd.x1 - nd.x0) / 2), half_y = (int)ceilf((float)(nd.y1 - nd.y0) / 2);
-    const int xm = nd.x0 + half_x, ym = nd.y0 + half_y;
-    int cnt[4] = {0, 0, 0, 0};
-    for (int k = nd.k0; k < nd.k1; k++) {
-      const QKey& kp = keys[perm[k]];
-      const int q = kp.x < xm ? (kp.y < ym ? 0 : 2) : (kp.y < ym ? 1 : 3);
-      tmp[k] = q;
-      cnt[q]++;
-    }
-    int start[4], fill[4];
-    start[0] = nd.k0;
-    for (int q = 1; q < 4; q++) start[q] = start[q - 1] + cnt[q - 1];
-    for (int q = 0; q < 4; q++) fill[q] = start[q];
-    std::vector<int> moved(nd.k1 - nd.k0);
-    for (int k = nd.k0; k < nd.k1; k++) moved[fill[tmp[k]]++ - nd.k0] = perm[k];
-    std::copy(moved.begin(), moved.end(), perm.begin() + nd.k0);
-    const int bx0[4] = {nd.x0, xm, nd.x0, xm}, bx1[4] = {xm, nd.x1, xm, nd.x1};
-    const int by0[4] = {nd.y0, nd.y0, ym, ym}, by1[4] = {ym, ym, nd.y1, nd.y1};
-    int expandable = 0;
-    for (int q = 0; q < 4; q++) {
-      if (cnt[q] == 0) continue;
-      QNode ch;
-      ch.x0 = bx0[q];
-      ch.x1 = bx1[q];
-      ch.y0 = by0[q];
-      ch.y1 = by1[q];
-      ch.k0 = start[q];
-      ch.k1 = start[q] + cnt[q];
-      ch.no_more = cnt[q] == 1;
-      nodes.push_back(ch);
-      const int cid = (int)nodes.size() - 1;
-      push_front(cid);
-      if (cnt[q] > 1) {
-        ++expandable;
-        grown.emplace_back(cnt[q], cid);
-      }
-    }
-    return expandable;
-  };
-  bool finish = false;
-  while (!finish) {
-    const int prev_size = size;
-    int to_expand = 0;
-    grown.clear();
-    for (int id = head; id >= 0;) {
-      if (nodes[id].no_more) {
-        id = nodes[id].next;
-        continue;
-      }
-      to_expand += divide(id);
-      id = erase(id);
-    }
-    if (size >= N || size == prev_size) {
-      finish = true;
-    } else if (size + to_expand * 3 > N) {
-      while (!finish) {
-        const int prev_size2 = size;
-        prev_grown = grown;
-        grown.clear();
-        std::sort(prev_grown.begin(), prev_grown.end());  // (size, creation order) ascending
-        for (int j = (int)prev_grown.size() - 1; j >= 0; j--) {
-          divide(prev_grown[j].second);
-          erase(prev_grown[j].second);
-          if (size >= N) break;
-        }
-        if (size >= N || size == prev_size2) finish = true;
-      }
-    }
-  }
-  result->reserve(size);
-  for (int id = head; id >= 0; id = nodes[id].next) {
-    int best = perm[nodes[id].k0];
-    for (int k = nodes[id].k0 + 1; k < nodes[id].k1; k++)
-      if (keys[perm[k]].response > keys[best].response) best = perm[k];
-    result->push_back(best);
-  }
 }
 
 }  // namespace lorb
@@ -1036,6 +868,20 @@ int orb_run(lorb_ctx* c, const uint8_t* image, int width, int height, int step, 
 }
 
 }  // namespace
+
+// ORBextractor::DistributeOctTree (:554-797) alone: host code, no device work.
+int lorb_orb_distribute(int n_keys, const float* x, const float* y, const float* response, int min_x, int max_x,
+                        int min_y, int max_y, int n_features, int* out_index, int* n_out) {
+  LORB_REQUIRE(n_keys >= 0 && n_out && (n_keys == 0 || (x && y && response && out_index)), "arguments");
+  LORB_REQUIRE(max_x > min_x && max_y > min_y && n_features >= 0, "bounds");
+  std::vector<QKey> keys(n_keys);
+  for (int i = 0; i < n_keys; i++) keys[i] = QKey{x[i], y[i], response[i]};
+  std::vector<int> chosen;
+  distribute_quadtree(keys, min_x, max_x, min_y, max_y, n_features, &chosen);
+  for (size_t i = 0; i < chosen.size(); i++) out_index[i] = chosen[i];
+  *n_out = (int)chosen.size();
+  return LORB_OK;
+}
 
 int lorb_orb_level_sizes(const lorb_orb_params* prm, int width, int height, int* level_w, int* level_h,
                          int* n_features_per_level, float* scale_factors) {

@@ -98,6 +98,41 @@ int ref_orb_describe(int n_levels, const int* w, const int* h, const int* step_r
   return 0;
 }
 
+// ORBextractor::DistributeOctTree (:554-797, a protected member: the library is compiled with
+// -fno-access-control) on given candidates, under the bump arena.  out_x/out_y/out_resp receive
+// the chosen keypoints in the reference's output order; returns their number.
+int ref_distribute_octree(int n_keys, const float* x, const float* y, const float* resp, int min_x, int max_x,
+                          int min_y, int max_y, int n_features, float* out_x, float* out_y, float* out_resp) {
+  const size_t arena = (size_t)1 << 28;
+  char* mem = (char*)std::malloc(arena);
+  if (!mem) return -1;
+  int n = -1;
+  lorb_arena::base = mem;
+  lorb_arena::used = 0;
+  lorb_arena::cap = arena;
+  lorb_arena::on = true;
+  {
+    ORBextractor ex(n_features, 1.2f, 8, 20, 7);
+    std::vector<cv::KeyPoint> in(n_keys);
+    for (int i = 0; i < n_keys; i++) {
+      in[i].pt = cv::Point2f(x[i], y[i]);
+      in[i].response = resp[i];
+    }
+    std::vector<cv::KeyPoint> out = ex.DistributeOctTree(in, min_x, max_x, min_y, max_y, n_features, 0);
+    n = (int)out.size();
+    for (int i = 0; i < n; i++) {
+      out_x[i] = out[i].pt.x;
+      out_y[i] = out[i].pt.y;
+      out_resp[i] = out[i].response;
+    }
+  }
+  lorb_arena::on = false;
+  lorb_arena::base = nullptr;
+  lorb_arena::cap = 0;
+  std::free(mem);
+  return n;
+}
+
 // The whole ORBextractor::operator() (:1087-1151) on one 8-bit image, under the bump arena.
 // Outputs in the reference's order (level by level): keypoint x, y (level-0 coordinates), octave,
 // angle, response, size, and the descriptor rows.  Returns the number of keypoints (<= cap) or -1.

@@ -271,6 +271,17 @@ def orb_extract(img, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min
                 desc=desc[:n], n_per_level=npl)
 
 
+def distribute_octree(x, y, resp, min_x, max_x, min_y, max_y, n_features):
+    """ORBextractor::DistributeOctTree of the compiled reference (bump arena) -> (x, y, response)."""
+    x, y, resp = _f32(x), _f32(y), _f32(resp)
+    n = len(x)
+    ox, oy, orr = np.zeros(n + 8, np.float32), np.zeros(n + 8, np.float32), np.zeros(n + 8, np.float32)
+    k = lib().ref_distribute_octree(n, _p(x, C.c_float), _p(y, C.c_float), _p(resp, C.c_float), min_x, max_x, min_y,
+                                    max_y, n_features, _p(ox, C.c_float), _p(oy, C.c_float), _p(orr, C.c_float))
+    assert 0 <= k <= n
+    return ox[:k], oy[:k], orr[:k]
+
+
 def compute_descriptor(desc):
     desc = _u8(desc).reshape(-1, 32)
     return int(lib().ref_compute_descriptor(_p(desc, C.c_uint8) if len(desc) else None, len(desc)))

@@ -182,3 +182,23 @@ ORB_EXTRACT = [
 def orb_extract_case(c):
     img = synth.make_orb_image(c[1], c[2], c[3])
     return synth.warp_orb_image(img) if c[5] else img
+
+
+# ---- ORBextractor::DistributeOctTree alone (host code): random candidate sets
+QUADTREE = [
+    # name, seed, n_keys, width, height (of the bordered region), n_features
+    ("lvl0_like", 0, 2800, 608, 448, 217), ("dense_small_budget", 1, 3000, 608, 448, 40),
+    ("sparse", 2, 150, 608, 448, 217), ("kitti_like", 3, 4000, 1209, 344, 400),
+    ("duplicates", 4, 1500, 300, 200, 500), ("one_key", 5, 1, 608, 448, 100),
+    ("budget_exceeds_keys", 6, 300, 400, 300, 2000), ("small_level", 7, 400, 147, 102, 61),
+]
+
+
+def quadtree_case(c):
+    _, seed, n, w, h, nf = c
+    rng = np.random.default_rng(seed + 8800)
+    span = 40 if c[0] == "duplicates" else w - 6  # many keys on the same pixel
+    x = rng.integers(0, span, n).astype(np.float32)
+    y = rng.integers(0, min(span, h - 6), n).astype(np.float32)
+    r = rng.integers(7, 80, n).astype(np.float32)
+    return x, y, r, 16, 16 + w, 16, 16 + h, nf

@@ -82,3 +82,37 @@ def test_level_plan():
     z = np.zeros(8, np.int32)
     p = z.ctypes.data_as(C.c_void_p)
     assert capi.load_library().lorb_orb_level_sizes(C.byref(prm), 100, 100, p, p, None, None) != 0  # too small
+
+
+@pytest.mark.parametrize("c", RC.QUADTREE, ids=[c[0] for c in RC.QUADTREE])
+def test_quadtree_matches_reference(c):
+    """The product's host quadtree (lorb_orb_distribute, no GPU needed) picks exactly the keypoints
+    the compiled reference's DistributeOctTree picks, in the same order."""
+    args = RC.quadtree_case(c)
+    g = OC.golden()
+    k = "qt/" + c[0]
+    assert str(g[k + "/digest"]) == RC.digest(*args)
+    idx = capi.orb_distribute(*args)
+    x, y, r = args[:3]
+    assert np.array_equal(x[idx], g[k + "/x"]) and np.array_equal(y[idx], g[k + "/y"])
+    assert np.array_equal(r[idx], g[k + "/response"])
+    assert len(idx) == len(set(idx.tolist())) and len(idx) <= len(x)
+
+
+def test_quadtree_fresh_vs_compiled_reference():
+    from oracle import reflib
+    if not reflib.available():
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(123)
+    for _ in range(60):
+        n, w, h = int(rng.integers(1, 2500)), int(rng.integers(100, 1300)), int(rng.integers(60, 700))
+        if round(np.float32(w) / np.float32(h)) < 1:
+            continue  # the reference divides by zero (nIni = 0)
+        x = rng.integers(0, w - 6, n).astype(np.float32)
+        y = rng.integers(0, h - 6, n).astype(np.float32)
+        r = rng.integers(7, 60, n).astype(np.float32)
+        nf = int(rng.integers(1, 1500))
+        idx = capi.orb_distribute(x, y, r, 16, 16 + w, 16, 16 + h, nf)
+        ox, oy, orr = reflib.distribute_octree(x, y, r, 16, 16 + w, 16, 16 + h, nf)
+        assert len(idx) == len(ox) and np.array_equal(x[idx], ox) and np.array_equal(y[idx], oy)
+        assert np.array_equal(r[idx], orr)
