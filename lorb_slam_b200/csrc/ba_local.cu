@@ -2092,13 +2092,30 @@ static int problem_build(lorb_ba_problem* pb, lorb_ctx* c, const std::vector<Win
       for (int i = 0; i <= W.P; i++) ptr[i] = 0;
       bool sorted = W.F == 0;  // fast path: window observations already grouped by ascending point
       bool bad = false;
-      for (int i = 0; i < W.O; i++) {
-        if (!(W.obs_pt[i] >= 0 && W.obs_pt[i] < W.P && W.obs_cam[i] >= 0 && W.obs_cam[i] < W.C)) {
-          bad = true;
-          break;
+      const bool big = W.O > 200000;  // a large window is staged alone: its loops use the host threads
+      if (big) {
+        int bad_i = 0, unsorted_i = 0;
+#pragma omp parallel for schedule(static) reduction(| : bad_i, unsorted_i)
+        for (int i = 0; i < W.O; i++) {
+          if (!(W.obs_pt[i] >= 0 && W.obs_pt[i] < W.P && W.obs_cam[i] >= 0 && W.obs_cam[i] < W.C)) {
+            bad_i |= 1;
+            continue;
+          }
+#pragma omp atomic
+          ptr[W.obs_pt[i] + 1]++;
+          if (i > 0 && W.obs_pt[i] < W.obs_pt[i - 1]) unsorted_i |= 1;
         }
-        ptr[W.obs_pt[i] + 1]++;
-        if (i > 0 && W.obs_pt[i] < W.obs_pt[i - 1]) sorted = false;
+        bad = bad_i != 0;
+        if (unsorted_i) sorted = false;
+      } else {
+        for (int i = 0; i < W.O; i++) {
+          if (!(W.obs_pt[i] >= 0 && W.obs_pt[i] < W.P && W.obs_cam[i] >= 0 && W.obs_cam[i] < W.C)) {
+            bad = true;
+            break;
+          }
+          ptr[W.obs_pt[i] + 1]++;
+          if (i > 0 && W.obs_pt[i] < W.obs_pt[i - 1]) sorted = false;
+        }
       }
       if (bad) {
         bad_obs |= 1;
@@ -2118,7 +2135,15 @@ static int problem_build(lorb_ba_problem* pb, lorb_ctx* c, const std::vector<Win
       for (int i = 0; i < W.P; i++) ptr[i + 1] += ptr[i];
       std::vector<int> fill;
       if (sorted) {  // the CSR order is the input order: two block copies
-        if (W.O) {
+        if (W.O && big) {
+          const int nchunk = 64;
+#pragma omp parallel for schedule(static)
+          for (int ch = 0; ch < nchunk; ch++) {
+            const size_t i0 = (size_t)W.O * ch / nchunk, i1 = (size_t)W.O * (ch + 1) / nchunk;
+            memcpy(&h_cam[b + i0], W.obs_cam + i0, (i1 - i0) * 4);
+            memcpy(&h_uv[b + i0], W.obs_uv + 2 * i0, (i1 - i0) * 8);
+          }
+        } else if (W.O) {
           memcpy(&h_cam[b], W.obs_cam, (size_t)W.O * 4);
           memcpy(&h_uv[b], W.obs_uv, (size_t)W.O * 8);
         }
@@ -2155,19 +2180,44 @@ static int problem_build(lorb_ba_problem* pb, lorb_ctx* c, const std::vector<Win
         ListOff& L = lo[w];
         L.obs_pt = h_obs_pt.size();
         h_obs_pt.resize(L.obs_pt + OT);
-        for (int pp = 0; pp < W.P; pp++)
-          for (int e = ptr[pp]; e < ptr[pp + 1]; e++) h_obs_pt[L.obs_pt + e] = pp;
-        // observations grouped by camera (counting sort), sliced into items of <= 1024
+        {
+          int* const op = &h_obs_pt[L.obs_pt];
+#pragma omp parallel for schedule(static) if (big)
+          for (int pp = 0; pp < W.P; pp++)
+            for (int e = ptr[pp]; e < ptr[pp + 1]; e++) op[e] = pp;
+        }
+        // observations grouped by camera (stable counting sort: one histogram per host thread over a
+        // static slice of the observations, so the order is the serial one), items of <= 1024
+        const int nthc = big ? std::max(1, std::min(omp_get_max_threads(), 64)) : 1;
         std::vector<int> cnt((size_t)W.C + 1, 0);
-        for (int e = 0; e < OT; e++)
-          if (cam[e] >= 0) cnt[cam[e] + 1]++;
-        for (int c2 = 0; c2 < W.C; c2++) cnt[c2 + 1] += cnt[c2];
+        std::vector<int> tcc((size_t)nthc * W.C, 0);
+        auto e_lo = [&](int t) { return (int)((long long)OT * t / nthc); };
+#pragma omp parallel for schedule(static, 1) num_threads(nthc) if (big)
+        for (int t = 0; t < nthc; t++) {
+          int* mine = &tcc[(size_t)t * W.C];
+          for (int e = e_lo(t); e < e_lo(t + 1); e++)
+            if (cam[e] >= 0) mine[cam[e]]++;
+        }
+        for (int c2 = 0; c2 < W.C; c2++) {
+          int run = cnt[c2];
+          for (int t = 0; t < nthc; t++) {  // exclusive offset of thread t inside camera c2
+            const int k2 = tcc[(size_t)t * W.C + c2];
+            tcc[(size_t)t * W.C + c2] = run;
+            run += k2;
+          }
+          cnt[c2 + 1] = run;
+        }
         L.cam_obs = h_cam_obs.size();
         h_cam_obs.resize(L.cam_obs + cnt[W.C]);
         {
-          std::vector<int> cur(cnt.begin(), cnt.end() - 1);
-          for (int e = 0; e < OT; e++)
-            if (cam[e] >= 0) h_cam_obs[L.cam_obs + cur[cam[e]]++] = make_int2(e, h_obs_pt[L.obs_pt + e]);
+          int2* const co = &h_cam_obs[L.cam_obs];
+          const int* const op = &h_obs_pt[L.obs_pt];
+#pragma omp parallel for schedule(static, 1) num_threads(nthc) if (big)
+          for (int t = 0; t < nthc; t++) {
+            int* cur = &tcc[(size_t)t * W.C];
+            for (int e = e_lo(t); e < e_lo(t + 1); e++)
+              if (cam[e] >= 0) co[cur[cam[e]]++] = make_int2(e, op[e]);
+          }
         }
         L.cam_items = h_cam_items.size();
         for (int c2 = 0; c2 < W.C; c2++)
