@@ -246,6 +246,9 @@ int lorb_ctx_destroy(lorb_ctx* c) {
   cudaStreamSynchronize(c->stream);
   dist_destroy(c);
   ba_cache_free(c);
+  for (auto& row : c->orb_ev)
+    for (auto& e : row)
+      if (e) cudaEventDestroy(e);
   for (auto& b : c->d) b.release();
   for (auto& b : c->h) b.release();
   c->bank.release();

@@ -292,15 +292,16 @@ __device__ __forceinline__ int arc9_min_max(const int (&d)[16]) {
 }
 
 __global__ void __launch_bounds__(256)
-    orb_fast_cells_kernel(OrbPlanDev P, uint32_t* __restrict__ slots, int* __restrict__ cell_count) {
+    orb_fast_cells_kernel(OrbPlanDev P, int cell_base, uint32_t* __restrict__ slots, int* __restrict__ cell_count) {
   __shared__ uint8_t s_img[CELL_MAX * CELL_MAX];
   __shared__ int16_t s_score[CELL_MAX * CELL_MAX];
   __shared__ uint8_t s_keep[CELL_MAX * CELL_MAX];
   __shared__ int s_warp[8];
   __shared__ int s_base;
+  const int cell = cell_base + blockIdx.x;  // cells are numbered level after level
   int l = 0;
-  while (l + 1 < P.n_levels && (int)blockIdx.x >= P.cell_start[l + 1]) ++l;
-  const int c = blockIdx.x - P.cell_start[l];
+  while (l + 1 < P.n_levels && cell >= P.cell_start[l + 1]) ++l;
+  const int c = cell - P.cell_start[l];
   const int ci = c / P.n_cols[l], cj = c % P.n_cols[l];
   const int w = P.w[l], h = P.h[l];
   const int min_b = ORB_EDGE - 3, max_bx = w - ORB_EDGE + 3, max_by = h - ORB_EDGE + 3;
@@ -309,7 +310,7 @@ __global__ void __launch_bounds__(256)
   const int sw = max_x - ini_x, sh = max_y - ini_y;
   // the reference skips these cells (:832-833, :841-842); cv::FAST returns nothing below 7 px
   if (ini_y >= max_by - 3 || ini_x >= max_bx - 6 || sw < 7 || sh < 7) {
-    if (threadIdx.x == 0) cell_count[blockIdx.x] = 0;
+    if (threadIdx.x == 0) cell_count[cell] = 0;
     return;
   }
   const uint8_t* __restrict__ img = P.raw[l];
@@ -362,7 +363,7 @@ __global__ void __launch_bounds__(256)
   }
   if (threadIdx.x == 0) s_base = 0;
   const int th = __syncthreads_or(any_ini) ? P.ini_th : P.min_th;
-  uint32_t* __restrict__ slot = slots + (size_t)blockIdx.x * P.slot_cap;
+  uint32_t* __restrict__ slot = slots + (size_t)cell * P.slot_cap;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int q0 = 0; q0 < n_in; q0 += blockDim.x) {
     const int q = q0 + threadIdx.x;
@@ -389,7 +390,7 @@ __global__ void __launch_bounds__(256)
     }
     __syncthreads();
   }
-  if (threadIdx.x == 0) cell_count[blockIdx.x] = s_base;
+  if (threadIdx.x == 0) cell_count[cell] = s_base;
 }
 
 // ------------------------------------------------------------------ host: level plan + quadtree
@@ -559,7 +560,7 @@ struct OrbJob {
   size_t i_kx = 0, i_ky = 0, i_kl = 0, i_sx = 0, i_sy = 0, i_tab = 0, kin_bytes = 0;
   size_t o_ang = 0, o_desc = 0, kout_bytes = 0;
   OrbPlanDev P;
-  cudaEvent_t ev = nullptr;
+  int slot = 0;  // which row of ctx->orb_ev this job uses
   std::vector<std::vector<int>> chosen;
   std::vector<std::vector<QKey>> keys;
   int n_total = 0;
@@ -633,6 +634,7 @@ struct OrbPipeline {
     J->o_desc = out.add((size_t)key_cap * 32);
     kout_cap_bytes = out.off;
     J->kout_base = (size_t)j * kout_cap_bytes;
+    J->slot = j;
   }
 
   int reserve(int n_jobs) {
@@ -679,16 +681,23 @@ struct OrbPipeline {
       for (int r = 0; r < height; r++) memcpy(hp + J->h_img + (size_t)r * width, J->image + (size_t)r * J->step, width);
     }
     LORB_CUDA_TRY(cudaMemcpyAsync(P.raw[0], hp + J->h_img, (size_t)width * height, cudaMemcpyHostToDevice, c->stream));
-    for (int l = 1; l < nl; l++) {
-      // scale = 1 / (dsize / ssize) in double, as cv::resize derives it from the two sizes
-      const double sx = 1. / ((double)L.w[l] / L.w[l - 1]), sy = 1. / ((double)L.h[l] / L.h[l - 1]);
-      const dim3 blk(32, 8), grd((L.w[l] + 31) / 32, (L.h[l] + 7) / 8);
-      LORB_LAUNCH(c, orb_resize_kernel, grd, blk, 0, P.raw[l - 1], L.w[l - 1], L.h[l - 1], P.raw[l], L.w[l], L.h[l],
-                  sx, sy);
+    // Level after level: resize from the level above, FAST over the level's cells, "candidates of
+    // level l are in host memory" event.  The host starts distributing level 0 (the largest)
+    // while the GPU is still building the rest of the pyramid.
+    for (int l = 0; l < nl; l++) {
+      if (l > 0) {
+        // scale = 1 / (dsize / ssize) in double, as cv::resize derives it from the two sizes
+        const double sx = 1. / ((double)L.w[l] / L.w[l - 1]), sy = 1. / ((double)L.h[l] / L.h[l - 1]);
+        const dim3 blk(32, 8), grd((L.w[l] + 31) / 32, (L.h[l] + 7) / 8);
+        LORB_LAUNCH(c, orb_resize_kernel, grd, blk, 0, P.raw[l - 1], L.w[l - 1], L.h[l - 1], P.raw[l], L.w[l],
+                    L.h[l], sx, sy);
+      }
+      LORB_LAUNCH(c, orb_fast_cells_kernel, P.cell_start[l + 1] - P.cell_start[l], 256, 0, P, P.cell_start[l],
+                  (uint32_t*)(hp + J->h_slots), (int*)(hp + J->h_cnt));
+      cudaEvent_t& ev = c->orb_ev[J->slot][l];
+      if (!ev) LORB_CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      LORB_CUDA_TRY(cudaEventRecord(ev, c->stream));
     }
-    LORB_LAUNCH(c, orb_fast_cells_kernel, n_cells, 256, 0, P, (uint32_t*)(hp + J->h_slots), (int*)(hp + J->h_cnt));
-    LORB_CUDA_TRY(cudaEventCreateWithFlags(&J->ev, cudaEventDisableTiming));
-    LORB_CUDA_TRY(cudaEventRecord(J->ev, c->stream));
     if (want_desc || J->O.blur_levels) LORB_LAUNCH(c, orb_blur_kernel, n_tiles, 256, 0, P);
     return LORB_OK;
   }
@@ -711,18 +720,20 @@ struct OrbPipeline {
 
   // Wait for the candidates of this job, run DistributeOctTree per level (:865-866).
   int select(OrbJob* J) {
-    cudaError_t ee = cudaEventSynchronize(J->ev);
-    cudaEventDestroy(J->ev);
-    J->ev = nullptr;
-    LORB_CUDA_TRY(ee);
     const int* cnt = (const int*)(c->h[2].as<uint8_t>() + J->stage_base + J->h_cnt);
-    for (int k = 0; k < n_cells; k++)
-      LORB_REQUIRE(cnt[k] >= 0 && cnt[k] <= slot_cap, "candidate slot overflow (internal)");
+    auto wait_level = [&](int l) -> int {
+      if (cudaEventSynchronize(c->orb_ev[J->slot][l]) != cudaSuccess) return 1;
+      for (int k = J->P.cell_start[l]; k < J->P.cell_start[l + 1]; k++)
+        if (cnt[k] < 0 || cnt[k] > slot_cap) return 2;
+      return 0;
+    };
     const ExtractOut& O = J->O;
     if (O.cand_level_start) {
       std::vector<QKey> kk;
       int total = 0;
       for (int l = 0; l < nl; l++) {
+        const int wr = wait_level(l);
+        LORB_REQUIRE(wr == 0, "FAST kernel failed or candidate slot overflow (internal)");
         level_keys(J, l, &kk);
         O.cand_level_start[l] = total;
         LORB_REQUIRE(total + (int)kk.size() <= O.cand_cap, "candidate capacity");
@@ -739,13 +750,21 @@ struct OrbPipeline {
     J->keys.assign(nl, std::vector<QKey>());
     J->n_total = 0;
     if (O.n_out || want_desc) {
-#pragma omp parallel for schedule(dynamic, 1) num_threads(std::min(nl, 8))
+      int failed = 0;
+      // one host thread per level: each waits for its own level's candidates (levels arrive in
+      // order, the largest first) and distributes them while the GPU goes on with the next levels
+#pragma omp parallel for schedule(static, 1) num_threads(std::min(nl, 8)) reduction(| : failed)
       for (int l = 0; l < nl; l++) {
+        if (wait_level(l) != 0) {
+          failed |= 1;
+          continue;
+        }
         level_keys(J, l, &J->keys[l]);
         const int min_b = ORB_EDGE - 3;
         distribute_quadtree(J->keys[l], min_b, L.w[l] - ORB_EDGE + 3, min_b, L.h[l] - ORB_EDGE + 3, L.n_features[l],
                             &J->chosen[l]);
       }
+      LORB_REQUIRE(!failed, "FAST kernel failed or candidate slot overflow (internal)");
       for (int l = 0; l < nl; l++) J->n_total += (int)J->chosen[l].size();
       if (O.n_out) *O.n_out = J->n_total;
       LORB_REQUIRE(J->n_total <= O.cap && J->n_total <= key_cap,
