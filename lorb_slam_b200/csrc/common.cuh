@@ -63,8 +63,9 @@ struct lorb_ctx {
   int plan_n_pairs = 0, plan_max_kf = 0;
   lorb::Dist* dist = nullptr;
   void* ba_cache = nullptr;  // reusable lorb_ba_problem of the host-buffer BA calls (ba_local.cu)
-  // per-level "candidates ready" events of the ORB extractor (orb.cu), two jobs x 16 levels, lazily created
-  cudaEvent_t orb_ev[2][16] = {};
+  // cached CUDA graphs of the ORB extractor's detection chain (orb.cu), one per job slot
+  void* orb_graph[2] = {nullptr, nullptr};
+  unsigned orb_seq = 0;  // call counter the FAST kernel echoes into the per-level host flags
   // optional event timing of the library's own kernels (lorb_ctx_profile)
   int prof_on = 0;
   void* prof = nullptr;  // lorb::Prof (ctx.cu)

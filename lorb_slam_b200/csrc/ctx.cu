@@ -46,6 +46,7 @@ void Buf::release() {
 
 void dist_destroy(lorb_ctx* ctx);  // dist.cu
 void ba_cache_free(lorb_ctx* ctx);  // ba_local.cu
+void orb_graph_free(lorb_ctx* ctx); // orb.cu
 
 // ---------------------------------------------------------------- microbench
 // kind 0: 8 x (XOR, POPC, add) per 256-bit pair; kind 1: carry-save body.
@@ -246,9 +247,7 @@ int lorb_ctx_destroy(lorb_ctx* c) {
   cudaStreamSynchronize(c->stream);
   dist_destroy(c);
   ba_cache_free(c);
-  for (auto& row : c->orb_ev)
-    for (auto& e : row)
-      if (e) cudaEventDestroy(e);
+  orb_graph_free(c);
   for (auto& b : c->d) b.release();
   for (auto& b : c->h) b.release();
   c->bank.release();

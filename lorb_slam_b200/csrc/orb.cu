@@ -9,7 +9,11 @@
 // points; the rotation uses sinf/cosf with the bits of the host's libm (libm_sincosf.cuh) and
 // separate fp32 multiply / add (the reference is compiled without FMA), each coordinate rounded
 // half-to-even as cvRound does.  The pattern (512 points, int8 pairs) sits in shared memory.
+#include <stdlib.h>
+
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <utility>
 #include <vector>
 
@@ -217,6 +221,12 @@ struct OrbPlanDev {
   int n_cols[ORB_MAX_LEVELS], w_cell[ORB_MAX_LEVELS], h_cell[ORB_MAX_LEVELS];
   int slot_cap;                        // candidate slots per cell
   int ini_th, min_th;
+  // completion signalling of the FAST kernel: per level a device counter of finished cells; the
+  // CTA that finishes last stores the call's sequence number (read from *seq) into the level's
+  // flag in mapped pinned host memory
+  int* done_ctr;
+  volatile unsigned* host_flag;
+  const unsigned* seq;
 };
 
 // cv::GaussianBlur(7x7, sigma 2, BORDER_REFLECT_101) of an 8-bit image in OpenCV 4's fixed-point
@@ -309,10 +319,9 @@ __global__ void __launch_bounds__(256)
   const int max_y = min(ini_y + P.h_cell[l] + 6, max_by), max_x = min(ini_x + P.w_cell[l] + 6, max_bx);
   const int sw = max_x - ini_x, sh = max_y - ini_y;
   // the reference skips these cells (:832-833, :841-842); cv::FAST returns nothing below 7 px
-  if (ini_y >= max_by - 3 || ini_x >= max_bx - 6 || sw < 7 || sh < 7) {
-    if (threadIdx.x == 0) cell_count[cell] = 0;
-    return;
-  }
+  const bool active = !(ini_y >= max_by - 3 || ini_x >= max_bx - 6 || sw < 7 || sh < 7);
+  if (threadIdx.x == 0) s_base = 0;
+  if (active) {
   const uint8_t* __restrict__ img = P.raw[l];
   for (int p = threadIdx.x; p < sw * sh; p += blockDim.x) {
     const int y = p / sw, x = p - y * sw;
@@ -361,7 +370,6 @@ __global__ void __launch_bounds__(256)
     s_keep[y * CELL_MAX + x] = keep;
     any_ini |= keep && v >= P.ini_th;
   }
-  if (threadIdx.x == 0) s_base = 0;
   const int th = __syncthreads_or(any_ini) ? P.ini_th : P.min_th;
   uint32_t* __restrict__ slot = slots + (size_t)cell * P.slot_cap;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -390,7 +398,21 @@ __global__ void __launch_bounds__(256)
     }
     __syncthreads();
   }
-  if (threadIdx.x == 0) cell_count[cell] = s_base;
+  }  // active
+  // publish: every thread's stores to host memory are fenced, then one thread counts the cell in;
+  // the last cell of the level raises the level's flag
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    cell_count[cell] = active ? s_base : 0;
+    __threadfence_system();
+    const int n_level = P.cell_start[l + 1] - P.cell_start[l];
+    if (atomicAdd(&P.done_ctr[l], 1) == n_level - 1) {
+      P.done_ctr[l] = 0;  // ready for the next call (stream ordered)
+      __threadfence_system();
+      P.host_flag[l] = *P.seq;
+    }
+  }
 }
 
 // ------------------------------------------------------------------ host: level plan + quadtree
@@ -436,6 +458,28 @@ static int make_level_plan(const lorb_orb_params* p, int width, int height, OrbL
     LORB_REQUIRE(L->w[l] - 2 * ORB_EDGE + 6 < 4096 && L->h[l] - 2 * ORB_EDGE + 6 < 4096, "image larger than 4096 px");
   }
   return LORB_OK;
+}
+
+struct OrbGraphKey {  // everything the captured chain depends on
+  OrbPlanDev P;
+  const void* stage;
+  int width, height, with_blur;
+};
+
+struct OrbGraph {
+  OrbGraphKey key;
+  cudaGraphExec_t exec = nullptr;
+  int n_kernels = 0;
+};
+
+void orb_graph_free(lorb_ctx* c) {
+  for (auto& g : c->orb_graph)
+    if (g) {
+      OrbGraph* G = static_cast<OrbGraph*>(g);
+      if (G->exec) cudaGraphExecDestroy(G->exec);
+      delete G;
+      g = nullptr;
+    }
 }
 
 }  // namespace lorb
@@ -556,7 +600,9 @@ struct OrbJob {
   // layout (offsets into the shared buffers, fixed by layout())
   size_t dev_base = 0, stage_base = 0, kin_base = 0, kout_base = 0;
   size_t o_raw[ORB_MAX_LEVELS], o_blur[ORB_MAX_LEVELS];
+  size_t o_hdr = 0, o_ctr = 0, h_hdr = 0, h_flag = 0;
   size_t h_img = 0, h_cnt = 0, h_slots = 0;
+  unsigned seq = 0;
   size_t i_kx = 0, i_ky = 0, i_kl = 0, i_sx = 0, i_sy = 0, i_tab = 0, kin_bytes = 0;
   size_t o_ang = 0, o_desc = 0, kout_bytes = 0;
   OrbPlanDev P;
@@ -570,7 +616,20 @@ struct OrbJob {
   const uint32_t* d_desc = nullptr;
 };
 
+// LORB_ORB_TRACE=1: host timeline of a call on stderr (microseconds since the call started)
+struct OrbTrace {
+  bool on;
+  std::chrono::steady_clock::time_point t0;
+  OrbTrace() : on(getenv("LORB_ORB_TRACE") != nullptr), t0(std::chrono::steady_clock::now()) {}
+  void mark(const char* what, int a = -1) const {
+    if (!on) return;
+    const double us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
+    fprintf(stderr, "[orb %8.1f us] %s %d\n", us, what, a);
+  }
+};
+
 struct OrbPipeline {
+  OrbTrace tr;
   lorb_ctx* c;
   OrbLevelPlan L;
   int nl = 0, width = 0, height = 0, n_cells = 0, n_tiles = 0, slot_cap = 0, key_cap = 0;
@@ -611,12 +670,16 @@ struct OrbPipeline {
   // Offsets of job j inside the shared device / pinned buffers.
   void layout(OrbJob* J, int j) {
     OPacker dv;
+    J->o_hdr = dv.add(256);  // [seq | pad], contiguous with level 0: one H2D copy brings both
     for (int l = 0; l < nl; l++) J->o_raw[l] = dv.add((size_t)L.w[l] * L.h[l]);
     for (int l = 0; l < nl; l++) J->o_blur[l] = dv.add((size_t)L.w[l] * L.h[l]);
+    J->o_ctr = dv.add(ORB_MAX_LEVELS * 4);
     dev_bytes = dv.off;
     J->dev_base = (size_t)j * dev_bytes;
     OPacker hs;
+    J->h_hdr = hs.add(256);
     J->h_img = hs.add((size_t)width * height);
+    J->h_flag = hs.add(ORB_MAX_LEVELS * 4);
     J->h_cnt = hs.add((size_t)n_cells * 4);
     J->h_slots = hs.add((size_t)n_cells * slot_cap * 4);
     stage_bytes = hs.off;
@@ -647,8 +710,13 @@ struct OrbPipeline {
     return LORB_OK;
   }
 
-  // H2D of the frame, pyramid chain, FAST per cell (candidates land in pinned memory), event,
-  // then the blur (it overlaps the host's quadtree).
+  // The detection chain of one frame -- H2D of [seq | frame], then level after level: resize from
+  // the level above, FAST over the level's cells (candidates and a per-level "ready" flag land in
+  // mapped pinned host memory), finally the blur of all levels -- is 17 dependent operations.
+  // Issued one by one they cost the host ~80 us (measured: longer than the GPU needs to run them),
+  // so they are captured once per (frame size, parameters, buffers) into a CUDA graph and replayed
+  // with a single launch.  The host starts distributing level 0 while the GPU is still on the
+  // smaller levels.
   int detect(OrbJob* J) {
     OrbPlanDev& P = J->P;
     memset(&P, 0, sizeof(P));
@@ -657,6 +725,7 @@ struct OrbPipeline {
     P.min_th = min_th;
     int cells = 0, tiles = 0;
     uint8_t* d = c->d[3].as<uint8_t>() + J->dev_base;
+    uint8_t* hp = c->h[2].as<uint8_t>() + J->stage_base;
     for (int l = 0; l < nl; l++) {
       P.w[l] = L.w[l];
       P.h[l] = L.h[l];
@@ -674,16 +743,73 @@ struct OrbPipeline {
     P.tile_start[nl] = tiles;
     P.cell_start[nl] = cells;
     P.slot_cap = slot_cap;
-    uint8_t* hp = c->h[2].as<uint8_t>() + J->stage_base;
+    P.done_ctr = (int*)(d + J->o_ctr);
+    P.host_flag = (volatile unsigned*)(hp + J->h_flag);
+    P.seq = (const unsigned*)(d + J->o_hdr);
+    const bool with_blur = want_desc || J->O.blur_levels;
+
+    OrbGraph*& G = reinterpret_cast<OrbGraph*&>(c->orb_graph[J->slot]);
+    OrbGraphKey key;
+    memset(&key, 0, sizeof(key));
+    key.P = P;
+    key.stage = hp;
+    key.width = width;
+    key.height = height;
+    key.with_blur = with_blur;
+    if (!G || memcmp(&G->key, &key, sizeof(key)) != 0) {
+      if (G) {
+        cudaGraphExecDestroy(G->exec);
+        delete G;
+        G = nullptr;
+      }
+      LORB_CUDA_TRY(cudaStreamSynchronize(c->stream));
+      memset(hp + J->h_flag, 0, ORB_MAX_LEVELS * 4);  // fresh pinned memory holds anything
+      LORB_CUDA_TRY(cudaMemsetAsync(P.done_ctr, 0, ORB_MAX_LEVELS * 4, c->stream));
+      LORB_CUDA_TRY(cudaStreamSynchronize(c->stream));
+      const long long launches_before = c->launches;
+      LORB_CUDA_TRY(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+      int rc = capture_chain(J, hp, with_blur);
+      cudaGraph_t graph = nullptr;
+      cudaError_t ce = cudaStreamEndCapture(c->stream, &graph);
+      if (rc != LORB_OK) {
+        if (graph) cudaGraphDestroy(graph);
+        return rc;
+      }
+      LORB_CUDA_TRY(ce);
+      OrbGraph* ng = new OrbGraph();
+      ng->key = key;
+      ng->n_kernels = (int)(c->launches - launches_before);
+      c->launches = launches_before;  // captured, not launched
+      ce = cudaGraphInstantiate(&ng->exec, graph, 0);
+      cudaGraphDestroy(graph);
+      if (ce != cudaSuccess) {
+        delete ng;
+        LORB_CUDA_TRY(ce);
+      }
+      G = ng;
+    }
+    // stage [seq | frame] and replay
+    J->seq = ++c->orb_seq;
+    if (J->seq == 0) J->seq = ++c->orb_seq;  // 0 is what a fresh flag holds
+    *(unsigned*)(hp + J->h_hdr) = J->seq;
     if (J->step == width) {
       memcpy(hp + J->h_img, J->image, (size_t)width * height);
     } else {
       for (int r = 0; r < height; r++) memcpy(hp + J->h_img + (size_t)r * width, J->image + (size_t)r * J->step, width);
     }
-    LORB_CUDA_TRY(cudaMemcpyAsync(P.raw[0], hp + J->h_img, (size_t)width * height, cudaMemcpyHostToDevice, c->stream));
-    // Level after level: resize from the level above, FAST over the level's cells, "candidates of
-    // level l are in host memory" event.  The host starts distributing level 0 (the largest)
-    // while the GPU is still building the rest of the pyramid.
+    tr.mark("image staged");
+    LORB_CUDA_TRY(cudaGraphLaunch(G->exec, c->stream));
+    c->launches += G->n_kernels;
+    tr.mark("detect queued");
+    return LORB_OK;
+  }
+
+  int capture_chain(OrbJob* J, uint8_t* hp, bool with_blur) {
+    const OrbPlanDev& P = J->P;
+    uint8_t* d = c->d[3].as<uint8_t>() + J->dev_base;
+    // the header and level 0 are contiguous on both sides
+    LORB_CUDA_TRY(cudaMemcpyAsync(d + J->o_hdr, hp + J->h_hdr, 256 + (size_t)width * height, cudaMemcpyHostToDevice,
+                                  c->stream));
     for (int l = 0; l < nl; l++) {
       if (l > 0) {
         // scale = 1 / (dsize / ssize) in double, as cv::resize derives it from the two sizes
@@ -694,11 +820,8 @@ struct OrbPipeline {
       }
       LORB_LAUNCH(c, orb_fast_cells_kernel, P.cell_start[l + 1] - P.cell_start[l], 256, 0, P, P.cell_start[l],
                   (uint32_t*)(hp + J->h_slots), (int*)(hp + J->h_cnt));
-      cudaEvent_t& ev = c->orb_ev[J->slot][l];
-      if (!ev) LORB_CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-      LORB_CUDA_TRY(cudaEventRecord(ev, c->stream));
     }
-    if (want_desc || J->O.blur_levels) LORB_LAUNCH(c, orb_blur_kernel, n_tiles, 256, 0, P);
+    if (with_blur) LORB_LAUNCH(c, orb_blur_kernel, n_tiles, 256, 0, P);
     return LORB_OK;
   }
 
@@ -721,8 +844,20 @@ struct OrbPipeline {
   // Wait for the candidates of this job, run DistributeOctTree per level (:865-866).
   int select(OrbJob* J) {
     const int* cnt = (const int*)(c->h[2].as<uint8_t>() + J->stage_base + J->h_cnt);
+    volatile const unsigned* flag = (volatile const unsigned*)(c->h[2].as<uint8_t>() + J->stage_base + J->h_flag);
+    const unsigned seq = J->seq;
+    // spin on the level's flag in pinned memory (the GPU raises it microseconds after the launch;
+    // a kernel fault is caught by the deadline and reported by the stream afterwards)
     auto wait_level = [&](int l) -> int {
-      if (cudaEventSynchronize(c->orb_ev[J->slot][l]) != cudaSuccess) return 1;
+      const auto deadline = std::chrono::steady_clock::now() + std::chrono::seconds(10);
+      unsigned spins = 0;
+      while (flag[l] != seq) {
+        if ((++spins & 0xfff) == 0 && std::chrono::steady_clock::now() > deadline) return 1;
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+      }
+      std::atomic_thread_fence(std::memory_order_acquire);
       for (int k = J->P.cell_start[l]; k < J->P.cell_start[l + 1]; k++)
         if (cnt[k] < 0 || cnt[k] > slot_cap) return 2;
       return 0;
@@ -759,11 +894,14 @@ struct OrbPipeline {
           failed |= 1;
           continue;
         }
+        tr.mark("candidates arrived, level", l);
         level_keys(J, l, &J->keys[l]);
         const int min_b = ORB_EDGE - 3;
         distribute_quadtree(J->keys[l], min_b, L.w[l] - ORB_EDGE + 3, min_b, L.h[l] - ORB_EDGE + 3, L.n_features[l],
                             &J->chosen[l]);
+        tr.mark("quadtree done, level", l);
       }
+      tr.mark("all levels distributed");
       LORB_REQUIRE(!failed, "FAST kernel failed or candidate slot overflow (internal)");
       for (int l = 0; l < nl; l++) J->n_total += (int)J->chosen[l].size();
       if (O.n_out) *O.n_out = J->n_total;
@@ -818,6 +956,7 @@ struct OrbPipeline {
     J->d_desc = (const uint32_t*)(dout + J->o_desc);
     uint8_t* ho = c->h[1].as<uint8_t>() + J->kout_base;
     LORB_CUDA_TRY(cudaMemcpyAsync(ho, dout, kout_cap_bytes, cudaMemcpyDeviceToHost, c->stream));
+    tr.mark("describe queued");
     return LORB_OK;
   }
 
@@ -882,7 +1021,9 @@ int orb_run(lorb_ctx* c, const uint8_t* image, int width, int height, int step, 
   LORB_TRY(pl.describe(&J));
   LORB_TRY(pl.queue_level_copies(&J));
   LORB_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  pl.tr.mark("stream drained");
   pl.finish(&J);
+  pl.tr.mark("results scattered");
   return LORB_OK;
 }
 
