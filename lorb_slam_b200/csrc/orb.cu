@@ -424,9 +424,9 @@ __global__ void __launch_bounds__(256)
     __syncthreads();
   }
   }  // active
-  // publish: every thread's stores to host memory are fenced, then one thread counts the cell in;
-  // the last cell of the level raises the level's flag
-  __threadfence_system();
+  // publish (the pattern of a grid barrier): block barrier, then one thread fences at system
+  // scope -- cumulative over the block's stores to host memory it has synchronised with -- and
+  // counts the cell in; the last cell of the level raises the level's flag
   __syncthreads();
   if (threadIdx.x == 0) {
     cell_count[cell] = active ? s_base : 0;
