@@ -174,3 +174,60 @@ def test_stereo_frame_front_end(ctx, seed):
         assert np.array_equal(ra["desc"], L["desc"]) and np.array_equal(rb["x"], R["x"])
         rs = reflib.stereo_matches(st)
         assert nm == rs["n_matched"] and np.array_equal(ur, rs["uright"]) and np.array_equal(dp, rs["depth"])
+
+
+@pytest.mark.parametrize("kw", [dict(nlevels=1), dict(nlevels=4, scale_factor=1.5), dict(ini_th=40, min_th=12),
+                                dict(ini_th=9, min_th=9), dict(nfeatures=64), dict(nfeatures=3000, nlevels=6)],
+                         ids=["one_level", "sf1.5", "th40_12", "th9_9", "n64", "n3000_l6"])
+def test_cuda_orb_extract_parameters_vs_reference(ctx, kw):
+    """Non-default ORBextractor constructor arguments, and a strided (non-contiguous) input image."""
+    from oracle import reflib
+    if not reflib.available():
+        pytest.skip("oracle/_ref not built")
+    img = synth.make_orb_image(77, 700, 500)
+    view = img[6:486, 20:660]  # 640x480 window of a 700-px-wide buffer: step 700
+    assert not view.flags["C_CONTIGUOUS"]
+    prm = dict(nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7)
+    prm.update(kw)
+    b = reflib.orb_extract(np.ascontiguousarray(view), **prm)
+    cap = prm["nfeatures"] + 64
+    # the ctypes wrapper makes arrays contiguous; call the C ABI with the strided view directly
+    import ctypes as C
+    p = capi.OrbParams(prm["nfeatures"], prm["scale_factor"], prm["nlevels"], prm["ini_th"], prm["min_th"])
+    pat = np.ascontiguousarray(OC.pattern(), np.int32).reshape(-1)
+    kx, ky, ka, kr, ks = (np.zeros(cap, np.float32) for _ in range(5))
+    ko, desc, n = np.zeros(cap, np.int32), np.zeros((cap, 32), np.uint8), C.c_int(0)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    rc = ctx._lib.lorb_orb_extract(ctx._h, C.c_void_p(view.ctypes.data), 640, 480, int(view.strides[0]), C.byref(p),
+                                   vp(pat), cap, vp(kx), vp(ky), vp(ko), vp(ka), vp(kr), vp(ks), vp(desc), C.byref(n),
+                                   None)
+    assert rc == 0 and n.value == b["n"] > 0
+    m = n.value
+    assert np.array_equal(kx[:m], b["x"]) and np.array_equal(ky[:m], b["y"]) and np.array_equal(ko[:m], b["octave"])
+    assert np.array_equal(ka[:m], b["angle"]) and np.array_equal(kr[:m], b["response"])
+    assert np.array_equal(ks[:m], b["size"]) and np.array_equal(desc[:m], b["desc"])
+
+
+def test_cuda_orb_extract_repeatable_and_reentrant(ctx):
+    """Same frame twice, a different frame size in between (graph re-capture), a second context on
+    another host thread at the same time: always the same bits."""
+    import threading
+    img, other = synth.make_orb_image(3), synth.make_orb_image(4, 752, 480)
+    a = ctx.orb_extract(img, OC.pattern())
+    ctx.orb_extract(other, OC.pattern(), nfeatures=500)
+    b = ctx.orb_extract(img, OC.pattern())
+    res = {}
+
+    def worker():
+        with capi.Context(0) as c2:
+            for _ in range(5):
+                res["t"] = c2.orb_extract(img, OC.pattern())
+
+    t = threading.Thread(target=worker)
+    t.start()
+    for _ in range(5):
+        c = ctx.orb_extract(img, OC.pattern())
+    t.join()
+    for r in (b, c, res["t"]):
+        assert r["n"] == a["n"] and np.array_equal(r["desc"], a["desc"]) and np.array_equal(r["x"], a["x"])
+        assert np.array_equal(r["angle"], a["angle"])
