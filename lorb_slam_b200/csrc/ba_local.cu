@@ -23,8 +23,11 @@
 #include <omp.h>
 
 #include <algorithm>
+#include <chrono>
 #include <new>
 #include <vector>
+
+#include <cub/cub.cuh>
 
 #include "ba_math.cuh"
 #include "dist.cuh"
@@ -1963,7 +1966,7 @@ struct lorb_ba_problem {
   std::vector<lorb::BADev> h_dev;     // host copies of the per-window descriptors
   std::vector<int> h_cam_off, h_pt_off;
   lorb::Buf params, topo, work, descs, hstate, counter, lists, stage;
-  lorb::Buf pairs_stage;  // pinned host copy of the pair records (grow-only: no per-call allocation or zero fill)
+  lorb::Buf list_scratch, list_scratch2;  // device scratch of the work-list builder (grow-only)
   int max_cam_items = 0, max_pair_items = 0;
   bool has_dup = false;  // some point is observed twice by the same window camera
   double *cams0 = nullptr, *pts0 = nullptr;  // initial parameters of all windows
@@ -2009,8 +2012,238 @@ static void host_fix_rotation(const float* rt, double* R) {
   R[11] = rt[5];
 }
 
+// ---- work lists of the large path, built on the device -----------------------------------
+// The large path (6C > 96) needs, per window, the observations grouped by camera (cam_obs /
+// cam_items) and one record per pair of observations of the same point grouped by camera block
+// (pairs / pair_items; 6.4 M records = 100 MB for 200 keyframes / 1.5 M observations).  They are
+// derived from the point-major CSR that is uploaded anyway: building them on the host and
+// uploading them took 15 of the 19 ms a cached lorb_ba_local call spends before the first LM
+// iteration.  Order inside a group is the serial one (point, then observation ascending): records
+// are generated point by point and grouped by a STABLE radix sort on the group key, so the fp64
+// summation order of the consuming kernels does not depend on scheduling.
+__global__ void __launch_bounds__(256)
+    lists_count_kernel(int P, const int* __restrict__ ptr, const int* __restrict__ cam, int* __restrict__ obs_pt,
+                       int* __restrict__ pcount) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const int a = ptr[p], b = ptr[p + 1];
+  int n = 0;
+  for (int e1 = a; e1 < b; e1++) {
+    obs_pt[e1] = p;
+    const int c1 = cam[e1];
+    if (c1 < 0) continue;
+    for (int e2 = a; e2 < b; e2++) n += cam[e2] >= c1;
+  }
+  pcount[p] = n;
+}
+
+__global__ void __launch_bounds__(256)
+    lists_gen_pairs_kernel(int P, int C, const int* __restrict__ ptr, const int* __restrict__ cam,
+                           const int* __restrict__ poff, uint32_t* __restrict__ key, uint32_t* __restrict__ idx,
+                           int4* __restrict__ rec, int* __restrict__ kcnt) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const int a = ptr[p], b = ptr[p + 1];
+  int i = poff[p];
+  for (int e1 = a; e1 < b; e1++) {
+    const int c1 = cam[e1];
+    if (c1 < 0) continue;
+    for (int e2 = a; e2 < b; e2++) {
+      const int c2 = cam[e2];
+      if (c2 < c1) continue;
+      const uint32_t k = (uint32_t)c1 * C + c2;
+      key[i] = k;
+      idx[i] = i;
+      rec[i] = make_int4(p, e1, e2, 0);
+      atomicAdd(&kcnt[k], 1);
+      i++;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    lists_gather_pairs_kernel(int n, const uint32_t* __restrict__ idx, const int4* __restrict__ rec,
+                              int4* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = rec[idx[i]];
+}
+
+__global__ void __launch_bounds__(256)
+    lists_cam_keys_kernel(int OT, int C, const int* __restrict__ cam, uint32_t* __restrict__ key,
+                          uint32_t* __restrict__ val, int* __restrict__ ccnt) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= OT) return;
+  const int c1 = cam[e];
+  key[e] = c1 >= 0 ? (uint32_t)c1 : (uint32_t)C;  // fixed observers sort behind every camera
+  val[e] = e;
+  if (c1 >= 0) atomicAdd(&ccnt[c1], 1);
+}
+
+__global__ void __launch_bounds__(256)
+    lists_cam_obs_kernel(int n_valid, const uint32_t* __restrict__ val, const int* __restrict__ obs_pt,
+                         int2* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_valid) out[i] = make_int2((int)val[i], obs_pt[val[i]]);
+}
+
+// nitems[k] = number of items of group k (chunks of `chunk` records)
+__global__ void __launch_bounds__(256)
+    lists_item_count_kernel(int n_groups, const int* __restrict__ cnt, int chunk, int* __restrict__ nitems) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n_groups) nitems[k] = (cnt[k] + chunk - 1) / chunk;
+}
+
+// items of group k: (a, b, start, length) with (a, b) = (k / C, k % C) for pair blocks (C > 0) or
+// (k, start, length, 0) for cameras (C == 0)
+__global__ void __launch_bounds__(256)
+    lists_item_write_kernel(int n_groups, int C, const int* __restrict__ cnt, const int* __restrict__ start,
+                            const int* __restrict__ ioff, int chunk, int4* __restrict__ items) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_groups) return;
+  const int n = cnt[k], s0 = start[k];
+  int o = ioff[k];
+  for (int st = 0; st < n; st += chunk, o++) {
+    const int len = min(chunk, n - st);
+    items[o] = C > 0 ? make_int4(k / C, k % C, s0 + st, len) : make_int4(k, s0 + st, len, 0);
+  }
+}
+
+struct DevListCounts {
+  int n_cam_obs, n_cam_items, n_pair_items;
+  long long n_pairs;
+};
+
+static int log2_ceil(unsigned v) {
+  int b = 1;
+  while (b < 32 && (1u << b) < v) b++;
+  return b;
+}
+
+// Phase 1 of a window: obs_pt, the camera-major lists (sizes bounded by OT) and the number of
+// pair records.  Phase 2: the pair records and their items into `pairs` / `pair_items`.
+struct DevListBuilder {
+  lorb_ctx* c;
+  Buf* scratch;
+  cudaStream_t s;
+
+  template <typename T>
+  static T* carve(uint8_t*& p, size_t n) {
+    T* r = reinterpret_cast<T*>(p);
+    p += (n * sizeof(T) + 255) & ~(size_t)255;
+    return r;
+  }
+
+  int phase1(int C, int P, int OT, const int* d_ptr, const int* d_cam, int* obs_pt, int2* cam_obs, int4* cam_items,
+             int cam_items_cap, int** poff_out, DevListCounts* out) {
+    // scratch: pcount / poff [P+1], keys / vals x2 [OT], ccnt / cstart / nitems / ioff [C+2], cub temp
+    size_t tmp_sort = 0, tmp_scan = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr,
+                                    (uint32_t*)nullptr, OT, 0, log2_ceil(C + 1), s);
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_scan, (int*)nullptr, (int*)nullptr, std::max(P, C) + 2, s);
+    const size_t tmp = std::max(tmp_sort, tmp_scan);
+    const size_t need = 2 * al((size_t)(P + 2) * 4) + 4 * al((size_t)std::max(OT, 1) * 4) + 4 * al((size_t)(C + 2) * 4) +
+                        al(tmp) + 1024;
+    LORB_TRY(scratch->reserve(need));
+    uint8_t* q = scratch->as<uint8_t>();
+    int* pcount = carve<int>(q, P + 2);
+    int* poff = carve<int>(q, P + 2);
+    uint32_t* k0 = carve<uint32_t>(q, std::max(OT, 1));
+    uint32_t* k1 = carve<uint32_t>(q, std::max(OT, 1));
+    uint32_t* v0 = carve<uint32_t>(q, std::max(OT, 1));
+    uint32_t* v1 = carve<uint32_t>(q, std::max(OT, 1));
+    int* ccnt = carve<int>(q, C + 2);
+    int* cstart = carve<int>(q, C + 2);
+    int* nitems = carve<int>(q, C + 2);
+    int* ioff = carve<int>(q, C + 2);
+    void* cub_tmp = q;
+    LORB_CUDA_TRY(cudaMemsetAsync(pcount, 0, (size_t)(P + 2) * 4, s));
+    LORB_CUDA_TRY(cudaMemsetAsync(ccnt, 0, (size_t)(C + 2) * 4, s));
+    LORB_LAUNCH(c, lists_count_kernel, (P + 255) / 256, 256, 0, P, d_ptr, d_cam, obs_pt, pcount);
+    size_t t1 = tmp;
+    LORB_CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp, t1, pcount, poff, P + 1, s));
+    // observations grouped by camera
+    LORB_LAUNCH(c, lists_cam_keys_kernel, (OT + 255) / 256, 256, 0, OT, C, d_cam, k0, v0, ccnt);
+    t1 = tmp;
+    LORB_CUDA_TRY(cub::DeviceRadixSort::SortPairs(cub_tmp, t1, k0, k1, v0, v1, OT, 0, log2_ceil(C + 1), s));
+    t1 = tmp;
+    LORB_CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp, t1, ccnt, cstart, C + 1, s));
+    LORB_LAUNCH(c, lists_item_count_kernel, (C + 255) / 256, 256, 0, C, ccnt, 1024, nitems);
+    t1 = tmp;
+    LORB_CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp, t1, nitems, ioff, C + 1, s));
+    int h[3];
+    LORB_CUDA_TRY(cudaMemcpyAsync(&h[0], poff + P, 4, cudaMemcpyDeviceToHost, s));
+    LORB_CUDA_TRY(cudaMemcpyAsync(&h[1], cstart + C, 4, cudaMemcpyDeviceToHost, s));
+    LORB_CUDA_TRY(cudaMemcpyAsync(&h[2], ioff + C, 4, cudaMemcpyDeviceToHost, s));
+    LORB_CUDA_TRY(cudaStreamSynchronize(s));
+    LORB_REQUIRE(h[0] >= 0 && h[1] >= 0 && h[1] <= OT && h[2] <= cam_items_cap, "work list sizes (internal)");
+    LORB_LAUNCH(c, lists_cam_obs_kernel, (h[1] + 255) / 256 + 1, 256, 0, h[1], v1, obs_pt, cam_obs);
+    LORB_LAUNCH(c, lists_item_write_kernel, (C + 255) / 256, 256, 0, C, 0, ccnt, cstart, ioff, 1024, cam_items);
+    out->n_pairs = h[0];
+    out->n_cam_obs = h[1];
+    out->n_cam_items = h[2];
+    *poff_out = poff;  // stays valid until the next phase1 call
+    return LORB_OK;
+  }
+
+  // pairs [n_pairs], pair_items [<= n_pairs / 2048 + C*(C+1)/2]; scratch2 holds keys, indices, records
+  int phase2(int C, int P, int n_pairs, const int* d_ptr, const int* d_cam, const int* poff, Buf* scratch2,
+             int4* pairs, int4* pair_items, int pair_items_cap, int* n_pair_items) {
+    *n_pair_items = 0;
+    if (n_pairs == 0) return LORB_OK;
+    const int nblk = C * C;
+    size_t tmp_sort = 0, tmp_scan = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr,
+                                    (uint32_t*)nullptr, n_pairs, 0, log2_ceil(nblk), s);
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_scan, (int*)nullptr, (int*)nullptr, nblk + 2, s);
+    const size_t tmp = std::max(tmp_sort, tmp_scan);
+    const size_t need = 4 * al((size_t)n_pairs * 4) + al((size_t)n_pairs * 16) + 4 * al((size_t)(nblk + 2) * 4) + al(tmp) + 1024;
+    LORB_TRY(scratch2->reserve(need));
+    uint8_t* q = scratch2->as<uint8_t>();
+    uint32_t* k0 = carve<uint32_t>(q, n_pairs);
+    uint32_t* k1 = carve<uint32_t>(q, n_pairs);
+    uint32_t* v0 = carve<uint32_t>(q, n_pairs);
+    uint32_t* v1 = carve<uint32_t>(q, n_pairs);
+    int4* rec = carve<int4>(q, n_pairs);
+    int* kcnt = carve<int>(q, nblk + 2);
+    int* kstart = carve<int>(q, nblk + 2);
+    int* nitems = carve<int>(q, nblk + 2);
+    int* ioff = carve<int>(q, nblk + 2);
+    void* cub_tmp = q;
+    LORB_CUDA_TRY(cudaMemsetAsync(kcnt, 0, (size_t)(nblk + 2) * 4, s));
+    LORB_LAUNCH(c, lists_gen_pairs_kernel, (P + 255) / 256, 256, 0, P, C, d_ptr, d_cam, poff, k0, v0, rec, kcnt);
+    size_t t1 = tmp;
+    LORB_CUDA_TRY(cub::DeviceRadixSort::SortPairs(cub_tmp, t1, k0, k1, v0, v1, n_pairs, 0, log2_ceil(nblk), s));
+    LORB_LAUNCH(c, lists_gather_pairs_kernel, (n_pairs + 255) / 256, 256, 0, n_pairs, v1, rec, pairs);
+    t1 = tmp;
+    LORB_CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp, t1, kcnt, kstart, nblk + 1, s));
+    LORB_LAUNCH(c, lists_item_count_kernel, (nblk + 255) / 256, 256, 0, nblk, kcnt, 2048, nitems);
+    t1 = tmp;
+    LORB_CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp, t1, nitems, ioff, nblk + 1, s));
+    int h = 0;
+    LORB_CUDA_TRY(cudaMemcpyAsync(&h, ioff + nblk, 4, cudaMemcpyDeviceToHost, s));
+    LORB_CUDA_TRY(cudaStreamSynchronize(s));
+    LORB_REQUIRE(h >= 0 && h <= pair_items_cap, "pair item count (internal)");
+    LORB_LAUNCH(c, lists_item_write_kernel, (nblk + 255) / 256, 256, 0, nblk, C, kcnt, kstart, ioff, 2048, pair_items);
+    *n_pair_items = h;
+    return LORB_OK;
+  }
+};
+
+// LORB_BA_TRACE=1: host timeline of problem_build on stderr (microseconds since it started)
+struct BuildTrace {
+  bool on;
+  std::chrono::steady_clock::time_point t0;
+  BuildTrace() : on(getenv("LORB_BA_TRACE") != nullptr), t0(std::chrono::steady_clock::now()) {}
+  void mark(const char* what) const {
+    if (!on) return;
+    fprintf(stderr, "[ba build %9.1f us] %s\n",
+            std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count(), what);
+  }
+};
+
 static int problem_build(lorb_ba_problem* pb, lorb_ctx* c, const std::vector<WindowSpec>& ws,
                          const float* K) {
+  const BuildTrace btr;
   pb->ctx = c;
   const int nw = (int)ws.size();
   pb->nw = nw;
@@ -2058,13 +2291,12 @@ static int problem_build(lorb_ba_problem* pb, lorb_ctx* c, const std::vector<Win
   double* h_pts = reinterpret_cast<double*>(sg + sb_ptr + sb_cam + sb_uv + sb_fix + sb_cams);
   std::vector<size_t> o_ptr(nw), o_obs(nw), o_fix(nw);
   // large-path work lists (windows with 6C > 96), concatenated over windows
-  std::vector<int> h_obs_pt;
-  std::vector<int2> h_cam_obs;
-  std::vector<int4> h_cam_items, h_pair_items;
-  int4* h_pairs = nullptr;  // in pb->pairs_stage
-  size_t n_pairs_total = 0;
-  struct ListOff { size_t obs_pt, cam_obs, cam_items, pairs, pair_items; int n_cam_items, n_pair_items; };
-  std::vector<ListOff> lo(nw, ListOff{0, 0, 0, 0, 0, 0, 0});
+  struct ListOff {
+    size_t obs_pt, cam_obs, cam_items, pairs, pair_items;
+    int n_cam_items, n_pair_items, large;
+    long long n_pairs;
+  };
+  std::vector<ListOff> lo(nw, ListOff{0, 0, 0, 0, 0, 0, 0, 0, 0});
   pb->max_cam_items = pb->max_pair_items = 0;
   pb->has_dup = false;
   {
@@ -2175,130 +2407,29 @@ static int problem_build(lorb_ba_problem* pb, lorb_ctx* c, const std::vector<Win
         if (dup) dup_any |= 1;
       }
       if (6 * W.C > 96) {
-        const int OT = W.O + W.F;
+        // large path: the work lists are built on the device from the CSR (DevListBuilder); the
+        // host only counts the pair records so that every buffer can be sized before the uploads
+        btr.mark("csr staged");
         const int* cam = &h_cam[b];
-        ListOff& L = lo[w];
-        L.obs_pt = h_obs_pt.size();
-        h_obs_pt.resize(L.obs_pt + OT);
-        {
-          int* const op = &h_obs_pt[L.obs_pt];
-#pragma omp parallel for schedule(static) if (big)
-          for (int pp = 0; pp < W.P; pp++)
-            for (int e = ptr[pp]; e < ptr[pp + 1]; e++) op[e] = pp;
-        }
-        // observations grouped by camera (stable counting sort: one histogram per host thread over a
-        // static slice of the observations, so the order is the serial one), items of <= 1024
-        const int nthc = big ? std::max(1, std::min(omp_get_max_threads(), 64)) : 1;
-        std::vector<int> cnt((size_t)W.C + 1, 0);
-        std::vector<int> tcc((size_t)nthc * W.C, 0);
-        auto e_lo = [&](int t) { return (int)((long long)OT * t / nthc); };
-#pragma omp parallel for schedule(static, 1) num_threads(nthc) if (big)
-        for (int t = 0; t < nthc; t++) {
-          int* mine = &tcc[(size_t)t * W.C];
-          for (int e = e_lo(t); e < e_lo(t + 1); e++)
-            if (cam[e] >= 0) mine[cam[e]]++;
-        }
-        for (int c2 = 0; c2 < W.C; c2++) {
-          int run = cnt[c2];
-          for (int t = 0; t < nthc; t++) {  // exclusive offset of thread t inside camera c2
-            const int k2 = tcc[(size_t)t * W.C + c2];
-            tcc[(size_t)t * W.C + c2] = run;
-            run += k2;
+        long long np = 0;
+#pragma omp parallel for schedule(static) reduction(+ : np) if (big)
+        for (int pp = 0; pp < W.P; pp++)
+          for (int e1 = ptr[pp]; e1 < ptr[pp + 1]; e1++) {
+            if (cam[e1] < 0) continue;
+            for (int e2 = ptr[pp]; e2 < ptr[pp + 1]; e2++) np += cam[e2] >= cam[e1];
           }
-          cnt[c2 + 1] = run;
-        }
-        L.cam_obs = h_cam_obs.size();
-        h_cam_obs.resize(L.cam_obs + cnt[W.C]);
-        {
-          int2* const co = &h_cam_obs[L.cam_obs];
-          const int* const op = &h_obs_pt[L.obs_pt];
-#pragma omp parallel for schedule(static, 1) num_threads(nthc) if (big)
-          for (int t = 0; t < nthc; t++) {
-            int* cur = &tcc[(size_t)t * W.C];
-            for (int e = e_lo(t); e < e_lo(t + 1); e++)
-              if (cam[e] >= 0) co[cur[cam[e]]++] = make_int2(e, op[e]);
-          }
-        }
-        L.cam_items = h_cam_items.size();
-        for (int c2 = 0; c2 < W.C; c2++)
-          for (int st0 = cnt[c2]; st0 < cnt[c2 + 1]; st0 += 1024)
-            h_cam_items.push_back(make_int4(c2, st0, std::min(1024, cnt[c2 + 1] - st0), 0));
-        L.n_cam_items = (int)(h_cam_items.size() - L.cam_items);
-        // pair records grouped by camera block (ci <= cj; equal cameras keep both orders), points
-        // ascending inside a block.  Counting sort over the points with one histogram per host thread
-        // (static point ranges), so the order does not depend on the thread count.
-        const int nth = std::max(1, std::min(omp_get_max_threads(), 64));
-        const size_t nblkC = (size_t)W.C * W.C;
-        std::vector<long long> kcnt(nblkC + 1, 0);
-        std::vector<long long> tcnt((size_t)nth * nblkC, 0);
-        auto p_lo = [&](int t) { return (int)((long long)W.P * t / nth); };
-#pragma omp parallel for schedule(static, 1) num_threads(nth)
-        for (int t = 0; t < nth; t++) {
-          long long* mine = &tcnt[(size_t)t * nblkC];
-          for (int pp = p_lo(t); pp < p_lo(t + 1); pp++)
-            for (int e1 = ptr[pp]; e1 < ptr[pp + 1]; e1++) {
-              if (cam[e1] < 0) continue;
-              for (int e2 = ptr[pp]; e2 < ptr[pp + 1]; e2++)
-                if (cam[e2] >= cam[e1]) mine[(size_t)cam[e1] * W.C + cam[e2]]++;
-            }
-        }
-        for (size_t k2 = 0; k2 < nblkC; k2++) {
-          long long run = kcnt[k2];
-          for (int t = 0; t < nth; t++) {  // exclusive offsets of thread t inside block k2
-            const long long c2 = tcnt[(size_t)t * nblkC + k2];
-            tcnt[(size_t)t * nblkC + k2] = run;
-            run += c2;
-          }
-          kcnt[k2 + 1] = run;
-        }
-        L.pairs = n_pairs_total;
-        {
-          const size_t need = (n_pairs_total + (size_t)kcnt[nblkC]) * sizeof(int4);
-          pb->pairs_stage.pinned = true;
-          if (need > pb->pairs_stage.cap) {  // grow, keeping the records of earlier windows
-            lorb::Buf nb2;
-            nb2.pinned = true;
-            if (nb2.reserve(need) != LORB_OK) {  // (no return from inside the OpenMP loop)
-              bad_obs |= 2;
-              continue;
-            }
-            if (n_pairs_total) memcpy(nb2.p, pb->pairs_stage.p, n_pairs_total * sizeof(int4));
-            pb->pairs_stage.release();
-            pb->pairs_stage = nb2;
-          }
-          h_pairs = pb->pairs_stage.as<int4>();
-          n_pairs_total += (size_t)kcnt[nblkC];
-        }
-#pragma omp parallel for schedule(static, 1) num_threads(nth)
-        for (int t = 0; t < nth; t++) {
-          long long* cur = &tcnt[(size_t)t * nblkC];
-          for (int pp = p_lo(t); pp < p_lo(t + 1); pp++)
-            for (int e1 = ptr[pp]; e1 < ptr[pp + 1]; e1++) {
-              if (cam[e1] < 0) continue;
-              for (int e2 = ptr[pp]; e2 < ptr[pp + 1]; e2++)
-                if (cam[e2] >= cam[e1])
-                  h_pairs[L.pairs + (size_t)cur[(size_t)cam[e1] * W.C + cam[e2]]++] = make_int4(pp, e1, e2, 0);
-            }
-        }
-        L.pair_items = h_pair_items.size();
-        for (int ci = 0; ci < W.C; ci++)
-          for (int cj = ci; cj < W.C; cj++) {
-            const long long s0 = kcnt[(size_t)ci * W.C + cj], s1 = kcnt[(size_t)ci * W.C + cj + 1];
-            for (long long st0 = s0; st0 < s1; st0 += 2048)
-              h_pair_items.push_back(make_int4(ci, cj, (int)st0, (int)std::min<long long>(2048, s1 - st0)));
-          }
-        L.n_pair_items = (int)(h_pair_items.size() - L.pair_items);
-        pb->max_cam_items = std::max(pb->max_cam_items, L.n_cam_items);
-        pb->max_pair_items = std::max(pb->max_pair_items, L.n_pair_items);
+        lo[w].large = 1;
+        lo[w].n_pairs = np;
+        btr.mark("pair records counted");
       }
       memcpy(&h_cams[6 * (size_t)pb->h_cam_off[w]], W.cams, (size_t)W.C * 48);
       if (W.P) memcpy(&h_pts[3 * (size_t)pb->h_pt_off[w]], W.pts, (size_t)W.P * 24);
     }
-    if (bad_obs & 2) return LORB_ERR_NOMEM;
     LORB_REQUIRE(!bad_obs, "observation index out of range");
     LORB_REQUIRE(!bad_fix, "fixed observation point out of range");
     pb->has_dup = dup_any != 0;
   }
+  btr.mark("staging done");
   // ---- device layout
   const size_t cb = al(pb->cam_doubles * 8), pbts = al(std::max<size_t>(pb->pt_doubles, 1) * 8);
   LORB_TRY(pb->params.reserve(3 * cb + 3 * pbts));
@@ -2372,47 +2503,88 @@ static int problem_build(lorb_ba_problem* pb, lorb_ctx* c, const std::vector<Win
       rot_off += (size_t)W.C * CAMROT;
     }
   }
+  cudaStream_t s = c->stream;
+  // the CSR goes up first: the device list builder reads it
+  LORB_CUDA_TRY(cudaMemcpyAsync(d_ptr, h_ptr, tot_ptr * 4, cudaMemcpyHostToDevice, s));
+  LORB_CUDA_TRY(cudaMemcpyAsync(d_ocam, h_cam, tot_obs * 4, cudaMemcpyHostToDevice, s));
+  pb->max_cam_items = pb->max_pair_items = 0;
   {
-    const size_t b0 = al(h_obs_pt.size() * 4), b1 = al(h_cam_obs.size() * 8),
-                 b2 = al(h_cam_items.size() * 16), b3 = al(n_pairs_total * 16),
-                 b4 = al(h_pair_items.size() * 16);
+    // layout of the list buffer: every size is known on the host
+    size_t n_obs_pt = 0, n_cam_obs = 0, n_cam_items = 0, n_pairs = 0, n_pair_items = 0;
+    long long max_pairs = 0;
+    for (int w = 0; w < nw; w++) {
+      ListOff& L = lo[w];
+      if (!L.large) continue;
+      const WindowSpec& W = ws[w];
+      const size_t OT = (size_t)W.O + W.F;
+      LORB_REQUIRE(L.n_pairs < (1ll << 31), "more than 2^31 pair records in one window");
+      L.obs_pt = n_obs_pt;
+      L.cam_obs = n_cam_obs;
+      L.cam_items = n_cam_items;
+      L.pairs = n_pairs;
+      L.pair_items = n_pair_items;
+      n_obs_pt += OT;
+      n_cam_obs += OT;
+      n_cam_items += (size_t)W.C + OT / 1024 + 1;
+      n_pairs += (size_t)L.n_pairs;
+      n_pair_items += (size_t)(L.n_pairs / 2048) + (size_t)W.C * (W.C + 1) / 2 + 1;
+      max_pairs = std::max(max_pairs, L.n_pairs);
+    }
+    const size_t b0 = al(n_obs_pt * 4), b1 = al(n_cam_obs * 8), b2 = al(n_cam_items * 16), b3 = al(n_pairs * 16),
+                 b4 = al(n_pair_items * 16);
     LORB_TRY(pb->lists.reserve(b0 + b1 + b2 + b3 + b4 + 256));
     uint8_t* lb = pb->lists.as<uint8_t>();
-    cudaStream_t s2 = c->stream;
-    if (!h_obs_pt.empty()) {
-      LORB_CUDA_TRY(cudaMemcpyAsync(lb, h_obs_pt.data(), h_obs_pt.size() * 4, cudaMemcpyHostToDevice, s2));
-      LORB_CUDA_TRY(cudaMemcpyAsync(lb + b0, h_cam_obs.data(), h_cam_obs.size() * 8, cudaMemcpyHostToDevice, s2));
-      LORB_CUDA_TRY(cudaMemcpyAsync(lb + b0 + b1, h_cam_items.data(), h_cam_items.size() * 16, cudaMemcpyHostToDevice, s2));
-      if (n_pairs_total)
-        LORB_CUDA_TRY(cudaMemcpyAsync(lb + b0 + b1 + b2, h_pairs, n_pairs_total * 16, cudaMemcpyHostToDevice, s2));
-      LORB_CUDA_TRY(cudaMemcpyAsync(lb + b0 + b1 + b2 + b3, h_pair_items.data(), h_pair_items.size() * 16, cudaMemcpyHostToDevice, s2));
-      LORB_CUDA_TRY(cudaStreamSynchronize(s2));
-    }
+    DevListBuilder bld{c, &pb->list_scratch, s};
     for (int w = 0; w < nw; w++) {
       BADev& d = pb->h_dev[w];
-      const ListOff& L = lo[w];
-      d.obs_pt = reinterpret_cast<const int*>(lb) + L.obs_pt;
-      d.cam_obs = reinterpret_cast<const int2*>(lb + b0) + L.cam_obs;
-      d.cam_items = reinterpret_cast<const int4*>(lb + b0 + b1) + L.cam_items;
-      d.pairs = reinterpret_cast<const int4*>(lb + b0 + b1 + b2) + L.pairs;
-      d.pair_items = reinterpret_cast<const int4*>(lb + b0 + b1 + b2 + b3) + L.pair_items;
+      ListOff& L = lo[w];
+      d.obs_pt = nullptr;
+      d.cam_obs = nullptr;
+      d.cam_items = nullptr;
+      d.pairs = nullptr;
+      d.pair_items = nullptr;
+      d.n_cam_items = d.n_pair_items = 0;
+      if (!L.large) continue;
+      const WindowSpec& W = ws[w];
+      const int OT = W.O + W.F;
+      int* obs_pt = reinterpret_cast<int*>(lb) + L.obs_pt;
+      int2* cam_obs = reinterpret_cast<int2*>(lb + b0) + L.cam_obs;
+      int4* cam_items = reinterpret_cast<int4*>(lb + b0 + b1) + L.cam_items;
+      int4* pairs = reinterpret_cast<int4*>(lb + b0 + b1 + b2) + L.pairs;
+      int4* pair_items = reinterpret_cast<int4*>(lb + b0 + b1 + b2 + b3) + L.pair_items;
+      const int* w_ptr = d_ptr + o_ptr[w];
+      const int* w_cam = d_ocam + o_obs[w];
+      DevListCounts cnt{};
+      int* poff = nullptr;
+      LORB_TRY(bld.phase1(W.C, W.P, OT, w_ptr, w_cam, obs_pt, cam_obs, cam_items, W.C + OT / 1024 + 1, &poff, &cnt));
+      LORB_REQUIRE(cnt.n_pairs == L.n_pairs, "pair record count differs between host and device (internal)");
+      LORB_TRY(bld.phase2(W.C, W.P, (int)L.n_pairs, w_ptr, w_cam, poff, &pb->list_scratch2, pairs, pair_items,
+                          (int)(L.n_pairs / 2048) + W.C * (W.C + 1) / 2 + 1, &L.n_pair_items));
+      L.n_cam_items = cnt.n_cam_items;
+      d.obs_pt = obs_pt;
+      d.cam_obs = cam_obs;
+      d.cam_items = cam_items;
+      d.pairs = pairs;
+      d.pair_items = pair_items;
       d.n_cam_items = L.n_cam_items;
       d.n_pair_items = L.n_pair_items;
+      pb->max_cam_items = std::max(pb->max_cam_items, L.n_cam_items);
+      pb->max_pair_items = std::max(pb->max_pair_items, L.n_pair_items);
     }
+    btr.mark("device work lists");
   }
   LORB_TRY(pb->descs.reserve(sizeof(BADev) * (size_t)nw));
   LORB_TRY(pb->counter.reserve(256));
   pb->hstate.pinned = true;
   LORB_TRY(pb->hstate.reserve(sizeof(LMState) * (size_t)nw + 64));
-  cudaStream_t s = c->stream;
   LORB_CUDA_TRY(cudaMemcpyAsync(pb->descs.p, pb->h_dev.data(), sizeof(BADev) * (size_t)nw, cudaMemcpyHostToDevice, s));
   LORB_CUDA_TRY(cudaMemcpyAsync(pb->cams0, h_cams, pb->cam_doubles * 8, cudaMemcpyHostToDevice, s));
   LORB_CUDA_TRY(cudaMemcpyAsync(pb->pts0, h_pts, pb->pt_doubles * 8, cudaMemcpyHostToDevice, s));
-  LORB_CUDA_TRY(cudaMemcpyAsync(d_ptr, h_ptr, tot_ptr * 4, cudaMemcpyHostToDevice, s));
-  LORB_CUDA_TRY(cudaMemcpyAsync(d_ocam, h_cam, tot_obs * 4, cudaMemcpyHostToDevice, s));
   LORB_CUDA_TRY(cudaMemcpyAsync(d_uv, h_uv, tot_obs * 8, cudaMemcpyHostToDevice, s));
   LORB_CUDA_TRY(cudaMemcpyAsync(d_fix, h_fix, tot_fix * 96, cudaMemcpyHostToDevice, s));
+  btr.mark("uploads queued");
   LORB_CUDA_TRY(cudaStreamSynchronize(s));  // host staging vectors go out of scope
+  btr.mark("uploads done");
   return LORB_OK;
 }
 
@@ -2665,7 +2837,8 @@ static void problem_free(lorb_ba_problem* pb) {
   pb->descs.release();
   pb->lists.release();
   pb->stage.release();
-  pb->pairs_stage.release();
+  pb->list_scratch.release();
+  pb->list_scratch2.release();
   pb->hstate.release();
   pb->counter.release();
   delete pb;

@@ -11,7 +11,10 @@ from lorb_slam_b200 import capi, synth  # noqa: E402
 pb = synth.make_ba_problem(0, C=200, P=200000, obs_per_point=(7, 8), traj_len=100.0)
 opt = capi.ba_options(max_num_iterations=10, function_tolerance=0.0, gradient_tolerance=0.0, parameter_tolerance=0.0)
 with capi.Context(0) as ctx:
+    import os
     for rep in range(4):
+        if rep == 3:
+            os.environ["LORB_BA_TRACE"] = "1"
         t0 = time.perf_counter()
         prob = ctx.ba_problem(pb)
         ctx.sync()
