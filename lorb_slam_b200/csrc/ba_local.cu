@@ -2126,6 +2126,8 @@ struct DevListBuilder {
   Buf* scratch;
   cudaStream_t s;
 
+  static int nblocks(long long n) { return (int)std::max<long long>(1, (n + 255) / 256); }  // empty inputs still launch
+
   template <typename T>
   static T* carve(uint8_t*& p, size_t n) {
     T* r = reinterpret_cast<T*>(p);
@@ -2158,16 +2160,16 @@ struct DevListBuilder {
     void* cub_tmp = q;
     LORB_CUDA_TRY(cudaMemsetAsync(pcount, 0, (size_t)(P + 2) * 4, s));
     LORB_CUDA_TRY(cudaMemsetAsync(ccnt, 0, (size_t)(C + 2) * 4, s));
-    LORB_LAUNCH(c, lists_count_kernel, (P + 255) / 256, 256, 0, P, d_ptr, d_cam, obs_pt, pcount);
+    LORB_LAUNCH(c, lists_count_kernel, nblocks(P), 256, 0, P, d_ptr, d_cam, obs_pt, pcount);
     size_t t1 = tmp;
     LORB_CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp, t1, pcount, poff, P + 1, s));
     // observations grouped by camera
-    LORB_LAUNCH(c, lists_cam_keys_kernel, (OT + 255) / 256, 256, 0, OT, C, d_cam, k0, v0, ccnt);
+    LORB_LAUNCH(c, lists_cam_keys_kernel, nblocks(OT), 256, 0, OT, C, d_cam, k0, v0, ccnt);
     t1 = tmp;
     LORB_CUDA_TRY(cub::DeviceRadixSort::SortPairs(cub_tmp, t1, k0, k1, v0, v1, OT, 0, log2_ceil(C + 1), s));
     t1 = tmp;
     LORB_CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp, t1, ccnt, cstart, C + 1, s));
-    LORB_LAUNCH(c, lists_item_count_kernel, (C + 255) / 256, 256, 0, C, ccnt, 1024, nitems);
+    LORB_LAUNCH(c, lists_item_count_kernel, nblocks(C), 256, 0, C, ccnt, 1024, nitems);
     t1 = tmp;
     LORB_CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp, t1, nitems, ioff, C + 1, s));
     int h[3];
@@ -2176,8 +2178,8 @@ struct DevListBuilder {
     LORB_CUDA_TRY(cudaMemcpyAsync(&h[2], ioff + C, 4, cudaMemcpyDeviceToHost, s));
     LORB_CUDA_TRY(cudaStreamSynchronize(s));
     LORB_REQUIRE(h[0] >= 0 && h[1] >= 0 && h[1] <= OT && h[2] <= cam_items_cap, "work list sizes (internal)");
-    LORB_LAUNCH(c, lists_cam_obs_kernel, (h[1] + 255) / 256 + 1, 256, 0, h[1], v1, obs_pt, cam_obs);
-    LORB_LAUNCH(c, lists_item_write_kernel, (C + 255) / 256, 256, 0, C, 0, ccnt, cstart, ioff, 1024, cam_items);
+    LORB_LAUNCH(c, lists_cam_obs_kernel, nblocks(h[1]), 256, 0, h[1], v1, obs_pt, cam_obs);
+    LORB_LAUNCH(c, lists_item_write_kernel, nblocks(C), 256, 0, C, 0, ccnt, cstart, ioff, 1024, cam_items);
     out->n_pairs = h[0];
     out->n_cam_obs = h[1];
     out->n_cam_items = h[2];
@@ -2210,20 +2212,20 @@ struct DevListBuilder {
     int* ioff = carve<int>(q, nblk + 2);
     void* cub_tmp = q;
     LORB_CUDA_TRY(cudaMemsetAsync(kcnt, 0, (size_t)(nblk + 2) * 4, s));
-    LORB_LAUNCH(c, lists_gen_pairs_kernel, (P + 255) / 256, 256, 0, P, C, d_ptr, d_cam, poff, k0, v0, rec, kcnt);
+    LORB_LAUNCH(c, lists_gen_pairs_kernel, nblocks(P), 256, 0, P, C, d_ptr, d_cam, poff, k0, v0, rec, kcnt);
     size_t t1 = tmp;
     LORB_CUDA_TRY(cub::DeviceRadixSort::SortPairs(cub_tmp, t1, k0, k1, v0, v1, n_pairs, 0, log2_ceil(nblk), s));
-    LORB_LAUNCH(c, lists_gather_pairs_kernel, (n_pairs + 255) / 256, 256, 0, n_pairs, v1, rec, pairs);
+    LORB_LAUNCH(c, lists_gather_pairs_kernel, nblocks(n_pairs), 256, 0, n_pairs, v1, rec, pairs);
     t1 = tmp;
     LORB_CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp, t1, kcnt, kstart, nblk + 1, s));
-    LORB_LAUNCH(c, lists_item_count_kernel, (nblk + 255) / 256, 256, 0, nblk, kcnt, 2048, nitems);
+    LORB_LAUNCH(c, lists_item_count_kernel, nblocks(nblk), 256, 0, nblk, kcnt, 2048, nitems);
     t1 = tmp;
     LORB_CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp, t1, nitems, ioff, nblk + 1, s));
     int h = 0;
     LORB_CUDA_TRY(cudaMemcpyAsync(&h, ioff + nblk, 4, cudaMemcpyDeviceToHost, s));
     LORB_CUDA_TRY(cudaStreamSynchronize(s));
     LORB_REQUIRE(h >= 0 && h <= pair_items_cap, "pair item count (internal)");
-    LORB_LAUNCH(c, lists_item_write_kernel, (nblk + 255) / 256, 256, 0, nblk, C, kcnt, kstart, ioff, 2048, pair_items);
+    LORB_LAUNCH(c, lists_item_write_kernel, nblocks(nblk), 256, 0, nblk, C, kcnt, kstart, ioff, 2048, pair_items);
     *n_pair_items = h;
     return LORB_OK;
   }

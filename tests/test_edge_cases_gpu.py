@@ -125,3 +125,37 @@ def test_profile_brackets_and_fp64_microbench(ctx):
     ctx.ba_local(pb, capi.ba_options(max_num_iterations=2))
     assert ctx.profile_read(0)[1] == s["iterations"]  # nothing recorded while disabled
     assert ctx.microbench_fp64(0, 64) > 1e12 and ctx.microbench_fp64(1, 64) > 1e12
+
+
+def test_large_path_device_work_lists_edge_cases(ctx):
+    """Windows on the work-list path (6C > 96), whose lists are built on the device: duplicate
+    (point, camera) observations, fixed out-of-window observers, unsorted observation order,
+    cameras without observations, and a window with no points at all."""
+    kw = dict(max_num_iterations=5)
+    pb = synth.make_ba_problem(21, C=20, P=260, obs_per_point=(2, 3, 9), fixed_frac=0.15, traj_len=6.0)
+    dup = np.flatnonzero(pb["obs_pt"] % 17 == 0)
+    pb["obs_cam"] = np.concatenate([pb["obs_cam"], pb["obs_cam"][dup]]).astype(np.int32)
+    pb["obs_pt"] = np.concatenate([pb["obs_pt"], pb["obs_pt"][dup]]).astype(np.int32)
+    pb["obs_uv"] = np.concatenate([pb["obs_uv"], pb["obs_uv"][dup] + np.float32(0.25)]).astype(np.float32)
+    perm = np.random.default_rng(5).permutation(len(pb["obs_pt"]))  # not grouped by point any more
+    for k in ("obs_cam", "obs_pt", "obs_uv"):
+        pb[k] = np.ascontiguousarray(pb[k][perm])
+    pb["O"] = len(pb["obs_pt"])
+    # cameras 18 and 19 lose all their observations (they stay in the system through the LM diagonal)
+    keep = pb["obs_cam"] < 18
+    for k in ("obs_cam", "obs_pt", "obs_uv"):
+        pb[k] = np.ascontiguousarray(pb[k][keep])
+    pb["O"] = len(pb["obs_pt"])
+    cams, pts, s = ctx.ba_local(pb, capi.ba_options(**kw))
+    oc, op, o = ref.ba_local(pb, ref.ba_options(**kw))
+    np.testing.assert_allclose(cams, oc, rtol=1e-6, atol=1e-8)
+    np.testing.assert_allclose(pts, op, rtol=1e-6, atol=1e-8)
+    assert s["iterations"] == o["iterations"] and s["termination"] == o["termination"]
+    # run-to-run: the lists come out of a stable sort, so the solve is reproducible to the bit
+    cams2, pts2, _ = ctx.ba_local(pb, capi.ba_options(**kw))
+    assert np.array_equal(cams, cams2) and np.array_equal(pts, pts2)
+    empty = dict(pb, pts=np.zeros((0, 3)), obs_cam=np.zeros(0, np.int32), obs_pt=np.zeros(0, np.int32),
+                 obs_uv=np.zeros((0, 2), np.float32), fix_pt=np.zeros(0, np.int32),
+                 fix_uv=np.zeros((0, 2), np.float32), fix_rt=np.zeros((0, 6), np.float32), O=0)
+    cams3, _, s3 = ctx.ba_local(empty, capi.ba_options(max_num_iterations=3))
+    assert s3["initial_cost"] == 0.0 and np.array_equal(cams3, pb["cams"])
