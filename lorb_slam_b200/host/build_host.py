@@ -29,7 +29,7 @@ def build(force=False):
     if not force and os.path.exists(OUT) and all(
             os.path.getmtime(p) <= os.path.getmtime(OUT) for p in _deps()):
         return OUT
-    cmd = ["/usr/bin/g++", "-std=c++11", "-O2", "-fPIC", "-shared", "-Wall", "-Wno-unused-variable",
+    cmd = ["/usr/bin/g++", "-std=c++11", "-O2", "-fPIC", "-shared", "-Wall", "-Wno-unused-variable", "-pthread",
            "-I", os.path.join(HERE, "shim"), "-o", OUT] + SRCS + [
         "-L", LIBDIR, "-llorb_cuda", "-Wl,-rpath,$ORIGIN"]
     r = subprocess.run(cmd, capture_output=True, text=True)

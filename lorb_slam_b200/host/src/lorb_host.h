@@ -1,5 +1,5 @@
-// lorb_host.h — glue shared by the drop-in Matcher / BA bodies: one lorb_ctx
-// per calling thread (the reference runs Matcher and the pose-only BA on the
+// lorb_host.h — glue shared by the drop-in Matcher / BA / ORBextractor bodies: one lorb_ctx
+// per calling thread (borrowed from a process-wide pool) (the reference runs Matcher and the pose-only BA on the
 // tracking thread and local BA on the mapper thread, example/main.cpp:36-37),
 // and a fatal-error policy: the reference has no error channel,
 // and a silent "0 matches" would hide a broken GPU path, so any non-zero C-ABI
@@ -8,30 +8,75 @@
 #define LORB_HOST_H
 #include <cstdio>
 #include <cstdlib>
+#include <mutex>
+#include <vector>
 
 #include "../../../include/lorb_cuda.h"
 
 namespace lorb_host {
-
-struct ThreadCtx {
-  lorb_ctx* ctx = nullptr;
-  ~ThreadCtx() {
-    if (ctx) lorb_ctx_destroy(ctx);
-  }
-};
 
 inline void die(const char* what, int rc) {
   std::fprintf(stderr, "[lorb] %s failed (status %d): %s\n", what, rc, lorb_last_error());
   std::abort();
 }
 
+// Contexts are pooled, not owned by threads: the reference starts fresh std::threads for every
+// frame (Frame::Frame, src/frame.cpp:42-45: one per image), and a context carries warm state worth
+// keeping -- stream, grow-only device / pinned buffers, the captured CUDA graph of the extractor.
+// A thread borrows a context on first use and hands it back when it exits; the pool destroys them
+// at process exit.  One context is never used by two threads at a time.
+class CtxPool {
+ public:
+  lorb_ctx* acquire() {
+    {
+      std::lock_guard<std::mutex> g(m_);
+      if (!free_.empty()) {
+        lorb_ctx* c = free_.back();
+        free_.pop_back();
+        return c;
+      }
+    }
+    lorb_ctx* c = nullptr;
+    const char* dev = std::getenv("LORB_DEVICE");
+    const int rc = lorb_ctx_create(dev ? std::atoi(dev) : 0, &c);
+    if (rc != LORB_OK) die("lorb_ctx_create", rc);
+    std::lock_guard<std::mutex> g(m_);
+    ++created_;
+    return c;
+  }
+  int created() {
+    std::lock_guard<std::mutex> g(m_);
+    return created_;
+  }
+  void release(lorb_ctx* c) {
+    std::lock_guard<std::mutex> g(m_);
+    free_.push_back(c);
+  }
+  ~CtxPool() {
+    for (lorb_ctx* c : free_) lorb_ctx_destroy(c);
+  }
+
+ private:
+  std::mutex m_;
+  std::vector<lorb_ctx*> free_;
+  int created_ = 0;
+};
+
+inline CtxPool& pool() {
+  static CtxPool p;  // one pool per process (inline function: shared by every translation unit)
+  return p;
+}
+
+struct ThreadCtx {
+  lorb_ctx* ctx = nullptr;
+  ~ThreadCtx() {
+    if (ctx) pool().release(ctx);
+  }
+};
+
 inline lorb_ctx* ctx() {
   static thread_local ThreadCtx t;
-  if (!t.ctx) {
-    const char* dev = std::getenv("LORB_DEVICE");
-    const int rc = lorb_ctx_create(dev ? std::atoi(dev) : 0, &t.ctx);
-    if (rc != LORB_OK) die("lorb_ctx_create", rc);
-  }
+  if (!t.ctx) t.ctx = pool().acquire();
   return t.ctx;
 }
 

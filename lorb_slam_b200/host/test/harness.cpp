@@ -5,8 +5,10 @@
 // compares those with the oracle.
 #include <cstring>
 #include <deque>
+#include <thread>
 
 #include "../include/ORBextractor.h"
+#include "../src/lorb_host.h"
 #include "../include/bundle_adjust.h"
 #include "../include/matcher.h"
 
@@ -266,6 +268,35 @@ int harness_orb_extract(const uint8_t* img, int w, int h, int nfeatures, int cap
 		out_pyr_sum[l] = s;
 	}
 	return n;
+}
+
+// Frame::Frame(imgLeft, imgRight, camera) extracts the two images on two freshly started threads
+// (reference src/frame.cpp:42-45) with two ORBextractor objects, every frame.  Runs that pattern
+// n_frames times; returns the number of GPU contexts the drop-in layer had to create (the pool
+// hands the same two back to the new threads) and the last frame's keypoint counts / descriptors.
+int harness_stereo_extract_threads(const uint8_t* left, const uint8_t* right, int w, int h, int nfeatures,
+                                   int n_frames, int cap, int* n_left, int* n_right, uint8_t* desc_left,
+                                   uint8_t* desc_right)
+{
+	cv::Mat imL(h, w, CV_8U), imR(h, w, CV_8U);
+	std::memcpy(imL.ptr<uint8_t>(), left, (size_t)w*h);
+	std::memcpy(imR.ptr<uint8_t>(), right, (size_t)w*h);
+	const int before = lorb_host::pool().created();
+	for(int f = 0; f < n_frames; f++)
+	{
+		ORBextractor exL(nfeatures, 1.2f, 8, 20, 7), exR(nfeatures, 1.2f, 8, 20, 7);
+		std::vector<cv::KeyPoint> kL, kR;
+		cv::Mat dL, dR;
+		std::thread tl([&]{ exL(imL, cv::Mat(), kL, dL); });
+		std::thread tr([&]{ exR(imR, cv::Mat(), kR, dR); });
+		tl.join();
+		tr.join();
+		*n_left = (int)kL.size();
+		*n_right = (int)kR.size();
+		for(int i = 0; i < *n_left && i < cap; i++) std::memcpy(desc_left + 32*(size_t)i, dL.ptr<uint8_t>(i), 32);
+		for(int i = 0; i < *n_right && i < cap; i++) std::memcpy(desc_right + 32*(size_t)i, dR.ptr<uint8_t>(i), 32);
+	}
+	return lorb_host::pool().created() - before;
 }
 
 }  // extern "C"

@@ -132,3 +132,23 @@ def _ref_level_shapes(img):
         out.append(np.zeros((int(np.rint(np.float32(img.shape[0]) * isf)), int(np.rint(np.float32(img.shape[1]) * isf))),
                             np.uint8))
     return out
+
+
+def test_orbextractor_on_fresh_threads_reuses_contexts():
+    """The reference extracts left / right on two NEW threads every frame (src/frame.cpp:42-45);
+    the drop-in layer's context pool must hand the same two GPU contexts back instead of creating
+    (and tearing down) one per thread per frame."""
+    import orb_checks as OC
+    Hl = C.CDLL(build_host.build())
+    st = synth.make_stereo_pair(8, 31)
+    left, right = st["pyr_left"][0], st["pyr_right"][0]
+    cap = 1064
+    nl, nr = C.c_int(0), C.c_int(0)
+    dl, dr = np.zeros((cap, 32), np.uint8), np.zeros((cap, 32), np.uint8)
+    created = Hl.harness_stereo_extract_threads(_p(left), _p(right), 640, 480, 1000, 6, cap, C.byref(nl), C.byref(nr),
+                                                _p(dl), _p(dr))
+    assert created <= 2
+    with __import__("lorb_slam_b200").capi.Context(0) as ctx:
+        a, b = ctx.orb_extract(left, OC.pattern()), ctx.orb_extract(right, OC.pattern())
+    assert nl.value == a["n"] and nr.value == b["n"]
+    assert np.array_equal(dl[:a["n"]], a["desc"]) and np.array_equal(dr[:b["n"]], b["desc"])
