@@ -148,7 +148,8 @@ def test_orbextractor_on_fresh_threads_reuses_contexts():
     created = Hl.harness_stereo_extract_threads(_p(left), _p(right), 640, 480, 1000, 6, cap, C.byref(nl), C.byref(nr),
                                                 _p(dl), _p(dr))
     assert created <= 2
-    with __import__("lorb_slam_b200").capi.Context(0) as ctx:
+    from lorb_slam_b200 import capi
+    with capi.Context(0) as ctx:
         a, b = ctx.orb_extract(left, OC.pattern()), ctx.orb_extract(right, OC.pattern())
     assert nl.value == a["n"] and nr.value == b["n"]
     assert np.array_equal(dl[:a["n"]], a["desc"]) and np.array_equal(dr[:b["n"]], b["desc"])
