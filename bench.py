@@ -387,6 +387,16 @@ def extras(ctx, local):
         for _ in range(reps):
             m = ctx.match_bf_crosscheck(a["desc"], b["desc"])
         dtm = (time.perf_counter() - t0) / reps
+        st0 = synth.make_stereo_pair(8, 0)
+        sl, sr = st0["pyr_left"][0], st0["pyr_right"][0]
+        sf = ctx.stereo_frame(sl, sr, pattern, float(st0["mbf"]), float(st0["mb"]))
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            ctx.stereo_frame(sl, sr, pattern, float(st0["mbf"]), float(st0["mb"]))
+        dts = (time.perf_counter() - t0) / reps
+        out["stereo_frame_2x640x480_e2e"] = {
+            "us_per_frame_pair": dts * 1e6, "keypoints_left": int(sf[0]["n"]), "keypoints_right": int(sf[1]["n"]),
+            "stereo_matches": int(sf[4])}
         out["orb_extract_1000f_640x480_e2e"] = {
             "us_per_frame": dt * 1e6, "frames_per_s": 1 / dt, "keypoints": int(a["n"]),
             "pair_match_us": dtm * 1e6, "pair_matches_kept": int(m["n_kept"])}
