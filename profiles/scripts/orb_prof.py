@@ -42,3 +42,29 @@ with capi.Context(0) as ctx:
     dt = (time.perf_counter() - t) / reps
     print("stereo frame 640x480 x2, 1000 features each: %d + %d keypoints, %d stereo matches, %.3f ms per frame pair"
           % (r[0]["n"], r[1]["n"], r[4], dt * 1e3))
+
+# aggregate throughput with several host threads, each with its own context (ctypes drops the GIL)
+import threading
+
+
+def _worker(n_iter, out, k):
+    with capi.Context(0) as c2:
+        im = synth.make_orb_image(k)
+        for _ in range(10):
+            c2.orb_extract(im, pattern)
+        barrier.wait()
+        t0 = time.perf_counter()
+        for _ in range(n_iter):
+            c2.orb_extract(im, pattern)
+        out[k] = time.perf_counter() - t0
+
+
+if reps > 1:
+    for nt in (1, 2, 4, 8):
+        barrier = threading.Barrier(nt)
+        out = {}
+        th = [threading.Thread(target=_worker, args=(reps, out, k)) for k in range(nt)]
+        [t.start() for t in th]
+        [t.join() for t in th]
+        print("%d host threads x own context: %.0f frames/s aggregate (640x480, 1000 features)"
+              % (nt, nt * reps / max(out.values())))
