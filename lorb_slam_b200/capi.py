@@ -26,7 +26,7 @@ EXPORTS = [
     "lorb_match_sweep_resident", "lorb_sweep_plan_upload", "lorb_sweep_plan_run",
     "lorb_sweep_plan_download", "lorb_sweep_plan_run_at", "lorb_search_proj_points", "lorb_search_proj_frame", "lorb_frustum_project", "lorb_compute_descriptors",
     "lorb_stereo_matches", "lorb_orb_describe", "lorb_orb_umax", "lorb_orb_selftest",
-    "lorb_orb_extract", "lorb_orb_level_sizes", "lorb_orb_stages", "lorb_stereo_frame", "lorb_orb_distribute",
+    "lorb_orb_extract", "lorb_orb_level_sizes", "lorb_orb_stages", "lorb_stereo_frame", "lorb_orb_distribute", "lorb_orb_distribute_gpu",
     "lorb_ba_default_options", "lorb_ba_pose_only", "lorb_ba_local", "lorb_ba_local_batched",
     "lorb_ba_problem_create", "lorb_ba_problem_create_batched", "lorb_ba_problem_reset", "lorb_ba_problem_solve",
     "lorb_ba_problem_download", "lorb_ba_problem_destroy", "lorb_dist_get_unique_id",
@@ -419,6 +419,14 @@ class Context:
             _ptr(cx), _ptr(cy), _ptr(cr), _ptr(ls)))
         t = int(ls[-1])
         return dict(raw=raw, blur=blur, cand_x=cx[:t], cand_y=cy[:t], cand_response=cr[:t], level_start=ls)
+
+    def orb_distribute_gpu(self, x, y, response, min_x, max_x, min_y, max_y, n_features):
+        x, y, r = (_arr(a, np.float32) for a in (x, y, response))
+        out = np.zeros(max(n_features + 16, len(x) + 16), np.int32)
+        n = C.c_int(0)
+        _check(self._lib.lorb_orb_distribute_gpu(self._h, len(x), _ptr(x), _ptr(y), _ptr(r), min_x, max_x, min_y,
+                                                 max_y, n_features, _ptr(out), C.byref(n)))
+        return out[:n.value]
 
     def orb_selftest(self, a, b):
         a, b = _arr(a, np.float32), _arr(b, np.float32)

@@ -20,6 +20,7 @@
 #include "common.cuh"
 #include "libm_sincosf.cuh"
 #include "orb_quadtree.h"
+#include "orb_quadtree_gpu.cuh"
 #include "stereo_dev.cuh"
 
 namespace lorb {
@@ -1100,6 +1101,55 @@ int lorb_orb_distribute(int n_keys, const float* x, const float* y, const float*
   distribute_quadtree(keys, min_x, max_x, min_y, max_y, n_features, &chosen);
   for (size_t i = 0; i < chosen.size(); i++) out_index[i] = chosen[i];
   *n_out = (int)chosen.size();
+  return LORB_OK;
+}
+
+// ORBextractor::DistributeOctTree on the device (orb_quadtree_gpu.cuh): one CTA, same result as
+// lorb_orb_distribute.  Coordinates must be integers in [0, 4096), responses integers in [0, 256)
+// (what the FAST kernel produces).
+int lorb_orb_distribute_gpu(lorb_ctx* c, int n_keys, const float* x, const float* y, const float* response, int min_x,
+                            int max_x, int min_y, int max_y, int n_features, int* out_index, int* n_out) {
+  LORB_REQUIRE(c && n_keys >= 0 && n_out && (n_keys == 0 || (x && y && response && out_index)), "arguments");
+  LORB_REQUIRE(max_x > min_x && max_y > min_y && n_features >= 0, "bounds");
+  *n_out = 0;
+  if (n_keys == 0) return LORB_OK;
+  LORB_CUDA_TRY(cudaSetDevice(c->device));
+  const int n_ini = std::max(1, (int)roundf((float)(max_x - min_x) / (max_y - min_y)));
+  const int node_cap = qt_node_cap(n_keys, n_features, n_ini);
+  OPacker pk;
+  const size_t o_keys = pk.add((size_t)n_keys * 4), o_scr = pk.add(qt_scratch_ints(n_keys, node_cap) * 4),
+               o_out = pk.add((size_t)qt_out_cap(n_features, n_ini) * 4), o_cnt = pk.add(4);
+  LORB_TRY(dev_reserve(c, 5, pk.off));
+  LORB_TRY(pin_reserve(c, 4, std::max((size_t)n_keys * 4, (size_t)qt_out_cap(n_features, n_ini) * 4 + 512)));
+  uint32_t* hk = c->h[4].as<uint32_t>();
+  for (int i = 0; i < n_keys; i++) {
+    LORB_REQUIRE(x[i] >= 0 && x[i] < 4096 && y[i] >= 0 && y[i] < 4096 && response[i] >= 0 && response[i] < 256 &&
+                     x[i] == (float)(int)x[i] && y[i] == (float)(int)y[i] && response[i] == (float)(int)response[i],
+                 "keys must be integer pixels below 4096 with integer responses below 256");
+    hk[i] = ((uint32_t)response[i] << 24) | ((uint32_t)y[i] << 12) | (uint32_t)x[i];
+  }
+  uint8_t* d = c->d[5].as<uint8_t>();
+  LORB_CUDA_TRY(cudaMemcpyAsync(d + o_keys, hk, (size_t)n_keys * 4, cudaMemcpyHostToDevice, c->stream));
+  QtArgs A;
+  memset(&A, 0, sizeof(A));
+  QtLevel& L = A.lv[0];
+  L.keys = (const uint32_t*)(d + o_keys);
+  L.n_keys = n_keys;
+  L.width = max_x - min_x;
+  L.height = max_y - min_y;
+  L.n_features = n_features;
+  L.scratch = (int*)(d + o_scr);
+  L.node_cap = node_cap;
+  L.out_index = (int*)(d + o_out);
+  L.out_count = (int*)(d + o_cnt);
+  LORB_LAUNCH(c, orb_quadtree_kernel, 1, QT_THREADS, 0, A);
+  int* ho = c->h[4].as<int>();
+  LORB_CUDA_TRY(cudaMemcpyAsync(ho, d + o_out, o_cnt + 4 - o_out, cudaMemcpyDeviceToHost, c->stream));
+  LORB_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  const int n = *(const int*)((const uint8_t*)ho + (o_cnt - o_out));
+  LORB_REQUIRE(n >= 0 && n <= qt_out_cap(n_features, n_ini), "device quadtree ran out of node slots (internal)");
+  memcpy(out_index, ho, (size_t)n * 4);
+  *n_out = n;
   return LORB_OK;
 }
 
