@@ -61,76 +61,38 @@ struct OrbTables {
   int umax[ORB_HALF_PATCH + 1];
 };
 
-// Optional second destinations of the descriptor kernel (all NULL for the plain call).  In the
-// extractor the keypoints are READ from mapped pinned host memory and angle / descriptors are also
-// WRITTEN there, so the step is one launch without copies; the device copies (descriptors, level-0
-// coordinates, levels) stay behind for the stereo matcher.
-struct OrbDescribeMirror {
-  float* h_angle;
-  uint32_t* h_desc;
-  const float *sx_in, *sy_in;  // KeyPoint::pt (level-0 coordinates)
-  float *d_sx, *d_sy;
-  int* d_lvl;
-};
 
-__global__ void __launch_bounds__(256)
-    orb_describe_kernel(OrbLevelsDev L, int n_kp, const float* __restrict__ kx, const float* __restrict__ ky,
-                        const int* __restrict__ klevel, const OrbTables* __restrict__ tab,
-                        float* __restrict__ out_angle, uint32_t* __restrict__ out_desc, int with_angle_in,
-                        OrbDescribeMirror M) {
-  __shared__ char2 s_pat[512];
-  __shared__ int s_umax[ORB_HALF_PATCH + 1];
-  for (int i = threadIdx.x; i < 512; i += blockDim.x) s_pat[i] = tab->pattern[i];
-  if (threadIdx.x <= ORB_HALF_PATCH) s_umax[threadIdx.x] = tab->umax[threadIdx.x];
-  __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (i >= n_kp) return;
-  const int l = klevel[i];
-  const int step = L.w[l];
-  const int px = __float2int_rn(kx[i]), py = __float2int_rn(ky[i]);  // cvRound(pt.x), cvRound(pt.y)
-  const size_t centre = (size_t)py * step + px;
-
-  float angle;
-  if (with_angle_in) {
-    angle = out_angle[i];
-  } else {
-    // IC_Angle: m_10 = sum u*I, m_01 = sum v*I over the circular patch
-    int m01 = 0, m10 = 0;
-    if (lane <= 2 * ORB_HALF_PATCH) {
-      const int v = lane - ORB_HALF_PATCH;
-      const int d = s_umax[v < 0 ? -v : v];
-      const uint8_t* row = L.raw[l] + centre + (ptrdiff_t)v * step;
-      int s = 0;
-      for (int u = -d; u <= d; ++u) {
-        const int val = row[u];
-        s += val;
-        m10 += u * val;
-      }
-      m01 = v * s;
+// IC_Angle (:79-106) by one warp: m_10 = sum u*I, m_01 = sum v*I over the radius-15 disc.
+__device__ __forceinline__ float orb_ic_angle(const uint8_t* __restrict__ centre, int step, int lane,
+                                              const int* s_umax) {
+  int m01 = 0, m10 = 0;
+  if (lane <= 2 * ORB_HALF_PATCH) {
+    const int v = lane - ORB_HALF_PATCH;
+    const int d = s_umax[v < 0 ? -v : v];
+    const uint8_t* row = centre + (ptrdiff_t)v * step;
+    int s = 0;
+    for (int u = -d; u <= d; ++u) {
+      const int val = row[u];
+      s += val;
+      m10 += u * val;
     }
+    m01 = v * s;
+  }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      m01 += __shfl_xor_sync(0xffffffffu, m01, o);
-      m10 += __shfl_xor_sync(0xffffffffu, m10, o);
-    }
-    angle = fast_atan2_cv((float)m01, (float)m10);
-    if (lane == 0) {
-      out_angle[i] = angle;
-      if (M.h_angle) M.h_angle[i] = angle;
-    }
+  for (int o = 16; o > 0; o >>= 1) {
+    m01 += __shfl_xor_sync(0xffffffffu, m01, o);
+    m10 += __shfl_xor_sync(0xffffffffu, m10, o);
   }
-  if (M.d_sx && lane == 0) {
-    M.d_sx[i] = M.sx_in[i];
-    M.d_sy[i] = M.sy_in[i];
-    M.d_lvl[i] = l;
-  }
+  return fast_atan2_cv((float)m01, (float)m10);
+}
 
-  // computeOrbDescriptor
+// computeOrbDescriptor (:110-149) by one warp: lane b computes byte b; lanes with (lane & 3) == 0
+// return the 32-bit word made of their own and the next three lanes' bytes.
+__device__ __forceinline__ uint32_t orb_brief_word(const uint8_t* __restrict__ img, int step, float angle, int lane,
+                                                   const char2* s_pat) {
   const float factorPI = (float)(3.1415926535897932384626433832795 / 180.f);
   const float rad = __fmul_rn(angle, factorPI);
   const float a = lorb_libm::cosf_libm(rad), b = lorb_libm::sinf_libm(rad);
-  const uint8_t* img = L.blur[l] + centre;
   uint32_t val = 0;
 #pragma unroll
   for (int bit = 0; bit < 8; bit++) {
@@ -143,13 +105,98 @@ __global__ void __launch_bounds__(256)
     const int t0 = img[r0 * step + c0], t1 = img[r1 * step + c1];
     val |= (uint32_t)(t0 < t1) << bit;
   }
-  // byte `lane` of the 32-byte row: gather 4 lanes into one 32-bit store
   const uint32_t b1 = __shfl_down_sync(0xffffffffu, val, 1), b2 = __shfl_down_sync(0xffffffffu, val, 2),
                  b3 = __shfl_down_sync(0xffffffffu, val, 3);
+  return val | (b1 << 8) | (b2 << 16) | (b3 << 24);
+}
+
+__global__ void __launch_bounds__(256)
+    orb_describe_kernel(OrbLevelsDev L, int n_kp, const float* __restrict__ kx, const float* __restrict__ ky,
+                        const int* __restrict__ klevel, const OrbTables* __restrict__ tab,
+                        float* __restrict__ out_angle, uint32_t* __restrict__ out_desc, int with_angle_in) {
+  __shared__ char2 s_pat[512];
+  __shared__ int s_umax[ORB_HALF_PATCH + 1];
+  for (int i = threadIdx.x; i < 512; i += blockDim.x) s_pat[i] = tab->pattern[i];
+  if (threadIdx.x <= ORB_HALF_PATCH) s_umax[threadIdx.x] = tab->umax[threadIdx.x];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (i >= n_kp) return;
+  const int l = klevel[i];
+  const int step = L.w[l];
+  const int px = __float2int_rn(kx[i]), py = __float2int_rn(ky[i]);  // cvRound(pt.x), cvRound(pt.y)
+  const size_t centre = (size_t)py * step + px;
+  float angle;
+  if (with_angle_in) {
+    angle = out_angle[i];
+  } else {
+    angle = orb_ic_angle(L.raw[l] + centre, step, lane, s_umax);
+    if (lane == 0) out_angle[i] = angle;
+  }
+  const uint32_t word = orb_brief_word(L.blur[l] + centre, step, angle, lane, s_pat);
+  if ((lane & 3) == 0) out_desc[(size_t)i * 8 + (lane >> 2)] = word;
+}
+
+// The same two stages for the keypoints the device quadtree selected (orb_quadtree_gpu.cuh): warp i
+// finds its level from the per-level counts, its keypoint from the level's chosen list, and writes
+// the finished KeyPoint (level-0 coordinates, octave, angle, response) and descriptor row both to
+// mapped pinned host memory (the caller's result) and to device arrays (the stereo matcher's input).
+struct OrbSelDev {
+  OrbLevelsDev LV;
+  int n_levels;
+  const uint32_t* keys[ORB_MAX_LEVELS];  // packed candidates of the level, candidate order
+  const int* chosen[ORB_MAX_LEVELS];
+  const int* count[ORB_MAX_LEVELS];
+  float scale[ORB_MAX_LEVELS];
+  const OrbTables* tab;
+  int cap;  // capacity of the output arrays
+  float *h_x, *h_y, *h_angle, *h_resp;
+  int* h_oct;
+  uint32_t* h_desc;
+  float *d_x, *d_y;
+  int* d_oct;
+  uint32_t* d_desc;
+};
+
+__global__ void __launch_bounds__(256) orb_describe_selected_kernel(OrbSelDev Q) {
+  __shared__ char2 s_pat[512];
+  __shared__ int s_umax[ORB_HALF_PATCH + 1];
+  for (int i = threadIdx.x; i < 512; i += blockDim.x) s_pat[i] = Q.tab->pattern[i];
+  if (threadIdx.x <= ORB_HALF_PATCH) s_umax[threadIdx.x] = Q.tab->umax[threadIdx.x];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (i >= Q.cap) return;
+  int l = 0, off = 0;
+  for (; l < Q.n_levels; l++) {
+    const int n = max(*Q.count[l], 0);
+    if (i < off + n) break;
+    off += n;
+  }
+  if (l == Q.n_levels) return;
+  const uint32_t e = Q.keys[l][Q.chosen[l][i - off]];
+  // pt = candidate + minBorder (:873-874), in level coordinates
+  const float x = __fadd_rn((float)(e & 0xfff), (float)(ORB_EDGE - 3));
+  const float y = __fadd_rn((float)((e >> 12) & 0xfff), (float)(ORB_EDGE - 3));
+  const int step = Q.LV.w[l];
+  const size_t centre = (size_t)__float2int_rn(y) * step + __float2int_rn(x);
+  const float angle = orb_ic_angle(Q.LV.raw[l] + centre, step, lane, s_umax);
+  const uint32_t word = orb_brief_word(Q.LV.blur[l] + centre, step, angle, lane, s_pat);
   if ((lane & 3) == 0) {
-    const uint32_t word = val | (b1 << 8) | (b2 << 16) | (b3 << 24);
-    out_desc[(size_t)i * 8 + (lane >> 2)] = word;
-    if (M.h_desc) M.h_desc[(size_t)i * 8 + (lane >> 2)] = word;
+    Q.h_desc[(size_t)i * 8 + (lane >> 2)] = word;
+    Q.d_desc[(size_t)i * 8 + (lane >> 2)] = word;
+  }
+  if (lane == 0) {
+    // keypoint->pt *= scale for level != 0 (:1142-1147)
+    const float sx = l ? __fmul_rn(x, Q.scale[l]) : x, sy = l ? __fmul_rn(y, Q.scale[l]) : y;
+    Q.h_x[i] = sx;
+    Q.h_y[i] = sy;
+    Q.h_oct[i] = l;
+    Q.h_angle[i] = angle;
+    Q.h_resp[i] = (float)(e >> 24);
+    Q.d_x[i] = sx;
+    Q.d_y[i] = sy;
+    Q.d_oct[i] = l;
   }
 }
 
@@ -431,9 +478,9 @@ __global__ void __launch_bounds__(256)
   __syncthreads();
   if (threadIdx.x == 0) {
     cell_count[cell] = active ? s_base : 0;
-    __threadfence_system();
+    if (P.host_flag) __threadfence_system();
     const int n_level = P.cell_start[l + 1] - P.cell_start[l];
-    if (atomicAdd(&P.done_ctr[l], 1) == n_level - 1) {
+    if (P.host_flag && atomicAdd(&P.done_ctr[l], 1) == n_level - 1) {
       P.done_ctr[l] = 0;  // ready for the next call (stream ordered)
       __threadfence_system();
       P.host_flag[l] = *P.seq;
@@ -490,16 +537,14 @@ struct OrbGraphKey {  // everything the captured chain depends on
   OrbPlanDev P;
   const void* stage;
   int width, height, with_blur;
+  int n_features[ORB_MAX_LEVELS];
+  uint64_t pattern_hash;
 };
 
 struct OrbGraph {
   OrbGraphKey key;
   cudaGraphExec_t exec = nullptr;
   int n_kernels = 0;
-  // descriptor tables resident in the job's device area
-  bool tab_valid = false;
-  uint64_t tab_hash = 0;
-  const void* tab_dev = nullptr;
 };
 
 void orb_graph_free(lorb_ctx* c) {
@@ -510,6 +555,15 @@ void orb_graph_free(lorb_ctx* c) {
       delete G;
       g = nullptr;
     }
+  for (auto& e : c->orb_ev)
+    if (e) {
+      cudaEventDestroy(e);
+      e = nullptr;
+    }
+  if (c->orb_stream2) {
+    cudaStreamDestroy(c->orb_stream2);
+    c->orb_stream2 = nullptr;
+  }
 }
 
 }  // namespace lorb
@@ -591,8 +645,7 @@ int lorb_orb_describe(lorb_ctx* c, const lorb_pyramid_view* raw, const lorb_pyra
   const int warps_per_cta = 8;
   LORB_LAUNCH(c, orb_describe_kernel, (n_kp + warps_per_cta - 1) / warps_per_cta, warps_per_cta * 32, 0, L, n_kp,
               (const float*)(d + i_kx), (const float*)(d + i_ky), (const int*)(d + i_kl),
-              (const OrbTables*)(d + i_tab), (float*)(dout + o_ang), (uint32_t*)(dout + o_desc), angle_in ? 1 : 0,
-              OrbDescribeMirror{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr});
+              (const OrbTables*)(d + i_tab), (float*)(dout + o_ang), (uint32_t*)(dout + o_desc), angle_in ? 1 : 0);
   uint8_t* ho = c->h[1].as<uint8_t>();
   LORB_CUDA_TRY(cudaMemcpyAsync(ho, dout, out.off, cudaMemcpyDeviceToHost, c->stream));
   LORB_CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -622,31 +675,6 @@ struct ExtractOut {
   int* level_h = nullptr;
 };
 
-// One image going through the extractor.  Two jobs (left, right) share the stream and interleave
-// so that the GPU works on one image while the host distributes the keypoints of the other.
-struct OrbJob {
-  const uint8_t* image = nullptr;
-  int step = 0;
-  ExtractOut O;
-  // layout (offsets into the shared buffers, fixed by layout())
-  size_t dev_base = 0, stage_base = 0, kin_base = 0, kout_base = 0;
-  size_t o_raw[ORB_MAX_LEVELS], o_blur[ORB_MAX_LEVELS];
-  size_t o_hdr = 0, o_ctr = 0, o_tab = 0, h_hdr = 0, h_flag = 0;
-  size_t h_img = 0, h_cnt = 0, h_slots = 0;
-  unsigned seq = 0;
-  size_t i_kx = 0, i_ky = 0, i_kl = 0, i_sx = 0, i_sy = 0, i_tab = 0, kin_bytes = 0;
-  size_t o_ang = 0, o_desc = 0, kout_bytes = 0;
-  OrbPlanDev P;
-  int slot = 0;  // which row of ctx->orb_ev this job uses
-  std::vector<std::vector<int>> chosen;
-  std::vector<std::vector<QKey>> keys;
-  int n_total = 0;
-  // device views of the selected keypoints (valid after describe())
-  const float *d_sx = nullptr, *d_sy = nullptr;  // level-0 coordinates (KeyPoint::pt)
-  const int* d_lvl = nullptr;
-  const uint32_t* d_desc = nullptr;
-};
-
 // LORB_ORB_TRACE=1: host timeline of a call on stderr (microseconds since the call started)
 struct OrbTrace {
   bool on;
@@ -659,6 +687,27 @@ struct OrbTrace {
   }
 };
 
+// One image going through the extractor.  Two jobs (left, right) share the context.
+struct OrbJob {
+  const uint8_t* image = nullptr;
+  int step = 0;
+  ExtractOut O;
+  int slot = 0;  // which cached graph / buffer half of the context this job uses
+  // layout: offsets into the job's device area (d[3]) and pinned area (h[2])
+  size_t dev_base = 0, pin_base = 0;
+  size_t o_hdr = 0, o_raw[ORB_MAX_LEVELS], o_blur[ORB_MAX_LEVELS], o_ctr = 0, o_tab = 0, o_slots = 0, o_cnt = 0;
+  size_t o_keys[ORB_MAX_LEVELS], o_qscr[ORB_MAX_LEVELS], o_chosen[ORB_MAX_LEVELS], o_count = 0;
+  size_t o_dx = 0, o_dy = 0, o_doct = 0, o_ddesc = 0;
+  size_t h_hdr = 0, h_img = 0, h_count = 0, h_x = 0, h_y = 0, h_oct = 0, h_ang = 0, h_resp = 0, h_desc = 0;
+  OrbPlanDev P;
+  int n_total = 0;
+  int n_level[ORB_MAX_LEVELS];
+  // device views of the selected keypoints (valid after the chain has run)
+  const float *d_sx = nullptr, *d_sy = nullptr;  // level-0 coordinates (KeyPoint::pt)
+  const int* d_lvl = nullptr;
+  const uint32_t* d_desc = nullptr;
+};
+
 struct OrbPipeline {
   OrbTrace tr;
   lorb_ctx* c;
@@ -667,7 +716,8 @@ struct OrbPipeline {
   bool want_desc = false;
   const int* pattern = nullptr;
   int ini_th = 0, min_th = 0;
-  size_t dev_bytes = 0, stage_bytes = 0, kin_cap_bytes = 0, kout_cap_bytes = 0;
+  int n_ini[ORB_MAX_LEVELS], out_cap[ORB_MAX_LEVELS], node_cap[ORB_MAX_LEVELS], lvl_key_cap[ORB_MAX_LEVELS];
+  size_t dev_bytes = 0, pin_bytes = 0;
 
   int plan(lorb_ctx* ctx, int w, int h, const lorb_orb_params* prm, const int* pat, bool desc, int cap) {
     c = ctx;
@@ -685,7 +735,7 @@ struct OrbPipeline {
         LORB_REQUIRE(pattern[2 * k] * pattern[2 * k] + pattern[2 * k + 1] * pattern[2 * k + 1] < ORB_EDGE * ORB_EDGE,
                      "pattern radius");
     }
-    n_cells = n_tiles = slot_cap = 0;
+    n_cells = n_tiles = slot_cap = key_cap = 0;
     for (int l = 0; l < nl; l++) {
       n_tiles += ((L.w[l] + BLUR_TX - 1) / BLUR_TX) * ((L.h[l] + BLUR_TY - 1) / BLUR_TY);
       n_cells += L.n_cols[l] * L.n_rows[l];
@@ -693,63 +743,75 @@ struct OrbPipeline {
       // suppression leaves no two adjacent survivors: at most ceil(w/2)*ceil(h/2) per interior
       slot_cap = std::max(slot_cap, ((L.w_cell[l] + 1) / 2) * ((L.h_cell[l] + 1) / 2));
     }
-    // the quadtree of a level stops at >= its share and one split adds at most 3 nodes
-    key_cap = std::max(cap, prm->nfeatures + 4 * nl);
+    for (int l = 0; l < nl; l++) {
+      const int bw = L.w[l] - 2 * ORB_EDGE + 6, bh = L.h[l] - 2 * ORB_EDGE + 6;
+      n_ini[l] = std::max(1, (int)roundf((float)bw / bh));
+      out_cap[l] = qt_out_cap(L.n_features[l], n_ini[l]);
+      lvl_key_cap[l] = L.n_cols[l] * L.n_rows[l] * slot_cap;
+      node_cap[l] = std::max(qt_node_cap(lvl_key_cap[l], L.n_features[l], n_ini[l]), L.n_cols[l] * L.n_rows[l] + 64);
+      key_cap += out_cap[l];
+    }
+    (void)cap;
     return LORB_OK;
   }
 
   // Offsets of job j inside the shared device / pinned buffers.
   void layout(OrbJob* J, int j) {
     OPacker dv;
-    J->o_hdr = dv.add(256);  // [seq | pad], contiguous with level 0: one H2D copy brings both
+    J->o_hdr = dv.add(256);  // [call number | pad], contiguous with level 0: one H2D copy brings both
     for (int l = 0; l < nl; l++) J->o_raw[l] = dv.add((size_t)L.w[l] * L.h[l]);
     for (int l = 0; l < nl; l++) J->o_blur[l] = dv.add((size_t)L.w[l] * L.h[l]);
     J->o_ctr = dv.add(ORB_MAX_LEVELS * 4);
     J->o_tab = dv.add(sizeof(OrbTables));
+    J->o_slots = dv.add((size_t)n_cells * slot_cap * 4);
+    J->o_cnt = dv.add((size_t)n_cells * 4);
+    for (int l = 0; l < nl; l++) {
+      J->o_keys[l] = dv.add((size_t)lvl_key_cap[l] * 4);
+      J->o_qscr[l] = dv.add(qt_scratch_ints(lvl_key_cap[l], node_cap[l]) * 4);
+      J->o_chosen[l] = dv.add((size_t)out_cap[l] * 4);
+    }
+    J->o_count = dv.add(ORB_MAX_LEVELS * 4);
+    J->o_dx = dv.add((size_t)key_cap * 4);
+    J->o_dy = dv.add((size_t)key_cap * 4);
+    J->o_doct = dv.add((size_t)key_cap * 4);
+    J->o_ddesc = dv.add((size_t)key_cap * 32);
     dev_bytes = dv.off;
     J->dev_base = (size_t)j * dev_bytes;
     OPacker hs;
     J->h_hdr = hs.add(256);
     J->h_img = hs.add((size_t)width * height);
-    J->h_flag = hs.add(ORB_MAX_LEVELS * 4);
-    J->h_cnt = hs.add((size_t)n_cells * 4);
-    J->h_slots = hs.add((size_t)n_cells * slot_cap * 4);
-    stage_bytes = hs.off;
-    J->stage_base = (size_t)j * stage_bytes;
-    OPacker in, out;
-    J->i_kx = in.add((size_t)key_cap * 4);
-    J->i_ky = in.add((size_t)key_cap * 4);
-    J->i_kl = in.add((size_t)key_cap * 4);
-    J->i_sx = in.add((size_t)key_cap * 4);
-    J->i_sy = in.add((size_t)key_cap * 4);
-    J->i_tab = in.add(sizeof(OrbTables));
-    kin_cap_bytes = in.off;
-    J->kin_base = (size_t)j * kin_cap_bytes;
-    J->o_ang = out.add((size_t)key_cap * 4);
-    J->o_desc = out.add((size_t)key_cap * 32);
-    kout_cap_bytes = out.off;
-    J->kout_base = (size_t)j * kout_cap_bytes;
+    J->h_count = hs.add(ORB_MAX_LEVELS * 4);
+    J->h_x = hs.add((size_t)key_cap * 4);
+    J->h_y = hs.add((size_t)key_cap * 4);
+    J->h_oct = hs.add((size_t)key_cap * 4);
+    J->h_ang = hs.add((size_t)key_cap * 4);
+    J->h_resp = hs.add((size_t)key_cap * 4);
+    J->h_desc = hs.add((size_t)key_cap * 32);
+    pin_bytes = hs.off;
+    J->pin_base = (size_t)j * pin_bytes;
     J->slot = j;
   }
 
   int reserve(int n_jobs) {
     LORB_TRY(dev_reserve(c, 3, dev_bytes * n_jobs));
-    LORB_TRY(pin_reserve(c, 2, stage_bytes * n_jobs));
-    LORB_TRY(pin_reserve(c, 0, kin_cap_bytes * n_jobs));
-    LORB_TRY(pin_reserve(c, 1, kout_cap_bytes * n_jobs));
-    LORB_TRY(dev_reserve(c, 0, kin_cap_bytes * n_jobs));
-    LORB_TRY(dev_reserve(c, 2, kout_cap_bytes * n_jobs));
+    LORB_TRY(pin_reserve(c, 2, pin_bytes * n_jobs));
+    if (!c->orb_stream2) {
+      LORB_CUDA_TRY(cudaStreamCreateWithFlags(&c->orb_stream2, cudaStreamNonBlocking));
+      for (auto& e : c->orb_ev) LORB_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
     return LORB_OK;
   }
 
-  // The detection chain of one frame -- H2D of [seq | frame], then level after level: resize from
-  // the level above, FAST over the level's cells (candidates and a per-level "ready" flag land in
-  // mapped pinned host memory), finally the blur of all levels -- is 17 dependent operations.
-  // Issued one by one they cost the host ~80 us (measured: longer than the GPU needs to run them),
-  // so they are captured once per (frame size, parameters, buffers) into a CUDA graph and replayed
-  // with a single launch.  The host starts distributing level 0 while the GPU is still on the
-  // smaller levels.
-  int detect(OrbJob* J) {
+  // One frame = ONE CUDA-graph launch.  The graph (captured once per frame size, parameters and
+  // buffers) holds the whole extractor:
+  //     H2D [call number | frame]
+  //     FAST level 0 ------------------> quadtree level 0 (side branch)
+  //     resize x7 -> FAST levels 1..7 -> quadtree levels 1..7 -> blur
+  //     (join) orientation + descriptors of the selected keypoints, results written to pinned memory
+  // Issued one by one these 13 operations cost the host more time than the GPU needs to run them,
+  // and a quadtree on the host (orb_quadtree.h, 80 us for level 0) would sit in the middle of the
+  // chain; as a graph the host stages the frame, launches, and waits once.
+  int launch(OrbJob* J) {
     OrbPlanDev& P = J->P;
     memset(&P, 0, sizeof(P));
     P.n_levels = nl;
@@ -757,7 +819,7 @@ struct OrbPipeline {
     P.min_th = min_th;
     int cells = 0, tiles = 0;
     uint8_t* d = c->d[3].as<uint8_t>() + J->dev_base;
-    uint8_t* hp = c->h[2].as<uint8_t>() + J->stage_base;
+    uint8_t* hp = c->h[2].as<uint8_t>() + J->pin_base;
     for (int l = 0; l < nl; l++) {
       P.w[l] = L.w[l];
       P.h[l] = L.h[l];
@@ -776,9 +838,8 @@ struct OrbPipeline {
     P.cell_start[nl] = cells;
     P.slot_cap = slot_cap;
     P.done_ctr = (int*)(d + J->o_ctr);
-    P.host_flag = (volatile unsigned*)(hp + J->h_flag);
+    P.host_flag = nullptr;  // the consumer of the candidates is the next kernel, not the host
     P.seq = (const unsigned*)(d + J->o_hdr);
-    const bool with_blur = want_desc || J->O.blur_levels;
 
     OrbGraph*& G = reinterpret_cast<OrbGraph*&>(c->orb_graph[J->slot]);
     OrbGraphKey key;
@@ -787,7 +848,12 @@ struct OrbPipeline {
     key.stage = hp;
     key.width = width;
     key.height = height;
-    key.with_blur = with_blur;
+    key.with_blur = 1;
+    for (int l = 0; l < nl; l++) key.n_features[l] = L.n_features[l];
+    uint64_t hsh = 1469598103934665603ull;
+    if (pattern)
+      for (int q = 0; q < 1024; q++) hsh = (hsh ^ (uint32_t)pattern[q]) * 1099511628211ull;
+    key.pattern_hash = hsh;
     if (!G || memcmp(&G->key, &key, sizeof(key)) != 0) {
       if (G) {
         cudaGraphExecDestroy(G->exec);
@@ -795,12 +861,19 @@ struct OrbPipeline {
         G = nullptr;
       }
       LORB_CUDA_TRY(cudaStreamSynchronize(c->stream));
-      memset(hp + J->h_flag, 0, ORB_MAX_LEVELS * 4);  // fresh pinned memory holds anything
-      LORB_CUDA_TRY(cudaMemsetAsync(P.done_ctr, 0, ORB_MAX_LEVELS * 4, c->stream));
-      LORB_CUDA_TRY(cudaStreamSynchronize(c->stream));
+      // descriptor tables live in the job's device area
+      OrbTables t;
+      memset(&t, 0, sizeof(t));
+      if (pattern)
+        for (int q = 0; q < 512; q++)
+          t.pattern[q] = make_char2((signed char)pattern[2 * q], (signed char)pattern[2 * q + 1]);
+      make_umax(t.umax);
+      LORB_CUDA_TRY(cudaMemcpyAsync(d + J->o_tab, &t, sizeof(t), cudaMemcpyHostToDevice, c->stream));
+      LORB_CUDA_TRY(cudaMemsetAsync(d + J->o_count, 0, ORB_MAX_LEVELS * 4, c->stream));
+      LORB_CUDA_TRY(cudaStreamSynchronize(c->stream));  // `t` is on this stack frame
       const long long launches_before = c->launches;
       LORB_CUDA_TRY(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-      int rc = capture_chain(J, hp, with_blur);
+      const int rc = capture_chain(J, d, hp);
       cudaGraph_t graph = nullptr;
       cudaError_t ce = cudaStreamEndCapture(c->stream, &graph);
       if (rc != LORB_OK) {
@@ -820,34 +893,64 @@ struct OrbPipeline {
       }
       G = ng;
     }
-    // stage [seq | frame] and replay
-    J->seq = ++c->orb_seq;
-    if (J->seq == 0) J->seq = ++c->orb_seq;  // 0 is what a fresh flag holds
-    *(unsigned*)(hp + J->h_hdr) = J->seq;
+    *(unsigned*)(hp + J->h_hdr) = ++c->orb_seq;
     if (J->step == width) {
       memcpy(hp + J->h_img, J->image, (size_t)width * height);
     } else {
       for (int r = 0; r < height; r++) memcpy(hp + J->h_img + (size_t)r * width, J->image + (size_t)r * J->step, width);
     }
-    tr.mark("image staged");
+    tr.mark("frame staged");
     LORB_CUDA_TRY(cudaGraphLaunch(G->exec, c->stream));
     c->launches += G->n_kernels;
-    tr.mark("detect queued");
+    tr.mark("graph launched");
+    J->d_sx = (const float*)(d + J->o_dx);
+    J->d_sy = (const float*)(d + J->o_dy);
+    J->d_lvl = (const int*)(d + J->o_doct);
+    J->d_desc = (const uint32_t*)(d + J->o_ddesc);
     return LORB_OK;
   }
 
-  int capture_chain(OrbJob* J, uint8_t* hp, bool with_blur) {
+  QtLevel qt_level(const OrbJob* J, uint8_t* d, uint8_t* hp, int l) const {
+    QtLevel q;
+    memset(&q, 0, sizeof(q));
+    q.width = L.w[l] - 2 * ORB_EDGE + 6;
+    q.height = L.h[l] - 2 * ORB_EDGE + 6;
+    q.n_features = L.n_features[l];
+    q.scratch = (int*)(d + J->o_qscr[l]);
+    q.node_cap = node_cap[l];
+    q.slots = (const uint32_t*)(d + J->o_slots) + (size_t)J->P.cell_start[l] * slot_cap;
+    q.cell_cnt = (const int*)(d + J->o_cnt) + J->P.cell_start[l];
+    q.n_cells = J->P.cell_start[l + 1] - J->P.cell_start[l];
+    q.slot_cap = slot_cap;
+    q.keys_flat = (uint32_t*)(d + J->o_keys[l]);
+    q.key_cap = lvl_key_cap[l];
+    q.out_index = (int*)(d + J->o_chosen[l]);
+    q.out_count = (int*)(d + J->o_count) + l;
+    q.out_count_host = (int*)(hp + J->h_count) + l;
+    return q;
+  }
+
+  int capture_chain(OrbJob* J, uint8_t* d, uint8_t* hp) {
     const OrbPlanDev& P = J->P;
-    uint8_t* d = c->d[3].as<uint8_t>() + J->dev_base;
+    cudaStream_t s = c->stream, s2 = c->orb_stream2;
     // the header and level 0 are contiguous on both sides
-    LORB_CUDA_TRY(cudaMemcpyAsync(d + J->o_hdr, hp + J->h_hdr, 256 + (size_t)width * height, cudaMemcpyHostToDevice,
-                                  c->stream));
-    // FAST on level 0 first: it holds 40 % of the candidates and its quadtree is the longest host
-    // step, so its candidates should reach the host before the GPU builds the smaller levels.
-    // A kernel that writes to host memory ends with a PCIe flush (~8 us), so the other levels
-    // share one launch instead of paying it seven times.
-    LORB_LAUNCH(c, orb_fast_cells_kernel, P.cell_start[1], 256, 0, P, 0, (uint32_t*)(hp + J->h_slots),
-                (int*)(hp + J->h_cnt));
+    LORB_CUDA_TRY(cudaMemcpyAsync(d + J->o_hdr, hp + J->h_hdr, 256 + (size_t)width * height, cudaMemcpyHostToDevice, s));
+    uint32_t* slots = (uint32_t*)(d + J->o_slots);
+    int* cnt = (int*)(d + J->o_cnt);
+    // level 0 holds 40 % of the candidates and has the longest quadtree: its FAST runs first and its
+    // quadtree on a side branch, under the pyramid chain and the other levels
+    LORB_LAUNCH(c, orb_fast_cells_kernel, P.cell_start[1], 256, 0, P, 0, slots, cnt);
+    LORB_CUDA_TRY(cudaEventRecord(c->orb_ev[0], s));
+    LORB_CUDA_TRY(cudaStreamWaitEvent(s2, c->orb_ev[0], 0));
+    {
+      QtArgs A;
+      memset(&A, 0, sizeof(A));
+      A.lv[0] = qt_level(J, d, hp, 0);
+      orb_quadtree_kernel<<<1, QT_THREADS, 0, s2>>>(A);
+      c->launches++;
+      LORB_CUDA_TRY(cudaGetLastError());
+    }
+    LORB_CUDA_TRY(cudaEventRecord(c->orb_ev[1], s2));
     for (int l = 1; l < nl; l++) {
       // scale = 1 / (dsize / ssize) in double, as cv::resize derives it from the two sizes
       const double sx = 1. / ((double)L.w[l] / L.w[l - 1]), sy = 1. / ((double)L.h[l] / L.h[l - 1]);
@@ -855,169 +958,41 @@ struct OrbPipeline {
       LORB_LAUNCH(c, orb_resize_kernel, grd, blk, 0, P.raw[l - 1], L.w[l - 1], L.h[l - 1], P.raw[l], L.w[l], L.h[l],
                   sx, sy);
     }
-    if (nl > 1)
-      LORB_LAUNCH(c, orb_fast_cells_kernel, P.cell_start[nl] - P.cell_start[1], 256, 0, P, P.cell_start[1],
-                  (uint32_t*)(hp + J->h_slots), (int*)(hp + J->h_cnt));
-    if (with_blur) LORB_LAUNCH(c, orb_blur_kernel, n_tiles, 256, 0, P);
-    return LORB_OK;
-  }
-
-  // vToDistributeKeys of level l (:813): cells in (row, column) order, row-major inside a cell
-  void level_keys(const OrbJob* J, int l, std::vector<QKey>* out) const {
-    const uint8_t* hp = c->h[2].as<uint8_t>() + J->stage_base;
-    const int* cnt = (const int*)(hp + J->h_cnt);
-    const uint32_t* slots = (const uint32_t*)(hp + J->h_slots);
-    size_t n = 0;
-    for (int k = J->P.cell_start[l]; k < J->P.cell_start[l + 1]; k++) n += cnt[k];
-    out->resize(n);
-    n = 0;
-    for (int k = J->P.cell_start[l]; k < J->P.cell_start[l + 1]; k++)
-      for (int e = 0; e < cnt[k]; e++) {
-        const uint32_t v = slots[(size_t)k * slot_cap + e];
-        (*out)[n++] = QKey{(float)(v & 0xfff), (float)((v >> 12) & 0xfff), (float)(v >> 24)};
-      }
-  }
-
-  // Wait for the candidates of this job, run DistributeOctTree per level (:865-866).
-  int select(OrbJob* J) {
-    const int* cnt = (const int*)(c->h[2].as<uint8_t>() + J->stage_base + J->h_cnt);
-    volatile const unsigned* flag = (volatile const unsigned*)(c->h[2].as<uint8_t>() + J->stage_base + J->h_flag);
-    const unsigned seq = J->seq;
-    // spin on the level's flag in pinned memory (the GPU raises it microseconds after the launch;
-    // a kernel fault is caught by the deadline and reported by the stream afterwards)
-    auto wait_level = [&](int l) -> int {
-      const auto deadline = std::chrono::steady_clock::now() + std::chrono::seconds(10);
-      unsigned spins = 0;
-      while (flag[l] != seq) {
-        if ((++spins & 0xfff) == 0 && std::chrono::steady_clock::now() > deadline) return 1;
-#if defined(__x86_64__)
-        __builtin_ia32_pause();
-#endif
-      }
-      std::atomic_thread_fence(std::memory_order_acquire);
-      for (int k = J->P.cell_start[l]; k < J->P.cell_start[l + 1]; k++)
-        if (cnt[k] < 0 || cnt[k] > slot_cap) return 2;
-      return 0;
-    };
-    const ExtractOut& O = J->O;
-    if (O.cand_level_start) {
-      std::vector<QKey> kk;
-      int total = 0;
-      for (int l = 0; l < nl; l++) {
-        const int wr = wait_level(l);
-        LORB_REQUIRE(wr == 0, "FAST kernel failed or candidate slot overflow (internal)");
-        level_keys(J, l, &kk);
-        O.cand_level_start[l] = total;
-        LORB_REQUIRE(total + (int)kk.size() <= O.cand_cap, "candidate capacity");
-        for (const QKey& q : kk) {
-          O.cand_x[total] = q.x;
-          O.cand_y[total] = q.y;
-          O.cand_resp[total] = q.response;
-          total++;
-        }
-      }
-      O.cand_level_start[nl] = total;
+    if (nl > 1) {
+      LORB_LAUNCH(c, orb_fast_cells_kernel, P.cell_start[nl] - P.cell_start[1], 256, 0, P, P.cell_start[1], slots, cnt);
+      QtArgs A;
+      memset(&A, 0, sizeof(A));
+      for (int l = 1; l < nl; l++) A.lv[l - 1] = qt_level(J, d, hp, l);
+      LORB_LAUNCH(c, orb_quadtree_kernel, nl - 1, QT_THREADS, 0, A);
     }
-    J->chosen.assign(nl, std::vector<int>());
-    J->keys.assign(nl, std::vector<QKey>());
-    J->n_total = 0;
-    if (O.n_out || want_desc) {
-      int failed = 0;
-      // one host thread per level: each waits for its own level's candidates (levels arrive in
-      // order, the largest first) and distributes them while the GPU goes on with the next levels
-#pragma omp parallel for schedule(static, 1) num_threads(std::min(nl, 8)) reduction(| : failed)
-      for (int l = 0; l < nl; l++) {
-        if (wait_level(l) != 0) {
-          failed |= 1;
-          continue;
-        }
-        tr.mark("candidates arrived, level", l);
-        level_keys(J, l, &J->keys[l]);
-        const int min_b = ORB_EDGE - 3;
-        distribute_quadtree(J->keys[l], min_b, L.w[l] - ORB_EDGE + 3, min_b, L.h[l] - ORB_EDGE + 3, L.n_features[l],
-                            &J->chosen[l]);
-        tr.mark("quadtree done, level", l);
-      }
-      tr.mark("all levels distributed");
-      LORB_REQUIRE(!failed, "FAST kernel failed or candidate slot overflow (internal)");
-      for (int l = 0; l < nl; l++) J->n_total += (int)J->chosen[l].size();
-      if (O.n_out) *O.n_out = J->n_total;
-      LORB_REQUIRE(J->n_total <= O.cap && J->n_total <= key_cap,
-                   "keypoint capacity (nfeatures + a few: the quadtree stops at >= N per level)");
-    }
-    return LORB_OK;
-  }
-
-  // Orientation + descriptors of the chosen keypoints; D2H of the results is queued, not awaited.
-  int describe(OrbJob* J) {
-    if (J->n_total == 0 || !(want_desc || J->O.kangle)) return LORB_OK;
-    uint8_t* h = c->h[0].as<uint8_t>() + J->kin_base;
-    float *hx = (float*)(h + J->i_kx), *hy = (float*)(h + J->i_ky);
-    float *sx = (float*)(h + J->i_sx), *sy = (float*)(h + J->i_sy);
-    int* hl = (int*)(h + J->i_kl);
-    int k = 0;
+    LORB_LAUNCH(c, orb_blur_kernel, n_tiles, 256, 0, P);
+    LORB_CUDA_TRY(cudaStreamWaitEvent(s, c->orb_ev[1], 0));  // join the level-0 branch
+    OrbSelDev Q;
+    memset(&Q, 0, sizeof(Q));
     for (int l = 0; l < nl; l++) {
-      const float scale = L.scale[l];
-      for (int id : J->chosen[l]) {
-        hx[k] = J->keys[l][id].x + (float)(ORB_EDGE - 3);  // pt += minBorder (:873-874)
-        hy[k] = J->keys[l][id].y + (float)(ORB_EDGE - 3);
-        sx[k] = l ? hx[k] * scale : hx[k];  // keypoint->pt *= scale (:1142-1147)
-        sy[k] = l ? hy[k] * scale : hy[k];
-        hl[k] = l;
-        k++;
-      }
+      Q.LV.raw[l] = P.raw[l];
+      Q.LV.blur[l] = P.blur[l];
+      Q.LV.w[l] = L.w[l];
+      Q.LV.h[l] = L.h[l];
+      Q.keys[l] = (const uint32_t*)(d + J->o_keys[l]);
+      Q.chosen[l] = (const int*)(d + J->o_chosen[l]);
+      Q.count[l] = (const int*)(d + J->o_count) + l;
+      Q.scale[l] = L.scale[l];
     }
-    // tables: uploaded only when the pattern changes (they live in the job's device area)
-    uint8_t* dbase = c->d[3].as<uint8_t>() + J->dev_base;
-    OrbTables* d_tab = (OrbTables*)(dbase + J->o_tab);
-    {
-      uint64_t hsh = 1469598103934665603ull;
-      if (pattern)
-        for (int q = 0; q < 1024; q++) hsh = (hsh ^ (uint32_t)pattern[q]) * 1099511628211ull;
-      OrbGraph* G = static_cast<OrbGraph*>(c->orb_graph[J->slot]);
-      if (!G->tab_valid || G->tab_hash != hsh || G->tab_dev != d_tab) {
-        OrbTables t;
-        memset(&t, 0, sizeof(t));
-        if (pattern)
-          for (int q = 0; q < 512; q++)
-            t.pattern[q] = make_char2((signed char)pattern[2 * q], (signed char)pattern[2 * q + 1]);
-        make_umax(t.umax);
-        LORB_CUDA_TRY(cudaMemcpyAsync(d_tab, &t, sizeof(t), cudaMemcpyHostToDevice, c->stream));
-        LORB_CUDA_TRY(cudaStreamSynchronize(c->stream));  // `t` is on this stack frame
-        G->tab_valid = true;
-        G->tab_hash = hsh;
-        G->tab_dev = d_tab;
-      }
-    }
-    uint8_t* din = c->d[0].as<uint8_t>() + J->kin_base;
-    uint8_t* dout = c->d[2].as<uint8_t>() + J->kout_base;
-    uint8_t* ho = c->h[1].as<uint8_t>() + J->kout_base;
-    OrbLevelsDev LV;
-    for (int l = 0; l < nl; l++) {
-      LV.raw[l] = J->P.raw[l];
-      LV.blur[l] = J->P.blur[l];
-      LV.w[l] = L.w[l];
-      LV.h[l] = L.h[l];
-    }
-    OrbDescribeMirror M;
-    M.h_angle = (float*)(ho + J->o_ang);
-    M.h_desc = (uint32_t*)(ho + J->o_desc);
-    M.sx_in = sx;
-    M.sy_in = sy;
-    M.d_sx = (float*)(din + J->i_sx);
-    M.d_sy = (float*)(din + J->i_sy);
-    M.d_lvl = (int*)(din + J->i_kl);
-    const int warps_per_cta = 8;
-    // keypoints are read straight from the pinned staging block (hx, hy, hl are host pointers);
-    // A/B on one box against H2D + kernel + D2H: 0.200 vs 0.209 ms per 640x480 frame
-    LORB_LAUNCH(c, orb_describe_kernel, (J->n_total + warps_per_cta - 1) / warps_per_cta, warps_per_cta * 32, 0, LV,
-                J->n_total, (const float*)hx, (const float*)hy, (const int*)hl, (const OrbTables*)d_tab,
-                (float*)(dout + J->o_ang), (uint32_t*)(dout + J->o_desc), 0, M);
-    J->d_sx = M.d_sx;
-    J->d_sy = M.d_sy;
-    J->d_lvl = M.d_lvl;
-    J->d_desc = (const uint32_t*)(dout + J->o_desc);
-    tr.mark("describe queued");
+    Q.n_levels = nl;
+    Q.tab = (const OrbTables*)(d + J->o_tab);
+    Q.cap = key_cap;
+    Q.h_x = (float*)(hp + J->h_x);
+    Q.h_y = (float*)(hp + J->h_y);
+    Q.h_oct = (int*)(hp + J->h_oct);
+    Q.h_angle = (float*)(hp + J->h_ang);
+    Q.h_resp = (float*)(hp + J->h_resp);
+    Q.h_desc = (uint32_t*)(hp + J->h_desc);
+    Q.d_x = (float*)(d + J->o_dx);
+    Q.d_y = (float*)(d + J->o_dy);
+    Q.d_oct = (int*)(d + J->o_doct);
+    Q.d_desc = (uint32_t*)(d + J->o_ddesc);
+    LORB_LAUNCH(c, orb_describe_selected_kernel, (key_cap + 7) / 8, 256, 0, Q);
     return LORB_OK;
   }
 
@@ -1035,32 +1010,65 @@ struct OrbPipeline {
     return LORB_OK;
   }
 
-  // After the stream has been synchronised: scatter the results into the caller's arrays.
-  void finish(OrbJob* J) {
+  // After the stream has been synchronised: counts, then the results into the caller's arrays.
+  int collect(OrbJob* J) {
     const ExtractOut& O = J->O;
-    if (J->n_total > 0 && (want_desc || O.kangle)) {
-      const uint8_t* h = c->h[0].as<uint8_t>() + J->kin_base;
-      const float *sx = (const float*)(h + J->i_sx), *sy = (const float*)(h + J->i_sy);
-      const uint8_t* ho = c->h[1].as<uint8_t>() + J->kout_base;
-      int k = 0;
+    const uint8_t* hp = c->h[2].as<uint8_t>() + J->pin_base;
+    const int* cnt = (const int*)(hp + J->h_count);
+    J->n_total = 0;
+    for (int l = 0; l < nl; l++) {
+      LORB_REQUIRE(cnt[l] >= 0 && cnt[l] <= out_cap[l], "device quadtree ran out of node slots (internal)");
+      J->n_level[l] = cnt[l];
+      J->n_total += cnt[l];
+    }
+    if (O.cand_level_start) {  // vToDistributeKeys (:813), for lorb_orb_stages: fetch the slots
+      std::vector<uint32_t> slots((size_t)n_cells * slot_cap);
+      std::vector<int> ccnt(n_cells);
+      const uint8_t* d = c->d[3].as<uint8_t>() + J->dev_base;
+      LORB_CUDA_TRY(cudaMemcpy(slots.data(), d + J->o_slots, slots.size() * 4, cudaMemcpyDeviceToHost));
+      LORB_CUDA_TRY(cudaMemcpy(ccnt.data(), d + J->o_cnt, ccnt.size() * 4, cudaMemcpyDeviceToHost));
+      int total = 0;
       for (int l = 0; l < nl; l++) {
-        const float patch = (float)(int)(31 * L.scale[l]);  // scaledPatchSize = PATCH_SIZE*mvScaleFactor (:868)
-        for (int id : J->chosen[l]) {
-          if (O.kx) O.kx[k] = sx[k];
-          if (O.ky) O.ky[k] = sy[k];
-          if (O.koct) O.koct[k] = l;
-          if (O.kangle) O.kangle[k] = ((const float*)(ho + J->o_ang))[k];
-          if (O.kresp) O.kresp[k] = J->keys[l][id].response;
-          if (O.ksize) O.ksize[k] = patch;
-          k++;
+        O.cand_level_start[l] = total;
+        for (int k = J->P.cell_start[l]; k < J->P.cell_start[l + 1]; k++) {
+          LORB_REQUIRE(ccnt[k] >= 0 && ccnt[k] <= slot_cap, "candidate slot overflow (internal)");
+          LORB_REQUIRE(total + ccnt[k] <= O.cand_cap, "candidate capacity");
+          for (int e = 0; e < ccnt[k]; e++) {
+            const uint32_t v = slots[(size_t)k * slot_cap + e];
+            O.cand_x[total] = (float)(v & 0xfff);
+            O.cand_y[total] = (float)((v >> 12) & 0xfff);
+            O.cand_resp[total] = (float)(v >> 24);
+            total++;
+          }
         }
       }
-      if (want_desc) memcpy(O.desc, ho + J->o_desc, (size_t)J->n_total * 32);
+      O.cand_level_start[nl] = total;
+    }
+    if (O.n_out) {
+      *O.n_out = J->n_total;
+      LORB_REQUIRE(J->n_total <= O.cap, "keypoint capacity (nfeatures + a few: the quadtree stops at >= N per level)");
+    }
+    if (O.kx || O.desc) {
+      const int n = J->n_total;
+      if (O.kx) memcpy(O.kx, hp + J->h_x, (size_t)n * 4);
+      if (O.ky) memcpy(O.ky, hp + J->h_y, (size_t)n * 4);
+      if (O.koct) memcpy(O.koct, hp + J->h_oct, (size_t)n * 4);
+      if (O.kangle) memcpy(O.kangle, hp + J->h_ang, (size_t)n * 4);
+      if (O.kresp) memcpy(O.kresp, hp + J->h_resp, (size_t)n * 4);
+      if (O.desc) memcpy(O.desc, hp + J->h_desc, (size_t)n * 32);
+      if (O.ksize) {
+        int k = 0;
+        for (int l = 0; l < nl; l++) {
+          const float patch = (float)(int)(31 * L.scale[l]);  // scaledPatchSize = PATCH_SIZE*mvScaleFactor (:868)
+          for (int i = 0; i < J->n_level[l]; i++) O.ksize[k++] = patch;
+        }
+      }
     }
     if (O.n_per_level)
-      for (int l = 0; l < nl; l++) O.n_per_level[l] = (int)J->chosen[l].size();
+      for (int l = 0; l < nl; l++) O.n_per_level[l] = J->n_level[l];
     if (O.level_w)
       for (int l = 0; l < nl; l++) O.level_w[l] = L.w[l], O.level_h[l] = L.h[l];
+    return LORB_OK;
   }
 };
 
@@ -1077,13 +1085,11 @@ int orb_run(lorb_ctx* c, const uint8_t* image, int width, int height, int step, 
   J.O = O;
   pl.layout(&J, 0);
   LORB_TRY(pl.reserve(1));
-  LORB_TRY(pl.detect(&J));
-  LORB_TRY(pl.select(&J));
-  LORB_TRY(pl.describe(&J));
+  LORB_TRY(pl.launch(&J));
   LORB_TRY(pl.queue_level_copies(&J));
   LORB_CUDA_TRY(cudaStreamSynchronize(c->stream));
   pl.tr.mark("stream drained");
-  pl.finish(&J);
+  LORB_TRY(pl.collect(&J));
   pl.tr.mark("results scattered");
   return LORB_OK;
 }
@@ -1135,6 +1141,7 @@ int lorb_orb_distribute_gpu(lorb_ctx* c, int n_keys, const float* x, const float
   QtLevel& L = A.lv[0];
   L.keys = (const uint32_t*)(d + o_keys);
   L.n_keys = n_keys;
+  L.key_cap = n_keys;
   L.width = max_x - min_x;
   L.height = max_y - min_y;
   L.n_features = n_features;
@@ -1224,12 +1231,15 @@ int lorb_stereo_frame(lorb_ctx* c, const uint8_t* left, const uint8_t* right, in
     pl.layout(&J[j], j);
   }
   LORB_TRY(pl.reserve(2));
-  LORB_TRY(pl.detect(&J[0]));
-  LORB_TRY(pl.detect(&J[1]));
-  LORB_TRY(pl.select(&J[0]));
-  LORB_TRY(pl.describe(&J[0]));
-  LORB_TRY(pl.select(&J[1]));
-  LORB_TRY(pl.describe(&J[1]));
+  // both frames go through their graphs back to back; the host needs the two keypoint counts to
+  // size the stereo launch, so it waits once here and once at the end
+  LORB_TRY(pl.launch(&J[0]));
+  LORB_TRY(pl.launch(&J[1]));
+  LORB_TRY(pl.queue_level_copies(&J[0]));
+  LORB_TRY(pl.queue_level_copies(&J[1]));
+  LORB_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  LORB_TRY(pl.collect(&J[0]));
+  LORB_TRY(pl.collect(&J[1]));
   const int n_left = J[0].n_total, n_right = J[1].n_total;
   if (n_matched) *n_matched = 0;
   size_t o_ur = 0, o_dp = 0, o_n = 0;
@@ -1269,13 +1279,7 @@ int lorb_stereo_frame(lorb_ctx* c, const uint8_t* left, const uint8_t* right, in
     uint8_t* ds = c->d[4].as<uint8_t>();
     LORB_TRY(stereo_launch(c, S, (float*)(ds + o_ur), (float*)(ds + o_dp), (int*)(ds + o_sad), (int*)(ds + o_n)));
     LORB_CUDA_TRY(cudaMemcpyAsync(c->h[3].as<uint8_t>(), ds, o_sad, cudaMemcpyDeviceToHost, c->stream));
-  }
-  LORB_TRY(pl.queue_level_copies(&J[0]));
-  LORB_TRY(pl.queue_level_copies(&J[1]));
-  LORB_CUDA_TRY(cudaStreamSynchronize(c->stream));
-  pl.finish(&J[0]);
-  pl.finish(&J[1]);
-  if (n_left > 0) {
+    LORB_CUDA_TRY(cudaStreamSynchronize(c->stream));
     const uint8_t* hs = c->h[3].as<uint8_t>();
     memcpy(out_uright, hs + o_ur, (size_t)n_left * 4);
     memcpy(out_depth, hs + o_dp, (size_t)n_left * 4);

@@ -34,9 +34,18 @@ struct QtLevel {
   // scratch (device), sized by the host: see qt_scratch_ints()
   int* scratch;
   int node_cap;          // capacity of the node table
+  // optional: the candidates still sit in the FAST kernel's per-cell slots (cells of this level in
+  // (row, column) order, row-major inside a cell); they are flattened into keys_flat first and
+  // `keys` / `n_keys` are ignored
+  const uint32_t* slots;
+  const int* cell_cnt;
+  int n_cells, slot_cap;
+  uint32_t* keys_flat;
+  int key_cap;           // capacity the scratch was sized for (>= number of keys)
   // outputs
-  int* out_index;        // [<= N + 3] chosen key indices in list order
-  int* out_count;
+  int* out_index;        // [qt_out_cap] chosen key indices in list order
+  int* out_count;        // device
+  int* out_count_host;   // mapped pinned copy (may be NULL)
 };
 
 struct QtArgs {
@@ -56,7 +65,7 @@ inline int qt_node_cap(int n_keys, int n_features, int n_ini) {
 // that the very first pass is unconditional and may turn the n_ini initial nodes into 4 * n_ini.
 inline int qt_out_cap(int n_features, int n_ini) { return std::max(n_features + 3, 4 * n_ini) + 4; }
 
-__host__ __device__ inline size_t qt_scratch_ints(int n_keys, int node_cap) {
+__host__ __device__ inline size_t qt_scratch_ints(int n_keys, int node_cap) {  // n_keys = key_cap
   // per key: node id, quadrant; per node: x0,x1,y0,y1,cnt,pos,flags,sel, best(2); lists x2; slots 3x4
   return (size_t)2 * n_keys + (size_t)10 * node_cap + (size_t)2 * node_cap + (size_t)12 * node_cap + 64;
 }
@@ -103,14 +112,12 @@ __global__ void __launch_bounds__(QT_THREADS) orb_quadtree_kernel(QtArgs A) {
   __shared__ int s_warp[32];
   __shared__ int s_total, s_misc[8];
   const int tid = threadIdx.x;
-  const int K = L.n_keys, N = L.n_features, cap = L.node_cap;
-  if (tid == 0) *L.out_count = 0;
+  const int N = L.n_features, cap = L.node_cap;
   const int n_ini = (int)roundf(__fdiv_rn((float)L.width, (float)L.height));
-  if (K == 0 || n_ini < 1) return;  // (the reference divides by zero for n_ini == 0)
   // ---- carve the scratch
   int* q = L.scratch;
-  int* key_node = q;            q += K;
-  int* key_quad = q;            q += K;
+  int* key_node = q;            q += L.key_cap;
+  int* key_quad = q;            q += L.key_cap;
   int* nx0 = q;                 q += cap;
   int* nx1 = q;                 q += cap;
   int* ny0 = q;                 q += cap;
@@ -129,6 +136,29 @@ __global__ void __launch_bounds__(QT_THREADS) orb_quadtree_kernel(QtArgs A) {
   int* crank = q;               q += 4 * cap;  // ... creation ranks of the non-empty ones
   int* scan = q;                q += 4 * cap;  // general scan buffer
 
+  // ---- candidates: given, or flattened from the per-cell slots
+  const uint32_t* keys = L.keys;
+  int K = L.n_keys;
+  if (L.slots) {
+    for (int i = tid; i < L.n_cells; i += QT_THREADS) scan[i] = min(L.cell_cnt[i], L.slot_cap);
+    __syncthreads();
+    K = qt_block_scan(scan, L.n_cells, s_warp, &s_total);
+    if (K > L.key_cap) K = 0;  // cannot happen (key_cap = cells x slot_cap); reported through the count
+    for (int c = tid >> 5; c < L.n_cells; c += QT_THREADS / 32) {
+      const int n = min(L.cell_cnt[c], L.slot_cap), off = scan[c];
+      for (int e = tid & 31; e < n && off + e < L.key_cap; e += 32)
+        L.keys_flat[off + e] = L.slots[(size_t)c * L.slot_cap + e];
+    }
+    __syncthreads();
+    keys = L.keys_flat;
+  }
+  if (K == 0 || n_ini < 1) {  // (the reference divides by zero for n_ini == 0)
+    if (tid == 0) {
+      *L.out_count = 0;
+      if (L.out_count_host) *L.out_count_host = 0;
+    }
+    return;
+  }
   const float h_x = __fdiv_rn((float)L.width, (float)n_ini);
   // ---- initial nodes (:571-594): key -> column (int)(x / hX)
   for (int i = tid; i < n_ini; i += QT_THREADS) {
@@ -140,7 +170,7 @@ __global__ void __launch_bounds__(QT_THREADS) orb_quadtree_kernel(QtArgs A) {
   }
   __syncthreads();
   for (int k = tid; k < K; k += QT_THREADS) {
-    const float x = (float)(L.keys[k] & 0xfff);
+    const float x = (float)(keys[k] & 0xfff);
     const int col = min((int)__fdiv_rn(x, h_x), n_ini - 1);
     key_node[k] = col;
     atomicAdd(&ncnt[col], 1);
@@ -195,7 +225,10 @@ __global__ void __launch_bounds__(QT_THREADS) orb_quadtree_kernel(QtArgs A) {
     }
     if (S == 0) break;  // nothing left to split: size == prev_size in the reference
     if (next_id + 4 * S > cap) {  // cannot happen for node_cap sized by the host; fail loudly
-      if (tid == 0) *L.out_count = -1;
+      if (tid == 0) {
+        *L.out_count = -1;
+        if (L.out_count_host) *L.out_count_host = -1;
+      }
       return;
     }
     // ---- quadrant of every key of a selected node, child counts (DivideNode :496-551)
@@ -204,7 +237,7 @@ __global__ void __launch_bounds__(QT_THREADS) orb_quadtree_kernel(QtArgs A) {
     for (int k = tid; k < K; k += QT_THREADS) {
       const int nd = key_node[k], s = nsel[nd];
       if (s < 0) continue;
-      const uint32_t e = L.keys[k];
+      const uint32_t e = keys[k];
       const float x = (float)(e & 0xfff), y = (float)((e >> 12) & 0xfff);
       const int hx = (int)ceilf(__fdiv_rn((float)(nx1[nd] - nx0[nd]), 2.0f));
       const int hy = (int)ceilf(__fdiv_rn((float)(ny1[nd] - ny0[nd]), 2.0f));
@@ -299,13 +332,16 @@ __global__ void __launch_bounds__(QT_THREADS) orb_quadtree_kernel(QtArgs A) {
   for (int i = tid; i < next_id; i += QT_THREADS) best[i] = 0ull;
   __syncthreads();
   for (int k = tid; k < K; k += QT_THREADS) {
-    const unsigned long long v = ((unsigned long long)(L.keys[k] >> 24) << 32) | (0xffffffffu - (unsigned)k);
+    const unsigned long long v = ((unsigned long long)(keys[k] >> 24) << 32) | (0xffffffffu - (unsigned)k);
     atomicMax(&best[key_node[k]], v);
   }
   __syncthreads();
   for (int p = tid; p < size; p += QT_THREADS)
     L.out_index[p] = (int)(0xffffffffu - (unsigned)(best[list[p]] & 0xffffffffull));
-  if (tid == 0) *L.out_count = size;
+  if (tid == 0) {
+    *L.out_count = size;
+    if (L.out_count_host) *L.out_count_host = size;
+  }
 }
 
 }  // namespace lorb
