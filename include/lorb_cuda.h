@@ -350,8 +350,8 @@ int lorb_stereo_frame(lorb_ctx* ctx, const uint8_t* left, const uint8_t* right, 
 int lorb_orb_distribute(int n_keys, const float* x, const float* y, const float* response, int min_x,
                         int max_x, int min_y, int max_y, int n_features, int* out_index, int* n_out);
 
-/* lorb_orb_distribute evaluated on the device (one CTA; what lorb_orb_extract runs between the FAST
- * and the descriptor kernels).  Keys must be integer pixels below 4096 with integer responses
+/* lorb_orb_distribute evaluated on the device (one CTA per level: what lorb_orb_extract runs between
+ * the FAST and the descriptor kernels).  Keys must be integer pixels below 4096 with integer responses
  * below 256, which is what the FAST stage produces. */
 int lorb_orb_distribute_gpu(lorb_ctx* ctx, int n_keys, const float* x, const float* y,
                             const float* response, int min_x, int max_x, int min_y, int max_y,

@@ -65,7 +65,6 @@ struct lorb_ctx {
   void* ba_cache = nullptr;  // reusable lorb_ba_problem of the host-buffer BA calls (ba_local.cu)
   // cached CUDA graphs of the ORB extractor's detection chain (orb.cu), one per job slot
   void* orb_graph[2] = {nullptr, nullptr};
-  unsigned orb_seq = 0;  // call counter carried in the frame header
   cudaStream_t orb_stream2 = nullptr;  // side branch of the extractor graph (capture only)
   cudaEvent_t orb_ev[2] = {nullptr, nullptr};
   // optional event timing of the library's own kernels (lorb_ctx_profile)

@@ -1,6 +1,8 @@
-// orb.cu — the descriptor side of ORBextractor (reference src/ORBextractor.cpp; SURVEY 8(f)
-// rank 5): intensity-centroid orientation (IC_Angle :79-106) and the steered BRIEF descriptor
-// (computeOrbDescriptor :110-149) for keypoints given in the coordinates of their pyramid level.
+// orb.cu — ORBextractor (reference src/ORBextractor.cpp): pyramid, FAST per
+// cell, quadtree selection (orb_quadtree_gpu.cuh), blur, orientation and descriptors, one CUDA graph
+// per frame (see OrbPipeline::launch).  First the descriptor side: intensity-centroid orientation
+// (IC_Angle :79-106) and the steered BRIEF descriptor (computeOrbDescriptor :110-149) for keypoints
+// given in the coordinates of their pyramid level.
 //
 // One warp per keypoint.  Orientation: lane r owns patch row v = r - 15 (31 rows of the circular
 // patch, half width umax[|v|]); the two moments are integer sums, so any summation order gives
@@ -294,12 +296,6 @@ struct OrbPlanDev {
   int n_cols[ORB_MAX_LEVELS], w_cell[ORB_MAX_LEVELS], h_cell[ORB_MAX_LEVELS];
   int slot_cap;                        // candidate slots per cell
   int ini_th, min_th;
-  // completion signalling of the FAST kernel: per level a device counter of finished cells; the
-  // CTA that finishes last stores the call's sequence number (read from *seq) into the level's
-  // flag in mapped pinned host memory
-  int* done_ctr;
-  volatile unsigned* host_flag;
-  const unsigned* seq;
 };
 
 // cv::GaussianBlur(7x7, sigma 2, BORDER_REFLECT_101) of an 8-bit image in OpenCV 4's fixed-point
@@ -359,8 +355,8 @@ __global__ void __launch_bounds__(256) orb_blur_kernel(OrbPlanDev P) {
 // suppression flags, block vote for "iniThFAST found something", ordered (row-major, as cv::FAST
 // emits) compaction into the cell's slot.  Candidates are packed score<<24 | y<<12 | x with x, y
 // relative to the level's 16-px margin (what the reference hands to DistributeOctTree).  The slots
-// and the per-cell counts live in mapped pinned host memory: the quadtree runs on the host, so the
-// few thousand 4-byte candidates go straight over PCIe and no gather kernel or copy is needed.
+// and the per-cell counts stay in device memory: the quadtree kernel (orb_quadtree_gpu.cuh) flattens
+// them into the reference's candidate order (cell row, cell column, row-major inside the cell).
 constexpr int CELL_MAX = 68;  // cell image side: wCell + 6 < 60 + 6
 
 __device__ __forceinline__ int arc9_min_max(const int (&d)[16]) {
@@ -472,20 +468,7 @@ __global__ void __launch_bounds__(256)
     __syncthreads();
   }
   }  // active
-  // publish (the pattern of a grid barrier): block barrier, then one thread fences at system
-  // scope -- cumulative over the block's stores to host memory it has synchronised with -- and
-  // counts the cell in; the last cell of the level raises the level's flag
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    cell_count[cell] = active ? s_base : 0;
-    if (P.host_flag) __threadfence_system();
-    const int n_level = P.cell_start[l + 1] - P.cell_start[l];
-    if (P.host_flag && atomicAdd(&P.done_ctr[l], 1) == n_level - 1) {
-      P.done_ctr[l] = 0;  // ready for the next call (stream ordered)
-      __threadfence_system();
-      P.host_flag[l] = *P.seq;
-    }
-  }
+  if (threadIdx.x == 0) cell_count[cell] = active ? s_base : 0;
 }
 
 // ------------------------------------------------------------------ host: level plan + quadtree
@@ -695,10 +678,10 @@ struct OrbJob {
   int slot = 0;  // which cached graph / buffer half of the context this job uses
   // layout: offsets into the job's device area (d[3]) and pinned area (h[2])
   size_t dev_base = 0, pin_base = 0;
-  size_t o_hdr = 0, o_raw[ORB_MAX_LEVELS], o_blur[ORB_MAX_LEVELS], o_ctr = 0, o_tab = 0, o_slots = 0, o_cnt = 0;
+  size_t o_raw[ORB_MAX_LEVELS], o_blur[ORB_MAX_LEVELS], o_tab = 0, o_slots = 0, o_cnt = 0;
   size_t o_keys[ORB_MAX_LEVELS], o_qscr[ORB_MAX_LEVELS], o_chosen[ORB_MAX_LEVELS], o_count = 0;
   size_t o_dx = 0, o_dy = 0, o_doct = 0, o_ddesc = 0;
-  size_t h_hdr = 0, h_img = 0, h_count = 0, h_x = 0, h_y = 0, h_oct = 0, h_ang = 0, h_resp = 0, h_desc = 0;
+  size_t h_img = 0, h_count = 0, h_x = 0, h_y = 0, h_oct = 0, h_ang = 0, h_resp = 0, h_desc = 0;
   OrbPlanDev P;
   int n_total = 0;
   int n_level[ORB_MAX_LEVELS];
@@ -758,10 +741,8 @@ struct OrbPipeline {
   // Offsets of job j inside the shared device / pinned buffers.
   void layout(OrbJob* J, int j) {
     OPacker dv;
-    J->o_hdr = dv.add(256);  // [call number | pad], contiguous with level 0: one H2D copy brings both
     for (int l = 0; l < nl; l++) J->o_raw[l] = dv.add((size_t)L.w[l] * L.h[l]);
     for (int l = 0; l < nl; l++) J->o_blur[l] = dv.add((size_t)L.w[l] * L.h[l]);
-    J->o_ctr = dv.add(ORB_MAX_LEVELS * 4);
     J->o_tab = dv.add(sizeof(OrbTables));
     J->o_slots = dv.add((size_t)n_cells * slot_cap * 4);
     J->o_cnt = dv.add((size_t)n_cells * 4);
@@ -778,7 +759,6 @@ struct OrbPipeline {
     dev_bytes = dv.off;
     J->dev_base = (size_t)j * dev_bytes;
     OPacker hs;
-    J->h_hdr = hs.add(256);
     J->h_img = hs.add((size_t)width * height);
     J->h_count = hs.add(ORB_MAX_LEVELS * 4);
     J->h_x = hs.add((size_t)key_cap * 4);
@@ -804,7 +784,7 @@ struct OrbPipeline {
 
   // One frame = ONE CUDA-graph launch.  The graph (captured once per frame size, parameters and
   // buffers) holds the whole extractor:
-  //     H2D [call number | frame]
+  //     H2D frame
   //     FAST level 0 ------------------> quadtree level 0 (side branch)
   //     resize x7 -> FAST levels 1..7 -> quadtree levels 1..7 -> blur
   //     (join) orientation + descriptors of the selected keypoints, results written to pinned memory
@@ -837,9 +817,6 @@ struct OrbPipeline {
     P.tile_start[nl] = tiles;
     P.cell_start[nl] = cells;
     P.slot_cap = slot_cap;
-    P.done_ctr = (int*)(d + J->o_ctr);
-    P.host_flag = nullptr;  // the consumer of the candidates is the next kernel, not the host
-    P.seq = (const unsigned*)(d + J->o_hdr);
 
     OrbGraph*& G = reinterpret_cast<OrbGraph*&>(c->orb_graph[J->slot]);
     OrbGraphKey key;
@@ -893,7 +870,6 @@ struct OrbPipeline {
       }
       G = ng;
     }
-    *(unsigned*)(hp + J->h_hdr) = ++c->orb_seq;
     if (J->step == width) {
       memcpy(hp + J->h_img, J->image, (size_t)width * height);
     } else {
@@ -933,8 +909,7 @@ struct OrbPipeline {
   int capture_chain(OrbJob* J, uint8_t* d, uint8_t* hp) {
     const OrbPlanDev& P = J->P;
     cudaStream_t s = c->stream, s2 = c->orb_stream2;
-    // the header and level 0 are contiguous on both sides
-    LORB_CUDA_TRY(cudaMemcpyAsync(d + J->o_hdr, hp + J->h_hdr, 256 + (size_t)width * height, cudaMemcpyHostToDevice, s));
+    LORB_CUDA_TRY(cudaMemcpyAsync(d + J->o_raw[0], hp + J->h_img, (size_t)width * height, cudaMemcpyHostToDevice, s));
     uint32_t* slots = (uint32_t*)(d + J->o_slots);
     int* cnt = (int*)(d + J->o_cnt);
     // level 0 holds 40 % of the candidates and has the longest quadtree: its FAST runs first and its
