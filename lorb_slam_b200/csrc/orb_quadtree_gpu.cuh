@@ -66,8 +66,8 @@ inline int qt_node_cap(int n_keys, int n_features, int n_ini) {
 inline int qt_out_cap(int n_features, int n_ini) { return std::max(n_features + 3, 4 * n_ini) + 4; }
 
 __host__ __device__ inline size_t qt_scratch_ints(int n_keys, int node_cap) {  // n_keys = key_cap
-  // per key: node id, quadrant; per node: x0,x1,y0,y1,cnt,pos,flags,sel, best(2); lists x2; slots 3x4
-  return (size_t)2 * n_keys + (size_t)10 * node_cap + (size_t)2 * node_cap + (size_t)12 * node_cap + 64;
+  // per key: node id, quadrant; per node: 10 fields, best (2 + alignment), two lists, three 4-wide slot arrays
+  return (size_t)2 * n_keys + (size_t)27 * node_cap + 64;
 }
 
 // In-place exclusive prefix sum of data[0..n) by the whole CTA; returns the total (to every thread).
