@@ -86,7 +86,7 @@ __device__ inline int qt_block_scan(int* data, int n, int* s_warp, int* s_total)
   if (lane == 31) s_warp[warp] = inc;
   __syncthreads();
   if (warp == 0) {
-    int w = s_warp[lane];
+    int w = lane < QT_THREADS / 32 ? s_warp[lane] : 0;
     int winc = w;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
