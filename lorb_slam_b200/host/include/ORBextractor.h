@@ -5,8 +5,8 @@
 // example/test.cpp keep compiling unchanged.  What is gone is the CPU machinery behind it
 // (ExtractorNode, ComputePyramid, ComputeKeyPointsOctTree, DistributeOctTree): the body
 // (src/ORBextractor.cpp of this directory) hands the image to lorb_orb_extract
-// (include/lorb_cuda.h), which runs the pyramid, FAST, blur, orientation and descriptors as sm_100a
-// kernels and the quadtree selection on the host.
+// (include/lorb_cuda.h), which runs the pyramid, FAST, the quadtree selection, blur, orientation and
+// descriptors as sm_100a kernels: one CUDA graph per frame.
 #ifndef ORBEXTRACTOR_H
 #define ORBEXTRACTOR_H
 
