@@ -67,6 +67,8 @@ struct lorb_ctx {
   void* orb_graph[2] = {nullptr, nullptr};
   cudaStream_t orb_stream2 = nullptr;  // side branch of the extractor graph (capture only)
   cudaEvent_t orb_ev[2] = {nullptr, nullptr};
+  cudaStream_t orb_stream3 = nullptr;  // second frame of a stereo pair runs its graph here, concurrently
+  cudaEvent_t orb_join = nullptr;
   // optional event timing of the library's own kernels (lorb_ctx_profile)
   int prof_on = 0;
   void* prof = nullptr;  // lorb::Prof (ctx.cu)

@@ -547,6 +547,14 @@ void orb_graph_free(lorb_ctx* c) {
     cudaStreamDestroy(c->orb_stream2);
     c->orb_stream2 = nullptr;
   }
+  if (c->orb_stream3) {
+    cudaStreamDestroy(c->orb_stream3);
+    c->orb_stream3 = nullptr;
+  }
+  if (c->orb_join) {
+    cudaEventDestroy(c->orb_join);
+    c->orb_join = nullptr;
+  }
 }
 
 }  // namespace lorb
@@ -778,6 +786,8 @@ struct OrbPipeline {
     if (!c->orb_stream2) {
       LORB_CUDA_TRY(cudaStreamCreateWithFlags(&c->orb_stream2, cudaStreamNonBlocking));
       for (auto& e : c->orb_ev) LORB_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      LORB_CUDA_TRY(cudaStreamCreateWithFlags(&c->orb_stream3, cudaStreamNonBlocking));
+      LORB_CUDA_TRY(cudaEventCreateWithFlags(&c->orb_join, cudaEventDisableTiming));
     }
     return LORB_OK;
   }
@@ -791,7 +801,8 @@ struct OrbPipeline {
   // Issued one by one these 13 operations cost the host more time than the GPU needs to run them,
   // and a quadtree on the host (orb_quadtree.h, 80 us for level 0) would sit in the middle of the
   // chain; as a graph the host stages the frame, launches, and waits once.
-  int launch(OrbJob* J) {
+  int launch(OrbJob* J, cudaStream_t run_on = nullptr) {
+    if (!run_on) run_on = c->stream;
     OrbPlanDev& P = J->P;
     memset(&P, 0, sizeof(P));
     P.n_levels = nl;
@@ -876,7 +887,7 @@ struct OrbPipeline {
       for (int r = 0; r < height; r++) memcpy(hp + J->h_img + (size_t)r * width, J->image + (size_t)r * J->step, width);
     }
     tr.mark("frame staged");
-    LORB_CUDA_TRY(cudaGraphLaunch(G->exec, c->stream));
+    LORB_CUDA_TRY(cudaGraphLaunch(G->exec, run_on));
     c->launches += G->n_kernels;
     tr.mark("graph launched");
     J->d_sx = (const float*)(d + J->o_dx);
@@ -1206,10 +1217,13 @@ int lorb_stereo_frame(lorb_ctx* c, const uint8_t* left, const uint8_t* right, in
     pl.layout(&J[j], j);
   }
   LORB_TRY(pl.reserve(2));
-  // both frames go through their graphs back to back; the host needs the two keypoint counts to
-  // size the stereo launch, so it waits once here and once at the end
+  // the two frames are independent: their graphs run concurrently on two streams (the reference
+  // uses two host threads); the host needs the two keypoint counts to size the stereo launch, so it
+  // waits once here and once at the end
   LORB_TRY(pl.launch(&J[0]));
-  LORB_TRY(pl.launch(&J[1]));
+  LORB_TRY(pl.launch(&J[1], c->orb_stream3));
+  LORB_CUDA_TRY(cudaEventRecord(c->orb_join, c->orb_stream3));
+  LORB_CUDA_TRY(cudaStreamWaitEvent(c->stream, c->orb_join, 0));
   LORB_TRY(pl.queue_level_copies(&J[0]));
   LORB_TRY(pl.queue_level_copies(&J[1]));
   LORB_CUDA_TRY(cudaStreamSynchronize(c->stream));
