@@ -14,7 +14,6 @@
 #include <stdlib.h>
 
 #include <algorithm>
-#include <atomic>
 #include <chrono>
 #include <utility>
 #include <vector>
