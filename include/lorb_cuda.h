@@ -293,8 +293,8 @@ int lorb_orb_describe(lorb_ctx* ctx, const lorb_pyramid_view* raw, const lorb_py
  * (the reference compares node addresses, :695) is creation order: last created first.
  *   params       the ORBextractor constructor arguments (:412-415)
  *   pattern      as lorb_orb_describe
- *   cap          capacity of the output arrays; the extractor returns slightly more than
- *                nfeatures (each level stops at >= its share), nfeatures + 64 is safe
+ *   cap          capacity of the output arrays (lorb_orb_max_keypoints gives the bound; the extractor
+ *                usually returns slightly more than nfeatures); LORB_ERR_ARG if it is too small
  * Outputs in the reference's order (level by level, nodes in list order): KeyPoint pt.x, pt.y,
  * octave, angle, response (may be NULL), size (may be NULL), descriptor rows; *n_out keypoints.
  * raw_levels (may be NULL): [nlevels] host buffers of level_w*level_h bytes (lorb_orb_level_sizes)
@@ -356,6 +356,12 @@ int lorb_orb_distribute(int n_keys, const float* x, const float* y, const float*
 int lorb_orb_distribute_gpu(lorb_ctx* ctx, int n_keys, const float* x, const float* y,
                             const float* response, int min_x, int max_x, int min_y, int max_y,
                             int n_features, int* out_index, int* n_out);
+
+/* Upper bound of the number of keypoints the extractor can return for this frame size: usually a few
+ * more than nfeatures (each level stops at >= its share), but a wide level with a small share keeps
+ * 4 nodes per initial quadtree column whatever its budget (src/ORBextractor.cpp:566-594, 610-672).
+ * Size the output arrays of lorb_orb_extract / lorb_stereo_frame with it. */
+int lorb_orb_max_keypoints(const lorb_orb_params* params, int width, int height, int* max_keypoints);
 
 /* Level geometry of the extractor: sizes of the pyramid levels (:1161-1163), mnFeaturesPerLevel
  * (:448-461, may be NULL) and mvScaleFactor (:428-436, may be NULL). */

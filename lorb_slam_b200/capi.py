@@ -26,7 +26,7 @@ EXPORTS = [
     "lorb_match_sweep_resident", "lorb_sweep_plan_upload", "lorb_sweep_plan_run",
     "lorb_sweep_plan_download", "lorb_sweep_plan_run_at", "lorb_search_proj_points", "lorb_search_proj_frame", "lorb_frustum_project", "lorb_compute_descriptors",
     "lorb_stereo_matches", "lorb_orb_describe", "lorb_orb_umax", "lorb_orb_selftest",
-    "lorb_orb_extract", "lorb_orb_level_sizes", "lorb_orb_stages", "lorb_stereo_frame", "lorb_orb_distribute", "lorb_orb_distribute_gpu",
+    "lorb_orb_extract", "lorb_orb_level_sizes", "lorb_orb_stages", "lorb_stereo_frame", "lorb_orb_distribute", "lorb_orb_distribute_gpu", "lorb_orb_max_keypoints",
     "lorb_ba_default_options", "lorb_ba_pose_only", "lorb_ba_local", "lorb_ba_local_batched",
     "lorb_ba_problem_create", "lorb_ba_problem_create_batched", "lorb_ba_problem_reset", "lorb_ba_problem_solve",
     "lorb_ba_problem_download", "lorb_ba_problem_destroy", "lorb_dist_get_unique_id",
@@ -353,12 +353,18 @@ class Context:
         _check(self._lib.lorb_orb_level_sizes(C.byref(prm), width, height, _ptr(w), _ptr(h), _ptr(nf), _ptr(sf)))
         return w, h, nf, sf
 
+    def orb_max_keypoints(self, width, height, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7):
+        prm = OrbParams(nfeatures, scale_factor, nlevels, ini_th, min_th)
+        n = C.c_int(0)
+        _check(self._lib.lorb_orb_max_keypoints(C.byref(prm), width, height, C.byref(n)))
+        return n.value
+
     def orb_extract(self, img, pattern, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7):
         """ORBextractor::operator() on one 8-bit image -> dict like oracle.reflib.orb_extract."""
         img = _arr(img, np.uint8)
         prm = OrbParams(nfeatures, scale_factor, nlevels, ini_th, min_th)
         pat = _arr(pattern, np.int32).reshape(-1)
-        cap = nfeatures + 64
+        cap = self.orb_max_keypoints(img.shape[1], img.shape[0], nfeatures, scale_factor, nlevels, ini_th, min_th)
         kx, ky = np.zeros(cap, np.float32), np.zeros(cap, np.float32)
         ko, ka = np.zeros(cap, np.int32), np.zeros(cap, np.float32)
         kr, ks = np.zeros(cap, np.float32), np.zeros(cap, np.float32)
@@ -379,7 +385,7 @@ class Context:
         assert left.shape == right.shape
         prm = OrbParams(nfeatures, scale_factor, nlevels, ini_th, min_th)
         pat = _arr(pattern, np.int32).reshape(-1)
-        cap = nfeatures + 64
+        cap = self.orb_max_keypoints(left.shape[1], left.shape[0], nfeatures, scale_factor, nlevels, ini_th, min_th)
         keep, views = [], []
         for _ in range(2):
             a = dict(x=np.zeros(cap, np.float32), y=np.zeros(cap, np.float32), octave=np.zeros(cap, np.int32),

@@ -1145,6 +1145,23 @@ int lorb_orb_distribute_gpu(lorb_ctx* c, int n_keys, const float* x, const float
   return LORB_OK;
 }
 
+// Upper bound of the number of keypoints ORBextractor::operator() can return for this geometry:
+// per level max(N_l + 3, 4 * nIni_l) -- the careful phase stops at the first split that reaches
+// N_l, but the first quadtree pass is unconditional and may already yield 4 nodes per initial
+// column (wide levels with small budgets return more than nfeatures in total).
+int lorb_orb_max_keypoints(const lorb_orb_params* prm, int width, int height, int* max_keypoints) {
+  LORB_REQUIRE(prm && max_keypoints, "arguments");
+  OrbLevelPlan L;
+  LORB_TRY(make_level_plan(prm, width, height, &L));
+  int total = 0;
+  for (int l = 0; l < L.n_levels; l++) {
+    const int bw = L.w[l] - 2 * ORB_EDGE + 6, bh = L.h[l] - 2 * ORB_EDGE + 6;
+    total += qt_out_cap(L.n_features[l], std::max(1, (int)roundf((float)bw / bh)));
+  }
+  *max_keypoints = total;
+  return LORB_OK;
+}
+
 int lorb_orb_level_sizes(const lorb_orb_params* prm, int width, int height, int* level_w, int* level_h,
                          int* n_features_per_level, float* scale_factors) {
   LORB_REQUIRE(prm && level_w && level_h, "arguments");

@@ -65,7 +65,8 @@ void ORBextractor::operator()(cv::InputArray _image, cv::InputArray /*mask*/, st
 		levels[l] = mvImagePyramid[l].ptr<uint8_t>();
 	}
 
-	const int cap = nfeatures + 64;  // every level stops at >= its share of nfeatures
+	int cap = 0;  // usually nfeatures + a few; wide levels with small shares can return more
+	LORB_HOST_CALL(lorb_orb_max_keypoints(&prm, image.cols, image.rows, &cap));
 	std::vector<float> x(cap), y(cap), angle(cap), response(cap), size(cap);
 	std::vector<int> octave(cap);
 	cv::Mat desc(cap, 32, CV_8U);

@@ -257,7 +257,7 @@ def orb_extract(img, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min
     """The reference's whole ORBextractor::operator() (src/ORBextractor.cpp:1087-1151) on one 8-bit
     image, run under the bump arena of ref_orb_harness.cpp (quadtree ties = creation order)."""
     img = np.ascontiguousarray(img, np.uint8)
-    cap = nfeatures + 64
+    cap = 4 * nfeatures + 1024  # wide levels with small budgets return more than their share
     kx, ky = np.zeros(cap, np.float32), np.zeros(cap, np.float32)
     ko, ka = np.zeros(cap, np.int32), np.zeros(cap, np.float32)
     kr, ks = np.zeros(cap, np.float32), np.zeros(cap, np.float32)
