@@ -258,3 +258,33 @@ def test_device_quadtree_matches_host_quadtree(ctx):
         a = capi.orb_distribute(x, y, r, 16, 16 + w, 16, 16 + h, nf)
         b = ctx.orb_distribute_gpu(x, y, r, 16, 16 + w, 16, 16 + h, nf)
         assert np.array_equal(a, b), (t, n, w, h, nf)
+
+
+def test_cuda_orb_extract_soak_vs_reference(ctx):
+    """A slice of profiles/scripts/orb_soak.py (300 frames there: 0 differ): varied frame sizes,
+    textures (low contrast, pure noise, half flat), budgets, level counts and thresholds, each
+    bit-exact against the compiled reference -- including wide frames with small budgets, which
+    return more keypoints than nfeatures + a few (lorb_orb_max_keypoints)."""
+    from oracle import reflib
+    if not reflib.available():
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(99)
+    over = 0
+    for f in range(28):
+        w, h = int(rng.choice([320, 512, 752, 1024, 1280])), int(rng.choice([240, 376, 480]))
+        img = synth.make_orb_image(500 + f, w, h)
+        if f % 4 == 1:
+            img = (128 + (img.astype(np.float32) - 128) * 0.15).astype(np.uint8)
+        elif f % 4 == 2:
+            img = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        elif f % 4 == 3:
+            img = img.copy()
+            img[:, : w // 2] = 100
+        nf, nl = int(rng.choice([100, 500, 2000])), int(rng.choice([4, 8]))
+        a = ctx.orb_extract(img, OC.pattern(), nfeatures=nf, nlevels=nl)
+        b = reflib.orb_extract(img, nfeatures=nf, nlevels=nl)
+        assert a["n"] == b["n"] <= ctx.orb_max_keypoints(w, h, nfeatures=nf, nlevels=nl), (f, w, h, nf, nl)
+        for k in ("x", "y", "octave", "angle", "response", "size", "desc"):
+            assert np.array_equal(a[k], b[k]), (f, k)
+        over += a["n"] > nf + 64
+    assert over > 0  # the case the fixed "nfeatures + 64" capacity used to miss
