@@ -287,4 +287,8 @@ def test_cuda_orb_extract_soak_vs_reference(ctx):
         for k in ("x", "y", "octave", "angle", "response", "size", "desc"):
             assert np.array_equal(a[k], b[k]), (f, k)
         over += a["n"] > nf + 64
-    assert over > 0  # the case the fixed "nfeatures + 64" capacity used to miss
+    # the case a fixed "nfeatures + 64" capacity misses: a wide frame with a small budget keeps 4 nodes
+    # per initial quadtree column on every level
+    img = synth.make_orb_image(640, 1280, 240)
+    a, b = ctx.orb_extract(img, OC.pattern(), nfeatures=100), reflib.orb_extract(img, nfeatures=100)
+    assert a["n"] == b["n"] > 100 + 64 and np.array_equal(a["desc"], b["desc"]) and np.array_equal(a["x"], b["x"])
