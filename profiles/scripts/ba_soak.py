@@ -1,0 +1,33 @@
+"""Soak: lorb_ba_local on random windows of every solver path (dense <= 10 cameras, privatised
+11..16, work lists > 16) against the fp64 oracle (rtol 1e-6), with fixed observers and varied
+observation counts per point."""
+import sys
+
+import numpy as np
+
+sys.path.insert(0, ".")
+from lorb_slam_b200 import capi, synth  # noqa: E402
+from oracle import ref  # noqa: E402
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 40
+rng = np.random.default_rng(77)
+bad = 0
+with capi.Context(0) as ctx:
+    for s in range(n):
+        C = int(rng.choice([2, 3, 5, 8, 10, 11, 14, 16, 17, 24, 40]))
+        P = int(rng.integers(30, 600))
+        k = tuple(int(v) for v in rng.choice(np.arange(2, min(C, 12) + 1), size=3))
+        ff = float(rng.choice([0.0, 0.0, 0.1, 0.3]))
+        pb = synth.make_ba_problem(900 + s, C=C, P=P, obs_per_point=k, fixed_frac=ff, traj_len=float(max(3.0, C * 0.4)))
+        it = int(rng.choice([3, 6, 50]))
+        kw = dict(max_num_iterations=it)
+        try:
+            cams, pts, sm = ctx.ba_local(pb, capi.ba_options(**kw))
+            oc, op, so = ref.ba_local(pb, ref.ba_options(**kw))
+            np.testing.assert_allclose(cams, oc, rtol=1e-6, atol=1e-8)
+            np.testing.assert_allclose(pts, op, rtol=1e-6, atol=1e-8)
+            assert sm["iterations"] == so["iterations"] and sm["termination"] == so["termination"]
+        except Exception as e:  # noqa: BLE001
+            bad += 1
+            print("MISMATCH", s, C, P, k, ff, it, str(e)[:200].replace("\n", " "))
+print("%d windows, %d differ" % (n, bad))

@@ -1,0 +1,40 @@
+"""Soak: the matching entry points against the compiled reference (oracle/_ref) on random inputs."""
+import sys
+
+import numpy as np
+
+sys.path.insert(0, ".")
+from lorb_slam_b200 import capi, synth  # noqa: E402
+from oracle import ref, reflib  # noqa: E402
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 40
+rng = np.random.default_rng(31)
+bad = {"proj_points": 0, "proj_frame": 0, "bf": 0, "frustum": 0, "stereo": 0}
+with capi.Context(0) as ctx:
+    for s in range(n):
+        nk, npt = int(rng.integers(50, 3000)), int(rng.integers(50, 6000))
+        fr = synth.make_frame(nk, 700 + s, stereo=bool(s % 2), claimed_frac=float(rng.choice([0, 0.2, 0.5])))
+        pts = synth.make_proj_points(fr, npt, 700 + s, nobs=(0, 1, 2), inactive_frac=0.1)
+        th = float(rng.choice([1.0, 2.0, 7.0, 15.0, 30.0]))
+        a, b = ctx.search_proj_points(fr, pts, th), reflib.search_proj_points(fr, pts, th)
+        bad["proj_points"] += not (a["n_matches"] == b["n_matches"] and np.array_equal(a["point_for_kp"], b["point_for_kp"]))
+        cur, last = synth.make_frame_pair(nk, 800 + s, motion=str(rng.choice(["forward", "backward", "still"])))
+        cur["kp_claim_obs"] = np.where(rng.random(nk) < 0.2, rng.integers(0, 3, nk), -1).astype(np.int32)
+        a, b = ctx.search_proj_frame(cur, last, th), reflib.search_proj_frame(cur, last, th)
+        bad["proj_frame"] += not (a["n_matches"] == b["n_matches"] and np.array_equal(
+            reflib.final_state_from_oracle(a["state_for_kp"], cur["kp_claim_obs"]), b["state_for_kp"]))
+        q = synth.descriptors_uniform(int(rng.integers(1, 1500)), rng)
+        t = synth.descriptors_noisy_copy(q[rng.integers(0, len(q), int(rng.integers(1, 1500)))], rng, 0.05)
+        a, o = ctx.match_bf_crosscheck(q, t), ref.bf_crosscheck(q, t)
+        bad["bf"] += not (np.array_equal(a["q"], o["q"]) and np.array_equal(a["t"], o["t"]) and np.array_equal(a["dist"], o["dist"]))
+        fp = synth.make_frustum_points(int(rng.integers(10, 8000)), 900 + s)
+        b, ow, lsf = reflib.frustum_project(fp)
+        fp2 = dict(fp, ow=ow, log_sf=float(lsf))  # the reference's own camera centre (mTcw.inv())
+        a = ctx.frustum_project(fp2)
+        iv = b["in_view"].astype(bool)
+        bad["frustum"] += not (np.array_equal(a["in_view"].astype(bool), iv) and all(
+            np.array_equal(a[k][iv], b[k][iv]) for k in ("proj_x", "proj_y", "proj_xr", "level", "view_cos")))
+        st = synth.make_stereo_pair(int(rng.integers(100, 2500)), 1000 + s)
+        a, b = ctx.stereo_matches(st), reflib.stereo_matches(st)
+        bad["stereo"] += not (a["n_matched"] == b["n_matched"] and np.array_equal(a["uright"], b["uright"]) and np.array_equal(a["depth"], b["depth"]))
+print(n, "rounds; mismatches:", bad)
