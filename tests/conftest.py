@@ -12,6 +12,16 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+@pytest.fixture(scope="session", autouse=True)
+def _library_present():
+    """A fresh checkout has no built artefacts (they are git-ignored): compile the C-ABI library
+    once (nvcc cross-compiles without a GPU) so that test order does not matter.  An existing
+    library is left alone -- staleness is test_capi_cpu's business."""
+    from lorb_slam_b200 import build
+    if not os.path.exists(build.LIB):
+        build.build_library()
+
+
 @pytest.fixture(scope="session")
 def ctx():
     """One lorb context on cuda:0 for the whole GPU session (fails loudly if the
