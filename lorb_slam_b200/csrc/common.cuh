@@ -66,7 +66,7 @@ struct lorb_ctx {
   // cached CUDA graphs of the ORB extractor's detection chain (orb.cu), one per job slot
   void* orb_graph[2] = {nullptr, nullptr};
   cudaStream_t orb_stream2 = nullptr;  // side branch of the extractor graph (capture only)
-  cudaEvent_t orb_ev[2] = {nullptr, nullptr};
+  cudaEvent_t orb_ev[3] = {nullptr, nullptr, nullptr};
   cudaStream_t orb_stream3 = nullptr;  // second frame of a stereo pair runs its graph here, concurrently
   cudaEvent_t orb_join = nullptr;
   // optional event timing of the library's own kernels (lorb_ctx_profile)

@@ -794,8 +794,8 @@ struct OrbPipeline {
   // One frame = ONE CUDA-graph launch.  The graph (captured once per frame size, parameters and
   // buffers) holds the whole extractor:
   //     H2D frame
-  //     FAST level 0 ------------------> quadtree level 0 (side branch)
-  //     resize x7 -> FAST levels 1..7 -> quadtree levels 1..7 -> blur
+  //     FAST level 0 -----------------> quadtree level 0 -> blur of all levels   (side branch;
+  //     resize x7 -> FAST levels 1..7 -> quadtree levels 1..7                     the blur waits for the pyramid)
   //     (join) orientation + descriptors of the selected keypoints, results written to pinned memory
   // Issued one by one these 13 operations cost the host more time than the GPU needs to run them,
   // and a quadtree on the host (orb_quadtree.h, 80 us for level 0) would sit in the middle of the
@@ -935,7 +935,6 @@ struct OrbPipeline {
       c->launches++;
       LORB_CUDA_TRY(cudaGetLastError());
     }
-    LORB_CUDA_TRY(cudaEventRecord(c->orb_ev[1], s2));
     for (int l = 1; l < nl; l++) {
       // scale = 1 / (dsize / ssize) in double, as cv::resize derives it from the two sizes
       const double sx = 1. / ((double)L.w[l] / L.w[l - 1]), sy = 1. / ((double)L.h[l] / L.h[l - 1]);
@@ -943,6 +942,14 @@ struct OrbPipeline {
       LORB_LAUNCH(c, orb_resize_kernel, grd, blk, 0, P.raw[l - 1], L.w[l - 1], L.h[l - 1], P.raw[l], L.w[l], L.h[l],
                   sx, sy);
     }
+    // the blur only needs the pyramid: it joins the side branch behind the level-0 quadtree and runs
+    // under the detection of levels 1..7
+    LORB_CUDA_TRY(cudaEventRecord(c->orb_ev[2], s));
+    LORB_CUDA_TRY(cudaStreamWaitEvent(s2, c->orb_ev[2], 0));
+    orb_blur_kernel<<<n_tiles, 256, 0, s2>>>(P);
+    c->launches++;
+    LORB_CUDA_TRY(cudaGetLastError());
+    LORB_CUDA_TRY(cudaEventRecord(c->orb_ev[1], s2));
     if (nl > 1) {
       LORB_LAUNCH(c, orb_fast_cells_kernel, P.cell_start[nl] - P.cell_start[1], 256, 0, P, P.cell_start[1], slots, cnt);
       QtArgs A;
@@ -950,8 +957,7 @@ struct OrbPipeline {
       for (int l = 1; l < nl; l++) A.lv[l - 1] = qt_level(J, d, hp, l);
       LORB_LAUNCH(c, orb_quadtree_kernel, nl - 1, QT_THREADS, 0, A);
     }
-    LORB_LAUNCH(c, orb_blur_kernel, n_tiles, 256, 0, P);
-    LORB_CUDA_TRY(cudaStreamWaitEvent(s, c->orb_ev[1], 0));  // join the level-0 branch
+    LORB_CUDA_TRY(cudaStreamWaitEvent(s, c->orb_ev[1], 0));  // join the side branch
     OrbSelDev Q;
     memset(&Q, 0, sizeof(Q));
     for (int l = 0; l < nl; l++) {
