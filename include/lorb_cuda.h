@@ -341,19 +341,15 @@ int lorb_stereo_frame(lorb_ctx* ctx, const uint8_t* left, const uint8_t* right, 
                       lorb_orb_keypoints* out_right, float* out_uright, float* out_depth, int* n_matched);
 
 /*
- * ORBextractor::DistributeOctTree (:554-797) on its own (host code, no device work): from the
- * candidate keypoints of one level (coordinates relative to min_x / min_y, in the order the
- * detection loop produced them) pick about n_features of them, spread over the image by a
- * quadtree.  out_index [n_keys] receives the indices of the chosen keypoints in the reference's
- * output order, *n_out their number.  Equal-size tie-break: see lorb_orb_extract.
+ * ORBextractor::DistributeOctTree (:554-797) on its own (one CTA on the device: what lorb_orb_extract
+ * runs per level between the FAST and the descriptor kernels): from the candidate keypoints of one
+ * level (coordinates relative to min_x / min_y, in the order the detection loop produced them) pick
+ * about n_features of them, spread over the image by a quadtree.  out_index [lorb_orb_max_keypoints or
+ * n_keys] receives the indices of the chosen keypoints in the reference's output order, *n_out their
+ * number.  Equal-size tie-break: see lorb_orb_extract.  Keys must be integer pixels below 4096 with
+ * integer responses below 256, which is what the FAST stage produces.
  */
-int lorb_orb_distribute(int n_keys, const float* x, const float* y, const float* response, int min_x,
-                        int max_x, int min_y, int max_y, int n_features, int* out_index, int* n_out);
-
-/* lorb_orb_distribute evaluated on the device (one CTA per level: what lorb_orb_extract runs between
- * the FAST and the descriptor kernels).  Keys must be integer pixels below 4096 with integer responses
- * below 256, which is what the FAST stage produces. */
-int lorb_orb_distribute_gpu(lorb_ctx* ctx, int n_keys, const float* x, const float* y,
+int lorb_orb_distribute(lorb_ctx* ctx, int n_keys, const float* x, const float* y,
                             const float* response, int min_x, int max_x, int min_y, int max_y,
                             int n_features, int* out_index, int* n_out);
 

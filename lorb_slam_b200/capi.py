@@ -26,26 +26,13 @@ EXPORTS = [
     "lorb_match_sweep_resident", "lorb_sweep_plan_upload", "lorb_sweep_plan_run",
     "lorb_sweep_plan_download", "lorb_sweep_plan_run_at", "lorb_search_proj_points", "lorb_search_proj_frame", "lorb_frustum_project", "lorb_compute_descriptors",
     "lorb_stereo_matches", "lorb_orb_describe", "lorb_orb_umax", "lorb_orb_selftest",
-    "lorb_orb_extract", "lorb_orb_level_sizes", "lorb_orb_stages", "lorb_stereo_frame", "lorb_orb_distribute", "lorb_orb_distribute_gpu", "lorb_orb_max_keypoints",
+    "lorb_orb_extract", "lorb_orb_level_sizes", "lorb_orb_stages", "lorb_stereo_frame", "lorb_orb_distribute", "lorb_orb_max_keypoints",
     "lorb_ba_default_options", "lorb_ba_pose_only", "lorb_ba_local", "lorb_ba_local_batched",
     "lorb_ba_problem_create", "lorb_ba_problem_create_batched", "lorb_ba_problem_reset", "lorb_ba_problem_solve",
     "lorb_ba_problem_download", "lorb_ba_problem_destroy", "lorb_dist_get_unique_id",
     "lorb_dist_init", "lorb_dist_finalize", "lorb_dist_allreduce_f64", "lorb_microbench_popc",
     "lorb_microbench_fp64", "lorb_ctx_profile", "lorb_ctx_profile_read",
 ]
-
-
-def orb_distribute(x, y, response, min_x, max_x, min_y, max_y, n_features):
-    """ORBextractor::DistributeOctTree (host code of the library; needs no GPU) -> chosen indices."""
-    x, y, r = (np.ascontiguousarray(a, np.float32) for a in (x, y, response))
-    out = np.zeros(max(1, len(x)), np.int32)
-    n = C.c_int(0)
-    rc = load_library().lorb_orb_distribute(len(x), x.ctypes.data_as(C.c_void_p), y.ctypes.data_as(C.c_void_p),
-                                            r.ctypes.data_as(C.c_void_p), min_x, max_x, min_y, max_y, n_features,
-                                            out.ctypes.data_as(C.c_void_p), C.byref(n))
-    if rc != OK:
-        raise LorbError("lorb error %d: %s" % (rc, load_library().lorb_last_error().decode()))
-    return out[:n.value]
 
 
 class LorbError(RuntimeError):
@@ -426,11 +413,12 @@ class Context:
         t = int(ls[-1])
         return dict(raw=raw, blur=blur, cand_x=cx[:t], cand_y=cy[:t], cand_response=cr[:t], level_start=ls)
 
-    def orb_distribute_gpu(self, x, y, response, min_x, max_x, min_y, max_y, n_features):
+    def orb_distribute(self, x, y, response, min_x, max_x, min_y, max_y, n_features):
+        """ORBextractor::DistributeOctTree alone (device quadtree) -> chosen indices."""
         x, y, r = (_arr(a, np.float32) for a in (x, y, response))
         out = np.zeros(max(n_features + 16, len(x) + 16), np.int32)
         n = C.c_int(0)
-        _check(self._lib.lorb_orb_distribute_gpu(self._h, len(x), _ptr(x), _ptr(y), _ptr(r), min_x, max_x, min_y,
+        _check(self._lib.lorb_orb_distribute(self._h, len(x), _ptr(x), _ptr(y), _ptr(r), min_x, max_x, min_y,
                                                  max_y, n_features, _ptr(out), C.byref(n)))
         return out[:n.value]
 

@@ -20,7 +20,6 @@
 
 #include "common.cuh"
 #include "libm_sincosf.cuh"
-#include "orb_quadtree.h"
 #include "orb_quadtree_gpu.cuh"
 #include "stereo_dev.cuh"
 
@@ -798,7 +797,7 @@ struct OrbPipeline {
   //     resize x7 -> FAST levels 1..7 -> quadtree levels 1..7                     the blur waits for the pyramid)
   //     (join) orientation + descriptors of the selected keypoints, results written to pinned memory
   // Issued one by one these 13 operations cost the host more time than the GPU needs to run them,
-  // and a quadtree on the host (orb_quadtree.h, 80 us for level 0) would sit in the middle of the
+  // and a quadtree on the host (80 us for level 0, sequential) would sit in the middle of the
   // chain; as a graph the host stages the frame, launches, and waits once.
   int launch(OrbJob* J, cudaStream_t run_on = nullptr) {
     if (!run_on) run_on = c->stream;
@@ -1087,24 +1086,10 @@ int orb_run(lorb_ctx* c, const uint8_t* image, int width, int height, int step, 
 
 }  // namespace
 
-// ORBextractor::DistributeOctTree (:554-797) alone: host code, no device work.
-int lorb_orb_distribute(int n_keys, const float* x, const float* y, const float* response, int min_x, int max_x,
-                        int min_y, int max_y, int n_features, int* out_index, int* n_out) {
-  LORB_REQUIRE(n_keys >= 0 && n_out && (n_keys == 0 || (x && y && response && out_index)), "arguments");
-  LORB_REQUIRE(max_x > min_x && max_y > min_y && n_features >= 0, "bounds");
-  std::vector<QKey> keys(n_keys);
-  for (int i = 0; i < n_keys; i++) keys[i] = QKey{x[i], y[i], response[i]};
-  std::vector<int> chosen;
-  distribute_quadtree(keys, min_x, max_x, min_y, max_y, n_features, &chosen);
-  for (size_t i = 0; i < chosen.size(); i++) out_index[i] = chosen[i];
-  *n_out = (int)chosen.size();
-  return LORB_OK;
-}
-
-// ORBextractor::DistributeOctTree on the device (orb_quadtree_gpu.cuh): one CTA, same result as
-// lorb_orb_distribute.  Coordinates must be integers in [0, 4096), responses integers in [0, 256)
-// (what the FAST kernel produces).
-int lorb_orb_distribute_gpu(lorb_ctx* c, int n_keys, const float* x, const float* y, const float* response, int min_x,
+// ORBextractor::DistributeOctTree (:554-797) alone, on the device (orb_quadtree_gpu.cuh): one CTA.
+// Coordinates must be integers in [0, 4096), responses integers in [0, 256) (what the FAST kernel
+// produces).
+int lorb_orb_distribute(lorb_ctx* c, int n_keys, const float* x, const float* y, const float* response, int min_x,
                             int max_x, int min_y, int max_y, int n_features, int* out_index, int* n_out) {
   LORB_REQUIRE(c && n_keys >= 0 && n_out && (n_keys == 0 || (x && y && response && out_index)), "arguments");
   LORB_REQUIRE(max_x > min_x && max_y > min_y && n_features >= 0, "bounds");

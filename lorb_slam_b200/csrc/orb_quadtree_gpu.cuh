@@ -1,7 +1,7 @@
 // orb_quadtree_gpu.cuh — ORBextractor::DistributeOctTree (reference src/ORBextractor.cpp:496-797) as ONE
 // CTA per pyramid level, so that a frame never leaves the device between the FAST kernel and the
-// descriptor kernel.  Same result as orb_quadtree.h (the host statement of the same function), bit for
-// bit, including the list order of the surviving nodes.
+// descriptor kernel.  Same result as the sequential CPU restatement (oracle/orb_quadtree_ref.h, itself
+// pinned to the compiled reference), bit for bit, including the list order of the surviving nodes.
 //
 // The reference walks a std::list and splits nodes one at a time, but what a whole pass does is a
 // function of its input that can be evaluated in parallel:
@@ -13,7 +13,8 @@
 //         L' = reverse(children of Sel, in (Sel order, n1..n4) order, empty ones dropped) ++ (L minus Sel)
 //     because the reference pushes children to the FRONT while it erases the parent;
 //   * creation ids grow in that same (Sel order, n1..n4) order, which is the tie-break among nodes of
-//     equal size (the reference compares node addresses; see orb_quadtree.h);
+//     equal size (the reference compares node addresses, :695; under an allocator that never reuses
+//     memory that is creation order, last created first -- how oracle/_ref runs the reference);
 //   * a leaf's keypoint is its first key of maximal response: a 64-bit atomicMax on (response, ~index).
 // Each of these is a histogram, a prefix sum or a rank-by-counting over at most a few thousand items:
 // block-wide primitives, all state in global scratch (L1-resident), shared memory only for the scans.

@@ -1,7 +1,8 @@
-// orb_quadtree.h — ORBextractor::DistributeOctTree (reference src/ORBextractor.cpp:496-797) as
-// plain host C++ (no CUDA): the sequential selection step between the FAST kernel and the
-// descriptor kernel of lorb_orb_extract.  Included by orb.cu; also callable on its own through
-// lorb_orb_distribute.
+// orb_quadtree_ref.h — CPU restatement of ORBextractor::DistributeOctTree (reference
+// src/ORBextractor.cpp:496-797), sequential like the reference.  TEST INFRASTRUCTURE ONLY (part of
+// oracle/orb_ref.cpp): the oracle of the device quadtree (lorb_slam_b200/csrc/orb_quadtree_gpu.cuh);
+// itself pinned to the compiled reference's DistributeOctTree (tests/golden/orb_golden.npz qt/*,
+// tests/test_orb_cpu.py).
 #pragma once
 #include <math.h>
 #include <stdint.h>
@@ -10,7 +11,7 @@
 #include <utility>
 #include <vector>
 
-namespace lorb {
+namespace orc {
 
 struct QKey {
   float x, y, response;
@@ -198,4 +199,4 @@ static void distribute_quadtree(const std::vector<QKey>& keys, int min_x, int ma
   }
 }
 
-}  // namespace lorb
+}  // namespace orc

@@ -11,6 +11,7 @@
 #include <string.h>
 
 #include "../lorb_slam_b200/csrc/libm_sincosf.cuh"
+#include "orb_quadtree_ref.h"
 
 extern "C" {
 
@@ -244,6 +245,18 @@ int orc_orb_level_candidates(const uint8_t* img, int cols, int rows, int step, i
 int orc_fast9_nms(const uint8_t* img, int w, int h, int step, int threshold, int* out_x, int* out_y,
                   int* out_score, int cap) {
   return orc::fast9_nms(img, w, h, step, threshold, out_x, out_y, out_score, cap);
+}
+
+// Part 3: ORBextractor::DistributeOctTree (:554-797), see orb_quadtree_ref.h.  out_index receives the
+// indices of the chosen keypoints in the reference's output order; returns their number.
+int orc_orb_distribute(int n_keys, const float* x, const float* y, const float* response, int min_x, int max_x,
+                       int min_y, int max_y, int n_features, int* out_index) {
+  std::vector<orc::QKey> keys(n_keys);
+  for (int i = 0; i < n_keys; i++) keys[i] = orc::QKey{x[i], y[i], response[i]};
+  std::vector<int> chosen;
+  orc::distribute_quadtree(keys, min_x, max_x, min_y, max_y, n_features, &chosen);
+  for (size_t i = 0; i < chosen.size(); i++) out_index[i] = chosen[i];
+  return (int)chosen.size();
 }
 
 }  // extern "C"

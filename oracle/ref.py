@@ -23,7 +23,8 @@ def build(force=False):
         os.path.exists(os.path.join(_LIBDIR, n)) for n in _LIBS)
     if not need:
         srcs = [os.path.join(_HERE, "match_ref.c"), os.path.join(_HERE, "ba_ref.cpp"),
-                os.path.join(_HERE, "orb_ref.cpp"), os.path.join(_HERE, "Makefile"),
+                os.path.join(_HERE, "orb_ref.cpp"), os.path.join(_HERE, "orb_quadtree_ref.h"),
+                os.path.join(_HERE, "Makefile"),
                 os.path.join(_HERE, "..", "lorb_slam_b200", "csrc", "libm_sincosf.cuh"),
                 os.path.join(_HERE, "..", "include", "lorb_cuda.h")]
         newest = max(os.path.getmtime(s) for s in srcs)
@@ -323,6 +324,16 @@ def orb_pyramid(img, sizes):
     for (w, h) in sizes[1:]:
         pyr.append(resize_linear(pyr[-1], int(w), int(h)))
     return pyr
+
+
+def orb_distribute(x, y, response, min_x, max_x, min_y, max_y, n_features):
+    """ORBextractor::DistributeOctTree restated (oracle/orb_quadtree_ref.h) -> chosen indices, in the
+    reference's output order."""
+    x, y, r = _f32(x), _f32(y), _f32(response)
+    out = np.zeros(max(1, len(x)), np.int32)
+    n = _orb().orc_orb_distribute(len(x), _p(x, C.c_float), _p(y, C.c_float), _p(r, C.c_float), min_x, max_x, min_y,
+                                  max_y, n_features, _p(out, C.c_int))
+    return out[:n]
 
 
 def fast_atan2(y, x):

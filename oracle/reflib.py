@@ -31,7 +31,8 @@ def build(force=False):
         return False
     srcs = [os.path.join(_HERE, "ref_harness.cpp"), os.path.join(_HERE, "refshim", "lorb_cvshim.hpp"),
             os.path.join(_HERE, "refshim", "lorb_ceresshim.hpp"), os.path.join(_HERE, "Makefile"),
-            os.path.join(_HERE, "ref_orb_harness.cpp"), os.path.join(_HERE, "orb_ref.cpp")]
+            os.path.join(_HERE, "ref_orb_harness.cpp"), os.path.join(_HERE, "orb_ref.cpp"),
+            os.path.join(_HERE, "orb_quadtree_ref.h")]
     if force or not os.path.exists(_LIB) or max(map(os.path.getmtime, srcs)) > os.path.getmtime(_LIB):
         subprocess.run(["make", "-C", _HERE, "ref", "REFERENCE=" + REFERENCE_ROOT], check=True,
                        capture_output=True)

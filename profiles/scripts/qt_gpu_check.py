@@ -9,8 +9,8 @@ bad = 0
 with capi.Context(0) as ctx:
     for c in RC.QUADTREE:
         args = RC.quadtree_case(c)
-        a = capi.orb_distribute(*args)
-        b = ctx.orb_distribute_gpu(*args)
+        a = ref.orb_distribute(*args)
+        b = ctx.orb_distribute(*args)
         ok = np.array_equal(a, b)
         print(c[0], len(a), len(b), ok)
         bad += not ok
@@ -23,9 +23,9 @@ with capi.Context(0) as ctx:
         span = w - 6 if t % 5 else 30
         x = rng.integers(0, span, n).astype(np.float32); y = rng.integers(0, min(span, h - 6), n).astype(np.float32)
         r = rng.integers(7, 60, n).astype(np.float32); nf = int(rng.integers(1, 1500))
-        a = capi.orb_distribute(x, y, r, 16, 16 + w, 16, 16 + h, nf)
+        a = ref.orb_distribute(x, y, r, 16, 16 + w, 16, 16 + h, nf)
         try:
-            b = ctx.orb_distribute_gpu(x, y, r, 16, 16 + w, 16, 16 + h, nf)
+            b = ctx.orb_distribute(x, y, r, 16, 16 + w, 16, 16 + h, nf)
         except Exception as e:
             print("ERROR trial", t, n, w, h, nf, span, str(e)[-60:])
             n_bad += 1
@@ -38,7 +38,7 @@ with capi.Context(0) as ctx:
     print("random mismatches:", n_bad)
     img = synth.make_orb_image(0)
     x, y, r = ref.orb_level_candidates(img)
-    for _ in range(5): ctx.orb_distribute_gpu(x, y, r, 16, 624, 16, 464, 217)
+    for _ in range(5): ctx.orb_distribute(x, y, r, 16, 624, 16, 464, 217)
     t0 = time.perf_counter()
-    for _ in range(200): ctx.orb_distribute_gpu(x, y, r, 16, 624, 16, 464, 217)
+    for _ in range(200): ctx.orb_distribute(x, y, r, 16, 624, 16, 464, 217)
     print("gpu quadtree e2e (incl. pack/H2D/D2H) %.1f us" % ((time.perf_counter() - t0) / 200 * 1e6))

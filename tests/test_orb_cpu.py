@@ -86,13 +86,14 @@ def test_level_plan():
 
 @pytest.mark.parametrize("c", RC.QUADTREE, ids=[c[0] for c in RC.QUADTREE])
 def test_quadtree_matches_reference(c):
-    """The product's host quadtree (lorb_orb_distribute, no GPU needed) picks exactly the keypoints
-    the compiled reference's DistributeOctTree picks, in the same order."""
+    """The CPU restatement of the quadtree (oracle/orb_quadtree_ref.h, the oracle of the device
+    quadtree) picks exactly the keypoints the compiled reference's DistributeOctTree picks, in the
+    same order."""
     args = RC.quadtree_case(c)
     g = OC.golden()
     k = "qt/" + c[0]
     assert str(g[k + "/digest"]) == RC.digest(*args)
-    idx = capi.orb_distribute(*args)
+    idx = ref.orb_distribute(*args)
     x, y, r = args[:3]
     assert np.array_equal(x[idx], g[k + "/x"]) and np.array_equal(y[idx], g[k + "/y"])
     assert np.array_equal(r[idx], g[k + "/response"])
@@ -112,7 +113,7 @@ def test_quadtree_fresh_vs_compiled_reference():
         y = rng.integers(0, h - 6, n).astype(np.float32)
         r = rng.integers(7, 60, n).astype(np.float32)
         nf = int(rng.integers(1, 1500))
-        idx = capi.orb_distribute(x, y, r, 16, 16 + w, 16, 16 + h, nf)
+        idx = ref.orb_distribute(x, y, r, 16, 16 + w, 16, 16 + h, nf)
         ox, oy, orr = reflib.distribute_octree(x, y, r, 16, 16 + w, 16, 16 + h, nf)
         assert len(idx) == len(ox) and np.array_equal(x[idx], ox) and np.array_equal(y[idx], oy)
         assert np.array_equal(r[idx], orr)

@@ -234,17 +234,17 @@ def test_cuda_orb_extract_repeatable_and_reentrant(ctx):
 
 
 def test_device_quadtree_matches_host_quadtree(ctx):
-    """orb_quadtree_gpu.cuh (one CTA, parallel rounds) == orb_quadtree.h (the sequential statement,
-    itself pinned to the compiled reference): golden cases + random ones incl. pixel clusters, wide
+    """orb_quadtree_gpu.cuh (one CTA, parallel rounds) == oracle/orb_quadtree_ref.h (the sequential CPU
+    restatement, itself pinned to the compiled reference): golden cases + random ones incl. pixel clusters, wide
     levels whose first pass overshoots the budget, and budgets of 1."""
     g = OC.golden()
     for c in RC.QUADTREE:
         args = RC.quadtree_case(c)
-        idx = ctx.orb_distribute_gpu(*args)
+        idx = ctx.orb_distribute(*args)
         x, y, r = args[:3]
         k = "qt/" + c[0]
         assert np.array_equal(x[idx], g[k + "/x"]) and np.array_equal(y[idx], g[k + "/y"])
-        assert np.array_equal(idx, capi.orb_distribute(*args))
+        assert np.array_equal(idx, ref.orb_distribute(*args))
     rng = np.random.default_rng(11)
     for t in range(150):
         n, w, h = int(rng.integers(1, 3000)), int(rng.integers(100, 1300)), int(rng.integers(60, 700))
@@ -255,8 +255,8 @@ def test_device_quadtree_matches_host_quadtree(ctx):
         y = rng.integers(0, min(span, h - 6), n).astype(np.float32)
         r = rng.integers(7, 60, n).astype(np.float32)
         nf = int(rng.integers(1, 1500)) if t % 7 else 1
-        a = capi.orb_distribute(x, y, r, 16, 16 + w, 16, 16 + h, nf)
-        b = ctx.orb_distribute_gpu(x, y, r, 16, 16 + w, 16, 16 + h, nf)
+        a = ref.orb_distribute(x, y, r, 16, 16 + w, 16, 16 + h, nf)
+        b = ctx.orb_distribute(x, y, r, 16, 16 + w, 16, 16 + h, nf)
         assert np.array_equal(a, b), (t, n, w, h, nf)
 
 
