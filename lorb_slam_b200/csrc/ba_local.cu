@@ -2520,6 +2520,7 @@ static int problem_build(lorb_ba_problem* pb, lorb_ctx* c, const std::vector<Win
       const WindowSpec& W = ws[w];
       const size_t OT = (size_t)W.O + W.F;
       LORB_REQUIRE(L.n_pairs < (1ll << 31), "more than 2^31 pair records in one window");
+      LORB_REQUIRE(W.C <= 8192, "more than 8192 cameras in one window (camera-block keys are C*C)");
       L.obs_pt = n_obs_pt;
       L.cam_obs = n_cam_obs;
       L.cam_items = n_cam_items;
