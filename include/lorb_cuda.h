@@ -122,6 +122,14 @@ int lorb_match_knn2(lorb_ctx* ctx, const uint8_t* q, int nq, const uint8_t* t, i
 int lorb_match_sweep(lorb_ctx* ctx, const uint8_t* bank, int n_kf, int n_desc, const int* pair_a,
                      const int* pair_b, int n_pairs, int* out_kept, int* out_matches, int* out_min);
 
+/* Two kernels compute the sweep, with identical results: LORB_SWEEP_POPC (XOR / POPC on the
+ * integer pipes, operands in registers / shared memory) and LORB_SWEEP_TENSOR (tcgen05.mma
+ * kind::i8 on +-32 expansions of the bit strings, distance and both tie-breaks read off the
+ * int32 accumulator).  Default: tensor (environment LORB_SWEEP_IMPL=popc|tensor overrides);
+ * impl = -1 restores the default.  Takes effect at the next bank / plan upload. */
+enum { LORB_SWEEP_POPC = 0, LORB_SWEEP_TENSOR = 1 };
+int lorb_sweep_set_impl(lorb_ctx* ctx, int impl);
+
 /* Resident form: upload the bank once, then sweep pair lists against it. */
 int lorb_bank_upload(lorb_ctx* ctx, const uint8_t* bank, int n_kf, int n_desc);
 /* Pair lists / outputs are host pointers; only the bank stays in HBM. */

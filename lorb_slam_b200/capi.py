@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "liblorb_cuda.so")
 
 OK = 0
 CROSSCHECK_MUTUAL, CROSSCHECK_LEGACY = 0, 1
+SWEEP_POPC, SWEEP_TENSOR, SWEEP_DEFAULT = 0, 1, -1
 TERMINATION = {0: "NO_CONVERGENCE", 1: "CONV_FUNCTION", 2: "CONV_GRADIENT", 3: "CONV_PARAMETER",
                4: "CONV_RADIUS", 5: "FAILURE"}
 
@@ -24,7 +25,7 @@ EXPORTS = [
     "lorb_ctx_launch_count", "lorb_last_error", "lorb_version",
     "lorb_match_bf_crosscheck", "lorb_match_knn2", "lorb_match_sweep", "lorb_bank_upload",
     "lorb_match_sweep_resident", "lorb_sweep_plan_upload", "lorb_sweep_plan_run",
-    "lorb_sweep_plan_download", "lorb_sweep_plan_run_at", "lorb_search_proj_points", "lorb_search_proj_frame", "lorb_frustum_project", "lorb_compute_descriptors",
+    "lorb_sweep_plan_download", "lorb_sweep_plan_run_at", "lorb_sweep_set_impl", "lorb_search_proj_points", "lorb_search_proj_frame", "lorb_frustum_project", "lorb_compute_descriptors",
     "lorb_stereo_matches", "lorb_orb_describe", "lorb_orb_umax", "lorb_orb_selftest",
     "lorb_orb_extract", "lorb_orb_level_sizes", "lorb_orb_stages", "lorb_stereo_frame", "lorb_orb_distribute", "lorb_orb_max_keypoints",
     "lorb_ba_default_options", "lorb_ba_pose_only", "lorb_ba_local", "lorb_ba_local_batched",
@@ -219,6 +220,11 @@ class Context:
                                          C.c_float(ratio), int(max_dist), _ptr(idx), _ptr(dist),
                                          _ptr(ok)))
         return idx[:len(q)], dist[:len(q)], ok[:len(q)]
+
+    def sweep_set_impl(self, impl):
+        """SWEEP_POPC / SWEEP_TENSOR / SWEEP_DEFAULT (or "popc" / "tensor" / "default")."""
+        impl = {"popc": SWEEP_POPC, "tensor": SWEEP_TENSOR, "default": SWEEP_DEFAULT}.get(impl, impl)
+        _check(self._lib.lorb_sweep_set_impl(self._h, int(impl)))
 
     def bank_upload(self, bank):
         bank = _arr(bank, np.uint8)

@@ -61,6 +61,12 @@ struct lorb_ctx {
   int bank_n_kf = 0, bank_n_desc = 0;
   lorb::Buf plan_pairs, plan_out;
   int plan_n_pairs = 0, plan_max_kf = 0;
+  // tensor-core form of the sweep (match_tc.cu): int8 operand images of the bank, unit list,
+  // row / column key scratch
+  int sweep_impl = -1;  // LORB_SWEEP_POPC / LORB_SWEEP_TENSOR; -1 = default (env LORB_SWEEP_IMPL)
+  lorb::Buf tc_img, tc_units, tc_keys;
+  int tc_img_n_kf = 0, tc_img_n_desc = 0, tc_n_units = 0;
+  size_t tc_keys_rows = 0;
   lorb::Dist* dist = nullptr;
   void* ba_cache = nullptr;  // reusable lorb_ba_problem of the host-buffer BA calls (ba_local.cu)
   // cached CUDA graphs of the ORB extractor's detection chain (orb.cu), one per job slot
@@ -91,6 +97,12 @@ void prof_end(lorb_ctx* c, int slot);
     int _rc = (expr);           \
     if (_rc != LORB_OK) return _rc; \
   } while (0)
+
+namespace tc {  // match_tc.cu
+int bank_expand(lorb_ctx* c);
+int plan_build(lorb_ctx* c, const int* pa, const int* pb, int n_pairs);
+int launch_sweep(lorb_ctx* c, int kf_base, int n_pairs, int* out);
+}  // namespace tc
 
 // Kernel launch bookkeeping: every launch goes through this so that
 // lorb_ctx_launch_count is the bench's "gpu_launches".

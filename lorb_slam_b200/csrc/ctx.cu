@@ -253,6 +253,9 @@ int lorb_ctx_destroy(lorb_ctx* c) {
   c->bank.release();
   c->plan_pairs.release();
   c->plan_out.release();
+  c->tc_img.release();
+  c->tc_units.release();
+  c->tc_keys.release();
   if (c->prof) {
     Prof* P = static_cast<Prof*>(c->prof);
     for (auto& e : P->ev) {

@@ -704,6 +704,26 @@ int lorb_compute_descriptors(lorb_ctx* c, int n_points, const int* offsets, cons
   return LORB_OK;
 }
 
+// Which kernel runs the sweep: the popc kernel above or the tensor-core kernel of match_tc.cu.
+// Both return identical results; LORB_SWEEP_IMPL=popc|tensor overrides the default.
+static int sweep_impl(lorb_ctx* c) {
+  if (c->sweep_impl >= 0) return c->sweep_impl;
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("LORB_SWEEP_IMPL");
+    v = (e && !strcmp(e, "popc")) ? LORB_SWEEP_POPC : LORB_SWEEP_TENSOR;
+  }
+  return v;
+}
+
+int lorb_sweep_set_impl(lorb_ctx* c, int impl) {
+  LORB_REQUIRE(c, "ctx");
+  LORB_REQUIRE(impl == LORB_SWEEP_POPC || impl == LORB_SWEEP_TENSOR || impl == -1, "impl");
+  c->sweep_impl = impl;
+  c->tc_img_n_kf = 0;  // operand images are rebuilt on the next plan upload if needed
+  return LORB_OK;
+}
+
 int lorb_bank_upload(lorb_ctx* c, const uint8_t* bank, int n_kf, int n_desc) {
   LORB_REQUIRE(c && bank, "ctx/bank");
   LORB_REQUIRE(n_kf > 0 && n_desc > 0 && n_desc <= 2048, "bank shape (n_desc <= 2048)");
@@ -711,9 +731,11 @@ int lorb_bank_upload(lorb_ctx* c, const uint8_t* bank, int n_kf, int n_desc) {
   const size_t bytes = (size_t)n_kf * n_desc * 32;
   LORB_TRY(c->bank.reserve(bytes));
   LORB_CUDA_TRY(cudaMemcpyAsync(c->bank.p, bank, bytes, cudaMemcpyHostToDevice, c->stream));
-  LORB_CUDA_TRY(cudaStreamSynchronize(c->stream));
   c->bank_n_kf = n_kf;
   c->bank_n_desc = n_desc;
+  c->tc_img_n_kf = 0;
+  if (sweep_impl(c) == LORB_SWEEP_TENSOR) LORB_TRY(tc::bank_expand(c));
+  LORB_CUDA_TRY(cudaStreamSynchronize(c->stream));
   return LORB_OK;
 }
 
@@ -744,6 +766,12 @@ int lorb_sweep_plan_upload(lorb_ctx* c, const int* pa, const int* pb, int n_pair
   LORB_CUDA_TRY(cudaMemcpyAsync(c->plan_pairs.p, hp, (size_t)n_pairs * 8, cudaMemcpyHostToDevice,
                                 c->stream));
   LORB_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  if (sweep_impl(c) == LORB_SWEEP_TENSOR) {
+    if (c->tc_img_n_kf != c->bank_n_kf || c->tc_img_n_desc != c->bank_n_desc) LORB_TRY(tc::bank_expand(c));
+    LORB_TRY(tc::plan_build(c, pa, pb, n_pairs));
+  } else {
+    c->tc_n_units = 0;
+  }
   return LORB_OK;
 }
 
@@ -752,6 +780,10 @@ int lorb_sweep_plan_run_at(lorb_ctx* c, int kf_base) {
   LORB_REQUIRE(c->bank_n_kf > 0, "no bank uploaded");
   LORB_REQUIRE(kf_base >= 0 && kf_base + c->plan_max_kf < c->bank_n_kf, "kf_base out of range");
   LORB_CUDA_TRY(cudaSetDevice(c->device));
+  if (sweep_impl(c) == LORB_SWEEP_TENSOR) {
+    LORB_REQUIRE(c->plan_n_pairs == 0 || c->tc_n_units > 0, "plan was uploaded for the popc kernel");
+    return tc::launch_sweep(c, kf_base, c->plan_n_pairs, c->plan_out.as<int>());
+  }
   return launch_sweep(c, c->bank.as<uint4>() + (size_t)kf_base * c->bank_n_desc * 2,
                       c->bank_n_desc, c->plan_pairs.as<int2>(), c->plan_n_pairs,
                       c->plan_out.as<int>());

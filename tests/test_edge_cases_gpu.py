@@ -9,7 +9,14 @@ from oracle import ref
 pytestmark = pytest.mark.gpu
 
 
-def test_sweep_maximum_descriptor_count_and_self_pairs(ctx):
+@pytest.fixture(params=["popc", "tensor"])
+def sweep_impl(ctx, request):
+    ctx.sweep_set_impl(request.param)
+    yield request.param
+    ctx.sweep_set_impl("default")
+
+
+def test_sweep_maximum_descriptor_count_and_self_pairs(ctx, sweep_impl):
     bank = synth.kf_bank(3, 2048, seed=5)          # the shared-memory resident limit
     pa = np.array([0, 1, 2, 0], np.int32)
     pb = np.array([0, 2, 1, 2], np.int32)          # a self pair, both orders of a pair
@@ -23,7 +30,7 @@ def test_sweep_maximum_descriptor_count_and_self_pairs(ctx):
         ctx.match_sweep(bank, [0], [7])            # pair index out of range
 
 
-def test_sweep_no_pairs(ctx):
+def test_sweep_no_pairs(ctx, sweep_impl):
     bank = synth.kf_bank(2, 64, seed=1)
     kept, mt, md = ctx.match_sweep(bank, np.zeros(0, np.int32), np.zeros(0, np.int32))
     assert len(kept) == 0

@@ -98,8 +98,16 @@ def test_properties_full_size(ctx):
     assert s1 == s2 and r1["min_dist"] == r2["min_dist"]
 
 
-@pytest.mark.parametrize("n_desc", [100, 512, 513, 1000, 2000, 2048])
-def test_sweep_vs_oracle(ctx, n_desc):
+@pytest.fixture(params=["popc", "tensor"])
+def sweep_impl(ctx, request):
+    """Both sweep kernels (XOR/POPC and tcgen05 int8) must give the oracle's numbers."""
+    ctx.sweep_set_impl(request.param)
+    yield request.param
+    ctx.sweep_set_impl("default")
+
+
+@pytest.mark.parametrize("n_desc", [1, 7, 100, 256, 257, 512, 513, 1000, 2000, 2048])
+def test_sweep_vs_oracle(ctx, sweep_impl, n_desc):
     n_kf = 6
     bank = synth.kf_bank(n_kf, n_desc, seed=n_desc)
     pa, pb = synth.all_pairs(n_kf)
@@ -114,7 +122,29 @@ def test_sweep_vs_oracle(ctx, n_desc):
     assert r["n_kept"] == kept[1] and len(r["q"]) == mt[1] and r["min_dist"] == md[1]
 
 
-def test_sweep_many_pairs_resident(ctx):
+@pytest.mark.parametrize("n_desc,nbytes,nvals", [(300, 1, 2), (777, 2, 4), (2000, 3, 4), (2048, 1, 3)])
+def test_sweep_tie_stress(ctx, sweep_impl, n_desc, nbytes, nvals):
+    """Low-entropy banks: almost every distance is tied many times over, so the three numbers
+    per pair depend on the lowest-index rule of both argmins inside the sweep kernels' own
+    mutual-test epilogues (only the tile kernel had seen such a bank)."""
+    rng = np.random.default_rng(n_desc + nbytes)
+    n_kf = 5
+    bank = np.stack([synth.descriptors_tie_stress(n_desc, rng, nbytes, nvals) for _ in range(n_kf)])
+    bank[3] = bank[1]  # identical keyframes: every row ties with its own copy and many others
+    pa, pb = synth.all_pairs(n_kf)
+    pa = np.concatenate([pa, [4, 2]]).astype(np.int32)
+    pb = np.concatenate([pb, [0, 2]]).astype(np.int32)
+    kept, mt, md = ctx.match_sweep(bank, pa, pb)
+    ok, om, od = ref.sweep(bank, pa, pb)
+    assert np.array_equal(kept, ok) and np.array_equal(mt, om) and np.array_equal(md, od)
+    for k in (0, 5):  # and the single-pair entry point agrees match by match
+        r = ctx.match_bf_crosscheck(bank[pa[k]], bank[pb[k]])
+        o = ref.bf_crosscheck(bank[pa[k]], bank[pb[k]])
+        assert np.array_equal(r["q"], o["q"]) and np.array_equal(r["t"], o["t"])
+        assert r["n_kept"] == kept[k] and len(r["q"]) == mt[k]
+
+
+def test_sweep_many_pairs_resident(ctx, sweep_impl):
     """More pairs than SMs, exercising the persistent loop, A reuse and B double buffering."""
     n_kf, n_desc = 24, 700
     bank = synth.kf_bank(n_kf, n_desc, seed=1)
@@ -128,6 +158,12 @@ def test_sweep_many_pairs_resident(ctx):
     ctx.sweep_plan_run()
     k2, m2, d2 = ctx.sweep_plan_download()
     assert np.array_equal(k2, ok[:50]) and np.array_equal(m2, om[:50]) and np.array_equal(d2, od[:50])
+    # the same plan shifted along the bank (what bench.py does block after block)
+    ctx.sweep_plan_upload(pa[:40] % 8, pb[:40] % 8)
+    ctx.sweep_plan_run(kf_base=9)
+    k3, m3, d3 = ctx.sweep_plan_download()
+    o3 = ref.sweep(bank, pa[:40] % 8 + 9, pb[:40] % 8 + 9)
+    assert np.array_equal(k3, o3[0]) and np.array_equal(m3, o3[1]) and np.array_equal(d3, o3[2])
 
 
 def test_compute_descriptors(ctx):
