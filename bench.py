@@ -3,6 +3,13 @@
 
     python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload NAME]
 
+The default line carries all three BASELINE metrics: the keyframe-pair sweep is the top-level
+record (descriptor-pairs/s); `ba_batched` (config 4: 512 windows split over the ranks) and
+`ba_large` (config 5: 200 keyframes / 200k points / 1.5M observations, points sharded over the
+ranks, NCCL all-reduce of the reduced camera system) are sub-objects with their own value, e2e,
+roofline, cpu_baseline and an in-run parity check.  `--impl reference` prints the same structure
+measured on the CPU path.
+
 Headline workload (default, `sweep`): BASELINE.json config 5's keyframe-pair
 matching sweep — a bank of 4096 keyframes x 2000 ORB descriptors (262 MB, larger
 than the 126 MB L2) resident in HBM.  One step = every pair among one block of
@@ -44,6 +51,28 @@ def _peaks():
         d = json.load(open(p))
         return d.get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def _tensor_peaks():
+    """(bf16 dense TFLOP/s burst, sustained, source) from the driver-written MEASURED_PEAKS.json."""
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        if "bf16_tflops" in d:
+            return (float(d["bf16_tflops"]), float(d.get("bf16_tflops_sustained", d["bf16_tflops"])),
+                    "measured (MEASURED_PEAKS.json: cuBLAS bf16 8192^3)")
+    return 1640.0, 1390.0, "fallback (B200_PROFILING.md)"
+
+
+def _profile_traffic(key):
+    """dram bytes per launch of a kernel from the committed ncu summary of this round, with its
+    provenance; (None, None) when no capture has been committed for it."""
+    p = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    if os.path.exists(p):
+        d = json.load(open(p)).get(key)
+        if d:
+            return d.get("dram_bytes_per_launch"), d.get("source")
+    return None, None
 
 
 class ClockSampler:
@@ -215,10 +244,13 @@ def cpu_baseline_sweep(bank, target_s=12.0):
     return out
 
 
+
 def run_sweep(args, rank, world, local):
     import torch
     from lorb_slam_b200 import capi
     ctx = capi.Context(local)
+    ctx.sweep_set_impl(args.sweep_impl)
+    tensor = args.sweep_impl == "tensor"
     bank = _make_bank(0)
     n_blocks = N_KF // BLOCK_KF
     pa, pb = _block_pairs()
@@ -245,9 +277,18 @@ def run_sweep(args, rank, world, local):
     ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if rank == 0 else None
     ms_max = _max_over_ranks(ms, world, local)
-    kernel_ms = ms / args.steps  # one kernel launch per step on this rank
-    # sanity: the last block's result equals the host-buffer path's
+    step_ms = ms / args.steps
     kept_dev = ctx.sweep_plan_download()[0]
+    # the dominant kernel alone (the tensor form adds a small finalize kernel per step)
+    kernel_ms = step_ms
+    if tensor and rank == 0:
+        ctx.profile(True)
+        for i in range(min(3, args.steps)):
+            ctx.sweep_plan_run(my_blocks[args.warmup + i] * BLOCK_KF)
+        tot, cnt = ctx.profile_read(3)
+        ctx.profile(False)
+        if cnt:
+            kernel_ms = tot / cnt
 
     # ---- e2e through the host-buffer entry point, pinned host inputs
     pinned = torch.empty((BLOCK_KF, N_DESC, 32), dtype=torch.uint8).pin_memory()
@@ -267,7 +308,6 @@ def run_sweep(args, rank, world, local):
         t_e2e += time.perf_counter() - t0
     assert np.array_equal(kept_e2e, kept_dev), "device-resident and host-buffer paths disagree"
     e2e_max = _max_over_ranks(t_e2e, world, local)
-    # restore the full bank for anything that follows
     total_pairs = float(world) * args.steps * n_pairs * PAIRS_PER_KF_PAIR
     value = total_pairs / (ms_max * 1e-3)
     e2e_value = total_pairs / e2e_max
@@ -275,21 +315,53 @@ def run_sweep(args, rank, world, local):
     res = None
     if rank == 0:
         hbm_peak, peak_src = _peaks()
+        pairs_per_launch = n_pairs * PAIRS_PER_KF_PAIR
+        sm_max = (clocks or {}).get("sm_max_mhz") or 1965.0
+        sm_count = torch.cuda.get_device_properties(local).multi_processor_count
         ctx.bank_upload(bank[:BLOCK_KF])  # small bank is enough for the micro-benchmarks
-        peak_words = ctx.microbench_popc(1, 4096)
-        peak_words_popc8 = ctx.microbench_popc(0, 4096)
-        words = n_pairs * PAIRS_PER_KF_PAIR * 8.0
-        achieved = words / (kernel_ms * 1e-3)
+        if tensor:
+            burst, sustained, tsrc = _tensor_peaks()
+            mb = ctx.microbench_tensor_i8(4096)
+            ops = pairs_per_launch * 512.0  # 256 multiply-adds per descriptor pair (the distance)
+            traffic, traffic_src = _profile_traffic("tc_sweep_kernel")
+            roof = {"bound": "tensor", "kernel": "tc_sweep_kernel (tcgen05.mma kind::i8, 128x256x32)",
+                    "avg_launch_ms": kernel_ms,
+                    "achieved": ops / (kernel_ms * 1e-3) / 1e12, "peak": mb / 1e12, "unit": "TOP/s (int8)",
+                    "frac": ops / (kernel_ms * 1e-3) / mb,
+                    "peak_source": "measured in this run: lorb_microbench_tensor_i8 = the kernel's own MMA stream "
+                                   "(tcgen05.mma kind::i8 128x256x32) on zeroed operands, no TMA, no epilogue, whole GPU; "
+                                   "MEASURED_PEAKS.json holds no int8 figure -- twice its bf16 numbers would be "
+                                   "%.0f (sustained) / %.0f (burst), %s" % (2.0 * sustained, 2.0 * burst, tsrc),
+                    "algorithmic_ops": "256 int8 multiply-adds (512 ops) per descriptor pair; executed: 288 per pair, "
+                                       "the ninth k-step carries both tie-break index terms",
+                    "frac_executed": ops * 288 / 256 / (kernel_ms * 1e-3) / mb,
+                    "traffic": traffic, "traffic_source": traffic_src}
+        else:
+            alu_peak_pairs = 64.0 * sm_count * sm_max * 1e6 / 17.75
+            peak_words = ctx.microbench_popc(1, 4096)
+            traffic, traffic_src = _profile_traffic("sweep_kernel")
+            roof = {"bound": "alu", "kernel": "sweep_kernel<4,true>", "avg_launch_ms": kernel_ms,
+                    "achieved": pairs_per_launch * 8.0 / (kernel_ms * 1e-3) / 1e9, "peak": alu_peak_pairs * 8.0 / 1e9,
+                    "unit": "G 32-bit words/s (1 descriptor pair = 8 words)",
+                    "frac": pairs_per_launch / (kernel_ms * 1e-3) / alu_peak_pairs,
+                    "peak_source": "hardware ALU issue ceiling: 64 lanes x %d SMs x %.0f MHz / 17.75 ALU "
+                                   "thread-instructions per pair (SASS count, profiles/README.md)" % (sm_count, sm_max),
+                    "loop_vs_register_body": pairs_per_launch * 8.0 / (kernel_ms * 1e-3) / peak_words,
+                    "traffic": traffic, "traffic_source": traffic_src}
+        popc_hw = 16.0 * sm_count * sm_max * 1e6  # 16 POPC / clk / SM
         alg_bytes = n_pairs * 2 * N_DESC * 32.0  # both descriptor blocks of every keyframe pair
         res = {
             "metric": "descriptor-pairs/s Hamming match", "value": value,
             "unit": "descriptor-pairs/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u32 (xor/popc on 256-bit strings)",
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": "s8 (tcgen05.mma kind::i8 on +-32 expansions of the bit strings, s32 accumulate)" if tensor
+                     else "u32 (xor/popc on 256-bit strings)",
             "data": "synthetic (uniform random 256-bit descriptors, seed 0)",
             "config": {"workload": "kf_pair_sweep: 4096 keyframes x 2000 descriptors resident "
                                    "(262 MB > 126 MB L2); step = all 8128 pairs of one 128-keyframe "
                                    "block, cross-check + max(2*minDist,30) filter",
+                       "kernel": args.sweep_impl,
                        "keyframe_pairs_per_step_per_gpu": n_pairs,
                        "descriptor_pairs_per_step_per_gpu": n_pairs * PAIRS_PER_KF_PAIR,
                        "l2": "bank larger than L2; a different 8 MB block every step",
@@ -299,19 +371,12 @@ def run_sweep(args, rank, world, local):
                     "d2h_bytes_per_step": int(3 * 4 * n_pairs)},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "alu",
-                         "bound_detail": "integer pipes (LOP3 on ALU 86%, POPC on XU 74% per ncu); "
-                                         "operands live in shared memory / registers",
-                         "achieved": achieved / 1e9, "peak": peak_words / 1e9,
-                         "unit": "G 32-bit words/s (1 descriptor pair = 8 words)",
-                         "frac": achieved / peak_words,
-                         "peak_source": "measured in this run: lorb_microbench_popc(kind=1), the "
-                                        "carry-save distance body on register operands, whole GPU",
-                         "peak_plain_popc8": peak_words_popc8 / 1e9,
-                         "frac_of_plain_popc8": achieved / peak_words_popc8,
-                         "traffic": 8295424,
-                         "traffic_source": "dram__bytes_read+write per launch, ncu --set full, "
-                                           "profiles/r01_sweep_kernel_ncu_full.csv"},
+            "roofline": roof,
+            "roofline_popc_survey_8d": {
+                "achieved": pairs_per_launch * 8.0 / (kernel_ms * 1e-3) / 1e9, "peak": popc_hw / 1e9,
+                "unit": "G 32-bit words/s", "frac": pairs_per_launch * 8.0 / (kernel_ms * 1e-3) / popc_hw,
+                "note": "SURVEY 8(d)'s definition (8 POPC per pair against 16 POPC/clk/SM at the max clock); "
+                        "above 1 because neither kernel issues 8 POPC per pair (tensor: none; popc: 4, carry-save)"},
             "roofline_hbm": {"bound": "hbm", "achieved": alg_bytes / (kernel_ms * 1e-3) / 1e9,
                              "peak": hbm_peak, "unit": "GB/s",
                              "frac": alg_bytes / (kernel_ms * 1e-3) / 1e9 / hbm_peak,
@@ -426,7 +491,8 @@ def extras(ctx, local):
     return out
 
 
-def _ba_rooflines(ctx, obs_per_launch, k_obs_per_point, n_reduced, build, backsub, solve, traffic, traffic_src):
+
+def _ba_rooflines(ctx, obs_per_launch, k_obs_per_point, n_reduced, prof, traffic_key):
     """roofline objects of one BA LM attempt from the library's own CUDA-event brackets
     (lorb_ctx_profile: slot 0 build pass, 1 back-substitution, 2 reduced-system solve).
     FLOP model of SURVEY 8(d): per observation 150 (linearise) + 216 (accumulate) + 216*k (Schur
@@ -436,6 +502,7 @@ def _ba_rooflines(ctx, obs_per_launch, k_obs_per_point, n_reduced, build, backsu
     dfma = ctx.microbench_fp64(0, 4096)
     dmma = ctx.microbench_fp64(1, 4096)
     fp64_peak = max(dfma, dmma)
+    build, backsub, solve = prof
     parts = {
         "build": (build, obs_per_launch * (150.0 + 216.0 + 216.0 * k_obs_per_point), obs_per_launch * 16.0),
         "backsub": (backsub, obs_per_launch * 60.0, obs_per_launch * 32.0),
@@ -446,6 +513,7 @@ def _ba_rooflines(ctx, obs_per_launch, k_obs_per_point, n_reduced, build, backsu
     ms = ms_tot / max(1, n)
     shares = {k: v[0][0] for k, v in parts.items()}
     tot = sum(shares.values()) or 1.0
+    traffic, traffic_src = _profile_traffic(traffic_key)
     roof = {"bound": "tensor", "bound_detail": "fp64: DMMA tensor-core contractions + DFMA Jacobians; latency-bound per ncu "
                                                "(profiles/README.md), HBM fraction below 1 %",
             "kernel": name, "avg_launch_ms": ms, "launches": int(n),
@@ -455,6 +523,7 @@ def _ba_rooflines(ctx, obs_per_launch, k_obs_per_point, n_reduced, build, backsu
                            % (dfma / 1e12, dmma / 1e12),
             "flop_model": "SURVEY 8(d): algorithmic flops of the kernel per launch",
             "share_of_attempt": {k: v / tot for k, v in shares.items()},
+            "ms_per_attempt_by_part": {k: parts[k][0][0] / max(1, parts[k][0][1]) for k in parts},
             "traffic": traffic, "traffic_source": traffic_src}
     hbm = {"bound": "hbm", "kernel": name, "achieved": byt / (ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
            "frac": byt / (ms * 1e-3) / 1e9 / hbm_peak, "peak_source": peak_src,
@@ -462,61 +531,117 @@ def _ba_rooflines(ctx, obs_per_launch, k_obs_per_point, n_reduced, build, backsu
     return roof, hbm
 
 
-def run_ba_batched(args, rank, world, local):
-    """BASELINE config 4: 512 independent 10-keyframe windows sharded over ranks
-    (weak scaling variant: `--windows` per GPU, default 512/8 = 64)."""
-    from lorb_slam_b200 import capi, synth
+def _rel_err(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.max(np.abs(a - b) / (1e-8 + 1e-6 * np.abs(b)))) if a.size else 0.0
+
+
+def cpu_baseline_ba_batched(pbs, iters=3):
+    """The oracle port of BA::LocalPoseOptimization (oracle/ba_ref.cpp: Ceres' LM + DENSE_SCHUR restated,
+    one thread per window as Ceres' num_threads=1) on a bounded sample: one window per host thread,
+    `iters` LM iterations each, OpenMP over windows."""
+    from lorb_slam_b200 import synth
+    from oracle import ref
+    cores = ref.set_num_threads(os.cpu_count() or 1)
+    n = min(len(pbs), cores)
+    bt = synth.batch_windows(pbs[:n])
+    opt = _ba_opts_fixed_iters(ref, iters)
+    t0 = time.perf_counter()
+    _, _, sums = ref.ba_local_batched(bt["cam_off"], bt["cams"], bt["pt_off"], bt["pts"], bt["obs_off"],
+                                      bt["obs_cam"], bt["obs_pt"], bt["obs_uv"], bt["K"], opt)
+    dt = time.perf_counter() - t0
+    it = sum(s["iterations"] for s in sums)
+    return {"value": float(sum(p["O"] for p in pbs[:n])) * it / n / dt, "unit": "observations*iterations/s",
+            "cores": cores, "kind": "port",
+            "sample": "%d windows (10 keyframes / 5000 points / 30000 observations each), %d LM iterations each, "
+                      "oracle/ba_ref.cpp -O2, OpenMP over windows (one thread per window)" % (n, iters)}
+
+
+def cpu_baseline_ba_large(pb, iters=2):
+    """The oracle port on the whole config-5 problem for `iters` LM iterations, one thread (Ceres'
+    default num_threads=1; the reference sets no other)."""
+    from oracle import ref
+    opt = _ba_opts_fixed_iters(ref, iters)
+    t0 = time.perf_counter()
+    _, _, s = ref.ba_local(pb, opt)
+    dt = time.perf_counter() - t0
+    return {"value": pb["O"] * (s["iterations"] + 1) / dt, "unit": "observations*iterations/s", "cores": 1,
+            "kind": "port",
+            "sample": "%d LM iterations (+ the initial evaluation, counted as one) of the full problem "
+                      "(%d keyframes / %d points / %d observations), oracle/ba_ref.cpp -O2, 1 thread"
+                      % (s["iterations"], pb["C"], pb["P"], pb["O"])}
+
+
+def run_ba_batched(args, rank, world, local, steps=None, want_cpu=True):
+    """BASELINE config 4: `--windows-total` (512) independent 10-keyframe windows split in contiguous
+    slices over the ranks (strong scaling: the batch is fixed), every window its own LM loop."""
+    import torch
+    from lorb_slam_b200 import capi, sharding, synth
+    steps = steps or args.steps
+    warmup = max(3, min(args.warmup, 3))
     ctx = capi.Context(local)
-    nw = args.windows
-    pbs = [synth.make_ba_problem(rank * nw + i, C=10, P=5000) for i in range(nw)]
+    total = args.windows_total
+    lo, hi = sharding.window_slice(rank, world, total)
+    nw = hi - lo
+    pbs = [synth.make_ba_problem(i, C=10, P=5000) for i in range(lo, hi)]
     bt = synth.batch_windows(pbs)
     opt = _ba_opts_fixed_iters(capi)
     obs = int(bt["obs_off"][-1])
     # ---- value: windows resident in HBM, only the solve is timed (reset + LM loop)
     prob = ctx.ba_problem_batched(bt)
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         prob.reset()
         prob.solve(opt)
+    st, ev0, ev1 = _events(ctx, local)
     _barrier(world)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     l0 = ctx.launch_count
     ctx.profile(True)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
+    ev0.record(st)
+    for _ in range(steps):
         prob.reset()
         sums = prob.solve(opt)
+    ev1.record(st)
     ctx.sync()
-    dt = time.perf_counter() - t0
+    dt = ev0.elapsed_time(ev1) * 1e-3
     launches = ctx.launch_count - l0
     prof = [ctx.profile_read(k) for k in range(3)]
     ctx.profile(False)
     clocks = sampler.stop() if rank == 0 else None
     dt_max = _max_over_ranks(dt, world, local)
+    cams_res, pts_res = prob.download()
     prob.close()
     iters = sum(s["iterations"] for s in sums) / len(sums)
-    value = world * args.steps * obs * iters / dt_max
+    total_obs = _sum_over_ranks(float(obs), world, local)
+    value = steps * total_obs * iters / dt_max
     # ---- e2e: the host-buffer call (upload of every window, solve, download) per step
     ctx.ba_local_batched(bt, opt)
     _barrier(world)
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        ctx.ba_local_batched(bt, opt)
+    for _ in range(steps):
+        e_cams, e_pts, _ = ctx.ba_local_batched(bt, opt)
     e2e_dt = _max_over_ranks(time.perf_counter() - t0, world, local)
-    e2e_value = world * args.steps * obs * iters / e2e_dt
+    e2e_value = steps * total_obs * iters / e2e_dt
+    same = bool(np.array_equal(e_cams, cams_res) and np.array_equal(e_pts, pts_res))
     res = None
     if rank == 0:
+        from oracle import ref
+        # parity inside the run: the first window of this rank against the oracle, full length
+        oc, op, so = ref.ba_local(pbs[0], _ba_opts_fixed_iters(ref))
+        pc, pp = cams_res[:10], pts_res[:pbs[0]["P"]]
+        err = max(_rel_err(pc, oc), _rel_err(pp, op))
         res = {"metric": "BA observations/s per LM iter", "value": value,
-               "unit": "observations*iterations/s", "n_gpus": world, "steps": args.steps,
-               "warmup": args.warmup, "ms_per_step": dt_max / args.steps * 1e3,
-               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-               "data": "synthetic (SURVEY 8(d) cfg 3 generator, seeds rank*W+i)",
-               "config": {"workload": "batched local BA: %d independent windows per GPU, each 10 "
-                                      "keyframes / 5000 points / 30000 observations, 10 LM "
-                                      "iterations (value: windows resident; e2e: "
-                                      "lorb_ba_local_batched with host buffers)" % nw,
-                          "l2": "%.0f MB of observations and parameters per GPU; parameters are "
+               "unit": "observations*iterations/s", "n_gpus": world, "steps": steps,
+               "warmup": warmup, "ms_per_step": dt_max / steps * 1e3,
+               "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+               "data": "synthetic (SURVEY 8(d) cfg 3 generator, window w = seed w)",
+               "config": {"workload": "batched local BA (BASELINE config 4): %d independent windows split over "
+                                      "%d rank(s) (%d on rank 0), each 10 keyframes / 5000 points / 30000 "
+                                      "observations, 10 LM iterations (value: windows resident; e2e: "
+                                      "lorb_ba_local_batched with host buffers)" % (total, world, nw),
+                          "l2": "%.0f MB of observations and parameters on rank 0; parameters are "
                                 "reset to the initial values before every step"
                                 % ((bt["obs_uv"].nbytes + 2 * bt["obs_cam"].nbytes + bt["pts"].nbytes
                                     + bt["cams"].nbytes) / 1e6)},
@@ -525,59 +650,104 @@ def run_ba_batched(args, rank, world, local):
                                                  bt["obs_uv"].nbytes + 2 * bt["obs_cam"].nbytes),
                        "d2h_bytes_per_step": int(bt["cams"].nbytes + bt["pts"].nbytes)},
                "gpu_launches": int(launches), "clocks": clocks,
-               "ms_per_local_ba": dt_max / args.steps / nw * 1e3, "lm_iterations": iters}
-        res["roofline"], res["roofline_hbm"] = _ba_rooflines(
-            ctx, obs, 6.0, 60, prof[0], prof[1], prof[2], 43960832 if nw == 64 else None,
-            "dram__bytes_read+write of ba_build_dense_kernel<1> per launch (64 windows), ncu --set full, "
-            "profiles/r01_ba_batched64_ncu_full.txt")
+               "ms_per_local_ba": dt_max / steps / nw * 1e3, "lm_iterations": iters,
+               "parity": {"ok": bool(err <= 1.0 and same), "max_err_over_tolerance": err,
+                          "tolerance": "rtol 1e-6 + atol 1e-8 on final cameras and points",
+                          "checked": "window %d (rank 0) against the oracle after 10 LM iterations; "
+                                     "host-buffer call == resident solve bit for bit: %s" % (lo, same),
+                          "lm_steps_ok_rejected": {"gpu": [sums[0]["num_successful_steps"], sums[0]["num_unsuccessful_steps"]],
+                                                   "oracle": [so["num_successful_steps"], so["num_unsuccessful_steps"]],
+                                                   "note": "tolerances are off (10 attempts forced): attempts past "
+                                                           "convergence accept or reject on rounding noise"}}}
+        res["roofline"], res["roofline_hbm"] = _ba_rooflines(ctx, obs, 6.0, 60, prof, "ba_build_dense_kernel")
+        if world == 1 and want_cpu:
+            res["cpu_baseline"] = cpu_baseline_ba_batched(pbs)
     ctx.close()
-    return res, None
+    return res
 
 
-def run_ba_large(args, rank, world, local):
-    """BASELINE config 5 BA: 200 keyframes / 200k points / 1.5M observations,
-    points sharded over the ranks, reduced camera system all-reduced over NCCL
-    every LM attempt.  Strong scaling (the problem is fixed)."""
+def run_ba_large(args, rank, world, local, steps=None, want_cpu=True):
+    """BASELINE config 5 BA: 200 keyframes / 200k points / 1.5M observations, points sharded over the
+    ranks, reduced camera system all-reduced over NCCL every LM attempt.  Strong scaling."""
     import torch
     import torch.distributed as dist
     from lorb_slam_b200 import capi, sharding, synth
+    steps = steps or args.steps
+    warmup = max(3, min(args.warmup, 3))
     ctx = capi.Context(local)
+    # the communicator exists at world 1 as well: the sharded code path (separate control kernel,
+    # collectives) is then exercised and checked on a one-GPU box too
+    uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        uid = torch.tensor(list(capi.Context.dist_unique_id()), dtype=torch.uint8, device="cuda")
     if world > 1:
-        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            uid = torch.tensor(list(capi.Context.dist_unique_id()), dtype=torch.uint8, device="cuda")
         dist.broadcast(uid, 0)
-        ctx.dist_init(bytes(uid.cpu().tolist()), rank, world)
+    ctx.dist_init(bytes(uid.cpu().tolist()), rank, world)
     pb = synth.make_ba_problem(0, C=args.large_cams, P=args.large_points, obs_per_point=(7, 8),
                                traj_len=100.0 * args.large_cams / 200.0)
     sh = sharding.shard_ba_by_point(pb, rank, world)
     opt = _ba_opts_fixed_iters(capi)
     prob = ctx.ba_problem(sh)
-    for _ in range(args.warmup):
+    sharded = world > 1
+    for _ in range(warmup):
         prob.reset()
-        prob.solve(opt, sharded=world > 1)
+        prob.solve(opt, sharded=sharded)
+    st, ev0, ev1 = _events(ctx, local)
     _barrier(world)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     l0 = ctx.launch_count
     ctx.profile(True)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
+    ev0.record(st)
+    for _ in range(steps):
         prob.reset()
-        s = prob.solve(opt, sharded=world > 1)
+        s = prob.solve(opt, sharded=sharded)
+    ev1.record(st)
     ctx.sync()
-    dt = time.perf_counter() - t0
+    dt = ev0.elapsed_time(ev1) * 1e-3
     launches = ctx.launch_count - l0
     prof = [ctx.profile_read(k) for k in range(3)]
     ctx.profile(False)
     clocks = sampler.stop() if rank == 0 else None
     dt_max = _max_over_ranks(dt, world, local)
+    cams_res, pts_res = prob.download()
+    # ---- parity inside the run: the un-sharded solve of the whole problem on rank 0 (at world 1: the
+    # sharded code path over a one-rank communicator) must give the same cameras / points
+    parity = None
+    if world == 1:
+        prob.reset()
+        s2 = prob.solve(opt, sharded=True)
+        c2, p2 = prob.download()
+        err = max(_rel_err(c2, cams_res), _rel_err(p2, pts_res))
+        parity = {"ok": bool(err <= 1.0 and s2["iterations"] == s["iterations"]), "max_err_over_tolerance": err,
+                  "tolerance": "rtol 1e-6 + atol 1e-8 on final cameras and points",
+                  "checked": "sharded code path (one-rank NCCL communicator) against the plain solve, "
+                             "%d LM iterations, final cost %.9g vs %.9g" % (s["iterations"], s2["final_cost"], s["final_cost"])}
     prob.close()
-    # e2e: the host-buffer call every step (work lists built on the host, upload, solve, download).
-    # One GPU: lorb_ba_local (the ctx keeps its grow-only buffers); sharded: create + solve + download.
+    if world > 1:
+        camt = torch.from_numpy(cams_res).cuda()
+        cam0 = camt.clone()
+        dist.broadcast(cam0, 0)
+        same_cams = torch.tensor([1.0 if torch.equal(camt, cam0) else 0.0], device="cuda")
+        dist.all_reduce(same_cams, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            full = ctx.ba_problem(pb)
+            s1 = full.solve(opt)
+            c1, p1 = full.download()
+            full.close()
+            lo, hi = sh["point_range"]
+            err = max(_rel_err(cams_res, c1), _rel_err(pts_res, p1[lo:hi]))
+            parity = {"ok": bool(err <= 1.0 and same_cams.item() == 1.0 and s1["iterations"] == s["iterations"]),
+                      "max_err_over_tolerance": err,
+                      "tolerance": "rtol 1e-6 + atol 1e-8 on final cameras and rank 0's points",
+                      "cameras_bit_identical_across_ranks": bool(same_cams.item() == 1.0),
+                      "checked": "%d-rank sharded solve against the one-GPU solve of the whole problem on rank 0, "
+                                 "final cost %.9g vs %.9g" % (world, s["final_cost"], s1["final_cost"])}
+    # ---- e2e: the host-buffer call every step.  One GPU: lorb_ba_local (the ctx keeps its grow-only
+    # buffers); sharded: create (upload + device work lists) + solve + download of this rank's shard.
     _barrier(world)
-    n_e2e = max(1, args.steps // 2)
+    n_e2e = max(1, steps // 2)
     if world == 1:
         ctx.ba_local(sh, opt)  # first call sizes the buffers
     t0 = time.perf_counter()
@@ -591,18 +761,18 @@ def run_ba_large(args, rank, world, local):
             p2.close()
     e2e = _max_over_ranks((time.perf_counter() - t0) / n_e2e, world, local)
     O = pb["O"]
-    value = args.steps * O * s["iterations"] / dt_max
+    value = steps * O * s["iterations"] / dt_max
     res = None
     if rank == 0:
         res = {"metric": "BA observations/s per LM iter", "value": value,
-               "unit": "observations*iterations/s", "n_gpus": world, "steps": args.steps,
-               "warmup": args.warmup, "ms_per_step": dt_max / args.steps * 1e3,
+               "unit": "observations*iterations/s", "n_gpus": world, "steps": steps,
+               "warmup": warmup, "ms_per_step": dt_max / steps * 1e3,
                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
                "data": "synthetic (SURVEY 8(d) cfg 5 generator, seed 0)",
-               "config": {"workload": "large BA: %d keyframes / %d points / %d observations, 10 LM "
-                                      "attempts, points sharded over ranks, NCCL all-reduce of the "
+               "config": {"workload": "large BA (BASELINE config 5): %d keyframes / %d points / %d observations, 10 LM "
+                                      "attempts, points sharded over %d rank(s), NCCL all-reduce of the "
                                       "%dx%d reduced camera system per attempt"
-                                      % (args.large_cams, args.large_points, O, 6 * args.large_cams,
+                                      % (args.large_cams, args.large_points, O, world, 6 * args.large_cams,
                                          6 * args.large_cams),
                           "l2": "observations + points (%.0f MB) streamed per pass" % (O * 12 / 1e6)},
                "e2e": {"value": O * s["iterations"] / e2e, "unit": "observations*iterations/s",
@@ -610,15 +780,15 @@ def run_ba_large(args, rank, world, local):
                                                  sh["pts"].nbytes + sh["cams"].nbytes),
                        "d2h_bytes_per_step": int(sh["pts"].nbytes + sh["cams"].nbytes)},
                "gpu_launches": int(launches), "clocks": clocks,
-               "ms_per_lm_iteration": dt_max / args.steps / s["iterations"] * 1e3,
-               "lm_iterations": s["iterations"], "final_cost": s["final_cost"]}
+               "ms_per_lm_iteration": dt_max / steps / s["iterations"] * 1e3,
+               "lm_iterations": s["iterations"], "final_cost": s["final_cost"], "parity": parity}
         res["roofline"], res["roofline_hbm"] = _ba_rooflines(
-            ctx, sh["O"] if "O" in sh else len(sh["obs_cam"]), 7.5, 6 * args.large_cams, prof[0], prof[1], prof[2],
-            None, None)
-    if world > 1:
-        ctx.dist_finalize()
+            ctx, len(sh["obs_cam"]), 7.5, 6 * args.large_cams, prof, "ba_schur_pairs_kernel")
+        if world == 1 and want_cpu:
+            res["cpu_baseline"] = cpu_baseline_ba_large(pb)
+    ctx.dist_finalize()
     ctx.close()
-    return res, None
+    return res
 
 
 def main():
@@ -627,8 +797,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="lorb", choices=["lorb", "reference"])
-    ap.add_argument("--workload", default="sweep", choices=["sweep", "ba_batched", "ba_large"])
-    ap.add_argument("--windows", type=int, default=64)
+    ap.add_argument("--workload", default="all", choices=["all", "sweep", "ba_batched", "ba_large"])
+    ap.add_argument("--sweep-impl", default=os.environ.get("LORB_SWEEP_IMPL", "tensor"), choices=["tensor", "popc"])
+    ap.add_argument("--windows-total", type=int, default=512)
     ap.add_argument("--large-cams", type=int, default=200)
     ap.add_argument("--large-points", type=int, default=200000)
     ap.add_argument("--no-extras", action="store_true")
@@ -640,14 +811,14 @@ def main():
         return reference_arm(args)
 
     rank, world, local = _dist_setup(args.gpus)
+    want_cpu = not args.no_cpu_baseline
     if args.workload == "ba_batched":
-        res, bank = run_ba_batched(args, rank, world, local)
+        res = run_ba_batched(args, rank, world, local, want_cpu=want_cpu)
     elif args.workload == "ba_large":
-        res, bank = run_ba_large(args, rank, world, local)
+        res = run_ba_large(args, rank, world, local, want_cpu=want_cpu)
     else:
         res, bank = run_sweep(args, rank, world, local)
-    if rank == 0:
-        if args.workload == "sweep":
+        if rank == 0:
             if not args.no_extras:
                 from lorb_slam_b200 import capi
                 ctx = capi.Context(local)
@@ -655,8 +826,18 @@ def main():
                     res["extra"] = extras(ctx, local)
                 finally:
                     ctx.close()
-            if world == 1 and not args.no_cpu_baseline:
+            if world == 1 and want_cpu:
                 res["cpu_baseline"] = cpu_baseline_sweep(bank)
+        del bank
+        if args.workload == "all":
+            # the other two BASELINE metrics, same contract, shorter runs
+            sub_steps = max(2, min(args.steps, 5))
+            b = run_ba_batched(args, rank, world, local, steps=sub_steps, want_cpu=want_cpu)
+            l = run_ba_large(args, rank, world, local, steps=sub_steps, want_cpu=want_cpu)
+            if rank == 0:
+                res["ba_batched"] = b
+                res["ba_large"] = l
+    if rank == 0:
         print(json.dumps(res), flush=True)
     if world > 1:
         import torch.distributed as dist
@@ -664,18 +845,8 @@ def main():
         dist.destroy_process_group()
 
 
-def reference_arm(args):
-    """The reference's own CPU path for the same metric/config, on the host cores of this box:
-    oracle/_ref (the reference's src/matcher.cpp compiled unmodified over the OpenCV stand-in; see
-    oracle/ref_harness.cpp) when its library is present, else the oracle port -- the one other
-    place bench.py may execute oracle/ -- with all host threads; each step is a bounded sample of
-    the workload.  Rank 0 only."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
+def _reference_sweep(args, cores):
     from oracle import ref
-    cores = os.cpu_count() or 1
-    cores = ref.set_num_threads(cores)  # torchrun exports OMP_NUM_THREADS=1: use every host thread
     bank = _make_bank(0)[:BLOCK_KF]
     pa, pb = _block_pairs()
     kind, desc, run = _cpu_sweepers(bank)[0]
@@ -690,16 +861,63 @@ def reference_arm(args):
     value = args.steps * n * PAIRS_PER_KF_PAIR / dt
     sample = ("%d keyframe pairs (2000x2000 descriptors each) per step out of the 8128 of a block; %s"
               % (n, desc))
-    print(json.dumps({
-        "impl": "reference", "metric": "descriptor-pairs/s Hamming match", "value": value,
-        "unit": "descriptor-pairs/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u64 popcnt", "data": "synthetic",
-        "config": {"workload": "kf_pair_sweep (bounded sample): " + sample},
-        "cpu_baseline": {"value": value, "unit": "descriptor-pairs/s", "cores": cores,
-                         "kind": kind, "sample": sample},
-        "e2e": {"value": value, "unit": "descriptor-pairs/s", "h2d_bytes_per_step": 0,
-                "d2h_bytes_per_step": 0}}), flush=True)
+    return {"impl": "reference", "metric": "descriptor-pairs/s Hamming match", "value": value,
+            "unit": "descriptor-pairs/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u64 popcnt", "data": "synthetic",
+            "config": {"workload": "kf_pair_sweep (bounded sample): " + sample},
+            "cpu_baseline": {"value": value, "unit": "descriptor-pairs/s", "cores": cores,
+                             "kind": kind, "sample": sample},
+            "e2e": {"value": value, "unit": "descriptor-pairs/s", "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 0}}
+
+
+def _reference_ba(args, which):
+    """CPU arm of a BA workload: the oracle port (oracle/_ref's Ceres stand-in is a dense
+    normal-equations LM, 15 060 unknowns squared for one config-3 window: not runnable at these sizes)."""
+    from lorb_slam_b200 import synth
+    from oracle import ref
+    cores = ref.set_num_threads(os.cpu_count() or 1)
+    if which == "ba_batched":
+        pbs = [synth.make_ba_problem(i, C=10, P=5000) for i in range(min(cores, args.windows_total))]
+        t0 = time.perf_counter()
+        cb = cpu_baseline_ba_batched(pbs, iters=3)
+        metric_cfg = "batched local BA (bounded sample): " + cb["sample"]
+    else:
+        pb = synth.make_ba_problem(0, C=args.large_cams, P=args.large_points, obs_per_point=(7, 8),
+                                   traj_len=100.0 * args.large_cams / 200.0)
+        t0 = time.perf_counter()
+        cb = cpu_baseline_ba_large(pb, iters=2)
+        metric_cfg = "large BA (bounded sample): " + cb["sample"]
+    dt = time.perf_counter() - t0
+    return {"impl": "reference", "metric": "BA observations/s per LM iter", "value": cb["value"],
+            "unit": "observations*iterations/s", "n_gpus": args.gpus, "steps": 1, "warmup": 0,
+            "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": {"workload": metric_cfg}, "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": "observations*iterations/s", "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 0}}
+
+
+def reference_arm(args):
+    """The reference's own CPU path for the same metrics/configs, on the host cores of this box:
+    the sweep through oracle/_ref (the reference's src/matcher.cpp compiled unmodified over the OpenCV
+    stand-in; see oracle/ref_harness.cpp) when its library is present, else the oracle port; the two BA
+    workloads through the oracle port -- the one other place bench.py may execute oracle/ -- each step
+    a bounded sample of the workload.  Rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import ref
+    cores = os.cpu_count() or 1
+    cores = ref.set_num_threads(cores)  # torchrun exports OMP_NUM_THREADS=1: use every host thread
+    if args.workload in ("ba_batched", "ba_large"):
+        out = _reference_ba(args, args.workload)
+    else:
+        out = _reference_sweep(args, cores)
+        if args.workload == "all":
+            out["ba_batched"] = _reference_ba(args, "ba_batched")
+            out["ba_large"] = _reference_ba(args, "ba_large")
+    print(json.dumps(out), flush=True)
 
 
 if __name__ == "__main__":

@@ -143,7 +143,34 @@ int lorb_sweep_plan_run(lorb_ctx* ctx);
 /* Same plan, keyframe indices shifted by kf_base (sweeps block after block of a
  * resident bank with one uploaded pair pattern). */
 int lorb_sweep_plan_run_at(lorb_ctx* ctx, int kf_base);
+/* Same plan with separate bases for the two sides: pair (a, b) of the plan is keyframe pair
+ * (kf_base_a + a, kf_base_b + b) of the bank (off-diagonal tiles of the keyframe grid). */
+int lorb_sweep_plan_run_at2(lorb_ctx* ctx, int kf_base_a, int kf_base_b);
 int lorb_sweep_plan_download(lorb_ctx* ctx, int* out_kept, int* out_matches, int* out_min);
+
+/*
+ * The whole sweep of BASELINE config 5 -- every unordered keyframe pair of the resident bank -- as
+ * the reference would do it one BFMatcher call at a time (src/matcher.cpp:36-56 per pair), split
+ * over the GPUs of a box the way SURVEY 8(e) row 1 says: the keyframes are cut into blocks of
+ * block_kf, the upper-triangular grid of (block, block) tiles is enumerated row-major and tile t
+ * belongs to rank t % world; no collective during compute.
+ *   lorb_sweep_tile_count   tiles of the grid
+ *   lorb_sweep_rank_tiles   the (block row, block column) of the tiles of `rank` (cap = capacity of
+ *                           the two arrays, which may be NULL to query *n_out)
+ *   lorb_sweep_pair_index   position of pair (a, b), a != b, in the result array: row-major upper
+ *                           triangle, a * n_kf - a (a + 1) / 2 + (b - a - 1) for a < b
+ *   lorb_match_sweep_all    runs the tiles of `rank` and writes out_kept[pair index] = number of kept
+ *                           matches of that pair (host array of n_kf (n_kf - 1) / 2 ints); entries of
+ *                           other ranks' tiles are left untouched, so a sum / gather over ranks of
+ *                           zero-initialised arrays is the complete result (33.5 MB for 4096 keyframes).
+ *                           *n_pairs_done = keyframe pairs this rank processed (may be NULL).
+ */
+long long lorb_sweep_tile_count(int n_kf, int block_kf);
+int lorb_sweep_rank_tiles(int n_kf, int block_kf, int rank, int world, int cap, int* tile_bi,
+                          int* tile_bj, int* n_out);
+long long lorb_sweep_pair_index(int n_kf, int a, int b);
+int lorb_match_sweep_all(lorb_ctx* ctx, int block_kf, int rank, int world, int* out_kept,
+                         long long* n_pairs_done);
 
 /* ------------------------------------------- projection-guided search (a5/a6) */
 
@@ -546,6 +573,11 @@ int lorb_dist_allreduce_f64(lorb_ctx* ctx, double* data, int n);
  * distance kernel body on register operands. */
 int lorb_microbench_popc(lorb_ctx* ctx, int kind, int iters, double* words_per_s);
 
+/* Tensor-pipe micro-benchmark for the tensor-core sweep's roofline denominator: the sweep's own
+ * MMA stream (tcgen05.mma kind::i8, 128 x 256 x 32, `tiles` x 9 per SM) on zeroed operands with
+ * no TMA traffic and no epilogue.  Returns int8 operations (2 per multiply-add) per second. */
+int lorb_microbench_tensor_i8(lorb_ctx* ctx, int tiles, double* ops_per_s);
+
 /* fp64 micro-benchmark for the BA roofline denominator ("a measured fp64 FMA
  * peak"): independent DFMA chains on register operands over the whole GPU.  kind 0 = scalar
  * DFMA (2 flop each), kind 1 = DMMA m8n8k4 on the tensor cores (512 flop per warp instruction).
@@ -554,7 +586,8 @@ int lorb_microbench_fp64(lorb_ctx* ctx, int kind, int iters, double* flop_per_s)
 
 /* Device-side timing of the library's own kernels, for bench.py's roofline: while enabled,
  * the BA solver brackets its dominant kernels with CUDA events on the ctx stream
- * (slot 0 = build pass of an LM attempt, 1 = back-substitution, 2 = reduced-system solve).
+ * (slot 0 = build pass of an LM attempt, 1 = back-substitution, 2 = reduced-system solve),
+ * the tensor-core sweep its main kernel (slot 3).
  * lorb_ctx_profile_read synchronises the stream and returns the accumulated milliseconds and
  * the number of bracketed launches of a slot since the last lorb_ctx_profile(ctx, 1). */
 #define LORB_PROF_SLOTS 4

@@ -25,14 +25,15 @@ EXPORTS = [
     "lorb_ctx_launch_count", "lorb_last_error", "lorb_version",
     "lorb_match_bf_crosscheck", "lorb_match_knn2", "lorb_match_sweep", "lorb_bank_upload",
     "lorb_match_sweep_resident", "lorb_sweep_plan_upload", "lorb_sweep_plan_run",
-    "lorb_sweep_plan_download", "lorb_sweep_plan_run_at", "lorb_sweep_set_impl", "lorb_search_proj_points", "lorb_search_proj_frame", "lorb_frustum_project", "lorb_compute_descriptors",
+    "lorb_sweep_plan_download", "lorb_sweep_plan_run_at", "lorb_sweep_set_impl", "lorb_sweep_plan_run_at2", "lorb_sweep_tile_count", "lorb_sweep_rank_tiles",
+    "lorb_sweep_pair_index", "lorb_match_sweep_all", "lorb_search_proj_points", "lorb_search_proj_frame", "lorb_frustum_project", "lorb_compute_descriptors",
     "lorb_stereo_matches", "lorb_orb_describe", "lorb_orb_umax", "lorb_orb_selftest",
     "lorb_orb_extract", "lorb_orb_level_sizes", "lorb_orb_stages", "lorb_stereo_frame", "lorb_orb_distribute", "lorb_orb_max_keypoints",
     "lorb_ba_default_options", "lorb_ba_pose_only", "lorb_ba_local", "lorb_ba_local_batched",
     "lorb_ba_problem_create", "lorb_ba_problem_create_batched", "lorb_ba_problem_reset", "lorb_ba_problem_solve",
     "lorb_ba_problem_download", "lorb_ba_problem_destroy", "lorb_dist_get_unique_id",
     "lorb_dist_init", "lorb_dist_finalize", "lorb_dist_allreduce_f64", "lorb_microbench_popc",
-    "lorb_microbench_fp64", "lorb_ctx_profile", "lorb_ctx_profile_read",
+    "lorb_microbench_fp64", "lorb_microbench_tensor_i8", "lorb_ctx_profile", "lorb_ctx_profile_read",
 ]
 
 
@@ -156,6 +157,24 @@ def _frame_view(fr):
     return v, keep
 
 
+def sweep_rank_tiles(n_kf, block_kf, rank, world):
+    """[(block row, block column)] of the tiles of `rank` (host logic only; no device needed)."""
+    lib = load_library()
+    n = C.c_int()
+    _check(lib.lorb_sweep_rank_tiles(int(n_kf), int(block_kf), int(rank), int(world), 0, C.c_void_p(0),
+                                     C.c_void_p(0), C.byref(n)))
+    bi, bj = np.zeros(max(1, n.value), np.int32), np.zeros(max(1, n.value), np.int32)
+    _check(lib.lorb_sweep_rank_tiles(int(n_kf), int(block_kf), int(rank), int(world), n.value, _ptr(bi),
+                                     _ptr(bj), C.byref(n)))
+    return list(zip(bi[:n.value].tolist(), bj[:n.value].tolist()))
+
+
+def sweep_pair_index(n_kf, a, b):
+    lib = load_library()
+    lib.lorb_sweep_pair_index.restype = C.c_longlong
+    return int(lib.lorb_sweep_pair_index(int(n_kf), int(a), int(b)))
+
+
 class Context:
     """One lorb_ctx: a CUDA stream plus device/pinned scratch.  Not thread-safe;
     make one per calling thread (the reference runs Matcher on the tracking
@@ -253,8 +272,22 @@ class Context:
         self._plan_n = len(pa)
         _check(self._lib.lorb_sweep_plan_upload(self._h, _ptr(pa), _ptr(pb), len(pa)))
 
-    def sweep_plan_run(self, kf_base=0):
-        _check(self._lib.lorb_sweep_plan_run_at(self._h, int(kf_base)))
+    def sweep_plan_run(self, kf_base=0, kf_base_b=None):
+        if kf_base_b is None:
+            _check(self._lib.lorb_sweep_plan_run_at(self._h, int(kf_base)))
+        else:
+            _check(self._lib.lorb_sweep_plan_run_at2(self._h, int(kf_base), int(kf_base_b)))
+
+    def match_sweep_all(self, n_kf, block_kf, rank=0, world=1, out=None):
+        """Every unordered keyframe pair of the resident bank, this rank's tiles of the keyframe
+        grid (lorb_match_sweep_all).  -> (kept counts [n_kf (n_kf - 1) / 2], pairs done)."""
+        n = n_kf * (n_kf - 1) // 2
+        if out is None:
+            out = np.zeros(max(1, n), np.int32)
+        done = C.c_longlong()
+        _check(self._lib.lorb_match_sweep_all(self._h, int(block_kf), int(rank), int(world), _ptr(out),
+                                              C.byref(done)))
+        return out[:n], done.value
 
     def sweep_plan_download(self):
         n = self._plan_n
@@ -538,6 +571,11 @@ class Context:
         ms, n = C.c_double(), C.c_longlong()
         _check(self._lib.lorb_ctx_profile_read(self._h, int(slot), C.byref(ms), C.byref(n)))
         return ms.value, n.value
+
+    def microbench_tensor_i8(self, tiles=4096):
+        r = C.c_double()
+        _check(self._lib.lorb_microbench_tensor_i8(self._h, int(tiles), C.byref(r)))
+        return r.value
 
     def microbench_popc(self, kind=0, iters=4096):
         r = C.c_double()

@@ -1776,27 +1776,35 @@ __global__ void __launch_bounds__(1024) ba_chol_solve_kernel(const BADev* __rest
   for (int i = tid; i < n; i += blockDim.x) p.rhs[i] = y[i];
 }
 
-// Candidate cameras x_c - y_c * scale_c (+ their rotation blocks).
-__global__ void ba_candcam_kernel(const BADev* __restrict__ probs) {
+// Candidate cameras x_c - y_c * scale_c (+ their rotation blocks).  One CTA per window: the
+// camera parts of |step|^2 and |x + step|^2 are summed in a fixed order (strided per thread,
+// then a fixed shuffle / shared-memory tree), so that every rank of a sharded solve -- cameras
+// are replicated there -- gets the same bits and takes the same trust-region decision.
+__global__ void __launch_bounds__(128) ba_candcam_kernel(const BADev* __restrict__ probs) {
   const BADev p = probs[blockIdx.y];
   LMState* st = p.st;
   if (st->done) return;
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= p.C) return;
+  __shared__ double red[32];
   const int cur = st->cur;
   double step2 = 0, xc2 = 0;
+  for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
 #pragma unroll
-  for (int a = 0; a < 6; a++) {
-    const double d = -p.rhs[6 * c + a] * p.scale_c[6 * c + a];
-    const double x = p.cams[cur][6 * c + a] + d;
-    p.cams[cur ^ 1][6 * c + a] = x;
-    step2 += d * d;
-    xc2 += x * x;
+    for (int a = 0; a < 6; a++) {
+      const double d = -p.rhs[6 * c + a] * p.scale_c[6 * c + a];
+      const double x = p.cams[cur][6 * c + a] + d;
+      p.cams[cur ^ 1][6 * c + a] = x;
+      step2 += d * d;
+      xc2 += x * x;
+    }
+    cam_rotation(p.cams[cur ^ 1] + 6 * c, p.camrot[cur ^ 1] + CAMROT * c, true);
   }
-  cam_rotation(p.cams[cur ^ 1] + 6 * c, p.camrot[cur ^ 1] + CAMROT * c, true);
+  const double s2 = block_sum(step2, red);
+  const double x2 = block_sum(xc2, red);
   // camera parts are replicated on every rank: kept apart from the all-reduced sums
-  atomicAdd(&p.tail[3], step2);
-  atomicAdd(&p.tail[4], xc2);
+  if (threadIdx.x == 0) {
+    p.tail[3] = s2;
+    p.tail[4] = x2;
+  }
 }
 
 // Back-substitution, model decrease, candidate points and candidate cost.
@@ -2762,7 +2770,7 @@ static int problem_solve(lorb_ba_problem* pb, const lorb_ba_options* optp, int s
       LORB_LAUNCH(c, ba_gradcheck_kernel, dim3(1, nw), 256, 0, dp, opt, 0);
       LORB_LAUNCH(c, ba_finish_kernel, grid_fin, 256, 0, dp, opt);
       LORB_TRY(run_cholesky(pb));
-      LORB_LAUNCH(c, ba_candcam_kernel, grid_cam, 128, 0, dp);
+      LORB_LAUNCH(c, ba_candcam_kernel, dim3(1, nw), 128, 0, dp);
     }
     prof_end(c, 2);
     prof_begin(c, 1);
@@ -2773,6 +2781,9 @@ static int problem_solve(lorb_ba_problem* pb, const lorb_ba_options* optp, int s
       LORB_LAUNCH(c, ba_control_kernel, nw, 1, 0, dp, opt, d_active);
     }
     if ((it + 1) % poll_every == 0 && it + 1 < opt.max_num_iterations) {
+      // every rank takes the same decisions (same bits in, see ba_candcam_kernel); the max over
+      // the ranks makes leaving the loop a collective decision whatever happens
+      if (sharded) LORB_TRY(dist_allreduce_max_i32(c, d_active, 1));
       LORB_CUDA_TRY(cudaMemcpyAsync(h_active, d_active, 4, cudaMemcpyDeviceToHost, s));
       LORB_CUDA_TRY(cudaStreamSynchronize(s));
       if (*h_active == 0) break;

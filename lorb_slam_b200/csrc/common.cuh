@@ -60,7 +60,7 @@ struct lorb_ctx {
   lorb::Buf bank;
   int bank_n_kf = 0, bank_n_desc = 0;
   lorb::Buf plan_pairs, plan_out;
-  int plan_n_pairs = 0, plan_max_kf = 0;
+  int plan_n_pairs = 0, plan_max_a = 0, plan_max_b = 0;
   // tensor-core form of the sweep (match_tc.cu): int8 operand images of the bank, unit list,
   // row / column key scratch
   int sweep_impl = -1;  // LORB_SWEEP_POPC / LORB_SWEEP_TENSOR; -1 = default (env LORB_SWEEP_IMPL)
@@ -101,7 +101,7 @@ void prof_end(lorb_ctx* c, int slot);
 namespace tc {  // match_tc.cu
 int bank_expand(lorb_ctx* c);
 int plan_build(lorb_ctx* c, const int* pa, const int* pb, int n_pairs);
-int launch_sweep(lorb_ctx* c, int kf_base, int n_pairs, int* out);
+int launch_sweep(lorb_ctx* c, int kf_base_a, int kf_base_b, int n_pairs, int* out);
 }  // namespace tc
 
 // Kernel launch bookkeeping: every launch goes through this so that

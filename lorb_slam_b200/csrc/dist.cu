@@ -96,6 +96,19 @@ int dist_allreduce_max_u64(lorb_ctx* c, double* dev, size_t n) {
   return LORB_OK;
 }
 
+int dist_allreduce_max_i32(lorb_ctx* c, int* dev, size_t n) {
+  NcclApi* api = nccl_api();
+  if (!api || !dist_ready(c)) {
+    set_error("collective requested without an initialised communicator");
+    return LORB_ERR_STATE;
+  }
+  LORB_NCCL_TRY(api, api->AllReduce(dev, dev, n, ncclInt32, ncclMax, c->dist->comm, c->stream));
+  return LORB_OK;
+}
+
+int dist_rank(lorb_ctx* c) { return dist_ready(c) ? c->dist->rank : 0; }
+int dist_world(lorb_ctx* c) { return dist_ready(c) ? c->dist->world : 1; }
+
 }  // namespace lorb
 
 using namespace lorb;

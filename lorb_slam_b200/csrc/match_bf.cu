@@ -352,9 +352,11 @@ constexpr int SWEEP_THREADS = 512;
 
 template <int QPT, bool CSA>
 __global__ void __launch_bounds__(SWEEP_THREADS, 1)
-    sweep_kernel(const uint4* __restrict__ bank, int n_desc, const int2* __restrict__ pairs,
-                 int n_pairs, int* __restrict__ out /* [n_pairs][3] kept, matches, min */) {
-  // `bank` already points at keyframe kf_base (lorb_sweep_plan_run_at)
+    sweep_kernel(const uint4* __restrict__ bank, const uint4* __restrict__ bank_b, int n_desc,
+                 const int2* __restrict__ pairs, int n_pairs,
+                 int* __restrict__ out /* [n_pairs][3] kept, matches, min */) {
+  // `bank` / `bank_b` already point at the base keyframes of the a / b side
+  // (lorb_sweep_plan_run_at, lorb_sweep_plan_run_at2)
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int desc_bytes = n_desc * 32;
   const int buf_bytes = (desc_bytes + 127) & ~127;
@@ -384,7 +386,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1)
     mbar_arrive_expect_tx(&bar[0], (uint32_t)desc_bytes);
     tma_load_1d(As, bank + kf_u4 * p0.x, (uint32_t)desc_bytes, &bar[0]);
     mbar_arrive_expect_tx(&bar[1], (uint32_t)desc_bytes);
-    tma_load_1d(Bs0, bank + kf_u4 * p0.y, (uint32_t)desc_bytes, &bar[1]);
+    tma_load_1d(Bs0, bank_b + kf_u4 * p0.y, (uint32_t)desc_bytes, &bar[1]);
   }
   uint32_t q[QPT][8], qidx[QPT], rowkey[QPT], rowkey2[QPT];
   int cur_a = -1;
@@ -399,7 +401,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1)
       const int2 pn = pairs[p + 1];
       uint64_t* nb = &bar[1 + ((i + 1) & 1)];
       mbar_arrive_expect_tx(nb, (uint32_t)desc_bytes);
-      tma_load_1d((i & 1) ? Bs0 : Bs1, bank + kf_u4 * pn.y, (uint32_t)desc_bytes, nb);
+      tma_load_1d((i & 1) ? Bs0 : Bs1, bank_b + kf_u4 * pn.y, (uint32_t)desc_bytes, nb);
     }
     for (int j = tid; j < n_desc; j += SWEEP_THREADS) colkey[j] = KEY_NONE;
     if (pr.x != cur_a) {
@@ -491,33 +493,33 @@ static bool use_csa() {
 }
 
 template <int QPT>
-static int launch_sweep_qpt(lorb_ctx* c, const uint4* bank, int n_desc, const int2* pairs,
-                            int n_pairs, int* out) {
+static int launch_sweep_qpt(lorb_ctx* c, const uint4* bank, const uint4* bank_b, int n_desc,
+                            const int2* pairs, int n_pairs, int* out) {
   const size_t smem = sweep_smem_bytes(n_desc);
   const int grid = std::min(n_pairs, c->sm_count);
   if (use_csa()) {
     LORB_CUDA_TRY(cudaFuncSetAttribute(sweep_kernel<QPT, true>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    LORB_LAUNCH(c, (sweep_kernel<QPT, true>), grid, SWEEP_THREADS, smem, bank, n_desc, pairs,
+    LORB_LAUNCH(c, (sweep_kernel<QPT, true>), grid, SWEEP_THREADS, smem, bank, bank_b, n_desc, pairs,
                 n_pairs, out);
   } else {
     LORB_CUDA_TRY(cudaFuncSetAttribute(sweep_kernel<QPT, false>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    LORB_LAUNCH(c, (sweep_kernel<QPT, false>), grid, SWEEP_THREADS, smem, bank, n_desc, pairs,
+    LORB_LAUNCH(c, (sweep_kernel<QPT, false>), grid, SWEEP_THREADS, smem, bank, bank_b, n_desc, pairs,
                 n_pairs, out);
   }
   return LORB_OK;
 }
 
-static int launch_sweep(lorb_ctx* c, const uint4* bank, int n_desc, const int2* pairs, int n_pairs,
-                        int* out) {
+static int launch_sweep(lorb_ctx* c, const uint4* bank, const uint4* bank_b, int n_desc,
+                        const int2* pairs, int n_pairs, int* out) {
   if (n_pairs == 0) return LORB_OK;
   const int qpt = (n_desc + SWEEP_THREADS - 1) / SWEEP_THREADS;
   switch (qpt) {
-    case 1: return launch_sweep_qpt<1>(c, bank, n_desc, pairs, n_pairs, out);
-    case 2: return launch_sweep_qpt<2>(c, bank, n_desc, pairs, n_pairs, out);
-    case 3: return launch_sweep_qpt<3>(c, bank, n_desc, pairs, n_pairs, out);
-    case 4: return launch_sweep_qpt<4>(c, bank, n_desc, pairs, n_pairs, out);
+    case 1: return launch_sweep_qpt<1>(c, bank, bank_b, n_desc, pairs, n_pairs, out);
+    case 2: return launch_sweep_qpt<2>(c, bank, bank_b, n_desc, pairs, n_pairs, out);
+    case 3: return launch_sweep_qpt<3>(c, bank, bank_b, n_desc, pairs, n_pairs, out);
+    case 4: return launch_sweep_qpt<4>(c, bank, bank_b, n_desc, pairs, n_pairs, out);
   }
   set_error("sweep: n_desc=%d exceeds the shared-memory resident limit (2048)", n_desc);
   return LORB_ERR_ARG;
@@ -755,8 +757,11 @@ int lorb_sweep_plan_upload(lorb_ctx* c, const int* pa, const int* pb, int n_pair
   LORB_TRY(check_pairs(c, pa, pb, n_pairs));
   LORB_CUDA_TRY(cudaSetDevice(c->device));
   c->plan_n_pairs = n_pairs;
-  c->plan_max_kf = 0;
-  for (int i = 0; i < n_pairs; i++) c->plan_max_kf = std::max(c->plan_max_kf, std::max(pa[i], pb[i]));
+  c->plan_max_a = c->plan_max_b = 0;
+  for (int i = 0; i < n_pairs; i++) {
+    c->plan_max_a = std::max(c->plan_max_a, pa[i]);
+    c->plan_max_b = std::max(c->plan_max_b, pb[i]);
+  }
   if (n_pairs == 0) return LORB_OK;
   LORB_TRY(c->plan_pairs.reserve((size_t)n_pairs * 8));
   LORB_TRY(c->plan_out.reserve((size_t)n_pairs * 12));
@@ -775,19 +780,22 @@ int lorb_sweep_plan_upload(lorb_ctx* c, const int* pa, const int* pb, int n_pair
   return LORB_OK;
 }
 
-int lorb_sweep_plan_run_at(lorb_ctx* c, int kf_base) {
+int lorb_sweep_plan_run_at2(lorb_ctx* c, int kf_base_a, int kf_base_b) {
   LORB_REQUIRE(c, "ctx");
   LORB_REQUIRE(c->bank_n_kf > 0, "no bank uploaded");
-  LORB_REQUIRE(kf_base >= 0 && kf_base + c->plan_max_kf < c->bank_n_kf, "kf_base out of range");
+  LORB_REQUIRE(kf_base_a >= 0 && kf_base_a + c->plan_max_a < c->bank_n_kf, "kf_base_a out of range");
+  LORB_REQUIRE(kf_base_b >= 0 && kf_base_b + c->plan_max_b < c->bank_n_kf, "kf_base_b out of range");
   LORB_CUDA_TRY(cudaSetDevice(c->device));
   if (sweep_impl(c) == LORB_SWEEP_TENSOR) {
     LORB_REQUIRE(c->plan_n_pairs == 0 || c->tc_n_units > 0, "plan was uploaded for the popc kernel");
-    return tc::launch_sweep(c, kf_base, c->plan_n_pairs, c->plan_out.as<int>());
+    return tc::launch_sweep(c, kf_base_a, kf_base_b, c->plan_n_pairs, c->plan_out.as<int>());
   }
-  return launch_sweep(c, c->bank.as<uint4>() + (size_t)kf_base * c->bank_n_desc * 2,
-                      c->bank_n_desc, c->plan_pairs.as<int2>(), c->plan_n_pairs,
-                      c->plan_out.as<int>());
+  const size_t kf_u4 = (size_t)c->bank_n_desc * 2;
+  return launch_sweep(c, c->bank.as<uint4>() + kf_u4 * kf_base_a, c->bank.as<uint4>() + kf_u4 * kf_base_b,
+                      c->bank_n_desc, c->plan_pairs.as<int2>(), c->plan_n_pairs, c->plan_out.as<int>());
 }
+
+int lorb_sweep_plan_run_at(lorb_ctx* c, int kf_base) { return lorb_sweep_plan_run_at2(c, kf_base, kf_base); }
 
 int lorb_sweep_plan_run(lorb_ctx* c) { return lorb_sweep_plan_run_at(c, 0); }
 
@@ -816,6 +824,87 @@ int lorb_match_sweep_resident(lorb_ctx* c, const int* pa, const int* pb, int n_p
   LORB_TRY(lorb_sweep_plan_upload(c, pa, pb, n_pairs));
   LORB_TRY(lorb_sweep_plan_run(c));
   return lorb_sweep_plan_download(c, out_kept, out_matches, out_min);
+}
+
+// ---- the whole sweep as a tile grid: blocks of block_kf keyframes, the
+// upper-triangular grid of (block, block) tiles dealt round-robin to the ranks.
+long long lorb_sweep_tile_count(int n_kf, int block_kf) {
+  if (n_kf <= 0 || block_kf <= 0) return 0;
+  const long long T = (n_kf + block_kf - 1) / block_kf;
+  return T * (T + 1) / 2;
+}
+
+long long lorb_sweep_pair_index(int n_kf, int a, int b) {
+  if (a > b) std::swap(a, b);
+  return (long long)a * n_kf - (long long)a * (a + 1) / 2 + (b - a - 1);
+}
+
+int lorb_sweep_rank_tiles(int n_kf, int block_kf, int rank, int world, int cap, int* tile_bi,
+                          int* tile_bj, int* n_out) {
+  LORB_REQUIRE(n_kf > 0 && block_kf > 0 && world >= 1 && rank >= 0 && rank < world && n_out, "arguments");
+  const int T = (n_kf + block_kf - 1) / block_kf;
+  long long t = 0;
+  int n = 0;
+  for (int bi = 0; bi < T; bi++)
+    for (int bj = bi; bj < T; bj++, t++) {
+      if (t % world != rank) continue;
+      // a one-keyframe diagonal block has no pair
+      if (bi == bj && std::min(block_kf, n_kf - bi * block_kf) < 2) continue;
+      if (n < cap && tile_bi && tile_bj) {
+        tile_bi[n] = bi;
+        tile_bj[n] = bj;
+      }
+      n++;
+    }
+  *n_out = n;
+  return LORB_OK;
+}
+
+int lorb_match_sweep_all(lorb_ctx* c, int block_kf, int rank, int world, int* out_kept,
+                         long long* n_pairs_done) {
+  LORB_REQUIRE(c && out_kept, "ctx / out_kept");
+  LORB_REQUIRE(c->bank_n_kf > 0, "no bank uploaded");
+  LORB_REQUIRE(block_kf >= 1, "block_kf");
+  const int n_kf = c->bank_n_kf;
+  int n_tiles = 0;
+  LORB_TRY(lorb_sweep_rank_tiles(n_kf, block_kf, rank, world, 0, nullptr, nullptr, &n_tiles));
+  std::vector<int> bi(std::max(1, n_tiles)), bj(std::max(1, n_tiles));
+  LORB_TRY(lorb_sweep_rank_tiles(n_kf, block_kf, rank, world, n_tiles, bi.data(), bj.data(), &n_tiles));
+  // tiles of one shape (rows, columns, diagonal?) share a plan: go shape by shape
+  std::vector<int> order(n_tiles);
+  auto shape = [&](int t) {
+    const int na = std::min(block_kf, n_kf - bi[t] * block_kf), nb = std::min(block_kf, n_kf - bj[t] * block_kf);
+    return ((long long)na << 33) | ((long long)nb << 1) | (bi[t] == bj[t] ? 1 : 0);
+  };
+  for (int t = 0; t < n_tiles; t++) order[t] = t;
+  std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return shape(x) > shape(y); });
+  long long done = 0, cur_shape = -1;
+  std::vector<int> pa, pb, kept;
+  for (int k = 0; k < n_tiles; k++) {
+    const int t = order[k];
+    const int na = std::min(block_kf, n_kf - bi[t] * block_kf), nb = std::min(block_kf, n_kf - bj[t] * block_kf);
+    const bool diag = bi[t] == bj[t];
+    if (shape(t) != cur_shape) {
+      pa.clear();
+      pb.clear();
+      for (int a = 0; a < na; a++)
+        for (int b = diag ? a + 1 : 0; b < nb; b++) {
+          pa.push_back(a);
+          pb.push_back(b);
+        }
+      LORB_TRY(lorb_sweep_plan_upload(c, pa.data(), pb.data(), (int)pa.size()));
+      kept.resize(pa.size());
+      cur_shape = shape(t);
+    }
+    const int base_a = bi[t] * block_kf, base_b = bj[t] * block_kf;
+    LORB_TRY(lorb_sweep_plan_run_at2(c, base_a, base_b));
+    LORB_TRY(lorb_sweep_plan_download(c, kept.data(), nullptr, nullptr));
+    for (size_t i = 0; i < pa.size(); i++)
+      out_kept[lorb_sweep_pair_index(n_kf, base_a + pa[i], base_b + pb[i])] = kept[i];
+    done += (long long)pa.size();
+  }
+  if (n_pairs_done) *n_pairs_done = done;
+  return LORB_OK;
 }
 
 int lorb_match_sweep(lorb_ctx* c, const uint8_t* bank, int n_kf, int n_desc, const int* pa,

@@ -106,7 +106,8 @@ __global__ void tc_fill_kernel(int* __restrict__ p, long long n, int v) {
 __device__ __forceinline__ int max3(int a, int b, int c) { return max(max(a, b), c); }
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
-    tc_sweep_kernel(const uint8_t* __restrict__ img, long long kf_bytes, const int4* __restrict__ units,
+    tc_sweep_kernel(const uint8_t* __restrict__ img, const uint8_t* __restrict__ img_b, long long kf_bytes,
+                    const int4* __restrict__ units,
                     int n_units, int n_mtiles, int n_pad, int* __restrict__ rowkey,
                     int* __restrict__ colkey) {
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -164,7 +165,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                       res_full);
           g++;
         }
-        const uint8_t* src = img + (size_t)un.y * kf_bytes;
+        const uint8_t* src = img_b + (size_t)un.y * kf_bytes;
         for (int m = 0; m < n_mtiles; m++, t++) {
           const uint32_t stage = t % STAGES, k = t / STAGES;
           mbar_wait_parity(&empty[stage], (k & 1u) ^ 1u);
@@ -361,6 +362,48 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// ---------------------------------------------------------------- tensor-pipe micro-benchmark
+// The sweep's own MMA stream (9 x tcgen05.mma kind::i8 128x256x32 per tile, two accumulator
+// buffers) on zeroed operands with no TMA and no epilogue: the rate at which this instruction
+// mix can possibly run on this part.
+__global__ void __launch_bounds__(128, 1) tc_mma_bench_kernel(int tiles) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + SLAB_BYTES + MTILE_BYTES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < (SLAB_BYTES + MTILE_BYTES) / 16; i += 128)
+    reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_barrier_init();
+  }
+  fence_proxy_async();  // generic-proxy zero fill -> async-proxy (tensor core) reads
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  if (tid == 0) {
+    constexpr uint32_t IDESC = idesc_s8(MT_ROWS, SLAB_COLS);
+    const uint32_t b_addr = smem_u32(smem), a_addr = b_addr + SLAB_BYTES;
+    for (int t = 0; t < tiles; t++) {
+      const uint32_t d_addr = tmem_base + (t & 1) * SLAB_COLS;
+#pragma unroll
+      for (int k = 0; k < 9; k++)
+        mma_s8(d_addr, smem_desc(a_addr + k * 256, 128, RG_BYTES), smem_desc(b_addr + k * 256, 128, RG_BYTES),
+               IDESC, k > 0 ? 1u : 0u);
+    }
+    mma_commit(bar);
+    mbar_wait_parity(bar, 0);
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) {
+    fence_after_sync();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // ---------------------------------------------------------------- host side
 int pad_of(int n_desc) { return (n_desc + SLAB_COLS - 1) / SLAB_COLS * SLAB_COLS; }
 size_t image_bytes(int n_desc) { return (size_t)(pad_of(n_desc) / 8) * RG_BYTES; }
@@ -408,7 +451,7 @@ int plan_build(lorb_ctx* c, const int* pa, const int* pb, int n_pairs) {
   return LORB_OK;
 }
 
-int launch_sweep(lorb_ctx* c, int kf_base, int n_pairs, int* out) {
+int launch_sweep(lorb_ctx* c, int kf_base_a, int kf_base_b, int n_pairs, int* out) {
   if (n_pairs == 0 || c->tc_n_units == 0) return LORB_OK;
   const int n_desc = c->bank_n_desc, n_pad = pad_of(n_desc);
   const size_t kf_bytes = image_bytes(n_desc);
@@ -417,12 +460,41 @@ int launch_sweep(lorb_ctx* c, int kf_base, int n_pairs, int* out) {
   int* rowkey = c->tc_keys.as<int>();
   int* colkey = rowkey + c->tc_keys_rows;
   const int grid = std::min(c->tc_n_units, c->sm_count);
+  prof_begin(c, 3);
   LORB_LAUNCH(c, tc_sweep_kernel, grid, TC_THREADS, TC_SMEM_BYTES,
-              c->tc_img.as<uint8_t>() + (size_t)kf_base * kf_bytes, (long long)kf_bytes,
+              c->tc_img.as<uint8_t>() + (size_t)kf_base_a * kf_bytes,
+              c->tc_img.as<uint8_t>() + (size_t)kf_base_b * kf_bytes, (long long)kf_bytes,
               c->tc_units.as<int4>(), c->tc_n_units, n_pad / MT_ROWS, n_pad, rowkey, colkey);
+  prof_end(c, 3);
   LORB_LAUNCH(c, tc_finalize_kernel, n_pairs, 256, 0, rowkey, colkey, n_desc, n_pad, out);
   return LORB_OK;
 }
 
 }  // namespace tc
 }  // namespace lorb
+
+extern "C" int lorb_microbench_tensor_i8(lorb_ctx* c, int tiles, double* ops_per_s) {
+  using namespace lorb;
+  using namespace lorb::tc;
+  LORB_REQUIRE(c && ops_per_s, "ctx/out");
+  LORB_REQUIRE(tiles > 0, "tiles");
+  LORB_CUDA_TRY(cudaSetDevice(c->device));
+  const int smem = SLAB_BYTES + MTILE_BYTES + 64;
+  LORB_CUDA_TRY(cudaFuncSetAttribute(tc_mma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  cudaEvent_t e0, e1;
+  LORB_CUDA_TRY(cudaEventCreate(&e0));
+  LORB_CUDA_TRY(cudaEventCreate(&e1));
+  for (int rep = 0; rep < 2; rep++) {  // first pass warms up
+    LORB_CUDA_TRY(cudaEventRecord(e0, c->stream));
+    LORB_LAUNCH(c, tc_mma_bench_kernel, c->sm_count, 128, smem, tiles);
+    LORB_CUDA_TRY(cudaEventRecord(e1, c->stream));
+    LORB_CUDA_TRY(cudaEventSynchronize(e1));
+  }
+  float ms = 0;
+  LORB_CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  // 9 MMAs of 128 x 256 x 32 multiply-adds per tile and SM, 2 operations each
+  *ops_per_s = (double)c->sm_count * tiles * 9.0 * MT_ROWS * SLAB_COLS * 32.0 * 2.0 / (ms * 1e-3);
+  return LORB_OK;
+}
