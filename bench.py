@@ -388,6 +388,63 @@ def run_sweep(args, rank, world, local):
     return res, bank
 
 
+def run_full_sweep(args, rank, world, local, bank):
+    """BASELINE config 5's sweep in full, as SURVEY 8(e) row 1 specifies it: all 8 386 560 unordered
+    keyframe pairs of the 4096-keyframe bank as an upper-triangular grid of 128 x 128-keyframe tiles
+    dealt round-robin to the ranks (lorb_match_sweep_all), no collective during compute, then one
+    gather (sum-reduce of the zero-initialised per-pair arrays, 33.5 MB) of the kept counts on rank 0;
+    64 random off-diagonal keyframe pairs are checked against the oracle."""
+    import torch
+    import torch.distributed as dist
+    from lorb_slam_b200 import capi
+    ctx = capi.Context(local)
+    ctx.sweep_set_impl(args.sweep_impl)
+    ctx.bank_upload(bank)
+    n_all = N_KF * (N_KF - 1) // 2
+    pinned = torch.zeros(n_all, dtype=torch.int32).pin_memory()
+    _barrier(world)
+    l0 = ctx.launch_count
+    t0 = time.perf_counter()
+    kept, done = ctx.match_sweep_all(N_KF, BLOCK_KF, rank, world, out=pinned.numpy())
+    ctx.sync()
+    t_compute = _max_over_ranks(time.perf_counter() - t0, world, local)
+    launches = ctx.launch_count - l0
+    t1 = time.perf_counter()
+    dev = pinned.cuda(non_blocking=True)
+    if world > 1:
+        dist.reduce(dev, 0, op=dist.ReduceOp.SUM)
+    torch.cuda.synchronize()
+    t_gather = _max_over_ranks(time.perf_counter() - t1, world, local)
+    total_done = _sum_over_ranks(float(done), world, local)
+    res = None
+    if rank == 0:
+        from oracle import ref
+        allk = dev.cpu().numpy()
+        rng = np.random.default_rng(7)
+        pa = rng.integers(0, N_KF, 64).astype(np.int32)
+        pb = ((pa + rng.integers(BLOCK_KF, N_KF - BLOCK_KF, 64)) % N_KF).astype(np.int32)  # other blocks
+        ref.set_num_threads(os.cpu_count() or 1)
+        ok_kept = ref.sweep(bank, pa, pb)[0]
+        got = np.array([allk[capi.sweep_pair_index(N_KF, int(a), int(b))] for a, b in zip(pa, pb)])
+        wall = t_compute + t_gather
+        res = {"metric": "descriptor-pairs/s Hamming match", "unit": "descriptor-pairs/s",
+               "value": total_done * PAIRS_PER_KF_PAIR / wall, "n_gpus": world, "scaling": "strong",
+               "keyframe_pairs": int(total_done), "descriptor_pairs": total_done * PAIRS_PER_KF_PAIR,
+               "wall_s": wall, "compute_s": t_compute, "gather_s": t_gather,
+               "gather_bytes": int(4 * n_all), "gpu_launches_rank0": int(launches),
+               "config": {"workload": "whole keyframe-pair sweep: 4096 keyframes x 2000 descriptors, all %d unordered "
+                                      "pairs = %d tiles of 128 x 128 keyframes, tile t on rank t %% %d, kept counts "
+                                      "gathered on rank 0" % (n_all, N_KF // BLOCK_KF * (N_KF // BLOCK_KF + 1) // 2, world),
+                          "kernel": args.sweep_impl},
+               "kept_total": int(allk.sum(dtype=np.int64)),
+               "parity": {"ok": bool(np.array_equal(got, ok_kept) and int(total_done) == n_all),
+                          "checked": "64 random keyframe pairs from different blocks against the oracle "
+                                     "(kept counts bit-exact); every pair processed exactly once: %s"
+                                     % (int(total_done) == n_all)}}
+    ctx.close()
+    return res
+
+
 # ------------------------------------------------------------------- BA extras
 def _ba_opts_fixed_iters(mod, iters=10):
     """Exactly `iters` LM attempts: tolerances disabled (negative), as BASELINE's
@@ -624,7 +681,8 @@ def run_ba_batched(args, rank, world, local, steps=None, want_cpu=True):
         e_cams, e_pts, _ = ctx.ba_local_batched(bt, opt)
     e2e_dt = _max_over_ranks(time.perf_counter() - t0, world, local)
     e2e_value = steps * total_obs * iters / e2e_dt
-    same = bool(np.array_equal(e_cams, cams_res) and np.array_equal(e_pts, pts_res))
+    # the two paths sum their partial results with atomics (no fixed order): compare by tolerance
+    same = bool(max(_rel_err(e_cams, cams_res), _rel_err(e_pts, pts_res)) <= 1.0)
     res = None
     if rank == 0:
         from oracle import ref
@@ -654,7 +712,7 @@ def run_ba_batched(args, rank, world, local, steps=None, want_cpu=True):
                "parity": {"ok": bool(err <= 1.0 and same), "max_err_over_tolerance": err,
                           "tolerance": "rtol 1e-6 + atol 1e-8 on final cameras and points",
                           "checked": "window %d (rank 0) against the oracle after 10 LM iterations; "
-                                     "host-buffer call == resident solve bit for bit: %s" % (lo, same),
+                                     "host-buffer call == resident solve within the same tolerance: %s" % (lo, same),
                           "lm_steps_ok_rejected": {"gpu": [sums[0]["num_successful_steps"], sums[0]["num_unsuccessful_steps"]],
                                                    "oracle": [so["num_successful_steps"], so["num_unsuccessful_steps"]],
                                                    "note": "tolerances are off (10 attempts forced): attempts past "
@@ -812,6 +870,10 @@ def main():
 
     rank, world, local = _dist_setup(args.gpus)
     want_cpu = not args.no_cpu_baseline
+    # torchrun exports OMP_NUM_THREADS=1 to every rank: give each rank its share of the host cores
+    # for the library's staging loops (the host-buffer calls of the e2e legs)
+    from lorb_slam_b200 import capi as _capi
+    _capi.set_host_threads(max(1, (os.cpu_count() or 1) // max(1, world)))
     if args.workload == "ba_batched":
         res = run_ba_batched(args, rank, world, local, want_cpu=want_cpu)
     elif args.workload == "ba_large":
@@ -828,6 +890,10 @@ def main():
                     ctx.close()
             if world == 1 and want_cpu:
                 res["cpu_baseline"] = cpu_baseline_sweep(bank)
+        if args.workload == "all":
+            f = run_full_sweep(args, rank, world, local, bank)
+            if rank == 0:
+                res["full_sweep"] = f
         del bank
         if args.workload == "all":
             # the other two BASELINE metrics, same contract, shorter runs

@@ -70,11 +70,15 @@ const char* lorb_version(void);
 
 /* Cross-check mode.  MUTUAL is what OpenCV >= 3.4 / 4.x does (executable pin:
  * cv2 4.13 in this image): keep (q,t) iff t = argmin_t' d(q,t') and
- * q = argmin_q' d(q',t), lowest index winning ties on both sides.
- * LEGACY restates OpenCV 3.1's batchDistance cross-check as recalled from its
- * source (the version the reference pins, CMakeLists.txt:10; not executable
- * here): for every train t take q = argmin_q' d(q',t); query q keeps the t of
- * smallest d among those (lowest t on ties). */
+ * q = argmin_q' d(q',t), lowest index winning ties on both sides.  It is the
+ * only mode the drop-in Matcher uses and the only one with a reference behind it.
+ *
+ * LEGACY is EXPERIMENTAL and UNPINNED: a restatement of OpenCV 3.1's
+ * batchDistance cross-check as recalled from its source (the version the
+ * reference's CMakeLists.txt:10 names; not executable here, so nothing pins it):
+ * for every train t take q = argmin_q' d(q',t); query q keeps the t of smallest
+ * d among those (lowest t on ties).  Kept for experiments against a real 3.1
+ * build; no product path selects it and no parity claim covers it. */
 enum { LORB_CROSSCHECK_MUTUAL = 0, LORB_CROSSCHECK_LEGACY = 1 };
 
 /*
@@ -516,12 +520,20 @@ int lorb_ba_local(lorb_ctx* ctx, int C, double* cams, int P, double* pts, int O,
  *   fixed observations [fix_off[w] .. fix_off[w+1]) likewise (fix_off may be
  *   NULL when there are none).
  * Every window runs its own LM loop (own trust region, own termination).
+ * Batches of 64 windows and more are cut into chunks that two host threads take alternately (the
+ * second with an internal context on the same device), so that staging / upload of one chunk
+ * overlaps the solve of another (LORB_BA_PIPELINE=0 turns that off).
  */
 int lorb_ba_local_batched(lorb_ctx* ctx, int n_windows, const int* cam_off, double* cams,
                           const int* pt_off, double* pts, const int* obs_off, const int* obs_cam,
                           const int* obs_pt, const float* obs_uv, const int* fix_off,
                           const int* fix_pt, const float* fix_uv, const float* fix_rt,
                           const float* K, const lorb_ba_options* opt, lorb_ba_summary* summaries);
+
+/* Team size of the library's host-side staging loops (OpenMP) for the calling thread.  Launchers
+ * such as torchrun export OMP_NUM_THREADS=1 to every rank; a host that knows how many ranks share
+ * the box hands each its share of the cores here. */
+int lorb_set_host_threads(int n);
 
 /* Device-resident local BA problem, for timing the solver without the
  * host<->device copies and for the multi-GPU sharded solve. */
@@ -540,6 +552,23 @@ int lorb_ba_problem_create_batched(lorb_ctx* ctx, int n_windows, const int* cam_
                                    const float* obs_uv, const int* fix_off, const int* fix_pt,
                                    const float* fix_uv, const float* fix_rt, const float* K,
                                    lorb_ba_problem** out);
+/*
+ * Sharding helpers of the multi-GPU paths, so that a C++ host need not restate them:
+ *   lorb_shard_range   contiguous [lo, hi) slice of n units (windows, points) owned by `rank`:
+ *                      sizes differ by at most one, the first n % world ranks take the extra unit
+ *   lorb_ba_problem_create_sharded
+ *                      the point shard of `rank` of a WHOLE problem given in the arrays of
+ *                      lorb_ba_problem_create: points [pt_lo, pt_hi) = lorb_shard_range(P) with all
+ *                      their observations (renumbered from 0), every camera replicated.  Solve with
+ *                      lorb_ba_problem_solve(..., sharded = 1); lorb_ba_problem_download then returns
+ *                      all C cameras (identical on every rank) and this rank's pt_hi - pt_lo points.
+ */
+int lorb_shard_range(long long n, int rank, int world, long long* lo, long long* hi);
+int lorb_ba_problem_create_sharded(lorb_ctx* ctx, int C, const double* cams, int P, const double* pts,
+                                   int O, const int* obs_cam, const int* obs_pt, const float* obs_uv,
+                                   int F, const int* fix_pt, const float* fix_uv, const float* fix_rt,
+                                   const float* K, int rank, int world, lorb_ba_problem** out,
+                                   int* pt_lo, int* pt_hi);
 /* Restore the parameters uploaded at creation (so a bench can re-solve). */
 int lorb_ba_problem_reset(lorb_ba_problem* p);
 /* Run LM on the resident problem.  If the ctx has a distributed group

@@ -30,7 +30,7 @@ EXPORTS = [
     "lorb_stereo_matches", "lorb_orb_describe", "lorb_orb_umax", "lorb_orb_selftest",
     "lorb_orb_extract", "lorb_orb_level_sizes", "lorb_orb_stages", "lorb_stereo_frame", "lorb_orb_distribute", "lorb_orb_max_keypoints",
     "lorb_ba_default_options", "lorb_ba_pose_only", "lorb_ba_local", "lorb_ba_local_batched",
-    "lorb_ba_problem_create", "lorb_ba_problem_create_batched", "lorb_ba_problem_reset", "lorb_ba_problem_solve",
+    "lorb_ba_problem_create", "lorb_ba_problem_create_batched", "lorb_ba_problem_create_sharded", "lorb_shard_range", "lorb_set_host_threads", "lorb_ba_problem_reset", "lorb_ba_problem_solve",
     "lorb_ba_problem_download", "lorb_ba_problem_destroy", "lorb_dist_get_unique_id",
     "lorb_dist_init", "lorb_dist_finalize", "lorb_dist_allreduce_f64", "lorb_microbench_popc",
     "lorb_microbench_fp64", "lorb_microbench_tensor_i8", "lorb_ctx_profile", "lorb_ctx_profile_read",
@@ -167,6 +167,17 @@ def sweep_rank_tiles(n_kf, block_kf, rank, world):
     _check(lib.lorb_sweep_rank_tiles(int(n_kf), int(block_kf), int(rank), int(world), n.value, _ptr(bi),
                                      _ptr(bj), C.byref(n)))
     return list(zip(bi[:n.value].tolist(), bj[:n.value].tolist()))
+
+
+def set_host_threads(n):
+    _check(load_library().lorb_set_host_threads(int(n)))
+
+
+def shard_range(n, rank, world):
+    """Contiguous [lo, hi) slice of n units owned by `rank` (lorb_shard_range; host logic only)."""
+    lo, hi = C.c_longlong(), C.c_longlong()
+    _check(load_library().lorb_shard_range(C.c_longlong(int(n)), int(rank), int(world), C.byref(lo), C.byref(hi)))
+    return int(lo.value), int(hi.value)
 
 
 def sweep_pair_index(n_kf, a, b):
@@ -537,6 +548,10 @@ class Context:
     def ba_problem_batched(self, bt):
         return BAProblem(self, None, batch=bt)
 
+    def ba_problem_sharded(self, pb, rank, world):
+        """This rank's point shard of the whole problem `pb` (lorb_ba_problem_create_sharded)."""
+        return BAProblem(self, pb, shard=(rank, world))
+
     # -- multi-GPU
     @staticmethod
     def dist_unique_id():
@@ -586,7 +601,7 @@ class Context:
 class BAProblem:
     """Device-resident local-BA problem (lorb_ba_problem_*)."""
 
-    def __init__(self, ctx, pb, batch=None):
+    def __init__(self, ctx, pb, batch=None, shard=None):
         self._ctx = ctx
         self._lib = ctx._lib
         self.nw = 1
@@ -614,6 +629,16 @@ class BAProblem:
         K = _arr(pb["K"], np.float32).reshape(4)
         self.C, self.P = len(cams), len(pts)
         h = C.c_void_p()
+        if shard is not None:
+            lo, hi = C.c_int(), C.c_int()
+            _check(self._lib.lorb_ba_problem_create_sharded(
+                ctx._h, len(cams), _ptr(cams), len(pts), _ptr(pts), len(oc), _ptr(oc), _ptr(op),
+                _ptr(ouv), len(fp), _ptr(fp), _ptr(fuv), _ptr(frt), _ptr(K), int(shard[0]), int(shard[1]),
+                C.byref(h), C.byref(lo), C.byref(hi)))
+            self.point_range = (lo.value, hi.value)
+            self.P = hi.value - lo.value
+            self._h = h
+            return
         _check(self._lib.lorb_ba_problem_create(
             ctx._h, len(cams), _ptr(cams), len(pts), _ptr(pts), len(oc), _ptr(oc), _ptr(op),
             _ptr(ouv), len(fp), _ptr(fp), _ptr(fuv), _ptr(frt), _ptr(K), C.byref(h)))

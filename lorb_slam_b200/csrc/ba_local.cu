@@ -25,6 +25,8 @@
 #include <algorithm>
 #include <chrono>
 #include <new>
+#include <string>
+#include <thread>
 #include <vector>
 
 #include <cub/cub.cuh>
@@ -2893,6 +2895,49 @@ int lorb_ba_problem_create(lorb_ctx* c, int C, const double* cams, int P, const 
   return LORB_OK;
 }
 
+int lorb_shard_range(long long n, int rank, int world, long long* lo, long long* hi) {
+  LORB_REQUIRE(n >= 0 && world >= 1 && rank >= 0 && rank < world && lo && hi, "arguments");
+  const long long base = n / world, rem = n % world;
+  *lo = rank * base + std::min<long long>(rank, rem);
+  *hi = *lo + base + (rank < rem ? 1 : 0);
+  return LORB_OK;
+}
+
+int lorb_ba_problem_create_sharded(lorb_ctx* c, int C, const double* cams, int P, const double* pts,
+                                   int O, const int* obs_cam, const int* obs_pt, const float* obs_uv,
+                                   int F, const int* fix_pt, const float* fix_uv, const float* fix_rt,
+                                   const float* K, int rank, int world, lorb_ba_problem** out,
+                                   int* pt_lo, int* pt_hi) {
+  LORB_REQUIRE(c && out && K, "ctx / out / K");
+  LORB_REQUIRE(C > 0 && P >= 0 && O >= 0 && F >= 0, "sizes");
+  LORB_REQUIRE(O == 0 || (obs_cam && obs_pt && obs_uv), "observations");
+  LORB_REQUIRE(F == 0 || (fix_pt && fix_uv && fix_rt), "fixed observations");
+  long long lo = 0, hi = 0;
+  LORB_TRY(lorb_shard_range(P, rank, world, &lo, &hi));
+  std::vector<int> oc, op, fp;
+  std::vector<float> ouv, fuv, frt;
+  for (int o = 0; o < O; o++) {
+    LORB_REQUIRE(obs_pt[o] >= 0 && obs_pt[o] < P, "observation point index");
+    if (obs_pt[o] < lo || obs_pt[o] >= hi) continue;
+    oc.push_back(obs_cam[o]);
+    op.push_back(obs_pt[o] - (int)lo);
+    ouv.push_back(obs_uv[2 * (size_t)o]);
+    ouv.push_back(obs_uv[2 * (size_t)o + 1]);
+  }
+  for (int f = 0; f < F; f++) {
+    LORB_REQUIRE(fix_pt[f] >= 0 && fix_pt[f] < P, "fixed observation point index");
+    if (fix_pt[f] < lo || fix_pt[f] >= hi) continue;
+    fp.push_back(fix_pt[f] - (int)lo);
+    fuv.insert(fuv.end(), fix_uv + 2 * (size_t)f, fix_uv + 2 * (size_t)f + 2);
+    frt.insert(frt.end(), fix_rt + 6 * (size_t)f, fix_rt + 6 * (size_t)f + 6);
+  }
+  if (pt_lo) *pt_lo = (int)lo;
+  if (pt_hi) *pt_hi = (int)hi;
+  return lorb_ba_problem_create(c, C, cams, (int)(hi - lo), pts ? pts + 3 * (size_t)lo : nullptr, (int)oc.size(),
+                                oc.data(), op.data(), ouv.data(), (int)fp.size(), fp.data(), fuv.data(),
+                                frt.data(), K, out);
+}
+
 int lorb_ba_problem_reset(lorb_ba_problem* pb) {
   LORB_REQUIRE(pb, "problem");
   LORB_CUDA_TRY(cudaSetDevice(pb->ctx->device));
@@ -3002,12 +3047,58 @@ int lorb_ba_local_batched(lorb_ctx* c, int n_windows, const int* cam_off, double
   std::vector<WindowSpec> ws;
   LORB_TRY(batched_specs(ws, n_windows, cam_off, cams, pt_off, pts, obs_off, obs_cam, obs_pt, obs_uv,
                          fix_off, fix_pt, fix_uv, fix_rt));
-  lorb_ba_problem* pb = cached_problem(c);
-  if (!pb) return LORB_ERR_NOMEM;
-  LORB_TRY(problem_build(pb, c, ws, K));
-  LORB_TRY(problem_reset(pb));
-  LORB_TRY(problem_solve(pb, opt, 0, summaries));
-  return lorb_ba_problem_download(pb, cams, pts);
+  // windows [lo, hi) through the reusable problem of context `cc`: stage + upload, solve, download
+  auto run_range = [&](lorb_ctx* cc, int lo, int hi) -> int {
+    lorb_ba_problem* pb = cached_problem(cc);
+    if (!pb) return LORB_ERR_NOMEM;
+    std::vector<WindowSpec> sub(ws.begin() + lo, ws.begin() + hi);
+    LORB_TRY(problem_build(pb, cc, sub, K));
+    LORB_TRY(problem_reset(pb));
+    LORB_TRY(problem_solve(pb, opt, 0, summaries ? summaries + lo : nullptr));
+    return lorb_ba_problem_download(pb, cams + 6 * (size_t)cam_off[lo], pts ? pts + 3 * (size_t)pt_off[lo] : nullptr);
+  };
+  static const bool pipeline = [] {
+    const char* e = getenv("LORB_BA_PIPELINE");
+    return !(e && atoi(e) == 0);
+  }();
+  if (!pipeline || n_windows < 64) return run_range(c, 0, n_windows);
+  // A large batch is cut into chunks that two host threads (this one and a helper with its own
+  // context on the same device) take alternately: while one chunk is being solved on the GPU the
+  // next one is staged into pinned memory and uploaded, so the host-side staging -- most of what
+  // the host-buffer call costs beyond the resident solve -- hides under the solves.
+  if (!c->aux) LORB_TRY(lorb_ctx_create(c->device, &c->aux));
+  lorb_ctx* c2 = c->aux;
+  const int n_chunks = n_windows >= 256 ? 8 : 4;
+  const long long l2 = c2->launches;
+  int rc2 = LORB_OK;
+  std::string err2;
+  auto chunk_lo = [&](int ch) { return (int)((long long)n_windows * ch / n_chunks); };
+  const int host_threads = omp_get_max_threads();  // the helper inherits this thread's team size
+  std::thread helper([&] {
+    cudaSetDevice(c2->device);
+    omp_set_num_threads(host_threads);
+    for (int ch = 1; ch < n_chunks && rc2 == LORB_OK; ch += 2) rc2 = run_range(c2, chunk_lo(ch), chunk_lo(ch + 1));
+    if (rc2 != LORB_OK) err2 = lorb_last_error();
+  });
+  int rc1 = LORB_OK;
+  for (int ch = 0; ch < n_chunks && rc1 == LORB_OK; ch += 2) rc1 = run_range(c, chunk_lo(ch), chunk_lo(ch + 1));
+  helper.join();
+  c->launches += c2->launches - l2;
+  if (rc1 != LORB_OK) return rc1;
+  if (rc2 != LORB_OK) {
+    set_error("%s", err2.c_str());
+    return rc2;
+  }
+  return LORB_OK;
+}
+
+/* Team size of the host-side staging loops (OpenMP) of the calling thread.  A launcher such as
+ * torchrun exports OMP_NUM_THREADS=1 to every rank; a host that knows how many ranks share the
+ * box gives each its share of the cores here. */
+int lorb_set_host_threads(int n) {
+  LORB_REQUIRE(n >= 1, "n");
+  omp_set_num_threads(n);
+  return LORB_OK;
 }
 
 }  // extern "C"

@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIBDIR = os.path.join(HERE, "..", "lib")
 OUT = os.path.join(LIBDIR, "libhost_dropin.so")
 SRCS = [os.path.join(HERE, "src", "matcher.cpp"), os.path.join(HERE, "src", "bundle_adjust.cpp"),
-        os.path.join(HERE, "src", "ORBextractor.cpp"),
+        os.path.join(HERE, "src", "ORBextractor.cpp"), os.path.join(HERE, "src", "local_map_index.cpp"),
         os.path.join(HERE, "test", "harness.cpp")]
 
 

@@ -11,6 +11,10 @@
 #include "../src/lorb_host.h"
 #include "../include/bundle_adjust.h"
 #include "../include/matcher.h"
+#include "../include/local_map_index.h"
+
+#include <algorithm>
+#include <chrono>
 
 using namespace Simple_ORB_SLAM;
 
@@ -239,6 +243,126 @@ void harness_local_ba(int C, float* cams, int P, float* pts, int O, const int* o
 	}
 }
 
+
+// The mapper's hand-off: keyframes are inserted one by one, as
+// LocalMapping::ProcessNewFrames would (reference src/local_mapping.cpp:48-78), and after every
+// insert from keyframe `first_ba` on the local BA of the new keyframe runs (the call the reference
+// has at src/local_mapping.cpp:32).  Two identical worlds are driven side by side:
+//   A: lorb_host::LocalMapIndex::InsertKeyFrame + Optimize (index maintained per insert)
+//   B: MapPoint::AddObservation per slot + BA::LocalPoseOptimization (re-walks the std::maps)
+// Keyframe k holds the slots [kf_off[k], kf_off[k+1]) = (point, u, v); its covisible list is
+// cov_idx[cov_off[k] .. cov_off[k+1]) (earlier keyframes).  Outputs: final float poses / points of
+// both worlds, the number of BA calls, and the host microseconds spent assembling in each world
+// (B: a dry run of the reference's own walks, :207-303).
+int harness_local_mapping(int n_kf, const float* kf_rt, const int* kf_off, const int* slot_pt,
+                          const float* slot_uv, const int* cov_off, const int* cov_idx, int P,
+                          const float* pts, const float* K4, int first_ba, float* out_cams_a,
+                          float* out_pts_a, float* out_cams_b, float* out_pts_b, double* us_assemble)
+{
+	Camera cam;
+	cam.fx = K4[0]; cam.fy = K4[1]; cam.cx = K4[2]; cam.cy = K4[3];
+	struct World
+	{
+		std::vector<Frame> frames;
+		std::vector<MapPoint> mps;
+	};
+	World W[2];
+	for(int w=0; w<2; w++)
+	{
+		W[w].frames.resize(n_kf);
+		W[w].mps.resize(P);
+		for(int p=0;p<P;p++) W[w].mps[p].mWorldPos = cv::Point3f(pts[3*p], pts[3*p+1], pts[3*p+2]);
+	}
+	lorb_host::LocalMapIndex index;
+	lorb_host::LocalBAWindow probe;
+	int n_ba = 0;
+	us_assemble[0] = us_assemble[1] = 0;
+	for(int k=0; k<n_kf; k++)
+	{
+		for(int w=0; w<2; w++)
+		{
+			Frame& F = W[w].frames[k];
+			F.mpCamera = &cam;
+			cv::Mat R(3,1,CV_32F), T(3,1,CV_32F);
+			for(int a=0;a<3;a++) { R.at<float>(a) = kf_rt[6*k+a]; T.at<float>(a) = kf_rt[6*k+3+a]; }
+			F.SetPose(T, R);
+			for(int s=kf_off[k]; s<kf_off[k+1]; s++)
+			{
+				cv::KeyPoint kp;
+				kp.pt = cv::Point2f(slot_uv[2*s], slot_uv[2*s+1]);
+				F.mvKeysUn.push_back(kp);
+				F.mvpMapPoints.push_back(slot_pt[s] >= 0 ? &W[w].mps[slot_pt[s]] : static_cast<MapPoint*>(NULL));
+			}
+			F.mnMapPoints = F.mvKeysUn.size();
+			for(int c=cov_off[k]; c<cov_off[k+1]; c++) F.mvpOrderedKeyFrames.push_back(&W[w].frames[cov_idx[c]]);
+		}
+		// world A: through the index
+		index.InsertKeyFrame(&W[0].frames[k]);
+		// world B: the reference's step 1 by hand
+		for(size_t i=0; i<W[1].frames[k].mvpMapPoints.size(); i++)
+		{
+			MapPoint* pMP = W[1].frames[k].mvpMapPoints[i];
+			if(pMP != NULL && !pMP->IsBad() && !pMP->mObservations.count(&W[1].frames[k]))
+				pMP->AddObservation(&W[1].frames[k], i);
+		}
+		if(k < first_ba)
+			continue;
+		{
+			const auto t0 = std::chrono::steady_clock::now();
+			index.Assemble(&W[0].frames[k], probe);
+			const auto t1 = std::chrono::steady_clock::now();
+			us_assemble[0] += std::chrono::duration<double, std::micro>(t1 - t0).count();
+			// dry run of the reference's walks (window, dedup by std::find, one std::map copy per point)
+			Frame* pCurr = &W[1].frames[k];
+			std::vector<Frame*> local;
+			local.push_back(pCurr);
+			std::vector<Frame*> cov = pCurr->GetCovisibleFrames();
+			for(size_t i=0;i<cov.size();i++) if(!cov[i]->IsBad()) local.push_back(cov[i]);
+			std::vector<MapPoint*> lmp;
+			for(size_t i=0;i<local.size();i++)
+			{
+				std::vector<MapPoint*> v = local[i]->GetMapPoints();
+				for(size_t j=0;j<v.size();j++)
+				{
+					if(v[j] == NULL || v[j]->IsBad()) continue;
+					if(std::find(lmp.begin(), lmp.end(), v[j]) != lmp.end()) continue;
+					lmp.push_back(v[j]);
+				}
+			}
+			size_t n_res = 0;
+			for(size_t i=0;i<lmp.size();i++)
+			{
+				std::map<Frame*, size_t> obs = lmp[i]->GetObservations();
+				for(std::map<Frame*, size_t>::const_iterator it = obs.begin(); it != obs.end(); it++)
+					if(!it->first->IsBad())
+						n_res += std::find(local.begin(), local.end(), it->first) != local.end() ? 2 : 1;
+			}
+			const auto t2 = std::chrono::steady_clock::now();
+			us_assemble[1] += std::chrono::duration<double, std::micro>(t2 - t1).count();
+			if(n_res == 0) return -1;
+		}
+		index.Optimize(&W[0].frames[k]);
+		BA::LocalPoseOptimization(&W[1].frames[k]);
+		n_ba++;
+	}
+	for(int w=0; w<2; w++)
+	{
+		float* oc = w == 0 ? out_cams_a : out_cams_b;
+		float* op = w == 0 ? out_pts_a : out_pts_b;
+		for(int k=0;k<n_kf;k++)
+			for(int a=0;a<3;a++)
+			{
+				oc[6*k+a] = W[w].frames[k].mRvec.at<float>(a);
+				oc[6*k+3+a] = W[w].frames[k].mTvec.at<float>(a);
+			}
+		for(int p=0;p<P;p++)
+		{
+			const cv::Point3f q = W[w].mps[p].GetPos();
+			op[3*p] = q.x; op[3*p+1] = q.y; op[3*p+2] = q.z;
+		}
+	}
+	return n_ba;
+}
 
 // ORBextractor(nfeatures, 1.2, 8, 20, 7)(image, Mat(), keypoints, descriptors) as Frame's
 // constructor calls it (reference src/frame.cpp:34-56, 132-133); returns the keypoint count.

@@ -12,16 +12,22 @@ shard: `--gpus N` runs replicas.
 import numpy as np
 
 
+def sweep_tiles(rank, world, n_kf, block_kf):
+    """(block row, block column) tiles of the keyframe grid owned by `rank` (lorb_sweep_rank_tiles)."""
+    from . import capi
+    return capi.sweep_rank_tiles(n_kf, block_kf, rank, world)
+
+
 def sweep_blocks(rank, world, n_blocks):
     """Blocks of the keyframe bank owned by `rank`."""
     return list(range(rank, n_blocks, world))
 
 
 def window_slice(rank, world, n_windows):
-    """Contiguous [lo, hi) slice of the independent windows owned by `rank`."""
-    base, rem = divmod(n_windows, world)
-    lo = rank * base + min(rank, rem)
-    return lo, lo + base + (1 if rank < rem else 0)
+    """Contiguous [lo, hi) slice of the independent windows owned by `rank` (the C ABI's
+    lorb_shard_range, so that Python and C++ hosts split identically)."""
+    from . import capi
+    return capi.shard_range(n_windows, rank, world)
 
 
 def shard_ba_by_point(pb, rank, world):

@@ -31,9 +31,12 @@ def main():
     for case, kw in (("blocked", dict(C=24, P=3000, obs_per_point=(5, 6, 7), traj_len=8.0)),
                      ("small", dict(C=8, P=1500, obs_per_point=(4, 5)))):
         pb = synth.make_ba_problem(31, **kw)
-        sh = sharding.shard_ba_by_point(pb, rank, world)
         opt = capi.ba_options(max_num_iterations=8)
-        prob = ctx.ba_problem(sh)
+        if case == "blocked":  # the C ABI's own sharding entry point
+            prob = ctx.ba_problem_sharded(pb, rank, world)
+            assert prob.point_range == sharding.window_slice(rank, world, len(pb["pts"]))
+        else:                  # the Python restatement of the same split
+            prob = ctx.ba_problem(sharding.shard_ba_by_point(pb, rank, world))
         s = prob.solve(opt, sharded=True)
         cams, pts = prob.download()
         prob.close()

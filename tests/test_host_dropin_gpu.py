@@ -100,6 +100,72 @@ def test_local_pose_optimization(H):
     np.testing.assert_allclose(pts, op.astype(np.float32), rtol=3e-6, atol=1e-6)
 
 
+def test_local_mapping_index_sequence(H):
+    """keyframes inserted one by one, the local BA of every new keyframe taken from
+    the index the mapper maintains per insert (lorb_host::LocalMapIndex) -- against the same sequence
+    through BA::LocalPoseOptimization's own std::map walks (bit for bit: the same flat problem must
+    reach lorb_ba_local) and against an oracle replay of the whole sequence (reference
+    src/local_mapping.cpp:19-78 driving src/bundle_adjust.cpp:207-330)."""
+    n_kf, P, first_ba, n_cov = 7, 500, 2, 3
+    pb = synth.make_ba_problem(9, C=n_kf, P=P, obs_per_point=(3, 4, 5))
+    rng = np.random.default_rng(9)
+    kf_rt = pb["cams"].astype(np.float32)
+    pts = pb["pts"].astype(np.float32)
+    slots = [[] for _ in range(n_kf)]
+    for c, p, uv in zip(pb["obs_cam"], pb["obs_pt"], pb["obs_uv"]):
+        slots[c].append((int(p), uv))
+    for k in range(n_kf):  # a few NULL slots (keypoints without a map point), shuffled slot order
+        slots[k] += [(-1, np.zeros(2, np.float32))] * 5
+        rng.shuffle(slots[k])
+    kf_off = np.cumsum([0] + [len(x) for x in slots]).astype(np.int32)
+    slot_pt = np.array([p for x in slots for p, _ in x], np.int32)
+    slot_uv = np.array([uv for x in slots for _, uv in x], np.float32)
+    cov = [[j for j in range(k - 1, max(-1, k - 1 - n_cov), -1)] for k in range(n_kf)]
+    cov_off = np.cumsum([0] + [len(x) for x in cov]).astype(np.int32)
+    cov_idx = np.array([j for x in cov for j in x] + [0], np.int32)
+    ca, cb = np.zeros((n_kf, 6), np.float32), np.zeros((n_kf, 6), np.float32)
+    pa_, pb_ = np.zeros((P, 3), np.float32), np.zeros((P, 3), np.float32)
+    us = np.zeros(2)
+    n_ba = H.harness_local_mapping(n_kf, _p(kf_rt), _p(kf_off), _p(slot_pt), _p(slot_uv), _p(cov_off),
+                                   _p(cov_idx), P, _p(pts), _p(pb["K"]), first_ba, _p(ca), _p(pa_),
+                                   _p(cb), _p(pb_), _p(us))
+    assert n_ba == n_kf - first_ba
+    assert np.array_equal(ca, cb) and np.array_equal(pa_, pb_)
+    print("assemble us per BA: index %.0f, std::map walks %.0f" % (us[0] / n_ba, us[1] / n_ba))
+    # oracle replay: same inserts, same windows, float write-back after every BA
+    cams_o, pts_o = kf_rt.copy(), pts.copy()
+    for k in range(first_ba, n_kf):
+        window = [k] + cov[k]
+        widx = {f: i for i, f in enumerate(window)}
+        order, seen = [], set()
+        for f in window:
+            for p, _ in slots[f]:
+                if p >= 0 and p not in seen:
+                    seen.add(p)
+                    order.append(p)
+        pidx = {p: i for i, p in enumerate(order)}
+        oc, op, ouv, fp, fuv, frt = [], [], [], [], [], []
+        for p in order:
+            for f in range(k + 1):  # observers inserted so far, in frame (= address) order
+                for q, uv in slots[f]:
+                    if q != p:
+                        continue
+                    if f in widx:
+                        oc.append(widx[f]); op.append(pidx[p]); ouv.append(uv)
+                    else:
+                        fp.append(pidx[p]); fuv.append(uv); frt.append(cams_o[f])
+        prob = dict(cams=cams_o[window].astype(np.float64), pts=pts_o[order].astype(np.float64),
+                    obs_cam=np.array(oc, np.int32), obs_pt=np.array(op, np.int32),
+                    obs_uv=np.array(ouv, np.float32).reshape(-1, 2), fix_pt=np.array(fp, np.int32),
+                    fix_uv=np.array(fuv, np.float32).reshape(-1, 2),
+                    fix_rt=np.array(frt, np.float32).reshape(-1, 6), K=pb["K"])
+        c2, p2, _ = ref.ba_local(prob)
+        cams_o[window] = c2.astype(np.float32)
+        pts_o[order] = p2.astype(np.float32)
+    np.testing.assert_allclose(ca, cams_o, rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(pa_, pts_o, rtol=2e-5, atol=2e-6)
+
+
 def test_orbextractor_class_matches_reference():
     """The drop-in ORBextractor class (host/include/ORBextractor.h) called as Frame's constructor
     calls it, against the compiled reference's extractor output (tests/golden/orb_golden.npz)."""

@@ -166,6 +166,22 @@ def test_sweep_many_pairs_resident(ctx, sweep_impl):
     assert np.array_equal(k3, o3[0]) and np.array_equal(m3, o3[1]) and np.array_equal(d3, o3[2])
 
 
+@pytest.mark.parametrize("n_kf,blk,n_desc", [(11, 4, 300), (9, 4, 130), (8, 8, 64)])
+def test_sweep_all_tile_grid(ctx, sweep_impl, n_kf, blk, n_desc):
+    """The whole sweep as a tile grid split over ranks: the union of the ranks'
+    results is the oracle's count for every unordered pair, ragged last block included."""
+    bank = synth.kf_bank(n_kf, n_desc, seed=n_kf)
+    ctx.bank_upload(bank)
+    pa, pb = synth.all_pairs(n_kf)
+    want = ref.sweep(bank, pa, pb)[0]
+    one, done = ctx.match_sweep_all(n_kf, blk)
+    assert done == len(pa) and np.array_equal(one, want)
+    world = 3
+    parts = [ctx.match_sweep_all(n_kf, blk, r, world) for r in range(world)]
+    assert sum(d for _, d in parts) == len(pa)
+    assert np.array_equal(sum(k for k, _ in parts), want)
+
+
 def test_compute_descriptors(ctx):
     """SURVEY 8(f) rank 4: MapPoint::ComputeDescriptor batched, bit-exact vs the oracle."""
     rng = np.random.default_rng(17)

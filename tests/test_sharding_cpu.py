@@ -10,7 +10,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from lorb_slam_b200 import sharding, synth
+from lorb_slam_b200 import capi, sharding, synth
 from oracle import ref
 
 
@@ -32,6 +32,17 @@ def _worker(rank, world, port, out):
         owned[sharding.sweep_blocks(rank, world, 32)] = 1
         dist.all_reduce(owned)
         assert bool((owned == 1).all())
+        # tiles of the keyframe grid (C-ABI helper, host logic only): every unordered pair of a
+        # ragged bank is in exactly one tile of exactly one rank
+        n_kf, blk = 37, 8
+        cover = torch.zeros(n_kf * (n_kf - 1) // 2, dtype=torch.int64)
+        for bi, bj in capi.sweep_rank_tiles(n_kf, blk, rank, world):
+            for a in range(bi * blk, min(n_kf, (bi + 1) * blk)):
+                for b in range(bj * blk, min(n_kf, (bj + 1) * blk)):
+                    if bi != bj or a < b:
+                        cover[capi.sweep_pair_index(n_kf, a, b)] += 1
+        dist.all_reduce(cover)
+        assert bool((cover == 1).all())
         # windows: contiguous disjoint cover, sizes differ by at most one
         lo, hi = sharding.window_slice(rank, world, 513)
         cnt = torch.tensor([hi - lo], dtype=torch.int64)
@@ -59,6 +70,14 @@ def test_sharding_world2_gloo():
     out = mgr.dict()
     mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
     assert sorted(out.keys()) == [0, 1]
+
+
+def test_sweep_tile_grid():
+    assert capi.sweep_rank_tiles(10, 4, 0, 1) == [(0, 0), (0, 1), (0, 2), (1, 1), (1, 2), (2, 2)]
+    # a last block of one keyframe has no diagonal tile
+    assert (2, 2) not in capi.sweep_rank_tiles(9, 4, 0, 1)
+    idx = sorted(capi.sweep_pair_index(6, a, b) for a in range(6) for b in range(a + 1, 6))
+    assert idx == list(range(15)) and capi.sweep_pair_index(6, 4, 1) == capi.sweep_pair_index(6, 1, 4)
 
 
 def test_window_slice_edges():
