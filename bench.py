@@ -674,12 +674,19 @@ def run_ba_batched(args, rank, world, local, steps=None, want_cpu=True):
     total_obs = _sum_over_ranks(float(obs), world, local)
     value = steps * total_obs * iters / dt_max
     # ---- e2e: the host-buffer call (upload of every window, solve, download) per step
-    ctx.ba_local_batched(bt, opt)
+    # (the call updates the caller's parameter arrays in place, as BA::LocalPoseOptimization's do;
+    # restoring the initial values between steps is staging of the next step's input: untimed)
+    io = dict(bt, cams=bt["cams"].copy(), pts=bt["pts"].copy())
+    ctx.ba_local_batched(io, opt, inplace=True)
     _barrier(world)
-    t0 = time.perf_counter()
+    e2e_dt = 0.0
     for _ in range(steps):
-        e_cams, e_pts, _ = ctx.ba_local_batched(bt, opt)
-    e2e_dt = _max_over_ranks(time.perf_counter() - t0, world, local)
+        io["cams"][...] = bt["cams"]
+        io["pts"][...] = bt["pts"]
+        t0 = time.perf_counter()
+        e_cams, e_pts, _ = ctx.ba_local_batched(io, opt, inplace=True)
+        e2e_dt += time.perf_counter() - t0
+    e2e_dt = _max_over_ranks(e2e_dt, world, local)
     e2e_value = steps * total_obs * iters / e2e_dt
     # the two paths sum their partial results with atomics (no fixed order): compare by tolerance
     same = bool(max(_rel_err(e_cams, cams_res), _rel_err(e_pts, pts_res)) <= 1.0)
@@ -802,21 +809,16 @@ def run_ba_large(args, rank, world, local, steps=None, want_cpu=True):
                       "cameras_bit_identical_across_ranks": bool(same_cams.item() == 1.0),
                       "checked": "%d-rank sharded solve against the one-GPU solve of the whole problem on rank 0, "
                                  "final cost %.9g vs %.9g" % (world, s["final_cost"], s1["final_cost"])}
-    # ---- e2e: the host-buffer call every step.  One GPU: lorb_ba_local (the ctx keeps its grow-only
-    # buffers); sharded: create (upload + device work lists) + solve + download of this rank's shard.
+    # ---- e2e: the host-buffer call every step (upload, device work lists, solve, download): lorb_ba_local
+    # on one GPU, lorb_ba_local_shard (this rank's shard, collective) on several.
     _barrier(world)
     n_e2e = max(1, steps // 2)
-    if world == 1:
-        ctx.ba_local(sh, opt)  # first call sizes the buffers
+    e2e_call = ctx.ba_local if world == 1 else ctx.ba_local_shard
+    e2e_call(sh, opt)  # first call sizes the grow-only buffers of the ctx
+    _barrier(world)
     t0 = time.perf_counter()
     for _ in range(n_e2e):
-        if world == 1:
-            ctx.ba_local(sh, opt)
-        else:
-            p2 = ctx.ba_problem(sh)
-            p2.solve(opt, sharded=True)
-            p2.download()
-            p2.close()
+        e2e_call(sh, opt)
     e2e = _max_over_ranks((time.perf_counter() - t0) / n_e2e, world, local)
     O = pb["O"]
     value = steps * O * s["iterations"] / dt_max

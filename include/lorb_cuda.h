@@ -514,15 +514,23 @@ int lorb_ba_local(lorb_ctx* ctx, int C, double* cams, int P, double* pts, int O,
                   const lorb_ba_options* opt, lorb_ba_summary* summary);
 
 /*
+ * lorb_ba_local for one rank of a point-sharded problem (BASELINE config 5 on several GPUs): the
+ * arrays hold THIS RANK'S points with all their observations (lorb_shard_range / the natural layout
+ * of a distributed map) and every camera; a collective call over the communicator of lorb_dist_init.
+ * On return cams holds all C cameras (identical on every rank), pts this rank's points.
+ */
+int lorb_ba_local_shard(lorb_ctx* ctx, int C, double* cams, int P, double* pts, int O, const int* obs_cam,
+                        const int* obs_pt, const float* obs_uv, int F, const int* fix_pt,
+                        const float* fix_uv, const float* fix_rt, const float* K,
+                        const lorb_ba_options* opt, lorb_ba_summary* summary);
+
+/*
  * Batched independent windows (BASELINE config 4).  Window w owns
  *   cams[cam_off[w] .. cam_off[w+1]), pts[pt_off[w] .. pt_off[w+1]),
  *   obs[obs_off[w] .. obs_off[w+1])  with obs_cam / obs_pt LOCAL to the window,
  *   fixed observations [fix_off[w] .. fix_off[w+1]) likewise (fix_off may be
  *   NULL when there are none).
  * Every window runs its own LM loop (own trust region, own termination).
- * Batches of 64 windows and more are cut into chunks that two host threads take alternately (the
- * second with an internal context on the same device), so that staging / upload of one chunk
- * overlaps the solve of another (LORB_BA_PIPELINE=0 turns that off).
  */
 int lorb_ba_local_batched(lorb_ctx* ctx, int n_windows, const int* cam_off, double* cams,
                           const int* pt_off, double* pts, const int* obs_off, const int* obs_cam,

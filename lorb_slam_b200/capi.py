@@ -29,7 +29,7 @@ EXPORTS = [
     "lorb_sweep_pair_index", "lorb_match_sweep_all", "lorb_search_proj_points", "lorb_search_proj_frame", "lorb_frustum_project", "lorb_compute_descriptors",
     "lorb_stereo_matches", "lorb_orb_describe", "lorb_orb_umax", "lorb_orb_selftest",
     "lorb_orb_extract", "lorb_orb_level_sizes", "lorb_orb_stages", "lorb_stereo_frame", "lorb_orb_distribute", "lorb_orb_max_keypoints",
-    "lorb_ba_default_options", "lorb_ba_pose_only", "lorb_ba_local", "lorb_ba_local_batched",
+    "lorb_ba_default_options", "lorb_ba_pose_only", "lorb_ba_local", "lorb_ba_local_batched", "lorb_ba_local_shard",
     "lorb_ba_problem_create", "lorb_ba_problem_create_batched", "lorb_ba_problem_create_sharded", "lorb_shard_range", "lorb_set_host_threads", "lorb_ba_problem_reset", "lorb_ba_problem_solve",
     "lorb_ba_problem_download", "lorb_ba_problem_destroy", "lorb_dist_get_unique_id",
     "lorb_dist_init", "lorb_dist_finalize", "lorb_dist_allreduce_f64", "lorb_microbench_popc",
@@ -510,7 +510,11 @@ class Context:
                                            C.byref(opt), C.byref(s)))
         return rt, s.as_dict()
 
-    def ba_local(self, pb, opt=None):
+    def ba_local_shard(self, pb, opt=None):
+        """lorb_ba_local_shard: `pb` is this rank's shard; collective over the ctx communicator."""
+        return self.ba_local(pb, opt, _entry="lorb_ba_local_shard")
+
+    def ba_local(self, pb, opt=None, _entry="lorb_ba_local"):
         cams = _arr(pb["cams"], np.float64).copy()
         pts = _arr(pb["pts"], np.float64).copy()
         oc, op = _arr(pb["obs_cam"], np.int32), _arr(pb["obs_pt"], np.int32)
@@ -521,14 +525,21 @@ class Context:
         K = _arr(pb["K"], np.float32).reshape(4)
         opt = opt or ba_options()
         s = BASummary()
-        _check(self._lib.lorb_ba_local(self._h, len(cams), _ptr(cams), len(pts), _ptr(pts), len(oc),
+        _check(getattr(self._lib, _entry)(self._h, len(cams), _ptr(cams), len(pts), _ptr(pts), len(oc),
                                        _ptr(oc), _ptr(op), _ptr(ouv), len(fp), _ptr(fp), _ptr(fuv),
                                        _ptr(frt), _ptr(K), C.byref(opt), C.byref(s)))
         return cams, pts, s.as_dict()
 
-    def ba_local_batched(self, bt, opt=None):
-        cams = _arr(bt["cams"], np.float64).copy()
-        pts = _arr(bt["pts"], np.float64).copy()
+    def ba_local_batched(self, bt, opt=None, inplace=False):
+        """inplace: bt["cams"] / bt["pts"] (contiguous float64) are updated where they lie, as a C++
+        caller's arrays would be; otherwise they are copied first."""
+        if inplace:
+            cams, pts = bt["cams"], bt["pts"]
+            assert cams.dtype == np.float64 and pts.dtype == np.float64
+            assert cams.flags.c_contiguous and pts.flags.c_contiguous
+        else:
+            cams = _arr(bt["cams"], np.float64).copy()
+            pts = _arr(bt["pts"], np.float64).copy()
         co, po, oo = (_arr(bt[k], np.int32) for k in ("cam_off", "pt_off", "obs_off"))
         oc, op = _arr(bt["obs_cam"], np.int32), _arr(bt["obs_pt"], np.int32)
         ouv = _arr(bt["obs_uv"], np.float32)

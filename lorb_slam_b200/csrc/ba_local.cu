@@ -25,8 +25,6 @@
 #include <algorithm>
 #include <chrono>
 #include <new>
-#include <string>
-#include <thread>
 #include <vector>
 
 #include <cub/cub.cuh>
@@ -51,8 +49,12 @@ struct BADev {
   Intr K;
   double* scale_c;       // 6C
   double* scale_p;       // 3P
-  double* lin;           // [S n*n | Hcc 21C | gc 6C | rhs_corr 6C | tail 4]
-  double* S;
+  double* lin;           // [S n*n (or Sp, packed) | Hcc 21C | gc 6C | rhs_corr 6C | tail 8 | gslot 16]
+  double* S;             // dense n x n reduced camera system (what the Cholesky factorises)
+  double* Sp;            // large path: packed upper block triangle the Schur products accumulate into
+                         // (block row ci: 6 rows of 6 (C - ci) doubles); nullptr = S lives in lin
+  double* gslot;         // [16] per-rank gradient maxima of a sharded solve (one sum all-reduce gathers them)
+  int rank, world;       // of the sharded solve (0, 1 otherwise)
   double* Hcc;
   double* gc;
   double* rhs_corr;
@@ -73,6 +75,27 @@ struct BADev {
 
 __device__ __forceinline__ int upper_idx(int a, int b) {  // a <= b, 6x6
   return a * 6 - (a * (a - 1)) / 2 + (b - a);
+}
+
+// Packed upper block triangle of the reduced camera system: element (a, b) of block (ci, cj), ci <= cj.
+__device__ __forceinline__ size_t packed_idx(int C, int ci, int a, int cj, int b) {
+  const size_t base = 36 * ((size_t)ci * C - (size_t)ci * (ci - 1) / 2);
+  return base + (size_t)a * (6 * (C - ci)) + 6 * (cj - ci) + b;
+}
+
+// Largest |gradient| entry of the point side: this rank's own maximum, or, in a sharded solve,
+// the maximum over the per-rank slots that the sum all-reduce of `lin` has gathered.
+__device__ __forceinline__ double point_gmax(const BADev& p, const LMState* st) {
+  double g = st->acc_gmax;
+  if (p.world > 1)
+    for (int r = 0; r < p.world && r < 16; r++) g = fmax(g, p.gslot[r]);
+  return g;
+}
+
+// Sharded solve: publish this rank's maximum in its slot before the all-reduce.
+__global__ void ba_gslot_kernel(const BADev* __restrict__ probs) {
+  const BADev p = probs[0];
+  if (p.world > 1 && p.rank < 16) p.gslot[p.rank] = p.st->acc_gmax;
 }
 
 __global__ void ba_camrot_kernel(const BADev* __restrict__ probs, int which /*0 = current, 1 = candidate*/, int force) {
@@ -869,11 +892,13 @@ __global__ void __launch_bounds__(256)
     acc[a] = v;
   }
   if (lane == 0) {
-    double* Sblk = p.S + (size_t)(6 * it.x) * p.n + 6 * it.y;
+    // block (ci, cj), ci <= cj, of the packed upper block triangle (or of the dense matrix)
+    double* Sblk = p.Sp ? p.Sp + packed_idx(p.C, it.x, 0, it.y, 0) : p.S + (size_t)(6 * it.x) * p.n + 6 * it.y;
+    const size_t ld = p.Sp ? (size_t)6 * (p.C - it.x) : (size_t)p.n;
 #pragma unroll
     for (int a = 0; a < 6; a++)
 #pragma unroll
-      for (int b = 0; b < 6; b++) atomicAdd(&Sblk[(size_t)a * p.n + b], -acc[6 * a + b]);
+      for (int b = 0; b < 6; b++) atomicAdd(&Sblk[(size_t)a * ld + b], -acc[6 * a + b]);
   }
 }
 
@@ -897,7 +922,7 @@ __global__ void ba_init_finish_kernel(const BADev* __restrict__ probs, lorb_ba_o
     st->x_norm = sqrt(xs + p.tail[1]);
     st->cost = 0.5 * p.tail[0];
     st->initial_cost = st->cost;
-    st->gmax = fmax(gmx, st->acc_gmax);
+    st->gmax = fmax(gmx, point_gmax(p, st));
     st->radius = opt.initial_trust_region_radius;
     st->decrease_factor = 2.0;
     st->iteration = st->n_success = st->n_fail = st->invalid_run = 0;
@@ -926,7 +951,7 @@ __global__ void ba_gradcheck_kernel(const BADev* __restrict__ probs, lorb_ba_opt
   for (int i = threadIdx.x; i < p.n; i += blockDim.x) gm = fmax(gm, fabs(p.gc[i] / p.scale_c[i]));
   const double gmx = block_max(gm, red);
   if (threadIdx.x == 0 && st->check_gradient) {
-    st->gmax = fmax(gmx, st->acc_gmax);
+    st->gmax = fmax(gmx, point_gmax(p, st));
     st->check_gradient = 0;
     if (st->gmax <= opt.gradient_tolerance) {
       st->termination = LORB_BA_CONV_GRADIENT;
@@ -946,7 +971,16 @@ __global__ void ba_finish_kernel(const BADev* __restrict__ probs, lorb_ba_option
        idx += (size_t)gridDim.x * blockDim.x) {
     const int i = (int)(idx / n), j = (int)(idx % n);
     const int ci = i / 6, cj = j / 6;
-    if (ci == cj) {
+    if (p.Sp) {  // unpack (and mirror) the packed upper block triangle into the dense matrix
+      const int a = i % 6, b = j % 6;
+      double v = ci <= cj ? p.Sp[packed_idx(p.C, ci, a, cj, b)] : p.Sp[packed_idx(p.C, cj, b, ci, a)];
+      if (ci == cj) {
+        double h = p.Hcc[HCC * (size_t)ci + (a <= b ? upper_idx(a, b) : upper_idx(b, a))];
+        if (a == b) h += clamp_diag(h, opt.min_lm_diagonal, opt.max_lm_diagonal) / radius;
+        v += h;
+      }
+      p.S[idx] = v;
+    } else if (ci == cj) {
       const int a = i % 6, b = j % 6;
       double v = p.Hcc[HCC * (size_t)ci + (a <= b ? upper_idx(a, b) : upper_idx(b, a))];
       if (a == b) v += clamp_diag(v, opt.min_lm_diagonal, opt.max_lm_diagonal) / radius;
@@ -1093,7 +1127,7 @@ __global__ void __launch_bounds__(256)
     s_done = 0;
     s_ok = (p.tail[2] == 0.0) ? 1 : 0;
     if (st->check_gradient) {
-      st->gmax = fmax(gmx, st->acc_gmax);
+      st->gmax = fmax(gmx, point_gmax(p, st));
       st->check_gradient = 0;
       if (st->gmax <= opt.gradient_tolerance) {
         st->termination = LORB_BA_CONV_GRADIENT;
@@ -1977,6 +2011,7 @@ struct lorb_ba_problem {
   std::vector<int> h_cam_off, h_pt_off;
   lorb::Buf params, topo, work, descs, hstate, counter, lists, stage;
   lorb::Buf list_scratch, list_scratch2;  // device scratch of the work-list builder (grow-only)
+  double *h_cams_stage = nullptr, *h_pts_stage = nullptr;  // pinned staging of the parameters (up and down)
   int max_cam_items = 0, max_pair_items = 0;
   bool has_dup = false;  // some point is observed twice by the same window camera
   double *cams0 = nullptr, *pts0 = nullptr;  // initial parameters of all windows
@@ -2264,7 +2299,7 @@ static int problem_build(lorb_ba_problem* pb, lorb_ctx* c, const std::vector<Win
   pb->h_dev.resize(nw);
   pb->h_cam_off.assign(nw + 1, 0);
   pb->h_pt_off.assign(nw + 1, 0);
-  size_t tot_obs = 0, tot_fix = 0, tot_ptr = 0, tot_lin = 0, tot_rot = 0, tot_dinv = 0;
+  size_t tot_obs = 0, tot_fix = 0, tot_ptr = 0, tot_lin = 0, tot_rot = 0, tot_dinv = 0, tot_sfull = 0;
   for (int w = 0; w < nw; w++) {
     const WindowSpec& W = ws[w];
     LORB_REQUIRE(W.C > 0 && W.P >= 0 && W.O >= 0 && W.F >= 0, "window sizes");
@@ -2273,9 +2308,14 @@ static int problem_build(lorb_ba_problem* pb, lorb_ctx* c, const std::vector<Win
     pb->maxC = std::max(pb->maxC, W.C);
     pb->maxP = std::max(pb->maxP, W.P);
     const int n = 6 * W.C;
-    const size_t lin = (size_t)n * n + (size_t)HCC * W.C + 12 * (size_t)W.C + 8;
+    // the large path accumulates the Schur products into the packed upper block triangle (half the
+    // memset and, sharded, half the all-reduce); its dense matrix is a separate buffer
+    const bool packed = n > 96;
+    const size_t lin = (packed ? (size_t)18 * W.C * (W.C + 1) : (size_t)n * n) + (size_t)HCC * W.C +
+                       12 * (size_t)W.C + 24;
     pb->lin_doubles_max = std::max(pb->lin_doubles_max, lin);
     tot_lin += lin;
+    if (packed) tot_sfull += (size_t)n * n;
     tot_obs += (size_t)W.O + W.F;
     tot_fix += W.F;
     tot_ptr += (size_t)W.P + 1;
@@ -2301,6 +2341,8 @@ static int problem_build(lorb_ba_problem* pb, lorb_ctx* c, const std::vector<Win
   double* h_fix = reinterpret_cast<double*>(sg + sb_ptr + sb_cam + sb_uv);
   double* h_cams = reinterpret_cast<double*>(sg + sb_ptr + sb_cam + sb_uv + sb_fix);
   double* h_pts = reinterpret_cast<double*>(sg + sb_ptr + sb_cam + sb_uv + sb_fix + sb_cams);
+  pb->h_cams_stage = h_cams;
+  pb->h_pts_stage = h_pts;
   std::vector<size_t> o_ptr(nw), o_obs(nw), o_fix(nw);
   // large-path work lists (windows with 6C > 96), concatenated over windows
   struct ListOff {
@@ -2460,8 +2502,8 @@ static int problem_build(lorb_ba_problem* pb, lorb_ctx* c, const std::vector<Win
   double* d_fix = (double*)(t + t_ptr + t_cam + t_uv);
   const size_t w_rot = al(tot_rot * 8), w_sc = cb, w_sp = pbts, w_lin = al(tot_lin * 8), w_rhs = cb,
                w_hinv = al(std::max<size_t>(totP, 1) * 48), w_gp = pbts,
-               w_st = al(sizeof(LMState) * (size_t)nw), w_dinv = al(tot_dinv * 8);
-  LORB_TRY(pb->work.reserve(2 * w_rot + w_sc + w_sp + w_lin + w_rhs + w_hinv + w_gp + w_st + w_dinv));
+               w_st = al(sizeof(LMState) * (size_t)nw), w_dinv = al(tot_dinv * 8), w_sfull = al(tot_sfull * 8);
+  LORB_TRY(pb->work.reserve(2 * w_rot + w_sc + w_sp + w_lin + w_rhs + w_hinv + w_gp + w_st + w_dinv + w_sfull));
   uint8_t* wk = pb->work.as<uint8_t>();
   double* d_rot[2] = {(double*)wk, (double*)(wk + w_rot)};
   wk += 2 * w_rot;
@@ -2472,11 +2514,12 @@ static int problem_build(lorb_ba_problem* pb, lorb_ctx* c, const std::vector<Win
   double* d_hinv = (double*)wk; wk += w_hinv;
   double* d_gp = (double*)wk;   wk += w_gp;
   pb->d_states = (LMState*)wk;  wk += w_st;
-  double* d_dinv = (double*)wk;
+  double* d_dinv = (double*)wk; wk += w_dinv;
+  double* d_sfull = (double*)wk;
   pb->lin_base = d_lin;
   pb->lin_bytes_total = tot_lin * 8;
   {
-    size_t lin_off = 0, rot_off = 0, dinv_off = 0;
+    size_t lin_off = 0, rot_off = 0, dinv_off = 0, sfull_off = 0;
     for (int w = 0; w < nw; w++) {
       const WindowSpec& W = ws[w];
       BADev& d = pb->h_dev[w];
@@ -2500,18 +2543,25 @@ static int problem_build(lorb_ba_problem* pb, lorb_ctx* c, const std::vector<Win
       d.scale_c = d_sc + co;
       d.scale_p = d_sp + po;
       d.lin = d_lin + lin_off;
-      d.S = d.lin;
-      d.Hcc = d.S + (size_t)d.n * d.n;
+      const bool packed = d.n > 96;
+      const size_t s_doubles = packed ? (size_t)18 * W.C * (W.C + 1) : (size_t)d.n * d.n;
+      d.Sp = packed ? d.lin : nullptr;
+      d.S = packed ? d_sfull + sfull_off : d.lin;
+      if (packed) sfull_off += (size_t)d.n * d.n;
+      d.Hcc = d.lin + s_doubles;
       d.gc = d.Hcc + (size_t)HCC * W.C;
       d.rhs_corr = d.gc + 6 * (size_t)W.C;
       d.tail = d.rhs_corr + 6 * (size_t)W.C;
+      d.gslot = d.tail + 8;
+      d.rank = 0;
+      d.world = 1;
       d.rhs = d_rhs + co;
       d.pt_hinv = d_hinv + 2 * po;
       d.pt_gp = d_gp + po;
       d.st = pb->d_states + w;
       d.dinv = d_dinv + dinv_off;
       dinv_off += (size_t)((d.n + NB - 1) / NB) * NB;
-      lin_off += (size_t)d.n * d.n + (size_t)HCC * W.C + 12 * (size_t)W.C + 8;
+      lin_off += s_doubles + (size_t)HCC * W.C + 12 * (size_t)W.C + 24;
       rot_off += (size_t)W.C * CAMROT;
     }
   }
@@ -2677,6 +2727,18 @@ static int problem_solve(lorb_ba_problem* pb, const lorb_ba_options* optp, int s
   const int nw = pb->nw;
   lorb_ba_options opt = *optp;
   LORB_REQUIRE(!sharded || (dist_ready(c) && nw == 1), "sharded solve needs lorb_dist_init and one window");
+
+  {
+    // the descriptor carries rank / world of a sharded solve (per-rank gradient slots)
+    BADev& h0 = pb->h_dev[0];
+    const int w_ = sharded ? dist_world(c) : 1, r_ = sharded ? dist_rank(c) : 0;
+    LORB_REQUIRE(w_ <= 16, "sharded solve supports up to 16 ranks");
+    if (h0.world != w_ || h0.rank != r_) {
+      h0.world = w_;
+      h0.rank = r_;
+      LORB_CUDA_TRY(cudaMemcpyAsync(pb->descs.p, &h0, sizeof(BADev), cudaMemcpyHostToDevice, c->stream));
+    }
+  }
   const int gx_pts = std::max(1, std::min((pb->maxP + 31) / 32, std::max(1, c->sm_count * 8 / nw)));
   const dim3 grid_pts(gx_pts, nw);
   const int ppc = DP_THREADS / 8;  // points per CTA round of the dense path
@@ -2747,9 +2809,9 @@ static int problem_solve(lorb_ba_problem* pb, const lorb_ba_options* optp, int s
   LORB_LAUNCH(c, fill_ones_kernel, 512, 256, 0, d0.scale_p, pb->pt_doubles);
   LORB_LAUNCH(c, ba_camrot_kernel, grid_cam, 128, 0, dp, 0, 1);
   LORB_TRY(launch_build(false, 1));
-  if (sharded) {
-    LORB_TRY(dist_allreduce_sum(c, d0.Hcc, (size_t)HCC * d0.C + 12 * (size_t)d0.C + 8));
-    LORB_TRY(dist_allreduce_max_u64(c, &d0.st->acc_gmax, 1));
+  if (sharded) {  // one collective: sums and, through the per-rank slots, the gradient maximum
+    LORB_LAUNCH(c, ba_gslot_kernel, 1, 1, 0, dp);
+    LORB_TRY(dist_allreduce_sum(c, d0.Hcc, (size_t)HCC * d0.C + 12 * (size_t)d0.C + 24));
   }
   LORB_LAUNCH(c, ba_init_finish_kernel, dim3(1, nw), 1024, 0, dp, opt);
   // ---- LM attempts; the device decides, the host polls a counter every few attempts
@@ -2761,9 +2823,9 @@ static int problem_solve(lorb_ba_problem* pb, const lorb_ba_options* optp, int s
     prof_begin(c, 0);
     LORB_TRY(launch_build(true, 0));
     prof_end(c, 0);
-    if (sharded) {
+    if (sharded) {  // ONE all-reduce per build pass: packed S, H_cc, g_c, Schur rhs, scalars, gradient slots
+      LORB_LAUNCH(c, ba_gslot_kernel, 1, 1, 0, dp);
       LORB_TRY(dist_allreduce_sum(c, d0.lin, pb->lin_doubles_max));
-      LORB_TRY(dist_allreduce_max_u64(c, &d0.st->acc_gmax, 1));
     }
     prof_begin(c, 2);
     if (small) {
@@ -2803,8 +2865,8 @@ static int problem_solve(lorb_ba_problem* pb, const lorb_ba_options* optp, int s
     LORB_LAUNCH(c, ba_camrot_kernel, grid_cam, 128, 0, dp, 0, 2);
     LORB_TRY(launch_build(false, 2));
     if (sharded) {
-      LORB_TRY(dist_allreduce_sum(c, d0.Hcc, (size_t)HCC * d0.C + 12 * (size_t)d0.C + 8));
-      LORB_TRY(dist_allreduce_max_u64(c, &d0.st->acc_gmax, 1));
+      LORB_LAUNCH(c, ba_gslot_kernel, 1, 1, 0, dp);
+      LORB_TRY(dist_allreduce_sum(c, d0.Hcc, (size_t)HCC * d0.C + 12 * (size_t)d0.C + 24));
     }
     LORB_LAUNCH(c, ba_gradcheck_kernel, dim3(1, nw), 256, 0, dp, opt, 2);
     LORB_CUDA_TRY(cudaMemcpyAsync(hs, pb->d_states, sizeof(LMState) * (size_t)nw, cudaMemcpyDeviceToHost, s));
@@ -2956,6 +3018,24 @@ int lorb_ba_problem_download(lorb_ba_problem* pb, double* cams, double* pts) {
   lorb_ctx* c = pb->ctx;
   LORB_CUDA_TRY(cudaSetDevice(c->device));
   const BADev& d0 = pb->h_dev[0];
+  const size_t cb = pb->cam_doubles * 8, pbytes = (pts ? pb->pt_doubles : 0) * 8;
+  if (cb + pbytes >= ((size_t)4 << 20) && pb->h_cams_stage) {
+    // a large result goes through the pinned staging block (a device-to-pageable copy runs at a
+    // fraction of the link) and is handed to the caller's arrays by the host threads
+    if (cams) LORB_CUDA_TRY(cudaMemcpyAsync(pb->h_cams_stage, d0.cams[0], cb, cudaMemcpyDeviceToHost, c->stream));
+    if (pbytes) LORB_CUDA_TRY(cudaMemcpyAsync(pb->h_pts_stage, d0.pts[0], pbytes, cudaMemcpyDeviceToHost, c->stream));
+    LORB_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (cams) memcpy(cams, pb->h_cams_stage, cb);
+    if (pbytes) {
+      const int nchunk = 64;
+#pragma omp parallel for schedule(static)
+      for (int ch = 0; ch < nchunk; ch++) {
+        const size_t i0 = pbytes / 8 * ch / nchunk, i1 = pbytes / 8 * (ch + 1) / nchunk;
+        memcpy(pts + i0, pb->h_pts_stage + i0, (i1 - i0) * 8);
+      }
+    }
+    return LORB_OK;
+  }
   if (cams)
     LORB_CUDA_TRY(cudaMemcpyAsync(cams, d0.cams[0], pb->cam_doubles * 8, cudaMemcpyDeviceToHost, c->stream));
   if (pts && pb->pt_doubles)
@@ -2986,6 +3066,29 @@ int lorb_ba_local(lorb_ctx* c, int C, double* cams, int P, double* pts, int O, c
   LORB_TRY(problem_build(pb, c, ws, K));
   LORB_TRY(problem_reset(pb));
   LORB_TRY(problem_solve(pb, opt, 0, summary));
+  return lorb_ba_problem_download(pb, cams, pts);
+}
+
+// Host-buffer form of the sharded solve: the arrays are THIS RANK'S shard (points with all their
+// observations, every camera), e.g. as cut by lorb_shard_range; collective over the ctx communicator.
+int lorb_ba_local_shard(lorb_ctx* c, int C, double* cams, int P, double* pts, int O, const int* obs_cam,
+                        const int* obs_pt, const float* obs_uv, int F, const int* fix_pt,
+                        const float* fix_uv, const float* fix_rt, const float* K,
+                        const lorb_ba_options* opt, lorb_ba_summary* summary) {
+  LORB_REQUIRE(c && opt && K, "ctx / options / K");
+  LORB_REQUIRE(dist_ready(c), "lorb_dist_init was not called");
+  LORB_REQUIRE(C > 0 && P >= 0 && O >= 0 && F >= 0, "sizes");
+  LORB_REQUIRE(cams && (P == 0 || pts), "parameters");
+  LORB_REQUIRE(O == 0 || (obs_cam && obs_pt && obs_uv), "observations");
+  LORB_REQUIRE(F == 0 || (fix_pt && fix_uv && fix_rt), "fixed observations");
+  LORB_CUDA_TRY(cudaSetDevice(c->device));
+  lorb_ba_problem* pb = cached_problem(c);
+  if (!pb) return LORB_ERR_NOMEM;
+  std::vector<WindowSpec> ws(1);
+  ws[0] = WindowSpec{C, P, O, F, cams, pts, obs_cam, obs_pt, obs_uv, fix_pt, fix_uv, fix_rt};
+  LORB_TRY(problem_build(pb, c, ws, K));
+  LORB_TRY(problem_reset(pb));
+  LORB_TRY(problem_solve(pb, opt, 1, summary));
   return lorb_ba_problem_download(pb, cams, pts);
 }
 
@@ -3047,49 +3150,12 @@ int lorb_ba_local_batched(lorb_ctx* c, int n_windows, const int* cam_off, double
   std::vector<WindowSpec> ws;
   LORB_TRY(batched_specs(ws, n_windows, cam_off, cams, pt_off, pts, obs_off, obs_cam, obs_pt, obs_uv,
                          fix_off, fix_pt, fix_uv, fix_rt));
-  // windows [lo, hi) through the reusable problem of context `cc`: stage + upload, solve, download
-  auto run_range = [&](lorb_ctx* cc, int lo, int hi) -> int {
-    lorb_ba_problem* pb = cached_problem(cc);
-    if (!pb) return LORB_ERR_NOMEM;
-    std::vector<WindowSpec> sub(ws.begin() + lo, ws.begin() + hi);
-    LORB_TRY(problem_build(pb, cc, sub, K));
-    LORB_TRY(problem_reset(pb));
-    LORB_TRY(problem_solve(pb, opt, 0, summaries ? summaries + lo : nullptr));
-    return lorb_ba_problem_download(pb, cams + 6 * (size_t)cam_off[lo], pts ? pts + 3 * (size_t)pt_off[lo] : nullptr);
-  };
-  static const bool pipeline = [] {
-    const char* e = getenv("LORB_BA_PIPELINE");
-    return !(e && atoi(e) == 0);
-  }();
-  if (!pipeline || n_windows < 64) return run_range(c, 0, n_windows);
-  // A large batch is cut into chunks that two host threads (this one and a helper with its own
-  // context on the same device) take alternately: while one chunk is being solved on the GPU the
-  // next one is staged into pinned memory and uploaded, so the host-side staging -- most of what
-  // the host-buffer call costs beyond the resident solve -- hides under the solves.
-  if (!c->aux) LORB_TRY(lorb_ctx_create(c->device, &c->aux));
-  lorb_ctx* c2 = c->aux;
-  const int n_chunks = n_windows >= 256 ? 8 : 4;
-  const long long l2 = c2->launches;
-  int rc2 = LORB_OK;
-  std::string err2;
-  auto chunk_lo = [&](int ch) { return (int)((long long)n_windows * ch / n_chunks); };
-  const int host_threads = omp_get_max_threads();  // the helper inherits this thread's team size
-  std::thread helper([&] {
-    cudaSetDevice(c2->device);
-    omp_set_num_threads(host_threads);
-    for (int ch = 1; ch < n_chunks && rc2 == LORB_OK; ch += 2) rc2 = run_range(c2, chunk_lo(ch), chunk_lo(ch + 1));
-    if (rc2 != LORB_OK) err2 = lorb_last_error();
-  });
-  int rc1 = LORB_OK;
-  for (int ch = 0; ch < n_chunks && rc1 == LORB_OK; ch += 2) rc1 = run_range(c, chunk_lo(ch), chunk_lo(ch + 1));
-  helper.join();
-  c->launches += c2->launches - l2;
-  if (rc1 != LORB_OK) return rc1;
-  if (rc2 != LORB_OK) {
-    set_error("%s", err2.c_str());
-    return rc2;
-  }
-  return LORB_OK;
+  lorb_ba_problem* pb = cached_problem(c);
+  if (!pb) return LORB_ERR_NOMEM;
+  LORB_TRY(problem_build(pb, c, ws, K));
+  LORB_TRY(problem_reset(pb));
+  LORB_TRY(problem_solve(pb, opt, 0, summaries));
+  return lorb_ba_problem_download(pb, cams, pts);
 }
 
 /* Team size of the host-side staging loops (OpenMP) of the calling thread.  A launcher such as

@@ -69,7 +69,6 @@ struct lorb_ctx {
   size_t tc_keys_rows = 0;
   lorb::Dist* dist = nullptr;
   void* ba_cache = nullptr;  // reusable lorb_ba_problem of the host-buffer BA calls (ba_local.cu)
-  lorb_ctx* aux = nullptr;   // helper context of the pipelined batched BA call (second host thread)
   // cached CUDA graphs of the ORB extractor's detection chain (orb.cu), one per job slot
   void* orb_graph[2] = {nullptr, nullptr};
   cudaStream_t orb_stream2 = nullptr;  // side branch of the extractor graph (capture only)

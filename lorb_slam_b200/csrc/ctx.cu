@@ -245,7 +245,6 @@ int lorb_ctx_destroy(lorb_ctx* c) {
   if (!c) return LORB_OK;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
-  if (c->aux) lorb_ctx_destroy(c->aux);
   dist_destroy(c);
   ba_cache_free(c);
   orb_graph_free(c);

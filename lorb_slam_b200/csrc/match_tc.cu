@@ -23,7 +23,8 @@
 // (keyframe pair (a, b), slab s): 256 descriptors of `a` stay resident in shared memory as the
 // N operand (77 824 B) while the 128-row tiles of `b` stream through a 3-stage ring as the M
 // operand (38 912 B each); one tile is 9 MMAs of 128 x 256 x 32.  Per CTA: warp 0 = TMA
-// producer, warp 1 = MMA issuer (one thread), warps 4..11 = epilogue (TMEM -> registers, row
+// producer, warp 1 = MMA issuer (one thread), warps 2..3 = flusher (finished units -> global
+// memory, off the epilogue's path), warps 4..11 = epilogue (TMEM -> registers, row
 // maxima to shared memory, column maxima kept in 128 registers per thread across the tiles of
 // a unit), TMEM double-buffered (2 x 256 columns).
 #include <algorithm>
@@ -122,6 +123,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   uint64_t* res_empty = bars + 7;   // every MMA reading the slab has completed
   uint64_t* tmem_full = bars + 8;   // [2] MMA -> epilogue
   uint64_t* tmem_empty = bars + 10; // [2] epilogue -> MMA
+  uint64_t* acc_full = bars + 12;   // [2] epilogue -> flusher: the unit's row / column maxima are complete
+  uint64_t* acc_empty = bars + 14;  // [2] flusher -> epilogue: the buffer has been flushed and reset
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_TMEM);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -138,6 +141,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     for (int b = 0; b < 2; b++) {
       mbar_init(&tmem_full[b], 1);
       mbar_init(&tmem_empty[b], EPI_THREADS / 32);
+      mbar_init(&acc_full[b], EPI_THREADS / 32);
+      mbar_init(&acc_empty[b], 2);
     }
     fence_barrier_init();
   }
@@ -206,6 +211,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         }
         if (u + 1 == u1 || (nxt.z >> 8)) mma_commit(res_empty);  // last unit on this slab
       }
+    } else if (warp >= 2) {
+      // ===================== flusher (warps 2, 3): hands a finished unit's maxima to global memory
+      // while the epilogue warps are already on the next unit (the buffers alternate): this slab's
+      // 256 columns are final; rows are merged over the slabs by RED.MAX
+      const int ft = tid - 64;  // 0..63
+      for (int u = u0; u < u1; u++) {
+        const int4 un = units[u];
+        const int buf = (u - u0) & 1;
+        mbar_wait_parity(&acc_full[buf], (uint32_t)(((u - u0) >> 1) & 1));
+        int* racc = rowacc + buf * MAX_PAD;
+        int* cacc = colacc + buf * SLAB_COLS;
+        const size_t po = (size_t)un.w * n_pad;
+        for (int j = ft; j < SLAB_COLS; j += 64) {
+          colkey[po + (size_t)(un.z & 255) * SLAB_COLS + j] = cacc[j];
+          cacc[j] = INT_LOWEST;
+        }
+        for (int i = ft; i < n_mtiles * MT_ROWS; i += 64) {
+          atomicMax(&rowkey[po + i], racc[i]);
+          racc[i] = INT_LOWEST;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[buf]);
+      }
     }
   } else {
     // ===================== epilogue: 8 warps; quarter q owns TMEM lanes [32q, 32q+32),
@@ -216,10 +244,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * 128);
     uint32_t t = 0;
     for (int u = u0; u < u1; u++) {
-      const int4 un = units[u];
       const int buf = (u - u0) & 1;
       int* racc = rowacc + buf * MAX_PAD;
       int* cacc = colacc + buf * SLAB_COLS;
+      // the flusher has emptied this buffer (it was last used two units ago)
+      mbar_wait_parity(&acc_empty[buf], (uint32_t)((((u - u0) >> 1) & 1) ^ 1));
       int colmax[128];
 #pragma unroll
       for (int k = 0; k < 128; k++) colmax[k] = INT_LOWEST;
@@ -276,16 +305,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       }
 #pragma unroll
       for (int c = 0; c < 4; c++) atomicMax(&cacc[h * 128 + c * 32 + lane], keep[c]);
-      named_bar_sync(1, EPI_THREADS);
-      // flush: this slab's 256 columns are final; rows are merged over the slabs in global memory
-      const size_t po = (size_t)un.w * n_pad;
-      colkey[po + (size_t)(un.z & 255) * SLAB_COLS + et] = cacc[et];
-      cacc[et] = INT_LOWEST;
-      for (int i = et; i < n_mtiles * MT_ROWS; i += EPI_THREADS) {
-        atomicMax(&rowkey[po + i], racc[i]);
-        racc[i] = INT_LOWEST;
-      }
-      // the buffers of this parity are touched again two units later, after the next barrier
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_full[buf]);  // release: this warp's shared-memory atomics are done
     }
   }
   fence_before_sync();

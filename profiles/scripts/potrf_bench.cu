@@ -48,6 +48,58 @@ __device__ __forceinline__ void potrf32(double (*A)[NB + 1], double* idg, int la
     if (lane > c) A[c][lane] = a[c];
 }
 
+__device__ __forceinline__ double rcp_fast(double d) {
+  // float seed + two Newton steps in double
+  double y = (double)__frcp_rn((float)d);
+  y = fma(y, fma(-d, y, 1.0), y);
+  y = fma(y, fma(-d, y, 1.0), y);
+  return y;
+}
+
+// Two pivots per step through the 2x2 block [d1 e; e d2]: one reciprocal (of its determinant) on the
+// dependency chain, the Cholesky columns of the pair computed off the chain.  VAR 4: __drcp_rn,
+// VAR 5: float-seeded reciprocal and rsqrt.
+template <int VAR>
+__device__ __forceinline__ void potrf32_pair(double (*A)[NB + 1], double* idg, int lane) {
+  double a[NB];
+#pragma unroll
+  for (int c = 0; c < NB; c++) a[c] = A[lane][c];
+  double my_is = 1.0;
+#pragma unroll
+  for (int c = 0; c < NB; c += 2) {
+    double d1 = __shfl_sync(0xffffffffu, a[c], c);
+    double e = __shfl_sync(0xffffffffu, a[c], c + 1);
+    double d2 = __shfl_sync(0xffffffffu, a[c + 1], c + 1);
+    double det = d1 * d2 - e * e;
+    if (!(d1 > 0.0) || !(det > 0.0)) {
+      d1 = d2 = det = 1.0;
+      e = 0.0;
+    }
+    const double rdet = VAR == 4 ? __drcp_rn(det) : rcp_fast(det);
+    const double x = a[c], y = a[c + 1];
+    const double u = (x * d2 - y * e) * rdet;
+    const double v = (y * d1 - x * e) * rdet;
+#pragma unroll
+    for (int q = c + 2; q < NB; q++) {
+      const double xq = __shfl_sync(0xffffffffu, x, q);
+      const double yq = __shfl_sync(0xffffffffu, y, q);
+      a[q] = fma(-v, yq, fma(-u, xq, a[q]));
+    }
+    const double is1 = VAR == 4 ? rsqrt(d1) : rsqrt_fast(d1);
+    const double s2 = det * (is1 * is1);
+    const double is2 = VAR == 4 ? rsqrt(s2) : rsqrt_fast(s2);
+    const double l1 = x * is1;
+    a[c] = l1;
+    a[c + 1] = (y - l1 * (e * is1)) * is2;
+    if (lane == c) my_is = is1;
+    if (lane == c + 1) my_is = is2;
+  }
+  idg[lane] = my_is;
+#pragma unroll
+  for (int c = 0; c < NB; c++)
+    if (lane > c) A[c][lane] = a[c];
+}
+
 template <int VAR>
 __global__ void bench(const double* in, double* out, long long* cyc) {
   __shared__ double A[NB][NB + 1];
@@ -56,7 +108,7 @@ __global__ void bench(const double* in, double* out, long long* cyc) {
   for (int c = 0; c < NB; c++) A[lane][c] = in[lane * NB + c];
   __syncwarp();
   const long long t0 = clock64();
-  potrf32<VAR>(A, idg, lane);
+  if (VAR >= 4) potrf32_pair<VAR>(A, idg, lane); else potrf32<VAR>(A, idg, lane);
   __syncwarp();
   const long long t1 = clock64();
   if (lane == 0) cyc[VAR] = t1 - t0;
@@ -78,10 +130,12 @@ int main() {
     bench<1><<<1, 32>>>(din, dout, dc);
     bench<2><<<1, 32>>>(din, dout, dc);
     bench<3><<<1, 32>>>(din, dout, dc);
+    bench<4><<<1, 32>>>(din, dout, dc);
+    bench<5><<<1, 32>>>(din, dout, dc);
   }
   cudaMemcpy(L, dout, sizeof(h), cudaMemcpyDeviceToHost);
-  long long c[4];
-  cudaMemcpy(c, dc, 32, cudaMemcpyDeviceToHost);
+  long long c[6];
+  cudaMemcpy(c, dc, 48, cudaMemcpyDeviceToHost);
   double err = 0;
   for (int i = 0; i < NB; i++)
     for (int j = 0; j <= i; j++) {
@@ -89,7 +143,7 @@ int main() {
       for (int k = 0; k <= j; k++) s += L[i * NB + k] * L[j * NB + k];
       err = fmax(err, fabs(s - h[i * NB + j]));
     }
-  printf("potrf32 cycles: rsqrt+branch %lld | select %lld | fast rsqrt %lld | + local next pivot %lld ; |LL^T - A| = %.3g (last variant)\n",
-         c[0], c[1], c[2], c[3], err);
+  printf("potrf32 cycles: rsqrt+branch %lld | select %lld | fast rsqrt %lld | + local next pivot %lld | 2x2 pivots drcp %lld | 2x2 fast %lld ; |LL^T - A| = %.3g (last variant)\n",
+         c[0], c[1], c[2], c[3], c[4], c[5], err);
   return 0;
 }

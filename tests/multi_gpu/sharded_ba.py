@@ -40,6 +40,11 @@ def main():
         s = prob.solve(opt, sharded=True)
         cams, pts = prob.download()
         prob.close()
+        # the host-buffer form of the same collective solve
+        c_hb, p_hb, s_hb = ctx.ba_local_shard(sharding.shard_ba_by_point(pb, rank, world), opt)
+        np.testing.assert_allclose(c_hb, cams, rtol=1e-6, atol=1e-8)
+        np.testing.assert_allclose(p_hb, pts, rtol=1e-6, atol=1e-8)
+        assert s_hb["iterations"] == s["iterations"]
         # gather the point shards on rank 0
         lo_hi = [sharding.window_slice(r_, world, len(pb["pts"])) for r_ in range(world)]
         mx = max(h - l for l, h in lo_hi)
