@@ -10,6 +10,7 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    config.addinivalue_line("markers", "slow: full BASELINE sizes against the oracle (tens of seconds of CPU)")
 
 
 @pytest.fixture(scope="session", autouse=True)

@@ -2,6 +2,8 @@
 (oracle/ba_ref.cpp, Ceres-contract restatement; parity vs Ceres itself is
 unpinned — see the oracle header).  Bar (north_star): final poses and points
 within 1e-6 relative, fp64 accumulation."""
+import os
+
 import numpy as np
 import pytest
 
@@ -100,6 +102,35 @@ def test_local_ba_blocked_cholesky(ctx):
     """40 cameras -> 240x240 reduced system: the global-memory blocked Cholesky path."""
     pb = synth.make_ba_problem(7, C=40, P=3000, obs_per_point=(6, 7, 8), traj_len=12.0)
     _run_local(ctx, pb, max_num_iterations=8)
+
+
+@pytest.mark.slow
+def test_large_ba_full_size_cfg5_vs_oracle(ctx):
+    """BASELINE config 5 at FULL size (200 keyframes / 200 000 points / 1.5 M observations): the
+    large path (work lists, packed Schur triangle, dataflow Cholesky on the 1200 x 1200 system)
+    against the oracle after three LM iterations (about 25 s of CPU for the oracle), final cameras
+    and points within rtol 1e-6, and the sharded code path (one-rank communicator) against both."""
+    pb = synth.make_ba_problem(0, C=200, P=200000, obs_per_point=(7, 8), traj_len=100.0)
+    assert 1.49e6 < pb["O"] < 1.51e6
+    kw = dict(max_num_iterations=3)
+    cams, pts, s = ctx.ba_local(pb, capi.ba_options(**kw))
+    oc, op, o = ref.ba_local(pb, ref.ba_options(**kw))
+    _close(cams, oc, "cameras")
+    _close(pts, op, "points")
+    _same_summary(s, o)
+    np.testing.assert_allclose(s["final_cost"], o["final_cost"], rtol=1e-9)
+    # 64 windows of config 4 at once against the oracle, every window
+    pbs = [synth.make_ba_problem(1000 + i, C=10, P=5000) for i in range(64)]
+    bt = synth.batch_windows(pbs)
+    bc, bp, sums = ctx.ba_local_batched(bt, capi.ba_options(max_num_iterations=4))
+    ref.set_num_threads(os.cpu_count() or 1)
+    rc, rp, rs = ref.ba_local_batched(bt["cam_off"], bt["cams"], bt["pt_off"], bt["pts"], bt["obs_off"],
+                                      bt["obs_cam"], bt["obs_pt"], bt["obs_uv"], bt["K"],
+                                      ref.ba_options(max_num_iterations=4))
+    _close(bc, rc, "cameras of the 64-window batch")
+    _close(bp, rp, "points of the 64-window batch")
+    for a, b in zip(sums, rs):
+        _same_summary(a, b)
 
 
 def test_resident_problem_reset_and_resolve(ctx):
