@@ -562,21 +562,31 @@ int lorb_ba_problem_create_batched(lorb_ctx* ctx, int n_windows, const int* cam_
                                    lorb_ba_problem** out);
 /*
  * Sharding helpers of the multi-GPU paths, so that a C++ host need not restate them:
- *   lorb_shard_range   contiguous [lo, hi) slice of n units (windows, points) owned by `rank`:
- *                      sizes differ by at most one, the first n % world ranks take the extra unit
+ *   lorb_shard_range   contiguous [lo, hi) slice of n units (batched windows) owned by `rank`: sizes
+ *                      differ by at most one, the first n % world ranks take the extra unit
+ *   lorb_ba_shard_points
+ *                      the points of `rank` in the large BA.  Any partition of the points, each with
+ *                      all its observations, is a valid shard; this one orders the points by the lowest
+ *                      window camera observing them and cuts that order into `world` runs of equal
+ *                      observation count, so that a rank meets a band of cameras (its camera-pair work
+ *                      lists shrink with world) and the ranks carry the same work.  out_point_ids
+ *                      (capacity P, may be NULL to query *n_out) receives the point indices.
  *   lorb_ba_problem_create_sharded
- *                      the point shard of `rank` of a WHOLE problem given in the arrays of
- *                      lorb_ba_problem_create: points [pt_lo, pt_hi) = lorb_shard_range(P) with all
- *                      their observations (renumbered from 0), every camera replicated.  Solve with
+ *                      that shard of a WHOLE problem given in the arrays of lorb_ba_problem_create:
+ *                      the points lorb_ba_shard_points names (renumbered in that order) with all their
+ *                      observations, every camera replicated.  Solve with
  *                      lorb_ba_problem_solve(..., sharded = 1); lorb_ba_problem_download then returns
- *                      all C cameras (identical on every rank) and this rank's pt_hi - pt_lo points.
+ *                      all C cameras (identical on every rank) and this rank's *n_points points, point
+ *                      i of the result being point out_point_ids[i] of the whole problem.
  */
 int lorb_shard_range(long long n, int rank, int world, long long* lo, long long* hi);
+int lorb_ba_shard_points(int P, int O, const int* obs_cam, const int* obs_pt, int rank, int world,
+                         int* out_point_ids, int* n_out);
 int lorb_ba_problem_create_sharded(lorb_ctx* ctx, int C, const double* cams, int P, const double* pts,
                                    int O, const int* obs_cam, const int* obs_pt, const float* obs_uv,
                                    int F, const int* fix_pt, const float* fix_uv, const float* fix_rt,
                                    const float* K, int rank, int world, lorb_ba_problem** out,
-                                   int* pt_lo, int* pt_hi);
+                                   int* out_point_ids, int* n_points);
 /* Restore the parameters uploaded at creation (so a bench can re-solve). */
 int lorb_ba_problem_reset(lorb_ba_problem* p);
 /* Run LM on the resident problem.  If the ctx has a distributed group

@@ -30,7 +30,7 @@ EXPORTS = [
     "lorb_stereo_matches", "lorb_orb_describe", "lorb_orb_umax", "lorb_orb_selftest",
     "lorb_orb_extract", "lorb_orb_level_sizes", "lorb_orb_stages", "lorb_stereo_frame", "lorb_orb_distribute", "lorb_orb_max_keypoints",
     "lorb_ba_default_options", "lorb_ba_pose_only", "lorb_ba_local", "lorb_ba_local_batched", "lorb_ba_local_shard",
-    "lorb_ba_problem_create", "lorb_ba_problem_create_batched", "lorb_ba_problem_create_sharded", "lorb_shard_range", "lorb_set_host_threads", "lorb_ba_problem_reset", "lorb_ba_problem_solve",
+    "lorb_ba_problem_create", "lorb_ba_problem_create_batched", "lorb_ba_problem_create_sharded", "lorb_shard_range", "lorb_ba_shard_points", "lorb_set_host_threads", "lorb_ba_problem_reset", "lorb_ba_problem_solve",
     "lorb_ba_problem_download", "lorb_ba_problem_destroy", "lorb_dist_get_unique_id",
     "lorb_dist_init", "lorb_dist_finalize", "lorb_dist_allreduce_f64", "lorb_microbench_popc",
     "lorb_microbench_fp64", "lorb_microbench_tensor_i8", "lorb_ctx_profile", "lorb_ctx_profile_read",
@@ -178,6 +178,16 @@ def shard_range(n, rank, world):
     lo, hi = C.c_longlong(), C.c_longlong()
     _check(load_library().lorb_shard_range(C.c_longlong(int(n)), int(rank), int(world), C.byref(lo), C.byref(hi)))
     return int(lo.value), int(hi.value)
+
+
+def ba_shard_points(P, obs_cam, obs_pt, rank, world):
+    """Point indices of `rank` in the point-sharded large BA (lorb_ba_shard_points; host logic only)."""
+    oc, op = _arr(obs_cam, np.int32), _arr(obs_pt, np.int32)
+    ids = np.zeros(max(1, int(P)), np.int32)
+    n = C.c_int()
+    _check(load_library().lorb_ba_shard_points(int(P), len(oc), _ptr(oc), _ptr(op), int(rank), int(world),
+                                               _ptr(ids), C.byref(n)))
+    return ids[:n.value].copy()
 
 
 def sweep_pair_index(n_kf, a, b):
@@ -641,13 +651,13 @@ class BAProblem:
         self.C, self.P = len(cams), len(pts)
         h = C.c_void_p()
         if shard is not None:
-            lo, hi = C.c_int(), C.c_int()
+            ids, n = np.zeros(max(1, len(pts)), np.int32), C.c_int()
             _check(self._lib.lorb_ba_problem_create_sharded(
                 ctx._h, len(cams), _ptr(cams), len(pts), _ptr(pts), len(oc), _ptr(oc), _ptr(op),
                 _ptr(ouv), len(fp), _ptr(fp), _ptr(fuv), _ptr(frt), _ptr(K), int(shard[0]), int(shard[1]),
-                C.byref(h), C.byref(lo), C.byref(hi)))
-            self.point_range = (lo.value, hi.value)
-            self.P = hi.value - lo.value
+                C.byref(h), _ptr(ids), C.byref(n)))
+            self.point_ids = ids[:n.value].copy()
+            self.P = n.value
             self._h = h
             return
         _check(self._lib.lorb_ba_problem_create(

@@ -2677,15 +2677,15 @@ static int run_cholesky(lorb_ba_problem* pb) {
     return LORB_OK;
   }
   const int nblk = (n + NB - 1) / NB;
-  static int coop_ok = -1, coop_blocks = 0;
-  if (coop_ok < 0) {
+  if (c->chol_coop_blocks < 0) {  // per context (= per device and calling thread)
     int dev_coop = 0, per_sm = 0;
     cudaDeviceGetAttribute(&dev_coop, cudaDevAttrCooperativeLaunch, c->device);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ba_chol_dataflow_kernel, 256, 0);
     const char* e = getenv("LORB_CHOL_DATAFLOW");
-    coop_ok = (dev_coop && per_sm > 0 && !(e && atoi(e) == 0)) ? 1 : 0;
-    coop_blocks = per_sm * c->sm_count;
+    c->chol_coop_blocks = (dev_coop && per_sm > 0 && !(e && atoi(e) == 0)) ? per_sm * c->sm_count : 0;
   }
+  const int coop_blocks = c->chol_coop_blocks;
+  const bool coop_ok = coop_blocks > 0;
   // (one CTA per block row of the solve must be co-resident as well)
   if (coop_ok && nw == 1 && nblk <= c->sm_count) {
     const int n_tiles = nblk * (nblk + 1) / 2;
@@ -2965,39 +2965,87 @@ int lorb_shard_range(long long n, int rank, int world, long long* lo, long long*
   return LORB_OK;
 }
 
+// Which points go to which rank.  Any partition of the points (each with all its observations) is a
+// valid shard; this one keeps a rank's points together along the trajectory: points are ordered by
+// the lowest window camera that observes them (ties by point index) and that order is cut into
+// `world` runs of equal observation count.  A rank then touches a band of cameras -- its camera /
+// camera-pair work lists are ~world times shorter than with an arbitrary split, where every rank
+// meets every camera pair -- and the ranks carry the same number of observations.
+int lorb_ba_shard_points(int P, int O, const int* obs_cam, const int* obs_pt, int rank, int world,
+                         int* out_point_ids, int* n_out) {
+  LORB_REQUIRE(P >= 0 && O >= 0 && world >= 1 && rank >= 0 && rank < world && n_out, "arguments");
+  LORB_REQUIRE(O == 0 || (obs_cam && obs_pt), "observations");
+  std::vector<int> key((size_t)P, 0x7fffffff), cnt((size_t)P, 0);
+  for (int o = 0; o < O; o++) {
+    LORB_REQUIRE(obs_pt[o] >= 0 && obs_pt[o] < P, "observation point index");
+    key[obs_pt[o]] = std::min(key[obs_pt[o]], obs_cam[o]);
+    cnt[obs_pt[o]]++;
+  }
+  std::vector<int> order((size_t)P);
+  for (int p = 0; p < P; p++) order[p] = p;
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return key[a] < key[b]; });
+  // cut k ends at the first position where the running observation count reaches k * O / world
+  // (points without observations follow the last observed point into the last rank)
+  long long run = 0;
+  int n = 0, r = 0;
+  for (int i = 0; i < P; i++) {
+    const int p = order[i];
+    while (r + 1 < world && run >= (long long)O * (r + 1) / world && (run > 0 || O == 0)) r++;
+    if (O == 0) r = (int)((long long)i * world / std::max(1, P));
+    if (r == rank) {
+      if (out_point_ids) out_point_ids[n] = p;
+      n++;
+    }
+    run += cnt[p];
+  }
+  *n_out = n;
+  return LORB_OK;
+}
+
 int lorb_ba_problem_create_sharded(lorb_ctx* c, int C, const double* cams, int P, const double* pts,
                                    int O, const int* obs_cam, const int* obs_pt, const float* obs_uv,
                                    int F, const int* fix_pt, const float* fix_uv, const float* fix_rt,
                                    const float* K, int rank, int world, lorb_ba_problem** out,
-                                   int* pt_lo, int* pt_hi) {
-  LORB_REQUIRE(c && out && K, "ctx / out / K");
+                                   int* out_point_ids, int* n_points) {
+  LORB_REQUIRE(c && out && K && out_point_ids && n_points, "ctx / out / K / point ids");
   LORB_REQUIRE(C > 0 && P >= 0 && O >= 0 && F >= 0, "sizes");
   LORB_REQUIRE(O == 0 || (obs_cam && obs_pt && obs_uv), "observations");
   LORB_REQUIRE(F == 0 || (fix_pt && fix_uv && fix_rt), "fixed observations");
-  long long lo = 0, hi = 0;
-  LORB_TRY(lorb_shard_range(P, rank, world, &lo, &hi));
-  std::vector<int> oc, op, fp;
-  std::vector<float> ouv, fuv, frt;
+  LORB_REQUIRE(P == 0 || pts, "points");
+  int n = 0;
+  LORB_TRY(lorb_ba_shard_points(P, O, obs_cam, obs_pt, rank, world, out_point_ids, &n));
+  *n_points = n;
+  std::vector<int> local((size_t)P, -1);
+  for (int i = 0; i < n; i++) local[out_point_ids[i]] = i;
+  std::vector<double> spts((size_t)n * 3);
+  for (int i = 0; i < n; i++)
+    for (int a = 0; a < 3; a++) spts[3 * (size_t)i + a] = pts[3 * (size_t)out_point_ids[i] + a];
+  // observations of the shard, grouped by local point (counting sort keeps their input order)
+  std::vector<int> start((size_t)n + 1, 0);
+  for (int o = 0; o < O; o++)
+    if (local[obs_pt[o]] >= 0) start[local[obs_pt[o]] + 1]++;
+  for (int i = 0; i < n; i++) start[i + 1] += start[i];
+  const int no = start[n];
+  std::vector<int> oc((size_t)no), op((size_t)no), fill(start.begin(), start.end() - 1), fp;
+  std::vector<float> ouv((size_t)no * 2), fuv, frt;
   for (int o = 0; o < O; o++) {
-    LORB_REQUIRE(obs_pt[o] >= 0 && obs_pt[o] < P, "observation point index");
-    if (obs_pt[o] < lo || obs_pt[o] >= hi) continue;
-    oc.push_back(obs_cam[o]);
-    op.push_back(obs_pt[o] - (int)lo);
-    ouv.push_back(obs_uv[2 * (size_t)o]);
-    ouv.push_back(obs_uv[2 * (size_t)o + 1]);
+    const int l = local[obs_pt[o]];
+    if (l < 0) continue;
+    const int d = fill[l]++;
+    oc[d] = obs_cam[o];
+    op[d] = l;
+    ouv[2 * (size_t)d] = obs_uv[2 * (size_t)o];
+    ouv[2 * (size_t)d + 1] = obs_uv[2 * (size_t)o + 1];
   }
   for (int f = 0; f < F; f++) {
     LORB_REQUIRE(fix_pt[f] >= 0 && fix_pt[f] < P, "fixed observation point index");
-    if (fix_pt[f] < lo || fix_pt[f] >= hi) continue;
-    fp.push_back(fix_pt[f] - (int)lo);
+    if (local[fix_pt[f]] < 0) continue;
+    fp.push_back(local[fix_pt[f]]);
     fuv.insert(fuv.end(), fix_uv + 2 * (size_t)f, fix_uv + 2 * (size_t)f + 2);
     frt.insert(frt.end(), fix_rt + 6 * (size_t)f, fix_rt + 6 * (size_t)f + 6);
   }
-  if (pt_lo) *pt_lo = (int)lo;
-  if (pt_hi) *pt_hi = (int)hi;
-  return lorb_ba_problem_create(c, C, cams, (int)(hi - lo), pts ? pts + 3 * (size_t)lo : nullptr, (int)oc.size(),
-                                oc.data(), op.data(), ouv.data(), (int)fp.size(), fp.data(), fuv.data(),
-                                frt.data(), K, out);
+  return lorb_ba_problem_create(c, C, cams, n, spts.data(), no, oc.data(), op.data(), ouv.data(), (int)fp.size(),
+                                fp.data(), fuv.data(), frt.data(), K, out);
 }
 
 int lorb_ba_problem_reset(lorb_ba_problem* pb) {

@@ -67,6 +67,8 @@ struct lorb_ctx {
   lorb::Buf tc_img, tc_units, tc_keys;
   int tc_img_n_kf = 0, tc_img_n_desc = 0, tc_n_units = 0;
   size_t tc_keys_rows = 0;
+  int proj_coop_blocks[2] = {-1, -1};  // co-resident CTAs of the cooperative claim resolution (match_proj.cu)
+  int chol_coop_blocks = -1;           // same for the dataflow Cholesky (ba_local.cu); 0 = not available
   lorb::Dist* dist = nullptr;
   void* ba_cache = nullptr;  // reusable lorb_ba_problem of the host-buffer BA calls (ba_local.cu)
   // cached CUDA graphs of the ORB extractor's detection chain (orb.cu), one per job slot

@@ -855,7 +855,8 @@ static int run_search(lorb_ctx* c, const lorb_frame_view* fv, int n_pts, const u
       LORB_TRY(launch_cand.launch(c, f, up.d + o_extra, d_mpd, d_segs, d_segl, d_cand,
                                   (int)std::min<size_t>(cand_cap, 0x7fffffff), d_counter));
     }
-    static int coop_blocks[2] = {-1, -1};  // per MODE: co-resident CTAs of the cooperative kernel
+    // per context (= per device and calling thread): co-resident CTAs of the cooperative kernel
+    int* coop_blocks = c->proj_coop_blocks;
     if (coop_blocks[MODE] < 0) {
       int dev_coop = 0, per_sm = 0;
       cudaDeviceGetAttribute(&dev_coop, cudaDevAttrCooperativeLaunch, c->device);

@@ -52,8 +52,14 @@ class CtxPool {
     std::lock_guard<std::mutex> g(m_);
     free_.push_back(c);
   }
-  ~CtxPool() {
+  // Explicit teardown for hosts that want the device memory back before exit (no thread may be
+  // inside a Matcher / BA / ORBextractor call).  There is deliberately NO destructor doing this: the
+  // pool object is never destroyed (see pool()), because CUDA's own atexit teardown may already have
+  // run when static destructors fire, and a thread that exits after main must still find a live pool.
+  void shutdown() {
+    std::lock_guard<std::mutex> g(m_);
     for (lorb_ctx* c : free_) lorb_ctx_destroy(c);
+    free_.clear();
   }
 
  private:
@@ -63,9 +69,13 @@ class CtxPool {
 };
 
 inline CtxPool& pool() {
-  static CtxPool p;  // one pool per process (inline function: shared by every translation unit)
-  return p;
+  // one pool per process (inline function: shared by every translation unit), leaked on purpose:
+  // contexts left in it at exit are reclaimed by the driver with the process
+  static CtxPool* p = new CtxPool();
+  return *p;
 }
+
+inline void shutdown() { pool().shutdown(); }
 
 struct ThreadCtx {
   lorb_ctx* ctx = nullptr;

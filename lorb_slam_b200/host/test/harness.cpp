@@ -364,6 +364,65 @@ int harness_local_mapping(int n_kf, const float* kf_rt, const int* kf_off, const
 	return n_ba;
 }
 
+// LocalMapIndex on its own (host logic only, no device call): insert the keyframes, then assemble the
+// local-BA problem of keyframe `k_ba` and hand its index arrays back.  Same inputs as
+// harness_local_mapping; bad_kf / bad_pt flag frames / points whose IsBad() is true.
+// out_sizes = {C, P, O, F, frames in index, points in index, observations in index}.
+int harness_local_map_assemble(int n_kf, const float* kf_rt, const int* kf_off, const int* slot_pt,
+                               const float* slot_uv, const int* cov_off, const int* cov_idx, int P,
+                               const float* pts, const uint8_t* bad_kf, const uint8_t* bad_pt, int k_ba,
+                               int cap, int* out_window, int* out_points, int* out_obs_cam, int* out_obs_pt,
+                               float* out_obs_uv, int* out_fix_pt, float* out_fix_uv, float* out_fix_rt,
+                               int* out_sizes)
+{
+	std::vector<Frame> frames(n_kf);
+	std::vector<MapPoint> mps(P);
+	for(int p=0;p<P;p++)
+	{
+		mps[p].mWorldPos = cv::Point3f(pts[3*p], pts[3*p+1], pts[3*p+2]);
+		mps[p].mbBadFlag = bad_pt && bad_pt[p];
+	}
+	lorb_host::LocalMapIndex index;
+	for(int k=0; k<n_kf; k++)
+	{
+		Frame& F = frames[k];
+		cv::Mat R(3,1,CV_32F), T(3,1,CV_32F);
+		for(int a=0;a<3;a++) { R.at<float>(a) = kf_rt[6*k+a]; T.at<float>(a) = kf_rt[6*k+3+a]; }
+		F.SetPose(T, R);
+		for(int s=kf_off[k]; s<kf_off[k+1]; s++)
+		{
+			cv::KeyPoint kp;
+			kp.pt = cv::Point2f(slot_uv[2*s], slot_uv[2*s+1]);
+			F.mvKeysUn.push_back(kp);
+			F.mvpMapPoints.push_back(slot_pt[s] >= 0 ? &mps[slot_pt[s]] : static_cast<MapPoint*>(NULL));
+		}
+		F.mnMapPoints = F.mvKeysUn.size();
+		for(int c=cov_off[k]; c<cov_off[k+1]; c++) F.mvpOrderedKeyFrames.push_back(&frames[cov_idx[c]]);
+		index.InsertKeyFrame(&F);
+	}
+	for(int k=0; k<n_kf; k++) frames[k].mbBadFlag = bad_kf && bad_kf[k];  // culled after insertion
+	lorb_host::LocalBAWindow w;
+	index.Assemble(&frames[k_ba], w);
+	const int C = (int)w.frames.size(), Pw = (int)w.points.size(), O = (int)w.obs_cam.size(), Fx = (int)w.fix_pt.size();
+	if(C > cap || Pw > cap || O > cap || Fx > cap) return -1;
+	for(int i=0;i<C;i++) out_window[i] = (int)(w.frames[i] - &frames[0]);
+	for(int i=0;i<Pw;i++) out_points[i] = (int)(w.points[i] - &mps[0]);
+	for(int i=0;i<O;i++)
+	{
+		out_obs_cam[i] = w.obs_cam[i]; out_obs_pt[i] = w.obs_pt[i];
+		out_obs_uv[2*i] = w.obs_uv[2*i]; out_obs_uv[2*i+1] = w.obs_uv[2*i+1];
+	}
+	for(int i=0;i<Fx;i++)
+	{
+		out_fix_pt[i] = w.fix_pt[i];
+		out_fix_uv[2*i] = w.fix_uv[2*i]; out_fix_uv[2*i+1] = w.fix_uv[2*i+1];
+		for(int a=0;a<6;a++) out_fix_rt[6*i+a] = w.fix_rt[6*i+a];
+	}
+	out_sizes[0] = C; out_sizes[1] = Pw; out_sizes[2] = O; out_sizes[3] = Fx;
+	out_sizes[4] = (int)index.NumFrames(); out_sizes[5] = (int)index.NumPoints(); out_sizes[6] = (int)index.NumObservations();
+	return 0;
+}
+
 // ORBextractor(nfeatures, 1.2, 8, 20, 7)(image, Mat(), keypoints, descriptors) as Frame's
 // constructor calls it (reference src/frame.cpp:34-56, 132-133); returns the keypoint count.
 // out_pyr_sum[l] = byte sum of mvImagePyramid[l] (the member ComputeStereoMatches reads).

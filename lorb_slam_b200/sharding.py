@@ -31,23 +31,30 @@ def window_slice(rank, world, n_windows):
 
 
 def shard_ba_by_point(pb, rank, world):
-    """Sub-problem of `rank`: a contiguous range of points with ALL their
-    observations (so H_pp, its inverse and every Schur product are rank-local),
-    every camera replicated.  Point indices are renumbered from 0."""
+    """Sub-problem of `rank`: its points (lorb_ba_shard_points: ordered by the lowest camera that
+    observes them, cut into runs of equal observation count) with ALL their observations (so H_pp, its
+    inverse and every Schur product are rank-local), every camera replicated.  Points are renumbered
+    in shard order; out["point_ids"] maps them back."""
+    from . import capi
     P = len(pb["pts"])
-    lo, hi = window_slice(rank, world, P)
-    sel = (pb["obs_pt"] >= lo) & (pb["obs_pt"] < hi)
+    ids = capi.ba_shard_points(P, pb["obs_cam"], pb["obs_pt"], rank, world)
+    local = np.full(P, -1, np.int64)
+    local[ids] = np.arange(len(ids))
+    lo = local[pb["obs_pt"]]
+    sel = np.flatnonzero(lo >= 0)
+    sel = sel[np.argsort(lo[sel], kind="stable")]  # grouped by local point, input order inside a point
     out = dict(pb)
-    out["pts"] = np.ascontiguousarray(pb["pts"][lo:hi])
+    out["pts"] = np.ascontiguousarray(pb["pts"][ids])
     out["obs_cam"] = np.ascontiguousarray(pb["obs_cam"][sel])
-    out["obs_pt"] = np.ascontiguousarray(pb["obs_pt"][sel] - lo)
+    out["obs_pt"] = np.ascontiguousarray(lo[sel].astype(np.int32))
     out["obs_uv"] = np.ascontiguousarray(pb["obs_uv"][sel])
     if len(pb.get("fix_pt", [])):
-        fs = (pb["fix_pt"] >= lo) & (pb["fix_pt"] < hi)
-        out["fix_pt"] = np.ascontiguousarray(pb["fix_pt"][fs] - lo)
+        fl = local[pb["fix_pt"]]
+        fs = np.flatnonzero(fl >= 0)
+        out["fix_pt"] = np.ascontiguousarray(fl[fs].astype(np.int32))
         out["fix_uv"] = np.ascontiguousarray(pb["fix_uv"][fs])
         out["fix_rt"] = np.ascontiguousarray(pb["fix_rt"][fs])
-    out["P"] = hi - lo
-    out["O"] = int(sel.sum())
-    out["point_range"] = (lo, hi)
+    out["P"] = len(ids)
+    out["O"] = len(sel)
+    out["point_ids"] = ids
     return out

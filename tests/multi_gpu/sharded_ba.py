@@ -34,7 +34,7 @@ def main():
         opt = capi.ba_options(max_num_iterations=8)
         if case == "blocked":  # the C ABI's own sharding entry point
             prob = ctx.ba_problem_sharded(pb, rank, world)
-            assert prob.point_range == sharding.window_slice(rank, world, len(pb["pts"]))
+            assert np.array_equal(prob.point_ids, sharding.shard_ba_by_point(pb, rank, world)["point_ids"])
         else:                  # the Python restatement of the same split
             prob = ctx.ba_problem(sharding.shard_ba_by_point(pb, rank, world))
         s = prob.solve(opt, sharded=True)
@@ -46,8 +46,9 @@ def main():
         np.testing.assert_allclose(p_hb, pts, rtol=1e-6, atol=1e-8)
         assert s_hb["iterations"] == s["iterations"]
         # gather the point shards on rank 0
-        lo_hi = [sharding.window_slice(r_, world, len(pb["pts"])) for r_ in range(world)]
-        mx = max(h - l for l, h in lo_hi)
+        ids_r = [capi.ba_shard_points(len(pb["pts"]), pb["obs_cam"], pb["obs_pt"], r_, world) for r_ in range(world)]
+        assert sorted(np.concatenate(ids_r).tolist()) == list(range(len(pb["pts"])))
+        mx = max(len(i_) for i_ in ids_r)
         buf = torch.zeros((mx, 3), dtype=torch.float64, device="cuda")
         buf[:len(pts)] = torch.from_numpy(pts).cuda()
         allb = [torch.zeros_like(buf) for _ in range(world)]
@@ -57,7 +58,9 @@ def main():
         dist.broadcast(cam0, 0)
         assert torch.equal(camt, cam0), "replicated cameras diverged between ranks"
         if rank == 0:
-            full_pts = np.concatenate([allb[r_][:h - l].cpu().numpy() for r_, (l, h) in enumerate(lo_hi)])
+            full_pts = np.zeros((len(pb["pts"]), 3))
+            for r_, i_ in enumerate(ids_r):
+                full_pts[i_] = allb[r_][:len(i_)].cpu().numpy()
             c1, p1, s1 = ctx.ba_local(pb, opt)
             np.testing.assert_allclose(cams, c1, rtol=1e-6, atol=1e-8)
             np.testing.assert_allclose(full_pts, p1, rtol=1e-6, atol=1e-8)

@@ -80,6 +80,34 @@ def test_sweep_tile_grid():
     assert idx == list(range(15)) and capi.sweep_pair_index(6, 4, 1) == capi.sweep_pair_index(6, 1, 4)
 
 
+def test_ba_point_shards_are_a_balanced_banded_partition():
+    """lorb_ba_shard_points: every point in exactly one shard, observation counts level, and a shard
+    meets far fewer camera pairs than an arbitrary split would (what shortens its work lists)."""
+    pb = synth.make_ba_problem(4, C=120, P=4000, obs_per_point=(5, 6, 7), traj_len=120.0)
+    world = 4
+    ids = [capi.ba_shard_points(pb["P"], pb["obs_cam"], pb["obs_pt"], r, world) for r in range(world)]
+    assert sorted(np.concatenate(ids).tolist()) == list(range(pb["P"]))
+    cnt = np.bincount(pb["obs_pt"], minlength=pb["P"])
+    per_rank = [int(cnt[i].sum()) for i in ids]
+    assert max(per_rank) - min(per_rank) <= 2 * cnt.max()
+
+    def pairs(point_ids):
+        keep = np.isin(pb["obs_pt"], point_ids)
+        oc, op = pb["obs_cam"][keep], pb["obs_pt"][keep]
+        seen = set()
+        for p in np.unique(op):
+            cs = oc[op == p]
+            seen.update((a, b) for a in cs for b in cs if a <= b)
+        return len(seen)
+    banded = pairs(ids[1])
+    arbitrary = pairs(np.arange(pb["P"])[1::world])
+    assert banded < 0.7 * arbitrary, (banded, arbitrary)
+    # degenerate inputs
+    assert len(capi.ba_shard_points(0, np.zeros(0, np.int32), np.zeros(0, np.int32), 0, 2)) == 0
+    one = [capi.ba_shard_points(3, np.zeros(0, np.int32), np.zeros(0, np.int32), r, 2) for r in range(2)]
+    assert sorted(np.concatenate(one).tolist()) == [0, 1, 2]
+
+
 def test_window_slice_edges():
     assert sharding.window_slice(0, 1, 7) == (0, 7)
     assert [sharding.window_slice(r, 4, 2) for r in range(4)] == [(0, 1), (1, 2), (2, 2), (2, 2)]
