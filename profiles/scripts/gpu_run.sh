@@ -1,22 +1,4 @@
 set -x
-N=$(nvidia-smi -L | wc -l)
-timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29711 bench.py --gpus $N --steps 10 --warmup 3 --no-extras > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err; echo rc=$?; tail -3 gpurun_out/bench_n$N.err
-python - <<PY
-import json
-d=json.loads(open('gpurun_out/bench_n$N.json').read().strip().split('\n')[-1])
-print('sweep', d['value']/1e9, 'e2e', d['e2e']['value']/1e9, d['roofline']['frac'])
-print('full', d['full_sweep']['value']/1e9, d['full_sweep']['wall_s'], d['full_sweep']['gather_s'], d['full_sweep']['parity'])
-for k in ('ba_batched','ba_large'):
-    b=d[k]; print(k, b['value']/1e9, 'e2e', b['e2e']['value']/1e9, b['roofline']['kernel'], b['roofline']['frac'], b['roofline']['ms_per_attempt_by_part'], b['parity'])
-PY
-if [ "$N" = "8" ]; then
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29712 bench.py --gpus 4 --steps 10 --warmup 3 --no-extras > gpurun_out/bench_n4.json 2> gpurun_out/bench_n4.err; echo rc=$?
-python - <<'PY'
-import json
-d=json.loads(open('gpurun_out/bench_n4.json').read().strip().split('\n')[-1])
-print('N4 sweep', d['value']/1e9, 'e2e', d['e2e']['value']/1e9)
-print('full', d['full_sweep']['value']/1e9, d['full_sweep']['wall_s'])
-for k in ('ba_batched','ba_large'):
-    b=d[k]; print(k, b['value']/1e9, 'e2e', b['e2e']['value']/1e9, b['roofline']['ms_per_attempt_by_part'], b['parity']['ok'])
-PY
-fi
+LORB_SWEEP_CLUSTER=2 timeout 300 python -m pytest tests/test_match_bf_gpu.py tests/test_edge_cases_gpu.py -x -q -m gpu -k sweep 2>&1 | tail -4
+LORB_SWEEP_CLUSTER=2 timeout 120 python profiles/scripts/sweep_probe.py 128 5 2>&1 | tail -4
+timeout 120 python profiles/scripts/sweep_probe.py 128 5 tensor 2>&1 | tail -2
