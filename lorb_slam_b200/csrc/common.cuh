@@ -65,7 +65,7 @@ struct lorb_ctx {
   // row / column key scratch
   int sweep_impl = -1;  // LORB_SWEEP_POPC / LORB_SWEEP_TENSOR; -1 = default (env LORB_SWEEP_IMPL)
   lorb::Buf tc_img, tc_units, tc_keys;
-  int tc_img_n_kf = 0, tc_img_n_desc = 0, tc_n_units = 0, tc_cluster = 1;
+  int tc_img_n_kf = 0, tc_img_n_desc = 0, tc_n_units = 0;
   size_t tc_keys_rows = 0;
   int proj_coop_blocks[2] = {-1, -1};  // co-resident CTAs of the cooperative claim resolution (match_proj.cu)
   int chol_coop_blocks = -1;           // same for the dataflow Cholesky (ba_local.cu); 0 = not available

@@ -48,7 +48,6 @@ constexpr int KEY_OFFSET = 1024 * 256;       // acc + i + j = KEY_OFFSET - 2048 
 constexpr int TC_THREADS = 384;
 constexpr int EPI_THREADS = 256;
 constexpr int INT_LOWEST = -2147483647 - 1;
-constexpr bool LORB_SWEEP_CLUSTER_DEFAULT = false;  // LORB_SWEEP_CLUSTER=2 turns the 2-CTA multicast form on
 
 // smem carve-up (bytes)
 constexpr int OFF_SLAB = 0;
@@ -107,11 +106,6 @@ __global__ void tc_fill_kernel(int* __restrict__ p, long long n, int v) {
 // ---------------------------------------------------------------- the sweep
 __device__ __forceinline__ int max3(int a, int b, int c) { return max(max(a, b), c); }
 
-// CL = 1: every CTA on its own.  CL = 2: clusters of two CTAs work on the two slabs of a slab pair of
-// the same keyframe `a` against the same stream of `b` tiles; each CTA fetches half of every streamed
-// tile and multicasts it into both (one L2 read instead of two), and a ring stage is released when
-// BOTH CTAs' MMAs have read it.  `units` then lists (a, b, slab PAIR, pair).
-template <int CL>
 __global__ void __launch_bounds__(TC_THREADS, 1)
     tc_sweep_kernel(const uint8_t* __restrict__ img, const uint8_t* __restrict__ img_b, long long kf_bytes,
                     const int4* __restrict__ units,
@@ -134,16 +128,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_TMEM);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int crank = CL == 2 ? (int)cluster_ctarank() : 0;
-  const int n_workers = (int)gridDim.x / CL, worker = (int)blockIdx.x / CL;
-  const int u0 = (int)(((long long)n_units * worker) / n_workers);
-  const int u1 = (int)(((long long)n_units * (worker + 1)) / n_workers);
-  auto slab_of = [&](const int4& un) { return CL == 2 ? 2 * (un.z & 255) + crank : (un.z & 255); };
+  const int u0 = (int)(((long long)n_units * blockIdx.x) / gridDim.x);
+  const int u1 = (int)(((long long)n_units * (blockIdx.x + 1)) / gridDim.x);
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; s++) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], CL);  // every CTA of the cluster that received the tile
+      mbar_init(&empty[s], 1);
     }
     mbar_init(res_full, 1);
     mbar_init(res_empty, 1);
@@ -162,7 +153,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
-  if (CL == 2) cluster_sync_all();  // the peer's barriers exist before anything is multicast at them
 
   if (warp < 4) {
     reg_dec<40>();
@@ -176,7 +166,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         if (u == u0 || (un.z >> 8)) {
           mbar_wait_parity(res_empty, (g & 1u) ^ 1u);
           mbar_arrive_expect_tx(res_full, SLAB_BYTES);
-          tma_load_1d(slab, img + (size_t)un.x * kf_bytes + (size_t)slab_of(un) * SLAB_BYTES, SLAB_BYTES,
+          tma_load_1d(slab, img + (size_t)un.x * kf_bytes + (size_t)(un.z & 255) * SLAB_BYTES, SLAB_BYTES,
                       res_full);
           g++;
         }
@@ -185,13 +175,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           const uint32_t stage = t % STAGES, k = t / STAGES;
           mbar_wait_parity(&empty[stage], (k & 1u) ^ 1u);
           mbar_arrive_expect_tx(&full[stage], MTILE_BYTES);
-          if (CL == 2) {  // this CTA's half of the tile, into both CTAs
-            const uint32_t half = MTILE_BYTES / 2, off = (uint32_t)crank * half;
-            tma_load_1d_multicast(ring + stage * MTILE_BYTES + off, src + (size_t)m * MTILE_BYTES + off, half,
-                                  &full[stage], (uint16_t)0x3);
-          } else {
-            tma_load_1d(ring + stage * MTILE_BYTES, src + (size_t)m * MTILE_BYTES, MTILE_BYTES, &full[stage]);
-          }
+          tma_load_1d(ring + stage * MTILE_BYTES, src + (size_t)m * MTILE_BYTES, MTILE_BYTES, &full[stage]);
         }
       }
     } else if (warp == 1 && lane == 0) {
@@ -222,10 +206,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           // index columns: M side reads (X, Y) at core matrices 16, 17; N side (Y, X) at 17, 18
           mma_s8(d_addr, smem_desc(a_addr + 16 * 128, 128, RG_BYTES),
                  smem_desc(slab_addr + 17 * 128, 128, RG_BYTES), IDESC, 1u);
-          if (CL == 2)
-            mma_commit_multicast(&empty[stage], (uint16_t)0x3);
-          else
-            mma_commit(&empty[stage]);
+          mma_commit(&empty[stage]);
           mma_commit(&tmem_full[acc]);
         }
         if (u + 1 == u1 || (nxt.z >> 8)) mma_commit(res_empty);  // last unit on this slab
@@ -243,7 +224,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         int* cacc = colacc + buf * SLAB_COLS;
         const size_t po = (size_t)un.w * n_pad;
         for (int j = ft; j < SLAB_COLS; j += 64) {
-          colkey[po + (size_t)slab_of(un) * SLAB_COLS + j] = cacc[j];
+          colkey[po + (size_t)(un.z & 255) * SLAB_COLS + j] = cacc[j];
           cacc[j] = INT_LOWEST;
         }
         for (int i = ft; i < n_mtiles * MT_ROWS; i += 64) {
@@ -259,7 +240,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     // half h the accumulator columns [128h, 128h+128)
     reg_inc<232>();
     const int ew = warp - 4, q = ew & 3, h = ew >> 2;
-    const int et = tid - 128;  // 0..255
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * 128);
     uint32_t t = 0;
     for (int u = u0; u < u1; u++) {
@@ -330,7 +310,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   }
   fence_before_sync();
   __syncthreads();
-  if (CL == 2) cluster_sync_all();  // no CTA leaves while its peer may still multicast at it
   if (warp == 1) {
     fence_after_sync();
     tmem_dealloc(tmem_base, 512);
@@ -477,22 +456,6 @@ int plan_build(lorb_ctx* c, const int* pa, const int* pb, int n_pairs) {
       for (int p = p0; p < p1; p++) units.push_back(make_int4(pa[p], pb[p], s | (p == p0 ? 256 : 0), p));
     p0 = p1;
   }
-  // clusters of two CTAs take slab pairs: same order, half as many entries (needs an even slab count)
-  static const bool want_cluster = [] {
-    const char* e = getenv("LORB_SWEEP_CLUSTER");
-    return e ? atoi(e) == 2 : LORB_SWEEP_CLUSTER_DEFAULT;
-  }();
-  c->tc_cluster = (want_cluster && n_slabs % 2 == 0) ? 2 : 1;
-  if (c->tc_cluster == 2) {
-    units.clear();
-    for (int p0 = 0; p0 < n_pairs;) {
-      int p1 = p0 + 1;
-      while (p1 < n_pairs && pa[p1] == pa[p0]) p1++;
-      for (int sp = 0; sp < n_slabs / 2; sp++)
-        for (int p = p0; p < p1; p++) units.push_back(make_int4(pa[p], pb[p], sp | (p == p0 ? 256 : 0), p));
-      p0 = p1;
-    }
-  }
   c->tc_n_units = (int)units.size();
   if (units.empty()) return LORB_OK;
   LORB_TRY(c->tc_units.reserve(units.size() * sizeof(int4)));
@@ -512,38 +475,16 @@ int launch_sweep(lorb_ctx* c, int kf_base_a, int kf_base_b, int n_pairs, int* ou
   if (n_pairs == 0 || c->tc_n_units == 0) return LORB_OK;
   const int n_desc = c->bank_n_desc, n_pad = pad_of(n_desc);
   const size_t kf_bytes = image_bytes(n_desc);
+  LORB_CUDA_TRY(cudaFuncSetAttribute(tc_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     TC_SMEM_BYTES));
   int* rowkey = c->tc_keys.as<int>();
   int* colkey = rowkey + c->tc_keys_rows;
-  const uint8_t* img_a = c->tc_img.as<uint8_t>() + (size_t)kf_base_a * kf_bytes;
-  const uint8_t* img_b = c->tc_img.as<uint8_t>() + (size_t)kf_base_b * kf_bytes;
+  const int grid = std::min(c->tc_n_units, c->sm_count);
   prof_begin(c, 3);
-  if (c->tc_cluster == 2) {
-    LORB_CUDA_TRY(cudaFuncSetAttribute(tc_sweep_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       TC_SMEM_BYTES));
-    const int workers = std::max(1, std::min(c->tc_n_units, c->sm_count / 2));
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * workers);
-    cfg.blockDim = dim3(TC_THREADS);
-    cfg.dynamicSmemBytes = TC_SMEM_BYTES;
-    cfg.stream = c->stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    LORB_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc_sweep_kernel<2>, img_a, img_b, (long long)kf_bytes,
-                                     (const int4*)c->tc_units.as<int4>(), c->tc_n_units, n_pad / MT_ROWS, n_pad,
-                                     rowkey, colkey));
-    c->launches++;
-  } else {
-    LORB_CUDA_TRY(cudaFuncSetAttribute(tc_sweep_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       TC_SMEM_BYTES));
-    const int grid = std::min(c->tc_n_units, c->sm_count);
-    LORB_LAUNCH(c, tc_sweep_kernel<1>, grid, TC_THREADS, TC_SMEM_BYTES, img_a, img_b, (long long)kf_bytes,
-                c->tc_units.as<int4>(), c->tc_n_units, n_pad / MT_ROWS, n_pad, rowkey, colkey);
-  }
+  LORB_LAUNCH(c, tc_sweep_kernel, grid, TC_THREADS, TC_SMEM_BYTES,
+              c->tc_img.as<uint8_t>() + (size_t)kf_base_a * kf_bytes,
+              c->tc_img.as<uint8_t>() + (size_t)kf_base_b * kf_bytes, (long long)kf_bytes,
+              c->tc_units.as<int4>(), c->tc_n_units, n_pad / MT_ROWS, n_pad, rowkey, colkey);
   prof_end(c, 3);
   LORB_LAUNCH(c, tc_finalize_kernel, n_pairs, 256, 0, rowkey, colkey, n_desc, n_pad, out);
   return LORB_OK;

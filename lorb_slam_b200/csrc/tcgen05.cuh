@@ -47,37 +47,6 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
                : "memory");
 }
 
-// Same, arriving on the barrier at this shared-memory offset in every CTA of `cta_mask` (the
-// consumers of a tile that was multicast into several CTAs each tell every producer).
-__device__ __forceinline__ void mma_commit_multicast(uint64_t* bar, uint16_t cta_mask) {
-  asm volatile(
-      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
-          smem_u32(bar)),
-      "h"(cta_mask)
-      : "memory");
-}
-
-// 1-D TMA bulk copy delivered to the same shared-memory offset (data and mbarrier) of every CTA in
-// `cta_mask` of the cluster: one L2 read feeds them all.
-__device__ __forceinline__ void tma_load_1d_multicast(void* smem_dst, const void* gmem_src, uint32_t bytes,
-                                                      uint64_t* bar, uint16_t cta_mask) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::
-          "r"(smem_u32(smem_dst)),
-      "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "h"(cta_mask)
-      : "memory");
-}
-
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-
 __device__ __forceinline__ void fence_before_sync() {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 }
