@@ -2793,11 +2793,28 @@ static int problem_solve(lorb_ba_problem* pb, const lorb_ba_options* optp, int s
       // large path: point side, then camera side and Schur products from the work lists
       if (full) LORB_LAUNCH(c, (ba_build_kernel<true, 3>), grid_pts, BA_THREADS, 0, dp, opt, force);
       else      LORB_LAUNCH(c, (ba_build_kernel<false, 3>), grid_pts, BA_THREADS, 0, dp, opt, force);
-      if (pb->max_cam_items > 0)
+      // camera rows (H_cc, g_c, Schur rhs) and Schur pairs (S) both need only the point side and write
+      // disjoint outputs; both are latency-bound gathers, so the camera rows run on a side stream
+      // beside the (six times longer) pair pass
+      const bool side = full && pb->max_cam_items > 0 && pb->max_pair_items > 0;
+      if (side) {
+        if (!c->ba_stream2) {
+          LORB_CUDA_TRY(cudaStreamCreateWithFlags(&c->ba_stream2, cudaStreamNonBlocking));
+          for (auto& e : c->ba_ev) LORB_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        }
+        LORB_CUDA_TRY(cudaEventRecord(c->ba_ev[0], c->stream));
+        LORB_CUDA_TRY(cudaStreamWaitEvent(c->ba_stream2, c->ba_ev[0], 0));
+        ba_cam_rows_kernel<<<dim3((pb->max_cam_items + 7) / 8, nw), 256, 0, c->ba_stream2>>>(dp, 1, force);
+        c->launches++;
+        LORB_CUDA_TRY(cudaGetLastError());
+        LORB_CUDA_TRY(cudaEventRecord(c->ba_ev[1], c->ba_stream2));
+      } else if (pb->max_cam_items > 0) {
         LORB_LAUNCH(c, ba_cam_rows_kernel, dim3((pb->max_cam_items + 7) / 8, nw), 256, 0, dp,
                     full ? 1 : 0, force);
+      }
       if (full && pb->max_pair_items > 0)
         LORB_LAUNCH(c, ba_schur_pairs_kernel, dim3((pb->max_pair_items + 7) / 8, nw), 256, 0, dp);
+      if (side) LORB_CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ba_ev[1], 0));
     }
 #undef LORB_BUILD
     return LORB_OK;
@@ -2926,6 +2943,14 @@ void ba_cache_free(lorb_ctx* c) {
   if (c && c->ba_cache) {
     problem_free(static_cast<lorb_ba_problem*>(c->ba_cache));
     c->ba_cache = nullptr;
+  }
+  if (c && c->ba_stream2) {
+    cudaStreamDestroy(c->ba_stream2);
+    c->ba_stream2 = nullptr;
+    for (auto& e : c->ba_ev) {
+      if (e) cudaEventDestroy(e);
+      e = nullptr;
+    }
   }
 }
 

@@ -6,6 +6,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <vector>
+
 #include "../../include/lorb_cuda.h"
 
 namespace lorb {
@@ -65,12 +67,16 @@ struct lorb_ctx {
   // row / column key scratch
   int sweep_impl = -1;  // LORB_SWEEP_POPC / LORB_SWEEP_TENSOR; -1 = default (env LORB_SWEEP_IMPL)
   lorb::Buf tc_img, tc_units, tc_keys;
-  int tc_img_n_kf = 0, tc_img_n_desc = 0, tc_n_units = 0;
+  int tc_img_n_kf = 0, tc_img_n_desc = 0;
+  long long tc_n_units = 0;
+  std::vector<long long> tc_chunk_units;  // first unit of every <= 16384-pair chunk of the plan (+ end)
   size_t tc_keys_rows = 0;
   int proj_coop_blocks[2] = {-1, -1};  // co-resident CTAs of the cooperative claim resolution (match_proj.cu)
   int chol_coop_blocks = -1;           // same for the dataflow Cholesky (ba_local.cu); 0 = not available
   lorb::Dist* dist = nullptr;
   void* ba_cache = nullptr;  // reusable lorb_ba_problem of the host-buffer BA calls (ba_local.cu)
+  cudaStream_t ba_stream2 = nullptr;  // side branch of the large-path build pass (camera rows beside the Schur pairs)
+  cudaEvent_t ba_ev[2] = {nullptr, nullptr};
   // cached CUDA graphs of the ORB extractor's detection chain (orb.cu), one per job slot
   void* orb_graph[2] = {nullptr, nullptr};
   cudaStream_t orb_stream2 = nullptr;  // side branch of the extractor graph (capture only)

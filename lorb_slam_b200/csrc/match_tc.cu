@@ -445,25 +445,35 @@ int bank_expand(lorb_ctx* c) {
 
 // Unit list of a pair plan: for every run of equal `a`, slab by slab, the pairs of the run.
 // A unit is (a, b, slab | first-of-its-(a, slab)-group << 8, pair index).
+// A launch handles at most TC_CHUNK_PAIRS keyframe pairs (its key scratch is 16 KB per pair); a longer
+// plan runs as several launches over consecutive chunks of the pair list.
+constexpr int TC_CHUNK_PAIRS = 16384;
+
 int plan_build(lorb_ctx* c, const int* pa, const int* pb, int n_pairs) {
   const int n_pad = pad_of(c->bank_n_desc), n_slabs = n_pad / SLAB_COLS;
   std::vector<int4> units;
   units.reserve((size_t)n_pairs * n_slabs);
-  for (int p0 = 0; p0 < n_pairs;) {
-    int p1 = p0 + 1;
-    while (p1 < n_pairs && pa[p1] == pa[p0]) p1++;
-    for (int s = 0; s < n_slabs; s++)
-      for (int p = p0; p < p1; p++) units.push_back(make_int4(pa[p], pb[p], s | (p == p0 ? 256 : 0), p));
-    p0 = p1;
+  c->tc_chunk_units.clear();
+  for (int c0 = 0; c0 < n_pairs; c0 += TC_CHUNK_PAIRS) {
+    const int c1 = std::min(n_pairs, c0 + TC_CHUNK_PAIRS);
+    c->tc_chunk_units.push_back((long long)units.size());
+    for (int p0 = c0; p0 < c1;) {
+      int p1 = p0 + 1;
+      while (p1 < c1 && pa[p1] == pa[p0]) p1++;
+      for (int s = 0; s < n_slabs; s++)
+        for (int p = p0; p < p1; p++) units.push_back(make_int4(pa[p], pb[p], s | (p == p0 ? 256 : 0), p - c0));
+      p0 = p1;
+    }
   }
-  c->tc_n_units = (int)units.size();
+  c->tc_chunk_units.push_back((long long)units.size());
+  c->tc_n_units = (long long)units.size();
   if (units.empty()) return LORB_OK;
   LORB_TRY(c->tc_units.reserve(units.size() * sizeof(int4)));
   LORB_CUDA_TRY(cudaMemcpyAsync(c->tc_units.p, units.data(), units.size() * sizeof(int4),
                                 cudaMemcpyHostToDevice, c->stream));
-  // row / column keys: [n_pairs][n_pad] each; the row keys start (and are left by the finalize
-  // kernel) at INT_MIN
-  const size_t keys = (size_t)n_pairs * n_pad;
+  // row / column keys of one chunk: [pairs][n_pad] each; the row keys start (and are left by the
+  // finalize kernel) at INT_MIN
+  const size_t keys = (size_t)std::min(n_pairs, TC_CHUNK_PAIRS) * n_pad;
   LORB_TRY(c->tc_keys.reserve(2 * keys * 4));
   LORB_LAUNCH(c, tc_fill_kernel, c->sm_count * 8, 256, 0, c->tc_keys.as<int>(), (long long)keys, INT_LOWEST);
   c->tc_keys_rows = keys;
@@ -479,14 +489,19 @@ int launch_sweep(lorb_ctx* c, int kf_base_a, int kf_base_b, int n_pairs, int* ou
                                      TC_SMEM_BYTES));
   int* rowkey = c->tc_keys.as<int>();
   int* colkey = rowkey + c->tc_keys_rows;
-  const int grid = std::min(c->tc_n_units, c->sm_count);
-  prof_begin(c, 3);
-  LORB_LAUNCH(c, tc_sweep_kernel, grid, TC_THREADS, TC_SMEM_BYTES,
-              c->tc_img.as<uint8_t>() + (size_t)kf_base_a * kf_bytes,
-              c->tc_img.as<uint8_t>() + (size_t)kf_base_b * kf_bytes, (long long)kf_bytes,
-              c->tc_units.as<int4>(), c->tc_n_units, n_pad / MT_ROWS, n_pad, rowkey, colkey);
-  prof_end(c, 3);
-  LORB_LAUNCH(c, tc_finalize_kernel, n_pairs, 256, 0, rowkey, colkey, n_desc, n_pad, out);
+  const int n_chunks = (int)c->tc_chunk_units.size() - 1;
+  for (int ch = 0; ch < n_chunks; ch++) {
+    const long long u0 = c->tc_chunk_units[ch], nu = c->tc_chunk_units[ch + 1] - u0;
+    const int base = ch * TC_CHUNK_PAIRS, np = std::min(n_pairs - base, TC_CHUNK_PAIRS);
+    const int grid = (int)std::min<long long>(nu, c->sm_count);
+    prof_begin(c, 3);
+    LORB_LAUNCH(c, tc_sweep_kernel, grid, TC_THREADS, TC_SMEM_BYTES,
+                c->tc_img.as<uint8_t>() + (size_t)kf_base_a * kf_bytes,
+                c->tc_img.as<uint8_t>() + (size_t)kf_base_b * kf_bytes, (long long)kf_bytes,
+                c->tc_units.as<int4>() + u0, (int)nu, n_pad / MT_ROWS, n_pad, rowkey, colkey);
+    prof_end(c, 3);
+    LORB_LAUNCH(c, tc_finalize_kernel, np, 256, 0, rowkey, colkey, n_desc, n_pad, out + 3 * (size_t)base);
+  }
   return LORB_OK;
 }
 

@@ -166,6 +166,19 @@ def test_sweep_many_pairs_resident(ctx, sweep_impl):
     assert np.array_equal(k3, o3[0]) and np.array_equal(m3, o3[1]) and np.array_equal(d3, o3[2])
 
 
+def test_sweep_long_plan(ctx, sweep_impl):
+    """A plan longer than one launch of the tensor-core kernel handles (16 384 keyframe pairs): the
+    chunks must tile the pair list without a seam, runs of equal `a` cut by a chunk border included."""
+    n_kf, n_desc = 200, 40
+    bank = synth.kf_bank(n_kf, n_desc, seed=11)
+    pa, pb = synth.all_pairs(n_kf)
+    assert len(pa) == 19900
+    ctx.bank_upload(bank)
+    kept, mt, md = ctx.match_sweep_resident(pa, pb)
+    ok, om, od = ref.sweep(bank, pa, pb)
+    assert np.array_equal(kept, ok) and np.array_equal(mt, om) and np.array_equal(md, od)
+
+
 @pytest.mark.parametrize("n_kf,blk,n_desc", [(11, 4, 300), (9, 4, 130), (8, 8, 64)])
 def test_sweep_all_tile_grid(ctx, sweep_impl, n_kf, blk, n_desc):
     """The whole sweep as a tile grid split over ranks: the union of the ranks'
