@@ -874,7 +874,8 @@ def main():
     # torchrun exports OMP_NUM_THREADS=1 to every rank: give each rank its share of the host cores
     # for the library's staging loops (the host-buffer calls of the e2e legs)
     from lorb_slam_b200 import capi as _capi
-    _capi.set_host_threads(max(1, (os.cpu_count() or 1) // max(1, world)))
+    _capi.set_host_threads(int(os.environ.get("LORB_BENCH_HOST_THREADS", 0)) or
+                           max(1, (os.cpu_count() or 1) // max(1, world)))
     if args.workload == "ba_batched":
         res = run_ba_batched(args, rank, world, local, want_cpu=want_cpu)
     elif args.workload == "ba_large":

@@ -326,24 +326,35 @@ __global__ void __launch_bounds__(256)
   const int p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   int* rk = rowkey + (size_t)p * n_pad;
   const int* ck = colkey + (size_t)p * n_pad;
-  int dd[8];
+  // the kernel is two dependent memory round trips (row key -> column -> column key): all eight
+  // row keys of a thread are fetched before the first is used, then all eight column keys
+  // (one iteration at a time this took 0.78 ms per 8128 pairs, 14 % of a sweep step)
+  int key[8], ckey[8], dd[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    const int i = tid + k * 256;
+    key[k] = i < n_pad ? __ldcg(rk + i) : INT_LOWEST;
+  }
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    const int i = tid + k * 256;
+    const int j = (KEY_OFFSET - (key[k] + i)) & 2047;  // 2048 d + j
+    ckey[k] = i < n_desc ? __ldcg(ck + j) : 0;
+  }
   int cnt = 0, lmin = 1 << 30;
 #pragma unroll
   for (int k = 0; k < 8; k++) {
     const int i = tid + k * 256;
     dd[k] = -1;
-    if (i < n_pad) {
-      const int key = rk[i];
-      rk[i] = INT_LOWEST;
-      if (i < n_desc) {
-        const int ur = KEY_OFFSET - (key + i);  // 2048 d + j
-        const int j = ur & 2047;
-        const int uc = KEY_OFFSET - (ck[j] + j);  // 2048 d' + i'
-        if ((uc & 2047) == i) {
-          dd[k] = ur >> 11;
-          cnt++;
-          lmin = min(lmin, dd[k]);
-        }
+    if (i < n_pad) rk[i] = INT_LOWEST;
+    if (i < n_desc) {
+      const int ur = KEY_OFFSET - (key[k] + i);
+      const int j = ur & 2047;
+      const int uc = KEY_OFFSET - (ckey[k] + j);  // 2048 d' + i'
+      if ((uc & 2047) == i) {
+        dd[k] = ur >> 11;
+        cnt++;
+        lmin = min(lmin, dd[k]);
       }
     }
   }
