@@ -669,6 +669,13 @@ def run_ba_batched(args, rank, world, local, steps=None, want_cpu=True):
     clocks = sampler.stop() if rank == 0 else None
     dt_max = _max_over_ranks(dt, world, local)
     cams_res, pts_res = prob.download()
+    # parity run: the same windows under Ceres' default tolerances (the timed runs force all 10
+    # attempts, and attempts past convergence accept or reject on rounding noise, which makes their
+    # end point a coin toss at the 1e-7 level -- not a fair thing to compare bit-for-tolerance)
+    popt = capi.ba_options(max_num_iterations=10)
+    prob.reset()
+    psums = prob.solve(popt)
+    pcams, ppts = prob.download()
     prob.close()
     iters = sum(s["iterations"] for s in sums) / len(sums)
     total_obs = _sum_over_ranks(float(obs), world, local)
@@ -684,19 +691,24 @@ def run_ba_batched(args, rank, world, local, steps=None, want_cpu=True):
         io["cams"][...] = bt["cams"]
         io["pts"][...] = bt["pts"]
         t0 = time.perf_counter()
-        e_cams, e_pts, _ = ctx.ba_local_batched(io, opt, inplace=True)
+        ctx.ba_local_batched(io, opt, inplace=True)
         e2e_dt += time.perf_counter() - t0
     e2e_dt = _max_over_ranks(e2e_dt, world, local)
     e2e_value = steps * total_obs * iters / e2e_dt
-    # the two paths sum their partial results with atomics (no fixed order): compare by tolerance
-    same = bool(max(_rel_err(e_cams, cams_res), _rel_err(e_pts, pts_res)) <= 1.0)
+    # the host-buffer call against the resident solve, same default-tolerance options (the two sum their
+    # partial results with atomics in no fixed order: compared by tolerance, not by bits)
+    io["cams"][...] = bt["cams"]
+    io["pts"][...] = bt["pts"]
+    e_cams, e_pts, _ = ctx.ba_local_batched(io, popt, inplace=True)
+    same = bool(max(_rel_err(e_cams, pcams), _rel_err(e_pts, ppts)) <= 1.0)
     res = None
     if rank == 0:
         from oracle import ref
-        # parity inside the run: the first window of this rank against the oracle, full length
-        oc, op, so = ref.ba_local(pbs[0], _ba_opts_fixed_iters(ref))
-        pc, pp = cams_res[:10], pts_res[:pbs[0]["P"]]
+        # parity inside the run: the first window of this rank against the oracle
+        oc, op, so = ref.ba_local(pbs[0], ref.ba_options(max_num_iterations=10))
+        pc, pp = pcams[:10], ppts[:pbs[0]["P"]]
         err = max(_rel_err(pc, oc), _rel_err(pp, op))
+        sums = psums
         res = {"metric": "BA observations/s per LM iter", "value": value,
                "unit": "observations*iterations/s", "n_gpus": world, "steps": steps,
                "warmup": warmup, "ms_per_step": dt_max / steps * 1e3,
@@ -718,12 +730,14 @@ def run_ba_batched(args, rank, world, local, steps=None, want_cpu=True):
                "ms_per_local_ba": dt_max / steps / nw * 1e3, "lm_iterations": iters,
                "parity": {"ok": bool(err <= 1.0 and same), "max_err_over_tolerance": err,
                           "tolerance": "rtol 1e-6 + atol 1e-8 on final cameras and points",
-                          "checked": "window %d (rank 0) against the oracle after 10 LM iterations; "
-                                     "host-buffer call == resident solve within the same tolerance: %s" % (lo, same),
-                          "lm_steps_ok_rejected": {"gpu": [sums[0]["num_successful_steps"], sums[0]["num_unsuccessful_steps"]],
-                                                   "oracle": [so["num_successful_steps"], so["num_unsuccessful_steps"]],
-                                                   "note": "tolerances are off (10 attempts forced): attempts past "
-                                                           "convergence accept or reject on rounding noise"}}}
+                          "checked": "window %d (rank 0) against the oracle, Ceres' default tolerances, at most 10 "
+                                     "LM iterations (the timed runs force all 10 attempts); host-buffer call == "
+                                     "resident solve within the same tolerance: %s" % (lo, same),
+                          "lm_iterations_ok_rejected_termination": {
+                              "gpu": [sums[0]["iterations"], sums[0]["num_successful_steps"],
+                                      sums[0]["num_unsuccessful_steps"], sums[0]["termination"]],
+                              "oracle": [so["iterations"], so["num_successful_steps"],
+                                         so["num_unsuccessful_steps"], so["termination"]]}}}
         res["roofline"], res["roofline_hbm"] = _ba_rooflines(ctx, obs, 6.0, 60, prof, "ba_build_dense_kernel")
         if world == 1 and want_cpu:
             res["cpu_baseline"] = cpu_baseline_ba_batched(pbs)
@@ -779,16 +793,23 @@ def run_ba_large(args, rank, world, local, steps=None, want_cpu=True):
     cams_res, pts_res = prob.download()
     # ---- parity inside the run: the un-sharded solve of the whole problem on rank 0 (at world 1: the
     # sharded code path over a one-rank communicator) must give the same cameras / points
+    # Both sides run under Ceres' default tolerances (at most 10 iterations): the timed runs force all 10
+    # attempts, and attempts past convergence accept or reject on rounding noise.
+    popt = capi.ba_options(max_num_iterations=10)
+    prob.reset()
+    sp = prob.solve(popt, sharded=sharded)
+    cams_res, pts_res = prob.download()
     parity = None
     if world == 1:
         prob.reset()
-        s2 = prob.solve(opt, sharded=True)
+        s2 = prob.solve(popt, sharded=True)
         c2, p2 = prob.download()
         err = max(_rel_err(c2, cams_res), _rel_err(p2, pts_res))
-        parity = {"ok": bool(err <= 1.0 and s2["iterations"] == s["iterations"]), "max_err_over_tolerance": err,
+        parity = {"ok": bool(err <= 1.0 and s2["iterations"] == sp["iterations"]), "max_err_over_tolerance": err,
                   "tolerance": "rtol 1e-6 + atol 1e-8 on final cameras and points",
-                  "checked": "sharded code path (one-rank NCCL communicator) against the plain solve, "
-                             "%d LM iterations, final cost %.9g vs %.9g" % (s["iterations"], s2["final_cost"], s["final_cost"])}
+                  "checked": "sharded code path (one-rank NCCL communicator) against the plain solve, default "
+                             "tolerances, %d vs %d LM iterations, final cost %.9g vs %.9g"
+                             % (s2["iterations"], sp["iterations"], s2["final_cost"], sp["final_cost"])}
     prob.close()
     if world > 1:
         camt = torch.from_numpy(cams_res).cuda()
@@ -798,16 +819,17 @@ def run_ba_large(args, rank, world, local, steps=None, want_cpu=True):
         dist.all_reduce(same_cams, op=dist.ReduceOp.MIN)
         if rank == 0:
             full = ctx.ba_problem(pb)
-            s1 = full.solve(opt)
+            s1 = full.solve(popt)
             c1, p1 = full.download()
             full.close()
             err = max(_rel_err(cams_res, c1), _rel_err(pts_res, p1[sh["point_ids"]]))
-            parity = {"ok": bool(err <= 1.0 and same_cams.item() == 1.0 and s1["iterations"] == s["iterations"]),
+            parity = {"ok": bool(err <= 1.0 and same_cams.item() == 1.0 and s1["iterations"] == sp["iterations"]),
                       "max_err_over_tolerance": err,
                       "tolerance": "rtol 1e-6 + atol 1e-8 on final cameras and rank 0's points",
                       "cameras_bit_identical_across_ranks": bool(same_cams.item() == 1.0),
                       "checked": "%d-rank sharded solve against the one-GPU solve of the whole problem on rank 0, "
-                                 "final cost %.9g vs %.9g" % (world, s["final_cost"], s1["final_cost"])}
+                                 "default tolerances, %d vs %d LM iterations, final cost %.9g vs %.9g"
+                                 % (world, sp["iterations"], s1["iterations"], sp["final_cost"], s1["final_cost"])}
     # ---- e2e: the host-buffer call every step (upload, device work lists, solve, download): lorb_ba_local
     # on one GPU, lorb_ba_local_shard (this rank's shard, collective) on several.
     _barrier(world)

@@ -1565,6 +1565,308 @@ __global__ void __launch_bounds__(256)
   if (tid == 0 && !s_ok) st->solve_ok = 0;
 }
 
+// ---- dataflow tiled Cholesky, chain form (n > 96, one window): ONE cooperative launch.
+// The factorisation's critical path is POTRF(j) -> TRSM(j+1, j) -> last update of (j+1, j+1) ->
+// POTRF(j+1).  In ba_chol_dataflow_kernel those three steps belong to three different CTAs, so a
+// block column costs two publish / consume hops through global memory and two tile reloads on top
+// of the arithmetic.  Here CTA 0 walks the whole chain with L_jj and L_(j+1)j staying in its shared
+// memory, and every other CTA is a helper working through a list of items in column order:
+//   * normal tiles (i, j), i >= j + 2: left-looking accumulation, TRSM against L_jj (as before);
+//   * the "sub partial" of column j: S(j+1, j) - sum_{k<j} L(j+1, k) L(j, k)^T, left in place for
+//     the chain CTA, which only has to apply L_jj^-T;
+//   * the "diagonal partial" of block d = j + 1: S(d, d) - sum_{k<=d-2} L(d, k) L(d, k)^T and the
+//     forward-substitution partial b_d - sum_{k<=d-2} L(d, k) y_k; the chain CTA subtracts the
+//     k = d - 1 term, whose tile it has just produced itself.
+// Item numbers grow with the column; an item depends only on smaller items and on chain output of
+// earlier columns, the chain on partials of smaller items: no deadlock while all CTAs are resident.
+__global__ void __launch_bounds__(256)
+    ba_chol_chain_kernel(const BADev* __restrict__ probs, int* __restrict__ flags, int* __restrict__ yflag,
+                         int* __restrict__ pflag /* [2T]: sub partial of column j, diagonal partial of block j */,
+                         double* __restrict__ ypart /* [T][32] */, int T) {
+  const BADev p = probs[0];
+  LMState* st = p.st;
+  if (st->done) return;
+  __shared__ double A[NB][NB + 1];
+  __shared__ double B[NB][NB + 1];
+  __shared__ double X[NB][NB + 1];
+  __shared__ double idg[NB];
+  __shared__ double sk[NB], vec[NB];
+  __shared__ int s_ok;
+  const int n = p.n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ty = tid >> 4, tx = tid & 15;
+  int* sflag = pflag;
+  int* dflag = pflag + T;
+  if (tid == 0) s_ok = 1;
+  __syncthreads();
+  auto publish = [&](int* f) {  // every thread has written its part: fence, barrier, one flag store
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) atomicExch(f, 1);
+  };
+  if (blockIdx.x == 0) {
+    // ================= the chain
+    __shared__ double Dn[NB][NB + 1];  // next diagonal partial, fetched by idle warps during POTRF
+    __shared__ double skn[NB];
+    __shared__ int have_next;
+    if (tid == 0) have_next = 0;
+    __syncthreads();
+    for (int j = 0; j < T; j++) {
+      const int j0 = j * NB, s0 = (j + 1) * NB;
+      const bool pre = have_next != 0;  // uniform: written before the last barrier of the previous column
+      if (j >= 2 && !pre) flag_wait(&dflag[j]);
+      // diagonal tile (partial) minus this CTA's own last term X X^T (X = L_j(j-1), still in X)
+      double acc[2][2];
+#pragma unroll
+      for (int a = 0; a < 2; a++)
+#pragma unroll
+        for (int b = 0; b < 2; b++) {
+          const int r = j0 + 2 * ty + a, c = j0 + 2 * tx + b;
+          if (pre)
+            acc[a][b] = Dn[2 * ty + a][2 * tx + b];
+          else
+            acc[a][b] = (r < n && c < n) ? __ldcg(&p.S[(size_t)r * n + c]) : (r == c ? 1.0 : 0.0);
+        }
+      {
+        // running right-hand side of the forward substitution: (partial) - X y_(j-1), 8 lanes per row
+        const int r = tid >> 3, sub8 = tid & 7;
+        double a2 = 0;
+        if (j >= 1) {
+#pragma unroll
+          for (int m = sub8; m < NB; m += 8) a2 += X[r][m] * vec[m];  // vec = y_(j-1)
+        }
+        a2 += __shfl_xor_sync(0xffffffffu, a2, 4);
+        a2 += __shfl_xor_sync(0xffffffffu, a2, 2);
+        a2 += __shfl_xor_sync(0xffffffffu, a2, 1);
+        if (sub8 == 0) {
+          double b0;
+          if (pre)
+            b0 = skn[r];
+          else
+            b0 = j0 + r < n ? (j >= 2 ? __ldcg(&ypart[j * NB + r]) : __ldcg(&p.rhs[j0 + r])) : 0.0;
+          sk[r] = b0 - a2;
+        }
+      }
+      if (j >= 1) {
+#pragma unroll 8
+        for (int m = 0; m < NB; m++) {
+          const double a0 = X[2 * ty][m], a1 = X[2 * ty + 1][m];
+          const double b0 = X[2 * tx][m], b1 = X[2 * tx + 1][m];
+          acc[0][0] -= a0 * b0;
+          acc[0][1] -= a0 * b1;
+          acc[1][0] -= a1 * b0;
+          acc[1][1] -= a1 * b1;
+        }
+      }
+      __syncthreads();  // X, vec, Dn, skn and have_next have been read
+      if (tid == 0) have_next = 0;
+#pragma unroll
+      for (int a = 0; a < 2; a++)
+#pragma unroll
+        for (int b = 0; b < 2; b++) A[2 * ty + a][2 * tx + b] = acc[a][b];
+      // meanwhile: the sub partial of this column into registers (needed right after POTRF)
+      const bool sub = j + 1 < T;
+      __syncthreads();
+      if (tid < 32) {
+        potrf32_warp(A, idg, &s_ok, tid);
+      } else if (warp == 2 || warp == 3) {
+        // if the next diagonal partial is already there, take it now (no waiting here: these warps
+        // are needed again as soon as the factorisation is done)
+        if (sub) {
+          const int jn = j + 1, jn0 = jn * NB;
+          int ready = 1;
+          if (jn >= 2) ready = *reinterpret_cast<const volatile int*>(&dflag[jn]);
+          ready = __shfl_sync(0xffffffffu, ready, 0);
+          if (ready) {
+            __threadfence();
+            for (int q = 0; q < 16; q++) {
+              const int r = (warp - 2) * 16 + q;
+              const int gr = jn0 + r, gc = jn0 + lane;
+              Dn[r][lane] = (gr < n && gc < n) ? __ldcg(&p.S[(size_t)gr * n + gc]) : (gr == gc ? 1.0 : 0.0);
+            }
+            if (warp == 2)
+              skn[lane] = jn0 + lane < n ? (jn >= 2 ? __ldcg(&ypart[jn * NB + lane]) : __ldcg(&p.rhs[jn0 + lane])) : 0.0;
+            if (warp == 3 && lane == 0) have_next = 1;
+          }
+        }
+      } else if (sub && warp >= 4) {
+        // warps 4..7 fetch the sub partial while warp 0 factorises (lane = column, 8 rows per warp)
+        if (j >= 1 && lane == 0) {
+          while (*reinterpret_cast<const volatile int*>(&sflag[j]) == 0) {
+          }
+          __threadfence();
+        }
+        __syncwarp();
+        for (int q = 0; q < 8; q++) {
+          const int r = (warp - 4) * 8 + q;
+          X[r][lane] = (s0 + r < n && j0 + lane < n) ? __ldcg(&p.S[(size_t)(s0 + r) * n + j0 + lane]) : 0.0;
+        }
+      }
+      __syncthreads();
+      // L_jj is final: warp 0 goes on to X L_jj^T = (sub partial), warp 1 finishes y_j, the others publish L_jj
+      if (tid < 32) {
+        if (sub) trsm32_warp(X, A, idg, tid);
+      } else if (warp == 1) {
+        double v = sk[lane];
+#pragma unroll 8
+        for (int c = 0; c < NB; c++) {
+          const double yc = __shfl_sync(0xffffffffu, v, c) * idg[c];
+          if (lane == c) v = yc;
+          if (lane > c) v -= A[c][lane] * yc;
+        }
+        vec[lane] = v;  // y_j, used by the next column
+        if (j0 + lane < n) p.rhs[j0 + lane] = v;
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) atomicExch(&yflag[j], 1);
+      } else {
+        for (int e = tid - 64; e < NB * NB; e += 192) {
+          const int r = e >> 5, c = e & 31;
+          if (j0 + r < n && c < r) p.S[(size_t)(j0 + r) * n + j0 + c] = A[c][r];
+        }
+        if (tid - 64 < NB) {
+          const int d = tid - 64;
+          if (j0 + d < n) p.S[(size_t)(j0 + d) * n + j0 + d] = 1.0 / idg[d];
+          p.dinv[(size_t)j * NB + d] = idg[d];
+        }
+        __threadfence();
+      }
+      __syncthreads();
+      if (tid == 0) atomicExch(&flags[j * T + j], 1);
+      if (sub) {
+        for (int e = tid; e < NB * NB; e += 256) {
+          const int r = e >> 5, c = e & 31;
+          if (s0 + r < n && j0 + c < n) p.S[(size_t)(s0 + r) * n + j0 + c] = X[r][c];
+        }
+        publish(&flags[(j + 1) * T + j]);
+      }
+    }
+    __syncthreads();
+    if (tid == 0 && !s_ok) st->solve_ok = 0;
+    return;
+  }
+  // ================= helpers: items in column order, dealt round-robin to CTAs 1 .. gridDim.x - 1
+  const int n_help = (int)gridDim.x - 1;
+  int g = 0, g_start = 0;  // column group of the current item and the number of its first item
+  auto group_items = [&](int gg) {
+    const int extra = (gg >= 1 && gg + 1 < T) ? 2 : 0;  // sub partial (gg+1, gg) and diagonal partial of block gg+1
+    return extra + max(0, T - gg - 2);
+  };
+  int total = 0;
+  for (int gg = 0; gg < T; gg++) total += group_items(gg);
+  for (int t = (int)blockIdx.x - 1; t < total; t += n_help) {
+    while (t >= g_start + group_items(g)) {
+      g_start += group_items(g);
+      g++;
+    }
+    const int local = t - g_start;
+    const bool has_extra = g >= 1 && g + 1 < T;
+    // kind 0: normal tile (i, g); 1: sub partial (g+1, g); 2: diagonal partial of block g+1
+    int kind = 0, i = 0, j = g, kmax = g;
+    if (has_extra && local == 0) {
+      kind = 1;
+      i = g + 1;
+    } else if (has_extra && local == 1) {
+      kind = 2;
+      i = j = g + 1;
+      kmax = g;  // k <= (g+1) - 2 = g - 1, i.e. k < g
+    } else {
+      i = g + 2 + (local - (has_extra ? 2 : 0));
+    }
+    const int i0 = i * NB, j0 = j * NB;
+    const bool ywarp = kind == 2 && warp == 1;
+    double skreg = (ywarp && i0 + lane < n) ? __ldcg(&p.rhs[i0 + lane]) : 0.0, yreg = 0.0;
+    double acc[2][2];
+#pragma unroll
+    for (int a = 0; a < 2; a++)
+#pragma unroll
+      for (int b = 0; b < 2; b++) {
+        const int r = i0 + 2 * ty + a, c = j0 + 2 * tx + b;
+        acc[a][b] = (r < n && c < n) ? __ldcg(&p.S[(size_t)r * n + c]) : (r == c ? 1.0 : 0.0);
+      }
+    for (int k = 0; k < kmax; k++) {
+      flag_wait(&flags[i * T + k]);
+      if (i != j) flag_wait(&flags[j * T + k]);
+      const int k0 = k * NB;
+      if (ywarp) {
+        if (lane == 0) {
+          while (*reinterpret_cast<const volatile int*>(&yflag[k]) == 0) {
+          }
+          __threadfence();
+        }
+        __syncwarp();
+        yreg = __ldcg(&p.rhs[k0 + lane]);
+      }
+      {
+        double ta[4], tb[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const int e = tid + 256 * q, r = e >> 5, c = e & 31;
+          ta[q] = (i0 + r < n) ? __ldcg(&p.S[(size_t)(i0 + r) * n + k0 + c]) : 0.0;
+          tb[q] = (j0 + r < n) ? __ldcg(&p.S[(size_t)(j0 + r) * n + k0 + c]) : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const int e = tid + 256 * q, r = e >> 5, c = e & 31;
+          A[r][c] = ta[q];
+          B[r][c] = tb[q];
+        }
+      }
+      __syncthreads();
+      if (ywarp) {
+        vec[lane] = yreg;
+        __syncwarp();
+        double a2 = 0;
+#pragma unroll 8
+        for (int m = 0; m < NB; m++) a2 += A[lane][m] * vec[m];
+        skreg -= a2;
+        __syncwarp();
+      }
+#pragma unroll 8
+      for (int m = 0; m < NB; m++) {
+        const double a0 = A[2 * ty][m], a1 = A[2 * ty + 1][m];
+        const double b0 = B[2 * tx][m], b1 = B[2 * tx + 1][m];
+        acc[0][0] -= a0 * b0;
+        acc[0][1] -= a0 * b1;
+        acc[1][0] -= a1 * b0;
+        acc[1][1] -= a1 * b1;
+      }
+      __syncthreads();
+    }
+    if (kind != 0) {
+      // partials go back in place (the chain CTA finishes them)
+#pragma unroll
+      for (int a = 0; a < 2; a++)
+#pragma unroll
+        for (int b = 0; b < 2; b++) {
+          const int r = i0 + 2 * ty + a, c = j0 + 2 * tx + b;
+          if (r < n && c < n && (kind == 1 || c <= r)) p.S[(size_t)r * n + c] = acc[a][b];
+        }
+      if (ywarp) ypart[i * NB + lane] = skreg;
+      publish(kind == 1 ? &sflag[g] : &dflag[i]);
+      continue;
+    }
+#pragma unroll
+    for (int a = 0; a < 2; a++)
+#pragma unroll
+      for (int b = 0; b < 2; b++) A[2 * ty + a][2 * tx + b] = acc[a][b];
+    flag_wait(&flags[j * T + j]);
+    for (int e = tid; e < NB * NB; e += 256) {
+      const int r = e >> 5, c = e & 31;  // B[m][c] = L_cm for m < c
+      B[c][r] = (r > c && j0 + r < n) ? __ldcg(&p.S[(size_t)(j0 + r) * n + j0 + c]) : 0.0;
+    }
+    if (tid < NB) idg[tid] = __ldcg(&p.dinv[(size_t)j * NB + tid]);
+    __syncthreads();
+    if (tid < 32) trsm32_warp(A, B, idg, tid);
+    __syncthreads();
+    for (int e = tid; e < NB * NB; e += 256) {
+      const int r = e >> 5, c = e & 31;
+      if (i0 + r < n && j0 + c < n) p.S[(size_t)(i0 + r) * n + j0 + c] = A[r][c];
+    }
+    publish(&flags[i * T + j]);
+    __syncthreads();
+  }
+}
+
 // ---- dataflow triangular solves (one cooperative launch, one CTA per block row).
 // Forward: CTA k accumulates b_k - sum_{j<k} L_kj y_j as the y_j are flagged ready
 // (tile loads are issued before the flag wait: the factor is complete), solves its
@@ -2683,21 +2985,39 @@ static int run_cholesky(lorb_ba_problem* pb) {
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ba_chol_dataflow_kernel, 256, 0);
     const char* e = getenv("LORB_CHOL_DATAFLOW");
     c->chol_coop_blocks = (dev_coop && per_sm > 0 && !(e && atoi(e) == 0)) ? per_sm * c->sm_count : 0;
+    int per_sm2 = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, ba_chol_chain_kernel, 256, 0);
+    c->chol_chain_blocks = per_sm2 * c->sm_count;
   }
   const int coop_blocks = c->chol_coop_blocks;
   const bool coop_ok = coop_blocks > 0;
   // (one CTA per block row of the solve must be co-resident as well)
   if (coop_ok && nw == 1 && nblk <= c->sm_count) {
     const int n_tiles = nblk * (nblk + 1) / 2;
-    LORB_TRY(dev_reserve(c, 14, ((size_t)nblk * nblk + 2 * (size_t)nblk) * 4));
+    // tile flags [T*T], y / x flags [2T], partial flags [2T] (chain form), forward-substitution partials [T][32]
+    const size_t flag_ints = (size_t)nblk * nblk + 4 * (size_t)nblk + 2;
+    LORB_TRY(dev_reserve(c, 14, flag_ints * 4 + (size_t)nblk * NB * 8));
     int* flags = c->d[14].as<int>();
-    LORB_CUDA_TRY(cudaMemsetAsync(flags, 0, ((size_t)nblk * nblk + 2 * (size_t)nblk) * 4, c->stream));
+    LORB_CUDA_TRY(cudaMemsetAsync(flags, 0, flag_ints * 4, c->stream));
     int T = nblk;
     int* sflags = flags + (size_t)nblk * nblk;  // y flags [T], x flags [T]
-    void* args[] = {(void*)&dp, (void*)&flags, (void*)&sflags, (void*)&T};
-    LORB_CUDA_TRY(cudaLaunchCooperativeKernel((void*)ba_chol_dataflow_kernel,
-                                              dim3(std::min(n_tiles, coop_blocks)), dim3(256), args, 0,
-                                              c->stream));
+    static const int chain_env = [] {
+      const char* e = getenv("LORB_CHOL_CHAIN");  // 0: the round-robin dataflow kernel (no dedicated chain CTA)
+      return e ? atoi(e) : 1;
+    }();
+    if (chain_env) {
+      int* pflag = sflags + 2 * (size_t)nblk;
+      double* ypart = reinterpret_cast<double*>(flags + (((size_t)nblk * nblk + 4 * (size_t)nblk + 1) & ~(size_t)1));
+      void* cargs[] = {(void*)&dp, (void*)&flags, (void*)&sflags, (void*)&pflag, (void*)&ypart, (void*)&T};
+      LORB_CUDA_TRY(cudaLaunchCooperativeKernel((void*)ba_chol_chain_kernel,
+                                                dim3(std::min(n_tiles + 1, c->chol_chain_blocks)), dim3(256), cargs, 0,
+                                                c->stream));
+    } else {
+      void* args[] = {(void*)&dp, (void*)&flags, (void*)&sflags, (void*)&T};
+      LORB_CUDA_TRY(cudaLaunchCooperativeKernel((void*)ba_chol_dataflow_kernel,
+                                                dim3(std::min(n_tiles, coop_blocks)), dim3(256), args, 0,
+                                                c->stream));
+    }
     c->launches++;
     int fwd_done = 1;  // the factorisation kernel also ran the forward substitution
     void* args2[] = {(void*)&dp, (void*)&sflags, (void*)&T, (void*)&fwd_done};

@@ -73,6 +73,7 @@ struct lorb_ctx {
   size_t tc_keys_rows = 0;
   int proj_coop_blocks[2] = {-1, -1};  // co-resident CTAs of the cooperative claim resolution (match_proj.cu)
   int chol_coop_blocks = -1;           // same for the dataflow Cholesky (ba_local.cu); 0 = not available
+  int chol_chain_blocks = 0;           // and for its chain form
   lorb::Dist* dist = nullptr;
   void* ba_cache = nullptr;  // reusable lorb_ba_problem of the host-buffer BA calls (ba_local.cu)
   cudaStream_t ba_stream2 = nullptr;  // side branch of the large-path build pass (camera rows beside the Schur pairs)
