@@ -879,12 +879,35 @@ int lorb_match_sweep_all(lorb_ctx* c, int block_kf, int rank, int world, int* ou
   for (int t = 0; t < n_tiles; t++) order[t] = t;
   std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return shape(x) > shape(y); });
   long long done = 0, cur_shape = -1;
-  std::vector<int> pa, pb, kept;
-  for (int k = 0; k < n_tiles; k++) {
-    const int t = order[k];
+  std::vector<int> pa, pb;
+  // Results come back through two pinned buffers: the copy of tile k is queued behind its kernels, the
+  // kernels of tile k+1 behind the copy, and the host scatters tile k while the GPU runs tile k+1.
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  for (auto& e : ev) LORB_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  struct Pending {
+    int base_a, base_b, n;
+    std::vector<int> pa, pb;
+  } pend[2];
+  pend[0].n = pend[1].n = 0;
+  auto scatter = [&](int slot) -> int {
+    Pending& P = pend[slot];
+    if (P.n == 0) return LORB_OK;
+    LORB_CUDA_TRY(cudaEventSynchronize(ev[slot]));
+    const int* r = c->h[5 + slot].as<int>();
+    for (int i = 0; i < P.n; i++)
+      out_kept[lorb_sweep_pair_index(n_kf, P.base_a + P.pa[i], P.base_b + P.pb[i])] = r[3 * (size_t)i];
+    done += P.n;
+    P.n = 0;
+    return LORB_OK;
+  };
+  int rc = LORB_OK;
+  for (int k = 0; k < n_tiles && rc == LORB_OK; k++) {
+    const int t = order[k], slot = k & 1;
     const int na = std::min(block_kf, n_kf - bi[t] * block_kf), nb = std::min(block_kf, n_kf - bj[t] * block_kf);
     const bool diag = bi[t] == bj[t];
     if (shape(t) != cur_shape) {
+      // a new plan overwrites the device pair list: drain what is in flight first
+      if ((rc = scatter(0)) != LORB_OK || (rc = scatter(1)) != LORB_OK) break;
       pa.clear();
       pb.clear();
       for (int a = 0; a < na; a++)
@@ -892,17 +915,31 @@ int lorb_match_sweep_all(lorb_ctx* c, int block_kf, int rank, int world, int* ou
           pa.push_back(a);
           pb.push_back(b);
         }
-      LORB_TRY(lorb_sweep_plan_upload(c, pa.data(), pb.data(), (int)pa.size()));
-      kept.resize(pa.size());
+      if ((rc = lorb_sweep_plan_upload(c, pa.data(), pb.data(), (int)pa.size())) != LORB_OK) break;
       cur_shape = shape(t);
     }
-    const int base_a = bi[t] * block_kf, base_b = bj[t] * block_kf;
-    LORB_TRY(lorb_sweep_plan_run_at2(c, base_a, base_b));
-    LORB_TRY(lorb_sweep_plan_download(c, kept.data(), nullptr, nullptr));
-    for (size_t i = 0; i < pa.size(); i++)
-      out_kept[lorb_sweep_pair_index(n_kf, base_a + pa[i], base_b + pb[i])] = kept[i];
-    done += (long long)pa.size();
+    if ((rc = scatter(slot)) != LORB_OK) break;  // the buffer of tile k-2
+    const int base_a = bi[t] * block_kf, base_b = bj[t] * block_kf, n = (int)pa.size();
+    if ((rc = lorb_sweep_plan_run_at2(c, base_a, base_b)) != LORB_OK) break;
+    if ((rc = pin_reserve(c, 5 + slot, (size_t)n * 12)) != LORB_OK) break;
+    if (cudaMemcpyAsync(c->h[5 + slot].p, c->plan_out.p, (size_t)n * 12, cudaMemcpyDeviceToHost, c->stream) !=
+            cudaSuccess ||
+        cudaEventRecord(ev[slot], c->stream) != cudaSuccess) {
+      set_error("sweep: result copy failed");
+      rc = LORB_ERR_CUDA;
+      break;
+    }
+    pend[slot].base_a = base_a;
+    pend[slot].base_b = base_b;
+    pend[slot].n = n;
+    pend[slot].pa = pa;
+    pend[slot].pb = pb;
   }
+  if (rc == LORB_OK) rc = scatter(0);
+  if (rc == LORB_OK) rc = scatter(1);
+  cudaStreamSynchronize(c->stream);
+  for (auto& e : ev) cudaEventDestroy(e);
+  if (rc != LORB_OK) return rc;
   if (n_pairs_done) *n_pairs_done = done;
   return LORB_OK;
 }

@@ -117,10 +117,6 @@ __device__ __forceinline__ void mbar_wait_parity(uint64_t* bar, uint32_t parity)
   }
 }
 
-__device__ __forceinline__ void named_bar_sync(int id, int threads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
-}
-
 template <int REGS>
 __device__ __forceinline__ void reg_dec() {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS));
