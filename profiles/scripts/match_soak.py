@@ -9,7 +9,7 @@ from oracle import ref, reflib  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 40
 rng = np.random.default_rng(31)
-bad = {"proj_points": 0, "proj_frame": 0, "bf": 0, "frustum": 0, "stereo": 0}
+bad = {"proj_points": 0, "proj_frame": 0, "bf": 0, "frustum": 0, "stereo": 0, "sweep_tensor": 0, "sweep_popc": 0}
 with capi.Context(0) as ctx:
     for s in range(n):
         nk, npt = int(rng.integers(50, 3000)), int(rng.integers(50, 6000))
@@ -37,4 +37,22 @@ with capi.Context(0) as ctx:
         st = synth.make_stereo_pair(int(rng.integers(100, 2500)), 1000 + s)
         a, b = ctx.stereo_matches(st), reflib.stereo_matches(st)
         bad["stereo"] += not (a["n_matched"] == b["n_matched"] and np.array_equal(a["uright"], b["uright"]) and np.array_equal(a["depth"], b["depth"]))
+        # keyframe-pair sweep, both kernels: random bank shape, random (repeated, unordered, self) pairs;
+        # every third bank is low-entropy (ties everywhere), every third has near-duplicate keyframes
+        n_kf, n_desc = int(rng.integers(2, 12)), int(rng.choice([1, 2, 31, 128, 255, 256, 257, 2047, 2048, int(rng.integers(1, 2049))]))
+        if s % 3 == 0:
+            bank = np.stack([synth.descriptors_tie_stress(n_desc, rng, int(rng.integers(1, 4)), int(rng.integers(2, 5))) for _ in range(n_kf)])
+        elif s % 3 == 1:
+            base = synth.descriptors_uniform(n_desc, rng)
+            bank = np.stack([synth.descriptors_noisy_copy(base[rng.permutation(n_desc)], rng, 0.03) for _ in range(n_kf)])
+        else:
+            bank = synth.kf_bank(n_kf, n_desc, seed=1100 + s)
+        npair = int(rng.integers(1, 40))
+        pa, pb = rng.integers(0, n_kf, npair).astype(np.int32), rng.integers(0, n_kf, npair).astype(np.int32)
+        want = ref.sweep(bank, pa, pb)
+        for impl in ("tensor", "popc"):
+            ctx.sweep_set_impl(impl)
+            got = ctx.match_sweep(bank, pa, pb)
+            bad["sweep_" + impl] += not all(np.array_equal(g, w) for g, w in zip(got, want))
+        ctx.sweep_set_impl("tensor")
 print(n, "rounds; mismatches:", bad)
