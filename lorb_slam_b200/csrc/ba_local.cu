@@ -151,6 +151,52 @@ __device__ __forceinline__ int eval_obs(const BADev& p, const double* __restrict
   return cam;
 }
 
+// Small windows keep their cameras in shared memory: the lanes of a warp evaluate observations of
+// up to 32 different (point, camera) pairs, so every load of camera data from global memory costs
+// one L1 wavefront per distinct camera (ncu: l1tex 50 % busy on 45 such loads per observation).
+// Layout per camera, CS_BUILD doubles: [0,36) R and dR, [36,39) t, [39,45) Jacobi scale; the
+// back-substitution appends [45,51) the camera step, [51,60) R and [60,63) t of the candidate.  Both
+// strides are odd, so the <= 16 cameras of a window start on distinct even banks and a warp-wide
+// load is conflict free (lanes on the same camera broadcast).
+constexpr int CS_BUILD = 45, CS_BACKSUB = 63, CS_MAX_CAMS = 16;
+
+__device__ __forceinline__ void cs_fill(const BADev& p, const double* __restrict__ cams,
+                                        const double* __restrict__ camrot, double* __restrict__ cs, int stride,
+                                        int tid, int nthreads) {
+  for (int i = tid; i < p.C * CS_BUILD; i += nthreads) {
+    const int c = i / CS_BUILD, k = i - c * CS_BUILD;
+    cs[c * stride + k] = k < 36 ? camrot[CAMROT * c + k] : k < 39 ? cams[6 * c + 3 + (k - 36)] : p.scale_c[6 * c + (k - 39)];
+  }
+}
+
+// eval_obs with the window's cameras in shared memory (same arithmetic, same order).
+__device__ __forceinline__ int eval_obs_cs(const BADev& p, const double* __restrict__ cs, int stride, int o,
+                                           const double X[3], const double sp[3], double r[2], double Jc[12],
+                                           double Jp[6]) {
+  const int cam = p.obs_cam[o];
+  const float2 uv = p.obs_uv[o];
+  if (cam >= 0) {
+    const double* cc = cs + cam * stride;
+    const double tt[3] = {cc[36], cc[37], cc[38]};
+    obs_eval<true, true>(cc, tt, X, p.K, (double)uv.x, (double)uv.y, r, Jc, Jp);
+#pragma unroll
+    for (int a = 0; a < 6; a++) {
+      Jc[a] *= cc[39 + a];
+      Jc[6 + a] *= cc[39 + a];
+    }
+  } else {
+    const double* f = p.fixrt + 12 * (size_t)(-1 - cam);
+    const double tt[3] = {f[9], f[10], f[11]};
+    obs_eval<false, true>(f, tt, X, p.K, (double)uv.x, (double)uv.y, r, Jc, Jp);
+  }
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+    Jp[a] *= sp[a];
+    Jp[3 + a] *= sp[a];
+  }
+  return cam;
+}
+
 __device__ __forceinline__ double group_sum8(double v) {
   v += __shfl_xor_sync(0xffffffffu, v, 4, 8);
   v += __shfl_xor_sync(0xffffffffu, v, 2, 8);
@@ -531,6 +577,7 @@ __global__ void __launch_bounds__(DP_THREADS)
   LMState* st = p.st;
   if (st->done && !force) return;
   __shared__ double red[DP_THREADS / 32];
+  __shared__ double cs[CS_MAX_CAMS * CS_BUILD];  // the window's cameras (6C <= 64: at most 10)
   extern __shared__ __align__(16) double dsm[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, gl = lane & 7, gw = lane >> 3;
   const int pair = warp >> 1, half = warp & 1, ptid = tid & 63;
@@ -547,6 +594,8 @@ __global__ void __launch_bounds__(DP_THREADS)
   const double* camrot = p.camrot[cur];
   const double radius = st->radius;
   const int n = p.n;
+  cs_fill(p, cams, camrot, cs, CS_BUILD, tid, DP_THREADS);
+  __syncthreads();
   double cost_acc = 0, gmax_acc = 0, xn_acc = 0, bad_acc = 0;
   double sacc[18][2], hacc[7][2], gown = 0.0, rown = 0.0;
 #pragma unroll
@@ -579,7 +628,7 @@ __global__ void __launch_bounds__(DP_THREADS)
       const int o = s + rd * 8 + gl;
       has = o < e;
       if (has) {
-        cam = eval_obs(p, cams, camrot, o, X, sp, r, Jc, Jp);
+        cam = eval_obs_cs(p, cs, CS_BUILD, o, X, sp, r, Jc, Jp);
         cost_acc += r[0] * r[0] + r[1] * r[1];
         h[0] += Jp[0] * Jp[0] + Jp[3] * Jp[3];
         h[1] += Jp[0] * Jp[1] + Jp[3] * Jp[4];
@@ -642,7 +691,7 @@ __global__ void __launch_bounds__(DP_THREADS)
         const bool has_i = oi < e;
         int ci = -1;
         if (rounds > 1) {
-          if (has_i) ci = eval_obs(p, cams, camrot, oi, X, sp, r, Jc, Jp);
+          if (has_i) ci = eval_obs_cs(p, cs, CS_BUILD, oi, X, sp, r, Jc, Jp);
         } else {
           ci = has ? cam : -1;  // single round: the Jacobians of phase 1 are still live
         }
@@ -2165,6 +2214,7 @@ __device__ __forceinline__ void lm_control(const BADev& p, const lorb_ba_options
   *p.st = loc;
 }
 
+template <bool CS>  // CS: every window of the launch has <= CS_MAX_CAMS cameras, kept in shared memory
 __global__ void __launch_bounds__(BA_THREADS, 2)  // latency-bound gathers: two CTAs per SM (ncu: long_scoreboard)
     ba_backsub_kernel(const BADev* __restrict__ probs, lorb_ba_options opt, int fuse_control,
                       int* __restrict__ n_active) {
@@ -2172,6 +2222,7 @@ __global__ void __launch_bounds__(BA_THREADS, 2)  // latency-bound gathers: two 
   LMState* st = p.st;
   if (st->done) return;
   __shared__ double red[BA_THREADS / 32];
+  __shared__ double cs[CS ? CS_MAX_CAMS * CS_BACKSUB : 1];
   const int cur = st->cur;
   const double* cams = p.cams[cur];
   const double* pts = p.pts[cur];
@@ -2181,6 +2232,14 @@ __global__ void __launch_bounds__(BA_THREADS, 2)  // latency-bound gathers: two 
   double* pts_c = p.pts[cur ^ 1];
   const double* yc = p.rhs;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, gl = lane & 7, gw = lane >> 3;
+  if (CS) {
+    cs_fill(p, cams, camrot, cs, CS_BACKSUB, tid, BA_THREADS);
+    for (int i = tid; i < p.C * 18; i += BA_THREADS) {
+      const int c = i / 18, k = i - c * 18;
+      cs[c * CS_BACKSUB + CS_BUILD + k] = k < 6 ? yc[6 * c + k] : k < 15 ? camrot_c[CAMROT * c + (k - 6)] : cams_c[6 * c + 3 + (k - 15)];
+    }
+    __syncthreads();
+  }
   double model_acc = 0, cost_acc = 0, step_acc = 0, xn_acc = 0;
   for (int base = (blockIdx.x * (BA_THREADS / 32) + warp) * 4; base < p.P;
        base += gridDim.x * (BA_THREADS / 8)) {
@@ -2207,13 +2266,14 @@ __global__ void __launch_bounds__(BA_THREADS, 2)  // latency-bound gathers: two 
       const int o = s + rd * 8 + gl;
       has = o < e;
       if (has) {
-        cam = eval_obs(p, cams, camrot, o, X, sp, r, Jc, Jp);
+        cam = CS ? eval_obs_cs(p, cs, CS_BACKSUB, o, X, sp, r, Jc, Jp) : eval_obs(p, cams, camrot, o, X, sp, r, Jc, Jp);
         jcy[0] = jcy[1] = 0;
         if (cam >= 0) {
+          const double* ycam = CS ? cs + cam * CS_BACKSUB + CS_BUILD : yc + 6 * cam;
 #pragma unroll
           for (int a = 0; a < 6; a++) {
-            jcy[0] += Jc[a] * yc[6 * cam + a];
-            jcy[1] += Jc[6 + a] * yc[6 * cam + a];
+            jcy[0] += Jc[a] * ycam[a];
+            jcy[1] += Jc[6 + a] * ycam[a];
           }
 #pragma unroll
           for (int a = 0; a < 3; a++) bsum[a] += Jp[a] * jcy[0] + Jp[3 + a] * jcy[1];
@@ -2247,13 +2307,14 @@ __global__ void __launch_bounds__(BA_THREADS, 2)  // latency-bound gathers: two 
       const int o = s + rd * 8 + gl;
       if (o < e) {
         if (rounds > 1) {
-          cam = eval_obs(p, cams, camrot, o, X, sp, r, Jc, Jp);
+          cam = CS ? eval_obs_cs(p, cs, CS_BACKSUB, o, X, sp, r, Jc, Jp) : eval_obs(p, cams, camrot, o, X, sp, r, Jc, Jp);
           jcy[0] = jcy[1] = 0;
           if (cam >= 0) {
+            const double* ycam = CS ? cs + cam * CS_BACKSUB + CS_BUILD : yc + 6 * cam;
 #pragma unroll
             for (int a = 0; a < 6; a++) {
-              jcy[0] += Jc[a] * yc[6 * cam + a];
-              jcy[1] += Jc[6 + a] * yc[6 * cam + a];
+              jcy[0] += Jc[a] * ycam[a];
+              jcy[1] += Jc[6 + a] * ycam[a];
             }
           }
         }
@@ -2262,9 +2323,10 @@ __global__ void __launch_bounds__(BA_THREADS, 2)  // latency-bound gathers: two 
         model_acc += m0 * (r[0] + 0.5 * m0) + m1 * (r[1] + 0.5 * m1);
         const float2 uv = p.obs_uv[o];
         if (cam >= 0) {
-          const double* t = cams_c + 6 * cam + 3;
+          const double* rc = CS ? cs + cam * CS_BACKSUB + 51 : camrot_c + CAMROT * cam;
+          const double* t = CS ? cs + cam * CS_BACKSUB + 60 : cams_c + 6 * cam + 3;
           const double tt[3] = {t[0], t[1], t[2]};
-          cost_acc += obs_cost(camrot_c + CAMROT * cam, tt, Xc, p.K, (double)uv.x, (double)uv.y);
+          cost_acc += obs_cost(rc, tt, Xc, p.K, (double)uv.x, (double)uv.y);
         } else {
           const double* f = p.fixrt + 12 * (size_t)(-1 - cam);
           const double tt[3] = {f[9], f[10], f[11]};
@@ -3175,7 +3237,10 @@ static int problem_solve(lorb_ba_problem* pb, const lorb_ba_options* optp, int s
     }
     prof_end(c, 2);
     prof_begin(c, 1);
-    LORB_LAUNCH(c, ba_backsub_kernel, grid_pts, BA_THREADS, 0, dp, opt, fuse_control, d_active);
+    if (pb->maxC <= CS_MAX_CAMS)
+      LORB_LAUNCH(c, ba_backsub_kernel<true>, grid_pts, BA_THREADS, 0, dp, opt, fuse_control, d_active);
+    else
+      LORB_LAUNCH(c, ba_backsub_kernel<false>, grid_pts, BA_THREADS, 0, dp, opt, fuse_control, d_active);
     prof_end(c, 1);
     if (sharded) {
       LORB_TRY(dist_allreduce_sum(c, &d0.st->acc_cost2, 4));

@@ -1,17 +1,11 @@
 set -x
-nproc
-T0=$(date +%s)
-timeout 900 python bench.py > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err; echo rc=$?; tail -1 gpurun_out/bench_final.err
-T1=$(date +%s); echo "bench wall $((T1-T0)) s"
-timeout 900 python bench.py --impl reference > gpurun_out/bench_final_ref.json 2> gpurun_out/bench_final_ref.err; echo rc=$?; tail -1 gpurun_out/bench_final_ref.err
-T2=$(date +%s); echo "ref wall $((T2-T1)) s"
+timeout 900 python -m pytest tests/test_ba_gpu.py tests/test_host_dropin_gpu.py tests/test_edge_cases_gpu.py tests/test_multi_gpu.py -x -q -m gpu 2>&1 | tail -3
+for W in ba_batched ba_large; do
+timeout 600 python bench.py --workload $W --no-cpu-baseline > gpurun_out/bench_$W.json 2> gpurun_out/bench_$W.err; echo rc=$?; tail -2 gpurun_out/bench_$W.err
 python - <<PY
 import json
-d=json.loads(open('gpurun_out/bench_final.json').read().strip().split('\n')[-1])
-print('sweep', d['value']/1e9, 'e2e', d['e2e']['value']/1e9, d['roofline']['frac'], d['clocks'], d['gpu_launches'])
-print('full', d['full_sweep']['value']/1e9, d['full_sweep']['wall_s'], d['full_sweep']['parity']['ok'])
-for k in ('ba_batched','ba_large'):
-    b=d[k]; print(k, b['value']/1e9, 'e2e', b['e2e']['value']/1e9, b['roofline']['ms_per_attempt_by_part'], b['parity']['ok'])
-r=json.loads(open('gpurun_out/bench_final_ref.json').read().strip().split('\n')[-1])
-print('ref', r['value']/1e9, r['cpu_baseline'])
+b=json.loads(open('gpurun_out/bench_$W.json').read().strip().split('\n')[-1])
+print('$W', b['value']/1e9, 'e2e', b['e2e']['value']/1e9, b['roofline']['ms_per_attempt_by_part'], b['parity']['ok'])
 PY
+done
+timeout 600 python profiles/scripts/match_soak.py 45 2>&1 | tail -2

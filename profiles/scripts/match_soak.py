@@ -8,10 +8,12 @@ from lorb_slam_b200 import capi, synth  # noqa: E402
 from oracle import ref, reflib  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 40
+legs = sys.argv[2].split(",") if len(sys.argv) > 2 else ["entry", "sweep"]  # entry points / keyframe-pair sweep
+verbose = len(sys.argv) > 3
 rng = np.random.default_rng(31)
 bad = {"proj_points": 0, "proj_frame": 0, "bf": 0, "frustum": 0, "stereo": 0, "sweep_tensor": 0, "sweep_popc": 0}
 with capi.Context(0) as ctx:
-    for s in range(n):
+    for s in range(n if "entry" in legs else 0):
         nk, npt = int(rng.integers(50, 3000)), int(rng.integers(50, 6000))
         fr = synth.make_frame(nk, 700 + s, stereo=bool(s % 2), claimed_frac=float(rng.choice([0, 0.2, 0.5])))
         pts = synth.make_proj_points(fr, npt, 700 + s, nobs=(0, 1, 2), inactive_frac=0.1)
@@ -37,6 +39,7 @@ with capi.Context(0) as ctx:
         st = synth.make_stereo_pair(int(rng.integers(100, 2500)), 1000 + s)
         a, b = ctx.stereo_matches(st), reflib.stereo_matches(st)
         bad["stereo"] += not (a["n_matched"] == b["n_matched"] and np.array_equal(a["uright"], b["uright"]) and np.array_equal(a["depth"], b["depth"]))
+    for s in range(n if "sweep" in legs else 0):
         # keyframe-pair sweep, both kernels: random bank shape, random (repeated, unordered, self) pairs;
         # every third bank is low-entropy (ties everywhere), every third has near-duplicate keyframes
         n_kf, n_desc = int(rng.integers(2, 12)), int(rng.choice([1, 2, 31, 128, 255, 256, 257, 2047, 2048, int(rng.integers(1, 2049))]))
@@ -48,6 +51,8 @@ with capi.Context(0) as ctx:
         else:
             bank = synth.kf_bank(n_kf, n_desc, seed=1100 + s)
         npair = int(rng.integers(1, 40))
+        if verbose:
+            print("sweep round", s, "n_kf", n_kf, "n_desc", n_desc, "pairs", npair, flush=True)
         pa, pb = rng.integers(0, n_kf, npair).astype(np.int32), rng.integers(0, n_kf, npair).astype(np.int32)
         want = ref.sweep(bank, pa, pb)
         for impl in ("tensor", "popc"):
