@@ -437,7 +437,11 @@ __global__ void __launch_bounds__(1024)
                    const int* __restrict__ mp_nobs, const float* __restrict__ last_angle,
                    const int* __restrict__ seg_start, const int* __restrict__ seg_len,
                    const uint32_t* __restrict__ cand, int* __restrict__ fp_a, int* __restrict__ fp_b,
-                   int* __restrict__ choice, int* __restrict__ out_for_kp, int* __restrict__ res) {
+                   int* __restrict__ choice, int* __restrict__ out_for_kp, int* __restrict__ res,
+                   const unsigned long long* __restrict__ cand_total, unsigned long long cand_cap) {
+  // the candidate arena overflowed: the segments point past its end and the host repeats the
+  // search with the exact size -- nothing to resolve in this attempt
+  if (*cand_total > cand_cap) return;
   __shared__ int s_changed, s_count;
   __shared__ int s_hist[LORB_HISTO_LENGTH];
   __shared__ int s_ind[3];
@@ -629,8 +633,10 @@ __global__ void __launch_bounds__(256)
                         const int* __restrict__ mp_nobs, const float* __restrict__ last_angle,
                         const int* __restrict__ seg_start, const int* __restrict__ seg_len,
                         const uint32_t* __restrict__ cand, int* fp_a, int* fp_b, int* choice,
-                        int* out_for_kp, int* res, int* scratch) {
+                        int* out_for_kp, int* res, int* scratch,
+                        const unsigned long long* __restrict__ cand_total, unsigned long long cand_cap) {
   namespace cg = cooperative_groups;
+  if (*cand_total > cand_cap) return;  // arena overflow (see resolve_kernel): every CTA leaves, before any grid barrier
   cg::grid_group grid = cg::this_grid();
   const int INF = 0x7fffffff;
   const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
@@ -875,9 +881,11 @@ static int run_search(lorb_ctx* c, const lorb_frame_view* fv, int n_pts, const u
       const uint32_t* a_cand = d_cand;
       const int* a_segs = d_segs;
       const int* a_segl = d_segl;
+      const unsigned long long* a_total = d_counter;
+      unsigned long long a_cap = cand_cap;
       void* args[] = {&a_nkp, &a_npts, &a_claim, &a_oct, &a_ang, (void*)&d_nobs, (void*)&d_lang,
                       &a_segs, &a_segl, &a_cand, &d_fpa, &d_fpb, &d_choice, &d_forkp, &d_res,
-                      &d_scratch};
+                      &d_scratch, &a_total, &a_cap};
       LORB_CUDA_TRY(cudaLaunchCooperativeKernel((void*)resolve_coop_kernel<MODE>, dim3(grid),
                                                 dim3(256), args, 0, c->stream));
       c->launches++;
@@ -889,11 +897,11 @@ static int run_search(lorb_ctx* c, const lorb_frame_view* fv, int n_pts, const u
                                            (int)std::max<size_t>(res_smem, 16)));
         LORB_LAUNCH(c, (resolve_kernel<MODE, true>), 1, 1024, res_smem, n_kp, n_pts, f.claim_obs,
                     f.octave, f.angle, d_nobs, d_lang, d_segs, d_segl, d_cand, d_fpa, d_fpb, d_choice,
-                    d_forkp, d_res);
+                    d_forkp, d_res, d_counter, (unsigned long long)cand_cap);
       } else {
         LORB_LAUNCH(c, (resolve_kernel<MODE, false>), 1, 1024, 0, n_kp, n_pts, f.claim_obs, f.octave,
                     f.angle, d_nobs, d_lang, d_segs, d_segl, d_cand, d_fpa, d_fpb, d_choice, d_forkp,
-                    d_res);
+                    d_res, d_counter, (unsigned long long)cand_cap);
       }
     }
     LORB_CUDA_TRY(cudaMemcpyAsync(outd + r_cnt, d_counter, 16, cudaMemcpyDeviceToDevice, c->stream));

@@ -1,6 +1,7 @@
 """Soak: lorb_ba_local on random windows of every solver path (dense <= 10 cameras, privatised
 11..16, work lists > 16) against the fp64 oracle (rtol 1e-6), with fixed observers and varied
 observation counts per point."""
+import os
 import sys
 
 import numpy as np
@@ -10,7 +11,7 @@ from lorb_slam_b200 import capi, synth  # noqa: E402
 from oracle import ref  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 40
-rng = np.random.default_rng(77)
+rng = np.random.default_rng(int(os.environ.get("LORB_SOAK_SEED", 77)))
 bad = 0
 with capi.Context(0) as ctx:
     for s in range(n):

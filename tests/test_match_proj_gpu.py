@@ -99,6 +99,24 @@ def test_frame_search_unprotected_overwrites(ctx):
     assert len(taken) > len(np.unique(taken))  # some keypoint was taken twice
 
 
+@pytest.mark.parametrize("stereo", [False, True])
+def test_candidate_arena_overflow_retry(ctx, stereo):
+    """More candidates than the first-attempt arena holds (max(128 per point, 2^18)): the search is
+    repeated with the exact size and the claim resolution of the overflowed attempt must not run on
+    segments that point past the arena (found by the soak: th = 30 on a 3000-keypoint frame hung)."""
+    fr = synth.make_frame(3000, seed=21, stereo=stereo, claimed_frac=0.2)
+    pts = synth.make_proj_points(fr, 2500, seed=21, nobs=(0, 1, 2), inactive_frac=0.1)
+    o = _cmp_points(ctx, fr, pts, 30.0)
+    assert o["n_candidates"] > max(2500 * 128, 1 << 18)
+    _cmp_points(ctx, fr, pts, 1.0)  # and the context is fine afterwards
+    cur, last = synth.make_frame_pair(3000, seed=5, motion="forward", stereo=stereo)
+    r, o = ctx.search_proj_frame(cur, last, 120.0), ref.search_proj_frame(cur, last, 120.0)
+    assert o["n_candidates"] > max(3000 * 128, 1 << 18)
+    assert r["n_candidates"] == o["n_candidates"] and r["n_matches"] == o["n_matches"]
+    assert np.array_equal(r["kp_for_item"], o["kp_for_item"])
+    assert np.array_equal(r["state_for_kp"], o["state_for_kp"])
+
+
 @pytest.mark.parametrize("seed", [0, 1, 2])
 def test_frustum_project(ctx, seed):
     """SURVEY 8(f) rank 1: Frame::IsInFrustum + PredictScale, bit-exact vs the oracle."""
