@@ -197,6 +197,14 @@ __device__ __forceinline__ int eval_obs_cs(const BADev& p, const double* __restr
   return cam;
 }
 
+// |g_a / s_a| of the unscaled point gradient, coordinate a = lane of the point's group: the three
+// divisions run on three lanes at once (the maximum over lanes is taken at the end of the kernel).
+__device__ __forceinline__ double point_grad_abs(const double g[3], const double sp[3], int a) {
+  const double ga = a == 0 ? g[0] : a == 1 ? g[1] : g[2];
+  const double sa = a == 0 ? sp[0] : a == 1 ? sp[1] : sp[2];
+  return fabs(ga / sa);
+}
+
 __device__ __forceinline__ double group_sum8(double v) {
   v += __shfl_xor_sync(0xffffffffu, v, 4, 8);
   v += __shfl_xor_sync(0xffffffffu, v, 2, 8);
@@ -286,7 +294,7 @@ __global__ void __launch_bounds__(BA_THREADS)
   const double* cams = p.cams[cur];
   const double* pts = p.pts[cur];
   const double* camrot = p.camrot[cur];
-  const double radius = st->radius;
+  const double radius = st->radius, inv_radius = 1.0 / radius;  // one division per kernel, not three per point
   const int n = p.n;
   double cost_acc = 0, gmax_acc = 0, xn_acc = 0, bad_acc = 0;
   for (int blk = blockIdx.x * (BA_THREADS / 8); blk < p.P; blk += gridDim.x * (BA_THREADS / 8)) {
@@ -348,18 +356,17 @@ __global__ void __launch_bounds__(BA_THREADS)
           p.scale_p[3 * (size_t)pt + 2] = 1.0 / (1.0 + sqrt(h[5]));
         }
         xn_acc += X[0] * X[0] + X[1] * X[1] + X[2] * X[2];
-        // gradient of the unscaled problem (this pass may run with scales already set)
-        gmax_acc = fmax(gmax_acc, fmax(fabs(g[0] / sp[0]), fmax(fabs(g[1] / sp[1]), fabs(g[2] / sp[2]))));
       }
+      // gradient of the unscaled problem (this pass may run with scales already set)
+      if (pv && gl < 3) gmax_acc = fmax(gmax_acc, point_grad_abs(g, sp, gl));
       continue;
     }
-    if (pv && gl == 0)
-      gmax_acc = fmax(gmax_acc, fmax(fabs(g[0] / sp[0]), fmax(fabs(g[1] / sp[1]), fabs(g[2] / sp[2]))));
+    if (pv && gl < 3) gmax_acc = fmax(gmax_acc, point_grad_abs(g, sp, gl));
     // LM diagonal on the scaled columns, clamped (LevenbergMarquardtStrategy)
     double hd[6] = {h[0], h[1], h[2], h[3], h[4], h[5]}, hi[6];
-    hd[0] += clamp_diag(h[0], opt.min_lm_diagonal, opt.max_lm_diagonal) / radius;
-    hd[3] += clamp_diag(h[3], opt.min_lm_diagonal, opt.max_lm_diagonal) / radius;
-    hd[5] += clamp_diag(h[5], opt.min_lm_diagonal, opt.max_lm_diagonal) / radius;
+    hd[0] += clamp_diag(h[0], opt.min_lm_diagonal, opt.max_lm_diagonal) * inv_radius;
+    hd[3] += clamp_diag(h[3], opt.min_lm_diagonal, opt.max_lm_diagonal) * inv_radius;
+    hd[5] += clamp_diag(h[5], opt.min_lm_diagonal, opt.max_lm_diagonal) * inv_radius;
     const bool ok = inv3_spd(hd, hi);
     if (pv && gl == 0) {
       if (!ok) bad_acc += 1.0;
@@ -472,10 +479,13 @@ __global__ void __launch_bounds__(BA_THREADS)
 // After one 64-thread named barrier the pair contracts its own tiles on the fp64 tensor cores
 // (DMMA m8n8k4): S_pair += Y^T W as 36 upper 8x8 tiles (18 per warp, compile-time lists, so a
 // k-step loads <= 11 fragments for 18 DMMAs) and H_cc += J^T J on the 13 tiles that meet a 6x6
-// diagonal block; g_c and the Schur rhs are one column dot product per thread.  A second pair
+// diagonal block; g_c is one column dot product per thread, the Schur right-hand side comes out of
+// the same contraction (g_p sits in a spare column of W).  A second pair
 // barrier, then every lane clears exactly what it stored.  No block-wide barrier and no atomic
 // in the round loop; the pairs are reduced through shared memory once at the end and the CTA
 // flushes one partial result.
+constexpr int DENSE_RHS_COL = 60;         // 6C <= 64 means C <= 10: columns 60..63 of the tiles are never a camera's
+static_assert(DENSE_N == 64 && DENSE_RHS_COL >= (DENSE_N / 6) * 6 && DENSE_RHS_COL < DENSE_N, "spare column");
 constexpr int DP_PTS = 8;                 // points per warp pair and round
 constexpr int DP_KW = 3 * DP_PTS;         // rows of the W / Y tiles
 constexpr int DP_KJ = 2 * DP_PTS;         // rows of the J / R tiles
@@ -585,19 +595,18 @@ __global__ void __launch_bounds__(DP_THREADS)
   double* const Wt = Yt + DP_KW * DENSE_DS;
   double* const Jt = Wt + DP_KW * DENSE_DS;
   double* const Rt = Jt + DP_KJ * DENSE_DS;
-  double* const gv = Rt + DP_KJ * DENSE_RC;
   for (int i = tid; i < DP_SMEM_DOUBLES; i += DP_THREADS) dsm[i] = 0.0;
   __syncthreads();
   const int cur = st->cur;
   const double* cams = p.cams[cur];
   const double* pts = p.pts[cur];
   const double* camrot = p.camrot[cur];
-  const double radius = st->radius;
+  const double radius = st->radius, inv_radius = 1.0 / radius;  // one division per kernel, not three per point
   const int n = p.n;
   cs_fill(p, cams, camrot, cs, CS_BUILD, tid, DP_THREADS);
   __syncthreads();
   double cost_acc = 0, gmax_acc = 0, xn_acc = 0, bad_acc = 0;
-  double sacc[18][2], hacc[7][2], gown = 0.0, rown = 0.0;
+  double sacc[18][2], hacc[7][2], gown = 0.0;
 #pragma unroll
   for (int t = 0; t < 18; t++) sacc[t][0] = sacc[t][1] = 0.0;
 #pragma unroll
@@ -652,8 +661,7 @@ __global__ void __launch_bounds__(DP_THREADS)
     for (int a = 0; a < 6; a++) h[a] = group_sum8(h[a]);
 #pragma unroll
     for (int a = 0; a < 3; a++) g[a] = group_sum8(g[a]);
-    if (pv && gl == 0)
-      gmax_acc = fmax(gmax_acc, fmax(fabs(g[0] / sp[0]), fmax(fabs(g[1] / sp[1]), fabs(g[2] / sp[2]))));
+    if (pv && gl < 3) gmax_acc = fmax(gmax_acc, point_grad_abs(g, sp, gl));
     if (!FULL) {
       if (pv && gl == 0) {
         if (opt.jacobi_scaling && force == 1) {
@@ -666,9 +674,9 @@ __global__ void __launch_bounds__(DP_THREADS)
     } else {
       // LM diagonal on the scaled columns, clamped (LevenbergMarquardtStrategy)
       double hd[6] = {h[0], h[1], h[2], h[3], h[4], h[5]}, hi[6];
-      hd[0] += clamp_diag(h[0], opt.min_lm_diagonal, opt.max_lm_diagonal) / radius;
-      hd[3] += clamp_diag(h[3], opt.min_lm_diagonal, opt.max_lm_diagonal) / radius;
-      hd[5] += clamp_diag(h[5], opt.min_lm_diagonal, opt.max_lm_diagonal) / radius;
+      hd[0] += clamp_diag(h[0], opt.min_lm_diagonal, opt.max_lm_diagonal) * inv_radius;
+      hd[3] += clamp_diag(h[3], opt.min_lm_diagonal, opt.max_lm_diagonal) * inv_radius;
+      hd[5] += clamp_diag(h[5], opt.min_lm_diagonal, opt.max_lm_diagonal) * inv_radius;
       const bool ok = inv3_spd(hd, hi);
       if (pv && gl == 0) {
         if (!ok) bad_acc += 1.0;
@@ -682,9 +690,11 @@ __global__ void __launch_bounds__(DP_THREADS)
         for (int a = 0; a < 6; a++) hi[a] = 0.0;
       }
       // ---- phase 2: W_i and Y_i = W_i H_pp^-1 into the pair's tiles
+      // g_p rides in the spare column DENSE_RHS_COL of W: the contraction then leaves the Schur
+      // right-hand side Y^T g_p in that column of the product (rewritten every round: never cleared)
       if (gl == 0) {
 #pragma unroll
-        for (int b2 = 0; b2 < 3; b2++) gv[ps * 3 + b2] = pv ? g[b2] : 0.0;
+        for (int b2 = 0; b2 < 3; b2++) Wt[(ps * 3 + b2) * DENSE_DS + DENSE_RHS_COL] = pv ? g[b2] : 0.0;
       }
       for (int ri = 0; ri < rounds; ri++) {
         const int oi = s + ri * 8 + gl;
@@ -724,12 +734,6 @@ __global__ void __launch_bounds__(DP_THREADS)
 #pragma unroll
       for (int k2 = 0; k2 < DP_KJ; k2++) a2 += Jt[k2 * DENSE_DS + ptid] * Rt[k2 * DENSE_RC + c2];
       gown += a2;
-      if (FULL) {
-        double a3 = 0;
-#pragma unroll
-        for (int k = 0; k < DP_KW; k++) a3 += Yt[k * DENSE_DS + ptid] * gv[k];
-        rown += a3;
-      }
     }
     pair_barrier(pair);
     // ---- clear exactly what this lane stored
@@ -761,7 +765,6 @@ __global__ void __launch_bounds__(DP_THREADS)
   double* const Sbuf = dsm;                        // 64 x 64
   double* const Hbuf = Sbuf + DENSE_N * DENSE_N;   // 21 per camera
   double* const Gbuf = Hbuf + HCC * 10 + 6;        // g_c
-  double* const Rbuf = Gbuf + DENSE_N;             // Schur rhs
   for (int i = tid; i < DENSE_N * DENSE_N + HCC * 10 + 6 + 2 * DENSE_N; i += DP_THREADS) dsm[i] = 0.0;
   __syncthreads();
   for (int pp = 0; pp < DP_NPAIR; pp++) {
@@ -770,10 +773,7 @@ __global__ void __launch_bounds__(DP_THREADS)
         dense_reduce<0, FULL>(Sbuf, Hbuf, lane, n, sacc, hacc);
       else
         dense_reduce<1, FULL>(Sbuf, Hbuf, lane, n, sacc, hacc);
-      if (ptid < n) {
-        Gbuf[ptid] += gown;
-        if (FULL) Rbuf[ptid] += rown;
-      }
+      if (ptid < n) Gbuf[ptid] += gown;
     }
     __syncthreads();
   }
@@ -781,7 +781,8 @@ __global__ void __launch_bounds__(DP_THREADS)
     if (Hbuf[i] != 0.0) atomicAdd(&p.Hcc[i], Hbuf[i]);
   if (tid < n) {
     if (Gbuf[tid] != 0.0) atomicAdd(&p.gc[tid], Gbuf[tid]);
-    if (FULL && Rbuf[tid] != 0.0) atomicAdd(&p.rhs_corr[tid], Rbuf[tid]);
+    const double rc = FULL ? Sbuf[tid * DENSE_N + DENSE_RHS_COL] : 0.0;
+    if (FULL && rc != 0.0) atomicAdd(&p.rhs_corr[tid], rc);
   }
   if (FULL) {
     for (int i = tid; i < DENSE_N * DENSE_N; i += DP_THREADS) {
@@ -1015,7 +1016,7 @@ __global__ void ba_finish_kernel(const BADev* __restrict__ probs, lorb_ba_option
   LMState* st = p.st;
   if (st->done) return;
   const int n = p.n;
-  const double radius = st->radius;
+  const double radius = st->radius, inv_radius = 1.0 / radius;  // one division per kernel, not three per point
   for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < (size_t)n * n;
        idx += (size_t)gridDim.x * blockDim.x) {
     const int i = (int)(idx / n), j = (int)(idx % n);
@@ -1025,14 +1026,14 @@ __global__ void ba_finish_kernel(const BADev* __restrict__ probs, lorb_ba_option
       double v = ci <= cj ? p.Sp[packed_idx(p.C, ci, a, cj, b)] : p.Sp[packed_idx(p.C, cj, b, ci, a)];
       if (ci == cj) {
         double h = p.Hcc[HCC * (size_t)ci + (a <= b ? upper_idx(a, b) : upper_idx(b, a))];
-        if (a == b) h += clamp_diag(h, opt.min_lm_diagonal, opt.max_lm_diagonal) / radius;
+        if (a == b) h += clamp_diag(h, opt.min_lm_diagonal, opt.max_lm_diagonal) * inv_radius;
         v += h;
       }
       p.S[idx] = v;
     } else if (ci == cj) {
       const int a = i % 6, b = j % 6;
       double v = p.Hcc[HCC * (size_t)ci + (a <= b ? upper_idx(a, b) : upper_idx(b, a))];
-      if (a == b) v += clamp_diag(v, opt.min_lm_diagonal, opt.max_lm_diagonal) / radius;
+      if (a == b) v += clamp_diag(v, opt.min_lm_diagonal, opt.max_lm_diagonal) * inv_radius;
       p.S[idx] += v;
     } else if (ci > cj) {
       p.S[idx] = p.S[(size_t)j * n + i];  // mirror the upper block triangle
@@ -1187,7 +1188,7 @@ __global__ void __launch_bounds__(256)
   }
   __syncthreads();
   if (s_done) return;
-  const double radius = st->radius;
+  const double radius = st->radius, inv_radius = 1.0 / radius;  // one division per kernel, not three per point
   // (the loads of four elements per thread are issued together: the loop was one exposed L2
   //  round trip per element, 8.5 us of the 50 us this kernel took)
   for (int base = 0; base < n * n; base += 4 * 256) {
@@ -1217,7 +1218,7 @@ __global__ void __launch_bounds__(256)
       const int idx = base + tid + 256 * q;
       if (dcase[q] < 0) continue;
       double v = vs[q] + vh[q];
-      if (dcase[q] == 2) v += clamp_diag(vh[q], opt.min_lm_diagonal, opt.max_lm_diagonal) / radius;
+      if (dcase[q] == 2) v += clamp_diag(vh[q], opt.min_lm_diagonal, opt.max_lm_diagonal) * inv_radius;
       A[idx] = v;
     }
   }

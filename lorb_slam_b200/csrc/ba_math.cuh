@@ -141,21 +141,22 @@ __device__ __forceinline__ double obs_cost(const double* __restrict__ R, const d
 }
 
 // inverse of a symmetric positive definite 3x3 given as (h00,h01,h02,h11,h12,h22);
-// returns false when a Cholesky pivot is not positive.
+// returns false when a Cholesky pivot is not positive.  The three pivots go through rsqrt (one
+// MUFU seed + Newton steps each) instead of three square roots and six divisions: this function
+// runs once per point and pass in every build kernel, where it was 8 % of the issue slots.
 __device__ __forceinline__ bool inv3_spd(const double h[6], double hi[6]) {
   const double l00s = h[0];
   if (!(l00s > 0.0)) return false;
-  const double l00 = sqrt(l00s);
-  const double l10 = h[1] / l00, l20 = h[2] / l00;
+  const double i00 = rsqrt(l00s);
+  const double l10 = h[1] * i00, l20 = h[2] * i00;
   const double l11s = h[3] - l10 * l10;
   if (!(l11s > 0.0)) return false;
-  const double l11 = sqrt(l11s);
-  const double l21 = (h[4] - l20 * l10) / l11;
+  const double i11 = rsqrt(l11s);
+  const double l21 = (h[4] - l20 * l10) * i11;
   const double l22s = h[5] - l20 * l20 - l21 * l21;
   if (!(l22s > 0.0)) return false;
-  const double l22 = sqrt(l22s);
+  const double i22 = rsqrt(l22s);
   // inverse of L (lower)
-  const double i00 = 1.0 / l00, i11 = 1.0 / l11, i22 = 1.0 / l22;
   const double i10 = -l10 * i00 * i11;
   const double i21 = -l21 * i11 * i22;
   const double i20 = -(l20 * i00 + l21 * i10) * i22;
