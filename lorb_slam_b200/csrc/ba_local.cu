@@ -205,6 +205,12 @@ __device__ __forceinline__ double point_grad_abs(const double g[3], const double
   return fabs(ga / sa);
 }
 
+// Start a line on its way into L1 without holding a register for it (the consumer is a few
+// hundred instructions later and the kernels below sit at their register cap).
+__device__ __forceinline__ void prefetch_l1(const void* ptr) {
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr));
+}
+
 __device__ __forceinline__ double group_sum8(double v) {
   v += __shfl_xor_sync(0xffffffffu, v, 4, 8);
   v += __shfl_xor_sync(0xffffffffu, v, 2, 8);
@@ -493,6 +499,7 @@ constexpr int DP_PAIR = 2 * DP_KW * DENSE_DS + DP_KJ * DENSE_DS + DP_KJ * DENSE_
 constexpr int DP_THREADS = 256;           // 4 warp pairs (384 threads = 6 pairs fit in smem but spill: measured slower)
 constexpr int DP_NPAIR = DP_THREADS / 64;
 constexpr int DP_SMEM_DOUBLES = DP_NPAIR * DP_PAIR;
+static_assert(DP_PAIR % 2 == 0 && DENSE_DS % 2 == 0 && (DP_KW * DENSE_DS) % 2 == 0, "128-bit tile stores stay aligned");
 static_assert(DP_SMEM_DOUBLES >= DENSE_N * DENSE_N + HCC * 10 + 2 * DENSE_N + 16, "reduction buffer fits");
 
 __device__ __forceinline__ void pair_barrier(int pair) {
@@ -651,7 +658,9 @@ __global__ void __launch_bounds__(DP_THREADS)
 #pragma unroll
           for (int comp = 0; comp < 2; comp++) {
 #pragma unroll
-            for (int a = 0; a < 6; a++) Jt[(ps * 2 + comp) * DENSE_DS + 6 * cam + a] = Jc[6 * comp + a];
+            for (int a = 0; a < 6; a += 2)  // a camera's six columns start 16-byte aligned: 128-bit stores
+              *reinterpret_cast<double2*>(&Jt[(ps * 2 + comp) * DENSE_DS + 6 * cam + a]) =
+                  make_double2(Jc[6 * comp + a], Jc[6 * comp + a + 1]);
             Rt[(ps * 2 + comp) * DENSE_RC + cam] = r[comp];
           }
         }
@@ -707,17 +716,27 @@ __global__ void __launch_bounds__(DP_THREADS)
         }
         if (has_i && ci >= 0) {
 #pragma unroll
-          for (int a = 0; a < 6; a++) {
-            const double w0 = Jc[a] * Jp[0] + Jc[6 + a] * Jp[3];
-            const double w1 = Jc[a] * Jp[1] + Jc[6 + a] * Jp[4];
-            const double w2 = Jc[a] * Jp[2] + Jc[6 + a] * Jp[5];
+          for (int a = 0; a < 6; a += 2) {  // two columns at a time: 128-bit stores
+            double w[2][3];
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+              w[q][0] = Jc[a + q] * Jp[0] + Jc[6 + a + q] * Jp[3];
+              w[q][1] = Jc[a + q] * Jp[1] + Jc[6 + a + q] * Jp[4];
+              w[q][2] = Jc[a + q] * Jp[2] + Jc[6 + a + q] * Jp[5];
+            }
             const int col = 6 * ci + a;
-            Wt[(ps * 3 + 0) * DENSE_DS + col] = w0;
-            Wt[(ps * 3 + 1) * DENSE_DS + col] = w1;
-            Wt[(ps * 3 + 2) * DENSE_DS + col] = w2;
-            Yt[(ps * 3 + 0) * DENSE_DS + col] = w0 * hi[0] + w1 * hi[1] + w2 * hi[2];
-            Yt[(ps * 3 + 1) * DENSE_DS + col] = w0 * hi[1] + w1 * hi[3] + w2 * hi[4];
-            Yt[(ps * 3 + 2) * DENSE_DS + col] = w0 * hi[2] + w1 * hi[4] + w2 * hi[5];
+#pragma unroll
+            for (int b2 = 0; b2 < 3; b2++)
+              *reinterpret_cast<double2*>(&Wt[(ps * 3 + b2) * DENSE_DS + col]) = make_double2(w[0][b2], w[1][b2]);
+            *reinterpret_cast<double2*>(&Yt[(ps * 3 + 0) * DENSE_DS + col]) =
+                make_double2(w[0][0] * hi[0] + w[0][1] * hi[1] + w[0][2] * hi[2],
+                             w[1][0] * hi[0] + w[1][1] * hi[1] + w[1][2] * hi[2]);
+            *reinterpret_cast<double2*>(&Yt[(ps * 3 + 1) * DENSE_DS + col]) =
+                make_double2(w[0][0] * hi[1] + w[0][1] * hi[3] + w[0][2] * hi[4],
+                             w[1][0] * hi[1] + w[1][1] * hi[3] + w[1][2] * hi[4]);
+            *reinterpret_cast<double2*>(&Yt[(ps * 3 + 2) * DENSE_DS + col]) =
+                make_double2(w[0][0] * hi[2] + w[0][1] * hi[4] + w[0][2] * hi[5],
+                             w[1][0] * hi[2] + w[1][1] * hi[4] + w[1][2] * hi[5]);
           }
         }
       }
@@ -743,14 +762,15 @@ __global__ void __launch_bounds__(DP_THREADS)
         const int ci = p.obs_cam[oi];
         if (ci >= 0) {
 #pragma unroll
-          for (int a = 0; a < 6; a++) {
-            Jt[(ps * 2 + 0) * DENSE_DS + 6 * ci + a] = 0.0;
-            Jt[(ps * 2 + 1) * DENSE_DS + 6 * ci + a] = 0.0;
+          for (int a = 0; a < 6; a += 2) {
+            const double2 z = make_double2(0.0, 0.0);
+            *reinterpret_cast<double2*>(&Jt[(ps * 2 + 0) * DENSE_DS + 6 * ci + a]) = z;
+            *reinterpret_cast<double2*>(&Jt[(ps * 2 + 1) * DENSE_DS + 6 * ci + a]) = z;
             if (FULL) {
 #pragma unroll
               for (int c2 = 0; c2 < 3; c2++) {
-                Wt[(ps * 3 + c2) * DENSE_DS + 6 * ci + a] = 0.0;
-                Yt[(ps * 3 + c2) * DENSE_DS + 6 * ci + a] = 0.0;
+                *reinterpret_cast<double2*>(&Wt[(ps * 3 + c2) * DENSE_DS + 6 * ci + a]) = z;
+                *reinterpret_cast<double2*>(&Yt[(ps * 3 + c2) * DENSE_DS + 6 * ci + a]) = z;
               }
             }
           }
@@ -2257,6 +2277,20 @@ __global__ void __launch_bounds__(BA_THREADS, 2)  // latency-bound gathers: two 
         sp[a] = p.scale_p[3 * (size_t)pt + a];
       }
     }
+    // ncu: a third of this kernel's stall samples waited on three dependent global loads (the point
+    // header of the next iteration, the observation's camera index, H_pp^-1 / g_p after the loop)
+    if (pv && gl == 0) {
+      prefetch_l1(p.pt_hinv + 6 * (size_t)pt);
+      prefetch_l1(p.pt_gp + 3 * (size_t)pt);
+    }
+    {
+      const int ptn = pt + (int)gridDim.x * (BA_THREADS / 8);
+      if (ptn < p.P && gl == 1) {
+        prefetch_l1(p.pt_ptr + ptn);
+        prefetch_l1(pts + 3 * (size_t)ptn);
+        prefetch_l1(p.scale_p + 3 * (size_t)ptn);
+      }
+    }
     const int rounds = __reduce_max_sync(0xffffffffu, (e - s + 7) >> 3);
     double bsum[3] = {0, 0, 0};
     double r[2], Jc[12], Jp[6];
@@ -2352,6 +2386,16 @@ __global__ void __launch_bounds__(BA_THREADS, 2)  // latency-bound gathers: two 
       lm_control(p, opt, n_active);
     }
   }
+}
+
+// End of a solve: windows whose current parameters sit in buffer 1 copy them to buffer 0 (where
+// download and the next solve expect them).  One launch for the whole batch.
+__global__ void __launch_bounds__(256) ba_make_current_kernel(const BADev* __restrict__ probs) {
+  const BADev p = probs[blockIdx.y];
+  if (p.st->cur != 1) return;
+  const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
+  for (int i = gtid; i < p.n; i += gsize) p.cams[0][i] = p.cams[1][i];
+  for (int i = gtid; i < 3 * p.P; i += gsize) p.pts[0][i] = p.pts[1][i];
 }
 
 __global__ void ba_control_kernel(const BADev* __restrict__ probs, lorb_ba_options opt, int* __restrict__ n_active) {
@@ -3276,12 +3320,11 @@ static int problem_solve(lorb_ba_problem* pb, const lorb_ba_options* optp, int s
     LORB_CUDA_TRY(cudaStreamSynchronize(s));
   }
   // make buffer 0 the current one so download / the next solve find the result there
+  bool any_cur1 = false;
+  for (int w = 0; w < nw; w++) any_cur1 |= hs[w].cur == 1;
+  if (any_cur1)
+    LORB_LAUNCH(c, ba_make_current_kernel, dim3(std::max(1, std::min(64, (3 * pb->maxP + 255) / 256)), nw), 256, 0, dp);
   for (int w = 0; w < nw; w++) {
-    if (hs[w].cur == 1) {
-      const BADev& d = pb->h_dev[w];
-      LORB_CUDA_TRY(cudaMemcpyAsync(d.cams[0], d.cams[1], (size_t)d.n * 8, cudaMemcpyDeviceToDevice, s));
-      if (d.P) LORB_CUDA_TRY(cudaMemcpyAsync(d.pts[0], d.pts[1], (size_t)d.P * 24, cudaMemcpyDeviceToDevice, s));
-    }
     if (sums) {
       lorb_ba_summary& sum = sums[w];
       sum.initial_cost = hs[w].initial_cost;

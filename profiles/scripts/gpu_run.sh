@@ -5,7 +5,6 @@ timeout 600 python bench.py --workload $W --no-cpu-baseline > gpurun_out/bench_$
 python - <<PY
 import json
 b=json.loads(open('gpurun_out/bench_$W.json').read().strip().split('\n')[-1])
-print('$W', b['value']/1e9, 'e2e', b['e2e']['value']/1e9, b['roofline']['ms_per_attempt_by_part'], b['parity'])
+print('$W', b['value']/1e9, 'e2e', b['e2e']['value']/1e9, b['roofline']['ms_per_attempt_by_part'], b['parity']['ok'])
 PY
 done
-LORB_SOAK_SEED=202 timeout 300 python profiles/scripts/ba_soak.py 120 > gpurun_out/soak_ba.log 2>&1; echo rc=$?; tail -3 gpurun_out/soak_ba.log
