@@ -156,8 +156,10 @@ __device__ __forceinline__ int eval_obs(const BADev& p, const double* __restrict
 // one L1 wavefront per distinct camera (ncu: l1tex 50 % busy on 45 such loads per observation).
 // Layout per camera, CS_BUILD doubles: [0,36) R and dR, [36,39) t, [39,45) Jacobi scale; the
 // back-substitution appends [45,51) the camera step, [51,60) R and [60,63) t of the candidate.  Both
-// strides are odd, so the <= 16 cameras of a window start on distinct even banks and a warp-wide
-// load is conflict free (lanes on the same camera broadcast).
+// strides are odd, so 16 consecutive cameras start on distinct even banks: a warp-wide load of a
+// window of <= 16 cameras is conflict free (lanes on the same camera broadcast).  The dense build
+// has at most 10 cameras; the back-substitution takes any window whose cameras fit twice per SM
+// (config 5: 200 cameras, 100 KB, a few-way bank conflict instead of one L1 wavefront per camera).
 constexpr int CS_BUILD = 45, CS_BACKSUB = 63, CS_MAX_CAMS = 16;
 
 __device__ __forceinline__ void cs_fill(const BADev& p, const double* __restrict__ cams,
@@ -2243,7 +2245,7 @@ __global__ void __launch_bounds__(BA_THREADS, 2)  // latency-bound gathers: two 
   LMState* st = p.st;
   if (st->done) return;
   __shared__ double red[BA_THREADS / 32];
-  __shared__ double cs[CS ? CS_MAX_CAMS * CS_BACKSUB : 1];
+  extern __shared__ __align__(16) double cs[];  // CS: maxC * CS_BACKSUB doubles
   const int cur = st->cur;
   const double* cams = p.cams[cur];
   const double* pts = p.pts[cur];
@@ -3168,6 +3170,14 @@ static int problem_solve(lorb_ba_problem* pb, const lorb_ba_options* optp, int s
   }
   const int gx_pts = std::max(1, std::min((pb->maxP + 31) / 32, std::max(1, c->sm_count * 8 / nw)));
   const dim3 grid_pts(gx_pts, nw);
+  // back-substitution with the cameras in shared memory: two CTAs per SM must fit (C <= 203); a CTA
+  // of a large window copies 100 KB, so such a launch is just the co-resident CTAs, grid-striding
+  const size_t backsub_smem = (size_t)pb->maxC * CS_BACKSUB * 8;
+  const bool backsub_cs = backsub_smem <= 100 * 1024;
+  if (backsub_cs && backsub_smem > 40 * 1024)
+    LORB_CUDA_TRY(cudaFuncSetAttribute(ba_backsub_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)backsub_smem));
+  const dim3 grid_backsub(backsub_smem > 16 * 1024 ? std::min(gx_pts, std::max(1, 2 * c->sm_count / nw)) : gx_pts, nw);
   const int ppc = DP_THREADS / 8;  // points per CTA round of the dense path
   const dim3 grid_dense(std::max(1, std::min((pb->maxP + ppc - 1) / ppc, std::max(1, c->sm_count * 8 / nw))), nw);
   const dim3 grid_cam((pb->maxC + 127) / 128, nw);
@@ -3282,8 +3292,8 @@ static int problem_solve(lorb_ba_problem* pb, const lorb_ba_options* optp, int s
     }
     prof_end(c, 2);
     prof_begin(c, 1);
-    if (pb->maxC <= CS_MAX_CAMS)
-      LORB_LAUNCH(c, ba_backsub_kernel<true>, grid_pts, BA_THREADS, 0, dp, opt, fuse_control, d_active);
+    if (backsub_cs)
+      LORB_LAUNCH(c, ba_backsub_kernel<true>, grid_backsub, BA_THREADS, backsub_smem, dp, opt, fuse_control, d_active);
     else
       LORB_LAUNCH(c, ba_backsub_kernel<false>, grid_pts, BA_THREADS, 0, dp, opt, fuse_control, d_active);
     prof_end(c, 1);

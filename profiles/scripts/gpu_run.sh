@@ -1,15 +1,10 @@
 set -x
-timeout 900 python bench.py > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err; echo rc=$?; tail -1 gpurun_out/bench_final.err
+timeout 900 python -m pytest tests/test_ba_gpu.py tests/test_host_dropin_gpu.py tests/test_edge_cases_gpu.py tests/test_multi_gpu.py tests/test_ref_golden_gpu.py -x -q -m gpu 2>&1 | tail -3
+for W in ba_batched ba_large; do
+timeout 600 python bench.py --workload $W --no-cpu-baseline > gpurun_out/bench_$W.json 2> gpurun_out/bench_$W.err; echo rc=$?; tail -2 gpurun_out/bench_$W.err
 python - <<PY
 import json
-d=json.loads(open('gpurun_out/bench_final.json').read().strip().split('\n')[-1])
-print('sweep', d['value']/1e9, 'e2e', d['e2e']['value']/1e9, d['roofline']['frac'], d['clocks'], d['gpu_launches'])
-print('full', d['full_sweep']['value']/1e9, d['full_sweep']['wall_s'], d['full_sweep']['parity']['ok'])
-for k in ('ba_batched','ba_large'):
-    b=d[k]; print(k, b['value']/1e9, 'e2e', b['e2e']['value']/1e9, b['roofline'], b['parity']['ok'])
-print(d.get('extras') or d.get('extra'))
+b=json.loads(open('gpurun_out/bench_$W.json').read().strip().split('\n')[-1])
+print('$W', b['value']/1e9, 'e2e', b['e2e']['value']/1e9, b['roofline']['ms_per_attempt_by_part'], b['parity']['ok'])
 PY
-python profiles/scripts/ba_batch_prof.py > gpurun_out/plain_bab.log 2>&1 && \
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:'ba_build_dense_kernel|ba_backsub_kernel' -c 5 -f -o gpurun_out/r02_ba_batch_full python profiles/scripts/ba_batch_prof.py > gpurun_out/ncu_bab_full.log 2>&1
-tail -2 gpurun_out/ncu_bab_full.log
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r02_ba_batched_launches.csv python bench.py --workload ba_batched --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_launch_bab.log 2>&1; echo rc=$?
+done
