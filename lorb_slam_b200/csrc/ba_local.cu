@@ -2871,9 +2871,11 @@ static int problem_build(lorb_ba_problem* pb, lorb_ctx* c, const std::vector<Win
               }
         if (dup) dup_any |= 1;
       }
-      if (6 * W.C > 96) {
+      if (any_large) {
         // large path: the work lists are built on the device from the CSR (DevListBuilder); the
-        // host only counts the pair records so that every buffer can be sized before the uploads
+        // host only counts the pair records so that every buffer can be sized before the uploads.
+        // One window with 6C > 96 puts the whole batch on this path (the build kernels are chosen
+        // per launch), so every window of such a batch gets its lists.
         btr.mark("csr staged");
         const int* cam = &h_cam[b];
         long long np = 0;

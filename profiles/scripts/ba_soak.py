@@ -41,4 +41,31 @@ with capi.Context(0) as ctx:
             else:
                 bad += 1
                 print("MISMATCH", s, C, P, k, ff, it, str(e)[:200].replace("\n", " "))
+    # heterogeneous batches: windows of different solver paths (dense / privatised / work lists) in
+    # one lorb_ba_local_batched call, every window against the oracle's single-window solve
+    nb = bad_b = 0
+    for s in range(n // 4):
+        nwin = int(rng.integers(2, 9))
+        pbs = []
+        for w in range(nwin):
+            C = int(rng.choice([3, 5, 8, 10, 10, 11, 14, 16, 17, 24]))
+            k = tuple(int(v) for v in rng.choice(np.arange(3, min(C, 10) + 1), size=3))
+            pbs.append(synth.make_ba_problem(5000 + 16 * s + w, C=C, P=int(rng.integers(30, 400)), obs_per_point=k,
+                                             traj_len=float(max(3.0, C * 0.4))))
+        it = int(rng.choice([3, 6, 20]))
+        kw = dict(max_num_iterations=it)
+        bt = synth.batch_windows(pbs)
+        cams, pts, sums = ctx.ba_local_batched(bt, capi.ba_options(**kw))
+        for w, pb in enumerate(pbs):
+            nb += 1
+            oc, op, so = ref.ba_local(pb, ref.ba_options(**kw))
+            gc = cams[bt["cam_off"][w]:bt["cam_off"][w + 1]]
+            gp = pts[bt["pt_off"][w]:bt["pt_off"][w + 1]]
+            ok = (np.allclose(gc, oc, rtol=1e-6, atol=1e-8) and np.allclose(gp, op, rtol=1e-6, atol=1e-8)
+                  and sums[w]["iterations"] == so["iterations"] and sums[w]["termination"] == so["termination"])
+            if not ok:
+                bad_b += 1
+                print("BATCH MISMATCH", s, w, [q["C"] for q in pbs], it, np.abs(gc - oc).max(), np.abs(gp - op).max(),
+                      sums[w]["iterations"], so["iterations"])
+    print("%d batched windows in %d heterogeneous batches, %d differ" % (nb, n // 4, bad_b))
 print("%d windows, %d differ, %d more within 10x the oracle's own sensitivity to a 1e-15 input change" % (n, bad, soft))

@@ -164,6 +164,23 @@ def test_batched_windows(ctx):
         _same_summary(sums[i], o)
 
 
+@pytest.mark.parametrize("cams_per_window", [(10, 17, 5, 24), (24, 10), (14, 10, 16, 3), (8, 10, 11, 10)])
+def test_batched_windows_of_mixed_solver_paths(ctx, cams_per_window):
+    """One batch, windows of different accumulation paths (dense <= 10 cameras, privatised <= 16,
+    work lists beyond): the build kernels are chosen per launch, so one window with 6C > 96 moves
+    the whole batch onto the work-list path and every window needs its lists (the soak found
+    batches with such a window returning garbage for all their windows)."""
+    pbs = [synth.make_ba_problem(300 + 7 * i + C, C=C, P=120 + 30 * i, obs_per_point=(3, 4, min(C, 6)),
+                                 traj_len=float(max(3.0, 0.4 * C))) for i, C in enumerate(cams_per_window)]
+    bt = synth.batch_windows(pbs)
+    cams, pts, sums = ctx.ba_local_batched(bt, capi.ba_options(max_num_iterations=8))
+    for i, pb in enumerate(pbs):
+        oc, op, o = ref.ba_local(pb, ref.ba_options(max_num_iterations=8))
+        _close(cams[bt["cam_off"][i]:bt["cam_off"][i + 1]], oc, f"cameras of window {i}")
+        _close(pts[bt["pt_off"][i]:bt["pt_off"][i + 1]], op, f"points of window {i}")
+        _same_summary(sums[i], o)
+
+
 def test_bad_arguments(ctx):
     pb = synth.make_ba_problem(9, C=3, P=50, obs_per_point=(3,))
     bad = dict(pb)
