@@ -483,21 +483,22 @@ __global__ void __launch_bounds__(BA_THREADS)
 // keeps private dense tiles of them in shared memory:
 //     J  [16 x 64]  rows (point slot, residual component), columns camera parameters
 //     R  [16 x 16]  residual of that row per camera
-//     W, Y = W H_pp^-1  [24 x 64]  rows (point slot, point coordinate)
+//     Z = L^-1 W^T  [24 x 64]  rows (point slot, point coordinate), H_pp^-1 = L^-T L^-1
 // After one 64-thread named barrier the pair contracts its own tiles on the fp64 tensor cores
-// (DMMA m8n8k4): S_pair += Y^T W as 36 upper 8x8 tiles (18 per warp, compile-time lists, so a
-// k-step loads <= 11 fragments for 18 DMMAs) and H_cc += J^T J on the 13 tiles that meet a 6x6
-// diagonal block; g_c is one column dot product per thread, the Schur right-hand side comes out of
-// the same contraction (g_p sits in a spare column of W).  A second pair
+// (DMMA m8n8k4): S_pair += Z^T Z (= W H_pp^-1 W^T) as 36 upper 8x8 tiles (18 per warp,
+// compile-time lists; both fragments of a tile pair come from the same 8 loads per k-step) and
+// H_cc += J^T J on the 13 tiles that meet a 6x6 diagonal block; g_c is one column dot product per
+// thread, the Schur right-hand side comes out of the same contraction (L^-1 g_p sits in a spare
+// column of Z).  A second pair
 // barrier, then every lane clears exactly what it stored.  No block-wide barrier and no atomic
 // in the round loop; the pairs are reduced through shared memory once at the end and the CTA
 // flushes one partial result.
 constexpr int DENSE_RHS_COL = 60;         // 6C <= 64 means C <= 10: columns 60..63 of the tiles are never a camera's
 static_assert(DENSE_N == 64 && DENSE_RHS_COL >= (DENSE_N / 6) * 6 && DENSE_RHS_COL < DENSE_N, "spare column");
 constexpr int DP_PTS = 8;                 // points per warp pair and round
-constexpr int DP_KW = 3 * DP_PTS;         // rows of the W / Y tiles
+constexpr int DP_KW = 3 * DP_PTS;         // rows of the Z tile
 constexpr int DP_KJ = 2 * DP_PTS;         // rows of the J / R tiles
-constexpr int DP_PAIR = 2 * DP_KW * DENSE_DS + DP_KJ * DENSE_DS + DP_KJ * DENSE_RC + DP_KW;  // doubles
+constexpr int DP_PAIR = DP_KW * DENSE_DS + DP_KJ * DENSE_DS + DP_KJ * DENSE_RC;  // doubles
 constexpr int DP_THREADS = 256;           // 4 warp pairs (384 threads = 6 pairs fit in smem but spill: measured slower)
 constexpr int DP_NPAIR = DP_THREADS / 64;
 constexpr int DP_SMEM_DOUBLES = DP_NPAIR * DP_PAIR;
@@ -537,7 +538,7 @@ struct DenseTiles {
 };
 
 template <int HALF, bool FULL>
-__device__ __forceinline__ void dense_contract(const double* __restrict__ Yt, const double* __restrict__ Wt,
+__device__ __forceinline__ void dense_contract(const double* __restrict__ Zt,
                                                const double* __restrict__ Jt, int lane,
                                                double (&sacc)[18][2], double (&hacc)[7][2]) {
   using T = DenseTiles<HALF>;
@@ -553,14 +554,11 @@ __device__ __forceinline__ void dense_contract(const double* __restrict__ Yt, co
   if (FULL) {
 #pragma unroll
     for (int k0 = 0; k0 < DP_KW; k0 += 4) {
-      double a[8], b[8];
+      double z[8];  // Z^T Z: the A and the B fragment of a tile pair are the same loads
 #pragma unroll
-      for (int i = 0; i < 8; i++) {
-        a[i] = Yt[fo + k0 * DENSE_DS + 8 * i];
-        b[i] = Wt[fo + k0 * DENSE_DS + 8 * i];
-      }
+      for (int i = 0; i < 8; i++) z[i] = Zt[fo + k0 * DENSE_DS + 8 * i];
 #pragma unroll
-      for (int t = 0; t < T::NS; t++) dmma884(sacc[t][0], sacc[t][1], a[T::si(t)], b[T::sj(t)]);
+      for (int t = 0; t < T::NS; t++) dmma884(sacc[t][0], sacc[t][1], z[T::si(t)], z[T::sj(t)]);
     }
   }
 }
@@ -600,9 +598,8 @@ __global__ void __launch_bounds__(DP_THREADS)
   extern __shared__ __align__(16) double dsm[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, gl = lane & 7, gw = lane >> 3;
   const int pair = warp >> 1, half = warp & 1, ptid = tid & 63;
-  double* const Yt = dsm + pair * DP_PAIR;
-  double* const Wt = Yt + DP_KW * DENSE_DS;
-  double* const Jt = Wt + DP_KW * DENSE_DS;
+  double* const Zt = dsm + pair * DP_PAIR;
+  double* const Jt = Zt + DP_KW * DENSE_DS;
   double* const Rt = Jt + DP_KJ * DENSE_DS;
   for (int i = tid; i < DP_SMEM_DOUBLES; i += DP_THREADS) dsm[i] = 0.0;
   __syncthreads();
@@ -688,7 +685,8 @@ __global__ void __launch_bounds__(DP_THREADS)
       hd[0] += clamp_diag(h[0], opt.min_lm_diagonal, opt.max_lm_diagonal) * inv_radius;
       hd[3] += clamp_diag(h[3], opt.min_lm_diagonal, opt.max_lm_diagonal) * inv_radius;
       hd[5] += clamp_diag(h[5], opt.min_lm_diagonal, opt.max_lm_diagonal) * inv_radius;
-      const bool ok = inv3_spd(hd, hi);
+      double il[6];
+      const bool ok = inv3_spd(hd, hi, il);
       if (pv && gl == 0) {
         if (!ok) bad_acc += 1.0;
 #pragma unroll
@@ -698,14 +696,17 @@ __global__ void __launch_bounds__(DP_THREADS)
       }
       if (!ok) {
 #pragma unroll
-        for (int a = 0; a < 6; a++) hi[a] = 0.0;
+        for (int a = 0; a < 6; a++) il[a] = 0.0;
       }
-      // ---- phase 2: W_i and Y_i = W_i H_pp^-1 into the pair's tiles
-      // g_p rides in the spare column DENSE_RHS_COL of W: the contraction then leaves the Schur
-      // right-hand side Y^T g_p in that column of the product (rewritten every round: never cleared)
+      // ---- phase 2: Z_i = L^-1 W_i^T into the pair's tile (H_pp^-1 = L^-T L^-1, so the Schur
+      // product W H_pp^-1 W^T of the point is Z^T Z: one tile, contracted with itself).
+      // L^-1 g_p rides in the spare column DENSE_RHS_COL: the contraction then leaves the Schur
+      // right-hand side W H_pp^-1 g_p in that column of the product (rewritten every round: never cleared)
       if (gl == 0) {
-#pragma unroll
-        for (int b2 = 0; b2 < 3; b2++) Wt[(ps * 3 + b2) * DENSE_DS + DENSE_RHS_COL] = pv ? g[b2] : 0.0;
+        const double g0 = pv ? g[0] : 0.0, g1 = pv ? g[1] : 0.0, g2 = pv ? g[2] : 0.0;
+        Zt[(ps * 3 + 0) * DENSE_DS + DENSE_RHS_COL] = il[0] * g0;
+        Zt[(ps * 3 + 1) * DENSE_DS + DENSE_RHS_COL] = il[1] * g0 + il[2] * g1;
+        Zt[(ps * 3 + 2) * DENSE_DS + DENSE_RHS_COL] = il[3] * g0 + il[4] * g1 + il[5] * g2;
       }
       for (int ri = 0; ri < rounds; ri++) {
         const int oi = s + ri * 8 + gl;
@@ -727,18 +728,13 @@ __global__ void __launch_bounds__(DP_THREADS)
               w[q][2] = Jc[a + q] * Jp[2] + Jc[6 + a + q] * Jp[5];
             }
             const int col = 6 * ci + a;
-#pragma unroll
-            for (int b2 = 0; b2 < 3; b2++)
-              *reinterpret_cast<double2*>(&Wt[(ps * 3 + b2) * DENSE_DS + col]) = make_double2(w[0][b2], w[1][b2]);
-            *reinterpret_cast<double2*>(&Yt[(ps * 3 + 0) * DENSE_DS + col]) =
-                make_double2(w[0][0] * hi[0] + w[0][1] * hi[1] + w[0][2] * hi[2],
-                             w[1][0] * hi[0] + w[1][1] * hi[1] + w[1][2] * hi[2]);
-            *reinterpret_cast<double2*>(&Yt[(ps * 3 + 1) * DENSE_DS + col]) =
-                make_double2(w[0][0] * hi[1] + w[0][1] * hi[3] + w[0][2] * hi[4],
-                             w[1][0] * hi[1] + w[1][1] * hi[3] + w[1][2] * hi[4]);
-            *reinterpret_cast<double2*>(&Yt[(ps * 3 + 2) * DENSE_DS + col]) =
-                make_double2(w[0][0] * hi[2] + w[0][1] * hi[4] + w[0][2] * hi[5],
-                             w[1][0] * hi[2] + w[1][1] * hi[4] + w[1][2] * hi[5]);
+            *reinterpret_cast<double2*>(&Zt[(ps * 3 + 0) * DENSE_DS + col]) =
+                make_double2(il[0] * w[0][0], il[0] * w[1][0]);
+            *reinterpret_cast<double2*>(&Zt[(ps * 3 + 1) * DENSE_DS + col]) =
+                make_double2(il[1] * w[0][0] + il[2] * w[0][1], il[1] * w[1][0] + il[2] * w[1][1]);
+            *reinterpret_cast<double2*>(&Zt[(ps * 3 + 2) * DENSE_DS + col]) =
+                make_double2(il[3] * w[0][0] + il[4] * w[0][1] + il[5] * w[0][2],
+                             il[3] * w[1][0] + il[4] * w[1][1] + il[5] * w[1][2]);
           }
         }
       }
@@ -746,9 +742,9 @@ __global__ void __launch_bounds__(DP_THREADS)
     pair_barrier(pair);
     // ---- contractions over the pair's 8 points
     if (half == 0)
-      dense_contract<0, FULL>(Yt, Wt, Jt, lane, sacc, hacc);
+      dense_contract<0, FULL>(Zt, Jt, lane, sacc, hacc);
     else
-      dense_contract<1, FULL>(Yt, Wt, Jt, lane, sacc, hacc);
+      dense_contract<1, FULL>(Zt, Jt, lane, sacc, hacc);
     if (ptid < n) {  // one column of g_c (and of the Schur right-hand side) per thread of the pair
       const int c2 = ptid / 6;
       double a2 = 0;
@@ -770,10 +766,8 @@ __global__ void __launch_bounds__(DP_THREADS)
             *reinterpret_cast<double2*>(&Jt[(ps * 2 + 1) * DENSE_DS + 6 * ci + a]) = z;
             if (FULL) {
 #pragma unroll
-              for (int c2 = 0; c2 < 3; c2++) {
-                *reinterpret_cast<double2*>(&Wt[(ps * 3 + c2) * DENSE_DS + 6 * ci + a]) = z;
-                *reinterpret_cast<double2*>(&Yt[(ps * 3 + c2) * DENSE_DS + 6 * ci + a]) = z;
-              }
+              for (int c2 = 0; c2 < 3; c2++)
+                *reinterpret_cast<double2*>(&Zt[(ps * 3 + c2) * DENSE_DS + 6 * ci + a]) = z;
             }
           }
           Rt[(ps * 2 + 0) * DENSE_RC + ci] = 0.0;

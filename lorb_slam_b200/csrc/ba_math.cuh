@@ -144,7 +144,9 @@ __device__ __forceinline__ double obs_cost(const double* __restrict__ R, const d
 // returns false when a Cholesky pivot is not positive.  The three pivots go through rsqrt (one
 // MUFU seed + Newton steps each) instead of three square roots and six divisions: this function
 // runs once per point and pass in every build kernel, where it was 8 % of the issue slots.
-__device__ __forceinline__ bool inv3_spd(const double h[6], double hi[6]) {
+// il (optional): the inverse Cholesky factor L^-1 = [i00 0 0; i10 i11 0; i20 i21 i22] as
+// (i00, i10, i11, i20, i21, i22), H^-1 = L^-T L^-1.
+__device__ __forceinline__ bool inv3_spd(const double h[6], double hi[6], double* il = nullptr) {
   const double l00s = h[0];
   if (!(l00s > 0.0)) return false;
   const double i00 = rsqrt(l00s);
@@ -167,6 +169,10 @@ __device__ __forceinline__ bool inv3_spd(const double h[6], double hi[6]) {
   hi[3] = i11 * i11 + i21 * i21;
   hi[4] = i21 * i22;
   hi[5] = i22 * i22;
+  if (il) {
+    il[0] = i00; il[1] = i10; il[2] = i11;
+    il[3] = i20; il[4] = i21; il[5] = i22;
+  }
   return true;
 }
 

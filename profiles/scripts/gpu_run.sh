@@ -1,13 +1,11 @@
 set -x
-nvidia-smi -L | wc -l
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29711 profiles/scripts/ba_shard_soak.py 60 > gpurun_out/soak_shard2.log 2>&1; echo rc=$?; tail -6 gpurun_out/soak_shard2.log | cut -c1-300
-timeout 600 python -m pytest tests/test_multi_gpu.py -x -q -m gpu 2>&1 | tail -3
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29752 bench.py --gpus 2 --steps 10 --warmup 3 --no-extras > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err; echo rc=$?
+timeout 900 python -m pytest tests/test_ba_gpu.py tests/test_host_dropin_gpu.py tests/test_edge_cases_gpu.py tests/test_ref_golden_gpu.py -x -q -m gpu 2>&1 | tail -3
+for W in ba_batched; do
+timeout 600 python bench.py --workload $W --no-cpu-baseline > gpurun_out/bench_$W.json 2> gpurun_out/bench_$W.err; echo rc=$?; tail -2 gpurun_out/bench_$W.err
 python - <<PY
 import json
-d=json.loads(open('gpurun_out/bench_n2.json').read().strip().split('\n')[-1])
-print('N2 sweep', d['value']/1e9, 'e2e', d['e2e']['value']/1e9)
-print('full', d['full_sweep']['value']/1e9, d['full_sweep']['wall_s'], d['full_sweep']['parity']['ok'])
-for k in ('ba_batched','ba_large'):
-    b=d[k]; print(k, b['value']/1e9, 'e2e', b['e2e']['value']/1e9, b['roofline']['ms_per_attempt_by_part'], b['parity']['ok'])
+b=json.loads(open('gpurun_out/bench_$W.json').read().strip().split('\n')[-1])
+print('$W', b['value']/1e9, 'e2e', b['e2e']['value']/1e9, b['roofline']['ms_per_attempt_by_part'], b['parity'])
 PY
+done
+LORB_SOAK_SEED=404 timeout 300 python profiles/scripts/ba_soak.py 80 > gpurun_out/soak_ba.log 2>&1; echo rc=$?; tail -3 gpurun_out/soak_ba.log | cut -c1-300
