@@ -479,69 +479,73 @@ __global__ void __launch_bounds__(BA_THREADS)
 
 // ---- dense path, n = 6C <= 64 and unique (point, camera) pairs (BASELINE configs 3 / 4).
 // H_cc, g_c, the Schur right-hand side and the Schur products of a window are dense contractions
-// over its points.  The CTA is four independent WARP PAIRS; a pair owns 8 points per round and
-// keeps private dense tiles of them in shared memory:
-//     J  [16 x 64]  rows (point slot, residual component), columns camera parameters
-//     R  [16 x 16]  residual of that row per camera
-//     Z = L^-1 W^T  [24 x 64]  rows (point slot, point coordinate), H_pp^-1 = L^-T L^-1
-// After one 64-thread named barrier the pair contracts its own tiles on the fp64 tensor cores
-// (DMMA m8n8k4): S_pair += Z^T Z (= W H_pp^-1 W^T) as 36 upper 8x8 tiles (18 per warp,
-// compile-time lists; both fragments of a tile pair come from the same 8 loads per k-step) and
-// H_cc += J^T J on the 13 tiles that meet a 6x6 diagonal block; g_c is one column dot product per
-// thread, the Schur right-hand side comes out of the same contraction (L^-1 g_p sits in a spare
-// column of Z).  A second pair
+// over its points.  The CTA is three independent GROUPS of four warps; a group owns 16 points per
+// round and keeps private dense tiles of them in shared memory:
+//     J  [32 x 64]  rows (point slot, residual component), columns camera parameters
+//     R  [32 x 16]  residual of that row per camera
+//     Z = L^-1 W^T  [48 x 64]  rows (point slot, point coordinate), H_pp^-1 = L^-T L^-1
+// After one 128-thread named barrier the group contracts its own tiles on the fp64 tensor cores
+// (DMMA m8n8k4): S_group += Z^T Z (= W H_pp^-1 W^T) as 36 upper 8x8 tiles (10 / 10 / 8 / 8 per
+// warp, compile-time lists; both fragments of a tile pair come from the same loads: 4 or 6 per
+// k-step) and H_cc += J^T J on the 13 tiles that meet a 6x6 diagonal block; g_c is a column dot
+// product per thread, the Schur right-hand side comes out of the same contraction (L^-1 g_p sits in
+// a spare column of Z).  Four warps per group instead of two (round 2): a warp carries 24-26
+// accumulator doubles instead of 50, which brings the kernel from 255 registers and 8 warps per SM
+// to <= 168 and 12.  A second group
 // barrier, then every lane clears exactly what it stored.  No block-wide barrier and no atomic
 // in the round loop; the pairs are reduced through shared memory once at the end and the CTA
 // flushes one partial result.
 constexpr int DENSE_RHS_COL = 60;         // 6C <= 64 means C <= 10: columns 60..63 of the tiles are never a camera's
 static_assert(DENSE_N == 64 && DENSE_RHS_COL >= (DENSE_N / 6) * 6 && DENSE_RHS_COL < DENSE_N, "spare column");
-constexpr int DP_PTS = 8;                 // points per warp pair and round
+constexpr int DP_GW = 4;                  // warps per point group
+constexpr int DP_PTS = 4 * DP_GW;         // points per group and round
 constexpr int DP_KW = 3 * DP_PTS;         // rows of the Z tile
 constexpr int DP_KJ = 2 * DP_PTS;         // rows of the J / R tiles
-constexpr int DP_PAIR = DP_KW * DENSE_DS + DP_KJ * DENSE_DS + DP_KJ * DENSE_RC;  // doubles
-constexpr int DP_THREADS = 256;           // 4 warp pairs (384 threads = 6 pairs fit in smem but spill: measured slower)
-constexpr int DP_NPAIR = DP_THREADS / 64;
-constexpr int DP_SMEM_DOUBLES = DP_NPAIR * DP_PAIR;
-static_assert(DP_PAIR % 2 == 0 && DENSE_DS % 2 == 0 && (DP_KW * DENSE_DS) % 2 == 0, "128-bit tile stores stay aligned");
+constexpr int DP_GROUP = DP_KW * DENSE_DS + DP_KJ * DENSE_DS + DP_KJ * DENSE_RC;  // doubles
+constexpr int DP_THREADS = 384;           // 3 groups of 4 warps: 12 warps per SM at <= 168 registers
+constexpr int DP_NGROUP = DP_THREADS / (32 * DP_GW);
+constexpr int DP_SMEM_DOUBLES = DP_NGROUP * DP_GROUP;
+static_assert(DP_GROUP % 2 == 0 && DENSE_DS % 2 == 0 && (DP_KW * DENSE_DS) % 2 == 0, "128-bit tile stores stay aligned");
 static_assert(DP_SMEM_DOUBLES >= DENSE_N * DENSE_N + HCC * 10 + 2 * DENSE_N + 16, "reduction buffer fits");
 
-__device__ __forceinline__ void pair_barrier(int pair) {
-  asm volatile("bar.sync %0, 64;" ::"r"(pair + 1) : "memory");
+__device__ __forceinline__ void group_barrier(int grp) {
+  asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(32 * DP_GW) : "memory");
 }
 
-// Upper 8x8 tiles of the 64x64 product, split between the two warps of a pair.
-template <int HALF>
+// Upper 8x8 tiles of the 64x64 product, split between the four warps of a group: the two diagonal
+// 4x4 tile blocks (10 upper tiles each, 4 distinct fragments per k-step) and the two halves of the
+// off-diagonal block (8 tiles, 6 fragments); the 13 tiles of J^T J that meet a 6x6 diagonal block
+// (block boundaries 24 and 48 are tile aligned) go 2 / 2 / 5 / 4, which evens out the DMMA counts.
+template <int Q>
 struct DenseTiles {
-  static constexpr int NS = 18;
-  static constexpr int NH = HALF == 0 ? 7 : 6;
+  static constexpr int NS = Q < 2 ? 10 : 8;
+  static constexpr int NH = Q < 2 ? 2 : (Q == 2 ? 5 : 4);
   __device__ static constexpr int si(int t) {
-    constexpr int a0[18] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 1, 1, 2, 2, 2};
-    constexpr int a1[18] = {2, 2, 2, 3, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 6, 6, 7};
-    return HALF == 0 ? a0[t] : a1[t];
+    constexpr int a[4][10] = {{0, 0, 0, 0, 1, 1, 1, 2, 2, 3}, {4, 4, 4, 4, 5, 5, 5, 6, 6, 7},
+                              {0, 0, 0, 0, 1, 1, 1, 1, 0, 0}, {2, 2, 2, 2, 3, 3, 3, 3, 0, 0}};
+    return a[Q][t];
   }
   __device__ static constexpr int sj(int t) {
-    constexpr int a0[18] = {0, 1, 2, 3, 4, 5, 6, 7, 1, 2, 3, 4, 5, 6, 7, 2, 3, 4};
-    constexpr int a1[18] = {5, 6, 7, 3, 4, 5, 6, 7, 4, 5, 6, 7, 5, 6, 7, 6, 7, 7};
-    return HALF == 0 ? a0[t] : a1[t];
+    constexpr int a[4][10] = {{0, 1, 2, 3, 1, 2, 3, 2, 3, 3}, {4, 5, 6, 7, 5, 6, 7, 6, 7, 7},
+                              {4, 5, 6, 7, 4, 5, 6, 7, 0, 0}, {4, 5, 6, 7, 4, 5, 6, 7, 0, 0}};
+    return a[Q][t];
   }
-  // tiles of J^T J that intersect a diagonal 6x6 block (block boundaries 24 and 48 are tile aligned)
   __device__ static constexpr int hi(int t) {
-    constexpr int a0[7] = {0, 0, 1, 1, 2, 3, 3};
-    constexpr int a1[7] = {4, 4, 5, 6, 6, 7, 7};
-    return HALF == 0 ? a0[t] : a1[t];
+    constexpr int a[4][5] = {{0, 1, 0, 0, 0}, {4, 5, 0, 0, 0}, {0, 1, 2, 3, 3}, {4, 6, 6, 7, 0}};
+    return a[Q][t];
   }
   __device__ static constexpr int hj(int t) {
-    constexpr int a0[7] = {0, 1, 1, 2, 2, 3, 4};
-    constexpr int a1[7] = {4, 5, 5, 6, 7, 7, 7};
-    return HALF == 0 ? a0[t] : a1[t];
+    constexpr int a[4][5] = {{0, 1, 0, 0, 0}, {4, 5, 0, 0, 0}, {1, 2, 2, 3, 4}, {5, 6, 7, 7, 0}};
+    return a[Q][t];
   }
 };
+constexpr int DP_NS_MAX = 10, DP_NH_MAX = 5;
 
-template <int HALF, bool FULL>
+template <int Q, bool FULL>
 __device__ __forceinline__ void dense_contract(const double* __restrict__ Zt,
                                                const double* __restrict__ Jt, int lane,
-                                               double (&sacc)[18][2], double (&hacc)[7][2]) {
-  using T = DenseTiles<HALF>;
+                                               double (&sacc)[DP_NS_MAX][2], double (&hacc)[DP_NH_MAX][2]) {
+  using T = DenseTiles<Q>;
   const int fo = (lane & 3) * DENSE_DS + (lane >> 2);
 #pragma unroll
   for (int k0 = 0; k0 < DP_KJ; k0 += 4) {
@@ -563,11 +567,13 @@ __device__ __forceinline__ void dense_contract(const double* __restrict__ Zt,
   }
 }
 
-// Adds this warp's accumulators into the CTA's reduction buffers (called by one pair at a time).
-template <int HALF, bool FULL>
+// Adds this warp's accumulators into the CTA's reduction buffers (called by one group at a time;
+// the four warps of a group own disjoint tiles).
+template <int Q, bool FULL>
 __device__ __forceinline__ void dense_reduce(double* __restrict__ Sbuf, double* __restrict__ Hbuf, int lane,
-                                             int n, const double (&sacc)[18][2], const double (&hacc)[7][2]) {
-  using T = DenseTiles<HALF>;
+                                             int n, const double (&sacc)[DP_NS_MAX][2],
+                                             const double (&hacc)[DP_NH_MAX][2]) {
+  using T = DenseTiles<Q>;
 #pragma unroll
   for (int t = 0; t < T::NH; t++)
 #pragma unroll
@@ -597,8 +603,8 @@ __global__ void __launch_bounds__(DP_THREADS)
   __shared__ double cs[CS_MAX_CAMS * CS_BUILD];  // the window's cameras (6C <= 64: at most 10)
   extern __shared__ __align__(16) double dsm[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, gl = lane & 7, gw = lane >> 3;
-  const int pair = warp >> 1, half = warp & 1, ptid = tid & 63;
-  double* const Zt = dsm + pair * DP_PAIR;
+  const int grp = warp / DP_GW, q = warp % DP_GW, gtid = tid % (32 * DP_GW);
+  double* const Zt = dsm + grp * DP_GROUP;
   double* const Jt = Zt + DP_KW * DENSE_DS;
   double* const Rt = Jt + DP_KJ * DENSE_DS;
   for (int i = tid; i < DP_SMEM_DOUBLES; i += DP_THREADS) dsm[i] = 0.0;
@@ -612,13 +618,14 @@ __global__ void __launch_bounds__(DP_THREADS)
   cs_fill(p, cams, camrot, cs, CS_BUILD, tid, DP_THREADS);
   __syncthreads();
   double cost_acc = 0, gmax_acc = 0, xn_acc = 0, bad_acc = 0;
-  double sacc[18][2], hacc[7][2], gown = 0.0;
+  double sacc[DP_NS_MAX][2], hacc[DP_NH_MAX][2], gown = 0.0;
 #pragma unroll
-  for (int t = 0; t < 18; t++) sacc[t][0] = sacc[t][1] = 0.0;
+  for (int t = 0; t < DP_NS_MAX; t++) sacc[t][0] = sacc[t][1] = 0.0;
 #pragma unroll
-  for (int t = 0; t < 7; t++) hacc[t][0] = hacc[t][1] = 0.0;
-  const int ps = half * 4 + gw;  // point slot inside the pair
-  // block-uniform trip count (pair barriers inside)
+  for (int t = 0; t < DP_NH_MAX; t++) hacc[t][0] = hacc[t][1] = 0.0;
+  const int ps = q * 4 + gw;  // point slot inside the group
+  const int gcol = gtid & 63, grow0 = (gtid >> 6) * (DP_KJ / 2);  // g_c: a column and half of the J rows per thread
+  // block-uniform trip count (group barriers inside)
   for (int blk = blockIdx.x * (DP_THREADS / 8); blk < p.P; blk += gridDim.x * (DP_THREADS / 8)) {
     const int pt = blk + warp * 4 + gw;
     const bool pv = pt < p.P;
@@ -698,7 +705,7 @@ __global__ void __launch_bounds__(DP_THREADS)
 #pragma unroll
         for (int a = 0; a < 6; a++) il[a] = 0.0;
       }
-      // ---- phase 2: Z_i = L^-1 W_i^T into the pair's tile (H_pp^-1 = L^-T L^-1, so the Schur
+      // ---- phase 2: Z_i = L^-1 W_i^T into the group's tile (H_pp^-1 = L^-T L^-1, so the Schur
       // product W H_pp^-1 W^T of the point is Z^T Z: one tile, contracted with itself).
       // L^-1 g_p rides in the spare column DENSE_RHS_COL: the contraction then leaves the Schur
       // right-hand side W H_pp^-1 g_p in that column of the product (rewritten every round: never cleared)
@@ -739,20 +746,23 @@ __global__ void __launch_bounds__(DP_THREADS)
         }
       }
     }
-    pair_barrier(pair);
-    // ---- contractions over the pair's 8 points
-    if (half == 0)
-      dense_contract<0, FULL>(Zt, Jt, lane, sacc, hacc);
-    else
-      dense_contract<1, FULL>(Zt, Jt, lane, sacc, hacc);
-    if (ptid < n) {  // one column of g_c (and of the Schur right-hand side) per thread of the pair
-      const int c2 = ptid / 6;
+    group_barrier(grp);
+    // ---- contractions over the group's 16 points
+    switch (q) {
+      case 0: dense_contract<0, FULL>(Zt, Jt, lane, sacc, hacc); break;
+      case 1: dense_contract<1, FULL>(Zt, Jt, lane, sacc, hacc); break;
+      case 2: dense_contract<2, FULL>(Zt, Jt, lane, sacc, hacc); break;
+      default: dense_contract<3, FULL>(Zt, Jt, lane, sacc, hacc); break;
+    }
+    if (gcol < n) {  // g_c: one column and half of the rows per thread of the group
+      const int c2 = gcol / 6;
       double a2 = 0;
 #pragma unroll
-      for (int k2 = 0; k2 < DP_KJ; k2++) a2 += Jt[k2 * DENSE_DS + ptid] * Rt[k2 * DENSE_RC + c2];
+      for (int k2 = 0; k2 < DP_KJ / 2; k2++)
+        a2 += Jt[(grow0 + k2) * DENSE_DS + gcol] * Rt[(grow0 + k2) * DENSE_RC + c2];
       gown += a2;
     }
-    pair_barrier(pair);
+    group_barrier(grp);
     // ---- clear exactly what this lane stored
     for (int ri = 0; ri < rounds; ri++) {
       const int oi = s + ri * 8 + gl;
@@ -783,13 +793,17 @@ __global__ void __launch_bounds__(DP_THREADS)
   double* const Gbuf = Hbuf + HCC * 10 + 6;        // g_c
   for (int i = tid; i < DENSE_N * DENSE_N + HCC * 10 + 6 + 2 * DENSE_N; i += DP_THREADS) dsm[i] = 0.0;
   __syncthreads();
-  for (int pp = 0; pp < DP_NPAIR; pp++) {
-    if (pair == pp) {
-      if (half == 0)
-        dense_reduce<0, FULL>(Sbuf, Hbuf, lane, n, sacc, hacc);
-      else
-        dense_reduce<1, FULL>(Sbuf, Hbuf, lane, n, sacc, hacc);
-      if (ptid < n) Gbuf[ptid] += gown;
+  for (int pp = 0; pp < 2 * DP_NGROUP; pp++) {  // (group, row half of the g_c partials)
+    if (grp == (pp >> 1)) {
+      if ((pp & 1) == 0) {
+        switch (q) {
+          case 0: dense_reduce<0, FULL>(Sbuf, Hbuf, lane, n, sacc, hacc); break;
+          case 1: dense_reduce<1, FULL>(Sbuf, Hbuf, lane, n, sacc, hacc); break;
+          case 2: dense_reduce<2, FULL>(Sbuf, Hbuf, lane, n, sacc, hacc); break;
+          default: dense_reduce<3, FULL>(Sbuf, Hbuf, lane, n, sacc, hacc); break;
+        }
+      }
+      if (gcol < n && (gtid >> 6) == (pp & 1)) Gbuf[gcol] += gown;
     }
     __syncthreads();
   }
