@@ -3189,7 +3189,22 @@ static int problem_solve(lorb_ba_problem* pb, const lorb_ba_options* optp, int s
                                        (int)backsub_smem));
   const dim3 grid_backsub(backsub_smem > 16 * 1024 ? std::min(gx_pts, std::max(1, 2 * c->sm_count / nw)) : gx_pts, nw);
   const int ppc = DP_THREADS / 8;  // points per CTA round of the dense path
-  const dim3 grid_dense(std::max(1, std::min((pb->maxP + ppc - 1) / ppc, std::max(1, c->sm_count * 8 / nw))), nw);
+  // CTAs per window of the dense build: a CTA pays about two rounds' worth of prologue, reduction
+  // and flush, and CTAs run in waves of one per SM -- minimise waves x (rounds per CTA + 2)
+  int gx_dense = 1;
+  {
+    const int gx_hi = std::max(1, std::min((pb->maxP + ppc - 1) / ppc, std::max(1, c->sm_count * 8 / nw)));
+    long long best = -1;
+    for (int g = 1; g <= gx_hi; g++) {
+      const long long waves = ((long long)nw * g + c->sm_count - 1) / c->sm_count;
+      const long long cost = waves * ((pb->maxP + (long long)ppc * g - 1) / ((long long)ppc * g) + 2);
+      if (best < 0 || cost < best) {
+        best = cost;
+        gx_dense = g;
+      }
+    }
+  }
+  const dim3 grid_dense(gx_dense, nw);
   const dim3 grid_cam((pb->maxC + 127) / 128, nw);
   const int nmax = 6 * pb->maxC;
   const dim3 grid_fin(std::max(1, std::min(c->sm_count * 2 / std::min(nw, c->sm_count) + 1, (nmax * nmax + 255) / 256)), nw);
