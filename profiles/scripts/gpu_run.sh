@@ -1,10 +1,5 @@
 set -x
-for NW in 8 64 128 256 512; do
-timeout 600 python bench.py --workload ba_batched --windows-total $NW --no-cpu-baseline > gpurun_out/bench_bb_$NW.json 2> gpurun_out/bench_bb_$NW.err; echo rc=$?
-python - <<PY
-import json
-b=json.loads(open('gpurun_out/bench_bb_$NW.json').read().strip().split('\n')[-1])
-print('$NW windows', b['value']/1e9, 'e2e', b['e2e']['value']/1e9, b['roofline']['ms_per_attempt_by_part'], b['parity']['ok'])
-PY
-done
-timeout 300 python -m pytest tests/test_ba_gpu.py -x -q -m gpu 2>&1 | tail -2
+LORB_SOAK_SEED=2031 timeout 900 python profiles/scripts/orb_soak.py 200 > gpurun_out/soak_orb.log 2>&1; echo rc=$?; tail -2 gpurun_out/soak_orb.log
+LORB_SOAK_SEED=9 timeout 600 python profiles/scripts/stereo_soak.py 30 > gpurun_out/soak_stereo.log 2>&1; echo rc=$?; tail -2 gpurun_out/soak_stereo.log
+LORB_SOAK_SEED=505 timeout 300 python profiles/scripts/match_soak.py 200 > gpurun_out/soak_match.log 2>&1; echo rc=$?; tail -1 gpurun_out/soak_match.log
+LORB_SOAK_SEED=606 timeout 300 python profiles/scripts/ba_soak.py 160 > gpurun_out/soak_ba.log 2>&1; echo rc=$?; tail -3 gpurun_out/soak_ba.log | cut -c1-250

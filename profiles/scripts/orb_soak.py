@@ -1,5 +1,6 @@
 """Soak: lorb_orb_extract against the compiled reference (oracle/_ref) on many random frames of
 varied size, texture, feature budget and thresholds.  Prints the number of frames that differ."""
+import os
 import sys
 import time
 
@@ -11,7 +12,7 @@ from oracle import reflib  # noqa: E402
 
 n_frames = int(sys.argv[1]) if len(sys.argv) > 1 else 200
 pattern = np.load("tests/golden/orb_golden.npz")["orb/pattern"].astype(np.int32)
-rng = np.random.default_rng(2026)
+rng = np.random.default_rng(int(os.environ.get("LORB_SOAK_SEED", 2026)))
 bad = 0
 t0 = time.time()
 with capi.Context(0) as ctx:
@@ -20,7 +21,7 @@ with capi.Context(0) as ctx:
         h = int(rng.choice([240, 376, 480, 512, 720]))
         if round(np.float32(w - 32) / np.float32(h - 32)) < 1:
             continue
-        img = synth.make_orb_image(1000 + f, w, h)
+        img = synth.make_orb_image(1000 + f + 7919 * (int(os.environ.get("LORB_SOAK_SEED", 2026)) - 2026), w, h)
         kind = f % 4
         if kind == 1:  # low contrast everywhere: minThFAST cells
             img = (128 + (img.astype(np.float32) - 128) * 0.15).astype(np.uint8)

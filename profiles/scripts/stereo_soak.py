@@ -1,4 +1,5 @@
 """Soak: lorb_stereo_frame against the compiled reference's extractor + Frame::ComputeStereoMatches."""
+import os
 import sys
 
 import numpy as np
@@ -9,13 +10,13 @@ from oracle import reflib  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 30
 pattern = np.load("tests/golden/orb_golden.npz")["orb/pattern"].astype(np.int32)
-rng = np.random.default_rng(5)
+rng = np.random.default_rng(int(os.environ.get("LORB_SOAK_SEED", 5)))
 bad = 0
 with capi.Context(0) as ctx:
     for s in range(n):
         w, h = int(rng.choice([512, 640, 752, 1024])), int(rng.choice([376, 480]))
         nf = int(rng.choice([500, 1000, 2000]))
-        st0 = synth.make_stereo_pair(8, 300 + s, w, h)
+        st0 = synth.make_stereo_pair(8, 300 + s + 1009 * (int(os.environ.get("LORB_SOAK_SEED", 5)) - 5), w, h)
         left, right = st0["pyr_left"][0], st0["pyr_right"][0]
         mbf, mb = float(st0["mbf"]), float(st0["mb"])
         L, R, ur, dp, nm = ctx.stereo_frame(left, right, pattern, mbf, mb, nfeatures=nf)
