@@ -787,6 +787,7 @@ def run_ba_large(args, rank, world, local, steps=None, want_cpu=True):
     dt = ev0.elapsed_time(ev1) * 1e-3
     launches = ctx.launch_count - l0
     prof = [ctx.profile_read(k) for k in range(3)]
+    coll_ms, coll_n = ctx.profile_read(4)  # the two all-reduces of every attempt, as seen by this rank
     ctx.profile(False)
     clocks = sampler.stop() if rank == 0 else None
     dt_max = _max_over_ranks(dt, world, local)
@@ -865,6 +866,12 @@ def run_ba_large(args, rank, world, local, steps=None, want_cpu=True):
                "lm_iterations": s["iterations"], "final_cost": s["final_cost"], "parity": parity}
         res["roofline"], res["roofline_hbm"] = _ba_rooflines(
             ctx, len(sh["obs_cam"]), 7.5, 6 * args.large_cams, prof, "ba_schur_pairs_kernel")
+        attempts = max(1, prof[0][1])
+        res["roofline"]["ms_per_attempt_by_part"]["collectives"] = coll_ms / attempts
+        res["roofline"]["collectives_note"] = (
+            "rank 0's CUDA-event brackets around the all-reduce of [packed S | H_cc | g_c | rhs | scalars | slots] "
+            "(%.1f MB) after the build pass and of four scalars after the back-substitution, both per attempt; "
+            "includes the wait for the slowest rank's build" % (6 * args.large_cams * (6 * args.large_cams + 7) * 4 / 1e6))
         if world == 1 and want_cpu:
             res["cpu_baseline"] = cpu_baseline_ba_large(pb)
     ctx.dist_finalize()

@@ -634,10 +634,12 @@ int lorb_microbench_fp64(lorb_ctx* ctx, int kind, int iters, double* flop_per_s)
 /* Device-side timing of the library's own kernels, for bench.py's roofline: while enabled,
  * the BA solver brackets its dominant kernels with CUDA events on the ctx stream
  * (slot 0 = build pass of an LM attempt, 1 = back-substitution, 2 = reduced-system solve),
- * the tensor-core sweep its main kernel (slot 3).
+ * the tensor-core sweep its main kernel (slot 3), the sharded BA its collectives (slot 4: the
+ * all-reduce after the build pass and the one after the back-substitution of every attempt, as
+ * seen by this rank, i.e. including the wait for the slowest rank).
  * lorb_ctx_profile_read synchronises the stream and returns the accumulated milliseconds and
  * the number of bracketed launches of a slot since the last lorb_ctx_profile(ctx, 1). */
-#define LORB_PROF_SLOTS 4
+#define LORB_PROF_SLOTS 5
 int lorb_ctx_profile(lorb_ctx* ctx, int enable);
 int lorb_ctx_profile_read(lorb_ctx* ctx, int slot, double* total_ms, long long* count);
 

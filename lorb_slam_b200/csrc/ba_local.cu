@@ -3303,8 +3303,10 @@ static int problem_solve(lorb_ba_problem* pb, const lorb_ba_options* optp, int s
     LORB_TRY(launch_build(true, 0));
     prof_end(c, 0);
     if (sharded) {  // ONE all-reduce per build pass: packed S, H_cc, g_c, Schur rhs, scalars, gradient slots
+      prof_begin(c, 4);
       LORB_LAUNCH(c, ba_gslot_kernel, 1, 1, 0, dp);
       LORB_TRY(dist_allreduce_sum(c, d0.lin, pb->lin_doubles_max));
+      prof_end(c, 4);
     }
     prof_begin(c, 2);
     if (small) {
@@ -3323,8 +3325,10 @@ static int problem_solve(lorb_ba_problem* pb, const lorb_ba_options* optp, int s
       LORB_LAUNCH(c, ba_backsub_kernel<false>, grid_pts, BA_THREADS, 0, dp, opt, fuse_control, d_active);
     prof_end(c, 1);
     if (sharded) {
+      prof_begin(c, 4);
       LORB_TRY(dist_allreduce_sum(c, &d0.st->acc_cost2, 4));
       LORB_LAUNCH(c, ba_control_kernel, nw, 1, 0, dp, opt, d_active);
+      prof_end(c, 4);
     }
     if ((it + 1) % poll_every == 0 && it + 1 < opt.max_num_iterations) {
       // every rank takes the same decisions (same bits in, see ba_candcam_kernel); the max over

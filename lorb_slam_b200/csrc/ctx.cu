@@ -107,8 +107,8 @@ struct Prof {
   struct Ev { cudaEvent_t a, b; int slot; };
   std::vector<Ev> ev;
   size_t used = 0;
-  double total[LORB_PROF_SLOTS] = {0, 0, 0, 0};
-  long long count[LORB_PROF_SLOTS] = {0, 0, 0, 0};
+  double total[LORB_PROF_SLOTS] = {};
+  long long count[LORB_PROF_SLOTS] = {};
 };
 
 void prof_begin(lorb_ctx* c, int slot) {
