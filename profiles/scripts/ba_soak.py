@@ -41,6 +41,20 @@ with capi.Context(0) as ctx:
             else:
                 bad += 1
                 print("MISMATCH", s, C, P, k, ff, it, str(e)[:200].replace("\n", " "))
+    # pose-only BA (BA::ProjectPoseOptimization): observation counts from the minimum up, good and bad starts
+    bad_p = 0
+    for s in range(n):
+        m = int(rng.choice([3, 4, 6, 10, 50, 300, 2000, 5000]))
+        po = synth.make_pose_only(4000 + s, m, pixel_noise=float(rng.choice([0.0, 1.0, 3.0])),
+                                  pose_noise=(float(rng.choice([0.0, 0.02, 0.3])), float(rng.choice([0.0, 0.1, 1.0]))))
+        it = int(rng.choice([1, 5, 50]))
+        rt, sm = ctx.ba_pose_only(po["xw"], po["uv"], po["K"], po["rt"], capi.ba_options(max_num_iterations=it))
+        ort, so = ref.ba_pose_only(po["xw"], po["uv"], po["K"], po["rt"], ref.ba_options(max_num_iterations=it))
+        if not (np.allclose(rt, ort, rtol=1e-6, atol=1e-8) and sm["iterations"] == so["iterations"]
+                and sm["termination"] == so["termination"]):
+            bad_p += 1
+            print("POSE MISMATCH", s, m, it, np.abs(rt - ort).max(), sm["iterations"], so["iterations"])
+    print("%d pose-only solves, %d differ" % (n, bad_p))
     # heterogeneous batches: windows of different solver paths (dense / privatised / work lists) in
     # one lorb_ba_local_batched call, every window against the oracle's single-window solve
     nb = bad_b = 0

@@ -12,7 +12,7 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 40
 legs = sys.argv[2].split(",") if len(sys.argv) > 2 else ["entry", "sweep"]  # entry points / keyframe-pair sweep
 verbose = len(sys.argv) > 3
 rng = np.random.default_rng(int(os.environ.get("LORB_SOAK_SEED", 31)))
-bad = {"proj_points": 0, "proj_frame": 0, "bf": 0, "frustum": 0, "stereo": 0, "sweep_tensor": 0, "sweep_popc": 0}
+bad = {"proj_points": 0, "proj_frame": 0, "bf": 0, "knn2": 0, "mp_desc": 0, "frustum": 0, "stereo": 0, "sweep_tensor": 0, "sweep_popc": 0}
 with capi.Context(0) as ctx:
     for s in range(n if "entry" in legs else 0):
         nk, npt = int(rng.integers(50, 3000)), int(rng.integers(50, 6000))
@@ -26,10 +26,22 @@ with capi.Context(0) as ctx:
         a, b = ctx.search_proj_frame(cur, last, th), reflib.search_proj_frame(cur, last, th)
         bad["proj_frame"] += not (a["n_matches"] == b["n_matches"] and np.array_equal(
             reflib.final_state_from_oracle(a["state_for_kp"], cur["kp_claim_obs"]), b["state_for_kp"]))
-        q = synth.descriptors_uniform(int(rng.integers(1, 1500)), rng)
-        t = synth.descriptors_noisy_copy(q[rng.integers(0, len(q), int(rng.integers(1, 1500)))], rng, 0.05)
+        big = 6000 if s % 5 == 0 else 1500  # every fifth round beyond one tile of the brute-force kernels
+        q = synth.descriptors_uniform(int(rng.integers(1, big)), rng)
+        t = synth.descriptors_noisy_copy(q[rng.integers(0, len(q), int(rng.integers(1, big)))], rng, 0.05)
+        if s % 7 == 3:  # ties everywhere
+            q, t = synth.descriptors_tie_stress(len(q), rng, 2, 3), synth.descriptors_tie_stress(len(t), rng, 2, 3)
         a, o = ctx.match_bf_crosscheck(q, t), ref.bf_crosscheck(q, t)
         bad["bf"] += not (np.array_equal(a["q"], o["q"]) and np.array_equal(a["t"], o["t"]) and np.array_equal(a["dist"], o["dist"]))
+        ki, kd, _ = ctx.match_knn2(q, t)
+        oi, od = ref.knn2(q, t)
+        bad["knn2"] += not (np.array_equal(ki, oi) and np.array_equal(kd, od))
+        sizes = rng.integers(0, 60, int(rng.integers(1, 400))).astype(np.int32)
+        offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+        dsc = synth.descriptors_tie_stress(int(offs[-1]), rng, 3, 4) if s % 2 else synth.descriptors_uniform(max(1, int(offs[-1])), rng)[:int(offs[-1])]
+        gb, gm = ctx.compute_descriptors(offs, dsc)
+        ob, om = ref.compute_descriptors(offs, dsc)
+        bad["mp_desc"] += not (np.array_equal(gb, ob) and np.array_equal(gm, om))
         fp = synth.make_frustum_points(int(rng.integers(10, 8000)), 900 + s)
         b, ow, lsf = reflib.frustum_project(fp)
         fp2 = dict(fp, ow=ow, log_sf=float(lsf))  # the reference's own camera centre (mTcw.inv())
