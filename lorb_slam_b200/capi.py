@@ -411,7 +411,7 @@ class Context:
         img = _arr(img, np.uint8)
         prm = OrbParams(nfeatures, scale_factor, nlevels, ini_th, min_th)
         pat = _arr(pattern, np.int32).reshape(-1)
-        cap = self.orb_max_keypoints(img.shape[1], img.shape[0], nfeatures, scale_factor, nlevels, ini_th, min_th)
+        cap = max(1, self.orb_max_keypoints(img.shape[1], img.shape[0], nfeatures, scale_factor, nlevels, ini_th, min_th))
         kx, ky = np.zeros(cap, np.float32), np.zeros(cap, np.float32)
         ko, ka = np.zeros(cap, np.int32), np.zeros(cap, np.float32)
         kr, ks = np.zeros(cap, np.float32), np.zeros(cap, np.float32)
@@ -432,7 +432,7 @@ class Context:
         assert left.shape == right.shape
         prm = OrbParams(nfeatures, scale_factor, nlevels, ini_th, min_th)
         pat = _arr(pattern, np.int32).reshape(-1)
-        cap = self.orb_max_keypoints(left.shape[1], left.shape[0], nfeatures, scale_factor, nlevels, ini_th, min_th)
+        cap = max(1, self.orb_max_keypoints(left.shape[1], left.shape[0], nfeatures, scale_factor, nlevels, ini_th, min_th))
         keep, views = [], []
         for _ in range(2):
             a = dict(x=np.zeros(cap, np.float32), y=np.zeros(cap, np.float32), octave=np.zeros(cap, np.int32),

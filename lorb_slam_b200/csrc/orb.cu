@@ -505,8 +505,14 @@ static int make_level_plan(const lorb_orb_params* p, int width, int height, OrbL
     const float bw = (float)(L->w[l] - 2 * ORB_EDGE + 6), bh = (float)(L->h[l] - 2 * ORB_EDGE + 6);
     L->n_cols[l] = (int)(bw / 30.f);  // W = 30 (:803)
     L->n_rows[l] = (int)(bh / 30.f);
-    // below one cell the reference divides by zero (:821-822)
-    LORB_REQUIRE(L->n_cols[l] >= 1 && L->n_rows[l] >= 1, "pyramid level smaller than one 30 px cell + margins");
+    LORB_REQUIRE(L->w[l] >= 7 && L->h[l] >= 7, "pyramid level smaller than the 7 x 7 blur kernel");
+    if (bw < 30.f || bh < 30.f) {
+      // Below one cell the reference computes nCols (or nRows) = 0, divides by it (:821-822) and then
+      // loops over no cells: the level is still part of the pyramid but yields no keypoints.  Same here.
+      L->n_cols[l] = L->n_rows[l] = 0;
+      L->w_cell[l] = L->h_cell[l] = 1;
+      continue;
+    }
     L->w_cell[l] = (int)ceilf(bw / L->n_cols[l]);
     L->h_cell[l] = (int)ceilf(bh / L->n_rows[l]);
     LORB_REQUIRE(L->w[l] - 2 * ORB_EDGE + 6 < 4096 && L->h[l] - 2 * ORB_EDGE + 6 < 4096, "image larger than 4096 px");
@@ -734,7 +740,7 @@ struct OrbPipeline {
     }
     for (int l = 0; l < nl; l++) {
       const int bw = L.w[l] - 2 * ORB_EDGE + 6, bh = L.h[l] - 2 * ORB_EDGE + 6;
-      n_ini[l] = std::max(1, (int)roundf((float)bw / bh));
+      n_ini[l] = L.n_cols[l] > 0 ? std::max(1, (int)roundf((float)bw / bh)) : 1;  // (a level without cells has no quadtree)
       out_cap[l] = qt_out_cap(L.n_features[l], n_ini[l]);
       lvl_key_cap[l] = L.n_cols[l] * L.n_rows[l] * slot_cap;
       node_cap[l] = std::max(qt_node_cap(lvl_key_cap[l], L.n_features[l], n_ini[l]), L.n_cols[l] * L.n_rows[l] + 64);
@@ -923,7 +929,7 @@ struct OrbPipeline {
     int* cnt = (int*)(d + J->o_cnt);
     // level 0 holds 40 % of the candidates and has the longest quadtree: its FAST runs first and its
     // quadtree on a side branch, under the pyramid chain and the other levels
-    LORB_LAUNCH(c, orb_fast_cells_kernel, P.cell_start[1], 256, 0, P, 0, slots, cnt);
+    if (P.cell_start[1] > 0) LORB_LAUNCH(c, orb_fast_cells_kernel, P.cell_start[1], 256, 0, P, 0, slots, cnt);
     LORB_CUDA_TRY(cudaEventRecord(c->orb_ev[0], s));
     LORB_CUDA_TRY(cudaStreamWaitEvent(s2, c->orb_ev[0], 0));
     {
@@ -950,7 +956,8 @@ struct OrbPipeline {
     LORB_CUDA_TRY(cudaGetLastError());
     LORB_CUDA_TRY(cudaEventRecord(c->orb_ev[1], s2));
     if (nl > 1) {
-      LORB_LAUNCH(c, orb_fast_cells_kernel, P.cell_start[nl] - P.cell_start[1], 256, 0, P, P.cell_start[1], slots, cnt);
+      if (P.cell_start[nl] > P.cell_start[1])
+        LORB_LAUNCH(c, orb_fast_cells_kernel, P.cell_start[nl] - P.cell_start[1], 256, 0, P, P.cell_start[1], slots, cnt);
       QtArgs A;
       memset(&A, 0, sizeof(A));
       for (int l = 1; l < nl; l++) A.lv[l - 1] = qt_level(J, d, hp, l);
@@ -1147,7 +1154,7 @@ int lorb_orb_max_keypoints(const lorb_orb_params* prm, int width, int height, in
   int total = 0;
   for (int l = 0; l < L.n_levels; l++) {
     const int bw = L.w[l] - 2 * ORB_EDGE + 6, bh = L.h[l] - 2 * ORB_EDGE + 6;
-    total += qt_out_cap(L.n_features[l], std::max(1, (int)roundf((float)bw / bh)));
+    if (L.n_cols[l] > 0) total += qt_out_cap(L.n_features[l], std::max(1, (int)roundf((float)bw / bh)));
   }
   *max_keypoints = total;
   return LORB_OK;

@@ -67,6 +67,8 @@ void ORBextractor::operator()(cv::InputArray _image, cv::InputArray /*mask*/, st
 
 	int cap = 0;  // usually nfeatures + a few; wide levels with small shares can return more
 	LORB_HOST_CALL(lorb_orb_max_keypoints(&prm, image.cols, image.rows, &cap));
+	if(cap < 1)
+		cap = 1;  // every level below one 30 px cell: no keypoints, but the output arrays must exist
 	std::vector<float> x(cap), y(cap), angle(cap), response(cap), size(cap);
 	std::vector<int> octave(cap);
 	cv::Mat desc(cap, 32, CV_8U);

@@ -176,6 +176,9 @@ ORB_EXTRACT = [
     ("752x480_n2000_s1", 1, 752, 480, 2000, False),
     ("320x240_n500_s2", 2, 320, 240, 500, False),
     ("640x480_n300_s3", 3, 640, 480, 300, False),
+    # levels 6 and 7 are smaller than one 30 px cell: part of the pyramid, no keypoints (the reference
+    # computes nCols = 0 there and loops over no cells)
+    ("161x241_n500_s4", 4, 161, 241, 500, False),
 ]
 
 

@@ -81,7 +81,10 @@ def test_level_plan():
     prm = capi.OrbParams(1000, 1.2, 8, 20, 7)
     z = np.zeros(8, np.int32)
     p = z.ctypes.data_as(C.c_void_p)
-    assert capi.load_library().lorb_orb_level_sizes(C.byref(prm), 100, 100, p, p, None, None) != 0  # too small
+    # levels below one 30 px cell stay in the pyramid (they yield no keypoints, as in the reference) ...
+    assert capi.load_library().lorb_orb_level_sizes(C.byref(prm), 100, 100, p, p, None, None) == 0
+    # ... but a level smaller than the 7 x 7 blur kernel is refused
+    assert capi.load_library().lorb_orb_level_sizes(C.byref(prm), 20, 20, p, p, None, None) != 0
 
 
 @pytest.mark.parametrize("c", RC.QUADTREE, ids=[c[0] for c in RC.QUADTREE])

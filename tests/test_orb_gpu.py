@@ -121,8 +121,10 @@ def test_cuda_orb_extract_flat_image(ctx):
     img = np.full((480, 640), 77, np.uint8)
     r = ctx.orb_extract(img, OC.pattern())
     assert r["n"] == 0
-    with pytest.raises(capi.LorbError):
-        ctx.orb_extract(np.zeros((40, 40), np.uint8), OC.pattern())
+    # every level below one 30 px cell: a pyramid without keypoints, as in the reference
+    assert ctx.orb_extract(synth.make_orb_image(3, 40, 40), OC.pattern())["n"] == 0
+    with pytest.raises(capi.LorbError):  # the last level would be 2 x 2: smaller than the blur kernel
+        ctx.orb_extract(np.zeros((8, 8), np.uint8), OC.pattern())
 
 
 def test_config0_extract_then_match(ctx):
