@@ -557,9 +557,15 @@ class Context:
         nw = int(bt["n_windows"])
         opt = opt or ba_options()
         sums = (BASummary * nw)()
+        null = C.c_void_p(0)
+        fo = fp = fuv = frt = None
+        if "fix_off" in bt:
+            fo, fp = _arr(bt["fix_off"], np.int32), _arr(bt["fix_pt"], np.int32)
+            fuv, frt = _arr(bt["fix_uv"], np.float32), _arr(bt["fix_rt"], np.float32)
         _check(self._lib.lorb_ba_local_batched(
             self._h, nw, _ptr(co), _ptr(cams), _ptr(po), _ptr(pts), _ptr(oo), _ptr(oc), _ptr(op),
-            _ptr(ouv), C.c_void_p(0), C.c_void_p(0), C.c_void_p(0), C.c_void_p(0), _ptr(K),
+            _ptr(ouv), _ptr(fo) if fo is not None else null, _ptr(fp) if fo is not None else null,
+            _ptr(fuv) if fo is not None else null, _ptr(frt) if fo is not None else null, _ptr(K),
             C.byref(opt), sums))
         return cams, pts, [s.as_dict() for s in sums]
 
@@ -635,10 +641,14 @@ class BAProblem:
             K = _arr(bt["K"], np.float32).reshape(4)
             self.C, self.P, self.nw = len(cams), len(pts), int(bt["n_windows"])
             h = C.c_void_p()
+            fix = [C.c_void_p(0)] * 4
+            if "fix_off" in bt:
+                self._fix = (_arr(bt["fix_off"], np.int32), _arr(bt["fix_pt"], np.int32),
+                             _arr(bt["fix_uv"], np.float32), _arr(bt["fix_rt"], np.float32))
+                fix = [_ptr(a) for a in self._fix]
             _check(self._lib.lorb_ba_problem_create_batched(
                 ctx._h, self.nw, _ptr(co), _ptr(cams), _ptr(po), _ptr(pts), _ptr(oo), _ptr(oc),
-                _ptr(op), _ptr(ouv), C.c_void_p(0), C.c_void_p(0), C.c_void_p(0), C.c_void_p(0),
-                _ptr(K), C.byref(h)))
+                _ptr(op), _ptr(ouv), fix[0], fix[1], fix[2], fix[3], _ptr(K), C.byref(h)))
             self._h = h
             return
         cams, pts = _arr(pb["cams"], np.float64), _arr(pb["pts"], np.float64)

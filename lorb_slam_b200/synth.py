@@ -360,12 +360,18 @@ def batch_windows(pbs):
     cam_off = np.cumsum([0] + [p["C"] for p in pbs]).astype(np.int32)
     pt_off = np.cumsum([0] + [p["P"] for p in pbs]).astype(np.int32)
     obs_off = np.cumsum([0] + [p["O"] for p in pbs]).astype(np.int32)
-    return dict(
+    bt = dict(
         n_windows=len(pbs), cam_off=cam_off, pt_off=pt_off, obs_off=obs_off,
         cams=np.concatenate([p["cams"] for p in pbs]), pts=np.concatenate([p["pts"] for p in pbs]),
         obs_cam=np.concatenate([p["obs_cam"] for p in pbs]),
         obs_pt=np.concatenate([p["obs_pt"] for p in pbs]),
         obs_uv=np.concatenate([p["obs_uv"] for p in pbs]), K=pbs[0]["K"].copy())
+    if any(p.get("F", 0) for p in pbs):  # fixed observations (window-local point indices), same offset form
+        bt["fix_off"] = np.cumsum([0] + [p.get("F", 0) for p in pbs]).astype(np.int32)
+        bt["fix_pt"] = np.concatenate([p["fix_pt"] for p in pbs]).astype(np.int32)
+        bt["fix_uv"] = np.concatenate([p["fix_uv"] for p in pbs]).astype(np.float32).reshape(-1, 2)
+        bt["fix_rt"] = np.concatenate([p["fix_rt"] for p in pbs]).astype(np.float32).reshape(-1, 6)
+    return bt
 
 
 # ------------------------------------------------------------- stereo matches

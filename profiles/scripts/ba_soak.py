@@ -42,7 +42,7 @@ with capi.Context(0) as ctx:
                 bad += 1
                 print("MISMATCH", s, C, P, k, ff, it, str(e)[:200].replace("\n", " "))
     # pose-only BA (BA::ProjectPoseOptimization): observation counts from the minimum up, good and bad starts
-    bad_p = 0
+    bad_p = noise_p = 0
     for s in range(n):
         m = int(rng.choice([3, 4, 6, 10, 50, 300, 2000, 5000]))
         po = synth.make_pose_only(4000 + s, m, pixel_noise=float(rng.choice([0.0, 1.0, 3.0])),
@@ -50,11 +50,15 @@ with capi.Context(0) as ctx:
         it = int(rng.choice([1, 5, 50]))
         rt, sm = ctx.ba_pose_only(po["xw"], po["uv"], po["K"], po["rt"], capi.ba_options(max_num_iterations=it))
         ort, so = ref.ba_pose_only(po["xw"], po["uv"], po["K"], po["rt"], ref.ba_options(max_num_iterations=it))
-        if not (np.allclose(rt, ort, rtol=1e-6, atol=1e-8) and sm["iterations"] == so["iterations"]
-                and sm["termination"] == so["termination"]):
+        same_x = np.allclose(rt, ort, rtol=1e-6, atol=1e-8)
+        if same_x and so["final_cost"] < 1e-18 and sm["iterations"] != so["iterations"]:
+            # exactly determined (3 observations, no noise): the cost reaches rounding noise and the
+            # tolerance tests of the last iterations fire on it -- same pose, iteration counts may differ
+            noise_p += 1
+        elif not (same_x and sm["iterations"] == so["iterations"] and sm["termination"] == so["termination"]):
             bad_p += 1
             print("POSE MISMATCH", s, m, it, np.abs(rt - ort).max(), sm["iterations"], so["iterations"])
-    print("%d pose-only solves, %d differ" % (n, bad_p))
+    print("%d pose-only solves, %d differ (%d more: same pose, zero-cost problem stopping one iteration apart)" % (n, bad_p, noise_p))
     # heterogeneous batches: windows of different solver paths (dense / privatised / work lists) in
     # one lorb_ba_local_batched call, every window against the oracle's single-window solve
     nb = bad_b = 0
@@ -65,7 +69,7 @@ with capi.Context(0) as ctx:
             C = int(rng.choice([3, 5, 8, 10, 10, 11, 14, 16, 17, 24]))
             k = tuple(int(v) for v in rng.choice(np.arange(3, min(C, 10) + 1), size=3))
             pbs.append(synth.make_ba_problem(5000 + 16 * s + w, C=C, P=int(rng.integers(30, 400)), obs_per_point=k,
-                                             traj_len=float(max(3.0, C * 0.4))))
+                                             fixed_frac=float(rng.choice([0.0, 0.0, 0.15])), traj_len=float(max(3.0, C * 0.4))))
         it = int(rng.choice([3, 6, 20]))
         kw = dict(max_num_iterations=it)
         bt = synth.batch_windows(pbs)
