@@ -1,10 +1,10 @@
 set -x
-for S in 1201 1202; do
-LORB_SOAK_SEED=$S timeout 500 python profiles/scripts/match_soak.py 400 > gpurun_out/soak_match_$S.log 2>&1; echo rc=$?; tail -1 gpurun_out/soak_match_$S.log
-LORB_SOAK_SEED=$S timeout 500 python profiles/scripts/ba_soak.py 300 > gpurun_out/soak_ba_$S.log 2>&1; echo rc=$?; tail -4 gpurun_out/soak_ba_$S.log | cut -c1-220
-done
-LORB_SOAK_SEED=2050 timeout 500 python profiles/scripts/orb_soak.py 300 > gpurun_out/soak_orb.log 2>&1; echo rc=$?; tail -2 gpurun_out/soak_orb.log
-LORB_SOAK_EXTREME=1 LORB_SOAK_SEED=2051 timeout 500 python profiles/scripts/orb_soak.py 200 > gpurun_out/soak_orb_x.log 2>&1; echo rc=$?; tail -2 gpurun_out/soak_orb_x.log
-LORB_SOAK_SEED=21 timeout 500 python profiles/scripts/stereo_soak.py 60 > gpurun_out/soak_stereo.log 2>&1; echo rc=$?; tail -2 gpurun_out/soak_stereo.log
-LORB_SOAK_SEED=31 timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 1 --master-addr 127.0.0.1 --master-port 29711 profiles/scripts/ba_shard_soak.py 150 > gpurun_out/soak_shard.log 2>&1; echo rc=$?; tail -2 gpurun_out/soak_shard.log
-timeout 300 python profiles/scripts/concurrency_stress.py 150 2>&1 | tail -4
+timeout 600 python -m pytest tests/test_match_bf_gpu.py tests/test_edge_cases_gpu.py tests/test_ref_golden_gpu.py -x -q -m gpu 2>&1 | tail -3
+timeout 600 python bench.py --workload sweep --no-cpu-baseline > gpurun_out/bench_sweep.json 2> gpurun_out/bench_sweep.err; echo rc=$?; tail -2 gpurun_out/bench_sweep.err
+python - <<PY
+import json
+d=json.loads(open('gpurun_out/bench_sweep.json').read().strip().split('\n')[-1])
+print('sweep', d['value']/1e9, 'e2e', d['e2e']['value']/1e9, d['roofline']['frac'], d['roofline']['peak'], d['roofline'].get('frac_executed'), d['clocks'])
+print('full', d.get('full_sweep',{}).get('value',0)/1e9, d.get('full_sweep',{}).get('wall_s'), d.get('full_sweep',{}).get('parity',{}).get('ok'))
+PY
+LORB_SOAK_SEED=1301 timeout 300 python profiles/scripts/match_soak.py 150 sweep > gpurun_out/soak_sweep.log 2>&1; echo rc=$?; tail -1 gpurun_out/soak_sweep.log
