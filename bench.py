@@ -64,6 +64,16 @@ def _tensor_peaks():
     return 1640.0, 1390.0, "fallback (B200_PROFILING.md)"
 
 
+def _rank_host_threads(world):
+    """This rank's share of the host cores for the library's staging loops.  The oracle and the library
+    share one OpenMP runtime, so every oracle leg that asks for all cores (rank 0's parity checks and CPU
+    baselines) must be followed by this call again -- or rank 0 stages its e2e batches on every core of the
+    box while the other ranks use their shares, and the max over the ranks is rank 0 fighting them."""
+    from lorb_slam_b200 import capi
+    capi.set_host_threads(int(os.environ.get("LORB_BENCH_HOST_THREADS", 0)) or
+                          max(1, (os.cpu_count() or 1) // max(1, world)))
+
+
 def _profile_traffic(key):
     """dram bytes per launch of a kernel from the committed ncu summary of this round, with its
     provenance; (None, None) when no capture has been committed for it."""
@@ -634,6 +644,7 @@ def run_ba_batched(args, rank, world, local, steps=None, want_cpu=True):
     slices over the ranks (strong scaling: the batch is fixed), every window its own LM loop."""
     import torch
     from lorb_slam_b200 import capi, sharding, synth
+    _rank_host_threads(world)  # an earlier oracle leg may have taken every core for rank 0
     steps = steps or args.steps
     warmup = max(3, min(args.warmup, 3))
     ctx = capi.Context(local)
@@ -749,6 +760,7 @@ def run_ba_large(args, rank, world, local, steps=None, want_cpu=True):
     """BASELINE config 5 BA: 200 keyframes / 200k points / 1.5M observations, points sharded over the
     ranks, reduced camera system all-reduced over NCCL every LM attempt.  Strong scaling."""
     import torch
+    _rank_host_threads(world)  # an earlier oracle leg may have taken every core for rank 0
     import torch.distributed as dist
     from lorb_slam_b200 import capi, sharding, synth
     steps = steps or args.steps
@@ -902,9 +914,7 @@ def main():
     want_cpu = not args.no_cpu_baseline
     # torchrun exports OMP_NUM_THREADS=1 to every rank: give each rank its share of the host cores
     # for the library's staging loops (the host-buffer calls of the e2e legs)
-    from lorb_slam_b200 import capi as _capi
-    _capi.set_host_threads(int(os.environ.get("LORB_BENCH_HOST_THREADS", 0)) or
-                           max(1, (os.cpu_count() or 1) // max(1, world)))
+    _rank_host_threads(world)
     if args.workload == "ba_batched":
         res = run_ba_batched(args, rank, world, local, want_cpu=want_cpu)
     elif args.workload == "ba_large":
