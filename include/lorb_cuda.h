@@ -540,7 +540,8 @@ int lorb_ba_local_batched(lorb_ctx* ctx, int n_windows, const int* cam_off, doub
 
 /* Team size of the library's host-side staging loops (OpenMP) for the calling thread.  Launchers
  * such as torchrun export OMP_NUM_THREADS=1 to every rank; a host that knows how many ranks share
- * the box hands each its share of the cores here. */
+ * the box hands each its share of the cores here.  (omp_set_num_threads on the process's OpenMP
+ * runtime: host code that changes the team size for its own loops changes it for the library.) */
 int lorb_set_host_threads(int n);
 
 /* Device-resident local BA problem, for timing the solver without the
