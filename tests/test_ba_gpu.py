@@ -181,6 +181,17 @@ def test_batched_windows_of_mixed_solver_paths(ctx, cams_per_window):
         _same_summary(sums[i], o)
 
 
+def test_window_with_more_cameras_than_fit_shared_memory(ctx):
+    """The back-substitution keeps a window's cameras in shared memory when they fit twice per SM
+    (up to 203); beyond that it gathers them from global memory: the other instantiation of the kernel."""
+    pb = synth.make_ba_problem(77, C=210, P=1500, obs_per_point=(5, 6, 7), traj_len=60.0)
+    cams, pts, s = ctx.ba_local(pb, capi.ba_options(max_num_iterations=4))
+    oc, op, o = ref.ba_local(pb, ref.ba_options(max_num_iterations=4))
+    _close(cams, oc, "cameras")
+    _close(pts, op, "points")
+    _same_summary(s, o)
+
+
 def test_bad_arguments(ctx):
     pb = synth.make_ba_problem(9, C=3, P=50, obs_per_point=(3,))
     bad = dict(pb)
