@@ -32,4 +32,17 @@ with capi.Context(0) as ctx:
     np.testing.assert_allclose(cams, oc, rtol=1e-6, atol=1e-8)
     np.testing.assert_allclose(pts, op, rtol=1e-6, atol=1e-8)
     assert s["iterations"] == o["iterations"] and s["termination"] == o["termination"]
+    # brute-force matching and the popc sweep kernel (LORB_HAMMING_CSA=0 selects the plain 8-popc body)
+    rng = np.random.default_rng(2)
+    q, t = synth.descriptors_uniform(1300, rng), synth.descriptors_tie_stress(2100, rng, 2, 3)
+    a, o = ctx.match_bf_crosscheck(q, t), ref.bf_crosscheck(q, t)
+    assert np.array_equal(a["q"], o["q"]) and np.array_equal(a["t"], o["t"]) and np.array_equal(a["dist"], o["dist"])
+    ki, kd, _ = ctx.match_knn2(q, t)
+    oi, od = ref.knn2(q, t)
+    assert np.array_equal(ki, oi) and np.array_equal(kd, od)
+    bank = synth.kf_bank(7, 777, seed=4)
+    pa, pb2 = synth.all_pairs(7)
+    ctx.sweep_set_impl("popc")
+    got, want = ctx.match_sweep(bank, pa, pb2), ref.sweep(bank, pa, pb2)
+    assert all(np.array_equal(g, w) for g, w in zip(got, want))
 print("FALLBACK_PATHS_OK")

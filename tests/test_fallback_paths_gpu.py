@@ -15,7 +15,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 @pytest.mark.parametrize("env", [
     {"LORB_RESOLVE_COOP": "0", "LORB_CHOL_CHAIN": "0"},
     {"LORB_RESOLVE_COOP": "0", "LORB_CHOL_DATAFLOW": "0"},
-], ids=["single-cta-resolve+dataflow-cholesky", "single-cta-resolve+multi-kernel-cholesky"])
+    {"LORB_HAMMING_CSA": "0"},
+], ids=["single-cta-resolve+dataflow-cholesky", "single-cta-resolve+multi-kernel-cholesky", "plain-popc-body"])
 def test_fallback_kernels_match_the_oracle(env):
     e = dict(os.environ, **env)
     r = subprocess.run([sys.executable, os.path.join(HERE, "fallback_paths.py")], env=e, capture_output=True,
